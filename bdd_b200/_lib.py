@@ -1,0 +1,124 @@
+"""Loader for libbdd_b200.so (the C-ABI library declared in include/bdd_b200.h).
+
+Fails loudly when the library is missing: there is no CPU or PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbdd_b200.so")
+
+OK = 0
+FLOAT, DOUBLE = 0, 1
+
+# every symbol include/bdd_b200.h declares (tests check that the library exports all of them)
+SYMBOLS = [
+    "bddb200_default_options", "bddb200_last_error", "bddb200_version", "bddb200_create", "bddb200_destroy",
+    "bddb200_nr_variables", "bddb200_nr_bdds", "bddb200_nr_layers", "bddb200_nr_bdd_nodes", "bddb200_nr_hops",
+    "bddb200_precision_of", "bddb200_device_of", "bddb200_nr_bdds_per_var", "bddb200_layer_primal_indices",
+    "bddb200_layer_bdd_indices", "bddb200_iteration", "bddb200_iterations", "bddb200_forward_pass",
+    "bddb200_backward_pass", "bddb200_forward_mm", "bddb200_backward_mm", "bddb200_normalize_delta",
+    "bddb200_get_delta", "bddb200_lower_bound", "bddb200_lower_bound_per_bdd", "bddb200_forward_run",
+    "bddb200_backward_run", "bddb200_flush_forward_states", "bddb200_flush_backward_states",
+    "bddb200_update_costs_host", "bddb200_update_costs_dev", "bddb200_set_cost", "bddb200_distribute_delta",
+    "bddb200_get_solver_costs", "bddb200_set_solver_costs", "bddb200_primal_objective_host",
+    "bddb200_min_marginals", "bddb200_bdds_solution", "bddb200_net_solver_costs", "bddb200_make_dual_feasible",
+    "bddb200_gradient_step", "bddb200_synchronize", "bddb200_stream", "bddb200_kernel_launches",
+    "bddb200_delta_sum_buffer", "bddb200_layout_stats",
+]
+
+
+class Options(C.Structure):
+    _fields_ = [
+        ("device", C.c_int),
+        ("stream", C.c_void_p),
+        ("deterministic", C.c_int),
+        ("lanes_per_bdd", C.c_int),
+        ("nr_variables", C.c_size_t),
+        ("nr_bdds_per_var_host", C.c_void_p),
+    ]
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `make -C bdd_b200/csrc` or __graft_entry__.build(). "
+            "bdd_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    vp, sz, dbl, i = C.c_void_p, C.c_size_t, C.c_double, C.c_int
+    sig = {
+        "bddb200_default_options": (None, [C.POINTER(Options)]),
+        "bddb200_last_error": (C.c_char_p, []),
+        "bddb200_version": (C.c_char_p, []),
+        "bddb200_create": (i, [vp, sz, vp, sz, vp, sz, i, C.POINTER(Options), C.POINTER(vp)]),
+        "bddb200_destroy": (None, [vp]),
+        "bddb200_nr_variables": (sz, [vp]),
+        "bddb200_nr_bdds": (sz, [vp]),
+        "bddb200_nr_layers": (sz, [vp]),
+        "bddb200_nr_bdd_nodes": (sz, [vp]),
+        "bddb200_nr_hops": (sz, [vp]),
+        "bddb200_precision_of": (i, [vp]),
+        "bddb200_device_of": (i, [vp]),
+        "bddb200_nr_bdds_per_var": (i, [vp, vp]),
+        "bddb200_layer_primal_indices": (i, [vp, vp]),
+        "bddb200_layer_bdd_indices": (i, [vp, vp]),
+        "bddb200_iteration": (i, [vp, dbl]),
+        "bddb200_iterations": (i, [vp, dbl, sz]),
+        "bddb200_forward_pass": (i, [vp, dbl]),
+        "bddb200_backward_pass": (i, [vp, dbl]),
+        "bddb200_forward_mm": (i, [vp, dbl, vp]),
+        "bddb200_backward_mm": (i, [vp, dbl, vp]),
+        "bddb200_normalize_delta": (i, [vp, vp]),
+        "bddb200_get_delta": (i, [vp, vp, i]),
+        "bddb200_lower_bound": (i, [vp, C.POINTER(dbl)]),
+        "bddb200_lower_bound_per_bdd": (i, [vp, vp]),
+        "bddb200_forward_run": (i, [vp]),
+        "bddb200_backward_run": (i, [vp]),
+        "bddb200_flush_forward_states": (None, [vp]),
+        "bddb200_flush_backward_states": (None, [vp]),
+        "bddb200_update_costs_host": (i, [vp, vp, sz, vp, sz]),
+        "bddb200_update_costs_dev": (i, [vp, vp, sz, vp, sz]),
+        "bddb200_set_cost": (i, [vp, dbl, sz]),
+        "bddb200_distribute_delta": (i, [vp]),
+        "bddb200_get_solver_costs": (i, [vp, vp, vp, vp]),
+        "bddb200_set_solver_costs": (i, [vp, vp, vp, vp]),
+        "bddb200_primal_objective_host": (i, [vp, vp]),
+        "bddb200_min_marginals": (i, [vp, i, vp, vp, vp]),
+        "bddb200_bdds_solution": (i, [vp, vp]),
+        "bddb200_net_solver_costs": (i, [vp, vp]),
+        "bddb200_make_dual_feasible": (i, [vp, vp]),
+        "bddb200_gradient_step": (i, [vp, vp, dbl]),
+        "bddb200_synchronize": (i, [vp]),
+        "bddb200_stream": (vp, [vp]),
+        "bddb200_kernel_launches": (sz, [vp]),
+        "bddb200_delta_sum_buffer": (i, [vp, C.POINTER(vp)]),
+        "bddb200_layout_stats": (i, [vp, sz, vp, sz, i, vp, sz]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(lib, name)
+        f.restype = res
+        f.argtypes = args
+    _lib = lib
+    return lib
+
+
+class BddB200Error(RuntimeError):
+    """Raised for any non-zero bddb200_status (the reference throws std::runtime_error)."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"bdd_b200 error {code}: {msg}")
+        self.code = code
+
+
+def check(code: int):
+    if code != OK:
+        raise BddB200Error(code, load().bddb200_last_error().decode())

@@ -1,0 +1,734 @@
+// bdd_b200/csrc/bdd_b200.cu -- implementation of the C ABI in include/bdd_b200.h.
+//
+// Host-side state machine mirrors bdd_cuda_base<REAL> / bdd_cuda_parallel_mma<REAL>
+// (forward_state_valid_ / backward_state_valid_, include/bdd_solver/bdd_cuda_base.h:211-212);
+// all device work is the kernels in kernels.cuh on one CUDA stream.  No thrust, no
+// per-hop launches, no host synchronisation except where a result is returned to the host.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <limits>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace bddb200;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct cuda_error : std::runtime_error {
+    cuda_error(const std::string& m) : std::runtime_error(m) {}
+};
+struct api_error : std::runtime_error {
+    int code;
+    api_error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define CUDA_CHECK(expr) do { cudaError_t e_ = (expr); if(e_ != cudaSuccess) \
+    throw cuda_error(std::string(#expr) + ": " + cudaGetErrorString(e_)); } while(0)
+
+template<typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { if(p) cudaFree(p); }
+    void alloc(size_t count) { if(p) { cudaFree(p); p = nullptr; } n = count; CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T))); }
+    void upload(const std::vector<T>& h, cudaStream_t st) { alloc(h.size()); if(!h.empty()) CUDA_CHECK(cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st)); }
+    void zero(cudaStream_t st) { if(n) CUDA_CHECK(cudaMemsetAsync(p, 0, n * sizeof(T), st)); }
+};
+
+inline unsigned blocks_for(size_t n, unsigned t = 256) { return (unsigned)((n + t - 1) / t); }
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------
+struct bddb200_solver {
+    int precision = 0;
+    int device = 0;
+    virtual ~bddb200_solver() {}
+    virtual size_t nr_variables() const = 0;
+    virtual size_t nr_bdds() const = 0;
+    virtual size_t nr_layers() const = 0;
+    virtual size_t nr_bdd_nodes() const = 0;
+    virtual size_t nr_hops() const = 0;
+    virtual void nr_bdds_per_var(int32_t* out) const = 0;
+    virtual void layer_primal_indices(int32_t* out) const = 0;
+    virtual void layer_bdd_indices(int32_t* out) const = 0;
+    virtual void iteration(double omega) = 0;
+    virtual void iterations(double omega, size_t n) = 0;
+    virtual void forward_pass(double omega) = 0;
+    virtual void backward_pass(double omega) = 0;
+    virtual void forward_mm(double omega, void* delta_dev) = 0;
+    virtual void backward_mm(double omega, void* delta_dev) = 0;
+    virtual void normalize_delta(void* delta_dev) const = 0;
+    virtual void get_delta(void* out, int out_is_host) = 0;
+    virtual double lower_bound() = 0;
+    virtual void lower_bound_per_bdd(void* out_dev) = 0;
+    virtual void forward_run() = 0;
+    virtual void backward_run() = 0;
+    virtual void flush_forward() = 0;
+    virtual void flush_backward() = 0;
+    virtual void update_costs_host(const double* lo, size_t n_lo, const double* hi, size_t n_hi) = 0;
+    virtual void update_costs_dev(const void* lo, size_t n_lo, const void* hi, size_t n_hi) = 0;
+    virtual void set_cost(double c, size_t var) = 0;
+    virtual void distribute_delta() = 0;
+    virtual void get_solver_costs(void* lo, void* hi, void* mmd) const = 0;
+    virtual void set_solver_costs(const void* lo, const void* hi, const void* mmd) = 0;
+    virtual void primal_objective_host(double* out) = 0;
+    virtual void min_marginals(int sorted, int32_t* primal_dev, void* lo_dev, void* hi_dev) = 0;
+    virtual void bdds_solution(char* sol_dev) = 0;
+    virtual void net_solver_costs(void* out_dev) const = 0;
+    virtual void make_dual_feasible(void* inout_dev) const = 0;
+    virtual void gradient_step(const void* dir_dev, double step) = 0;
+    virtual void synchronize() = 0;
+    virtual void* stream_handle() = 0;
+    virtual size_t kernel_launches() const = 0;
+    virtual void* delta_sum_buffer() = 0;
+};
+
+namespace {
+
+template<typename REAL>
+class SolverImpl final : public bddb200_solver {
+public:
+    SolverImpl(const bddb200_instruction* instrs, size_t n_instr, const size_t* delims, size_t n_bdds,
+               const double* costs_hi, size_t n_costs, const bddb200_options& opt)
+    {
+        precision = sizeof(REAL) == 8 ? BDDB200_DOUBLE : BDDB200_FLOAT;
+        device = opt.device;
+        deterministic_ = opt.deterministic != 0;
+        int count = 0;
+        if(cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+            throw api_error(BDDB200_ERR_NO_DEVICE, "no CUDA device available: libbdd_b200 has no CPU fallback");
+        if(device < 0 || device >= count) throw api_error(BDDB200_ERR_INVALID_ARGUMENT, "invalid device ordinal");
+        CUDA_CHECK(cudaSetDevice(device));
+        if(opt.stream) { stream_ = (cudaStream_t)opt.stream; own_stream_ = false; }
+        else { CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking)); own_stream_ = true; }
+
+        HostLayout L = build_layout(instrs, n_instr, delims, n_bdds, opt.lanes_per_bdd, opt.nr_variables);
+        n_vars_ = L.n_vars; n_bdds_ = L.n_bdds; n_instr_ = delims[n_bdds] - delims[0];
+        n_ext_ = L.n_layers_ext; n_slots_ = L.n_slots; n_lay_ = L.n_lay; max_hops_ = L.max_hops;
+        n_bundles_ = L.bundles.size(); n_small_ = L.n_small_bundles;
+        tile_small_ = std::max<uint32_t>(L.max_tile_small, 32u); tile_large_ = L.max_tile_large;
+
+        h_nr_bdds_per_var_ = L.nr_bdds_per_var;
+        if(opt.nr_bdds_per_var_host != nullptr)
+        {
+            if(opt.nr_variables < L.n_vars) throw api_error(BDDB200_ERR_INVALID_ARGUMENT, "nr_bdds_per_var_host given but nr_variables too small");
+            for(size_t v = 0; v < n_vars_; ++v)
+            {
+                if(opt.nr_bdds_per_var_host[v] < h_nr_bdds_per_var_[v])
+                    throw api_error(BDDB200_ERR_INVALID_ARGUMENT, "global nr_bdds_per_var smaller than the local count");
+                h_nr_bdds_per_var_[v] = opt.nr_bdds_per_var_host[v];
+            }
+        }
+        h_ext_var_ = L.ext_var; h_ext_bdd_ = L.ext_bdd;
+
+        // shared memory budget of the large class (one warp per CTA)
+        int max_optin = 0;
+        CUDA_CHECK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        if((size_t)tile_large_ * 3 * sizeof(REAL) > (size_t)max_optin)
+            throw api_error(BDDB200_ERR_TOO_WIDE, "widest BDD layer needs " + std::to_string((size_t)tile_large_ * 3 * sizeof(REAL)) +
+                            " bytes of shared memory per warp (limit " + std::to_string(max_optin) + "); split the BDD (split_qbdd)");
+        CUDA_CHECK(cudaDeviceGetAttribute(&n_sms_, cudaDevAttrMultiProcessorCount, device));
+
+        std::vector<int2> lay_vn(L.n_lay);
+        for(size_t i = 0; i < L.n_lay; ++i)
+        {
+            const int v = L.lay_var[i];
+            lay_vn[i] = make_int2(v, v >= 0 ? h_nr_bdds_per_var_[v] : 0);
+        }
+        std::vector<uint32_t> bdd_bundle(2 * n_bdds);
+        for(size_t g = 0; g < L.bundles.size(); ++g)
+            for(uint32_t q = 0; q < (32u >> L.bundles[g].logP); ++q)
+            {
+                const int32_t b = L.bundle_bdd[L.bundles[g].bdd_base + q];
+                if(b >= 0) { bdd_bundle[2 * b] = (uint32_t)g; bdd_bundle[2 * b + 1] = q; }
+            }
+
+        d_bundles_.upload(L.bundles, stream_);
+        d_hops_.upload(L.hops, stream_);
+        d_topo_.upload(L.topo, stream_);
+        d_lay_vn_.upload(lay_vn, stream_);
+        d_bundle_bdd_.upload(L.bundle_bdd, stream_);
+        d_bdd_bundle_.upload(bdd_bundle, stream_);
+        d_ext2lay_.upload(L.ext2lay, stream_);
+        d_ext_var_.upload(L.ext_var, stream_);
+        d_ext_bdd_.upload(L.ext_bdd, stream_);
+        d_bdd_ext_begin_.upload(L.bdd_ext_begin, stream_);
+        d_var_lay_begin_.upload(L.var_lay_begin, stream_);
+        d_var_lay_.upload(L.var_lay, stream_);
+        d_sorted_ext_.upload(L.sorted_ext, stream_);
+        d_nr_bdds_.upload(h_nr_bdds_per_var_, stream_);
+
+        d_cfr_.alloc(n_slots_); d_cft_.alloc(n_slots_);
+        for(int i = 0; i < 2; ++i) { d_lo_[i].alloc(n_lay_); d_hi_[i].alloc(n_lay_); d_lo_[i].zero(stream_); d_hi_[i].zero(stream_); }
+        d_mmd_.alloc(n_lay_); d_mmd_.zero(stream_);
+        d_mm_lo_.alloc(n_lay_); d_mm_hi_.alloc(n_lay_);
+        for(int i = 0; i < 3; ++i) { d_delta_[i].alloc(2 * n_vars_); d_delta_[i].zero(stream_); }
+        d_delta_tmp_.alloc(2 * n_vars_);
+        d_bdd_lb_.alloc(n_bdds_);
+        d_lb_partial_.alloc(LB_BLOCKS + 1);
+        CUDA_CHECK(cudaMallocHost(&h_lb_, sizeof(double)));
+
+        configure_kernels();
+
+        if(costs_hi != nullptr && n_costs > 0)
+            update_costs_host(nullptr, 0, costs_hi, n_costs);
+        CUDA_CHECK(cudaStreamSynchronize(stream_));   // host vectors of the layout go out of scope
+    }
+
+    ~SolverImpl() override
+    {
+        cudaSetDevice(device);
+        if(graph_exec_) cudaGraphExecDestroy(graph_exec_);
+        if(h_lb_) cudaFreeHost(h_lb_);
+        if(own_stream_ && stream_) cudaStreamDestroy(stream_);
+    }
+
+    size_t nr_variables() const override { return n_vars_; }
+    size_t nr_bdds() const override { return n_bdds_; }
+    size_t nr_layers() const override { return n_ext_; }
+    size_t nr_bdd_nodes() const override { return n_instr_; }
+    size_t nr_hops() const override { return max_hops_ > 0 ? max_hops_ - 1 : 0; }
+    void nr_bdds_per_var(int32_t* out) const override { std::memcpy(out, h_nr_bdds_per_var_.data(), sizeof(int32_t) * n_vars_); }
+    void layer_primal_indices(int32_t* out) const override { std::memcpy(out, h_ext_var_.data(), sizeof(int32_t) * n_ext_); }
+    void layer_bdd_indices(int32_t* out) const override { std::memcpy(out, h_ext_bdd_.data(), sizeof(int32_t) * n_ext_); }
+
+    // ---------------------------------------------------------------- sweep launches ---
+    template<int MODE, bool FORWARD>
+    void launch_sweep(SweepArgs<REAL> a)
+    {
+        auto kern = sweep_kernel<REAL, MODE, FORWARD>;
+        constexpr int NBUF = FORWARD ? 3 : 2;
+        if(n_small_ > 0)
+        {
+            a.bundle_first = 0; a.bundle_count = (uint32_t)n_small_; a.tile_slots = tile_small_;
+            const size_t smem = (size_t)warps_per_cta_ * NBUF * tile_small_ * sizeof(REAL);
+            kern<<<blocks_for(n_small_, warps_per_cta_), warps_per_cta_ * 32, smem, stream_>>>(a);
+            ++launches_;
+        }
+        if(n_bundles_ > n_small_)
+        {
+            a.bundle_first = (uint32_t)n_small_; a.bundle_count = (uint32_t)(n_bundles_ - n_small_); a.tile_slots = tile_large_;
+            if(n_small_ > 0) a.zero_buf = nullptr;
+            const size_t smem = (size_t)NBUF * tile_large_ * sizeof(REAL);
+            kern<<<(unsigned)(n_bundles_ - n_small_), 32, smem, stream_>>>(a);
+            ++launches_;
+        }
+        CUDA_CHECK(cudaGetLastError());
+    }
+
+    void configure_kernels()
+    {
+        const size_t large = (size_t)3 * tile_large_ * sizeof(REAL);
+        const size_t small = (size_t)warps_per_cta_ * 3 * tile_small_ * sizeof(REAL);
+        const int need = (int)std::max(large, small);
+        if(need > 48 * 1024)
+        {
+            CUDA_CHECK(cudaFuncSetAttribute(sweep_kernel<REAL, MODE_MMA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
+            CUDA_CHECK(cudaFuncSetAttribute(sweep_kernel<REAL, MODE_MMA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
+            CUDA_CHECK(cudaFuncSetAttribute(sweep_kernel<REAL, MODE_PLAIN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
+            CUDA_CHECK(cudaFuncSetAttribute(sweep_kernel<REAL, MODE_PLAIN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
+            CUDA_CHECK(cudaFuncSetAttribute(sweep_kernel<REAL, MODE_MM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
+        }
+    }
+
+    SweepArgs<REAL> base_args() const
+    {
+        SweepArgs<REAL> a{};
+        a.bundles = d_bundles_.p; a.hops = d_hops_.p; a.topo = d_topo_.p; a.lay_vn = d_lay_vn_.p; a.bundle_bdd = d_bundle_bdd_.p;
+        a.cfr = d_cfr_.p; a.cft = d_cft_.p;
+        a.lo_in = d_lo_[cc_].p; a.hi_in = d_hi_[cc_].p; a.lo_out = d_lo_[cc_ ^ 1].p; a.hi_out = d_hi_[cc_ ^ 1].p;
+        a.mmd = d_mmd_.p; a.mm_lo_out = d_mm_lo_.p; a.mm_hi_out = d_mm_hi_.p; a.bdd_lb = d_bdd_lb_.p;
+        a.omega = 0; a.n_zero = (uint32_t)(2 * n_vars_);
+        return a;
+    }
+
+    // one MMA pass on explicit delta buffers.  zero_buf is cleared by the same launch.
+    template<bool FORWARD>
+    void mma_pass(double omega, const REAL* delta_in, bool normalize_in, REAL* delta_out, REAL* zero_buf)
+    {
+        SweepArgs<REAL> a = base_args();
+        a.omega = (REAL)omega;
+        a.delta_in = delta_in; a.delta_out = delta_out; a.zero_buf = zero_buf;
+        a.normalize_in = normalize_in ? 1 : 0;
+        a.accumulate = deterministic_ ? 0 : 1;
+        launch_sweep<MODE_MMA, FORWARD>(a);
+        cc_ ^= 1;   // thrust::swap(lo_cost_, lo_cost_out_), bdd_cuda_parallel_mma.cu:246-247
+        if(deterministic_)
+        {
+            delta_segsum_kernel<REAL><<<blocks_for(n_vars_), 256, 0, stream_>>>(d_var_lay_begin_.p, d_var_lay_.p, d_mmd_.p, delta_out, (uint32_t)n_vars_);
+            ++launches_;
+            CUDA_CHECK(cudaGetLastError());
+        }
+    }
+
+    void forward_pass(double omega) override
+    {
+        set_device();
+        if(!backward_valid_) backward_run();     // bdd_cuda_parallel_mma.cu:210-211
+        REAL* in = d_delta_[dcur_].p;
+        REAL* out = d_delta_[(dcur_ + 1) % 3].p;
+        REAL* zero = d_delta_[(dcur_ + 2) % 3].p;
+        mma_pass<true>(omega, in, delta_needs_norm_, out, zero);
+        dcur_ = (dcur_ + 1) % 3; delta_needs_norm_ = true;
+        forward_valid_ = true; backward_valid_ = false;
+    }
+
+    void backward_pass(double omega) override
+    {
+        set_device();
+        if(!forward_valid_) throw api_error(BDDB200_ERR_STATE, "backward_mm needs a valid forward state (call forward_mm first)");
+        REAL* in = d_delta_[dcur_].p;
+        REAL* out = d_delta_[(dcur_ + 1) % 3].p;
+        REAL* zero = d_delta_[(dcur_ + 2) % 3].p;
+        mma_pass<false>(omega, in, delta_needs_norm_, out, zero);
+        dcur_ = (dcur_ + 1) % 3; delta_needs_norm_ = true;
+        forward_valid_ = false; backward_valid_ = true; lb_valid_ = false;
+    }
+
+    void iteration(double omega) override
+    {
+        forward_pass(omega);
+        backward_pass(omega);
+    }
+
+    void iterations(double omega, size_t n) override
+    {
+        set_device();
+        if(n == 0) return;
+        if(!backward_valid_) backward_run();
+        // The delta buffers rotate with period 3 passes and an iteration is 2 passes: a graph of
+        // 3 iterations (6 sweep launches) returns to the same buffer assignment.
+        const size_t per_graph = 3;
+        if(n >= per_graph)
+        {
+            if(graph_exec_ == nullptr || graph_omega_ != omega || graph_dcur_ != dcur_ || graph_cc_ != cc_ || graph_norm_ != delta_needs_norm_)
+            {
+                if(graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
+                if(!delta_needs_norm_)
+                {   // first passes read a normalised vector: run one plain iteration so that the
+                    // captured graph always starts from the steady state
+                    iteration(omega); --n;
+                }
+            }
+            if(n >= per_graph && graph_exec_ == nullptr)
+            {
+                cudaGraph_t graph = nullptr;
+                const size_t launches_before = launches_;
+                CUDA_CHECK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+                for(size_t i = 0; i < per_graph; ++i) iteration(omega);
+                CUDA_CHECK(cudaStreamEndCapture(stream_, &graph));
+                graph_launches_ = launches_ - launches_before;
+                launches_ = launches_before;
+                CUDA_CHECK(cudaGraphInstantiate(&graph_exec_, graph, 0));
+                cudaGraphDestroy(graph);
+                graph_omega_ = omega; graph_dcur_ = dcur_; graph_cc_ = cc_; graph_norm_ = delta_needs_norm_;
+            }
+            while(n >= per_graph && graph_exec_ != nullptr)
+            {
+                CUDA_CHECK(cudaGraphLaunch(graph_exec_, stream_));
+                launches_ += graph_launches_;
+                n -= per_graph;
+            }
+            forward_valid_ = false; backward_valid_ = true; lb_valid_ = false;
+        }
+        for(size_t i = 0; i < n; ++i) iteration(omega);
+    }
+
+    // forward_mm(omega, delta) on a caller-owned vector: in = values to add (already
+    // normalised by the caller), out = raw sums (bdd_cuda_parallel_mma.cu:207-257).
+    void forward_mm(double omega, void* delta_dev) override
+    {
+        set_device();
+        if(!backward_valid_) backward_run();
+        external_pass<true>(omega, static_cast<REAL*>(delta_dev));
+        forward_valid_ = true; backward_valid_ = false;
+    }
+    void backward_mm(double omega, void* delta_dev) override
+    {
+        set_device();
+        if(!forward_valid_) throw api_error(BDDB200_ERR_STATE, "backward_mm needs a valid forward state (call forward_mm first)");
+        external_pass<false>(omega, static_cast<REAL*>(delta_dev));
+        forward_valid_ = false; backward_valid_ = true; lb_valid_ = false;
+    }
+    template<bool FORWARD>
+    void external_pass(double omega, REAL* delta)
+    {
+        REAL* out = d_delta_tmp_.p;
+        if(!deterministic_) d_delta_tmp_.zero(stream_);
+        mma_pass<FORWARD>(omega, delta, false, out, nullptr);
+        CUDA_CHECK(cudaMemcpyAsync(delta, out, sizeof(REAL) * 2 * n_vars_, cudaMemcpyDeviceToDevice, stream_));
+    }
+
+    void normalize_delta(void* delta_dev) const override
+    {
+        set_device();
+        REAL* d = static_cast<REAL*>(delta_dev);
+        normalize_kernel<REAL><<<blocks_for(2 * n_vars_), 256, 0, stream_>>>(d, d, d_nr_bdds_.p, (uint32_t)(2 * n_vars_));
+        ++launches_;
+        CUDA_CHECK(cudaGetLastError());
+    }
+
+    void get_delta(void* out, int out_is_host) override
+    {
+        set_device();
+        const REAL* src = d_delta_[dcur_].p;
+        if(delta_needs_norm_)
+        {
+            normalize_kernel<REAL><<<blocks_for(2 * n_vars_), 256, 0, stream_>>>(src, d_delta_tmp_.p, d_nr_bdds_.p, (uint32_t)(2 * n_vars_));
+            ++launches_;
+            src = d_delta_tmp_.p;
+        }
+        CUDA_CHECK(cudaMemcpyAsync(out, src, sizeof(REAL) * 2 * n_vars_, out_is_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, stream_));
+        if(out_is_host) CUDA_CHECK(cudaStreamSynchronize(stream_));
+    }
+
+    void* delta_sum_buffer() override { return d_delta_[dcur_].p; }
+
+    // ---------------------------------------------------------------- plain runs -------
+    void forward_run() override
+    {
+        set_device();
+        if(forward_valid_) return;
+        SweepArgs<REAL> a = base_args();
+        launch_sweep<MODE_PLAIN, true>(a);
+        forward_valid_ = true;
+    }
+    void backward_run() override
+    {
+        set_device();
+        if(backward_valid_) return;
+        SweepArgs<REAL> a = base_args();
+        launch_sweep<MODE_PLAIN, false>(a);
+        backward_valid_ = true; lb_valid_ = false;
+    }
+    void flush_forward() override { forward_valid_ = false; }
+    void flush_backward() override { backward_valid_ = false; lb_valid_ = false; }
+
+    double lower_bound() override
+    {
+        set_device();
+        backward_run();
+        if(!lb_valid_)
+        {
+            lb_partial_kernel<REAL><<<LB_BLOCKS, 256, 0, stream_>>>(d_bdd_lb_.p, d_lb_partial_.p, (uint32_t)n_bdds_);
+            lb_final_kernel<<<1, 256, 0, stream_>>>(d_lb_partial_.p, d_lb_partial_.p + LB_BLOCKS, LB_BLOCKS);
+            launches_ += 2;
+            CUDA_CHECK(cudaMemcpyAsync(h_lb_, d_lb_partial_.p + LB_BLOCKS, sizeof(double), cudaMemcpyDeviceToHost, stream_));
+            CUDA_CHECK(cudaStreamSynchronize(stream_));
+            lb_ = *h_lb_; lb_valid_ = true;
+        }
+        return lb_;
+    }
+
+    void lower_bound_per_bdd(void* out_dev) override
+    {
+        set_device();
+        backward_run();
+        CUDA_CHECK(cudaMemcpyAsync(out_dev, d_bdd_lb_.p, sizeof(REAL) * n_bdds_, cudaMemcpyDeviceToDevice, stream_));
+    }
+
+    // ---------------------------------------------------------------- costs -------------
+    void update_costs_host(const double* lo, size_t n_lo, const double* hi, size_t n_hi) override
+    {
+        set_device();
+        auto up = [&](const double* c, size_t n, REAL* dst) {
+            if(n == 0) return;
+            if(n > n_vars_) throw api_error(BDDB200_ERR_INVALID_ARGUMENT, "more costs than variables");
+            std::vector<REAL> h(n);
+            for(size_t i = 0; i < n; ++i) h[i] = (REAL)c[i];     // device_vector<REAL>(cost_begin, cost_end), bdd_cuda_base.cu:485
+            DevBuf<REAL> d; d.upload(h, stream_);
+            update_costs_kernel<REAL><<<blocks_for(n_lay_), 256, 0, stream_>>>(d_lay_vn_.p, dst, d.p, (uint32_t)n, (uint32_t)n_lay_);
+            ++launches_;
+            CUDA_CHECK(cudaGetLastError());
+            CUDA_CHECK(cudaStreamSynchronize(stream_));
+        };
+        up(lo, n_lo, d_lo_[cc_].p);
+        up(hi, n_hi, d_hi_[cc_].p);
+        flush_forward(); flush_backward();
+    }
+    void update_costs_dev(const void* lo, size_t n_lo, const void* hi, size_t n_hi) override
+    {
+        set_device();
+        if((n_lo != 0 && n_lo != n_vars_) || (n_hi != 0 && n_hi != n_vars_))
+            throw api_error(BDDB200_ERR_INVALID_ARGUMENT, "device cost vectors must have 0 or nr_variables entries");  // bdd_cuda_base.cu:537-538
+        if(n_lo) { update_costs_kernel<REAL><<<blocks_for(n_lay_), 256, 0, stream_>>>(d_lay_vn_.p, d_lo_[cc_].p, static_cast<const REAL*>(lo), (uint32_t)n_lo, (uint32_t)n_lay_); ++launches_; }
+        if(n_hi) { update_costs_kernel<REAL><<<blocks_for(n_lay_), 256, 0, stream_>>>(d_lay_vn_.p, d_hi_[cc_].p, static_cast<const REAL*>(hi), (uint32_t)n_hi, (uint32_t)n_lay_); ++launches_; }
+        CUDA_CHECK(cudaGetLastError());
+        flush_forward(); flush_backward();
+    }
+    void set_cost(double c, size_t var) override
+    {
+        set_device();
+        if(var >= n_vars_ || h_nr_bdds_per_var_[var] <= 0) throw api_error(BDDB200_ERR_INVALID_ARGUMENT, "set_cost: variable not covered by any BDD");
+        const REAL add = (REAL)c / h_nr_bdds_per_var_[var];
+        set_cost_kernel<REAL><<<blocks_for(n_lay_), 256, 0, stream_>>>(d_lay_vn_.p, d_hi_[cc_].p, (int)var, add, (uint32_t)n_lay_);
+        ++launches_;
+        CUDA_CHECK(cudaGetLastError());
+        flush_forward(); flush_backward();
+    }
+    void distribute_delta() override
+    {
+        set_device();
+        distribute_kernel<REAL><<<blocks_for(n_lay_), 256, 0, stream_>>>(d_lay_vn_.p, d_lo_[cc_].p, d_hi_[cc_].p, d_mmd_.p, (uint32_t)n_lay_);
+        ++launches_;
+        CUDA_CHECK(cudaGetLastError());
+        for(int i = 0; i < 3; ++i) d_delta_[i].zero(stream_);
+        delta_needs_norm_ = false;
+        flush_forward(); flush_backward();
+    }
+    void get_solver_costs(void* lo, void* hi, void* mmd) const override
+    {
+        set_device();
+        const unsigned nb = blocks_for(n_ext_);
+        if(lo) { gather_ext_kernel<REAL><<<nb, 256, 0, stream_>>>(d_ext2lay_.p, d_ext_var_.p, d_lo_[cc_].p, static_cast<REAL*>(lo), (REAL)0, (uint32_t)n_ext_); ++launches_; }
+        if(hi) { gather_ext_kernel<REAL><<<nb, 256, 0, stream_>>>(d_ext2lay_.p, d_ext_var_.p, d_hi_[cc_].p, static_cast<REAL*>(hi), (REAL)0, (uint32_t)n_ext_); ++launches_; }
+        if(mmd) { gather_ext_kernel<REAL><<<nb, 256, 0, stream_>>>(d_ext2lay_.p, d_ext_var_.p, d_mmd_.p, static_cast<REAL*>(mmd), (REAL)0, (uint32_t)n_ext_); ++launches_; }
+        CUDA_CHECK(cudaGetLastError());
+    }
+    void set_solver_costs(const void* lo, const void* hi, const void* mmd) override
+    {
+        set_device();
+        const unsigned nb = blocks_for(n_ext_);
+        scatter_ext_kernel<REAL><<<nb, 256, 0, stream_>>>(d_ext2lay_.p, d_ext_var_.p, static_cast<const REAL*>(lo), d_lo_[cc_].p, (uint32_t)n_ext_);
+        scatter_ext_kernel<REAL><<<nb, 256, 0, stream_>>>(d_ext2lay_.p, d_ext_var_.p, static_cast<const REAL*>(hi), d_hi_[cc_].p, (uint32_t)n_ext_);
+        scatter_ext_kernel<REAL><<<nb, 256, 0, stream_>>>(d_ext2lay_.p, d_ext_var_.p, static_cast<const REAL*>(mmd), d_mmd_.p, (uint32_t)n_ext_);
+        launches_ += 3;
+        CUDA_CHECK(cudaGetLastError());
+        flush_forward(); flush_backward();
+    }
+    void primal_objective_host(double* out) override
+    {
+        set_device();
+        DevBuf<double> d; d.alloc(n_vars_);
+        primal_objective_kernel<REAL><<<blocks_for(n_vars_), 256, 0, stream_>>>(d_var_lay_begin_.p, d_var_lay_.p, d_lo_[cc_].p, d_hi_[cc_].p, d.p, (uint32_t)n_vars_);
+        ++launches_;
+        CUDA_CHECK(cudaMemcpyAsync(out, d.p, sizeof(double) * n_vars_, cudaMemcpyDeviceToHost, stream_));
+        CUDA_CHECK(cudaStreamSynchronize(stream_));
+    }
+
+    // ---------------------------------------------------------------- min-marginals ----
+    void min_marginals(int sorted, int32_t* primal_dev, void* lo_dev, void* hi_dev) override
+    {
+        set_device();
+        forward_run();                                   // bdd_cuda_base.cu:721
+        SweepArgs<REAL> a = base_args();
+        launch_sweep<MODE_MM, false>(a);                 // backward_run(true), :728
+        backward_valid_ = true; lb_valid_ = false;
+        const unsigned nb = blocks_for(n_ext_);
+        const REAL INF = std::numeric_limits<REAL>::infinity();
+        DevBuf<REAL> tmp;
+        if(sorted) tmp.alloc(n_ext_);
+        auto emit = [&](const REAL* src, void* dst) {
+            if(dst == nullptr) return;
+            REAL* stage = sorted ? tmp.p : static_cast<REAL*>(dst);
+            gather_ext_kernel<REAL><<<nb, 256, 0, stream_>>>(d_ext2lay_.p, d_ext_var_.p, src, stage, INF, (uint32_t)n_ext_);
+            ++launches_;
+            if(sorted) { permute_kernel<REAL><<<nb, 256, 0, stream_>>>(d_sorted_ext_.p, stage, static_cast<REAL*>(dst), (uint32_t)n_ext_); ++launches_; }
+        };
+        emit(d_mm_lo_.p, lo_dev);
+        emit(d_mm_hi_.p, hi_dev);
+        if(primal_dev)
+        {
+            if(sorted) { permute_kernel<int32_t><<<nb, 256, 0, stream_>>>(d_sorted_ext_.p, d_ext_var_.p, primal_dev, (uint32_t)n_ext_); ++launches_; }
+            else CUDA_CHECK(cudaMemcpyAsync(primal_dev, d_ext_var_.p, sizeof(int32_t) * n_ext_, cudaMemcpyDeviceToDevice, stream_));
+        }
+        CUDA_CHECK(cudaGetLastError());
+        if(sorted) CUDA_CHECK(cudaStreamSynchronize(stream_));   // tmp is freed on return
+    }
+
+    // ---------------------------------------------------------------- L-BFGS surface ---
+    void bdds_solution(char* sol_dev) override
+    {
+        set_device();
+        forward_run();
+        backward_valid_ = false;       // backward_run(true) always recomputes, bdd_cuda_base.cu:1171
+        backward_run();
+        bdds_solution_kernel<REAL><<<blocks_for(n_bdds_, 128), 128, 0, stream_>>>(d_bundles_.p, d_hops_.p, d_topo_.p, d_bdd_bundle_.p, d_bdd_ext_begin_.p,
+            d_cfr_.p, d_cft_.p, d_lo_[cc_].p, d_hi_[cc_].p, sol_dev, (uint32_t)n_bdds_);
+        ++launches_;
+        CUDA_CHECK(cudaGetLastError());
+    }
+    void net_solver_costs(void* out_dev) const override
+    {
+        set_device();
+        net_costs_kernel<REAL><<<blocks_for(n_ext_), 256, 0, stream_>>>(d_ext2lay_.p, d_ext_var_.p, d_lo_[cc_].p, d_hi_[cc_].p, d_mmd_.p, static_cast<REAL*>(out_dev), (uint32_t)n_ext_);
+        ++launches_;
+        CUDA_CHECK(cudaGetLastError());
+    }
+    void make_dual_feasible(void* inout_dev) const override
+    {
+        set_device();
+        REAL* d = static_cast<REAL*>(inout_dev);
+        dual_feasible_kernel<REAL><<<blocks_for(n_vars_), 256, 0, stream_>>>(d_var_lay_begin_.p, d_sorted_ext_.p, d_nr_bdds_.p, d, (uint32_t)n_vars_);
+        zero_terminals_kernel<REAL><<<blocks_for(n_ext_), 256, 0, stream_>>>(d_ext_var_.p, d, (uint32_t)n_ext_);
+        launches_ += 2;
+        CUDA_CHECK(cudaGetLastError());
+    }
+    void gradient_step(const void* dir_dev, double step) override
+    {
+        set_device();
+        gradient_step_kernel<REAL><<<blocks_for(n_ext_), 256, 0, stream_>>>(d_ext2lay_.p, d_ext_var_.p, d_hi_[cc_].p, static_cast<const REAL*>(dir_dev), (REAL)step, (uint32_t)n_ext_);
+        ++launches_;
+        CUDA_CHECK(cudaGetLastError());
+        flush_forward(); flush_backward();
+    }
+
+    void synchronize() override { set_device(); CUDA_CHECK(cudaStreamSynchronize(stream_)); }
+    void* stream_handle() override { return (void*)stream_; }
+    size_t kernel_launches() const override { return launches_; }
+
+private:
+    void set_device() const { CUDA_CHECK(cudaSetDevice(device)); }
+
+    static constexpr unsigned LB_BLOCKS = 128;
+    cudaStream_t stream_ = nullptr;
+    bool own_stream_ = false;
+    bool deterministic_ = false;
+    int n_sms_ = 0;
+    unsigned warps_per_cta_ = 4;
+    size_t n_vars_ = 0, n_bdds_ = 0, n_instr_ = 0, n_ext_ = 0, n_slots_ = 0, n_lay_ = 0, max_hops_ = 0, n_bundles_ = 0, n_small_ = 0;
+    uint32_t tile_small_ = 32, tile_large_ = 0;
+    std::vector<int32_t> h_nr_bdds_per_var_, h_ext_var_, h_ext_bdd_;
+
+    DevBuf<BundleDesc> d_bundles_;
+    DevBuf<HopRec> d_hops_;
+    DevBuf<uint32_t> d_topo_, d_bdd_bundle_, d_ext2lay_, d_bdd_ext_begin_, d_var_lay_begin_, d_var_lay_, d_sorted_ext_;
+    DevBuf<int2> d_lay_vn_;
+    DevBuf<int32_t> d_bundle_bdd_, d_ext_var_, d_ext_bdd_, d_nr_bdds_;
+    DevBuf<REAL> d_cfr_, d_cft_, d_lo_[2], d_hi_[2], d_mmd_, d_mm_lo_, d_mm_hi_, d_delta_[3], d_delta_tmp_, d_bdd_lb_;
+    DevBuf<double> d_lb_partial_;
+    double* h_lb_ = nullptr;
+
+    int cc_ = 0;                 // which of the two lo/hi cost buffers is current
+    int dcur_ = 0;               // which delta buffer holds the current (pending) sums
+    bool delta_needs_norm_ = false;
+    bool forward_valid_ = false, backward_valid_ = false, lb_valid_ = false;
+    double lb_ = 0.0;
+    mutable size_t launches_ = 0;
+
+    cudaGraphExec_t graph_exec_ = nullptr;
+    double graph_omega_ = 0.0;
+    int graph_dcur_ = 0, graph_cc_ = 0;
+    bool graph_norm_ = false;
+    size_t graph_launches_ = 0;
+};
+
+template<typename F>
+int guarded(F&& f)
+{
+    try { f(); return BDDB200_OK; }
+    catch(const layout_error& e) { g_last_error = e.what(); return e.code; }
+    catch(const api_error& e) { g_last_error = e.what(); return e.code; }
+    catch(const cuda_error& e) { g_last_error = e.what(); return BDDB200_ERR_CUDA; }
+    catch(const std::bad_alloc&) { g_last_error = "out of host memory"; return BDDB200_ERR_INVALID_ARGUMENT; }
+    catch(const std::exception& e) { g_last_error = e.what(); return BDDB200_ERR_INVALID_ARGUMENT; }
+}
+
+#define REQUIRE_SOLVER(s) if((s) == nullptr) { g_last_error = "null solver handle"; return BDDB200_ERR_INVALID_ARGUMENT; }
+
+} // namespace
+
+// ======================================================================== C ABI ========
+extern "C" {
+
+void bddb200_default_options(bddb200_options* o)
+{
+    if(!o) return;
+    std::memset(o, 0, sizeof(*o));
+}
+const char* bddb200_last_error(void) { return g_last_error.c_str(); }
+const char* bddb200_version(void) { return "bdd_b200 0.1 (sm_100a)"; }
+
+int bddb200_create(const bddb200_instruction* instrs, size_t n_instr, const size_t* delims, size_t n_bdds,
+                   const double* costs_hi, size_t n_costs, int precision, const bddb200_options* opts, bddb200_solver** out)
+{
+    if(out == nullptr || instrs == nullptr || delims == nullptr) { g_last_error = "null argument"; return BDDB200_ERR_INVALID_ARGUMENT; }
+    *out = nullptr;
+    bddb200_options o; bddb200_default_options(&o);
+    if(opts) o = *opts;
+    return guarded([&] {
+        if(precision == BDDB200_DOUBLE) *out = new SolverImpl<double>(instrs, n_instr, delims, n_bdds, costs_hi, n_costs, o);
+        else if(precision == BDDB200_FLOAT) *out = new SolverImpl<float>(instrs, n_instr, delims, n_bdds, costs_hi, n_costs, o);
+        else throw api_error(BDDB200_ERR_INVALID_ARGUMENT, "precision must be BDDB200_FLOAT or BDDB200_DOUBLE");
+    });
+}
+void bddb200_destroy(bddb200_solver* s) { delete s; }
+
+size_t bddb200_nr_variables(const bddb200_solver* s) { return s ? s->nr_variables() : 0; }
+size_t bddb200_nr_bdds(const bddb200_solver* s) { return s ? s->nr_bdds() : 0; }
+size_t bddb200_nr_layers(const bddb200_solver* s) { return s ? s->nr_layers() : 0; }
+size_t bddb200_nr_bdd_nodes(const bddb200_solver* s) { return s ? s->nr_bdd_nodes() : 0; }
+size_t bddb200_nr_hops(const bddb200_solver* s) { return s ? s->nr_hops() : 0; }
+int bddb200_precision_of(const bddb200_solver* s) { return s ? s->precision : -1; }
+int bddb200_device_of(const bddb200_solver* s) { return s ? s->device : -1; }
+int bddb200_nr_bdds_per_var(const bddb200_solver* s, int32_t* out) { REQUIRE_SOLVER(s); return guarded([&] { s->nr_bdds_per_var(out); }); }
+int bddb200_layer_primal_indices(const bddb200_solver* s, int32_t* out) { REQUIRE_SOLVER(s); return guarded([&] { s->layer_primal_indices(out); }); }
+int bddb200_layer_bdd_indices(const bddb200_solver* s, int32_t* out) { REQUIRE_SOLVER(s); return guarded([&] { s->layer_bdd_indices(out); }); }
+
+int bddb200_iteration(bddb200_solver* s, double omega) { REQUIRE_SOLVER(s); return guarded([&] { s->iteration(omega); }); }
+int bddb200_iterations(bddb200_solver* s, double omega, size_t n) { REQUIRE_SOLVER(s); return guarded([&] { s->iterations(omega, n); }); }
+int bddb200_forward_pass(bddb200_solver* s, double omega) { REQUIRE_SOLVER(s); return guarded([&] { s->forward_pass(omega); }); }
+int bddb200_backward_pass(bddb200_solver* s, double omega) { REQUIRE_SOLVER(s); return guarded([&] { s->backward_pass(omega); }); }
+int bddb200_forward_mm(bddb200_solver* s, double omega, void* d) { REQUIRE_SOLVER(s); return guarded([&] { s->forward_mm(omega, d); }); }
+int bddb200_backward_mm(bddb200_solver* s, double omega, void* d) { REQUIRE_SOLVER(s); return guarded([&] { s->backward_mm(omega, d); }); }
+int bddb200_normalize_delta(const bddb200_solver* s, void* d) { REQUIRE_SOLVER(s); return guarded([&] { s->normalize_delta(d); }); }
+int bddb200_get_delta(bddb200_solver* s, void* out, int out_is_host) { REQUIRE_SOLVER(s); return guarded([&] { s->get_delta(out, out_is_host); }); }
+int bddb200_lower_bound(bddb200_solver* s, double* out) { REQUIRE_SOLVER(s); return guarded([&] { *out = s->lower_bound(); }); }
+int bddb200_lower_bound_per_bdd(bddb200_solver* s, void* out) { REQUIRE_SOLVER(s); return guarded([&] { s->lower_bound_per_bdd(out); }); }
+
+int bddb200_forward_run(bddb200_solver* s) { REQUIRE_SOLVER(s); return guarded([&] { s->forward_run(); }); }
+int bddb200_backward_run(bddb200_solver* s) { REQUIRE_SOLVER(s); return guarded([&] { s->backward_run(); }); }
+void bddb200_flush_forward_states(bddb200_solver* s) { if(s) s->flush_forward(); }
+void bddb200_flush_backward_states(bddb200_solver* s) { if(s) s->flush_backward(); }
+
+int bddb200_update_costs_host(bddb200_solver* s, const double* lo, size_t n_lo, const double* hi, size_t n_hi)
+{ REQUIRE_SOLVER(s); return guarded([&] { s->update_costs_host(lo, n_lo, hi, n_hi); }); }
+int bddb200_update_costs_dev(bddb200_solver* s, const void* lo, size_t n_lo, const void* hi, size_t n_hi)
+{ REQUIRE_SOLVER(s); return guarded([&] { s->update_costs_dev(lo, n_lo, hi, n_hi); }); }
+int bddb200_set_cost(bddb200_solver* s, double c, size_t var) { REQUIRE_SOLVER(s); return guarded([&] { s->set_cost(c, var); }); }
+int bddb200_distribute_delta(bddb200_solver* s) { REQUIRE_SOLVER(s); return guarded([&] { s->distribute_delta(); }); }
+int bddb200_get_solver_costs(const bddb200_solver* s, void* lo, void* hi, void* mmd) { REQUIRE_SOLVER(s); return guarded([&] { s->get_solver_costs(lo, hi, mmd); }); }
+int bddb200_set_solver_costs(bddb200_solver* s, const void* lo, const void* hi, const void* mmd)
+{
+    REQUIRE_SOLVER(s);
+    if(!lo || !hi || !mmd) { g_last_error = "null cost vector"; return BDDB200_ERR_INVALID_ARGUMENT; }
+    return guarded([&] { s->set_solver_costs(lo, hi, mmd); });
+}
+int bddb200_primal_objective_host(bddb200_solver* s, double* out) { REQUIRE_SOLVER(s); return guarded([&] { s->primal_objective_host(out); }); }
+
+int bddb200_min_marginals(bddb200_solver* s, int sorted, int32_t* primal, void* lo, void* hi)
+{ REQUIRE_SOLVER(s); return guarded([&] { s->min_marginals(sorted, primal, lo, hi); }); }
+
+int bddb200_bdds_solution(bddb200_solver* s, char* sol) { REQUIRE_SOLVER(s); return guarded([&] { s->bdds_solution(sol); }); }
+int bddb200_net_solver_costs(const bddb200_solver* s, void* out) { REQUIRE_SOLVER(s); return guarded([&] { s->net_solver_costs(out); }); }
+int bddb200_make_dual_feasible(const bddb200_solver* s, void* d) { REQUIRE_SOLVER(s); return guarded([&] { s->make_dual_feasible(d); }); }
+int bddb200_gradient_step(bddb200_solver* s, const void* dir, double step) { REQUIRE_SOLVER(s); return guarded([&] { s->gradient_step(dir, step); }); }
+
+int bddb200_synchronize(bddb200_solver* s) { REQUIRE_SOLVER(s); return guarded([&] { s->synchronize(); }); }
+void* bddb200_stream(bddb200_solver* s) { return s ? s->stream_handle() : nullptr; }
+size_t bddb200_kernel_launches(const bddb200_solver* s) { return s ? s->kernel_launches() : 0; }
+int bddb200_delta_sum_buffer(bddb200_solver* s, void** out) { REQUIRE_SOLVER(s); return guarded([&] { *out = s->delta_sum_buffer(); }); }
+
+int bddb200_layout_stats(const bddb200_instruction* instrs, size_t n_instr, const size_t* delims, size_t n_bdds, int lanes_per_bdd, uint64_t* out, size_t n)
+{
+    return guarded([&] {
+        const HostLayout L = build_layout(instrs, n_instr, delims, n_bdds, lanes_per_bdd);
+        const uint64_t vals[8] = {L.n_slots, L.n_lay, L.bundles.size(), L.n_real_nodes, L.max_hops,
+                                  std::max(L.max_tile_small, L.max_tile_large), L.n_small_bundles, L.n_layers_ext};
+        for(size_t i = 0; i < n && i < 8; ++i) out[i] = vals[i];
+    });
+}
+
+} // extern "C"

@@ -1,0 +1,326 @@
+// bdd_b200/csrc/layout.hpp -- host-side layout builder: BDD::bdd_collection (flat
+// instruction array) -> the bundle/hop-major SoA the sm_100a sweep kernels stream.
+//
+// Replaces the reference's constructor chain bdd_cuda_base.cu:31-46 (initialize,
+// populate_bdd_nodes, reorder_bdd_nodes, compress_bdd_nodes_to_layer,
+// reorder_within_bdd_layers, set_special_nodes_indices, find_primal_variable_ordering;
+// SURVEY 3.2), which sorts all nodes of all BDDs by hop with thrust and launches one kernel
+// per hop.  Here the unit of work is a *bundle*: 32/P BDDs processed by ONE warp, P lanes
+// per BDD, swept hop by hop without any grid- or block-level synchronisation (within a
+// pass BDDs are independent).
+//
+// Memory layout (all arrays indexed by "slot" or "layer entry"):
+//   bundle g, hop k owns a tile of 32 * J[g][k] node slots starting at hop.node_off;
+//   slot (j, lane) = node_off + j*32 + lane holds, for the BDD owning that lane group
+//   (bdd_local = lane >> logP), the node with index  c = j*P + (lane & (P-1))  of that BDD's
+//   layer k.  A warp therefore reads every per-node array with fully coalesced 128-byte
+//   rows, and a BDD's frontier stays in the same shared-memory banks from hop to hop.
+//   topo[slot] = lo_child | hi_child << 16, children given as slot index inside the NEXT
+//   hop's tile (0xFFFF = arc into the bot sink: value +inf, no memory access);
+//   TOPO_TOP marks the BDD's top sink (cost_from_terminal 0), TOPO_PAD an unused slot.
+//   Layer entry (g, k, bdd_local) = layer_base + k*(32/P) + bdd_local holds the layer's
+//   variable, the (global) number of BDDs of that variable, lo/hi arc cost and the deferred
+//   min-marginal difference.
+#pragma once
+
+#include <algorithm>
+#include <climits>
+#include <cstddef>
+#include <cstdint>
+#include <numeric>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/bdd_b200.h"
+
+namespace bddb200 {
+
+constexpr uint32_t TOPO_PAD = 0xFFFFFFFFu;
+constexpr uint32_t TOPO_TOP = 0xFFFFFFFEu;
+constexpr uint32_t CHILD_BOT = 0xFFFFu;
+constexpr uint32_t MAX_TILE_SLOTS = 0xFFFFu;      // child slot indices are 16 bit
+constexpr uint32_t SMALL_CLASS_MAX_J = 8;         // bundles with J <= 8 share multi-warp CTAs
+
+struct HopRec {
+    uint32_t node_off;   // first slot of the tile
+    uint32_t J;          // rows of 32 slots
+};
+
+struct BundleDesc {
+    uint32_t hop_base;   // index of the bundle's first HopRec
+    uint32_t n_hops;     // hops incl. the terminal hop of the longest BDD
+    uint32_t layer_base; // first layer entry
+    uint32_t logP;       // log2(lanes per BDD)
+    uint32_t bdd_base;   // first entry in bundle_bdd (32 >> logP entries)
+    uint32_t max_J;
+    uint32_t work;       // sum of J over hops (scheduling weight)
+    uint32_t pad_;
+};
+
+struct layout_error : std::runtime_error {
+    int code;
+    layout_error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+struct HostLayout {
+    size_t n_vars = 0, n_bdds = 0, n_instr = 0;
+    size_t n_layers_ext = 0;   // sum over BDDs of (nr variables + 1)
+    size_t n_real_nodes = 0;   // non-terminal nodes
+    size_t n_slots = 0, n_lay = 0, max_hops = 0;
+    size_t n_small_bundles = 0;          // bundles [0, n_small) have max_J <= SMALL_CLASS_MAX_J
+    uint32_t max_tile_small = 0, max_tile_large = 0;  // slots
+    std::vector<BundleDesc> bundles;
+    std::vector<HopRec> hops;
+    std::vector<int32_t> bundle_bdd;     // per bundle lane group: external BDD index or -1
+    std::vector<uint32_t> topo;          // per slot
+    std::vector<int32_t> lay_var;        // per layer entry: variable or -1
+    std::vector<uint32_t> ext2lay;       // external layer -> layer entry
+    std::vector<int32_t> ext_var;        // external layer -> variable (INT_MAX terminal)
+    std::vector<int32_t> ext_bdd;        // external layer -> BDD
+    std::vector<uint32_t> bdd_ext_begin; // per BDD: first external layer (n_bdds+1)
+    std::vector<uint32_t> root_slot, top_slot;  // per BDD
+    std::vector<int32_t> nr_bdds_per_var;       // counted from this collection
+    // variable -> layer entries in (variable, BDD index) order (deterministic delta sums,
+    // make_dual_feasible, sorted min-marginals)
+    std::vector<uint32_t> var_lay_begin; // n_vars+1
+    std::vector<uint32_t> var_lay;       // layer entries
+    std::vector<uint32_t> sorted_ext;    // external layers sorted by (var, bdd), terminals last
+};
+
+inline uint32_t pow2ceil(uint32_t x) { uint32_t p = 1; while(p < x) p <<= 1; return p; }
+inline uint32_t ilog2(uint32_t x) { uint32_t l = 0; while((1u << l) < x) ++l; return l; }
+
+// lanes_per_bdd: 0 = heuristic (about <= 4 nodes of a layer per lane), else forced.
+inline HostLayout build_layout(const bddb200_instruction* instrs, size_t n_instr,
+                               const size_t* delims, size_t n_bdds, int lanes_per_bdd,
+                               size_t nr_variables_override = 0)
+{
+    constexpr size_t TOPSINK = (size_t)-1, BOTSINK = (size_t)-1 - 1;
+    if(n_bdds == 0) throw layout_error(BDDB200_ERR_INVALID_ARGUMENT, "empty BDD collection");
+    if(lanes_per_bdd != 0 && (lanes_per_bdd < 1 || lanes_per_bdd > 32 || (lanes_per_bdd & (lanes_per_bdd - 1))))
+        throw layout_error(BDDB200_ERR_INVALID_ARGUMENT, "lanes_per_bdd must be 0 or a power of two <= 32");
+    if(delims[n_bdds] > n_instr) throw layout_error(BDDB200_ERR_INVALID_ARGUMENT, "delimiters exceed instruction array");
+
+    HostLayout L;
+    L.n_bdds = n_bdds; L.n_instr = n_instr;
+
+    // ---- pass 1: layers of every BDD, validation, widths ------------------------------
+    L.bdd_ext_begin.assign(n_bdds + 1, 0);
+    std::vector<uint32_t> ext_first_instr;   // per external layer: first instruction; layer e spans [efi[e], efi[e+1])
+    std::vector<uint32_t> bdd_maxw(n_bdds, 1);
+    size_t max_var = 0;
+    for(size_t b = 0; b < n_bdds; ++b)
+    {
+        const size_t first = delims[b], last = delims[b+1];
+        if(last < first + 3) throw layout_error(BDDB200_ERR_INVALID_ARGUMENT, "BDD " + std::to_string(b) + " has no inner node");
+        // the two sinks close every BDD, in either order (bdd_collection.cpp:403-428 vs :1581-1586)
+        if(!((instrs[last-2].index == BOTSINK && instrs[last-1].index == TOPSINK) || (instrs[last-2].index == TOPSINK && instrs[last-1].index == BOTSINK)))
+            throw layout_error(BDDB200_ERR_INVALID_ARGUMENT, "BDD " + std::to_string(b) + ": last two instructions must be the bot and top sink");
+        L.bdd_ext_begin[b] = (uint32_t)ext_first_instr.size();
+        size_t prev = TOPSINK;
+        for(size_t i = first; i + 2 < last; ++i)
+        {
+            const size_t var = instrs[i].index;
+            if(var >= BOTSINK) throw layout_error(BDDB200_ERR_INVALID_ARGUMENT, "terminal instruction inside BDD " + std::to_string(b));
+            if(var != prev)
+            {
+                ext_first_instr.push_back((uint32_t)i);
+                L.ext_var.push_back((int32_t)var);
+                L.ext_bdd.push_back((int32_t)b);
+                prev = var;
+                if(var > max_var) max_var = var;
+            }
+        }
+        ext_first_instr.push_back((uint32_t)(last - 2));   // terminal layer entry = end of the inner nodes
+        L.ext_var.push_back(INT_MAX);
+        L.ext_bdd.push_back((int32_t)b);
+        L.n_real_nodes += last - first - 2;
+    }
+    L.bdd_ext_begin[n_bdds] = (uint32_t)ext_first_instr.size();
+    L.n_layers_ext = ext_first_instr.size();
+    L.n_vars = std::max(max_var + 1, nr_variables_override);
+    if(L.n_vars > (size_t)INT_MAX / 2) throw layout_error(BDDB200_ERR_INVALID_ARGUMENT, "too many variables");
+
+    // QBDD check (reference: assert(is_qbdd && is_reordered), bdd_cuda_base.cu:100-101):
+    // every arc of layer k enters layer k+1 or the bot sink; the top sink only from the last layer.
+    for(size_t b = 0; b < n_bdds; ++b)
+    {
+        const size_t last = delims[b+1];
+        const size_t bot = instrs[last-2].index == BOTSINK ? last - 2 : last - 1, top = instrs[last-2].index == BOTSINK ? last - 1 : last - 2;
+        const uint32_t eb = L.bdd_ext_begin[b], ee = L.bdd_ext_begin[b+1] - 1; // ee = terminal layer
+        uint32_t maxw = 1;
+        for(uint32_t e = eb; e < ee; ++e)
+        {
+            const size_t lb = ext_first_instr[e], le = ext_first_instr[e+1];
+            const bool last_layer = (e + 1 == ee);
+            const size_t ne = last_layer ? le : ext_first_instr[e+2];   // next layer = [le, ne)
+            maxw = std::max<uint32_t>(maxw, (uint32_t)(le - lb));
+            for(size_t i = lb; i < le; ++i)
+            {
+                for(const size_t c : {instrs[i].lo, instrs[i].hi})
+                {
+                    if(c == bot) continue;
+                    if(last_layer ? (c != top) : !(c >= le && c < ne))
+                        throw layout_error(BDDB200_ERR_NOT_QBDD, "BDD " + std::to_string(b) + " is not a reordered QBDD (arc skips a layer)");
+                }
+            }
+        }
+        bdd_maxw[b] = maxw;
+    }
+
+    // ---- lanes per BDD, sort, bundles --------------------------------------------------
+    std::vector<uint8_t> bdd_logP(n_bdds);
+    for(size_t b = 0; b < n_bdds; ++b)
+    {
+        uint32_t P = lanes_per_bdd ? (uint32_t)lanes_per_bdd : std::min<uint32_t>(32, pow2ceil((bdd_maxw[b] + 3) / 4));
+        bdd_logP[b] = (uint8_t)ilog2(P);
+    }
+    std::vector<uint32_t> order(n_bdds);
+    std::iota(order.begin(), order.end(), 0u);
+    auto nlay = [&](uint32_t b) { return L.bdd_ext_begin[b+1] - L.bdd_ext_begin[b]; };
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+        if(bdd_logP[x] != bdd_logP[y]) return bdd_logP[x] < bdd_logP[y];
+        return nlay(x) > nlay(y);
+    });
+
+    struct ProtoBundle { uint32_t first, count, logP, n_hops, max_J, work; std::vector<uint32_t> J; };
+    std::vector<ProtoBundle> protos;
+    for(size_t pos = 0; pos < n_bdds;)
+    {
+        const uint32_t logP = bdd_logP[order[pos]];
+        const uint32_t bpw = 32u >> logP, P = 1u << logP;
+        size_t end = pos;
+        while(end < n_bdds && end - pos < bpw && bdd_logP[order[end]] == logP) ++end;
+        ProtoBundle pb;
+        pb.first = (uint32_t)pos; pb.count = (uint32_t)(end - pos); pb.logP = logP;
+        pb.n_hops = 0;
+        for(size_t q = pos; q < end; ++q) pb.n_hops = std::max(pb.n_hops, nlay(order[q]));
+        pb.J.assign(pb.n_hops, 0);
+        for(size_t q = pos; q < end; ++q)
+        {
+            const uint32_t b = order[q];
+            const uint32_t eb = L.bdd_ext_begin[b], ee = L.bdd_ext_begin[b+1];
+            for(uint32_t e = eb; e < ee; ++e)
+            {
+                const uint32_t w = (e + 1 < ee) ? (ext_first_instr[e+1] - ext_first_instr[e]) : 1u;   // terminal layer: the top sink
+                pb.J[e - eb] = std::max(pb.J[e - eb], (w + P - 1) / P);
+            }
+        }
+        pb.max_J = *std::max_element(pb.J.begin(), pb.J.end());
+        pb.work = std::accumulate(pb.J.begin(), pb.J.end(), 0u);
+        if(pb.max_J * 32u > MAX_TILE_SLOTS)
+            throw layout_error(BDDB200_ERR_TOO_WIDE, "a BDD layer is wider than " + std::to_string(MAX_TILE_SLOTS) + " nodes; split the BDD (split_qbdd)");
+        protos.push_back(std::move(pb));
+        pos = end;
+    }
+    // small class first; inside a class heavy bundles first (longest-processing-time order)
+    std::vector<uint32_t> border(protos.size());
+    std::iota(border.begin(), border.end(), 0u);
+    std::stable_sort(border.begin(), border.end(), [&](uint32_t x, uint32_t y) {
+        const bool sx = protos[x].max_J <= SMALL_CLASS_MAX_J, sy = protos[y].max_J <= SMALL_CLASS_MAX_J;
+        if(sx != sy) return sx;
+        return protos[x].work > protos[y].work;
+    });
+
+    // ---- emit --------------------------------------------------------------------------
+    L.bundles.reserve(protos.size());
+    size_t slot = 0, lay = 0;
+    for(const uint32_t pi : border)
+    {
+        const ProtoBundle& pb = protos[pi];
+        BundleDesc bd{};
+        bd.hop_base = (uint32_t)L.hops.size();
+        bd.n_hops = pb.n_hops; bd.logP = pb.logP; bd.max_J = pb.max_J; bd.work = pb.work;
+        bd.layer_base = (uint32_t)lay;
+        bd.bdd_base = (uint32_t)L.bundle_bdd.size();
+        const uint32_t bpw = 32u >> pb.logP;
+        for(uint32_t k = 0; k < pb.n_hops; ++k)
+        {
+            if(slot > 0xFFFFFFFFull - 32ull * pb.J[k]) throw layout_error(BDDB200_ERR_INVALID_ARGUMENT, "collection too large (slot index overflow)");
+            L.hops.push_back(HopRec{(uint32_t)slot, pb.J[k]});
+            slot += 32ull * pb.J[k];
+        }
+        for(uint32_t q = 0; q < bpw; ++q)
+            L.bundle_bdd.push_back(q < pb.count ? (int32_t)order[pb.first + q] : -1);
+        lay += (size_t)pb.n_hops * bpw;
+        if(pb.max_J <= SMALL_CLASS_MAX_J) { L.n_small_bundles++; L.max_tile_small = std::max(L.max_tile_small, pb.max_J * 32u); }
+        else L.max_tile_large = std::max(L.max_tile_large, pb.max_J * 32u);
+        L.max_hops = std::max<size_t>(L.max_hops, pb.n_hops);
+        L.bundles.push_back(bd);
+    }
+    L.n_slots = slot; L.n_lay = lay;
+    if(lay > 0xFFFFFFF0ull) throw layout_error(BDDB200_ERR_INVALID_ARGUMENT, "collection too large (layer index overflow)");
+
+    L.topo.assign(L.n_slots, TOPO_PAD);
+    L.lay_var.assign(L.n_lay, -1);
+    L.ext2lay.assign(L.n_layers_ext, 0);
+    L.root_slot.assign(n_bdds, 0);
+    L.top_slot.assign(n_bdds, 0);
+    L.nr_bdds_per_var.assign(L.n_vars, 0);
+
+    for(size_t g = 0; g < L.bundles.size(); ++g)
+    {
+        const BundleDesc& bd = L.bundles[g];
+        const uint32_t logP = bd.logP, P = 1u << logP, bpw = 32u >> logP;
+        for(uint32_t q = 0; q < bpw; ++q)
+        {
+            const int32_t bi = L.bundle_bdd[bd.bdd_base + q];
+            if(bi < 0) continue;
+            const size_t b = (size_t)bi;
+            const size_t last = delims[b+1];
+            const size_t bot = instrs[last-2].index == BOTSINK ? last - 2 : last - 1, top = instrs[last-2].index == BOTSINK ? last - 1 : last - 2;
+            const uint32_t eb = L.bdd_ext_begin[b], ee = L.bdd_ext_begin[b+1] - 1;
+            auto tile_slot = [&](uint32_t c) { return (c >> logP) * 32u + (q << logP) + (c & (P - 1)); };
+            for(uint32_t e = eb; e <= ee; ++e)
+            {
+                const uint32_t k = e - eb;
+                const uint32_t layer_entry = bd.layer_base + k * bpw + q;
+                L.ext2lay[e] = layer_entry;
+                const HopRec& hr = L.hops[bd.hop_base + k];
+                if(e == ee)
+                {
+                    L.topo[hr.node_off + tile_slot(0)] = TOPO_TOP;
+                    L.top_slot[b] = hr.node_off + tile_slot(0);
+                    continue;
+                }
+                const size_t lb = ext_first_instr[e], le = ext_first_instr[e+1];
+                const size_t next_first = le;   // first instruction of the next layer (or the bot sink)
+                L.lay_var[layer_entry] = L.ext_var[e];
+                L.nr_bdds_per_var[L.ext_var[e]]++;
+                if(k == 0) L.root_slot[b] = hr.node_off + tile_slot(0);
+                for(size_t i = lb; i < le; ++i)
+                {
+                    auto child = [&](size_t c) -> uint32_t {
+                        if(c == bot) return CHILD_BOT;
+                        if(c == top) return tile_slot(0);
+                        return tile_slot((uint32_t)(c - next_first));
+                    };
+                    L.topo[hr.node_off + tile_slot((uint32_t)(i - lb))] = child(instrs[i].lo) | (child(instrs[i].hi) << 16);
+                }
+            }
+        }
+    }
+
+    // ---- variable -> layers (sorted by variable, then BDD index) ------------------------
+    L.var_lay_begin.assign(L.n_vars + 1, 0);
+    for(size_t e = 0; e < L.n_layers_ext; ++e)
+        if(L.ext_var[e] != INT_MAX) L.var_lay_begin[L.ext_var[e] + 1]++;
+    for(size_t v = 0; v < L.n_vars; ++v) L.var_lay_begin[v+1] += L.var_lay_begin[v];
+    L.var_lay.assign(L.var_lay_begin[L.n_vars], 0);
+    L.sorted_ext.assign(L.n_layers_ext, 0);
+    {
+        std::vector<uint32_t> fill(L.var_lay_begin.begin(), L.var_lay_begin.end() - 1);
+        size_t term = L.var_lay_begin[L.n_vars];
+        for(size_t e = 0; e < L.n_layers_ext; ++e)   // external order is BDD-major => BDD index ascending per variable
+        {
+            if(L.ext_var[e] == INT_MAX) { L.sorted_ext[term++] = (uint32_t)e; continue; }
+            const uint32_t p = fill[L.ext_var[e]]++;
+            L.var_lay[p] = L.ext2lay[e];
+            L.sorted_ext[p] = (uint32_t)e;
+        }
+    }
+    return L;
+}
+
+} // namespace bddb200

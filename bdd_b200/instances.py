@@ -33,8 +33,9 @@ BOTSINK = np.uint64(0xFFFFFFFFFFFFFFFE)  # bdd_instruction::botsink_index (bdd_c
 @dataclass
 class BddCollection:
     """Flat ``bdd_collection``: ``instrs[i] = (lo, hi, index)`` with absolute lo/hi, the
-    last two instructions of every BDD being the bot sink and the top sink
-    (bdd_collection.cpp:1581-1586); ``delims`` has nr_bdds+1 entries."""
+    last two instructions of every BDD being its two sinks (this module emits bot, top like
+    bdd_collection.cpp:1581-1586; the reference's add_bdd may emit them in the other order and
+    every consumer here accepts both); ``delims`` has nr_bdds+1 entries."""
 
     instrs: np.ndarray  # uint64 [n, 3]
     delims: np.ndarray  # uint64 [B + 1]
@@ -126,13 +127,37 @@ def qbdd_template(coeffs: Sequence[int], ineq: int, rhs: int) -> Optional[QbddTe
     # every emitted node is reachable; the function is constant true iff no arc enters the bot sink
     if not any(BOT in key for nl in nodes_per_layer for key in nl):
         return None
-    offsets = np.cumsum([0] + [len(nl) for nl in nodes_per_layer])
+    # A variable the function does not depend on (every node of its layer has lo == hi) gets
+    # no layer at all: the reference's reduced BDD does not contain it and make_qbdd only
+    # bridges between the variables that are present.  Splice such layers out bottom-up.
+    keep = [not all(l == h for (l, h) in nl) for nl in nodes_per_layer]
+    resolve: List[Dict[int, int]] = [dict() for _ in range(n + 1)]   # node id in layer k -> (layer, id) it stands for
+    new_ids: List[Dict[int, int]] = [dict() for _ in range(n)]
+    target: List[List[Tuple[int, int]]] = [[] for _ in range(n)]     # per kept layer: children as (code or (layer,id))
+    def stands_for(k: int, i: int):
+        """(layer, id) of the first kept node reached from node i of layer k, or a terminal code."""
+        while True:
+            if i < 0:
+                return i
+            if keep[k]:
+                return (k, i)
+            i = nodes_per_layer[k][i][0]
+            k += 1
+    kept_layers = [k for k in range(n) if keep[k]]
+    offsets = {}
+    off = 0
+    for k in kept_layers:
+        offsets[k] = off
+        off += len(nodes_per_layer[k])
     layer, lo, hi = [], [], []
-    for k in range(n):
+    for k in kept_layers:
         for (l, h) in nodes_per_layer[k]:
+            cl = stands_for(k + 1, l) if l >= 0 else l
+            ch = stands_for(k + 1, h) if h >= 0 else h
             layer.append(k)
-            lo.append(l if l < 0 else int(offsets[k + 1]) + l)
-            hi.append(h if h < 0 else int(offsets[k + 1]) + h)
+            lo.append(cl if isinstance(cl, int) else offsets[cl[0]] + cl[1])
+            hi.append(ch if isinstance(ch, int) else offsets[ch[0]] + ch[1])
+    del resolve, new_ids, target
     return QbddTemplate(np.asarray(layer, np.int64), np.asarray(lo, np.int64), np.asarray(hi, np.int64))
 
 
@@ -333,11 +358,13 @@ def _both_values_feasible(t: QbddTemplate) -> bool:
     """True iff no variable of the constraint is forced: every layer has a node whose lo arc
     and a node whose hi arc avoids the bot sink (all nodes of a reduced BDD reach the top sink)."""
     nl = int(t.layer.max()) + 1
+    present = np.zeros(nl, dtype=bool)
+    present[t.layer] = True
     lo_ok = np.zeros(nl, dtype=bool)
     hi_ok = np.zeros(nl, dtype=bool)
     np.logical_or.at(lo_ok, t.layer, t.lo != -1)
     np.logical_or.at(hi_ok, t.layer, t.hi != -1)
-    return bool(lo_ok.all() and hi_ok.all())
+    return bool((lo_ok | ~present).all() and (hi_ok | ~present).all())
 
 
 def random_inequalities(nr_constraints: int, nr_vars: int, max_len: int = 8, max_coeff: int = 4, seed: int = 0) -> Tuple[BddCollection, np.ndarray]:

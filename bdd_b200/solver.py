@@ -1,0 +1,318 @@
+"""Host-side mirror of the reference's GPU solver class over the C ABI.
+
+``bdd_cuda_parallel_mma`` has the method set of ``LPMP::bdd_cuda_parallel_mma<REAL>`` and its
+base ``LPMP::bdd_cuda_base<REAL>`` (include/bdd_solver/bdd_cuda_parallel_mma.h:7-52,
+include/bdd_solver/bdd_cuda_base.h:57-226): same names, argument meaning and error behaviour
+(exceptions), with ``torch`` CUDA tensors standing in for ``thrust::device_vector``.  Every
+method is one call into libbdd_b200.so (include/bdd_b200.h); PyTorch only owns device
+buffers and streams.  There is no CPU fallback.
+
+``run_solver`` is the termination loop of include/run_solver_util.h:10-77.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Options, check
+from .instances import BddCollection
+
+INT_MAX = 2 ** 31 - 1
+
+
+class bdd_cuda_parallel_mma:
+    """``bdd_cuda_parallel_mma<REAL>(bdd_col, costs)`` (bdd_cuda_parallel_mma.cu:7-17).
+
+    precision: "float" or "double" (REAL).  ``deterministic`` selects fixed-order per-variable
+    sums; ``nr_variables`` / ``nr_bdds_per_var`` put the solver in shard mode.
+    """
+
+    def __init__(self, bdd_col: BddCollection, costs: Optional[Sequence[float]] = None, precision: str = "float",
+                 device: int = 0, deterministic: bool = False, lanes_per_bdd: int = 0, nr_variables: int = 0,
+                 nr_bdds_per_var: Optional[np.ndarray] = None, stream: Optional[torch.cuda.Stream] = None):
+        self.lib = _lib.load()
+        if precision not in ("float", "double"):
+            raise ValueError("precision must be 'float' or 'double'")
+        if not torch.cuda.is_available():
+            raise RuntimeError("bdd_cuda_parallel_mma needs a CUDA device (no CPU fallback)")
+        self.precision = precision
+        self.value_type = torch.float64 if precision == "double" else torch.float32
+        self.np_type = np.float64 if precision == "double" else np.float32
+        self.device = torch.device("cuda", device)
+        self.stream = stream if stream is not None else torch.cuda.Stream(self.device)
+        instrs = np.ascontiguousarray(bdd_col.instrs, dtype=np.uint64)
+        delims = np.ascontiguousarray(bdd_col.delims, dtype=np.uint64)
+        opts = Options()
+        self.lib.bddb200_default_options(C.byref(opts))
+        opts.device = device
+        opts.stream = self.stream.cuda_stream
+        opts.deterministic = int(deterministic)
+        opts.lanes_per_bdd = int(lanes_per_bdd)
+        opts.nr_variables = int(nr_variables)
+        self._nbpv = None
+        if nr_bdds_per_var is not None:
+            self._nbpv = np.ascontiguousarray(nr_bdds_per_var, dtype=np.int32)
+            opts.nr_bdds_per_var_host = self._nbpv.ctypes.data
+        cptr, ncost = None, 0
+        if costs is not None:
+            self._costs = np.ascontiguousarray(costs, dtype=np.float64)
+            cptr, ncost = self._costs.ctypes.data, self._costs.shape[0]
+        h = C.c_void_p()
+        check(self.lib.bddb200_create(instrs.ctypes.data, instrs.shape[0], delims.ctypes.data, delims.shape[0] - 1,
+                                      cptr, ncost, _lib.DOUBLE if precision == "double" else _lib.FLOAT,
+                                      C.byref(opts), C.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        h = getattr(self, "h", None)
+        if h:
+            self.lib.bddb200_destroy(h)
+            self.h = None
+
+    # ------------------------------------------------------------------ helpers --------
+    def _empty(self, n: int, dtype=None) -> torch.Tensor:
+        with torch.cuda.stream(self.stream):
+            return torch.empty(n, dtype=dtype or self.value_type, device=self.device)
+
+    def _in(self, t: torch.Tensor, n: Optional[int] = None, dtype=None) -> torch.Tensor:
+        dtype = dtype or self.value_type
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+            raise TypeError(f"expected a contiguous CUDA tensor of dtype {dtype}")
+        if n is not None and t.numel() != n:
+            raise ValueError(f"expected {n} elements, got {t.numel()}")
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        return t
+
+    def _out(self):
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+
+    # ------------------------------------------------------------------ sizes ----------
+    def nr_variables(self) -> int:
+        return self.lib.bddb200_nr_variables(self.h)
+
+    def nr_bdds(self, var: Optional[int] = None) -> int:
+        if var is None:
+            return self.lib.bddb200_nr_bdds(self.h)
+        return int(self.get_num_bdds_per_var()[var])
+
+    def nr_layers(self) -> int:
+        return self.lib.bddb200_nr_layers(self.h)
+
+    def nr_bdd_nodes(self) -> int:
+        return self.lib.bddb200_nr_bdd_nodes(self.h)
+
+    def nr_hops(self) -> int:
+        return self.lib.bddb200_nr_hops(self.h)
+
+    def get_num_bdds_per_var(self) -> np.ndarray:
+        out = np.empty(self.nr_variables(), dtype=np.int32)
+        check(self.lib.bddb200_nr_bdds_per_var(self.h, out.ctypes.data))
+        return out
+
+    def get_primal_variable_index(self) -> np.ndarray:
+        out = np.empty(self.nr_layers(), dtype=np.int32)
+        check(self.lib.bddb200_layer_primal_indices(self.h, out.ctypes.data))
+        return out
+
+    def get_bdd_index(self) -> np.ndarray:
+        out = np.empty(self.nr_layers(), dtype=np.int32)
+        check(self.lib.bddb200_layer_bdd_indices(self.h, out.ctypes.data))
+        return out
+
+    # ------------------------------------------------------------------ hot path -------
+    def iteration(self, omega: float = 0.5):
+        check(self.lib.bddb200_iteration(self.h, omega))
+
+    def iterations(self, n: int, omega: float = 0.5):
+        check(self.lib.bddb200_iterations(self.h, omega, n))
+
+    def forward_pass(self, omega: float = 0.5):
+        check(self.lib.bddb200_forward_pass(self.h, omega))
+
+    def backward_pass(self, omega: float = 0.5):
+        check(self.lib.bddb200_backward_pass(self.h, omega))
+
+    def forward_mm(self, omega: float, delta_lo_hi: torch.Tensor):
+        check(self.lib.bddb200_forward_mm(self.h, omega, self._in(delta_lo_hi, 2 * self.nr_variables()).data_ptr()))
+        self._out()
+
+    def backward_mm(self, omega: float, delta_lo_hi: torch.Tensor):
+        check(self.lib.bddb200_backward_mm(self.h, omega, self._in(delta_lo_hi, 2 * self.nr_variables()).data_ptr()))
+        self._out()
+
+    def normalize_delta(self, delta_lo_hi: torch.Tensor):
+        check(self.lib.bddb200_normalize_delta(self.h, self._in(delta_lo_hi, 2 * self.nr_variables()).data_ptr()))
+        self._out()
+
+    def get_delta(self) -> torch.Tensor:
+        out = self._empty(2 * self.nr_variables())
+        check(self.lib.bddb200_get_delta(self.h, out.data_ptr(), 0))
+        self._out()
+        return out
+
+    def delta_sum_view(self) -> torch.Tensor:
+        """The solver's current un-normalised delta sums as a tensor aliasing solver memory
+        (for the multi-GPU all-reduce; valid until the next pass)."""
+        p = C.c_void_p()
+        check(self.lib.bddb200_delta_sum_buffer(self.h, C.byref(p)))
+        n = 2 * self.nr_variables()
+        itemsize = 8 if self.precision == "double" else 4
+        iface = {"shape": (n,), "typestr": "<f8" if self.precision == "double" else "<f4",
+                 "data": (p.value, False), "version": 3, "strides": (itemsize,)}
+        holder = type("_DevView", (), {"__cuda_array_interface__": iface})()
+        with torch.cuda.stream(self.stream):
+            return torch.as_tensor(holder, device=self.device)
+
+    def lower_bound(self) -> float:
+        out = C.c_double()
+        check(self.lib.bddb200_lower_bound(self.h, C.byref(out)))
+        return out.value
+
+    def lower_bound_per_bdd(self) -> torch.Tensor:
+        out = self._empty(self.nr_bdds())
+        check(self.lib.bddb200_lower_bound_per_bdd(self.h, out.data_ptr()))
+        self._out()
+        return out
+
+    def forward_run(self):
+        check(self.lib.bddb200_forward_run(self.h))
+
+    def backward_run(self):
+        check(self.lib.bddb200_backward_run(self.h))
+
+    def flush_forward_states(self):
+        self.lib.bddb200_flush_forward_states(self.h)
+
+    def flush_backward_states(self):
+        self.lib.bddb200_flush_backward_states(self.h)
+
+    # ------------------------------------------------------------------ costs ----------
+    def update_costs(self, cost_delta_0, cost_delta_1):
+        """update_costs(lo, hi): host sequences (std::vector overload, bdd_cuda_base.cu:519-523)
+        or CUDA tensors of REAL (device_vector overload, :525-558)."""
+        if isinstance(cost_delta_0, torch.Tensor) or isinstance(cost_delta_1, torch.Tensor):
+            lo = cost_delta_0 if isinstance(cost_delta_0, torch.Tensor) else None
+            hi = cost_delta_1 if isinstance(cost_delta_1, torch.Tensor) else None
+            nlo = lo.numel() if lo is not None else 0
+            nhi = hi.numel() if hi is not None else 0
+            check(self.lib.bddb200_update_costs_dev(self.h, self._in(lo).data_ptr() if nlo else None, nlo,
+                                                    self._in(hi).data_ptr() if nhi else None, nhi))
+            return
+        lo = np.ascontiguousarray(cost_delta_0 if cost_delta_0 is not None else [], dtype=np.float64)
+        hi = np.ascontiguousarray(cost_delta_1 if cost_delta_1 is not None else [], dtype=np.float64)
+        check(self.lib.bddb200_update_costs_host(self.h, lo.ctypes.data if lo.size else None, lo.size,
+                                                 hi.ctypes.data if hi.size else None, hi.size))
+
+    def set_cost(self, c: float, var: int):
+        check(self.lib.bddb200_set_cost(self.h, c, var))
+
+    def distribute_delta(self):
+        check(self.lib.bddb200_distribute_delta(self.h))
+
+    def get_solver_costs(self) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        n = self.nr_layers()
+        lo, hi, mm = self._empty(n), self._empty(n), self._empty(n)
+        check(self.lib.bddb200_get_solver_costs(self.h, lo.data_ptr(), hi.data_ptr(), mm.data_ptr()))
+        self._out()
+        return lo, hi, mm
+
+    def set_solver_costs(self, costs: Tuple[torch.Tensor, torch.Tensor, torch.Tensor]):
+        n = self.nr_layers()
+        lo, hi, mm = (self._in(t, n) for t in costs)
+        check(self.lib.bddb200_set_solver_costs(self.h, lo.data_ptr(), hi.data_ptr(), mm.data_ptr()))
+
+    def get_primal_objective_vector_host(self) -> np.ndarray:
+        out = np.empty(self.nr_variables(), dtype=np.float64)
+        check(self.lib.bddb200_primal_objective_host(self.h, out.ctypes.data))
+        return out
+
+    # ------------------------------------------------------------------ min-marginals --
+    def min_marginals_cuda(self, get_sorted: bool = True) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """(primal index, mm_lo, mm_hi) per layer; sorted by (variable, BDD) with the
+        nr_bdds() terminal entries last when get_sorted (bdd_cuda_base.cu:716-751)."""
+        n = self.nr_layers()
+        idx, lo, hi = self._empty(n, torch.int32), self._empty(n), self._empty(n)
+        check(self.lib.bddb200_min_marginals(self.h, int(get_sorted), idx.data_ptr(), lo.data_ptr(), hi.data_ptr()))
+        self._out()
+        return idx, lo, hi
+
+    def min_marginals(self) -> List[np.ndarray]:
+        """two_dim_variable_array<array<double,2>>: per variable an [nr_bdds(var), 2] array
+        (bdd_cuda_base.cu:753-786)."""
+        _, lo, hi = self.min_marginals_cuda(True)
+        self.synchronize()
+        lo = lo.cpu().numpy().astype(np.float64)
+        hi = hi.cpu().numpy().astype(np.float64)
+        counts = self.get_num_bdds_per_var()
+        local = np.bincount(self.get_primal_variable_index()[self.get_primal_variable_index() != INT_MAX], minlength=self.nr_variables())
+        out, pos = [], 0
+        for v in range(self.nr_variables()):
+            k = int(local[v])
+            out.append(np.stack([lo[pos:pos + k], hi[pos:pos + k]], axis=1))
+            pos += k
+        del counts
+        return out
+
+    # ------------------------------------------------------------------ L-BFGS surface -
+    def bdds_solution_vec(self) -> torch.Tensor:
+        out = self._empty(self.nr_layers(), torch.int8)
+        check(self.lib.bddb200_bdds_solution(self.h, out.data_ptr()))
+        self._out()
+        return out
+
+    def net_solver_costs(self) -> torch.Tensor:
+        out = self._empty(self.nr_layers())
+        check(self.lib.bddb200_net_solver_costs(self.h, out.data_ptr()))
+        self._out()
+        return out
+
+    def make_dual_feasible(self, d: torch.Tensor):
+        check(self.lib.bddb200_make_dual_feasible(self.h, self._in(d, self.nr_layers()).data_ptr()))
+        self._out()
+
+    def gradient_step(self, g: torch.Tensor, step_size: float):
+        check(self.lib.bddb200_gradient_step(self.h, self._in(g, self.nr_layers()).data_ptr(), step_size))
+
+    # ------------------------------------------------------------------ plumbing -------
+    def synchronize(self):
+        check(self.lib.bddb200_synchronize(self.h))
+
+    def kernel_launches(self) -> int:
+        return self.lib.bddb200_kernel_launches(self.h)
+
+
+def run_solver(s, max_iter: int = 1000, tolerance: float = 1e-6, improvement_slope: float = 1e-9,
+               time_limit: float = 3600.0, verbose: bool = False, log=print):
+    """include/run_solver_util.h:10-77: iterate until one of the four stop rules fires.
+    Returns the list of (iteration, lower bound, seconds)."""
+    start = time.monotonic()
+    lb_initial = s.lower_bound()
+    lb_first_iter = float("inf")
+    lb_prev = lb_post = lb_initial
+    trace = [(-1, lb_initial, 0.0)]
+    if verbose:
+        log(f"[bdd solver] initial lower bound = {lb_prev}, time = 0 s")
+    for it in range(max_iter):
+        s.iteration()
+        lb_prev = lb_post
+        lb_post = s.lower_bound()
+        if it == 0:
+            lb_first_iter = lb_post
+        spent = time.monotonic() - start
+        trace.append((it, lb_post, spent))
+        if verbose:
+            log(f"[bdd solver] iteration {it}, lower bound = {lb_post}, time = {spent:.3f} s")
+        if spent > time_limit:
+            break
+        if abs(lb_prev - lb_post) < abs(tolerance * lb_prev):
+            break
+        if abs(lb_prev - lb_post) < improvement_slope * abs(lb_initial - lb_first_iter):
+            break
+        if lb_post == float("inf"):
+            break
+    return trace

@@ -1,0 +1,177 @@
+/* include/bdd_b200.h -- C ABI of libbdd_b200.so, the B200-native (sm_100a) deferred
+ * min-marginal-averaging sweep.
+ *
+ * Drop-in boundary.  The reference has no FFI for this path: callers use the C++ class
+ * LPMP::bdd_cuda_parallel_mma<REAL> (include/bdd_solver/bdd_cuda_parallel_mma.h:7-52) and
+ * its base LPMP::bdd_cuda_base<REAL> (include/bdd_solver/bdd_cuda_base.h:57-226) by duck
+ * typing.  Every entry point below is what a method of those two classes binds to; the
+ * header-only shim bdd_b200/csrc/host/bdd_cuda_parallel_mma.h re-creates the class on top
+ * of this ABI, and bdd_b200/solver.py is the ctypes mirror.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only.  `*_host` arguments are host memory, `*_dev` arguments
+ *    are device memory on the solver's device; `void*` REAL buffers hold float when the
+ *    solver was created with BDDB200_FLOAT and double with BDDB200_DOUBLE.
+ *  - Every function returns a bddb200_status; BDDB200_OK == 0.  The reference signals
+ *    construction / configuration errors with std::runtime_error
+ *    (SURVEY 8b "Error convention"); the C++ shim maps non-zero codes to that exception
+ *    with bddb200_last_error() as message.
+ *  - Not thread safe per solver (same as the reference, which runs on one host thread and
+ *    the default stream, include/cuda_utils.h:111-114).  All work of one solver is issued
+ *    on one CUDA stream (bddb200_options.stream, default: a private non-blocking stream).
+ *  - "Layer order" of every per-layer vector (length bddb200_nr_layers): BDD-major -- the
+ *    layers of BDD 0 in BDD order followed by its terminal layer, then BDD 1, ...  The
+ *    terminal layer entries carry primal index INT_MAX, solution 0 and are left untouched
+ *    by cost functions, as in the reference (bdd_cuda_base.cu:124, 1198, 1270-1271).
+ *    (The reference's own order is its hop-sorted one, bdd_cuda_base.cu:146-188; callers
+ *    only rely on all per-layer vectors of one solver sharing one order.)
+ *  - delta vectors: 2 * nr_variables REALs, delta[2v] = lo, delta[2v+1] = hi
+ *    (delta_lo_hi_, include/bdd_solver/bdd_cuda_base.h:201).
+ */
+#ifndef BDD_B200_H
+#define BDD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bddb200_solver bddb200_solver;
+
+/* Memory layout of BDD::bdd_instruction (include/bdd_collection/bdd_collection.h:14-17):
+ * lo / hi are absolute indices into the instruction array; index is the variable, or
+ * SIZE_MAX for the top sink and SIZE_MAX-1 for the bot sink (:19-24).  The last two
+ * instructions of every BDD are its two sinks, in either order (bdd_collection.cpp:403-428,
+ * :1581-1586); a sink is recognised by the index field of the instruction an arc points to. */
+typedef struct bddb200_instruction {
+    size_t lo;
+    size_t hi;
+    size_t index;
+} bddb200_instruction;
+
+typedef enum bddb200_status {
+    BDDB200_OK = 0,
+    BDDB200_ERR_INVALID_ARGUMENT = 1,
+    BDDB200_ERR_CUDA = 2,
+    BDDB200_ERR_NOT_QBDD = 3,       /* reference: assert(is_qbdd), bdd_cuda_base.cu:100-101 */
+    BDDB200_ERR_TOO_WIDE = 4,       /* a BDD layer does not fit the shared-memory frontier  */
+    BDDB200_ERR_STATE = 5,          /* e.g. backward_mm without a valid forward state (reference: assert, bdd_cuda_parallel_mma.cu:304) */
+    BDDB200_ERR_NO_DEVICE = 6
+} bddb200_status;
+
+typedef enum bddb200_precision { BDDB200_FLOAT = 0, BDDB200_DOUBLE = 1 } bddb200_precision;
+
+typedef struct bddb200_options {
+    int device;                     /* CUDA device ordinal (reference: always 0)                      */
+    void* stream;                   /* cudaStream_t to run on; NULL = private non-blocking stream     */
+    int deterministic;              /* 1: per-variable sums in fixed BDD order (bit-reproducible, and  *
+                                     *    bit-identical to the single-threaded CPU solver in double);  *
+                                     * 0: atomic accumulation like bdd_cuda_parallel_mma.cu:358-393     */
+    int lanes_per_bdd;              /* 0 = choose from the BDD widths; else force 1,2,4,8,16 or 32     */
+    size_t nr_variables;            /* 0 = max variable + 1 (bdd_cuda_base.cu:59-64); larger when this  *
+                                     * solver holds one shard of a bigger problem                       */
+    const int32_t* nr_bdds_per_var_host; /* NULL = counted from this collection; else global counts of *
+                                     * length nr_variables (shard mode, cf. the hybrid solver's         *
+                                     * bdd_multi_parallel_mma_base.cu:191-215)                          */
+} bddb200_options;
+
+void bddb200_default_options(bddb200_options* opts);
+const char* bddb200_last_error(void);
+const char* bddb200_version(void);
+
+/* ---- construction: bdd_cuda_parallel_mma(const bdd_collection&[, costs]) --------------
+ * (bdd_cuda_parallel_mma.cu:7-27 on top of bdd_cuda_base.cu:31-53).  costs_hi_host may be
+ * NULL (n_costs = 0).  opts may be NULL. */
+int bddb200_create(const bddb200_instruction* instrs_host, size_t n_instr,
+                   const size_t* delimiters_host, size_t n_bdds,
+                   const double* costs_hi_host, size_t n_costs,
+                   int precision, const bddb200_options* opts, bddb200_solver** out);
+void bddb200_destroy(bddb200_solver* s);
+
+/* ---- sizes (bdd_cuda_base.h:101-117) -------------------------------------------------- */
+size_t bddb200_nr_variables(const bddb200_solver* s);
+size_t bddb200_nr_bdds(const bddb200_solver* s);
+size_t bddb200_nr_layers(const bddb200_solver* s);        /* incl. one terminal layer per BDD */
+size_t bddb200_nr_bdd_nodes(const bddb200_solver* s);     /* incl. both terminals per BDD      */
+size_t bddb200_nr_hops(const bddb200_solver* s);          /* length of the longest BDD         */
+int bddb200_precision_of(const bddb200_solver* s);
+int bddb200_device_of(const bddb200_solver* s);
+int bddb200_nr_bdds_per_var(const bddb200_solver* s, int32_t* out_host);   /* nr_bdds(var), get_num_bdds_per_var */
+int bddb200_layer_primal_indices(const bddb200_solver* s, int32_t* out_host); /* get_primal_variable_index: INT_MAX on terminal layers */
+int bddb200_layer_bdd_indices(const bddb200_solver* s, int32_t* out_host);    /* get_bdd_index */
+
+/* ---- the hot path ---------------------------------------------------------------------
+ * iteration(omega): forward_mm, normalize, backward_mm, normalize
+ * (bdd_cuda_parallel_mma.cu:142-153) on the solver's own delta vector. */
+int bddb200_iteration(bddb200_solver* s, double omega);
+/* n back-to-back iterations captured once in a CUDA graph and replayed. */
+int bddb200_iterations(bddb200_solver* s, double omega, size_t n);
+/* The two halves of iteration() on the solver's own (rotating, un-normalised) delta sums;
+ * a multi-GPU driver all-reduces bddb200_delta_sum_buffer() between them. */
+int bddb200_forward_pass(bddb200_solver* s, double omega);
+int bddb200_backward_pass(bddb200_solver* s, double omega);
+/* forward_mm / backward_mm(omega, delta) (bdd_cuda_parallel_mma.cu:207-257, 301-346):
+ * delta_dev is read as the values to add to the arc costs and overwritten with the newly
+ * collected, NOT yet normalised, per-variable min-marginal differences. */
+int bddb200_forward_mm(bddb200_solver* s, double omega, void* delta_dev);
+int bddb200_backward_mm(bddb200_solver* s, double omega, void* delta_dev);
+/* normalize_delta (bdd_cuda_parallel_mma.cu:421-430): delta[i] /= nr_bdds(i/2). */
+int bddb200_normalize_delta(const bddb200_solver* s, void* delta_dev);
+/* the solver's own delta vector after iteration() (normalised), copied out */
+int bddb200_get_delta(bddb200_solver* s, void* out_dev_or_host, int out_is_host);
+/* lower_bound() (bdd_cuda_base.cu:1243-1251): runs a plain backward pass if needed. */
+int bddb200_lower_bound(bddb200_solver* s, double* out_host);
+int bddb200_lower_bound_per_bdd(bddb200_solver* s, void* out_dev);   /* :1253-1259 */
+
+/* ---- plain shortest-path runs (bdd_cuda_base.cu:588-612, 670-713) -------------------- */
+int bddb200_forward_run(bddb200_solver* s);
+int bddb200_backward_run(bddb200_solver* s);
+void bddb200_flush_forward_states(bddb200_solver* s);   /* bdd_cuda_base.cu:393-403 */
+void bddb200_flush_backward_states(bddb200_solver* s);
+
+/* ---- costs ----------------------------------------------------------------------------
+ * update_costs (bdd_cuda_base.cu:476-558): cost[layer] += c[var] / nr_bdds(var). */
+int bddb200_update_costs_host(bddb200_solver* s, const double* lo_host, size_t n_lo, const double* hi_host, size_t n_hi);
+int bddb200_update_costs_dev(bddb200_solver* s, const void* lo_dev, size_t n_lo, const void* hi_dev, size_t n_hi);
+int bddb200_set_cost(bddb200_solver* s, double c, size_t var);      /* :439-452 */
+/* distribute_delta (bdd_cuda_base.cu:1396-1436) */
+int bddb200_distribute_delta(bddb200_solver* s);
+/* get/set_solver_costs (bdd_cuda_base.cu:1308-1344): three per-layer vectors, layer order */
+int bddb200_get_solver_costs(const bddb200_solver* s, void* lo_dev, void* hi_dev, void* mm_diff_dev);
+int bddb200_set_solver_costs(bddb200_solver* s, const void* lo_dev, const void* hi_dev, const void* mm_diff_dev);
+/* get_primal_objective_vector_host (bdd_cuda_base.cu:1352-1373): sum over layers of hi - lo */
+int bddb200_primal_objective_host(bddb200_solver* s, double* out_host);
+
+/* ---- min-marginals (bdd_cuda_base.cu:716-751) -----------------------------------------
+ * sorted = 1: entries ordered by (variable, BDD index), the nr_bdds terminal entries last,
+ * as min_marginals_cuda(true); sorted = 0: layer order.  All outputs have nr_layers entries
+ * and may be NULL. */
+int bddb200_min_marginals(bddb200_solver* s, int sorted, int32_t* primal_index_dev, void* mm_lo_dev, void* mm_hi_dev);
+
+/* ---- L-BFGS support surface (include/bdd_solver/lbfgs.h:22-27) -------------------------- */
+int bddb200_bdds_solution(bddb200_solver* s, char* sol_dev);                 /* bdds_solution_vec, bdd_cuda_base.cu:1137-1202 */
+int bddb200_net_solver_costs(const bddb200_solver* s, void* out_dev);         /* bdd_cuda_parallel_mma.cu:449-463 */
+int bddb200_make_dual_feasible(const bddb200_solver* s, void* inout_dev);     /* bdd_cuda_base.cu:1277-1303 */
+int bddb200_gradient_step(bddb200_solver* s, const void* dir_dev, double step); /* bdd_cuda_parallel_mma.h:62-77 */
+
+/* ---- stream plumbing / diagnostics ------------------------------------------------------ */
+int bddb200_synchronize(bddb200_solver* s);
+void* bddb200_stream(bddb200_solver* s);
+/* number of kernels of this library launched by this solver so far (bench.py's gpu_launches) */
+size_t bddb200_kernel_launches(const bddb200_solver* s);
+/* device buffers of the solver's own delta sums, for multi-GPU exchange: *sum_dev receives the
+ * buffer holding the UN-normalised sums written by the last pass (2 * nr_variables REALs). */
+int bddb200_delta_sum_buffer(bddb200_solver* s, void** sum_dev);
+
+/* Layout statistics computed on the host only (no GPU needed): fills up to n of
+ * {slots, layer entries, bundles, real nodes, max hops, max tile slots, nr classes}. */
+int bddb200_layout_stats(const bddb200_instruction* instrs_host, size_t n_instr,
+                         const size_t* delimiters_host, size_t n_bdds, int lanes_per_bdd,
+                         uint64_t* out, size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BDD_B200_H */

