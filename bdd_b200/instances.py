@@ -55,6 +55,15 @@ class BddCollection:
     def select(self, bdd_ids: Sequence[int]) -> "BddCollection":
         """Sub-collection with the given BDDs (what bdd_collection::remove leaves behind,
         bdd_collection.h:370-419); used to shard by constraint."""
+        ids = np.asarray(bdd_ids, dtype=np.int64)
+        if ids.size > 0 and np.array_equal(ids, np.arange(ids[0], ids[0] + ids.size)):
+            # contiguous block: one slice, one shift
+            first, last = int(self.delims[ids[0]]), int(self.delims[ids[-1] + 1])
+            blk = self.instrs[first:last].copy()
+            inner = blk[:, 2] < BOTSINK
+            blk[inner, 0] -= np.uint64(first)
+            blk[inner, 1] -= np.uint64(first)
+            return BddCollection(blk, self.delims[ids[0]: ids[-1] + 2] - np.uint64(first))
         parts = []
         delims = [0]
         for b in bdd_ids:

@@ -84,6 +84,12 @@ class Oracle:
     def nr_bdds_of_var(self, v: int) -> int:
         return self._fn("oracle_nr_bdds_of_var", C.c_size_t, [C.c_void_p, C.c_size_t])(self.h, v)
 
+    def set_shard(self, n_vars: int, counts: np.ndarray):
+        counts = np.ascontiguousarray(counts, dtype=np.uint64)
+        assert counts.shape[0] == n_vars
+        self._fn("oracle_set_shard", None, [C.c_void_p, C.c_size_t, _szp])(self.h, n_vars, counts)
+        self.n_vars = n_vars
+
     def layer_vars(self) -> np.ndarray:
         out = np.empty(self.n_layers, dtype=np.uint64)
         self._fn("oracle_layer_vars", None, [C.c_void_p, _szp])(self.h, out)

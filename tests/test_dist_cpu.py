@@ -1,0 +1,127 @@
+"""World-size-2 (and 3) gloo tests of the constraint-sharding logic (bdd_b200/dist.py) on CPU.
+The local solver is a stand-in built on the CPU oracle in shard mode (test infrastructure);
+on the GPU box the same sharded_mma class drives bdd_cuda_parallel_mma.  Mirrors
+test/test_hybrid_parallel_mma_base.cu:14-167 (split solver == whole solver, pass by pass)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class OracleLocal:
+    """forward_pass / backward_pass / delta_sum_view / lower_bound on top of the oracle."""
+
+    def __init__(self, col, costs, nr_vars, counts, precision):
+        import bindings as B
+        self.o = B.Oracle(col.instrs, col.delims, None, precision)
+        self.o.set_shard(nr_vars, counts)
+        self.o.update_costs(None, costs)
+        self.counts = np.maximum(counts, 1).astype(self.o.dtype)
+        self.sums = torch.zeros(2 * nr_vars, dtype=torch.float64 if precision == "double" else torch.float32)
+
+    def _normalized(self):
+        d = self.sums.numpy().copy()
+        d[0::2] /= self.counts
+        d[1::2] /= self.counts
+        return d
+
+    def forward_pass(self, omega):
+        d = self._normalized()
+        self.o.forward_mm(omega, d)
+        self.sums.copy_(torch.from_numpy(d))
+
+    def backward_pass(self, omega):
+        d = self._normalized()
+        self.o.backward_mm(omega, d)
+        self.sums.copy_(torch.from_numpy(d))
+
+    def delta_sum_view(self):
+        return self.sums
+
+    def lower_bound(self):
+        return self.o.lower_bound()
+
+
+def _worker(rank, world, port, gen, q):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import bindings as B
+    from bdd_b200 import instances
+    from bdd_b200.dist import sharded_mma
+    B.oracle_set_num_threads(1)
+    col, costs = {"cover": lambda: instances.set_cover(m=200, n=300, k=7, seed=2),
+                  "mrf": lambda: instances.grid_mrf(5, 4, 3, seed=1)}[gen]()
+    s = sharded_mma(col, costs, rank, world, lambda c, cs, nv, cnt: OracleLocal(c, cs, nv, cnt, "double"))
+    lbs = [s.lower_bound()]
+    for _ in range(12):
+        s.iteration()
+        lbs.append(s.lower_bound())
+    if rank == 0:
+        q.put((lbs, s.local.sums.numpy().copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("gen", ["cover", "mrf"])
+def test_sharded_equals_single(gen, world):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import bindings as B
+    from bdd_b200 import instances
+    col, costs = {"cover": lambda: instances.set_cover(m=200, n=300, k=7, seed=2),
+                  "mrf": lambda: instances.grid_mrf(5, 4, 3, seed=1)}[gen]()
+    B.oracle_set_num_threads(1)
+    o = B.Oracle(col.instrs, col.delims, costs, "double")
+    want = [o.lower_bound()]
+    for _ in range(12):
+        o.iteration()
+        want.append(o.lower_bound())
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, gen, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    lbs, sums = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert np.allclose(lbs, want, rtol=0, atol=1e-9)
+    # the all-reduced sums, normalised, equal the single solver's delta vector
+    from bdd_b200.dist import global_nr_bdds_per_var
+    cnt = np.maximum(global_nr_bdds_per_var(col), 1)
+    d = sums.copy(); d[0::2] /= cnt; d[1::2] /= cnt
+    assert np.allclose(d, o.get_delta(), rtol=0, atol=1e-9)
+
+
+def test_partition_and_counts():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import bindings as B
+    from bdd_b200 import instances
+    from bdd_b200.dist import global_nr_bdds_per_var, partition_bdds
+    col, costs = instances.random_inequalities(90, 50, seed=4)
+    parts = partition_bdds(col, 4)
+    assert np.array_equal(np.concatenate(parts), np.arange(col.nr_bdds))
+    sizes = [int(np.diff(col.delims.astype(np.int64))[p].sum()) for p in parts]
+    assert max(sizes) - min(sizes) <= 2 * int(np.diff(col.delims.astype(np.int64)).max())
+    o = B.Oracle(col.instrs, col.delims, costs, "double")
+    cnt = global_nr_bdds_per_var(col)
+    assert np.array_equal(cnt, [o.nr_bdds_of_var(v) for v in range(o.n_vars)])
+    # shards see the same structure as select() of the reference's remove()
+    sub = col.select(parts[1])
+    so = B.Oracle(sub.instrs, sub.delims, None, "double")
+    assert so.n_bdds == len(parts[1])
