@@ -38,6 +38,9 @@ class Options(C.Structure):
         ("lanes_per_bdd", C.c_int),
         ("nr_variables", C.c_size_t),
         ("nr_bdds_per_var_host", C.c_void_p),
+        ("stage_bytes", C.c_int),
+        ("n_stages", C.c_int),
+        ("warps_per_cta", C.c_int),
     ]
 
 

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <limits>
 #include <cstring>
 #include <memory>
@@ -114,11 +115,23 @@ public:
         if(opt.stream) { stream_ = (cudaStream_t)opt.stream; own_stream_ = false; }
         else { CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking)); own_stream_ = true; }
 
-        HostLayout L = build_layout(instrs, n_instr, delims, n_bdds, opt.lanes_per_bdd, opt.nr_variables);
+        size_t stage_budget = opt.stage_bytes ? (size_t)opt.stage_bytes : DEFAULT_STAGE_BUDGET;
+        if(const char* e = std::getenv("BDDB200_STAGE_BYTES")) stage_budget = (size_t)std::atol(e);
+        n_stages_ = opt.n_stages ? (unsigned)opt.n_stages : 3u;
+        if(const char* e = std::getenv("BDDB200_STAGES")) n_stages_ = (unsigned)std::atoi(e);
+        if(n_stages_ < 2 || n_stages_ > 8) throw api_error(BDDB200_ERR_INVALID_ARGUMENT, "n_stages must be in [2, 8]");
+        if(stage_budget < 1024 || stage_budget > 96 * 1024) throw api_error(BDDB200_ERR_INVALID_ARGUMENT, "stage_bytes must be in [1 KiB, 96 KiB]");
+        forced_wpc_ = opt.warps_per_cta > 0 ? (unsigned)opt.warps_per_cta : 0u;
+        if(const char* e = std::getenv("BDDB200_WARPS_PER_CTA")) forced_wpc_ = (unsigned)std::atoi(e);
+        if(forced_wpc_ > 16) throw api_error(BDDB200_ERR_INVALID_ARGUMENT, "warps_per_cta must be <= 16");
+
+        HostLayout L = build_layout(instrs, n_instr, delims, n_bdds, opt.lanes_per_bdd, opt.nr_variables, sizeof(REAL), stage_budget);
         n_vars_ = L.n_vars; n_bdds_ = L.n_bdds; n_instr_ = delims[n_bdds] - delims[0];
         n_ext_ = L.n_layers_ext; n_slots_ = L.n_slots; n_lay_ = L.n_lay; max_hops_ = L.max_hops;
         n_bundles_ = L.bundles.size(); n_small_ = L.n_small_bundles;
         tile_small_ = std::max<uint32_t>(L.max_tile_small, 32u); tile_large_ = L.max_tile_large;
+        stage_small_ = (uint32_t)((std::max<size_t>(L.stage_small, 128) + 127) & ~(size_t)127);
+        stage_large_ = (uint32_t)((L.stage_large + 127) & ~(size_t)127);
 
         h_nr_bdds_per_var_ = L.nr_bdds_per_var;
         if(opt.nr_bdds_per_var_host != nullptr)
@@ -133,13 +146,9 @@ public:
         }
         h_ext_var_ = L.ext_var; h_ext_bdd_ = L.ext_bdd;
 
-        // shared memory budget of the large class (one warp per CTA)
-        int max_optin = 0;
-        CUDA_CHECK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-        if((size_t)tile_large_ * 3 * sizeof(REAL) > (size_t)max_optin)
-            throw api_error(BDDB200_ERR_TOO_WIDE, "widest BDD layer needs " + std::to_string((size_t)tile_large_ * 3 * sizeof(REAL)) +
-                            " bytes of shared memory per warp (limit " + std::to_string(max_optin) + "); split the BDD (split_qbdd)");
+        CUDA_CHECK(cudaDeviceGetAttribute(&max_optin_, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
         CUDA_CHECK(cudaDeviceGetAttribute(&n_sms_, cudaDevAttrMultiProcessorCount, device));
+        plan_launch();
 
         std::vector<int2> lay_vn(L.n_lay);
         for(size_t i = 0; i < L.n_lay; ++i)
@@ -156,6 +165,7 @@ public:
             }
 
         d_bundles_.upload(L.bundles, stream_);
+        d_chunks_.upload(L.chunks, stream_);
         d_hops_.upload(L.hops, stream_);
         d_topo_.upload(L.topo, stream_);
         d_lay_vn_.upload(lay_vn, stream_);
@@ -171,7 +181,7 @@ public:
         d_nr_bdds_.upload(h_nr_bdds_per_var_, stream_);
 
         d_cfr_.alloc(n_slots_); d_cft_.alloc(n_slots_);
-        for(int i = 0; i < 2; ++i) { d_lo_[i].alloc(n_lay_); d_hi_[i].alloc(n_lay_); d_lo_[i].zero(stream_); d_hi_[i].zero(stream_); }
+        for(int i = 0; i < 2; ++i) { d_lohi_[i].alloc(2 * n_lay_); d_lohi_[i].zero(stream_); }
         d_mmd_.alloc(n_lay_); d_mmd_.zero(stream_);
         d_mm_lo_.alloc(n_lay_); d_mm_hi_.alloc(n_lay_);
         for(int i = 0; i < 3; ++i) { d_delta_[i].alloc(2 * n_vars_); d_delta_[i].zero(stream_); }
@@ -209,30 +219,57 @@ public:
     void launch_sweep(SweepArgs<REAL> a)
     {
         auto kern = sweep_kernel<REAL, MODE, FORWARD>;
-        constexpr int NBUF = FORWARD ? 3 : 2;
         if(n_small_ > 0)
         {
             a.bundle_first = 0; a.bundle_count = (uint32_t)n_small_; a.tile_slots = tile_small_;
-            const size_t smem = (size_t)warps_per_cta_ * NBUF * tile_small_ * sizeof(REAL);
-            kern<<<blocks_for(n_small_, warps_per_cta_), warps_per_cta_ * 32, smem, stream_>>>(a);
+            a.stage_bytes = stage_small_; a.n_stages = n_stages_; a.warp_smem_bytes = warp_smem_small_;
+            kern<<<blocks_for(n_small_, warps_per_cta_), warps_per_cta_ * 32, (size_t)warps_per_cta_ * warp_smem_small_, stream_>>>(a);
             ++launches_;
         }
         if(n_bundles_ > n_small_)
         {
             a.bundle_first = (uint32_t)n_small_; a.bundle_count = (uint32_t)(n_bundles_ - n_small_); a.tile_slots = tile_large_;
+            a.stage_bytes = stage_large_; a.n_stages = n_stages_large_; a.warp_smem_bytes = warp_smem_large_;
             if(n_small_ > 0) a.zero_buf = nullptr;
-            const size_t smem = (size_t)NBUF * tile_large_ * sizeof(REAL);
-            kern<<<(unsigned)(n_bundles_ - n_small_), 32, smem, stream_>>>(a);
+            kern<<<(unsigned)(n_bundles_ - n_small_), 32, warp_smem_large_, stream_>>>(a);
             ++launches_;
         }
         CUDA_CHECK(cudaGetLastError());
     }
 
+    // Shared memory of one warp: n_stages pipeline stages, two frontier buffers, the mbarriers.
+    static uint32_t warp_smem(uint32_t n_stages, uint32_t stage_bytes, uint32_t tile_slots)
+    {
+        return (uint32_t)((((size_t)n_stages * stage_bytes + 2 * (size_t)tile_slots * sizeof(REAL) + 8 * (size_t)n_stages) + 127) & ~(size_t)127);
+    }
+
+    // Choose warps per CTA for the small class (bundles that fit the stage budget) and the
+    // pipeline depth of the large class (one warp per CTA).
+    void plan_launch()
+    {
+        const size_t budget = (size_t)max_optin_;
+        warp_smem_small_ = warp_smem(n_stages_, stage_small_, tile_small_);
+        if(n_small_ > 0 && warp_smem_small_ > budget)
+            throw api_error(BDDB200_ERR_TOO_WIDE, "stage_bytes * n_stages does not fit the shared memory of one SM");
+        const unsigned max_wps = (unsigned)std::max<size_t>(1, std::min<size_t>(16, budget / std::max<uint32_t>(warp_smem_small_, 1u)));
+        if(forced_wpc_) warps_per_cta_ = std::min(forced_wpc_, max_wps);
+        else if(n_small_ <= (size_t)n_sms_ * max_wps)
+            warps_per_cta_ = (unsigned)std::max<size_t>(1, (n_small_ + n_sms_ - 1) / n_sms_);   // less than one wave: one CTA per SM
+        else warps_per_cta_ = std::min(4u, max_wps);
+        if(n_bundles_ > n_small_)
+        {
+            n_stages_large_ = n_stages_;
+            while(n_stages_large_ > 2 && warp_smem(n_stages_large_, stage_large_, tile_large_) > budget) --n_stages_large_;
+            warp_smem_large_ = warp_smem(n_stages_large_, stage_large_, tile_large_);
+            if(warp_smem_large_ > budget)
+                throw api_error(BDDB200_ERR_TOO_WIDE, "widest BDD layer needs " + std::to_string(warp_smem_large_) +
+                                " bytes of shared memory per warp (limit " + std::to_string(budget) + "); split the BDD (split_qbdd)");
+        }
+    }
+
     void configure_kernels()
     {
-        const size_t large = (size_t)3 * tile_large_ * sizeof(REAL);
-        const size_t small = (size_t)warps_per_cta_ * 3 * tile_small_ * sizeof(REAL);
-        const int need = (int)std::max(large, small);
+        const int need = (int)std::max<size_t>((size_t)warps_per_cta_ * warp_smem_small_, warp_smem_large_);
         if(need > 48 * 1024)
         {
             CUDA_CHECK(cudaFuncSetAttribute(sweep_kernel<REAL, MODE_MMA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
@@ -246,9 +283,10 @@ public:
     SweepArgs<REAL> base_args() const
     {
         SweepArgs<REAL> a{};
-        a.bundles = d_bundles_.p; a.hops = d_hops_.p; a.topo = d_topo_.p; a.lay_vn = d_lay_vn_.p; a.bundle_bdd = d_bundle_bdd_.p;
+        using R2 = typename real2<REAL>::type;
+        a.bundles = d_bundles_.p; a.chunks = d_chunks_.p; a.topo = d_topo_.p; a.lay_vn = d_lay_vn_.p; a.bundle_bdd = d_bundle_bdd_.p;
         a.cfr = d_cfr_.p; a.cft = d_cft_.p;
-        a.lo_in = d_lo_[cc_].p; a.hi_in = d_hi_[cc_].p; a.lo_out = d_lo_[cc_ ^ 1].p; a.hi_out = d_hi_[cc_ ^ 1].p;
+        a.lohi_in = reinterpret_cast<const R2*>(d_lohi_[cc_].p); a.lohi_out = reinterpret_cast<R2*>(d_lohi_[cc_ ^ 1].p);
         a.mmd = d_mmd_.p; a.mm_lo_out = d_mm_lo_.p; a.mm_hi_out = d_mm_hi_.p; a.bdd_lb = d_bdd_lb_.p;
         a.omega = 0; a.n_zero = (uint32_t)(2 * n_vars_);
         return a;
@@ -454,8 +492,8 @@ public:
             CUDA_CHECK(cudaGetLastError());
             CUDA_CHECK(cudaStreamSynchronize(stream_));
         };
-        up(lo, n_lo, d_lo_[cc_].p);
-        up(hi, n_hi, d_hi_[cc_].p);
+        up(lo, n_lo, d_lohi_[cc_].p);
+        up(hi, n_hi, d_lohi_[cc_].p + 1);
         flush_forward(); flush_backward();
     }
     void update_costs_dev(const void* lo, size_t n_lo, const void* hi, size_t n_hi) override
@@ -463,8 +501,8 @@ public:
         set_device();
         if((n_lo != 0 && n_lo != n_vars_) || (n_hi != 0 && n_hi != n_vars_))
             throw api_error(BDDB200_ERR_INVALID_ARGUMENT, "device cost vectors must have 0 or nr_variables entries");  // bdd_cuda_base.cu:537-538
-        if(n_lo) { update_costs_kernel<REAL><<<blocks_for(n_lay_), 256, 0, stream_>>>(d_lay_vn_.p, d_lo_[cc_].p, static_cast<const REAL*>(lo), (uint32_t)n_lo, (uint32_t)n_lay_); ++launches_; }
-        if(n_hi) { update_costs_kernel<REAL><<<blocks_for(n_lay_), 256, 0, stream_>>>(d_lay_vn_.p, d_hi_[cc_].p, static_cast<const REAL*>(hi), (uint32_t)n_hi, (uint32_t)n_lay_); ++launches_; }
+        if(n_lo) { update_costs_kernel<REAL><<<blocks_for(n_lay_), 256, 0, stream_>>>(d_lay_vn_.p, d_lohi_[cc_].p, static_cast<const REAL*>(lo), (uint32_t)n_lo, (uint32_t)n_lay_); ++launches_; }
+        if(n_hi) { update_costs_kernel<REAL><<<blocks_for(n_lay_), 256, 0, stream_>>>(d_lay_vn_.p, d_lohi_[cc_].p + 1, static_cast<const REAL*>(hi), (uint32_t)n_hi, (uint32_t)n_lay_); ++launches_; }
         CUDA_CHECK(cudaGetLastError());
         flush_forward(); flush_backward();
     }
@@ -473,7 +511,7 @@ public:
         set_device();
         if(var >= n_vars_ || h_nr_bdds_per_var_[var] <= 0) throw api_error(BDDB200_ERR_INVALID_ARGUMENT, "set_cost: variable not covered by any BDD");
         const REAL add = (REAL)c / h_nr_bdds_per_var_[var];
-        set_cost_kernel<REAL><<<blocks_for(n_lay_), 256, 0, stream_>>>(d_lay_vn_.p, d_hi_[cc_].p, (int)var, add, (uint32_t)n_lay_);
+        set_cost_kernel<REAL><<<blocks_for(n_lay_), 256, 0, stream_>>>(d_lay_vn_.p, d_lohi_[cc_].p + 1, (int)var, add, (uint32_t)n_lay_);
         ++launches_;
         CUDA_CHECK(cudaGetLastError());
         flush_forward(); flush_backward();
@@ -481,7 +519,7 @@ public:
     void distribute_delta() override
     {
         set_device();
-        distribute_kernel<REAL><<<blocks_for(n_lay_), 256, 0, stream_>>>(d_lay_vn_.p, d_lo_[cc_].p, d_hi_[cc_].p, d_mmd_.p, (uint32_t)n_lay_);
+        distribute_kernel<REAL><<<blocks_for(n_lay_), 256, 0, stream_>>>(d_lay_vn_.p, d_lohi_[cc_].p, d_mmd_.p, (uint32_t)n_lay_);
         ++launches_;
         CUDA_CHECK(cudaGetLastError());
         for(int i = 0; i < 3; ++i) d_delta_[i].zero(stream_);
@@ -492,18 +530,18 @@ public:
     {
         set_device();
         const unsigned nb = blocks_for(n_ext_);
-        if(lo) { gather_ext_kernel<REAL><<<nb, 256, 0, stream_>>>(d_ext2lay_.p, d_ext_var_.p, d_lo_[cc_].p, static_cast<REAL*>(lo), (REAL)0, (uint32_t)n_ext_); ++launches_; }
-        if(hi) { gather_ext_kernel<REAL><<<nb, 256, 0, stream_>>>(d_ext2lay_.p, d_ext_var_.p, d_hi_[cc_].p, static_cast<REAL*>(hi), (REAL)0, (uint32_t)n_ext_); ++launches_; }
-        if(mmd) { gather_ext_kernel<REAL><<<nb, 256, 0, stream_>>>(d_ext2lay_.p, d_ext_var_.p, d_mmd_.p, static_cast<REAL*>(mmd), (REAL)0, (uint32_t)n_ext_); ++launches_; }
+        if(lo) { gather_ext_kernel<REAL><<<nb, 256, 0, stream_>>>(d_ext2lay_.p, d_ext_var_.p, d_lohi_[cc_].p, 2u, static_cast<REAL*>(lo), (REAL)0, (uint32_t)n_ext_); ++launches_; }
+        if(hi) { gather_ext_kernel<REAL><<<nb, 256, 0, stream_>>>(d_ext2lay_.p, d_ext_var_.p, d_lohi_[cc_].p + 1, 2u, static_cast<REAL*>(hi), (REAL)0, (uint32_t)n_ext_); ++launches_; }
+        if(mmd) { gather_ext_kernel<REAL><<<nb, 256, 0, stream_>>>(d_ext2lay_.p, d_ext_var_.p, d_mmd_.p, 1u, static_cast<REAL*>(mmd), (REAL)0, (uint32_t)n_ext_); ++launches_; }
         CUDA_CHECK(cudaGetLastError());
     }
     void set_solver_costs(const void* lo, const void* hi, const void* mmd) override
     {
         set_device();
         const unsigned nb = blocks_for(n_ext_);
-        scatter_ext_kernel<REAL><<<nb, 256, 0, stream_>>>(d_ext2lay_.p, d_ext_var_.p, static_cast<const REAL*>(lo), d_lo_[cc_].p, (uint32_t)n_ext_);
-        scatter_ext_kernel<REAL><<<nb, 256, 0, stream_>>>(d_ext2lay_.p, d_ext_var_.p, static_cast<const REAL*>(hi), d_hi_[cc_].p, (uint32_t)n_ext_);
-        scatter_ext_kernel<REAL><<<nb, 256, 0, stream_>>>(d_ext2lay_.p, d_ext_var_.p, static_cast<const REAL*>(mmd), d_mmd_.p, (uint32_t)n_ext_);
+        scatter_ext_kernel<REAL><<<nb, 256, 0, stream_>>>(d_ext2lay_.p, d_ext_var_.p, static_cast<const REAL*>(lo), d_lohi_[cc_].p, 2u, (uint32_t)n_ext_);
+        scatter_ext_kernel<REAL><<<nb, 256, 0, stream_>>>(d_ext2lay_.p, d_ext_var_.p, static_cast<const REAL*>(hi), d_lohi_[cc_].p + 1, 2u, (uint32_t)n_ext_);
+        scatter_ext_kernel<REAL><<<nb, 256, 0, stream_>>>(d_ext2lay_.p, d_ext_var_.p, static_cast<const REAL*>(mmd), d_mmd_.p, 1u, (uint32_t)n_ext_);
         launches_ += 3;
         CUDA_CHECK(cudaGetLastError());
         flush_forward(); flush_backward();
@@ -512,7 +550,7 @@ public:
     {
         set_device();
         DevBuf<double> d; d.alloc(n_vars_);
-        primal_objective_kernel<REAL><<<blocks_for(n_vars_), 256, 0, stream_>>>(d_var_lay_begin_.p, d_var_lay_.p, d_lo_[cc_].p, d_hi_[cc_].p, d.p, (uint32_t)n_vars_);
+        primal_objective_kernel<REAL><<<blocks_for(n_vars_), 256, 0, stream_>>>(d_var_lay_begin_.p, d_var_lay_.p, d_lohi_[cc_].p, d.p, (uint32_t)n_vars_);
         ++launches_;
         CUDA_CHECK(cudaMemcpyAsync(out, d.p, sizeof(double) * n_vars_, cudaMemcpyDeviceToHost, stream_));
         CUDA_CHECK(cudaStreamSynchronize(stream_));
@@ -533,7 +571,7 @@ public:
         auto emit = [&](const REAL* src, void* dst) {
             if(dst == nullptr) return;
             REAL* stage = sorted ? tmp.p : static_cast<REAL*>(dst);
-            gather_ext_kernel<REAL><<<nb, 256, 0, stream_>>>(d_ext2lay_.p, d_ext_var_.p, src, stage, INF, (uint32_t)n_ext_);
+            gather_ext_kernel<REAL><<<nb, 256, 0, stream_>>>(d_ext2lay_.p, d_ext_var_.p, src, 1u, stage, INF, (uint32_t)n_ext_);
             ++launches_;
             if(sorted) { permute_kernel<REAL><<<nb, 256, 0, stream_>>>(d_sorted_ext_.p, stage, static_cast<REAL*>(dst), (uint32_t)n_ext_); ++launches_; }
         };
@@ -556,14 +594,14 @@ public:
         backward_valid_ = false;       // backward_run(true) always recomputes, bdd_cuda_base.cu:1171
         backward_run();
         bdds_solution_kernel<REAL><<<blocks_for(n_bdds_, 128), 128, 0, stream_>>>(d_bundles_.p, d_hops_.p, d_topo_.p, d_bdd_bundle_.p, d_bdd_ext_begin_.p,
-            d_cfr_.p, d_cft_.p, d_lo_[cc_].p, d_hi_[cc_].p, sol_dev, (uint32_t)n_bdds_);
+            d_cfr_.p, d_cft_.p, d_lohi_[cc_].p, sol_dev, (uint32_t)n_bdds_);
         ++launches_;
         CUDA_CHECK(cudaGetLastError());
     }
     void net_solver_costs(void* out_dev) const override
     {
         set_device();
-        net_costs_kernel<REAL><<<blocks_for(n_ext_), 256, 0, stream_>>>(d_ext2lay_.p, d_ext_var_.p, d_lo_[cc_].p, d_hi_[cc_].p, d_mmd_.p, static_cast<REAL*>(out_dev), (uint32_t)n_ext_);
+        net_costs_kernel<REAL><<<blocks_for(n_ext_), 256, 0, stream_>>>(d_ext2lay_.p, d_ext_var_.p, d_lohi_[cc_].p, d_mmd_.p, static_cast<REAL*>(out_dev), (uint32_t)n_ext_);
         ++launches_;
         CUDA_CHECK(cudaGetLastError());
     }
@@ -579,7 +617,7 @@ public:
     void gradient_step(const void* dir_dev, double step) override
     {
         set_device();
-        gradient_step_kernel<REAL><<<blocks_for(n_ext_), 256, 0, stream_>>>(d_ext2lay_.p, d_ext_var_.p, d_hi_[cc_].p, static_cast<const REAL*>(dir_dev), (REAL)step, (uint32_t)n_ext_);
+        gradient_step_kernel<REAL><<<blocks_for(n_ext_), 256, 0, stream_>>>(d_ext2lay_.p, d_ext_var_.p, d_lohi_[cc_].p, static_cast<const REAL*>(dir_dev), (REAL)step, (uint32_t)n_ext_);
         ++launches_;
         CUDA_CHECK(cudaGetLastError());
         flush_forward(); flush_backward();
@@ -596,18 +634,20 @@ private:
     cudaStream_t stream_ = nullptr;
     bool own_stream_ = false;
     bool deterministic_ = false;
-    int n_sms_ = 0;
-    unsigned warps_per_cta_ = 4;
+    int n_sms_ = 0, max_optin_ = 0;
+    unsigned warps_per_cta_ = 4, forced_wpc_ = 0, n_stages_ = 3, n_stages_large_ = 2;
+    uint32_t stage_small_ = 0, stage_large_ = 0, warp_smem_small_ = 0, warp_smem_large_ = 0;
     size_t n_vars_ = 0, n_bdds_ = 0, n_instr_ = 0, n_ext_ = 0, n_slots_ = 0, n_lay_ = 0, max_hops_ = 0, n_bundles_ = 0, n_small_ = 0;
     uint32_t tile_small_ = 32, tile_large_ = 0;
     std::vector<int32_t> h_nr_bdds_per_var_, h_ext_var_, h_ext_bdd_;
 
     DevBuf<BundleDesc> d_bundles_;
+    DevBuf<ChunkRec> d_chunks_;
     DevBuf<HopRec> d_hops_;
     DevBuf<uint32_t> d_topo_, d_bdd_bundle_, d_ext2lay_, d_bdd_ext_begin_, d_var_lay_begin_, d_var_lay_, d_sorted_ext_;
     DevBuf<int2> d_lay_vn_;
     DevBuf<int32_t> d_bundle_bdd_, d_ext_var_, d_ext_bdd_, d_nr_bdds_;
-    DevBuf<REAL> d_cfr_, d_cft_, d_lo_[2], d_hi_[2], d_mmd_, d_mm_lo_, d_mm_hi_, d_delta_[3], d_delta_tmp_, d_bdd_lb_;
+    DevBuf<REAL> d_cfr_, d_cft_, d_lohi_[2], d_mmd_, d_mm_lo_, d_mm_hi_, d_delta_[3], d_delta_tmp_, d_bdd_lb_;
     DevBuf<double> d_lb_partial_;
     double* h_lb_ = nullptr;
 
@@ -725,9 +765,10 @@ int bddb200_layout_stats(const bddb200_instruction* instrs, size_t n_instr, cons
 {
     return guarded([&] {
         const HostLayout L = build_layout(instrs, n_instr, delims, n_bdds, lanes_per_bdd);
-        const uint64_t vals[8] = {L.n_slots, L.n_lay, L.bundles.size(), L.n_real_nodes, L.max_hops,
-                                  std::max(L.max_tile_small, L.max_tile_large), L.n_small_bundles, L.n_layers_ext};
-        for(size_t i = 0; i < n && i < 8; ++i) out[i] = vals[i];
+        const uint64_t vals[11] = {L.n_slots, L.n_lay, L.bundles.size(), L.n_real_nodes, L.max_hops,
+                                   std::max(L.max_tile_small, L.max_tile_large), L.n_small_bundles, L.n_layers_ext,
+                                   L.chunks.size(), L.stage_small, L.stage_large};
+        for(size_t i = 0; i < n && i < 11; ++i) out[i] = vals[i];
     });
 }
 

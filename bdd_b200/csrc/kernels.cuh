@@ -10,14 +10,20 @@
 // global memory for every arc.
 //
 // Design: ONE launch per pass.  A warp owns a bundle of 32/P BDDs and walks it hop by hop
-// (see layout.hpp).  The chain-dependent frontier (cost_from_root going forward,
-// cost_from_terminal going backward) lives in shared memory; with P == 1 a BDD never leaves
-// its lane, so the walk needs no synchronisation at all, with P > 1 one __syncwarp per hop.
-// Per-layer min-marginals are lane-local minima followed by log2(P) xor-shuffles; the
-// cross-BDD sum of min-marginal differences is a red.global.add per layer (or, in
-// deterministic mode, a fixed-order segmented sum in delta_segsum_kernel); the division by
-// the number of BDDs per variable is folded into the read of delta_in; the buffer of the
-// pass after next is zeroed by the same launch.  Everything else is coalesced streaming.
+// (see layout.hpp).  No global load sits on the hop-to-hop dependency chain: the bundle's
+// hops are cut into chunks, and every input of a chunk (topology, the opposite direction's
+// DP values, {variable, nr_bdds}, {lo, hi} arc costs) is one contiguous range that lane 0
+// brings into a shared-memory pipeline stage with cp.async.bulk (TMA 1-D bulk copy, SASS
+// UBLKCP) completing on a per-warp mbarrier; the per-variable delta values are gathered into
+// the same stage with cp.async (LDGSTS) one chunk ahead.  The chain-dependent frontier
+// (cost_from_root going forward, cost_from_terminal going backward) lives in shared memory;
+// with P == 1 a BDD never leaves its lane, so the walk needs no synchronisation at all,
+// with P > 1 one __syncwarp per hop.  Per-layer min-marginals are lane-local minima followed
+// by log2(P) xor-shuffles; the cross-BDD sum of min-marginal differences is a
+// red.global.add per layer (or, in deterministic mode, a fixed-order segmented sum in
+// delta_segsum_kernel); the division by the number of BDDs per variable is folded into the
+// read of delta_in; the buffer of the pass after next is zeroed by the same launch.
+// Outputs are coalesced streaming stores.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -54,19 +60,66 @@ __device__ __forceinline__ void smem_atomic_min(double* addr, double v)
     else atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
 }
 
+// ---- async-copy plumbing (PTX) ---------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// try_wait suspends the thread in hardware for a bounded time per call; a copy that never
+// completes (a size/alignment bug) traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    for(uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
+        if(spins > (1u << 22)) __trap();
+}
+// 1-D bulk copy global -> shared (TMA engine), completion counted in bytes on `bar`.
+// dst, src and bytes must be multiples of 16.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+template<int BYTES>
+__device__ __forceinline__ void cp_async_gather(void* dst, const void* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" :: "r"(smem_u32(dst)), "l"(__cvta_generic_to_global(src)), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template<int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
 template<typename REAL>
 struct SweepArgs {
     const BundleDesc* bundles;
-    const HopRec* hops;
+    const ChunkRec* chunks;
     const uint32_t* topo;
     const int2* lay_vn;        // per layer entry {variable or -1, nr_bdds(variable)}
     const int32_t* bundle_bdd;
     REAL* cfr;                 // cost from root, per slot
     REAL* cft;                 // cost from terminal, per slot
-    const REAL* lo_in;
-    const REAL* hi_in;
-    REAL* lo_out;
-    REAL* hi_out;
+    const typename real2<REAL>::type* lohi_in;   // per layer entry {lo, hi} arc cost
+    typename real2<REAL>::type* lohi_out;
     REAL* mmd;                 // deferred min-marginal difference per layer entry
     const REAL* delta_in;      // 2V
     REAL* delta_out;           // 2V (zeroed before the launch or by the previous pass)
@@ -78,6 +131,9 @@ struct SweepArgs {
     uint32_t n_zero;
     uint32_t bundle_first, bundle_count;
     uint32_t tile_slots;       // capacity of one shared-memory frontier buffer, in slots
+    uint32_t stage_bytes;      // capacity of one pipeline stage
+    uint32_t n_stages;         // pipeline depth (>= 2)
+    uint32_t warp_smem_bytes;  // n_stages * stage_bytes + 2 frontier buffers + mbarriers, rounded to 128
     int normalize_in;          // divide delta_in by nr_bdds(var) while reading
     int accumulate;            // add |mm_diff| to delta_out with atomics
 };
@@ -94,222 +150,315 @@ __device__ __forceinline__ REAL group_min(REAL v)
     return v;
 }
 
-// Layer record + the damped min-marginal update shared by both directions.
-//   mm_diff = omega * (mm_hi - mm_lo), 0 if either is infinite  (bdd_cuda_parallel_mma.cu:29-42)
-//   lo' = lo + min(mm_diff, 0) + delta[2v];  hi' = hi + min(-mm_diff, 0) + delta[2v+1]   (:185-193, :280-281)
-template<typename REAL>
-struct LayerState {
-    int var;
-    REAL lo_c, hi_c, d0, d1;
+// Where the pieces of one chunk live inside a pipeline stage.
+template<typename REAL, int MODE, bool FORWARD>
+struct ChunkGeom {
+    static constexpr bool NEED_DP = FORWARD ? (MODE == MODE_MMA) : (MODE != MODE_PLAIN);
+    static constexpr bool NEED_DELTA = (MODE == MODE_MMA);
+    uint32_t slot_off, lay_off, n, J, Jn, ne;
+    uint32_t topo_bytes, dp_bytes, o_dp, o_vn, o_lohi, o_delta;
+    __device__ __forceinline__ ChunkGeom(const ChunkRec& c, uint32_t bpw)
+    {
+        slot_off = c.slot_off; lay_off = c.lay_off; n = c.n_hops; J = c.J; Jn = c.J_next;
+        ne = (n * bpw + 1u) & ~1u;
+        topo_bytes = n * J * 128u;
+        const uint32_t dp_rows = FORWARD ? ((n - 1u) * J + Jn) : n * J;
+        dp_bytes = NEED_DP ? dp_rows * 32u * (uint32_t)sizeof(REAL) : 0u;
+        o_dp = topo_bytes;
+        o_vn = o_dp + dp_bytes;
+        o_lohi = o_vn + ne * 8u;
+        o_delta = o_lohi + ne * 2u * (uint32_t)sizeof(REAL);
+    }
 };
 
-template<typename REAL, int MODE>
-__device__ __forceinline__ LayerState<REAL> load_layer(const SweepArgs<REAL>& a, uint32_t lay)
+// lane l keeps the ChunkRec of pipeline position (base + l); refilled every 32 chunks
+struct ChunkCache {
+    ChunkRec mine;
+    uint32_t base;
+};
+__device__ __forceinline__ ChunkRec shfl_chunk(const ChunkRec& r, int src)
 {
-    LayerState<REAL> s;
-    const int2 vn = __ldg(a.lay_vn + lay);
-    s.var = vn.x;
-    s.lo_c = 0; s.hi_c = 0; s.d0 = 0; s.d1 = 0;
-    if(s.var >= 0)
-    {
-        s.lo_c = a.lo_in[lay];
-        s.hi_c = a.hi_in[lay];
-        if(MODE == MODE_MMA)
-        {
-            using R2 = typename real2<REAL>::type;
-            const R2 d = *reinterpret_cast<const R2*>(a.delta_in + 2 * (size_t)s.var);
-            s.d0 = d.x; s.d1 = d.y;
-            if(a.normalize_in)
-            {
-                const REAL n = (REAL)vn.y;
-                s.d0 /= n; s.d1 /= n;
-            }
-        }
-    }
-    return s;
+    ChunkRec o;
+    o.slot_off = __shfl_sync(0xffffffffu, r.slot_off, src);
+    o.lay_off = __shfl_sync(0xffffffffu, r.lay_off, src);
+    o.hop_first = 0;
+    o.n_hops = __shfl_sync(0xffffffffu, r.n_hops, src);
+    o.J = __shfl_sync(0xffffffffu, r.J, src);
+    o.J_next = __shfl_sync(0xffffffffu, r.J_next, src);
+    return o;
 }
 
-template<typename REAL>
-__device__ __forceinline__ void store_layer(const SweepArgs<REAL>& a, uint32_t lay, int var, REAL lo_n, REAL hi_n, REAL diff)
+// One pass over one bundle.
+//   forward : forward_mm (bdd_cuda_parallel_mma.cu:207-257) for MODE_MMA, forward_run
+//             (bdd_cuda_base.cu:588-612) for MODE_PLAIN.
+//   backward: backward_mm (:301-346) for MODE_MMA, backward_run(false) (bdd_cuda_base.cu:670-713)
+//             for MODE_PLAIN, backward_run(true) + the per-layer min reduction of
+//             min_marginals_cuda (:716-736) for MODE_MM.
+// Layer update shared by both directions:
+//   mm_diff = omega * (mm_hi - mm_lo), 0 if either is infinite  (bdd_cuda_parallel_mma.cu:29-42)
+//   lo' = lo + min(mm_diff, 0) + delta[2v];  hi' = hi + min(-mm_diff, 0) + delta[2v+1]   (:185-193, :280-281)
+template<typename REAL, int LOGP, int MODE, bool FORWARD>
+__device__ __forceinline__ void sweep_bundle(const SweepArgs<REAL>& a, const BundleDesc& bd, unsigned char* wsm, const int lane)
 {
-    a.lo_out[lay] = lo_n;
-    a.hi_out[lay] = hi_n;
-    a.mmd[lay] = diff;
-    if(a.accumulate)
-    {
-        // compute_delta_atomic, bdd_cuda_parallel_mma.cu:358-376
-        if(diff > 0) atomicAdd(a.delta_out + 2 * (size_t)var + 1, diff);
-        else if(diff < 0) atomicAdd(a.delta_out + 2 * (size_t)var, -diff);
-    }
-}
-
-// ------------------------------------------------------------------ forward ------------
-// forward_mm (bdd_cuda_parallel_mma.cu:207-257) for MODE_MMA, forward_run
-// (bdd_cuda_base.cu:588-612) for MODE_PLAIN.
-template<typename REAL, int LOGP, int MODE>
-__device__ __forceinline__ void sweep_forward(const SweepArgs<REAL>& a, const BundleDesc& bd, REAL* tiles, const int lane)
-{
+    using R2 = typename real2<REAL>::type;
+    using Geom = ChunkGeom<REAL, MODE, FORWARD>;
     constexpr int P = 1 << LOGP;
-    constexpr int BPW = 32 >> LOGP;
+    constexpr uint32_t BPW = 32u >> LOGP;
     const int bl = lane >> LOGP;
     const int p = lane & (P - 1);
     const REAL INF = real_inf<REAL>();
-    REAL* cur = tiles;
-    REAL* nxt = tiles + a.tile_slots;
-    REAL* spare = tiles + 2 * (size_t)a.tile_slots;
-    const HopRec* hops = a.hops + bd.hop_base;
-    const uint32_t n_hops = bd.n_hops;
+    const uint32_t NS = a.n_stages;
+    const uint32_t nc = bd.n_chunks;
 
-    HopRec h = hops[0];
-    HopRec hn = n_hops > 1 ? hops[1] : HopRec{0u, 0u};
-    for(uint32_t j = 0; j < h.J; ++j) cur[j * 32 + lane] = INF;
-    if(p == 0 && a.topo[h.node_off + lane] != TOPO_PAD) cur[lane] = 0;   // flush_costs_from_root, bdd_cuda_base.cu:1438-1445
-    for(uint32_t j = 0; j < hn.J; ++j) nxt[j * 32 + lane] = INF;
-    if(P > 1) __syncwarp();
+    unsigned char* stages = wsm;
+    REAL* cur = reinterpret_cast<REAL*>(wsm + (size_t)NS * a.stage_bytes);
+    REAL* nxt = cur + a.tile_slots;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(nxt + a.tile_slots);
 
-    for(uint32_t k = 0; k < n_hops; ++k)
+    if(lane == 0)
     {
-        const HopRec hnn = (k + 2 < n_hops) ? hops[k + 2] : HopRec{0u, 0u};
-        for(uint32_t j = 0; j < hnn.J; ++j) spare[j * 32 + lane] = INF;
+        for(uint32_t s = 0; s < NS; ++s) mbar_init(bars + s, 1);
+        mbar_fence_init();
+    }
+    if(FORWARD)
+    {   // invariant: a frontier buffer is all +inf outside the tile it currently holds
+        for(uint32_t i = lane; i < 2 * a.tile_slots; i += 32) cur[i] = INF;
+        __syncwarp();
+        if(p == 0 && a.bundle_bdd[bd.bdd_base + bl] >= 0) cur[lane] = 0;   // flush_costs_from_root, bdd_cuda_base.cu:1438-1445
+    }
+    __syncwarp();
 
-        const uint32_t lay = bd.layer_base + k * BPW + bl;
-        const LayerState<REAL> ls = load_layer<REAL, MODE>(a, lay);
-        REAL lo_n = ls.lo_c, hi_n = ls.hi_c, diff = 0;
-        if(MODE == MODE_MMA)
+    // pipeline position i (0 .. nc-1) -> chunk index
+    auto chunk_of = [&](uint32_t i) { return bd.chunk_base + (FORWARD ? i : nc - 1 - i); };
+    // lookups at loop position i only ask for positions in [i + 1, i + NS]: on a miss the
+    // window restarts at `low`, the lowest position that can still be asked for
+    ChunkCache cache;
+    cache.base = 0;
+    cache.mine = a.chunks[chunk_of(min((uint32_t)lane, nc - 1))];
+    auto get_chunk = [&](uint32_t i, uint32_t low) -> ChunkRec {
+        if(i >= cache.base + 32)
         {
-            REAL mm0 = INF, mm1 = INF;
-            for(uint32_t j = 0; j < h.J; ++j)
+            cache.base = low;
+            cache.mine = a.chunks[chunk_of(min(low + lane, nc - 1))];
+        }
+        return shfl_chunk(cache.mine, (int)(i - cache.base));
+    };
+
+    // lane 0: start the bulk copies of pipeline position i into stage i % NS
+    auto issue = [&](uint32_t i, const ChunkRec& cr) {
+        const Geom g(cr, BPW);
+        if(lane == 0)
+        {
+            unsigned char* st = stages + (size_t)(i % NS) * a.stage_bytes;
+            uint64_t* bar = bars + (i % NS);
+            const uint32_t lay_bytes8 = g.ne * 8u, lohi_bytes = g.ne * 2u * (uint32_t)sizeof(REAL);
+            mbar_arrive_expect_tx(bar, g.topo_bytes + g.dp_bytes + lay_bytes8 + lohi_bytes);
+            bulk_g2s(st, a.topo + g.slot_off, g.topo_bytes, bar);
+            if(Geom::NEED_DP && g.dp_bytes > 0)
             {
-                const uint32_t t = __ldg(a.topo + h.node_off + j * 32 + lane);
-                if(t < TOPO_TOP)
+                const REAL* src = FORWARD ? a.cft + g.slot_off + 32u * g.J : a.cfr + g.slot_off;
+                bulk_g2s(st + g.o_dp, src, g.dp_bytes, bar);
+            }
+            bulk_g2s(st + g.o_vn, a.lay_vn + g.lay_off, lay_bytes8, bar);
+            bulk_g2s(st + g.o_lohi, a.lohi_in + g.lay_off, lohi_bytes, bar);
+        }
+    };
+    // all lanes: wait for position i's bulk data, then gather its delta values
+    auto land = [&](uint32_t i, const ChunkRec& cr) {
+        mbar_wait(bars + (i % NS), (i / NS) & 1u);
+        if(Geom::NEED_DELTA)
+        {
+            const Geom g(cr, BPW);
+            unsigned char* st = stages + (size_t)(i % NS) * a.stage_bytes;
+            const int2* s_vn = reinterpret_cast<const int2*>(st + g.o_vn);
+            R2* s_delta = reinterpret_cast<R2*>(st + g.o_delta);
+            for(uint32_t e = lane; e < g.n * BPW; e += 32)
+            {
+                const int var = s_vn[e].x;
+                if(var >= 0) cp_async_gather<(int)sizeof(R2)>(s_delta + e, a.delta_in + 2 * (size_t)var);
+            }
+            cp_async_commit();
+        }
+    };
+
+    {
+        const uint32_t pre = min(NS, nc);
+        for(uint32_t i = 0; i < pre; ++i) issue(i, get_chunk(i, 0));
+    }
+    ChunkRec cr = get_chunk(0, 0);
+    land(0, cr);
+
+    for(uint32_t i = 0; i < nc; ++i)
+    {
+        ChunkRec cr_next = cr;
+        if(i + 1 < nc)
+        {
+            cr_next = get_chunk(i + 1, i + 1);
+            land(i + 1, cr_next);
+            if(Geom::NEED_DELTA) cp_async_wait<1>();
+        }
+        else if(Geom::NEED_DELTA) cp_async_wait<0>();
+        __syncwarp();
+
+        const Geom g(cr, BPW);
+        const unsigned char* st = stages + (size_t)(i % NS) * a.stage_bytes;
+        const uint32_t* s_topo = reinterpret_cast<const uint32_t*>(st);
+        const REAL* s_dp = reinterpret_cast<const REAL*>(st + g.o_dp);
+        const int2* s_vn = reinterpret_cast<const int2*>(st + g.o_vn);
+        const R2* s_lohi = reinterpret_cast<const R2*>(st + g.o_lohi);
+        const R2* s_delta = reinterpret_cast<const R2*>(st + g.o_delta);
+        const uint32_t J = g.J;
+
+        for(uint32_t hh = 0; hh < g.n; ++hh)
+        {
+            const uint32_t h = FORWARD ? hh : g.n - 1 - hh;
+            const uint32_t e = h * BPW + bl;
+            const uint32_t lay = g.lay_off + e;
+            const int2 vn = s_vn[e];
+            const int var = vn.x;
+            REAL lo_c = 0, hi_c = 0, d0 = 0, d1 = 0;
+            if(var >= 0)
+            {
+                const R2 c2 = s_lohi[e];
+                lo_c = c2.x; hi_c = c2.y;
+                if(MODE == MODE_MMA)
                 {
+                    const R2 d = s_delta[e];
+                    d0 = d.x; d1 = d.y;
+                    if(a.normalize_in)
+                    {
+                        const REAL n = (REAL)vn.y;
+                        d0 /= n; d1 /= n;
+                    }
+                }
+            }
+            const uint32_t* trow = s_topo + h * J * 32u + lane;
+            const uint32_t gslot = g.slot_off + h * J * 32u + lane;
+            REAL lo_n = lo_c, hi_n = hi_c, diff = 0;
+
+            if(FORWARD)
+            {
+                if(MODE == MODE_MMA)
+                {
+                    const REAL* child = s_dp + h * J * 32u;     // cost_from_terminal of the next hop's tile
+                    REAL mm0 = INF, mm1 = INF;
+                    for(uint32_t j = 0; j < J; ++j)
+                    {
+                        const uint32_t t = trow[j * 32];
+                        if(t < TOPO_TOP)
+                        {
+                            const REAL c = cur[j * 32 + lane];
+                            const uint32_t lo = t & 0xFFFFu, hi = t >> 16;
+                            const REAL ta = lo == CHILD_BOT ? INF : child[lo];
+                            const REAL tb = hi == CHILD_BOT ? INF : child[hi];
+                            const REAL m0 = c + lo_c + ta;     // same association as bdd_cuda_parallel_mma.cu:83-84
+                            const REAL m1 = c + hi_c + tb;
+                            mm0 = m0 < mm0 ? m0 : mm0;
+                            mm1 = m1 < mm1 ? m1 : mm1;
+                        }
+                    }
+                    mm0 = group_min<P>(mm0);
+                    mm1 = group_min<P>(mm1);
+                    if(isfinite(mm0) && isfinite(mm1)) diff = a.omega * (mm1 - mm0);
+                    lo_n = lo_c + (diff < 0 ? diff : (REAL)0) + d0;
+                    hi_n = hi_c + (-diff < 0 ? -diff : (REAL)0) + d1;
+                }
+                for(uint32_t j = 0; j < J; ++j)
+                {
+                    const uint32_t t = trow[j * 32];
                     const REAL c = cur[j * 32 + lane];
-                    const uint32_t lo = t & 0xFFFFu, hi = t >> 16;
-                    const REAL ta = lo == CHILD_BOT ? INF : a.cft[hn.node_off + lo];
-                    const REAL tb = hi == CHILD_BOT ? INF : a.cft[hn.node_off + hi];
-                    const REAL m0 = c + ls.lo_c + ta;     // same association as bdd_cuda_parallel_mma.cu:83-84
-                    const REAL m1 = c + ls.hi_c + tb;
-                    mm0 = m0 < mm0 ? m0 : mm0;
-                    mm1 = m1 < mm1 ? m1 : mm1;
+                    cur[j * 32 + lane] = INF;                    // restore the all-inf invariant
+                    a.cfr[gslot + j * 32] = c;
+                    if(t < TOPO_TOP)
+                    {
+                        const uint32_t lo = t & 0xFFFFu, hi = t >> 16;
+                        if(lo != CHILD_BOT)
+                        {
+                            const REAL v = c + lo_n;
+                            if(P == 1) { if(v < nxt[lo]) nxt[lo] = v; } else smem_atomic_min(nxt + lo, v);
+                        }
+                        if(hi != CHILD_BOT)
+                        {
+                            const REAL v = c + hi_n;
+                            if(P == 1) { if(v < nxt[hi]) nxt[hi] = v; } else smem_atomic_min(nxt + hi, v);
+                        }
+                    }
                 }
             }
-            mm0 = group_min<P>(mm0);
-            mm1 = group_min<P>(mm1);
-            if(isfinite(mm0) && isfinite(mm1)) diff = a.omega * (mm1 - mm0);
-            lo_n = ls.lo_c + (diff < 0 ? diff : (REAL)0) + ls.d0;
-            hi_n = ls.hi_c + (-diff < 0 ? -diff : (REAL)0) + ls.d1;
-        }
-        for(uint32_t j = 0; j < h.J; ++j)
-        {
-            const uint32_t s = h.node_off + j * 32 + lane;
-            const uint32_t t = __ldg(a.topo + s);
-            const REAL c = cur[j * 32 + lane];
-            a.cfr[s] = c;
-            if(t < TOPO_TOP)
+            else
             {
-                const uint32_t lo = t & 0xFFFFu, hi = t >> 16;
-                if(lo != CHILD_BOT)
+                if(MODE != MODE_PLAIN)
                 {
-                    const REAL v = c + lo_n;
-                    if(P == 1) { if(v < nxt[lo]) nxt[lo] = v; } else smem_atomic_min(nxt + lo, v);
+                    const REAL* mine = s_dp + h * J * 32u + lane;   // cost_from_root of this hop's tile
+                    REAL mm0 = INF, mm1 = INF;
+                    for(uint32_t j = 0; j < J; ++j)
+                    {
+                        const uint32_t t = trow[j * 32];
+                        if(t < TOPO_TOP)
+                        {
+                            const REAL c = mine[j * 32];
+                            const uint32_t lo = t & 0xFFFFu, hi = t >> 16;
+                            const REAL ta = lo == CHILD_BOT ? INF : nxt[lo];
+                            const REAL tb = hi == CHILD_BOT ? INF : nxt[hi];
+                            REAL m0, m1;
+                            if(MODE == MODE_MMA) { m0 = c + lo_c + ta; m1 = c + hi_c + tb; }
+                            else { m0 = c + (ta + lo_c); m1 = c + (tb + hi_c); }   // path costs, bdd_cuda_base.cu:636-641
+                            mm0 = m0 < mm0 ? m0 : mm0;
+                            mm1 = m1 < mm1 ? m1 : mm1;
+                        }
+                    }
+                    mm0 = group_min<P>(mm0);
+                    mm1 = group_min<P>(mm1);
+                    if(MODE == MODE_MMA)
+                    {
+                        if(isfinite(mm0) && isfinite(mm1)) diff = a.omega * (mm1 - mm0);
+                        lo_n = lo_c + (diff < 0 ? diff : (REAL)0) + d0;
+                        hi_n = hi_c + (-diff < 0 ? -diff : (REAL)0) + d1;
+                    }
+                    else if(p == 0 && var >= 0)
+                    {
+                        a.mm_lo_out[lay] = mm0;
+                        a.mm_hi_out[lay] = mm1;
+                    }
                 }
-                if(hi != CHILD_BOT)
+                for(uint32_t j = 0; j < J; ++j)
                 {
-                    const REAL v = c + hi_n;
-                    if(P == 1) { if(v < nxt[hi]) nxt[hi] = v; } else smem_atomic_min(nxt + hi, v);
+                    const uint32_t t = trow[j * 32];
+                    REAL val = t == TOPO_TOP ? (REAL)0 : INF;          // set_special_nodes_costs, bdd_cuda_base.cu:217-227
+                    if(t < TOPO_TOP)
+                    {
+                        const uint32_t lo = t & 0xFFFFu, hi = t >> 16;
+                        const REAL ta = lo == CHILD_BOT ? INF : nxt[lo];
+                        const REAL tb = hi == CHILD_BOT ? INF : nxt[hi];
+                        const REAL vh = hi_n + tb, vl = lo_n + ta;        // bdd_cuda_parallel_mma.cu:286
+                        val = vh < vl ? vh : vl;
+                    }
+                    cur[j * 32 + lane] = val;
+                    a.cft[gslot + j * 32] = val;
                 }
             }
-        }
-        if(MODE == MODE_MMA && p == 0 && ls.var >= 0)
-            store_layer(a, lay, ls.var, lo_n, hi_n, diff);
-        if(P > 1) __syncwarp();
-        REAL* tmp = cur; cur = nxt; nxt = spare; spare = tmp;
-        h = hn; hn = hnn;
-    }
-}
 
-// ------------------------------------------------------------------ backward -----------
-// backward_mm (bdd_cuda_parallel_mma.cu:301-346) for MODE_MMA, backward_run(false)
-// (bdd_cuda_base.cu:670-713) for MODE_PLAIN, backward_run(true) + the per-layer min
-// reduction of min_marginals_cuda (bdd_cuda_base.cu:716-736) for MODE_MM.
-template<typename REAL, int LOGP, int MODE>
-__device__ __forceinline__ void sweep_backward(const SweepArgs<REAL>& a, const BundleDesc& bd, REAL* tiles, const int lane)
-{
-    constexpr int P = 1 << LOGP;
-    constexpr int BPW = 32 >> LOGP;
-    const int bl = lane >> LOGP;
-    const int p = lane & (P - 1);
-    const REAL INF = real_inf<REAL>();
-    REAL* cur = tiles;
-    REAL* nxt = tiles + a.tile_slots;
-    const HopRec* hops = a.hops + bd.hop_base;
-    const uint32_t n_hops = bd.n_hops;
-
-    HopRec hn = HopRec{0u, 0u};
-    for(int k = (int)n_hops - 1; k >= 0; --k)
-    {
-        const HopRec h = hops[k];
-        const uint32_t lay = bd.layer_base + (uint32_t)k * BPW + bl;
-        const LayerState<REAL> ls = load_layer<REAL, MODE>(a, lay);
-        REAL lo_n = ls.lo_c, hi_n = ls.hi_c, diff = 0;
-        if(MODE != MODE_PLAIN)
-        {
-            REAL mm0 = INF, mm1 = INF;
-            for(uint32_t j = 0; j < h.J; ++j)
+            if(MODE == MODE_MMA && p == 0 && var >= 0)
             {
-                const uint32_t s = h.node_off + j * 32 + lane;
-                const uint32_t t = __ldg(a.topo + s);
-                if(t < TOPO_TOP)
-                {
-                    const REAL c = a.cfr[s];
-                    const uint32_t lo = t & 0xFFFFu, hi = t >> 16;
-                    const REAL ta = lo == CHILD_BOT ? INF : nxt[lo];
-                    const REAL tb = hi == CHILD_BOT ? INF : nxt[hi];
-                    REAL m0, m1;
-                    if(MODE == MODE_MMA) { m0 = c + ls.lo_c + ta; m1 = c + ls.hi_c + tb; }
-                    else { m0 = c + (ta + ls.lo_c); m1 = c + (tb + ls.hi_c); }   // path costs, bdd_cuda_base.cu:636-641
-                    mm0 = m0 < mm0 ? m0 : mm0;
-                    mm1 = m1 < mm1 ? m1 : mm1;
+                R2 o; o.x = lo_n; o.y = hi_n;
+                a.lohi_out[lay] = o;
+                a.mmd[lay] = diff;
+                if(a.accumulate)
+                {   // compute_delta_atomic, bdd_cuda_parallel_mma.cu:358-376
+                    if(diff > 0) atomicAdd(a.delta_out + 2 * (size_t)var + 1, diff);
+                    else if(diff < 0) atomicAdd(a.delta_out + 2 * (size_t)var, -diff);
                 }
             }
-            mm0 = group_min<P>(mm0);
-            mm1 = group_min<P>(mm1);
-            if(MODE == MODE_MMA)
-            {
-                if(isfinite(mm0) && isfinite(mm1)) diff = a.omega * (mm1 - mm0);
-                lo_n = ls.lo_c + (diff < 0 ? diff : (REAL)0) + ls.d0;
-                hi_n = ls.hi_c + (-diff < 0 ? -diff : (REAL)0) + ls.d1;
-            }
-            else if(p == 0 && ls.var >= 0)
-            {
-                a.mm_lo_out[lay] = mm0;
-                a.mm_hi_out[lay] = mm1;
-            }
+            if(P > 1) __syncwarp();
+            REAL* tmp = cur; cur = nxt; nxt = tmp;
         }
-        for(uint32_t j = 0; j < h.J; ++j)
-        {
-            const uint32_t s = h.node_off + j * 32 + lane;
-            const uint32_t t = __ldg(a.topo + s);
-            REAL val = t == TOPO_TOP ? (REAL)0 : INF;          // set_special_nodes_costs, bdd_cuda_base.cu:217-227
-            if(t < TOPO_TOP)
-            {
-                const uint32_t lo = t & 0xFFFFu, hi = t >> 16;
-                const REAL ta = lo == CHILD_BOT ? INF : nxt[lo];
-                const REAL tb = hi == CHILD_BOT ? INF : nxt[hi];
-                const REAL vh = hi_n + tb, vl = lo_n + ta;        // bdd_cuda_parallel_mma.cu:286
-                val = vh < vl ? vh : vl;
-            }
-            cur[j * 32 + lane] = val;
-            a.cft[s] = val;
-        }
-        if(MODE == MODE_MMA && p == 0 && ls.var >= 0)
-            store_layer(a, lay, ls.var, lo_n, hi_n, diff);
-        if(P > 1) __syncwarp();
-        REAL* tmp = cur; cur = nxt; nxt = tmp;
-        hn = h;
+
+        __syncwarp();                                   // every lane is done with stage i % NS
+        if(i + NS < nc) issue(i + NS, get_chunk(i + NS, i + 1));
+        cr = cr_next;
     }
-    (void)hn;
-    if(p == 0)
+
+    if(!FORWARD && p == 0)
     {
         const int32_t bi = a.bundle_bdd[bd.bdd_base + bl];
         if(bi >= 0) a.bdd_lb[bi] = nxt[lane];   // root = node 0 of hop 0
@@ -317,9 +466,9 @@ __device__ __forceinline__ void sweep_backward(const SweepArgs<REAL>& a, const B
 }
 
 template<typename REAL, int MODE, bool FORWARD>
-__global__ void __launch_bounds__(256) sweep_kernel(const SweepArgs<REAL> a)
+__global__ void __launch_bounds__(512, 1) sweep_kernel(const SweepArgs<REAL> a)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wpc = blockDim.x >> 5;
     if(MODE == MODE_MMA && a.zero_buf != nullptr)
@@ -328,12 +477,10 @@ __global__ void __launch_bounds__(256) sweep_kernel(const SweepArgs<REAL> a)
     uint32_t g = blockIdx.x * wpc + warp;
     if(g >= a.bundle_count) return;
     g += a.bundle_first;
-    constexpr int NBUF = FORWARD ? 3 : 2;
-    REAL* tiles = reinterpret_cast<REAL*>(smem_raw) + (size_t)warp * NBUF * a.tile_slots;
+    unsigned char* wsm = smem_raw + (size_t)warp * a.warp_smem_bytes;
     const BundleDesc bd = a.bundles[g];
 #define BDDB200_DISPATCH(LP) \
-    case LP: if(FORWARD) sweep_forward<REAL, LP, (MODE == MODE_MM ? MODE_PLAIN : MODE)>(a, bd, tiles, lane); \
-             else sweep_backward<REAL, LP, MODE>(a, bd, tiles, lane); break;
+    case LP: sweep_bundle<REAL, LP, (FORWARD && MODE == MODE_MM ? MODE_PLAIN : MODE), FORWARD>(a, bd, wsm, lane); break;
     switch(bd.logP)
     {
         BDDB200_DISPATCH(0) BDDB200_DISPATCH(1) BDDB200_DISPATCH(2)
@@ -342,6 +489,7 @@ __global__ void __launch_bounds__(256) sweep_kernel(const SweepArgs<REAL> a)
     }
 #undef BDDB200_DISPATCH
 }
+
 
 // ------------------------------------------------------------------ small kernels ------
 
@@ -375,14 +523,14 @@ __global__ void normalize_kernel(const REAL* __restrict__ in, REAL* __restrict__
 
 // set_vars_costs_func, bdd_cuda_base.cu:454-474
 template<typename REAL>
-__global__ void update_costs_kernel(const int2* __restrict__ lay_vn, REAL* __restrict__ cost, const REAL* __restrict__ c, uint32_t n_c, uint32_t n_lay)
+__global__ void update_costs_kernel(const int2* __restrict__ lay_vn, REAL* __restrict__ cost /* lohi + component */, const REAL* __restrict__ c, uint32_t n_c, uint32_t n_lay)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= n_lay) return;
     const int2 vn = lay_vn[i];
     if(vn.x < 0) return;
-    if((uint32_t)vn.x >= n_c) { cost[i] = 0; return; }
-    cost[i] += c[vn.x] / (REAL)vn.y;
+    if((uint32_t)vn.x >= n_c) { cost[2 * (size_t)i] = 0; return; }
+    cost[2 * (size_t)i] += c[vn.x] / (REAL)vn.y;
 }
 
 // set_var_cost_func, bdd_cuda_base.cu:425-452
@@ -390,35 +538,35 @@ template<typename REAL>
 __global__ void set_cost_kernel(const int2* __restrict__ lay_vn, REAL* __restrict__ hi, int var, REAL add, uint32_t n_lay)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if(i < n_lay && lay_vn[i].x == var) hi[i] += add;
+    if(i < n_lay && lay_vn[i].x == var) hi[2 * (size_t)i] += add;   // hi = lohi + 1
 }
 
 // distribute_deffered_mm_diff_func, bdd_cuda_base.cu:1396-1414
 template<typename REAL>
-__global__ void distribute_kernel(const int2* __restrict__ lay_vn, REAL* __restrict__ lo, REAL* __restrict__ hi, REAL* __restrict__ mmd, uint32_t n_lay)
+__global__ void distribute_kernel(const int2* __restrict__ lay_vn, REAL* __restrict__ lohi, REAL* __restrict__ mmd, uint32_t n_lay)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= n_lay || lay_vn[i].x < 0) return;
     const REAL d = mmd[i];
-    if(d > 0) hi[i] += d; else lo[i] -= d;
+    if(d > 0) lohi[2 * (size_t)i + 1] += d; else lohi[2 * (size_t)i] -= d;
     mmd[i] = 0;
 }
 
-// out[e] = src[ext2lay[e]] for inner layers, `fill` for terminal layers
+// out[e] = src[stride * ext2lay[e]] for inner layers, `fill` for terminal layers
 template<typename T>
-__global__ void gather_ext_kernel(const uint32_t* __restrict__ ext2lay, const int32_t* __restrict__ ext_var, const T* __restrict__ src, T* __restrict__ out, T fill, uint32_t n_ext)
+__global__ void gather_ext_kernel(const uint32_t* __restrict__ ext2lay, const int32_t* __restrict__ ext_var, const T* __restrict__ src, uint32_t stride, T* __restrict__ out, T fill, uint32_t n_ext)
 {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if(e >= n_ext) return;
-    out[e] = ext_var[e] == INT_MAX ? fill : src[ext2lay[e]];
+    out[e] = ext_var[e] == INT_MAX ? fill : src[(size_t)stride * ext2lay[e]];
 }
 
 template<typename T>
-__global__ void scatter_ext_kernel(const uint32_t* __restrict__ ext2lay, const int32_t* __restrict__ ext_var, const T* __restrict__ in, T* __restrict__ dst, uint32_t n_ext)
+__global__ void scatter_ext_kernel(const uint32_t* __restrict__ ext2lay, const int32_t* __restrict__ ext_var, const T* __restrict__ in, T* __restrict__ dst, uint32_t stride, uint32_t n_ext)
 {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if(e >= n_ext || ext_var[e] == INT_MAX) return;
-    dst[ext2lay[e]] = in[e];
+    dst[(size_t)stride * ext2lay[e]] = in[e];
 }
 
 // out[i] = src[perm[i]]
@@ -431,24 +579,24 @@ __global__ void permute_kernel(const uint32_t* __restrict__ perm, const T* __res
 
 // compute_net_costs_func, bdd_cuda_parallel_mma.cu:432-447 (layer order, terminals 0)
 template<typename REAL>
-__global__ void net_costs_kernel(const uint32_t* __restrict__ ext2lay, const int32_t* __restrict__ ext_var, const REAL* __restrict__ lo, const REAL* __restrict__ hi,
+__global__ void net_costs_kernel(const uint32_t* __restrict__ ext2lay, const int32_t* __restrict__ ext_var, const REAL* __restrict__ lohi,
                                  const REAL* __restrict__ mmd, REAL* __restrict__ out, uint32_t n_ext)
 {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if(e >= n_ext) return;
     if(ext_var[e] == INT_MAX) { out[e] = 0; return; }
     const uint32_t l = ext2lay[e];
-    out[e] = hi[l] - lo[l] + mmd[l];
+    out[e] = lohi[2 * (size_t)l + 1] - lohi[2 * (size_t)l] + mmd[l];
 }
 
 // add_scaled_product_func, bdd_cuda_parallel_mma.h:53-60
 template<typename REAL>
-__global__ void gradient_step_kernel(const uint32_t* __restrict__ ext2lay, const int32_t* __restrict__ ext_var, REAL* __restrict__ hi, const REAL* __restrict__ g, REAL step, uint32_t n_ext)
+__global__ void gradient_step_kernel(const uint32_t* __restrict__ ext2lay, const int32_t* __restrict__ ext_var, REAL* __restrict__ lohi, const REAL* __restrict__ g, REAL step, uint32_t n_ext)
 {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if(e >= n_ext || ext_var[e] == INT_MAX) return;
-    const uint32_t l = ext2lay[e];
-    hi[l] = hi[l] + step * g[e];
+    const size_t l = 2 * (size_t)ext2lay[e] + 1;
+    lohi[l] = lohi[l] + step * g[e];
 }
 
 // make_dual_feasible, bdd_cuda_base.cu:1261-1303: subtract the per-variable mean; terminals 0.
@@ -475,13 +623,13 @@ __global__ void zero_terminals_kernel(const int32_t* __restrict__ ext_var, REAL*
 
 // compute_primal_objective_vec, bdd_cuda_base.cu:1352-1362
 template<typename REAL>
-__global__ void primal_objective_kernel(const uint32_t* __restrict__ var_lay_begin, const uint32_t* __restrict__ var_lay, const REAL* __restrict__ lo, const REAL* __restrict__ hi,
+__global__ void primal_objective_kernel(const uint32_t* __restrict__ var_lay_begin, const uint32_t* __restrict__ var_lay, const REAL* __restrict__ lohi,
                                         double* __restrict__ out, uint32_t n_vars)
 {
     const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
     if(v >= n_vars) return;
     REAL s = 0;
-    for(uint32_t i = var_lay_begin[v]; i < var_lay_begin[v + 1]; ++i) s += hi[var_lay[i]] - lo[var_lay[i]];
+    for(uint32_t i = var_lay_begin[v]; i < var_lay_begin[v + 1]; ++i) s += lohi[2 * (size_t)var_lay[i] + 1] - lohi[2 * (size_t)var_lay[i]];
     out[v] = (double)s;
 }
 
@@ -524,7 +672,7 @@ __global__ void lb_final_kernel(const double* __restrict__ partial, double* __re
 template<typename REAL>
 __global__ void bdds_solution_kernel(const BundleDesc* __restrict__ bundles, const HopRec* __restrict__ hops, const uint32_t* __restrict__ topo,
                                      const uint32_t* __restrict__ bdd_bundle, const uint32_t* __restrict__ bdd_ext_begin,
-                                     const REAL* __restrict__ cfr, const REAL* __restrict__ cft, const REAL* __restrict__ lo_c, const REAL* __restrict__ hi_c,
+                                     const REAL* __restrict__ cfr, const REAL* __restrict__ cft, const REAL* __restrict__ lohi,
                                      char* __restrict__ sol, uint32_t n_bdds)
 {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -543,8 +691,8 @@ __global__ void bdds_solution_kernel(const BundleDesc* __restrict__ bundles, con
         const uint32_t lay = bd.layer_base + k * bpw + q;
         const uint32_t lo = t & 0xFFFFu, hi = t >> 16;
         const REAL c = cfr[s];
-        const REAL lo_path = c + ((lo == CHILD_BOT ? INF : cft[hn.node_off + lo]) + lo_c[lay]);
-        const REAL hi_path = c + ((hi == CHILD_BOT ? INF : cft[hn.node_off + hi]) + hi_c[lay]);
+        const REAL lo_path = c + ((lo == CHILD_BOT ? INF : cft[hn.node_off + lo]) + lohi[2 * (size_t)lay]);
+        const REAL hi_path = c + ((hi == CHILD_BOT ? INF : cft[hn.node_off + hi]) + lohi[2 * (size_t)lay + 1]);
         const bool take_lo = (hi_path - lo_path > 0);
         sol[e0 + k] = take_lo ? 0 : 1;
         ts = take_lo ? lo : hi;

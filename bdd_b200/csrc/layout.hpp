@@ -1,5 +1,5 @@
 // bdd_b200/csrc/layout.hpp -- host-side layout builder: BDD::bdd_collection (flat
-// instruction array) -> the bundle/hop-major SoA the sm_100a sweep kernels stream.
+// instruction array) -> the bundle/chunk/hop-major SoA the sm_100a sweep kernels stream.
 //
 // Replaces the reference's constructor chain bdd_cuda_base.cu:31-46 (initialize,
 // populate_bdd_nodes, reorder_bdd_nodes, compress_bdd_nodes_to_layer,
@@ -10,17 +10,22 @@
 // pass BDDs are independent).
 //
 // Memory layout (all arrays indexed by "slot" or "layer entry"):
-//   bundle g, hop k owns a tile of 32 * J[g][k] node slots starting at hop.node_off;
-//   slot (j, lane) = node_off + j*32 + lane holds, for the BDD owning that lane group
+//   A bundle's hops are cut into *chunks* of consecutive hops; inside a chunk every hop owns a
+//   tile of 32 * J node slots (J uniform per chunk), tiles and chunks of a bundle are
+//   contiguous.  One chunk is what the kernel stages into one shared-memory pipeline stage
+//   with a handful of bulk-async copies (every per-slot / per-layer array of a chunk is one
+//   contiguous, 16-byte aligned range).
+//   slot (j, lane) of a tile = tile_off + j*32 + lane holds, for the BDD owning that lane group
 //   (bdd_local = lane >> logP), the node with index  c = j*P + (lane & (P-1))  of that BDD's
-//   layer k.  A warp therefore reads every per-node array with fully coalesced 128-byte
+//   layer.  A warp therefore touches every per-node array in fully coalesced 128-byte
 //   rows, and a BDD's frontier stays in the same shared-memory banks from hop to hop.
 //   topo[slot] = lo_child | hi_child << 16, children given as slot index inside the NEXT
 //   hop's tile (0xFFFF = arc into the bot sink: value +inf, no memory access);
 //   TOPO_TOP marks the BDD's top sink (cost_from_terminal 0), TOPO_PAD an unused slot.
 //   Layer entry (g, k, bdd_local) = layer_base + k*(32/P) + bdd_local holds the layer's
-//   variable, the (global) number of BDDs of that variable, lo/hi arc cost and the deferred
-//   min-marginal difference.
+//   variable, the (global) number of BDDs of that variable, lo/hi arc cost (interleaved) and
+//   the deferred min-marginal difference.  layer_base is even so that 8-byte entries of a
+//   chunk start 16-byte aligned.
 #pragma once
 
 #include <algorithm>
@@ -47,16 +52,37 @@ struct HopRec {
     uint32_t J;          // rows of 32 slots
 };
 
+// One pipeline stage worth of consecutive hops of a bundle.
+struct ChunkRec {
+    uint32_t slot_off;   // first slot of the chunk's first tile
+    uint32_t lay_off;    // first layer entry (even)
+    uint32_t hop_first;  // first hop of the chunk inside its bundle
+    uint32_t n_hops;
+    uint32_t J;          // rows of 32 slots per tile, uniform inside the chunk
+    uint32_t J_next;     // J of the following chunk (0: last chunk)
+    uint32_t pad_[2];
+};
+
 struct BundleDesc {
     uint32_t hop_base;   // index of the bundle's first HopRec
     uint32_t n_hops;     // hops incl. the terminal hop of the longest BDD
-    uint32_t layer_base; // first layer entry
+    uint32_t layer_base; // first layer entry (even)
     uint32_t logP;       // log2(lanes per BDD)
     uint32_t bdd_base;   // first entry in bundle_bdd (32 >> logP entries)
     uint32_t max_J;
-    uint32_t work;       // sum of J over hops (scheduling weight)
-    uint32_t pad_;
+    uint32_t chunk_base; // index of the bundle's first ChunkRec
+    uint32_t n_chunks;
 };
+
+// Shared-memory bytes one chunk occupies in a pipeline stage (worst case over the forward
+// and the backward kernel): topo + the opposite direction's DP values + {var, nr_bdds} +
+// {lo, hi} + gathered {delta_lo, delta_hi}.
+inline size_t chunk_stage_bytes(uint32_t n_hops, uint32_t J, uint32_t J_next, uint32_t bpw, size_t R)
+{
+    const size_t ne = ((size_t)n_hops * bpw + 1) & ~(size_t)1;
+    const size_t dp_rows = std::max<size_t>((size_t)n_hops * J, (size_t)(n_hops - 1) * J + J_next);
+    return (size_t)n_hops * J * 128 + dp_rows * 32 * R + ne * (8 + 4 * R);
+}
 
 struct layout_error : std::runtime_error {
     int code;
@@ -68,9 +94,11 @@ struct HostLayout {
     size_t n_layers_ext = 0;   // sum over BDDs of (nr variables + 1)
     size_t n_real_nodes = 0;   // non-terminal nodes
     size_t n_slots = 0, n_lay = 0, max_hops = 0;
-    size_t n_small_bundles = 0;          // bundles [0, n_small) have max_J <= SMALL_CLASS_MAX_J
+    size_t n_small_bundles = 0;          // bundles [0, n_small): every chunk fits the stage budget
     uint32_t max_tile_small = 0, max_tile_large = 0;  // slots
+    size_t stage_small = 0, stage_large = 0;          // largest chunk_stage_bytes per class
     std::vector<BundleDesc> bundles;
+    std::vector<ChunkRec> chunks;
     std::vector<HopRec> hops;
     std::vector<int32_t> bundle_bdd;     // per bundle lane group: external BDD index or -1
     std::vector<uint32_t> topo;          // per slot
@@ -91,10 +119,15 @@ struct HostLayout {
 inline uint32_t pow2ceil(uint32_t x) { uint32_t p = 1; while(p < x) p <<= 1; return p; }
 inline uint32_t ilog2(uint32_t x) { uint32_t l = 0; while((1u << l) < x) ++l; return l; }
 
+constexpr size_t DEFAULT_STAGE_BUDGET = 12 * 1024;   // bytes of one pipeline stage of the small class
+
 // lanes_per_bdd: 0 = heuristic (about <= 4 nodes of a layer per lane), else forced.
+// real_bytes: sizeof(REAL) of the solver (chunk sizes depend on it); stage_budget: shared-memory
+// bytes one chunk of a small-class bundle may occupy.
 inline HostLayout build_layout(const bddb200_instruction* instrs, size_t n_instr,
                                const size_t* delims, size_t n_bdds, int lanes_per_bdd,
-                               size_t nr_variables_override = 0)
+                               size_t nr_variables_override = 0, size_t real_bytes = 4,
+                               size_t stage_budget = DEFAULT_STAGE_BUDGET)
 {
     constexpr size_t TOPSINK = (size_t)-1, BOTSINK = (size_t)-1 - 1;
     if(n_bdds == 0) throw layout_error(BDDB200_ERR_INVALID_ARGUMENT, "empty BDD collection");
@@ -184,7 +217,8 @@ inline HostLayout build_layout(const bddb200_instruction* instrs, size_t n_instr
         return nlay(x) > nlay(y);
     });
 
-    struct ProtoBundle { uint32_t first, count, logP, n_hops, max_J, work; std::vector<uint32_t> J; };
+    struct ProtoChunk { uint32_t first, n, J; };
+    struct ProtoBundle { uint32_t first, count, logP, n_hops, max_J, work; bool small; std::vector<uint32_t> J; std::vector<ProtoChunk> chunks; };
     std::vector<ProtoBundle> protos;
     for(size_t pos = 0; pos < n_bdds;)
     {
@@ -208,9 +242,49 @@ inline HostLayout build_layout(const bddb200_instruction* instrs, size_t n_instr
             }
         }
         pb.max_J = *std::max_element(pb.J.begin(), pb.J.end());
-        pb.work = std::accumulate(pb.J.begin(), pb.J.end(), 0u);
         if(pb.max_J * 32u > MAX_TILE_SLOTS)
             throw layout_error(BDDB200_ERR_TOO_WIDE, "a BDD layer is wider than " + std::to_string(MAX_TILE_SLOTS) + " nodes; split the BDD (split_qbdd)");
+
+        // Cut the hops into chunks, back to front (so that the J of the following chunk is
+        // known): a chunk grows towards the root while it fits the stage budget and padding
+        // its tiles to a common J wastes at most a quarter of its rows (+2).  With one BDD
+        // per warp (bpw == 1) chunks start at even hops to keep layer ranges 16-byte aligned.
+        {
+            uint32_t e = pb.n_hops;          // exclusive end of the chunk being formed
+            uint32_t J_next = 0;
+            std::vector<ProtoChunk> rev;
+            while(e > 0)
+            {
+                uint32_t a = e - 1, Jc = pb.J[a], real = pb.J[a];
+                uint32_t best_a = a, best_J = Jc;
+                while(a > 0)
+                {
+                    const uint32_t na = a - 1;
+                    const uint32_t nJ = std::max(Jc, pb.J[na]);
+                    const uint32_t nreal = real + pb.J[na];
+                    const uint32_t n = e - na;
+                    if(chunk_stage_bytes(n, nJ, J_next, bpw, real_bytes) > stage_budget) break;
+                    if((size_t)n * nJ > (size_t)nreal + nreal / 4 + 2) break;
+                    a = na; Jc = nJ; real = nreal;
+                    if(bpw > 1 || (a % 2) == 0) { best_a = a; best_J = Jc; }
+                }
+                if(bpw == 1 && (best_a % 2) != 0)
+                {   // a one-hop chunk at an odd hop: take the previous hop along regardless of the budget
+                    best_a -= 1; best_J = std::max(best_J, pb.J[best_a]);
+                }
+                rev.push_back(ProtoChunk{best_a, e - best_a, best_J});
+                J_next = best_J;
+                e = best_a;
+            }
+            pb.chunks.assign(rev.rbegin(), rev.rend());
+        }
+        pb.work = 0; pb.small = true;
+        for(size_t c = 0; c < pb.chunks.size(); ++c)
+        {
+            const uint32_t Jn = c + 1 < pb.chunks.size() ? pb.chunks[c+1].J : 0u;
+            pb.work += pb.chunks[c].n * pb.chunks[c].J;
+            if(chunk_stage_bytes(pb.chunks[c].n, pb.chunks[c].J, Jn, bpw, real_bytes) > stage_budget) pb.small = false;
+        }
         protos.push_back(std::move(pb));
         pos = end;
     }
@@ -218,8 +292,7 @@ inline HostLayout build_layout(const bddb200_instruction* instrs, size_t n_instr
     std::vector<uint32_t> border(protos.size());
     std::iota(border.begin(), border.end(), 0u);
     std::stable_sort(border.begin(), border.end(), [&](uint32_t x, uint32_t y) {
-        const bool sx = protos[x].max_J <= SMALL_CLASS_MAX_J, sy = protos[y].max_J <= SMALL_CLASS_MAX_J;
-        if(sx != sy) return sx;
+        if(protos[x].small != protos[y].small) return protos[x].small;
         return protos[x].work > protos[y].work;
     });
 
@@ -231,24 +304,40 @@ inline HostLayout build_layout(const bddb200_instruction* instrs, size_t n_instr
         const ProtoBundle& pb = protos[pi];
         BundleDesc bd{};
         bd.hop_base = (uint32_t)L.hops.size();
-        bd.n_hops = pb.n_hops; bd.logP = pb.logP; bd.max_J = pb.max_J; bd.work = pb.work;
+        bd.n_hops = pb.n_hops; bd.logP = pb.logP; bd.max_J = 0;
+        lay = (lay + 1) & ~(size_t)1;
         bd.layer_base = (uint32_t)lay;
         bd.bdd_base = (uint32_t)L.bundle_bdd.size();
+        bd.chunk_base = (uint32_t)L.chunks.size();
+        bd.n_chunks = (uint32_t)pb.chunks.size();
         const uint32_t bpw = 32u >> pb.logP;
-        for(uint32_t k = 0; k < pb.n_hops; ++k)
+        for(size_t c = 0; c < pb.chunks.size(); ++c)
         {
-            if(slot > 0xFFFFFFFFull - 32ull * pb.J[k]) throw layout_error(BDDB200_ERR_INVALID_ARGUMENT, "collection too large (slot index overflow)");
-            L.hops.push_back(HopRec{(uint32_t)slot, pb.J[k]});
-            slot += 32ull * pb.J[k];
+            const ProtoChunk& pc = pb.chunks[c];
+            ChunkRec cr{};
+            cr.slot_off = (uint32_t)slot; cr.lay_off = (uint32_t)(lay + (size_t)pc.first * bpw);
+            cr.hop_first = pc.first; cr.n_hops = pc.n; cr.J = pc.J;
+            cr.J_next = c + 1 < pb.chunks.size() ? pb.chunks[c+1].J : 0u;
+            L.chunks.push_back(cr);
+            bd.max_J = std::max(bd.max_J, pc.J);
+            const size_t sb = chunk_stage_bytes(pc.n, pc.J, cr.J_next, bpw, real_bytes);
+            if(pb.small) L.stage_small = std::max(L.stage_small, sb); else L.stage_large = std::max(L.stage_large, sb);
+            for(uint32_t k = 0; k < pc.n; ++k)
+            {
+                if(slot > 0xFFFFFFFFull - 32ull * pc.J) throw layout_error(BDDB200_ERR_INVALID_ARGUMENT, "collection too large (slot index overflow)");
+                L.hops.push_back(HopRec{(uint32_t)slot, pc.J});
+                slot += 32ull * pc.J;
+            }
         }
         for(uint32_t q = 0; q < bpw; ++q)
             L.bundle_bdd.push_back(q < pb.count ? (int32_t)order[pb.first + q] : -1);
         lay += (size_t)pb.n_hops * bpw;
-        if(pb.max_J <= SMALL_CLASS_MAX_J) { L.n_small_bundles++; L.max_tile_small = std::max(L.max_tile_small, pb.max_J * 32u); }
-        else L.max_tile_large = std::max(L.max_tile_large, pb.max_J * 32u);
+        if(pb.small) { L.n_small_bundles++; L.max_tile_small = std::max(L.max_tile_small, bd.max_J * 32u); }
+        else L.max_tile_large = std::max(L.max_tile_large, bd.max_J * 32u);
         L.max_hops = std::max<size_t>(L.max_hops, pb.n_hops);
         L.bundles.push_back(bd);
     }
+    lay = ((lay + 1) & ~(size_t)1) + 2;     // bulk copies of a chunk's layer range may read one entry past it
     L.n_slots = slot; L.n_lay = lay;
     if(lay > 0xFFFFFFF0ull) throw layout_error(BDDB200_ERR_INVALID_ARGUMENT, "collection too large (layer index overflow)");
 

@@ -75,6 +75,10 @@ typedef struct bddb200_options {
     const int32_t* nr_bdds_per_var_host; /* NULL = counted from this collection; else global counts of *
                                      * length nr_variables (shard mode, cf. the hybrid solver's         *
                                      * bdd_multi_parallel_mma_base.cu:191-215)                          */
+    /* kernel tuning; 0 = automatic */
+    int stage_bytes;                /* shared-memory budget of one pipeline stage (chunk of hops)      */
+    int n_stages;                   /* pipeline depth per warp, 2..8 (default 3)                       */
+    int warps_per_cta;              /* bundles (warps) per CTA for bundles that fit the stage budget   */
 } bddb200_options;
 
 void bddb200_default_options(bddb200_options* opts);
@@ -166,7 +170,8 @@ size_t bddb200_kernel_launches(const bddb200_solver* s);
 int bddb200_delta_sum_buffer(bddb200_solver* s, void** sum_dev);
 
 /* Layout statistics computed on the host only (no GPU needed): fills up to n of
- * {slots, layer entries, bundles, real nodes, max hops, max tile slots, nr classes}. */
+ * {slots, layer entries, bundles, real nodes, max hops, max tile slots, small-class bundles,
+ *  layers, chunks, largest small-class stage bytes, largest large-class stage bytes}. */
 int bddb200_layout_stats(const bddb200_instruction* instrs_host, size_t n_instr,
                          const size_t* delimiters_host, size_t n_bdds, int lanes_per_bdd,
                          uint64_t* out, size_t n);

@@ -48,12 +48,13 @@ def test_create_without_gpu_fails_loudly():
 
 def layout_stats(col, lanes=0):
     lib = _lib.load()
-    out = np.zeros(8, dtype=np.uint64)
+    out = np.zeros(11, dtype=np.uint64)
     instrs = np.ascontiguousarray(col.instrs); delims = np.ascontiguousarray(col.delims)
-    rc = lib.bddb200_layout_stats(instrs.ctypes.data, instrs.shape[0], delims.ctypes.data, delims.shape[0] - 1, lanes, out.ctypes.data, 8)
+    rc = lib.bddb200_layout_stats(instrs.ctypes.data, instrs.shape[0], delims.ctypes.data, delims.shape[0] - 1, lanes, out.ctypes.data, 11)
     if rc != 0:
         raise RuntimeError(lib.bddb200_last_error().decode())
-    return dict(zip(["slots", "layer_entries", "bundles", "real_nodes", "max_hops", "max_tile", "small_bundles", "ext_layers"], out.tolist()))
+    return dict(zip(["slots", "layer_entries", "bundles", "real_nodes", "max_hops", "max_tile", "small_bundles", "ext_layers",
+                     "chunks", "stage_small", "stage_large"], out.tolist()))
 
 
 def test_layout_set_cover_is_tight():
@@ -62,8 +63,10 @@ def test_layout_set_cover_is_tight():
     assert st["real_nodes"] == 2048 * 39
     assert st["bundles"] == 2048 // 32 and st["small_bundles"] == st["bundles"]
     assert st["max_hops"] == 21
-    # one lane per BDD, 2 rows per hop except the root hop and the terminal hop: 1 + 19*2 + 1 rows
-    assert st["slots"] == st["bundles"] * 32 * 40
+    # one lane per BDD, tiles of a chunk share one height: 21 hops x 2 rows (root and terminal hop padded)
+    assert st["slots"] == st["bundles"] * 32 * 42
+    # 21 hops x 1280 B (float) do not fit one 12 KiB stage: 3 chunks per bundle, each within the budget
+    assert st["chunks"] == 3 * st["bundles"] and 0 < st["stage_small"] <= 12 * 1024 and st["stage_large"] == 0
     assert st["ext_layers"] == 2048 * 21
     # forcing more lanes per BDD trades padding for parallelism
     st2 = layout_stats(col, lanes=2)
