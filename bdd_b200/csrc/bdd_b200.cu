@@ -240,7 +240,7 @@ public:
     // Shared memory of one warp: n_stages pipeline stages, two frontier buffers, the mbarriers.
     static uint32_t warp_smem(uint32_t n_stages, uint32_t stage_bytes, uint32_t tile_slots)
     {
-        return (uint32_t)((((size_t)n_stages * stage_bytes + 2 * (size_t)tile_slots * sizeof(REAL) + 8 * (size_t)n_stages) + 127) & ~(size_t)127);
+        return (uint32_t)((((size_t)n_stages * stage_bytes + 2 * (size_t)tile_slots * sizeof(REAL) + 8 * (size_t)n_stages + INV_TAB * sizeof(REAL)) + 127) & ~(size_t)127);
     }
 
     // Choose warps per CTA for the small class (bundles that fit the stage budget) and the
@@ -299,7 +299,7 @@ public:
         SweepArgs<REAL> a = base_args();
         a.omega = (REAL)omega;
         a.delta_in = delta_in; a.delta_out = delta_out; a.zero_buf = zero_buf;
-        a.normalize_in = normalize_in ? 1 : 0;
+        a.normalize_in = !normalize_in ? NORM_NONE : (deterministic_ ? NORM_DIVIDE : NORM_RECIPROCAL);
         a.accumulate = deterministic_ ? 0 : 1;
         launch_sweep<MODE_MMA, FORWARD>(a);
         cc_ ^= 1;   // thrust::swap(lo_cost_, lo_cost_out_), bdd_cuda_parallel_mma.cu:246-247

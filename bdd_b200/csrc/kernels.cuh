@@ -150,6 +150,18 @@ __device__ __forceinline__ REAL group_min(REAL v)
     return v;
 }
 
+enum NormalizeMode { NORM_NONE = 0, NORM_DIVIDE = 1, NORM_RECIPROCAL = 2 };
+constexpr int INV_TAB = 64;
+
+// omega * (mm_hi - mm_lo), 0 if either min-marginal is infinite (compute_mm_diff_flush_mm_lo,
+// bdd_cuda_parallel_mma.cu:29-42): inf - finite, finite - inf and inf - inf all fail the test.
+template<typename REAL>
+__device__ __forceinline__ REAL mm_difference(REAL omega, REAL mm0, REAL mm1)
+{
+    const REAL d = mm1 - mm0;
+    return fabs(d) < real_inf<REAL>() ? omega * d : (REAL)0;
+}
+
 // Where the pieces of one chunk live inside a pipeline stage.
 template<typename REAL, int MODE, bool FORWARD>
 struct ChunkGeom {
@@ -197,9 +209,15 @@ __device__ __forceinline__ ChunkRec shfl_chunk(const ChunkRec& r, int src)
 // Layer update shared by both directions:
 //   mm_diff = omega * (mm_hi - mm_lo), 0 if either is infinite  (bdd_cuda_parallel_mma.cu:29-42)
 //   lo' = lo + min(mm_diff, 0) + delta[2v];  hi' = hi + min(-mm_diff, 0) + delta[2v+1]   (:185-193, :280-281)
-template<typename REAL, int LOGP, int MODE, bool FORWARD>
+//
+// JMAX > 0 selects the register-resident variant for one lane per BDD (LOGP == 0) with at most
+// JMAX rows per tile: the frontier of a BDD is JMAX registers of its lane, child look-ups and
+// relaxations are unrolled selects, shared memory only holds the staged inputs.
+template<typename REAL, int LOGP, int MODE, bool FORWARD, int JMAX = 0>
 __device__ __forceinline__ void sweep_bundle(const SweepArgs<REAL>& a, const BundleDesc& bd, unsigned char* wsm, const int lane)
 {
+    static_assert(JMAX == 0 || LOGP == 0, "register frontier needs one lane per BDD");
+    constexpr int JM = JMAX > 0 ? JMAX : 1;
     using R2 = typename real2<REAL>::type;
     using Geom = ChunkGeom<REAL, MODE, FORWARD>;
     constexpr int P = 1 << LOGP;
@@ -214,17 +232,28 @@ __device__ __forceinline__ void sweep_bundle(const SweepArgs<REAL>& a, const Bun
     REAL* cur = reinterpret_cast<REAL*>(wsm + (size_t)NS * a.stage_bytes);
     REAL* nxt = cur + a.tile_slots;
     uint64_t* bars = reinterpret_cast<uint64_t*>(nxt + a.tile_slots);
+    REAL* inv_tab = reinterpret_cast<REAL*>(bars + NS);      // 1 / n for n < INV_TAB
 
     if(lane == 0)
     {
         for(uint32_t s = 0; s < NS; ++s) mbar_init(bars + s, 1);
         mbar_fence_init();
     }
+    if(MODE == MODE_MMA && a.normalize_in == NORM_RECIPROCAL)
+        for(int i = lane; i < INV_TAB; i += 32) inv_tab[i] = (REAL)1 / (REAL)(i > 0 ? i : 1);
+    REAL fr[JM];          // register frontier (JMAX > 0): cost_from_root of this hop / cost_from_terminal of the next
+#pragma unroll
+    for(int j = 0; j < JM; ++j) fr[j] = INF;
     if(FORWARD)
-    {   // invariant: a frontier buffer is all +inf outside the tile it currently holds
-        for(uint32_t i = lane; i < 2 * a.tile_slots; i += 32) cur[i] = INF;
-        __syncwarp();
-        if(p == 0 && a.bundle_bdd[bd.bdd_base + bl] >= 0) cur[lane] = 0;   // flush_costs_from_root, bdd_cuda_base.cu:1438-1445
+    {
+        const bool has_bdd = p == 0 && a.bundle_bdd[bd.bdd_base + bl] >= 0;
+        if(JMAX > 0) { if(has_bdd) fr[0] = 0; }
+        else
+        {   // invariant: a frontier buffer is all +inf outside the tile it currently holds
+            for(uint32_t i = lane; i < 2 * a.tile_slots; i += 32) cur[i] = INF;
+            __syncwarp();
+            if(has_bdd) cur[lane] = 0;   // flush_costs_from_root, bdd_cuda_base.cu:1438-1445
+        }
     }
     __syncwarp();
 
@@ -325,10 +354,15 @@ __device__ __forceinline__ void sweep_bundle(const SweepArgs<REAL>& a, const Bun
                 {
                     const R2 d = s_delta[e];
                     d0 = d.x; d1 = d.y;
-                    if(a.normalize_in)
+                    if(a.normalize_in == NORM_DIVIDE)
                     {
                         const REAL n = (REAL)vn.y;
                         d0 /= n; d1 /= n;
+                    }
+                    else if(a.normalize_in == NORM_RECIPROCAL)
+                    {
+                        const REAL r = vn.y < INV_TAB ? inv_tab[vn.y] : (REAL)1 / (REAL)vn.y;
+                        d0 *= r; d1 *= r;
                     }
                 }
             }
@@ -336,7 +370,120 @@ __device__ __forceinline__ void sweep_bundle(const SweepArgs<REAL>& a, const Bun
             const uint32_t gslot = g.slot_off + h * J * 32u + lane;
             REAL lo_n = lo_c, hi_n = hi_c, diff = 0;
 
-            if(FORWARD)
+            if constexpr (JMAX > 0)
+            {
+                // ---- one lane per BDD, frontier in registers ------------------------------
+                uint32_t t[JM];
+#pragma unroll
+                for(int j = 0; j < JM; ++j) t[j] = (uint32_t)j < J ? trow[j * 32] : TOPO_PAD;
+                if(FORWARD)
+                {
+                    if(MODE == MODE_MMA)
+                    {
+                        const uint32_t Jc = (h + 1 < g.n) ? J : g.Jn;       // rows of the next hop's tile
+                        const REAL* child = s_dp + h * J * 32u + lane;      // its cost_from_terminal
+                        REAL dpv[JM];
+#pragma unroll
+                        for(int r = 0; r < JM; ++r) dpv[r] = (uint32_t)r < Jc ? child[r * 32] : INF;
+                        REAL mm0 = INF, mm1 = INF;
+#pragma unroll
+                        for(int j = 0; j < JM; ++j)
+                        {
+                            if(t[j] < TOPO_TOP)
+                            {
+                                const uint32_t lo_row = (t[j] & 0xFFFFu) >> 5, hi_row = t[j] >> 21;   // CHILD_BOT -> row 2047: matches nothing
+                                REAL ta = INF, tb = INF;
+#pragma unroll
+                                for(int r = 0; r < JM; ++r) { ta = lo_row == (uint32_t)r ? dpv[r] : ta; tb = hi_row == (uint32_t)r ? dpv[r] : tb; }
+                                const REAL m0 = fr[j] + lo_c + ta;
+                                const REAL m1 = fr[j] + hi_c + tb;
+                                mm0 = m0 < mm0 ? m0 : mm0;
+                                mm1 = m1 < mm1 ? m1 : mm1;
+                            }
+                        }
+                        diff = mm_difference(a.omega, mm0, mm1);
+                        lo_n = lo_c + (diff < 0 ? diff : (REAL)0) + d0;
+                        hi_n = hi_c + (-diff < 0 ? -diff : (REAL)0) + d1;
+                    }
+                    REAL nx[JM];
+#pragma unroll
+                    for(int r = 0; r < JM; ++r) nx[r] = INF;
+#pragma unroll
+                    for(int j = 0; j < JM; ++j)
+                    {
+                        if((uint32_t)j < J) a.cfr[gslot + j * 32] = fr[j];
+                        if(t[j] < TOPO_TOP)
+                        {
+                            const uint32_t lo_row = (t[j] & 0xFFFFu) >> 5, hi_row = t[j] >> 21;
+                            const REAL v0 = fr[j] + lo_n, v1 = fr[j] + hi_n;
+#pragma unroll
+                            for(int r = 0; r < JM; ++r)
+                            {
+                                nx[r] = (lo_row == (uint32_t)r && v0 < nx[r]) ? v0 : nx[r];
+                                nx[r] = (hi_row == (uint32_t)r && v1 < nx[r]) ? v1 : nx[r];
+                            }
+                        }
+                    }
+#pragma unroll
+                    for(int r = 0; r < JM; ++r) fr[r] = nx[r];
+                }
+                else
+                {
+                    if(MODE != MODE_PLAIN)
+                    {
+                        const REAL* mine = s_dp + h * J * 32u + lane;       // cost_from_root of this hop's tile
+                        REAL mm0 = INF, mm1 = INF;
+#pragma unroll
+                        for(int j = 0; j < JM; ++j)
+                        {
+                            if(t[j] < TOPO_TOP)
+                            {
+                                const REAL c = mine[j * 32];
+                                const uint32_t lo_row = (t[j] & 0xFFFFu) >> 5, hi_row = t[j] >> 21;
+                                REAL ta = INF, tb = INF;
+#pragma unroll
+                                for(int r = 0; r < JM; ++r) { ta = lo_row == (uint32_t)r ? fr[r] : ta; tb = hi_row == (uint32_t)r ? fr[r] : tb; }
+                                REAL m0, m1;
+                                if(MODE == MODE_MMA) { m0 = c + lo_c + ta; m1 = c + hi_c + tb; }
+                                else { m0 = c + (ta + lo_c); m1 = c + (tb + hi_c); }
+                                mm0 = m0 < mm0 ? m0 : mm0;
+                                mm1 = m1 < mm1 ? m1 : mm1;
+                            }
+                        }
+                        if(MODE == MODE_MMA)
+                        {
+                            diff = mm_difference(a.omega, mm0, mm1);
+                            lo_n = lo_c + (diff < 0 ? diff : (REAL)0) + d0;
+                            hi_n = hi_c + (-diff < 0 ? -diff : (REAL)0) + d1;
+                        }
+                        else if(var >= 0)
+                        {
+                            a.mm_lo_out[lay] = mm0;
+                            a.mm_hi_out[lay] = mm1;
+                        }
+                    }
+                    REAL nv[JM];
+#pragma unroll
+                    for(int j = 0; j < JM; ++j)
+                    {
+                        REAL val = t[j] == TOPO_TOP ? (REAL)0 : INF;
+                        if(t[j] < TOPO_TOP)
+                        {
+                            const uint32_t lo_row = (t[j] & 0xFFFFu) >> 5, hi_row = t[j] >> 21;
+                            REAL ta = INF, tb = INF;
+#pragma unroll
+                            for(int r = 0; r < JM; ++r) { ta = lo_row == (uint32_t)r ? fr[r] : ta; tb = hi_row == (uint32_t)r ? fr[r] : tb; }
+                            const REAL vh = hi_n + tb, vl = lo_n + ta;
+                            val = vh < vl ? vh : vl;
+                        }
+                        nv[j] = val;
+                        if((uint32_t)j < J) a.cft[gslot + j * 32] = val;
+                    }
+#pragma unroll
+                    for(int r = 0; r < JM; ++r) fr[r] = nv[r];
+                }
+            }
+            else if(FORWARD)
             {
                 if(MODE == MODE_MMA)
                 {
@@ -359,7 +506,7 @@ __device__ __forceinline__ void sweep_bundle(const SweepArgs<REAL>& a, const Bun
                     }
                     mm0 = group_min<P>(mm0);
                     mm1 = group_min<P>(mm1);
-                    if(isfinite(mm0) && isfinite(mm1)) diff = a.omega * (mm1 - mm0);
+                    diff = mm_difference(a.omega, mm0, mm1);
                     lo_n = lo_c + (diff < 0 ? diff : (REAL)0) + d0;
                     hi_n = hi_c + (-diff < 0 ? -diff : (REAL)0) + d1;
                 }
@@ -411,7 +558,7 @@ __device__ __forceinline__ void sweep_bundle(const SweepArgs<REAL>& a, const Bun
                     mm1 = group_min<P>(mm1);
                     if(MODE == MODE_MMA)
                     {
-                        if(isfinite(mm0) && isfinite(mm1)) diff = a.omega * (mm1 - mm0);
+                        diff = mm_difference(a.omega, mm0, mm1);
                         lo_n = lo_c + (diff < 0 ? diff : (REAL)0) + d0;
                         hi_n = hi_c + (-diff < 0 ? -diff : (REAL)0) + d1;
                     }
@@ -449,8 +596,11 @@ __device__ __forceinline__ void sweep_bundle(const SweepArgs<REAL>& a, const Bun
                     else if(diff < 0) atomicAdd(a.delta_out + 2 * (size_t)var, -diff);
                 }
             }
-            if(P > 1) __syncwarp();
-            REAL* tmp = cur; cur = nxt; nxt = tmp;
+            if(JMAX == 0)
+            {
+                if(P > 1) __syncwarp();
+                REAL* tmp = cur; cur = nxt; nxt = tmp;
+            }
         }
 
         __syncwarp();                                   // every lane is done with stage i % NS
@@ -461,7 +611,7 @@ __device__ __forceinline__ void sweep_bundle(const SweepArgs<REAL>& a, const Bun
     if(!FORWARD && p == 0)
     {
         const int32_t bi = a.bundle_bdd[bd.bdd_base + bl];
-        if(bi >= 0) a.bdd_lb[bi] = nxt[lane];   // root = node 0 of hop 0
+        if(bi >= 0) a.bdd_lb[bi] = JMAX > 0 ? fr[0] : nxt[lane];   // root = node 0 of hop 0
     }
 }
 
@@ -479,8 +629,16 @@ __global__ void __launch_bounds__(512, 1) sweep_kernel(const SweepArgs<REAL> a)
     g += a.bundle_first;
     unsigned char* wsm = smem_raw + (size_t)warp * a.warp_smem_bytes;
     const BundleDesc bd = a.bundles[g];
+    constexpr int M = (FORWARD && MODE == MODE_MM) ? MODE_PLAIN : MODE;
+    if(bd.logP == 0 && bd.max_J <= 4)
+    {
+        if(bd.max_J <= 1) sweep_bundle<REAL, 0, M, FORWARD, 1>(a, bd, wsm, lane);
+        else if(bd.max_J == 2) sweep_bundle<REAL, 0, M, FORWARD, 2>(a, bd, wsm, lane);
+        else sweep_bundle<REAL, 0, M, FORWARD, 4>(a, bd, wsm, lane);
+        return;
+    }
 #define BDDB200_DISPATCH(LP) \
-    case LP: sweep_bundle<REAL, LP, (FORWARD && MODE == MODE_MM ? MODE_PLAIN : MODE), FORWARD>(a, bd, wsm, lane); break;
+    case LP: sweep_bundle<REAL, LP, M, FORWARD>(a, bd, wsm, lane); break;
     switch(bd.logP)
     {
         BDDB200_DISPATCH(0) BDDB200_DISPATCH(1) BDDB200_DISPATCH(2)

@@ -1,0 +1,6 @@
+#!/bin/bash
+# parity tests, then a bench line (no ncu)
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_gpu.log | cut -c1-300
+timeout 600 python bench.py --steps 200 --warmup 10 "$@" > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
+cat gpurun_out/bench.json
