@@ -26,7 +26,7 @@ SYMBOLS = [
     "bddb200_get_solver_costs", "bddb200_set_solver_costs", "bddb200_primal_objective_host",
     "bddb200_min_marginals", "bddb200_bdds_solution", "bddb200_net_solver_costs", "bddb200_make_dual_feasible",
     "bddb200_gradient_step", "bddb200_synchronize", "bddb200_stream", "bddb200_kernel_launches",
-    "bddb200_delta_sum_buffer", "bddb200_layout_stats",
+    "bddb200_delta_sum_buffer", "bddb200_layout_stats", "bddb200_trace_pass",
 ]
 
 
@@ -105,6 +105,7 @@ def load() -> C.CDLL:
         "bddb200_kernel_launches": (sz, [vp]),
         "bddb200_delta_sum_buffer": (i, [vp, C.POINTER(vp)]),
         "bddb200_layout_stats": (i, [vp, sz, vp, sz, i, vp, sz]),
+        "bddb200_trace_pass": (i, [vp, i, dbl, vp, sz, C.POINTER(sz)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(lib, name)

@@ -94,6 +94,7 @@ struct bddb200_solver {
     virtual void* stream_handle() = 0;
     virtual size_t kernel_launches() const = 0;
     virtual void* delta_sum_buffer() = 0;
+    virtual size_t trace_pass(int forward, double omega, unsigned long long* out_host, size_t max_bundles) = 0;
 };
 
 namespace {
@@ -125,7 +126,9 @@ public:
         if(const char* e = std::getenv("BDDB200_WARPS_PER_CTA")) forced_wpc_ = (unsigned)std::atoi(e);
         if(forced_wpc_ > 16) throw api_error(BDDB200_ERR_INVALID_ARGUMENT, "warps_per_cta must be <= 16");
 
-        HostLayout L = build_layout(instrs, n_instr, delims, n_bdds, opt.lanes_per_bdd, opt.nr_variables, sizeof(REAL), stage_budget);
+        int lanes_per_bdd = opt.lanes_per_bdd;
+        if(const char* e = std::getenv("BDDB200_LANES_PER_BDD")) lanes_per_bdd = std::atoi(e);
+        HostLayout L = build_layout(instrs, n_instr, delims, n_bdds, lanes_per_bdd, opt.nr_variables, sizeof(REAL), stage_budget);
         n_vars_ = L.n_vars; n_bdds_ = L.n_bdds; n_instr_ = delims[n_bdds] - delims[0];
         n_ext_ = L.n_layers_ext; n_slots_ = L.n_slots; n_lay_ = L.n_lay; max_hops_ = L.max_hops;
         n_bundles_ = L.bundles.size(); n_small_ = L.n_small_bundles;
@@ -166,6 +169,8 @@ public:
 
         d_bundles_.upload(L.bundles, stream_);
         d_chunks_.upload(L.chunks, stream_);
+        d_desc_fwd_.upload(L.desc_fwd, stream_);
+        d_desc_bwd_.upload(L.desc_bwd, stream_);
         d_hops_.upload(L.hops, stream_);
         d_topo_.upload(L.topo, stream_);
         d_lay_vn_.upload(lay_vn, stream_);
@@ -219,11 +224,12 @@ public:
     void launch_sweep(SweepArgs<REAL> a)
     {
         auto kern = sweep_kernel<REAL, MODE, FORWARD>;
+        a.desc = FORWARD ? d_desc_fwd_.p : d_desc_bwd_.p;
         if(n_small_ > 0)
         {
             a.bundle_first = 0; a.bundle_count = (uint32_t)n_small_; a.tile_slots = tile_small_;
             a.stage_bytes = stage_small_; a.n_stages = n_stages_; a.warp_smem_bytes = warp_smem_small_;
-            kern<<<blocks_for(n_small_, warps_per_cta_), warps_per_cta_ * 32, (size_t)warps_per_cta_ * warp_smem_small_, stream_>>>(a);
+            kern<<<blocks_for(n_small_, warps_per_cta_), warps_per_cta_ * 32, INV_TAB_BYTES + (size_t)warps_per_cta_ * warp_smem_small_, stream_>>>(a);
             ++launches_;
         }
         if(n_bundles_ > n_small_)
@@ -231,7 +237,7 @@ public:
             a.bundle_first = (uint32_t)n_small_; a.bundle_count = (uint32_t)(n_bundles_ - n_small_); a.tile_slots = tile_large_;
             a.stage_bytes = stage_large_; a.n_stages = n_stages_large_; a.warp_smem_bytes = warp_smem_large_;
             if(n_small_ > 0) a.zero_buf = nullptr;
-            kern<<<(unsigned)(n_bundles_ - n_small_), 32, warp_smem_large_, stream_>>>(a);
+            kern<<<(unsigned)(n_bundles_ - n_small_), 32, INV_TAB_BYTES + warp_smem_large_, stream_>>>(a);
             ++launches_;
         }
         CUDA_CHECK(cudaGetLastError());
@@ -240,14 +246,14 @@ public:
     // Shared memory of one warp: n_stages pipeline stages, two frontier buffers, the mbarriers.
     static uint32_t warp_smem(uint32_t n_stages, uint32_t stage_bytes, uint32_t tile_slots)
     {
-        return (uint32_t)((((size_t)n_stages * stage_bytes + 2 * (size_t)tile_slots * sizeof(REAL) + 8 * (size_t)n_stages + INV_TAB * sizeof(REAL)) + 127) & ~(size_t)127);
+        return (uint32_t)((((size_t)n_stages * stage_bytes + 2 * (size_t)tile_slots * sizeof(REAL) + 8 * (size_t)n_stages) + 127) & ~(size_t)127);
     }
 
     // Choose warps per CTA for the small class (bundles that fit the stage budget) and the
     // pipeline depth of the large class (one warp per CTA).
     void plan_launch()
     {
-        const size_t budget = (size_t)max_optin_;
+        const size_t budget = (size_t)max_optin_ - INV_TAB_BYTES;
         warp_smem_small_ = warp_smem(n_stages_, stage_small_, tile_small_);
         if(n_small_ > 0 && warp_smem_small_ > budget)
             throw api_error(BDDB200_ERR_TOO_WIDE, "stage_bytes * n_stages does not fit the shared memory of one SM");
@@ -269,7 +275,7 @@ public:
 
     void configure_kernels()
     {
-        const int need = (int)std::max<size_t>((size_t)warps_per_cta_ * warp_smem_small_, warp_smem_large_);
+        const int need = (int)(INV_TAB_BYTES + std::max<size_t>((size_t)warps_per_cta_ * warp_smem_small_, warp_smem_large_));
         if(need > 48 * 1024)
         {
             CUDA_CHECK(cudaFuncSetAttribute(sweep_kernel<REAL, MODE_MMA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
@@ -284,11 +290,11 @@ public:
     {
         SweepArgs<REAL> a{};
         using R2 = typename real2<REAL>::type;
-        a.bundles = d_bundles_.p; a.chunks = d_chunks_.p; a.topo = d_topo_.p; a.lay_vn = d_lay_vn_.p; a.bundle_bdd = d_bundle_bdd_.p;
+        a.chunks = d_chunks_.p; a.topo = d_topo_.p; a.lay_vn = d_lay_vn_.p; a.bundle_bdd = d_bundle_bdd_.p;
         a.cfr = d_cfr_.p; a.cft = d_cft_.p;
         a.lohi_in = reinterpret_cast<const R2*>(d_lohi_[cc_].p); a.lohi_out = reinterpret_cast<R2*>(d_lohi_[cc_ ^ 1].p);
         a.mmd = d_mmd_.p; a.mm_lo_out = d_mm_lo_.p; a.mm_hi_out = d_mm_hi_.p; a.bdd_lb = d_bdd_lb_.p;
-        a.omega = 0; a.n_zero = (uint32_t)(2 * n_vars_);
+        a.omega = 0; a.n_zero = (uint32_t)(2 * n_vars_); a.trace = trace_;
         return a;
     }
 
@@ -433,6 +439,20 @@ public:
     }
 
     void* delta_sum_buffer() override { return d_delta_[dcur_].p; }
+
+    // diagnostics: one MMA pass with per-bundle clock64() stamps (kernels.cuh, TRACE_EVENTS per bundle)
+    size_t trace_pass(int forward, double omega, unsigned long long* out_host, size_t max_bundles) override
+    {
+        set_device();
+        const size_t n = std::min(max_bundles, n_small_);
+        DevBuf<unsigned long long> tr; tr.alloc((n_small_ + 64) * TRACE_EVENTS); tr.zero(stream_);
+        trace_ = tr.p;
+        if(forward) forward_pass(omega); else backward_pass(omega);
+        trace_ = nullptr;
+        CUDA_CHECK(cudaMemcpyAsync(out_host, tr.p, n * TRACE_EVENTS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream_));
+        CUDA_CHECK(cudaStreamSynchronize(stream_));
+        return n;
+    }
 
     // ---------------------------------------------------------------- plain runs -------
     void forward_run() override
@@ -643,6 +663,7 @@ private:
 
     DevBuf<BundleDesc> d_bundles_;
     DevBuf<ChunkRec> d_chunks_;
+    DevBuf<uint32_t> d_desc_fwd_, d_desc_bwd_;
     DevBuf<HopRec> d_hops_;
     DevBuf<uint32_t> d_topo_, d_bdd_bundle_, d_ext2lay_, d_bdd_ext_begin_, d_var_lay_begin_, d_var_lay_, d_sorted_ext_;
     DevBuf<int2> d_lay_vn_;
@@ -651,6 +672,7 @@ private:
     DevBuf<double> d_lb_partial_;
     double* h_lb_ = nullptr;
 
+    unsigned long long* trace_ = nullptr;
     int cc_ = 0;                 // which of the two lo/hi cost buffers is current
     int dcur_ = 0;               // which delta buffer holds the current (pending) sums
     bool delta_needs_norm_ = false;
@@ -760,6 +782,9 @@ int bddb200_synchronize(bddb200_solver* s) { REQUIRE_SOLVER(s); return guarded([
 void* bddb200_stream(bddb200_solver* s) { return s ? s->stream_handle() : nullptr; }
 size_t bddb200_kernel_launches(const bddb200_solver* s) { return s ? s->kernel_launches() : 0; }
 int bddb200_delta_sum_buffer(bddb200_solver* s, void** out) { REQUIRE_SOLVER(s); return guarded([&] { *out = s->delta_sum_buffer(); }); }
+
+int bddb200_trace_pass(bddb200_solver* s, int forward, double omega, unsigned long long* out_host, size_t max_bundles, size_t* n_out)
+{ REQUIRE_SOLVER(s); return guarded([&] { *n_out = s->trace_pass(forward, omega, out_host, max_bundles); }); }
 
 int bddb200_layout_stats(const bddb200_instruction* instrs, size_t n_instr, const size_t* delims, size_t n_bdds, int lanes_per_bdd, uint64_t* out, size_t n)
 {

@@ -69,7 +69,8 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
 }
 __device__ __forceinline__ void mbar_fence_init()
 {
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // make the generic-proxy mbarrier initialisation visible to the async proxy (TMA) of this CTA
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
 {
@@ -109,9 +110,12 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template<int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
+constexpr uint32_t INV_TAB_BYTES = 256 * 8;   // INV_TAB REALs, sized for double
+constexpr int TRACE_EVENTS = 16;
+
 template<typename REAL>
 struct SweepArgs {
-    const BundleDesc* bundles;
+    const uint32_t* desc;      // DESC_WORDS words per bundle, in this pass's direction
     const ChunkRec* chunks;
     const uint32_t* topo;
     const int2* lay_vn;        // per layer entry {variable or -1, nr_bdds(variable)}
@@ -134,6 +138,8 @@ struct SweepArgs {
     uint32_t stage_bytes;      // capacity of one pipeline stage
     uint32_t n_stages;         // pipeline depth (>= 2)
     uint32_t warp_smem_bytes;  // n_stages * stage_bytes + 2 frontier buffers + mbarriers, rounded to 128
+                               // (the CTA's dynamic shared memory starts with the INV_TAB_BYTES reciprocal table)
+    unsigned long long* trace; // diagnostics: TRACE_EVENTS clock64() stamps per bundle (null = off)
     int normalize_in;          // divide delta_in by nr_bdds(var) while reading
     int accumulate;            // add |mm_diff| to delta_out with atomics
 };
@@ -151,7 +157,8 @@ __device__ __forceinline__ REAL group_min(REAL v)
 }
 
 enum NormalizeMode { NORM_NONE = 0, NORM_DIVIDE = 1, NORM_RECIPROCAL = 2 };
-constexpr int INV_TAB = 64;
+constexpr int INV_TAB = 256;
+constexpr uint32_t CHILD_LIMIT = 0xFFE0u;   // child slot indices are below this; CHILD_BOT and the halves of TOPO_TOP / TOPO_PAD are not
 
 // omega * (mm_hi - mm_lo), 0 if either min-marginal is infinite (compute_mm_diff_flush_mm_lo,
 // bdd_cuda_parallel_mma.cu:29-42): inf - finite, finite - inf and inf - inf all fail the test.
@@ -183,17 +190,19 @@ struct ChunkGeom {
     }
 };
 
-// lane l keeps the ChunkRec of pipeline position (base + l); refilled every 32 chunks
-struct ChunkCache {
-    ChunkRec mine;
-    uint32_t base;
-};
-__device__ __forceinline__ ChunkRec shfl_chunk(const ChunkRec& r, int src)
+// lane l keeps the chunk record of pipeline position (base + l)
+struct ChunkLite { uint32_t slot_off, lay_off, n_hops, J, J_next; };
+__device__ __forceinline__ ChunkRec to_rec(const ChunkLite& c)
 {
-    ChunkRec o;
+    ChunkRec r;
+    r.slot_off = c.slot_off; r.lay_off = c.lay_off; r.hop_first = 0; r.n_hops = c.n_hops; r.J = c.J; r.J_next = c.J_next;
+    return r;
+}
+__device__ __forceinline__ ChunkLite shfl_chunk(const ChunkLite& r, int src)
+{
+    ChunkLite o;
     o.slot_off = __shfl_sync(0xffffffffu, r.slot_off, src);
     o.lay_off = __shfl_sync(0xffffffffu, r.lay_off, src);
-    o.hop_first = 0;
     o.n_hops = __shfl_sync(0xffffffffu, r.n_hops, src);
     o.J = __shfl_sync(0xffffffffu, r.J, src);
     o.J_next = __shfl_sync(0xffffffffu, r.J_next, src);
@@ -210,14 +219,20 @@ __device__ __forceinline__ ChunkRec shfl_chunk(const ChunkRec& r, int src)
 //   mm_diff = omega * (mm_hi - mm_lo), 0 if either is infinite  (bdd_cuda_parallel_mma.cu:29-42)
 //   lo' = lo + min(mm_diff, 0) + delta[2v];  hi' = hi + min(-mm_diff, 0) + delta[2v+1]   (:185-193, :280-281)
 //
-// JMAX > 0 selects the register-resident variant for one lane per BDD (LOGP == 0) with at most
-// JMAX rows per tile: the frontier of a BDD is JMAX registers of its lane, child look-ups and
-// relaxations are unrolled selects, shared memory only holds the staged inputs.
-template<typename REAL, int LOGP, int MODE, bool FORWARD, int JMAX = 0>
-__device__ __forceinline__ void sweep_bundle(const SweepArgs<REAL>& a, const BundleDesc& bd, unsigned char* wsm, const int lane)
+// `w` is this lane's word of the bundle's 32-word descriptor block (layout.hpp, DescWord).
+//
+// JMAX > 0 selects the register variant for narrow bundles (at most JMAX rows per tile): the
+// frontier entry of slot (j, lane) is register fr[j] of that lane, the hop body is branch
+// free, relaxation along the arcs is a pull over the P lanes of the BDD with xor-shuffles
+// (forward), children are selected from registers (backward, P == 1) or read from a
+// shared-memory frontier (backward, P > 1).  JMAX == 0 is the generic variant with the
+// frontier in shared memory and shared-memory atomic minima for the forward relaxation.
+template<typename REAL, int LOGP, int MODE, bool FORWARD, int JMAX>
+__device__ __forceinline__ void sweep_bundle(const SweepArgs<REAL>& a, const uint32_t w, unsigned char* wsm, const REAL* inv_tab, const int lane)
 {
-    static_assert(JMAX == 0 || LOGP == 0, "register frontier needs one lane per BDD");
-    constexpr int JM = JMAX > 0 ? JMAX : 1;
+    constexpr bool RP = JMAX > 0;
+    constexpr int JM = RP ? JMAX : 1;
+    constexpr bool SMEM_FRONTIER = !RP || (!FORWARD && LOGP > 0);
     using R2 = typename real2<REAL>::type;
     using Geom = ChunkGeom<REAL, MODE, FORWARD>;
     constexpr int P = 1 << LOGP;
@@ -226,51 +241,58 @@ __device__ __forceinline__ void sweep_bundle(const SweepArgs<REAL>& a, const Bun
     const int p = lane & (P - 1);
     const REAL INF = real_inf<REAL>();
     const uint32_t NS = a.n_stages;
-    const uint32_t nc = bd.n_chunks;
+    const uint32_t nc = __shfl_sync(0xffffffffu, w, DESC_N_CHUNKS);
+    const uint32_t bdd_base = __shfl_sync(0xffffffffu, w, DESC_BDD_BASE);
+    const uint32_t chunk_base = __shfl_sync(0xffffffffu, w, DESC_CHUNK_BASE);
+    int32_t bdd_index = -1;
+    if(!FORWARD && p == 0) bdd_index = a.bundle_bdd[bdd_base + bl];     // consumed after the last hop
+    unsigned long long* trace = a.trace ? a.trace + (size_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * TRACE_EVENTS : nullptr;
+    uint32_t trace_k = 1;
+    auto stamp = [&]() { if(trace && lane == 0 && trace_k < TRACE_EVENTS) trace[trace_k] = clock64(); ++trace_k; };
+    stamp();   // 1: descriptor block arrived
 
     unsigned char* stages = wsm;
     REAL* cur = reinterpret_cast<REAL*>(wsm + (size_t)NS * a.stage_bytes);
     REAL* nxt = cur + a.tile_slots;
     uint64_t* bars = reinterpret_cast<uint64_t*>(nxt + a.tile_slots);
-    REAL* inv_tab = reinterpret_cast<REAL*>(bars + NS);      // 1 / n for n < INV_TAB
 
     if(lane == 0)
     {
         for(uint32_t s = 0; s < NS; ++s) mbar_init(bars + s, 1);
         mbar_fence_init();
     }
-    if(MODE == MODE_MMA && a.normalize_in == NORM_RECIPROCAL)
-        for(int i = lane; i < INV_TAB; i += 32) inv_tab[i] = (REAL)1 / (REAL)(i > 0 ? i : 1);
-    REAL fr[JM];          // register frontier (JMAX > 0): cost_from_root of this hop / cost_from_terminal of the next
+    REAL fr[JM];          // register frontier: cost_from_root of this hop / cost_from_terminal of the next
 #pragma unroll
     for(int j = 0; j < JM; ++j) fr[j] = INF;
-    if(FORWARD)
-    {
-        const bool has_bdd = p == 0 && a.bundle_bdd[bd.bdd_base + bl] >= 0;
-        if(JMAX > 0) { if(has_bdd) fr[0] = 0; }
-        else
-        {   // invariant: a frontier buffer is all +inf outside the tile it currently holds
-            for(uint32_t i = lane; i < 2 * a.tile_slots; i += 32) cur[i] = INF;
-            __syncwarp();
-            if(has_bdd) cur[lane] = 0;   // flush_costs_from_root, bdd_cuda_base.cu:1438-1445
-        }
+    if(FORWARD && SMEM_FRONTIER)
+    {   // invariant: a frontier buffer is all +inf outside the tile it currently holds
+        for(uint32_t i = lane; i < 2 * a.tile_slots; i += 32) cur[i] = INF;
     }
     __syncwarp();
 
-    // pipeline position i (0 .. nc-1) -> chunk index
-    auto chunk_of = [&](uint32_t i) { return bd.chunk_base + (FORWARD ? i : nc - 1 - i); };
-    // lookups at loop position i only ask for positions in [i + 1, i + NS]: on a miss the
-    // window restarts at `low`, the lowest position that can still be asked for
-    ChunkCache cache;
-    cache.base = 0;
-    cache.mine = a.chunks[chunk_of(min((uint32_t)lane, nc - 1))];
+    // ---- chunk records: the first DESC_CHUNKS pipeline positions come with the descriptor
+    // block, later ones from the chunk table (off the critical path).  Lookups at loop
+    // position i only ask for positions in [i + 1, i + NS]; on a miss the window restarts at
+    // `low`, the lowest position that can still be asked for.
+    auto chunk_of = [&](uint32_t i) { return chunk_base + (FORWARD ? i : nc - 1 - i); };
+    ChunkLite mine;
+    {
+        const int k = DESC_FIRST_CHUNK + DESC_CHUNK_WORDS * min(lane, DESC_CHUNKS - 1);
+        mine.slot_off = __shfl_sync(0xffffffffu, w, k);
+        mine.lay_off = __shfl_sync(0xffffffffu, w, k + 1);
+        mine.n_hops = __shfl_sync(0xffffffffu, w, k + 2);
+        mine.J = __shfl_sync(0xffffffffu, w, k + 3);
+        mine.J_next = __shfl_sync(0xffffffffu, w, k + 4);
+    }
+    uint32_t cache_base = 0, cache_count = DESC_CHUNKS;
     auto get_chunk = [&](uint32_t i, uint32_t low) -> ChunkRec {
-        if(i >= cache.base + 32)
+        if(i >= cache_base + cache_count)
         {
-            cache.base = low;
-            cache.mine = a.chunks[chunk_of(min(low + lane, nc - 1))];
+            cache_base = low; cache_count = 32;
+            const ChunkRec r = a.chunks[chunk_of(min(low + lane, nc - 1))];
+            mine.slot_off = r.slot_off; mine.lay_off = r.lay_off; mine.n_hops = r.n_hops; mine.J = r.J; mine.J_next = r.J_next;
         }
-        return shfl_chunk(cache.mine, (int)(i - cache.base));
+        return to_rec(shfl_chunk(mine, (int)(i - cache_base)));
     };
 
     // lane 0: start the bulk copies of pipeline position i into stage i % NS
@@ -314,8 +336,16 @@ __device__ __forceinline__ void sweep_bundle(const SweepArgs<REAL>& a, const Bun
         const uint32_t pre = min(NS, nc);
         for(uint32_t i = 0; i < pre; ++i) issue(i, get_chunk(i, 0));
     }
+    stamp();       // 2: first bulk copies issued
     ChunkRec cr = get_chunk(0, 0);
     land(0, cr);
+    stamp();       // 3: first chunk landed
+    if(FORWARD)
+    {   // flush_costs_from_root (bdd_cuda_base.cu:1438-1445): the root is slot `lane` of the first tile
+        const bool has_bdd = p == 0 && reinterpret_cast<const uint32_t*>(stages)[lane] != TOPO_PAD;
+        if(SMEM_FRONTIER) { if(has_bdd) cur[lane] = 0; }
+        else if(has_bdd) fr[0] = 0;
+    }
 
     for(uint32_t i = 0; i < nc; ++i)
     {
@@ -328,6 +358,7 @@ __device__ __forceinline__ void sweep_bundle(const SweepArgs<REAL>& a, const Bun
         }
         else if(Geom::NEED_DELTA) cp_async_wait<0>();
         __syncwarp();
+        stamp();   // 4 + 2i: chunk i ready (next chunk landed, own gathers complete)
 
         const Geom g(cr, BPW);
         const unsigned char* st = stages + (size_t)(i % NS) * a.stage_bytes;
@@ -345,142 +376,157 @@ __device__ __forceinline__ void sweep_bundle(const SweepArgs<REAL>& a, const Bun
             const uint32_t lay = g.lay_off + e;
             const int2 vn = s_vn[e];
             const int var = vn.x;
-            REAL lo_c = 0, hi_c = 0, d0 = 0, d1 = 0;
-            if(var >= 0)
+            const R2 c2 = s_lohi[e];                       // entries without a layer hold {0, 0}
+            const REAL lo_c = c2.x, hi_c = c2.y;
+            REAL d0 = 0, d1 = 0;
+            if(MODE == MODE_MMA)
             {
-                const R2 c2 = s_lohi[e];
-                lo_c = c2.x; hi_c = c2.y;
-                if(MODE == MODE_MMA)
+                const R2 d = s_delta[e];                   // not gathered (garbage) where var < 0
+                d0 = var >= 0 ? d.x : (REAL)0; d1 = var >= 0 ? d.y : (REAL)0;
+                if(a.normalize_in == NORM_DIVIDE)
                 {
-                    const R2 d = s_delta[e];
-                    d0 = d.x; d1 = d.y;
-                    if(a.normalize_in == NORM_DIVIDE)
-                    {
-                        const REAL n = (REAL)vn.y;
-                        d0 /= n; d1 /= n;
-                    }
-                    else if(a.normalize_in == NORM_RECIPROCAL)
-                    {
-                        const REAL r = vn.y < INV_TAB ? inv_tab[vn.y] : (REAL)1 / (REAL)vn.y;
-                        d0 *= r; d1 *= r;
-                    }
+                    const REAL n = (REAL)(var >= 0 ? vn.y : 1);
+                    d0 /= n; d1 /= n;
+                }
+                else if(a.normalize_in == NORM_RECIPROCAL)
+                {
+                    REAL r = inv_tab[min(max(vn.y, 0), INV_TAB - 1)];
+                    if(vn.y >= INV_TAB) r = (REAL)1 / (REAL)vn.y;
+                    d0 *= r; d1 *= r;
                 }
             }
             const uint32_t* trow = s_topo + h * J * 32u + lane;
             const uint32_t gslot = g.slot_off + h * J * 32u + lane;
             REAL lo_n = lo_c, hi_n = hi_c, diff = 0;
 
-            if constexpr (JMAX > 0)
+            if constexpr (RP)
             {
-                // ---- one lane per BDD, frontier in registers ------------------------------
                 uint32_t t[JM];
 #pragma unroll
                 for(int j = 0; j < JM; ++j) t[j] = (uint32_t)j < J ? trow[j * 32] : TOPO_PAD;
+                // TOPO_TOP / TOPO_PAD words decode to child indices >= CHILD_LIMIT: their candidates are +inf
                 if(FORWARD)
                 {
                     if(MODE == MODE_MMA)
                     {
-                        const uint32_t Jc = (h + 1 < g.n) ? J : g.Jn;       // rows of the next hop's tile
-                        const REAL* child = s_dp + h * J * 32u + lane;      // its cost_from_terminal
-                        REAL dpv[JM];
-#pragma unroll
-                        for(int r = 0; r < JM; ++r) dpv[r] = (uint32_t)r < Jc ? child[r * 32] : INF;
+                        const REAL* child = s_dp + h * J * 32u;             // cost_from_terminal of the next hop's tile
                         REAL mm0 = INF, mm1 = INF;
 #pragma unroll
                         for(int j = 0; j < JM; ++j)
                         {
-                            if(t[j] < TOPO_TOP)
-                            {
-                                const uint32_t lo_row = (t[j] & 0xFFFFu) >> 5, hi_row = t[j] >> 21;   // CHILD_BOT -> row 2047: matches nothing
-                                REAL ta = INF, tb = INF;
-#pragma unroll
-                                for(int r = 0; r < JM; ++r) { ta = lo_row == (uint32_t)r ? dpv[r] : ta; tb = hi_row == (uint32_t)r ? dpv[r] : tb; }
-                                const REAL m0 = fr[j] + lo_c + ta;
-                                const REAL m1 = fr[j] + hi_c + tb;
-                                mm0 = m0 < mm0 ? m0 : mm0;
-                                mm1 = m1 < mm1 ? m1 : mm1;
-                            }
+                            const uint32_t lo = t[j] & 0xFFFFu, hi = t[j] >> 16;
+                            const REAL ta = lo < CHILD_LIMIT ? child[lo] : INF;
+                            const REAL tb = hi < CHILD_LIMIT ? child[hi] : INF;
+                            const REAL m0 = fr[j] + lo_c + ta;     // same association as bdd_cuda_parallel_mma.cu:83-84
+                            const REAL m1 = fr[j] + hi_c + tb;
+                            mm0 = m0 < mm0 ? m0 : mm0;
+                            mm1 = m1 < mm1 ? m1 : mm1;
                         }
+                        mm0 = group_min<P>(mm0);
+                        mm1 = group_min<P>(mm1);
                         diff = mm_difference(a.omega, mm0, mm1);
                         lo_n = lo_c + (diff < 0 ? diff : (REAL)0) + d0;
                         hi_n = hi_c + (-diff < 0 ? -diff : (REAL)0) + d1;
                     }
+                    // relaxation as a pull: every slot collects the arcs of the P lanes of its BDD
                     REAL nx[JM];
 #pragma unroll
                     for(int r = 0; r < JM; ++r) nx[r] = INF;
 #pragma unroll
-                    for(int j = 0; j < JM; ++j)
+                    for(int d = 0; d < P; ++d)
                     {
-                        if((uint32_t)j < J) a.cfr[gslot + j * 32] = fr[j];
-                        if(t[j] < TOPO_TOP)
+#pragma unroll
+                        for(int j = 0; j < JM; ++j)
                         {
-                            const uint32_t lo_row = (t[j] & 0xFFFFu) >> 5, hi_row = t[j] >> 21;
-                            const REAL v0 = fr[j] + lo_n, v1 = fr[j] + hi_n;
+                            uint32_t tp = t[j];
+                            REAL x = fr[j];
+                            if(d > 0)
+                            {
+                                tp = (uint32_t)j < J ? trow[j * 32 + ((lane ^ d) - lane)] : TOPO_PAD;
+                                x = __shfl_xor_sync(0xffffffffu, fr[j], d);
+                            }
+                            const REAL v0 = x + lo_n, v1 = x + hi_n;
+                            const uint32_t lo = tp & 0xFFFFu, hi = tp >> 16;
 #pragma unroll
                             for(int r = 0; r < JM; ++r)
                             {
-                                nx[r] = (lo_row == (uint32_t)r && v0 < nx[r]) ? v0 : nx[r];
-                                nx[r] = (hi_row == (uint32_t)r && v1 < nx[r]) ? v1 : nx[r];
+                                const uint32_t sr = (uint32_t)(r * 32 + lane);
+                                nx[r] = (lo == sr && v0 < nx[r]) ? v0 : nx[r];
+                                nx[r] = (hi == sr && v1 < nx[r]) ? v1 : nx[r];
                             }
                         }
                     }
 #pragma unroll
-                    for(int r = 0; r < JM; ++r) fr[r] = nx[r];
+                    for(int j = 0; j < JM; ++j)
+                    {
+                        if((uint32_t)j < J) a.cfr[gslot + j * 32] = fr[j];
+                        fr[j] = nx[j];
+                    }
                 }
                 else
                 {
+                    REAL ta[JM], tb[JM];
+#pragma unroll
+                    for(int j = 0; j < JM; ++j)
+                    {
+                        const uint32_t lo = t[j] & 0xFFFFu, hi = t[j] >> 16;
+                        if(LOGP == 0)
+                        {   // children live in this lane: select by row (CHILD_BOT / TOP / PAD -> no match)
+                            ta[j] = INF; tb[j] = INF;
+#pragma unroll
+                            for(int r = 0; r < JM; ++r)
+                            {
+                                ta[j] = (lo >> 5) == (uint32_t)r ? fr[r] : ta[j];
+                                tb[j] = (hi >> 5) == (uint32_t)r ? fr[r] : tb[j];
+                            }
+                        }
+                        else
+                        {
+                            ta[j] = lo < CHILD_LIMIT ? nxt[lo] : INF;
+                            tb[j] = hi < CHILD_LIMIT ? nxt[hi] : INF;
+                        }
+                    }
                     if(MODE != MODE_PLAIN)
                     {
-                        const REAL* mine = s_dp + h * J * 32u + lane;       // cost_from_root of this hop's tile
+                        const REAL* mine_dp = s_dp + h * J * 32u + lane;    // cost_from_root of this hop's tile
                         REAL mm0 = INF, mm1 = INF;
 #pragma unroll
                         for(int j = 0; j < JM; ++j)
                         {
-                            if(t[j] < TOPO_TOP)
-                            {
-                                const REAL c = mine[j * 32];
-                                const uint32_t lo_row = (t[j] & 0xFFFFu) >> 5, hi_row = t[j] >> 21;
-                                REAL ta = INF, tb = INF;
-#pragma unroll
-                                for(int r = 0; r < JM; ++r) { ta = lo_row == (uint32_t)r ? fr[r] : ta; tb = hi_row == (uint32_t)r ? fr[r] : tb; }
-                                REAL m0, m1;
-                                if(MODE == MODE_MMA) { m0 = c + lo_c + ta; m1 = c + hi_c + tb; }
-                                else { m0 = c + (ta + lo_c); m1 = c + (tb + hi_c); }
-                                mm0 = m0 < mm0 ? m0 : mm0;
-                                mm1 = m1 < mm1 ? m1 : mm1;
-                            }
+                            const REAL c = (uint32_t)j < J ? mine_dp[j * 32] : INF;
+                            REAL m0, m1;
+                            if(MODE == MODE_MMA) { m0 = c + lo_c + ta[j]; m1 = c + hi_c + tb[j]; }
+                            else { m0 = c + (ta[j] + lo_c); m1 = c + (tb[j] + hi_c); }   // path costs, bdd_cuda_base.cu:636-641
+                            mm0 = m0 < mm0 ? m0 : mm0;
+                            mm1 = m1 < mm1 ? m1 : mm1;
                         }
+                        mm0 = group_min<P>(mm0);
+                        mm1 = group_min<P>(mm1);
                         if(MODE == MODE_MMA)
                         {
                             diff = mm_difference(a.omega, mm0, mm1);
                             lo_n = lo_c + (diff < 0 ? diff : (REAL)0) + d0;
                             hi_n = hi_c + (-diff < 0 ? -diff : (REAL)0) + d1;
                         }
-                        else if(var >= 0)
+                        else if(p == 0 && var >= 0)
                         {
                             a.mm_lo_out[lay] = mm0;
                             a.mm_hi_out[lay] = mm1;
                         }
                     }
-                    REAL nv[JM];
 #pragma unroll
                     for(int j = 0; j < JM; ++j)
                     {
-                        REAL val = t[j] == TOPO_TOP ? (REAL)0 : INF;
-                        if(t[j] < TOPO_TOP)
+                        const REAL vh = hi_n + tb[j], vl = lo_n + ta[j];      // bdd_cuda_parallel_mma.cu:286
+                        REAL val = vh < vl ? vh : vl;                          // +inf for TOPO_PAD
+                        val = t[j] == TOPO_TOP ? (REAL)0 : val;               // set_special_nodes_costs, bdd_cuda_base.cu:217-227
+                        if((uint32_t)j < J)
                         {
-                            const uint32_t lo_row = (t[j] & 0xFFFFu) >> 5, hi_row = t[j] >> 21;
-                            REAL ta = INF, tb = INF;
-#pragma unroll
-                            for(int r = 0; r < JM; ++r) { ta = lo_row == (uint32_t)r ? fr[r] : ta; tb = hi_row == (uint32_t)r ? fr[r] : tb; }
-                            const REAL vh = hi_n + tb, vl = lo_n + ta;
-                            val = vh < vl ? vh : vl;
+                            a.cft[gslot + j * 32] = val;
+                            if(LOGP > 0) cur[j * 32 + lane] = val;
                         }
-                        nv[j] = val;
-                        if((uint32_t)j < J) a.cft[gslot + j * 32] = val;
+                        if(LOGP == 0) fr[j] = (uint32_t)j < J ? val : INF;
                     }
-#pragma unroll
-                    for(int r = 0; r < JM; ++r) fr[r] = nv[r];
                 }
             }
             else if(FORWARD)
@@ -536,14 +582,14 @@ __device__ __forceinline__ void sweep_bundle(const SweepArgs<REAL>& a, const Bun
             {
                 if(MODE != MODE_PLAIN)
                 {
-                    const REAL* mine = s_dp + h * J * 32u + lane;   // cost_from_root of this hop's tile
+                    const REAL* mine_dp = s_dp + h * J * 32u + lane;   // cost_from_root of this hop's tile
                     REAL mm0 = INF, mm1 = INF;
                     for(uint32_t j = 0; j < J; ++j)
                     {
                         const uint32_t t = trow[j * 32];
                         if(t < TOPO_TOP)
                         {
-                            const REAL c = mine[j * 32];
+                            const REAL c = mine_dp[j * 32];
                             const uint32_t lo = t & 0xFFFFu, hi = t >> 16;
                             const REAL ta = lo == CHILD_BOT ? INF : nxt[lo];
                             const REAL tb = hi == CHILD_BOT ? INF : nxt[hi];
@@ -590,13 +636,10 @@ __device__ __forceinline__ void sweep_bundle(const SweepArgs<REAL>& a, const Bun
                 R2 o; o.x = lo_n; o.y = hi_n;
                 a.lohi_out[lay] = o;
                 a.mmd[lay] = diff;
-                if(a.accumulate)
-                {   // compute_delta_atomic, bdd_cuda_parallel_mma.cu:358-376
-                    if(diff > 0) atomicAdd(a.delta_out + 2 * (size_t)var + 1, diff);
-                    else if(diff < 0) atomicAdd(a.delta_out + 2 * (size_t)var, -diff);
-                }
+                // compute_delta_atomic, bdd_cuda_parallel_mma.cu:358-376: |diff| goes to the hi slot if diff > 0, else to lo
+                if(a.accumulate && diff != 0) atomicAdd(a.delta_out + 2 * (size_t)var + (diff > 0 ? 1 : 0), fabs(diff));
             }
-            if(JMAX == 0)
+            if(SMEM_FRONTIER)
             {
                 if(P > 1) __syncwarp();
                 REAL* tmp = cur; cur = nxt; nxt = tmp;
@@ -604,15 +647,13 @@ __device__ __forceinline__ void sweep_bundle(const SweepArgs<REAL>& a, const Bun
         }
 
         __syncwarp();                                   // every lane is done with stage i % NS
+        stamp();   // 5 + 2i: chunk i computed
         if(i + NS < nc) issue(i + NS, get_chunk(i + NS, i + 1));
         cr = cr_next;
     }
 
-    if(!FORWARD && p == 0)
-    {
-        const int32_t bi = a.bundle_bdd[bd.bdd_base + bl];
-        if(bi >= 0) a.bdd_lb[bi] = JMAX > 0 ? fr[0] : nxt[lane];   // root = node 0 of hop 0
-    }
+    if(!FORWARD && p == 0 && bdd_index >= 0)
+        a.bdd_lb[bdd_index] = SMEM_FRONTIER ? nxt[lane] : fr[0];   // root = node 0 of hop 0
 }
 
 template<typename REAL, int MODE, bool FORWARD>
@@ -621,33 +662,60 @@ __global__ void __launch_bounds__(512, 1) sweep_kernel(const SweepArgs<REAL> a)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wpc = blockDim.x >> 5;
-    if(MODE == MODE_MMA && a.zero_buf != nullptr)
-        for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_zero; i += gridDim.x * blockDim.x)
-            a.zero_buf[i] = 0;
+    REAL* inv_tab = reinterpret_cast<REAL*>(smem_raw);       // 1 / n for n < INV_TAB, shared by the CTA
+    if(MODE == MODE_MMA)
+    {
+        if(a.zero_buf != nullptr)
+            for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_zero; i += gridDim.x * blockDim.x)
+                a.zero_buf[i] = 0;
+        if(a.normalize_in == NORM_RECIPROCAL)
+        {
+            for(int i = threadIdx.x; i < INV_TAB; i += blockDim.x) inv_tab[i] = (REAL)1 / (REAL)(i > 0 ? i : 1);
+            __syncthreads();
+        }
+    }
     uint32_t g = blockIdx.x * wpc + warp;
     if(g >= a.bundle_count) return;
     g += a.bundle_first;
-    unsigned char* wsm = smem_raw + (size_t)warp * a.warp_smem_bytes;
-    const BundleDesc bd = a.bundles[g];
+    unsigned char* wsm = smem_raw + INV_TAB_BYTES + (size_t)warp * a.warp_smem_bytes;
+    if(a.trace && lane == 0)
+    {
+        unsigned long long* tr = a.trace + (size_t)(blockIdx.x * wpc + warp) * TRACE_EVENTS;
+        unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        tr[0] = clock64(); tr[TRACE_EVENTS - 1] = smid;
+    }
+    const uint32_t w = a.desc[(size_t)g * DESC_WORDS + lane];
+    const uint32_t logP = __shfl_sync(0xffffffffu, w, DESC_LOGP);
+    const uint32_t max_J = __shfl_sync(0xffffffffu, w, DESC_MAX_J);
     constexpr int M = (FORWARD && MODE == MODE_MM) ? MODE_PLAIN : MODE;
-    if(bd.logP == 0 && bd.max_J <= 4)
+#define BDDB200_RUN(LP, JX) sweep_bundle<REAL, LP, M, FORWARD, JX>(a, w, wsm, inv_tab, lane)
+    if(logP == 0)
     {
-        if(bd.max_J <= 1) sweep_bundle<REAL, 0, M, FORWARD, 1>(a, bd, wsm, lane);
-        else if(bd.max_J == 2) sweep_bundle<REAL, 0, M, FORWARD, 2>(a, bd, wsm, lane);
-        else sweep_bundle<REAL, 0, M, FORWARD, 4>(a, bd, wsm, lane);
-        return;
+        if(max_J <= 1) BDDB200_RUN(0, 1);
+        else if(max_J == 2) BDDB200_RUN(0, 2);
+        else if(max_J <= 4) BDDB200_RUN(0, 4);
+        else BDDB200_RUN(0, 0);
     }
-#define BDDB200_DISPATCH(LP) \
-    case LP: sweep_bundle<REAL, LP, M, FORWARD>(a, bd, wsm, lane); break;
-    switch(bd.logP)
+    else if(logP <= 3 && max_J <= 2)
     {
-        BDDB200_DISPATCH(0) BDDB200_DISPATCH(1) BDDB200_DISPATCH(2)
-        BDDB200_DISPATCH(3) BDDB200_DISPATCH(4) BDDB200_DISPATCH(5)
-        default: break;
+        if(logP == 1) { if(max_J <= 1) BDDB200_RUN(1, 1); else BDDB200_RUN(1, 2); }
+        else if(logP == 2) { if(max_J <= 1) BDDB200_RUN(2, 1); else BDDB200_RUN(2, 2); }
+        else { if(max_J <= 1) BDDB200_RUN(3, 1); else BDDB200_RUN(3, 2); }
     }
-#undef BDDB200_DISPATCH
+    else
+    {
+        switch(logP)
+        {
+            case 1: BDDB200_RUN(1, 0); break;
+            case 2: BDDB200_RUN(2, 0); break;
+            case 3: BDDB200_RUN(3, 0); break;
+            case 4: BDDB200_RUN(4, 0); break;
+            case 5: BDDB200_RUN(5, 0); break;
+            default: break;
+        }
+    }
+#undef BDDB200_RUN
 }
-
 
 // ------------------------------------------------------------------ small kernels ------
 

@@ -74,6 +74,17 @@ struct BundleDesc {
     uint32_t n_chunks;
 };
 
+// Descriptor block of a bundle: DESC_WORDS 32-bit words that a warp fetches with ONE coalesced
+// 128-byte load (lane l reads word l).  There is one block per bundle and pass direction; the
+// chunk records are listed in the order the pass visits them (forward: first chunk first,
+// backward: last chunk first), so the first DESC_CHUNKS pipeline stages can be started
+// without a second, dependent global load.
+constexpr int DESC_WORDS = 32;
+enum DescWord { DESC_N_CHUNKS = 0, DESC_LOGP = 1, DESC_BDD_BASE = 2, DESC_MAX_J = 3, DESC_CHUNK_BASE = 4,
+                DESC_N_HOPS = 5, DESC_LAYER_BASE = 6, DESC_FIRST_CHUNK = 7 };
+constexpr int DESC_CHUNK_WORDS = 5;   // {slot_off, lay_off, n_hops, J, J_next}
+constexpr int DESC_CHUNKS = 5;
+
 // Shared-memory bytes one chunk occupies in a pipeline stage (worst case over the forward
 // and the backward kernel): topo + the opposite direction's DP values + {var, nr_bdds} +
 // {lo, hi} + gathered {delta_lo, delta_hi}.
@@ -99,6 +110,7 @@ struct HostLayout {
     size_t stage_small = 0, stage_large = 0;          // largest chunk_stage_bytes per class
     std::vector<BundleDesc> bundles;
     std::vector<ChunkRec> chunks;
+    std::vector<uint32_t> desc_fwd, desc_bwd;   // DESC_WORDS per bundle
     std::vector<HopRec> hops;
     std::vector<int32_t> bundle_bdd;     // per bundle lane group: external BDD index or -1
     std::vector<uint32_t> topo;          // per slot
@@ -336,6 +348,24 @@ inline HostLayout build_layout(const bddb200_instruction* instrs, size_t n_instr
         else L.max_tile_large = std::max(L.max_tile_large, bd.max_J * 32u);
         L.max_hops = std::max<size_t>(L.max_hops, pb.n_hops);
         L.bundles.push_back(bd);
+    }
+    L.desc_fwd.assign(L.bundles.size() * DESC_WORDS, 0u);
+    L.desc_bwd.assign(L.bundles.size() * DESC_WORDS, 0u);
+    for(size_t g = 0; g < L.bundles.size(); ++g)
+    {
+        const BundleDesc& bd = L.bundles[g];
+        for(int dir = 0; dir < 2; ++dir)
+        {
+            uint32_t* d = (dir == 0 ? L.desc_fwd.data() : L.desc_bwd.data()) + g * DESC_WORDS;
+            d[DESC_N_CHUNKS] = bd.n_chunks; d[DESC_LOGP] = bd.logP; d[DESC_BDD_BASE] = bd.bdd_base; d[DESC_MAX_J] = bd.max_J;
+            d[DESC_CHUNK_BASE] = bd.chunk_base; d[DESC_N_HOPS] = bd.n_hops; d[DESC_LAYER_BASE] = bd.layer_base;
+            for(uint32_t k = 0; k < (uint32_t)DESC_CHUNKS && k < bd.n_chunks; ++k)
+            {
+                const ChunkRec& c = L.chunks[bd.chunk_base + (dir == 0 ? k : bd.n_chunks - 1 - k)];
+                uint32_t* q = d + DESC_FIRST_CHUNK + DESC_CHUNK_WORDS * k;
+                q[0] = c.slot_off; q[1] = c.lay_off; q[2] = c.n_hops; q[3] = c.J; q[4] = c.J_next;
+            }
+        }
     }
     lay = ((lay + 1) & ~(size_t)1) + 2;     // bulk copies of a chunk's layer range may read one entry past it
     L.n_slots = slot; L.n_lay = lay;

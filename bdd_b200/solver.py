@@ -282,6 +282,13 @@ class bdd_cuda_parallel_mma:
     def synchronize(self):
         check(self.lib.bddb200_synchronize(self.h))
 
+    def trace_pass(self, forward: bool, omega: float = 0.5, max_bundles: int = 1 << 20) -> np.ndarray:
+        """Diagnostics: per-bundle clock64() stamps of one MMA pass, [n_bundles, 16] (include/bdd_b200.h)."""
+        out = np.zeros((max_bundles, 16), dtype=np.uint64)
+        n = C.c_size_t()
+        check(self.lib.bddb200_trace_pass(self.h, int(forward), omega, out.ctypes.data, max_bundles, C.byref(n)))
+        return out[: n.value]
+
     def kernel_launches(self) -> int:
         return self.lib.bddb200_kernel_launches(self.h)
 

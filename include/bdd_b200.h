@@ -169,6 +169,12 @@ size_t bddb200_kernel_launches(const bddb200_solver* s);
  * buffer holding the UN-normalised sums written by the last pass (2 * nr_variables REALs). */
 int bddb200_delta_sum_buffer(bddb200_solver* s, void** sum_dev);
 
+/* Diagnostics: run ONE forward (forward != 0) or backward MMA pass and return, for the first
+ * max_bundles bundles, 16 clock64() stamps each: [0] warp start, [1] descriptor loaded,
+ * [2] first bulk copies issued, [3] first chunk landed, [4+2i] chunk i ready, [5+2i] chunk i
+ * computed, [15] SM id.  The pass is a real one (solver state advances). */
+int bddb200_trace_pass(bddb200_solver* s, int forward, double omega, unsigned long long* out_host, size_t max_bundles, size_t* n_out);
+
 /* Layout statistics computed on the host only (no GPU needed): fills up to n of
  * {slots, layer entries, bundles, real nodes, max hops, max tile slots, small-class bundles,
  *  layers, chunks, largest small-class stage bytes, largest large-class stage bytes}. */
