@@ -15,14 +15,14 @@ FLOAT, DOUBLE = 0, 1
 
 # every symbol include/bdd_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = [
-    "bddb200_default_options", "bddb200_last_error", "bddb200_version", "bddb200_create", "bddb200_destroy",
+    "bddb200_default_options", "bddb200_last_error", "bddb200_version", "bddb200_create", "bddb200_destroy", "bddb200_clone",
     "bddb200_nr_variables", "bddb200_nr_bdds", "bddb200_nr_layers", "bddb200_nr_bdd_nodes", "bddb200_nr_hops",
     "bddb200_precision_of", "bddb200_device_of", "bddb200_nr_bdds_per_var", "bddb200_layer_primal_indices",
     "bddb200_layer_bdd_indices", "bddb200_iteration", "bddb200_iterations", "bddb200_forward_pass",
     "bddb200_backward_pass", "bddb200_forward_mm", "bddb200_backward_mm", "bddb200_normalize_delta",
     "bddb200_get_delta", "bddb200_lower_bound", "bddb200_lower_bound_per_bdd", "bddb200_forward_run",
     "bddb200_backward_run", "bddb200_flush_forward_states", "bddb200_flush_backward_states",
-    "bddb200_update_costs_host", "bddb200_update_costs_dev", "bddb200_set_cost", "bddb200_distribute_delta",
+    "bddb200_update_costs_host", "bddb200_update_costs_host_real", "bddb200_update_costs_dev", "bddb200_set_cost", "bddb200_distribute_delta",
     "bddb200_get_solver_costs", "bddb200_set_solver_costs", "bddb200_primal_objective_host",
     "bddb200_min_marginals", "bddb200_bdds_solution", "bddb200_net_solver_costs", "bddb200_make_dual_feasible",
     "bddb200_gradient_step", "bddb200_synchronize", "bddb200_stream", "bddb200_kernel_launches",
@@ -64,6 +64,7 @@ def load() -> C.CDLL:
         "bddb200_version": (C.c_char_p, []),
         "bddb200_create": (i, [vp, sz, vp, sz, vp, sz, i, C.POINTER(Options), C.POINTER(vp)]),
         "bddb200_destroy": (None, [vp]),
+        "bddb200_clone": (i, [vp, C.POINTER(vp)]),
         "bddb200_nr_variables": (sz, [vp]),
         "bddb200_nr_bdds": (sz, [vp]),
         "bddb200_nr_layers": (sz, [vp]),
@@ -90,6 +91,7 @@ def load() -> C.CDLL:
         "bddb200_flush_backward_states": (None, [vp]),
         "bddb200_update_costs_host": (i, [vp, vp, sz, vp, sz]),
         "bddb200_update_costs_dev": (i, [vp, vp, sz, vp, sz]),
+        "bddb200_update_costs_host_real": (i, [vp, vp, sz, vp, sz]),
         "bddb200_set_cost": (i, [vp, dbl, sz]),
         "bddb200_distribute_delta": (i, [vp]),
         "bddb200_get_solver_costs": (i, [vp, vp, vp, vp]),

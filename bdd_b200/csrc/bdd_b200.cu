@@ -45,6 +45,7 @@ struct DevBuf {
     void alloc(size_t count) { if(p) { cudaFree(p); p = nullptr; } n = count; CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T))); }
     void upload(const std::vector<T>& h, cudaStream_t st) { alloc(h.size()); if(!h.empty()) CUDA_CHECK(cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st)); }
     void zero(cudaStream_t st) { if(n) CUDA_CHECK(cudaMemsetAsync(p, 0, n * sizeof(T), st)); }
+    void clone_from(const DevBuf& o, cudaStream_t st) { alloc(o.n); if(o.n) CUDA_CHECK(cudaMemcpyAsync(p, o.p, o.n * sizeof(T), cudaMemcpyDeviceToDevice, st)); }
 };
 
 inline unsigned blocks_for(size_t n, unsigned t = 256) { return (unsigned)((n + t - 1) / t); }
@@ -79,6 +80,7 @@ struct bddb200_solver {
     virtual void flush_forward() = 0;
     virtual void flush_backward() = 0;
     virtual void update_costs_host(const double* lo, size_t n_lo, const double* hi, size_t n_hi) = 0;
+    virtual void update_costs_host_real(const void* lo, size_t n_lo, const void* hi, size_t n_hi) = 0;
     virtual void update_costs_dev(const void* lo, size_t n_lo, const void* hi, size_t n_hi) = 0;
     virtual void set_cost(double c, size_t var) = 0;
     virtual void distribute_delta() = 0;
@@ -95,6 +97,7 @@ struct bddb200_solver {
     virtual size_t kernel_launches() const = 0;
     virtual void* delta_sum_buffer() = 0;
     virtual size_t trace_pass(int forward, double omega, unsigned long long* out_host, size_t max_bundles) = 0;
+    virtual bddb200_solver* clone() const = 0;
 };
 
 namespace {
@@ -192,7 +195,7 @@ public:
         for(int i = 0; i < 3; ++i) { d_delta_[i].alloc(2 * n_vars_); d_delta_[i].zero(stream_); }
         d_delta_tmp_.alloc(2 * n_vars_);
         d_bdd_lb_.alloc(n_bdds_);
-        d_lb_partial_.alloc(LB_BLOCKS + 1);
+        d_lb_partial_.alloc(LB_BLOCKS + 2); d_lb_partial_.zero(stream_);
         CUDA_CHECK(cudaMallocHost(&h_lb_, sizeof(double)));
 
         configure_kernels();
@@ -202,11 +205,45 @@ public:
         CUDA_CHECK(cudaStreamSynchronize(stream_));   // host vectors of the layout go out of scope
     }
 
+    // deep copy (the reference class is copyable: all members are thrust::device_vectors)
+    bddb200_solver* clone() const override { return new SolverImpl(*this, 0); }
+    SolverImpl(const SolverImpl& o, int)
+    {
+        precision = o.precision; device = o.device; deterministic_ = o.deterministic_;
+        CUDA_CHECK(cudaSetDevice(device));
+        CUDA_CHECK(cudaStreamSynchronize(o.stream_));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking)); own_stream_ = true;
+        n_sms_ = o.n_sms_; max_optin_ = o.max_optin_; warps_per_cta_ = o.warps_per_cta_; forced_wpc_ = o.forced_wpc_;
+        n_stages_ = o.n_stages_; n_stages_large_ = o.n_stages_large_;
+        stage_small_ = o.stage_small_; stage_large_ = o.stage_large_; warp_smem_small_ = o.warp_smem_small_; warp_smem_large_ = o.warp_smem_large_;
+        n_vars_ = o.n_vars_; n_bdds_ = o.n_bdds_; n_instr_ = o.n_instr_; n_ext_ = o.n_ext_; n_slots_ = o.n_slots_; n_lay_ = o.n_lay_;
+        max_hops_ = o.max_hops_; n_bundles_ = o.n_bundles_; n_small_ = o.n_small_; tile_small_ = o.tile_small_; tile_large_ = o.tile_large_;
+        h_nr_bdds_per_var_ = o.h_nr_bdds_per_var_; h_ext_var_ = o.h_ext_var_; h_ext_bdd_ = o.h_ext_bdd_;
+        d_bundles_.clone_from(o.d_bundles_, stream_); d_chunks_.clone_from(o.d_chunks_, stream_);
+        d_desc_fwd_.clone_from(o.d_desc_fwd_, stream_); d_desc_bwd_.clone_from(o.d_desc_bwd_, stream_);
+        d_hops_.clone_from(o.d_hops_, stream_); d_topo_.clone_from(o.d_topo_, stream_); d_bdd_bundle_.clone_from(o.d_bdd_bundle_, stream_);
+        d_ext2lay_.clone_from(o.d_ext2lay_, stream_); d_bdd_ext_begin_.clone_from(o.d_bdd_ext_begin_, stream_);
+        d_var_lay_begin_.clone_from(o.d_var_lay_begin_, stream_); d_var_lay_.clone_from(o.d_var_lay_, stream_); d_sorted_ext_.clone_from(o.d_sorted_ext_, stream_);
+        d_lay_vn_.clone_from(o.d_lay_vn_, stream_); d_bundle_bdd_.clone_from(o.d_bundle_bdd_, stream_);
+        d_ext_var_.clone_from(o.d_ext_var_, stream_); d_ext_bdd_.clone_from(o.d_ext_bdd_, stream_); d_nr_bdds_.clone_from(o.d_nr_bdds_, stream_);
+        d_cfr_.clone_from(o.d_cfr_, stream_); d_cft_.clone_from(o.d_cft_, stream_);
+        for(int i = 0; i < 2; ++i) d_lohi_[i].clone_from(o.d_lohi_[i], stream_);
+        d_mmd_.clone_from(o.d_mmd_, stream_); d_mm_lo_.clone_from(o.d_mm_lo_, stream_); d_mm_hi_.clone_from(o.d_mm_hi_, stream_);
+        for(int i = 0; i < 3; ++i) d_delta_[i].clone_from(o.d_delta_[i], stream_);
+        d_delta_tmp_.clone_from(o.d_delta_tmp_, stream_); d_bdd_lb_.clone_from(o.d_bdd_lb_, stream_); d_lb_partial_.clone_from(o.d_lb_partial_, stream_);
+        CUDA_CHECK(cudaMallocHost(&h_lb_, sizeof(double)));
+        cc_ = o.cc_; dcur_ = o.dcur_; delta_needs_norm_ = o.delta_needs_norm_;
+        forward_valid_ = o.forward_valid_; backward_valid_ = o.backward_valid_; lb_valid_ = o.lb_valid_; lb_ = o.lb_;
+        configure_kernels();
+        CUDA_CHECK(cudaStreamSynchronize(stream_));
+    }
+
     ~SolverImpl() override
     {
         cudaSetDevice(device);
         if(graph_exec_) cudaGraphExecDestroy(graph_exec_);
         if(h_lb_) cudaFreeHost(h_lb_);
+        if(h_stage_) { cudaFreeHost(h_stage_); cudaEventDestroy(stage_free_); }
         if(own_stream_ && stream_) cudaStreamDestroy(stream_);
     }
 
@@ -286,6 +323,11 @@ public:
         }
     }
 
+    void zero_lb_sum()
+    {
+        if(!deterministic_) CUDA_CHECK(cudaMemsetAsync(d_lb_partial_.p + LB_BLOCKS + 1, 0, sizeof(double), stream_));
+    }
+
     SweepArgs<REAL> base_args() const
     {
         SweepArgs<REAL> a{};
@@ -295,6 +337,7 @@ public:
         a.lohi_in = reinterpret_cast<const R2*>(d_lohi_[cc_].p); a.lohi_out = reinterpret_cast<R2*>(d_lohi_[cc_ ^ 1].p);
         a.mmd = d_mmd_.p; a.mm_lo_out = d_mm_lo_.p; a.mm_hi_out = d_mm_hi_.p; a.bdd_lb = d_bdd_lb_.p;
         a.omega = 0; a.n_zero = (uint32_t)(2 * n_vars_); a.trace = trace_;
+        a.lb_sum = deterministic_ ? nullptr : d_lb_partial_.p + LB_BLOCKS + 1;
         return a;
     }
 
@@ -468,6 +511,7 @@ public:
         set_device();
         if(backward_valid_) return;
         SweepArgs<REAL> a = base_args();
+        zero_lb_sum();
         launch_sweep<MODE_PLAIN, false>(a);
         backward_valid_ = true; lb_valid_ = false;
     }
@@ -480,10 +524,15 @@ public:
         backward_run();
         if(!lb_valid_)
         {
-            lb_partial_kernel<REAL><<<LB_BLOCKS, 256, 0, stream_>>>(d_bdd_lb_.p, d_lb_partial_.p, (uint32_t)n_bdds_);
-            lb_final_kernel<<<1, 256, 0, stream_>>>(d_lb_partial_.p, d_lb_partial_.p + LB_BLOCKS, LB_BLOCKS);
-            launches_ += 2;
-            CUDA_CHECK(cudaMemcpyAsync(h_lb_, d_lb_partial_.p + LB_BLOCKS, sizeof(double), cudaMemcpyDeviceToHost, stream_));
+            const double* src = d_lb_partial_.p + LB_BLOCKS + 1;      // accumulated by the backward sweep itself
+            if(deterministic_)
+            {   // fixed-shape two-stage tree over the per-BDD values (bit-reproducible)
+                lb_partial_kernel<REAL><<<LB_BLOCKS, 256, 0, stream_>>>(d_bdd_lb_.p, d_lb_partial_.p, (uint32_t)n_bdds_);
+                lb_final_kernel<<<1, 256, 0, stream_>>>(d_lb_partial_.p, d_lb_partial_.p + LB_BLOCKS, LB_BLOCKS);
+                launches_ += 2;
+                src = d_lb_partial_.p + LB_BLOCKS;
+            }
+            CUDA_CHECK(cudaMemcpyAsync(h_lb_, src, sizeof(double), cudaMemcpyDeviceToHost, stream_));
             CUDA_CHECK(cudaStreamSynchronize(stream_));
             lb_ = *h_lb_; lb_valid_ = true;
         }
@@ -498,24 +547,33 @@ public:
     }
 
     // ---------------------------------------------------------------- costs -------------
-    void update_costs_host(const double* lo, size_t n_lo, const double* hi, size_t n_hi) override
+    // Host cost vectors go through a pinned staging buffer (converted to REAL on the way), one
+    // H2D copy and one kernel, all asynchronous; the caller's arrays are free on return.
+    template<typename SRC>
+    void update_costs_host_impl(const SRC* lo, size_t n_lo, const SRC* hi, size_t n_hi)
     {
         set_device();
-        auto up = [&](const double* c, size_t n, REAL* dst) {
-            if(n == 0) return;
-            if(n > n_vars_) throw api_error(BDDB200_ERR_INVALID_ARGUMENT, "more costs than variables");
-            std::vector<REAL> h(n);
-            for(size_t i = 0; i < n; ++i) h[i] = (REAL)c[i];     // device_vector<REAL>(cost_begin, cost_end), bdd_cuda_base.cu:485
-            DevBuf<REAL> d; d.upload(h, stream_);
-            update_costs_kernel<REAL><<<blocks_for(n_lay_), 256, 0, stream_>>>(d_lay_vn_.p, dst, d.p, (uint32_t)n, (uint32_t)n_lay_);
-            ++launches_;
-            CUDA_CHECK(cudaGetLastError());
-            CUDA_CHECK(cudaStreamSynchronize(stream_));
-        };
-        up(lo, n_lo, d_lohi_[cc_].p);
-        up(hi, n_hi, d_lohi_[cc_].p + 1);
+        if(n_lo > n_vars_ || n_hi > n_vars_) throw api_error(BDDB200_ERR_INVALID_ARGUMENT, "more costs than variables");
+        if(n_lo + n_hi == 0) return;
+        if(h_stage_ == nullptr)
+        {
+            CUDA_CHECK(cudaMallocHost(&h_stage_, sizeof(REAL) * 2 * std::max<size_t>(n_vars_, 1)));
+            d_stage_.alloc(2 * n_vars_);
+            CUDA_CHECK(cudaEventCreateWithFlags(&stage_free_, cudaEventDisableTiming));
+        }
+        else CUDA_CHECK(cudaEventSynchronize(stage_free_));     // previous upload has left the staging buffer
+        for(size_t i = 0; i < n_lo; ++i) h_stage_[i] = (REAL)lo[i];          // device_vector<REAL>(cost_begin, cost_end), bdd_cuda_base.cu:485
+        for(size_t i = 0; i < n_hi; ++i) h_stage_[n_lo + i] = (REAL)hi[i];
+        CUDA_CHECK(cudaMemcpyAsync(d_stage_.p, h_stage_, sizeof(REAL) * (n_lo + n_hi), cudaMemcpyHostToDevice, stream_));
+        CUDA_CHECK(cudaEventRecord(stage_free_, stream_));
+        update_costs_lohi_kernel<REAL><<<blocks_for(n_lay_), 256, 0, stream_>>>(d_lay_vn_.p, d_lohi_[cc_].p, d_stage_.p, (uint32_t)n_lo, (uint32_t)n_hi, (uint32_t)n_lay_);
+        ++launches_;
+        CUDA_CHECK(cudaGetLastError());
         flush_forward(); flush_backward();
     }
+    void update_costs_host(const double* lo, size_t n_lo, const double* hi, size_t n_hi) override { update_costs_host_impl<double>(lo, n_lo, hi, n_hi); }
+    void update_costs_host_real(const void* lo, size_t n_lo, const void* hi, size_t n_hi) override
+    { update_costs_host_impl<REAL>(static_cast<const REAL*>(lo), n_lo, static_cast<const REAL*>(hi), n_hi); }
     void update_costs_dev(const void* lo, size_t n_lo, const void* hi, size_t n_hi) override
     {
         set_device();
@@ -582,6 +640,7 @@ public:
         set_device();
         forward_run();                                   // bdd_cuda_base.cu:721
         SweepArgs<REAL> a = base_args();
+        zero_lb_sum();
         launch_sweep<MODE_MM, false>(a);                 // backward_run(true), :728
         backward_valid_ = true; lb_valid_ = false;
         const unsigned nb = blocks_for(n_ext_);
@@ -671,6 +730,9 @@ private:
     DevBuf<REAL> d_cfr_, d_cft_, d_lohi_[2], d_mmd_, d_mm_lo_, d_mm_hi_, d_delta_[3], d_delta_tmp_, d_bdd_lb_;
     DevBuf<double> d_lb_partial_;
     double* h_lb_ = nullptr;
+    REAL* h_stage_ = nullptr;            // pinned staging of host cost vectors
+    DevBuf<REAL> d_stage_;
+    cudaEvent_t stage_free_ = nullptr;
 
     unsigned long long* trace_ = nullptr;
     int cc_ = 0;                 // which of the two lo/hi cost buffers is current
@@ -727,6 +789,13 @@ int bddb200_create(const bddb200_instruction* instrs, size_t n_instr, const size
     });
 }
 void bddb200_destroy(bddb200_solver* s) { delete s; }
+int bddb200_clone(const bddb200_solver* s, bddb200_solver** out)
+{
+    if(out == nullptr) { g_last_error = "null argument"; return BDDB200_ERR_INVALID_ARGUMENT; }
+    *out = nullptr;
+    REQUIRE_SOLVER(s);
+    return guarded([&] { *out = s->clone(); });
+}
 
 size_t bddb200_nr_variables(const bddb200_solver* s) { return s ? s->nr_variables() : 0; }
 size_t bddb200_nr_bdds(const bddb200_solver* s) { return s ? s->nr_bdds() : 0; }
@@ -757,6 +826,8 @@ void bddb200_flush_backward_states(bddb200_solver* s) { if(s) s->flush_backward(
 
 int bddb200_update_costs_host(bddb200_solver* s, const double* lo, size_t n_lo, const double* hi, size_t n_hi)
 { REQUIRE_SOLVER(s); return guarded([&] { s->update_costs_host(lo, n_lo, hi, n_hi); }); }
+int bddb200_update_costs_host_real(bddb200_solver* s, const void* lo, size_t n_lo, const void* hi, size_t n_hi)
+{ REQUIRE_SOLVER(s); return guarded([&] { s->update_costs_host_real(lo, n_lo, hi, n_hi); }); }
 int bddb200_update_costs_dev(bddb200_solver* s, const void* lo, size_t n_lo, const void* hi, size_t n_hi)
 { REQUIRE_SOLVER(s); return guarded([&] { s->update_costs_dev(lo, n_lo, hi, n_hi); }); }
 int bddb200_set_cost(bddb200_solver* s, double c, size_t var) { REQUIRE_SOLVER(s); return guarded([&] { s->set_cost(c, var); }); }

@@ -131,6 +131,7 @@ struct SweepArgs {
     REAL* mm_lo_out;           // MODE_MM
     REAL* mm_hi_out;
     REAL* bdd_lb;              // backward: cost_from_terminal of every BDD's root
+    double* lb_sum;            // backward: += sum of the roots' cost_from_terminal (null = off); forward kernels zero it
     REAL omega;
     uint32_t n_zero;
     uint32_t bundle_first, bundle_count;
@@ -652,8 +653,19 @@ __device__ __forceinline__ void sweep_bundle(const SweepArgs<REAL>& a, const uin
         cr = cr_next;
     }
 
-    if(!FORWARD && p == 0 && bdd_index >= 0)
-        a.bdd_lb[bdd_index] = SMEM_FRONTIER ? nxt[lane] : fr[0];   // root = node 0 of hop 0
+    if(!FORWARD)
+    {
+        const REAL root = SMEM_FRONTIER ? nxt[lane] : fr[0];       // root = node 0 of hop 0
+        const bool mine_valid = p == 0 && bdd_index >= 0;
+        if(mine_valid) a.bdd_lb[bdd_index] = root;
+        if(a.lb_sum != nullptr)
+        {   // lower_bound, bdd_cuda_base.cu:1243-1251: sum over BDDs in double
+            double v = mine_valid ? (double)root : 0.0;
+#pragma unroll
+            for(int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if(lane == 0) atomicAdd(a.lb_sum, v);
+        }
+    }
 }
 
 template<typename REAL, int MODE, bool FORWARD>
@@ -663,6 +675,7 @@ __global__ void __launch_bounds__(512, 1) sweep_kernel(const SweepArgs<REAL> a)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wpc = blockDim.x >> 5;
     REAL* inv_tab = reinterpret_cast<REAL*>(smem_raw);       // 1 / n for n < INV_TAB, shared by the CTA
+    if(FORWARD && a.lb_sum != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *a.lb_sum = 0.0;
     if(MODE == MODE_MMA)
     {
         if(a.zero_buf != nullptr)
@@ -757,6 +770,19 @@ __global__ void update_costs_kernel(const int2* __restrict__ lay_vn, REAL* __res
     if(vn.x < 0) return;
     if((uint32_t)vn.x >= n_c) { cost[2 * (size_t)i] = 0; return; }
     cost[2 * (size_t)i] += c[vn.x] / (REAL)vn.y;
+}
+
+// both cost vectors in one launch (host path): c = [lo costs (n_lo) | hi costs (n_hi)]
+template<typename REAL>
+__global__ void update_costs_lohi_kernel(const int2* __restrict__ lay_vn, REAL* __restrict__ lohi, const REAL* __restrict__ c, uint32_t n_lo, uint32_t n_hi, uint32_t n_lay)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n_lay) return;
+    const int2 vn = lay_vn[i];
+    if(vn.x < 0) return;
+    const REAL n = (REAL)vn.y;
+    if(n_lo > 0) { if((uint32_t)vn.x >= n_lo) lohi[2 * (size_t)i] = 0; else lohi[2 * (size_t)i] += c[vn.x] / n; }
+    if(n_hi > 0) { if((uint32_t)vn.x >= n_hi) lohi[2 * (size_t)i + 1] = 0; else lohi[2 * (size_t)i + 1] += c[n_lo + vn.x] / n; }
 }
 
 // set_var_cost_func, bdd_cuda_base.cu:425-452

@@ -203,10 +203,23 @@ class bdd_cuda_parallel_mma:
             check(self.lib.bddb200_update_costs_dev(self.h, self._in(lo).data_ptr() if nlo else None, nlo,
                                                     self._in(hi).data_ptr() if nhi else None, nhi))
             return
-        lo = np.ascontiguousarray(cost_delta_0 if cost_delta_0 is not None else [], dtype=np.float64)
-        hi = np.ascontiguousarray(cost_delta_1 if cost_delta_1 is not None else [], dtype=np.float64)
-        check(self.lib.bddb200_update_costs_host(self.h, lo.ctypes.data if lo.size else None, lo.size,
-                                                 hi.ctypes.data if hi.size else None, hi.size))
+        def as_host(x):
+            if x is None:
+                return None
+            if isinstance(x, np.ndarray) and x.dtype == self.np_type and x.flags.c_contiguous:
+                return x
+            return np.ascontiguousarray(x, dtype=np.float64)
+        lo, hi = as_host(cost_delta_0), as_host(cost_delta_1)
+        real = [a.dtype == self.np_type for a in (lo, hi) if a is not None and a.size]
+        if real and all(real) and self.np_type != np.float64:
+            fn = self.lib.bddb200_update_costs_host_real      # std::vector<REAL> overload
+        else:
+            lo = None if lo is None else np.ascontiguousarray(lo, dtype=np.float64)
+            hi = None if hi is None else np.ascontiguousarray(hi, dtype=np.float64)
+            fn = self.lib.bddb200_update_costs_host
+        nlo = 0 if lo is None else lo.size
+        nhi = 0 if hi is None else hi.size
+        check(fn(self.h, lo.ctypes.data if nlo else None, nlo, hi.ctypes.data if nhi else None, nhi))
 
     def set_cost(self, c: float, var: int):
         check(self.lib.bddb200_set_cost(self.h, c, var))

@@ -327,8 +327,8 @@ def run_ours(args):
 
     # ---- e2e: host buffers every step -----------------------------------------------------------
     rng = np.random.default_rng(123)
-    pert = rng.integers(-1, 2, size=V).astype(np.float64)
-    zeros = np.zeros(V, dtype=np.float64)
+    pert = rng.integers(-1, 2, size=V).astype(local.np_type)     # std::vector<REAL> overload of update_costs
+    zeros = np.zeros(V, dtype=local.np_type)
     e2e_steps = K
     for k in range(3):
         local.update_costs(zeros, pert if k % 2 == 0 else -pert)

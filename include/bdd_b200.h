@@ -5,7 +5,7 @@
  * LPMP::bdd_cuda_parallel_mma<REAL> (include/bdd_solver/bdd_cuda_parallel_mma.h:7-52) and
  * its base LPMP::bdd_cuda_base<REAL> (include/bdd_solver/bdd_cuda_base.h:57-226) by duck
  * typing.  Every entry point below is what a method of those two classes binds to; the
- * header-only shim bdd_b200/csrc/host/bdd_cuda_parallel_mma.h re-creates the class on top
+ * header-only shim bdd_b200/csrc/host/bdd_solver/bdd_cuda_parallel_mma.h re-creates the class on top
  * of this ABI, and bdd_b200/solver.py is the ctypes mirror.
  *
  * Conventions
@@ -93,6 +93,9 @@ int bddb200_create(const bddb200_instruction* instrs_host, size_t n_instr,
                    const double* costs_hi_host, size_t n_costs,
                    int precision, const bddb200_options* opts, bddb200_solver** out);
 void bddb200_destroy(bddb200_solver* s);
+/* copy constructor of the reference class (all its members are thrust::device_vectors): a deep
+ * copy with its own stream on the same device */
+int bddb200_clone(const bddb200_solver* s, bddb200_solver** out);
 
 /* ---- sizes (bdd_cuda_base.h:101-117) -------------------------------------------------- */
 size_t bddb200_nr_variables(const bddb200_solver* s);
@@ -138,6 +141,10 @@ void bddb200_flush_backward_states(bddb200_solver* s);
 /* ---- costs ----------------------------------------------------------------------------
  * update_costs (bdd_cuda_base.cu:476-558): cost[layer] += c[var] / nr_bdds(var). */
 int bddb200_update_costs_host(bddb200_solver* s, const double* lo_host, size_t n_lo, const double* hi_host, size_t n_hi);
+/* update_costs(const std::vector<REAL>&, const std::vector<REAL>&) (bdd_cuda_base.cu:519-523): host
+ * arrays of the solver's REAL type.  Both host variants stage through pinned memory and return
+ * without waiting for the device; the caller's arrays may be reused immediately. */
+int bddb200_update_costs_host_real(bddb200_solver* s, const void* lo_host, size_t n_lo, const void* hi_host, size_t n_hi);
 int bddb200_update_costs_dev(bddb200_solver* s, const void* lo_dev, size_t n_lo, const void* hi_dev, size_t n_hi);
 int bddb200_set_cost(bddb200_solver* s, double c, size_t var);      /* :439-452 */
 /* distribute_delta (bdd_cuda_base.cu:1396-1436) */
