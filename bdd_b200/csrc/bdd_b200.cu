@@ -213,7 +213,7 @@ public:
         CUDA_CHECK(cudaSetDevice(device));
         CUDA_CHECK(cudaStreamSynchronize(o.stream_));
         CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking)); own_stream_ = true;
-        n_sms_ = o.n_sms_; max_optin_ = o.max_optin_; warps_per_cta_ = o.warps_per_cta_; forced_wpc_ = o.forced_wpc_;
+        n_sms_ = o.n_sms_; max_optin_ = o.max_optin_; warps_per_cta_ = o.warps_per_cta_; grid_small_ = o.grid_small_; forced_wpc_ = o.forced_wpc_;
         n_stages_ = o.n_stages_; n_stages_large_ = o.n_stages_large_;
         stage_small_ = o.stage_small_; stage_large_ = o.stage_large_; warp_smem_small_ = o.warp_smem_small_; warp_smem_large_ = o.warp_smem_large_;
         n_vars_ = o.n_vars_; n_bdds_ = o.n_bdds_; n_instr_ = o.n_instr_; n_ext_ = o.n_ext_; n_slots_ = o.n_slots_; n_lay_ = o.n_lay_;
@@ -266,7 +266,7 @@ public:
         {
             a.bundle_first = 0; a.bundle_count = (uint32_t)n_small_; a.tile_slots = tile_small_;
             a.stage_bytes = stage_small_; a.n_stages = n_stages_; a.warp_smem_bytes = warp_smem_small_;
-            kern<<<blocks_for(n_small_, warps_per_cta_), warps_per_cta_ * 32, INV_TAB_BYTES + (size_t)warps_per_cta_ * warp_smem_small_, stream_>>>(a);
+            kern<<<grid_small_, warps_per_cta_ * 32, INV_TAB_BYTES + (size_t)warps_per_cta_ * warp_smem_small_, stream_>>>(a);
             ++launches_;
         }
         if(n_bundles_ > n_small_)
@@ -295,10 +295,14 @@ public:
         if(n_small_ > 0 && warp_smem_small_ > budget)
             throw api_error(BDDB200_ERR_TOO_WIDE, "stage_bytes * n_stages does not fit the shared memory of one SM");
         const unsigned max_wps = (unsigned)std::max<size_t>(1, std::min<size_t>(16, budget / std::max<uint32_t>(warp_smem_small_, 1u)));
-        if(forced_wpc_) warps_per_cta_ = std::min(forced_wpc_, max_wps);
+        // the kernel deals the bundles evenly over the CTAs (each gets floor or ceil of n / grid)
+        if(forced_wpc_) { warps_per_cta_ = std::min(forced_wpc_, max_wps); grid_small_ = blocks_for(n_small_, warps_per_cta_); }
         else if(n_small_ <= (size_t)n_sms_ * max_wps)
-            warps_per_cta_ = (unsigned)std::max<size_t>(1, (n_small_ + n_sms_ - 1) / n_sms_);   // less than one wave: one CTA per SM
-        else warps_per_cta_ = std::min(4u, max_wps);
+        {   // less than one wave: one CTA on every SM
+            grid_small_ = (unsigned)std::max<size_t>(1, std::min<size_t>(n_small_, (size_t)n_sms_));
+            warps_per_cta_ = (unsigned)std::max<size_t>(1, (n_small_ + grid_small_ - 1) / grid_small_);
+        }
+        else { warps_per_cta_ = std::min(4u, max_wps); grid_small_ = blocks_for(n_small_, warps_per_cta_); }
         if(n_bundles_ > n_small_)
         {
             n_stages_large_ = n_stages_;
@@ -714,7 +718,7 @@ private:
     bool own_stream_ = false;
     bool deterministic_ = false;
     int n_sms_ = 0, max_optin_ = 0;
-    unsigned warps_per_cta_ = 4, forced_wpc_ = 0, n_stages_ = 3, n_stages_large_ = 2;
+    unsigned warps_per_cta_ = 4, grid_small_ = 1, forced_wpc_ = 0, n_stages_ = 3, n_stages_large_ = 2;
     uint32_t stage_small_ = 0, stage_large_ = 0, warp_smem_small_ = 0, warp_smem_large_ = 0;
     size_t n_vars_ = 0, n_bdds_ = 0, n_instr_ = 0, n_ext_ = 0, n_slots_ = 0, n_lay_ = 0, max_hops_ = 0, n_bundles_ = 0, n_small_ = 0;
     uint32_t tile_small_ = 32, tile_large_ = 0;

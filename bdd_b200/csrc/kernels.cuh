@@ -687,8 +687,11 @@ __global__ void __launch_bounds__(512, 1) sweep_kernel(const SweepArgs<REAL> a)
             __syncthreads();
         }
     }
-    uint32_t g = blockIdx.x * wpc + warp;
-    if(g >= a.bundle_count) return;
+    // bundles are dealt evenly over the CTAs: CTA b owns [b*n/G, (b+1)*n/G), at most blockDim.x/32 of them
+    const uint32_t g_lo = (uint32_t)(((uint64_t)blockIdx.x * a.bundle_count) / gridDim.x);
+    const uint32_t g_hi = (uint32_t)(((uint64_t)(blockIdx.x + 1) * a.bundle_count) / gridDim.x);
+    uint32_t g = g_lo + warp;
+    if(g >= g_hi) return;
     g += a.bundle_first;
     unsigned char* wsm = smem_raw + INV_TAB_BYTES + (size_t)warp * a.warp_smem_bytes;
     if(a.trace && lane == 0)

@@ -51,10 +51,10 @@ def make_instance(n_shards: int, workload: str):
         col, costs = instances.set_cover(m=25000 * n_shards, n=50000 * n_shards, k=20, seed=1)
         return col, costs, "float"
     if workload == "qap_5m":
-        col, costs = instances.qap(n=36, seed=2)
+        col, costs = instances.qap(n=40, seed=2)       # 5.06 M nodes
         return col, costs, "double"
     if workload == "grid_mrf_20m":
-        col, costs = instances.grid_mrf(260, 260, 4, seed=4)
+        col, costs = instances.grid_mrf(283, 283, 4, seed=4)   # 20.0 M nodes
         return col, costs, "float"
     if workload == "assignment_5m":
         col, costs = instances.assignment(1118, seed=3)
@@ -418,7 +418,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="set_cover_1m")
+    ap.add_argument("--workload", default=os.environ.get("BENCH_WORKLOAD", "set_cover_1m"))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
