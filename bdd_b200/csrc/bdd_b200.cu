@@ -131,7 +131,10 @@ public:
 
         int lanes_per_bdd = opt.lanes_per_bdd;
         if(const char* e = std::getenv("BDDB200_LANES_PER_BDD")) lanes_per_bdd = std::atoi(e);
-        HostLayout L = build_layout(instrs, n_instr, delims, n_bdds, lanes_per_bdd, opt.nr_variables, sizeof(REAL), stage_budget);
+        bool lane_class = true;       // BDDB200_NO_LANE=1: run narrow one-lane-per-BDD bundles through the generic kernel (A/B checks)
+        if(const char* e = std::getenv("BDDB200_NO_LANE")) lane_class = std::atoi(e) == 0;
+        HostLayout L = build_layout(instrs, n_instr, delims, n_bdds, lanes_per_bdd, opt.nr_variables, sizeof(REAL), stage_budget, lane_class);
+        n_lane_ = L.n_lane_bundles; lane_max_J_ = L.lane_max_J; lane_max_hops_ = L.lane_max_hops;
         n_vars_ = L.n_vars; n_bdds_ = L.n_bdds; n_instr_ = delims[n_bdds] - delims[0];
         n_ext_ = L.n_layers_ext; n_slots_ = L.n_slots; n_lay_ = L.n_lay; max_hops_ = L.max_hops;
         n_bundles_ = L.bundles.size(); n_small_ = L.n_small_bundles;
@@ -152,6 +155,10 @@ public:
         }
         h_ext_var_ = L.ext_var; h_ext_bdd_ = L.ext_bdd;
 
+        // the lane-class kernels normalise through a reciprocal table; a variable shared by more BDDs than it holds
+        // switches the solver to exact division + fixed-order sums (the deterministic kernels)
+        if(n_lane_ > 0 && !h_nr_bdds_per_var_.empty() && *std::max_element(h_nr_bdds_per_var_.begin(), h_nr_bdds_per_var_.end()) >= INV_TAB)
+            deterministic_ = true;
         CUDA_CHECK(cudaDeviceGetAttribute(&max_optin_, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
         CUDA_CHECK(cudaDeviceGetAttribute(&n_sms_, cudaDevAttrMultiProcessorCount, device));
         plan_launch();
@@ -174,6 +181,7 @@ public:
         d_chunks_.upload(L.chunks, stream_);
         d_desc_fwd_.upload(L.desc_fwd, stream_);
         d_desc_bwd_.upload(L.desc_bwd, stream_);
+        d_desc_lane_.upload(L.desc_lane, stream_);
         d_hops_.upload(L.hops, stream_);
         d_topo_.upload(L.topo, stream_);
         d_lay_vn_.upload(lay_vn, stream_);
@@ -187,6 +195,14 @@ public:
         d_var_lay_.upload(L.var_lay, stream_);
         d_sorted_ext_.upload(L.sorted_ext, stream_);
         d_nr_bdds_.upload(h_nr_bdds_per_var_, stream_);
+        {   // reciprocals for the lane-class kernels' normalisation (same rounding as the device division)
+            std::vector<REAL> inv(INV_TAB);
+            for(int i = 0; i < INV_TAB; ++i) inv[i] = (REAL)1 / (REAL)(i > 0 ? i : 1);
+            d_inv_tab_.upload(inv, stream_);
+            const int max_n = h_nr_bdds_per_var_.empty() ? 0 : *std::max_element(h_nr_bdds_per_var_.begin(), h_nr_bdds_per_var_.end());
+            inv_count_ = (uint32_t)std::min<int>(INV_TAB, std::max(max_n, 0) + 1);
+        }
+        if(const char* e = std::getenv("BDDB200_NO_PDL")) pdl_ = std::atoi(e) == 0;
 
         d_cfr_.alloc(n_slots_); d_cft_.alloc(n_slots_);
         for(int i = 0; i < 2; ++i) { d_lohi_[i].alloc(2 * n_lay_); d_lohi_[i].zero(stream_); }
@@ -215,12 +231,14 @@ public:
         CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking)); own_stream_ = true;
         n_sms_ = o.n_sms_; max_optin_ = o.max_optin_; warps_per_cta_ = o.warps_per_cta_; grid_small_ = o.grid_small_; forced_wpc_ = o.forced_wpc_;
         n_stages_ = o.n_stages_; n_stages_large_ = o.n_stages_large_;
+        n_lane_ = o.n_lane_; lane_max_J_ = o.lane_max_J_; lane_max_hops_ = o.lane_max_hops_; lane_wpc_ = o.lane_wpc_; lane_grid_ = o.lane_grid_;
+        lane_chunk_hops_ = o.lane_chunk_hops_; lane_stages_ = o.lane_stages_; lane_stage_bytes_ = o.lane_stage_bytes_; lane_warp_smem_ = o.lane_warp_smem_;
         stage_small_ = o.stage_small_; stage_large_ = o.stage_large_; warp_smem_small_ = o.warp_smem_small_; warp_smem_large_ = o.warp_smem_large_;
         n_vars_ = o.n_vars_; n_bdds_ = o.n_bdds_; n_instr_ = o.n_instr_; n_ext_ = o.n_ext_; n_slots_ = o.n_slots_; n_lay_ = o.n_lay_;
         max_hops_ = o.max_hops_; n_bundles_ = o.n_bundles_; n_small_ = o.n_small_; tile_small_ = o.tile_small_; tile_large_ = o.tile_large_;
         h_nr_bdds_per_var_ = o.h_nr_bdds_per_var_; h_ext_var_ = o.h_ext_var_; h_ext_bdd_ = o.h_ext_bdd_;
         d_bundles_.clone_from(o.d_bundles_, stream_); d_chunks_.clone_from(o.d_chunks_, stream_);
-        d_desc_fwd_.clone_from(o.d_desc_fwd_, stream_); d_desc_bwd_.clone_from(o.d_desc_bwd_, stream_);
+        d_desc_fwd_.clone_from(o.d_desc_fwd_, stream_); d_desc_bwd_.clone_from(o.d_desc_bwd_, stream_); d_desc_lane_.clone_from(o.d_desc_lane_, stream_);
         d_hops_.clone_from(o.d_hops_, stream_); d_topo_.clone_from(o.d_topo_, stream_); d_bdd_bundle_.clone_from(o.d_bdd_bundle_, stream_);
         d_ext2lay_.clone_from(o.d_ext2lay_, stream_); d_bdd_ext_begin_.clone_from(o.d_bdd_ext_begin_, stream_);
         d_var_lay_begin_.clone_from(o.d_var_lay_begin_, stream_); d_var_lay_.clone_from(o.d_var_lay_, stream_); d_sorted_ext_.clone_from(o.d_sorted_ext_, stream_);
@@ -230,6 +248,7 @@ public:
         for(int i = 0; i < 2; ++i) d_lohi_[i].clone_from(o.d_lohi_[i], stream_);
         d_mmd_.clone_from(o.d_mmd_, stream_); d_mm_lo_.clone_from(o.d_mm_lo_, stream_); d_mm_hi_.clone_from(o.d_mm_hi_, stream_);
         for(int i = 0; i < 3; ++i) d_delta_[i].clone_from(o.d_delta_[i], stream_);
+        d_inv_tab_.clone_from(o.d_inv_tab_, stream_); inv_count_ = o.inv_count_; pdl_ = o.pdl_;
         d_delta_tmp_.clone_from(o.d_delta_tmp_, stream_); d_bdd_lb_.clone_from(o.d_bdd_lb_, stream_); d_lb_partial_.clone_from(o.d_lb_partial_, stream_);
         CUDA_CHECK(cudaMallocHost(&h_lb_, sizeof(double)));
         cc_ = o.cc_; dcur_ = o.dcur_; delta_needs_norm_ = o.delta_needs_norm_;
@@ -261,20 +280,42 @@ public:
     void launch_sweep(SweepArgs<REAL> a)
     {
         auto kern = sweep_kernel<REAL, MODE, FORWARD>;
+        if(n_lane_ > 0)
+        {   // lane-local class: bundles [0, n_lane)
+            a.desc = reinterpret_cast<const uint32_t*>(d_desc_lane_.p);
+            a.bundle_first = 0; a.bundle_count = (uint32_t)n_lane_; a.tile_slots = 0;
+            a.stage_bytes = lane_stage_bytes_; a.n_stages = lane_stages_; a.chunk_hops = lane_chunk_hops_; a.warp_smem_bytes = lane_warp_smem_;
+            a.inv_tab_g = d_inv_tab_.p; a.inv_count = inv_count_;
+            a.bundles_per_cta = (uint32_t)(n_lane_ / lane_grid_); a.bundles_rem = (uint32_t)(n_lane_ % lane_grid_);
+            a.zero_pairs_per_bundle = (uint32_t)((n_vars_ + n_lane_ - 1) / n_lane_);
+            // programmatic dependent launch: the kernel's start-up (descriptor, static topology, variable indices) overlaps the
+            // tail of the previous kernel in the stream; it waits (griddepcontrol.wait) before touching anything a pass writes
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(lane_grid_); cfg.blockDim = dim3(lane_wpc_ * 32);
+            cfg.dynamicSmemBytes = (size_t)lane_wpc_ * lane_warp_smem_; cfg.stream = stream_;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr; cfg.numAttrs = pdl_ ? 1 : 0;
+            if(MODE == MODE_MMA && deterministic_) CUDA_CHECK(cudaLaunchKernelEx(&cfg, sweep_lane_kernel<REAL, MODE, FORWARD, MODE == MODE_MMA>, a));
+            else CUDA_CHECK(cudaLaunchKernelEx(&cfg, sweep_lane_kernel<REAL, MODE, FORWARD, false>, a));
+            ++launches_;
+            a.zero_buf = nullptr;
+        }
         a.desc = FORWARD ? d_desc_fwd_.p : d_desc_bwd_.p;
         if(n_small_ > 0)
         {
-            a.bundle_first = 0; a.bundle_count = (uint32_t)n_small_; a.tile_slots = tile_small_;
+            a.bundle_first = (uint32_t)n_lane_; a.bundle_count = (uint32_t)n_small_; a.tile_slots = tile_small_;
             a.stage_bytes = stage_small_; a.n_stages = n_stages_; a.warp_smem_bytes = warp_smem_small_;
             kern<<<grid_small_, warps_per_cta_ * 32, INV_TAB_BYTES + (size_t)warps_per_cta_ * warp_smem_small_, stream_>>>(a);
             ++launches_;
         }
-        if(n_bundles_ > n_small_)
+        if(n_bundles_ > n_lane_ + n_small_)
         {
-            a.bundle_first = (uint32_t)n_small_; a.bundle_count = (uint32_t)(n_bundles_ - n_small_); a.tile_slots = tile_large_;
+            a.bundle_first = (uint32_t)(n_lane_ + n_small_); a.bundle_count = (uint32_t)(n_bundles_ - n_lane_ - n_small_); a.tile_slots = tile_large_;
             a.stage_bytes = stage_large_; a.n_stages = n_stages_large_; a.warp_smem_bytes = warp_smem_large_;
             if(n_small_ > 0) a.zero_buf = nullptr;
-            kern<<<(unsigned)(n_bundles_ - n_small_), 32, INV_TAB_BYTES + warp_smem_large_, stream_>>>(a);
+            kern<<<(unsigned)(n_bundles_ - n_lane_ - n_small_), 32, INV_TAB_BYTES + warp_smem_large_, stream_>>>(a);
             ++launches_;
         }
         CUDA_CHECK(cudaGetLastError());
@@ -303,7 +344,8 @@ public:
             warps_per_cta_ = (unsigned)std::max<size_t>(1, (n_small_ + grid_small_ - 1) / grid_small_);
         }
         else { warps_per_cta_ = std::min(4u, max_wps); grid_small_ = blocks_for(n_small_, warps_per_cta_); }
-        if(n_bundles_ > n_small_)
+        if(n_lane_ > 0) plan_lane_launch();
+        if(n_bundles_ > n_lane_ + n_small_)
         {
             n_stages_large_ = n_stages_;
             while(n_stages_large_ > 2 && warp_smem(n_stages_large_, stage_large_, tile_large_) > budget) --n_stages_large_;
@@ -314,8 +356,55 @@ public:
         }
     }
 
+    // Lane-local class: warps per CTA, CTAs per SM, pipeline depth and hops per stage.
+    void plan_lane_launch()
+    {
+        auto env_u = [](const char* name, unsigned dflt) { const char* e = std::getenv(name); return e ? (unsigned)std::atoi(e) : dflt; };
+        const size_t per_hop = lane_hop_bytes(lane_max_J_, sizeof(REAL));
+        lane_stages_ = std::min((unsigned)LANE_MAX_STAGES, std::max(1u, env_u("BDDB200_LANE_STAGES", 2)));
+        unsigned ctas_per_sm = 1;
+        const unsigned forced = env_u("BDDB200_LANE_WARPS_PER_CTA", 0);
+        if(forced) { lane_wpc_ = std::min(forced, 16u); lane_grid_ = blocks_for(n_lane_, lane_wpc_); ctas_per_sm = std::max(1u, env_u("BDDB200_LANE_CTAS_PER_SM", 1)); }
+        else if(n_lane_ <= (size_t)n_sms_ * 8)
+        {   // less than one wave: one CTA on every SM, the shared memory goes into deep stages
+            lane_grid_ = (unsigned)std::min<size_t>(n_lane_, (size_t)n_sms_);
+            lane_wpc_ = (unsigned)((n_lane_ + lane_grid_ - 1) / lane_grid_);
+        }
+        else
+        {   // several waves: as many resident warps as leave every stage about six hops (the per-chunk cost -- four bulk-copy
+            // issues, one batch of gathers -- is about two hops of arithmetic)
+            const size_t warps = std::min<size_t>(16, std::max<size_t>(4, (size_t)(227 * 1024) / (lane_stages_ * 6 * per_hop)));
+            if(warps >= 12) { ctas_per_sm = 2; lane_wpc_ = (unsigned)(warps / 2); } else lane_wpc_ = (unsigned)warps;
+            lane_grid_ = blocks_for(n_lane_, lane_wpc_);
+        }
+        const size_t sm_total = 228 * 1024;                             // per SM; every resident CTA reserves 1 KiB
+        const size_t static_smem = INV_TAB * sizeof(REAL) + 16 * LANE_MAX_STAGES * 8 + 128;   // reciprocal table + mbarriers
+        size_t cta_budget = std::min<size_t>((size_t)max_optin_, sm_total / ctas_per_sm - 1024) - static_smem;
+        const size_t warp_budget = cta_budget / lane_wpc_;
+        size_t hops = (warp_budget - 128) / (lane_stages_ * per_hop);
+        if(hops < 1) throw api_error(BDDB200_ERR_TOO_WIDE, "lane-class stage does not fit the shared memory of one SM");
+        hops = std::min<size_t>(hops, lane_max_hops_);
+        if(const unsigned f = env_u("BDDB200_LANE_CHUNK_HOPS", 0)) hops = std::min<size_t>(hops, f);
+        const size_t nc = (lane_max_hops_ + hops - 1) / hops;
+        hops = (lane_max_hops_ + nc - 1) / nc;                         // chunks of equal length
+        lane_chunk_hops_ = (uint32_t)hops;
+        lane_stage_bytes_ = (uint32_t)(hops * per_hop);
+        lane_warp_smem_ = (uint32_t)((((size_t)lane_stages_ * lane_stage_bytes_) + 127) & ~(size_t)127);
+    }
+
     void configure_kernels()
     {
+        const int need_lane = (int)((size_t)lane_wpc_ * lane_warp_smem_);
+        if(n_lane_ > 0 && need_lane > 40 * 1024)
+        {
+            CUDA_CHECK(cudaFuncSetAttribute(sweep_lane_kernel<REAL, MODE_MMA, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need_lane));
+            CUDA_CHECK(cudaFuncSetAttribute(sweep_lane_kernel<REAL, MODE_MMA, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need_lane));
+            CUDA_CHECK(cudaFuncSetAttribute(sweep_lane_kernel<REAL, MODE_MMA, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, need_lane));
+            CUDA_CHECK(cudaFuncSetAttribute(sweep_lane_kernel<REAL, MODE_MMA, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, need_lane));
+            CUDA_CHECK(cudaFuncSetAttribute(sweep_lane_kernel<REAL, MODE_PLAIN, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need_lane));
+            CUDA_CHECK(cudaFuncSetAttribute(sweep_lane_kernel<REAL, MODE_PLAIN, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need_lane));
+            CUDA_CHECK(cudaFuncSetAttribute(sweep_lane_kernel<REAL, MODE_MM, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need_lane));
+        }
         const int need = (int)(INV_TAB_BYTES + std::max<size_t>((size_t)warps_per_cta_ * warp_smem_small_, warp_smem_large_));
         if(need > 48 * 1024)
         {
@@ -491,8 +580,8 @@ public:
     size_t trace_pass(int forward, double omega, unsigned long long* out_host, size_t max_bundles) override
     {
         set_device();
-        const size_t n = std::min(max_bundles, n_small_);
-        DevBuf<unsigned long long> tr; tr.alloc((n_small_ + 64) * TRACE_EVENTS); tr.zero(stream_);
+        const size_t n = std::min(max_bundles, n_lane_ > 0 ? n_lane_ : n_small_);      // bundles of the first launch
+        DevBuf<unsigned long long> tr; tr.alloc((n_bundles_ + 64) * TRACE_EVENTS); tr.zero(stream_);
         trace_ = tr.p;
         if(forward) forward_pass(omega); else backward_pass(omega);
         trace_ = nullptr;
@@ -718,6 +807,9 @@ private:
     bool own_stream_ = false;
     bool deterministic_ = false;
     int n_sms_ = 0, max_optin_ = 0;
+    size_t n_lane_ = 0;
+    uint32_t lane_max_J_ = 0, lane_max_hops_ = 0, lane_chunk_hops_ = 1, lane_stages_ = 2, lane_stage_bytes_ = 0, lane_warp_smem_ = 0;
+    unsigned lane_wpc_ = 1, lane_grid_ = 1;
     unsigned warps_per_cta_ = 4, grid_small_ = 1, forced_wpc_ = 0, n_stages_ = 3, n_stages_large_ = 2;
     uint32_t stage_small_ = 0, stage_large_ = 0, warp_smem_small_ = 0, warp_smem_large_ = 0;
     size_t n_vars_ = 0, n_bdds_ = 0, n_instr_ = 0, n_ext_ = 0, n_slots_ = 0, n_lay_ = 0, max_hops_ = 0, n_bundles_ = 0, n_small_ = 0;
@@ -727,6 +819,10 @@ private:
     DevBuf<BundleDesc> d_bundles_;
     DevBuf<ChunkRec> d_chunks_;
     DevBuf<uint32_t> d_desc_fwd_, d_desc_bwd_;
+    DevBuf<LaneDesc> d_desc_lane_;
+    DevBuf<REAL> d_inv_tab_;
+    uint32_t inv_count_ = 1;
+    bool pdl_ = true;
     DevBuf<HopRec> d_hops_;
     DevBuf<uint32_t> d_topo_, d_bdd_bundle_, d_ext2lay_, d_bdd_ext_begin_, d_var_lay_begin_, d_var_lay_, d_sorted_ext_;
     DevBuf<int2> d_lay_vn_;
@@ -865,10 +961,10 @@ int bddb200_layout_stats(const bddb200_instruction* instrs, size_t n_instr, cons
 {
     return guarded([&] {
         const HostLayout L = build_layout(instrs, n_instr, delims, n_bdds, lanes_per_bdd);
-        const uint64_t vals[11] = {L.n_slots, L.n_lay, L.bundles.size(), L.n_real_nodes, L.max_hops,
+        const uint64_t vals[13] = {L.n_slots, L.n_lay, L.bundles.size(), L.n_real_nodes, L.max_hops,
                                    std::max(L.max_tile_small, L.max_tile_large), L.n_small_bundles, L.n_layers_ext,
-                                   L.chunks.size(), L.stage_small, L.stage_large};
-        for(size_t i = 0; i < n && i < 11; ++i) out[i] = vals[i];
+                                   L.chunks.size(), L.stage_small, L.stage_large, L.n_lane_bundles, L.n_topo};
+        for(size_t i = 0; i < n && i < 13; ++i) out[i] = vals[i];
     });
 }
 

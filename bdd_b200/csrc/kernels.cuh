@@ -110,7 +110,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template<int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
-constexpr uint32_t INV_TAB_BYTES = 256 * 8;   // INV_TAB REALs, sized for double
+constexpr uint32_t INV_TAB_BYTES = 1024 * 8;   // INV_TAB REALs, sized for double
 constexpr int TRACE_EVENTS = 16;
 
 template<typename REAL>
@@ -138,6 +138,11 @@ struct SweepArgs {
     uint32_t tile_slots;       // capacity of one shared-memory frontier buffer, in slots
     uint32_t stage_bytes;      // capacity of one pipeline stage
     uint32_t n_stages;         // pipeline depth (>= 2)
+    uint32_t chunk_hops;       // lane-class kernel: hops per pipeline stage
+    const REAL* inv_tab_g;     // lane-class kernel: 1 / n for n < inv_count (global memory, copied into shared memory per CTA)
+    uint32_t inv_count;
+    uint32_t bundles_per_cta, bundles_rem;   // lane-class kernel: CTA b owns bundles_per_cta (+1 if b < bundles_rem) consecutive bundles
+    uint32_t zero_pairs_per_bundle;          // lane-class kernel: every warp clears this many {lo, hi} pairs of zero_buf
     uint32_t warp_smem_bytes;  // n_stages * stage_bytes + 2 frontier buffers + mbarriers, rounded to 128
                                // (the CTA's dynamic shared memory starts with the INV_TAB_BYTES reciprocal table)
     unsigned long long* trace; // diagnostics: TRACE_EVENTS clock64() stamps per bundle (null = off)
@@ -158,7 +163,7 @@ __device__ __forceinline__ REAL group_min(REAL v)
 }
 
 enum NormalizeMode { NORM_NONE = 0, NORM_DIVIDE = 1, NORM_RECIPROCAL = 2 };
-constexpr int INV_TAB = 256;
+constexpr int INV_TAB = 1024;
 constexpr uint32_t CHILD_LIMIT = 0xFFE0u;   // child slot indices are below this; CHILD_BOT and the halves of TOPO_TOP / TOPO_PAD are not
 
 // omega * (mm_hi - mm_lo), 0 if either min-marginal is infinite (compute_mm_diff_flush_mm_lo,
@@ -733,6 +738,427 @@ __global__ void __launch_bounds__(512, 1) sweep_kernel(const SweepArgs<REAL> a)
 #undef BDDB200_RUN
 }
 
+// ======================================================================================
+// Lane-local class (layout.hpp, CLS_LANE): one lane per BDD, J <= 4 nodes per layer.
+//
+// A BDD never leaves its lane, so the whole walk is register arithmetic: the frontier
+// (cost_from_root going forward, cost_from_terminal going backward) is J registers per lane,
+// the topology of a (hop, lane) is one word of one-hot arc targets, child look-ups are
+// predicated selects on its bits.  No shuffle, no shared-memory frontier, no __syncwarp inside
+// a chunk, and the hop body is straight-line code (no branch): with about one warp per
+// scheduler the pass time is the per-warp instruction chain, so everything that is not
+// min-plus arithmetic is kept off it.
+// Tiles are uniform (J rows per hop), so every per-hop array of a bundle is contiguous over any
+// range of hops and the chunk size is a launch parameter (chunk_hops).
+// Staging: four lanes issue the four bulk-async copies of a chunk (topology, opposite DP rows,
+// {var, nr_bdds}, {lo, hi}) in one instruction onto the chunk's mbarrier; all lanes gather the
+// chunk's delta values with cp.async one chunk ahead (the first chunk's variables are read
+// straight from global memory so that its gathers overlap its bulk copies); the hop loop reads
+// shared memory one hop ahead of the arithmetic (register double buffer).
+// DET = deterministic mode: exact division by nr_bdds(var), no atomics (delta_segsum_kernel sums).
+// ======================================================================================
+template<typename REAL> __device__ __forceinline__ REAL rmin(REAL a, REAL b);
+template<> __device__ __forceinline__ float rmin<float>(float a, float b) { return fminf(a, b); }
+template<> __device__ __forceinline__ double rmin<double>(double a, double b) { return fmin(a, b); }
+
+// shared-memory load through a 32-bit shared address (a generic pointer makes the compiler rebuild the window base per use)
+template<typename REAL> __device__ __forceinline__ REAL lds_real(uint32_t addr);
+template<> __device__ __forceinline__ float lds_real<float>(uint32_t addr) { float v; asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; }
+template<> __device__ __forceinline__ double lds_real<double>(uint32_t addr) { double v; asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr)); return v; }
+
+// predicated cp.async / red: no branch in the instruction stream
+__device__ __forceinline__ void cp_async_gather_if(bool p, float2* dst, const float* src)
+{
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q cp.async.ca.shared.global [%1], [%2], 8; }"
+                 :: "r"((uint32_t)p), "r"(smem_u32(dst)), "l"(__cvta_generic_to_global(src)) : "memory");
+}
+__device__ __forceinline__ void cp_async_gather_if(bool p, double2* dst, const double* src)
+{
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q cp.async.ca.shared.global [%1], [%2], 16; }"
+                 :: "r"((uint32_t)p), "r"(smem_u32(dst)), "l"(__cvta_generic_to_global(src)) : "memory");
+}
+__device__ __forceinline__ void red_add_if(bool p, float* addr, float v)
+{
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q red.global.add.f32 [%1], %2; }"
+                 :: "r"((uint32_t)p), "l"(__cvta_generic_to_global(addr)), "f"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_if(bool p, double* addr, double v)
+{
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q red.global.add.f64 [%1], %2; }"
+                 :: "r"((uint32_t)p), "l"(__cvta_generic_to_global(addr)), "d"(v) : "memory");
+}
+
+// programmatic dependent launch: everything before pdl_wait() may overlap the tail of the previous kernel in
+// the stream and must not touch anything that kernel reads or writes
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template<typename REAL, int J>
+struct LaneHopIn {
+    uint32_t t;        // one-hot arc targets
+    int var;           // variable, LAY_NONE or LAY_TOP
+    REAL lo, hi;       // arc costs
+    REAL d0, d1;       // normalised delta_in of the layer's variable
+    REAL c[J];         // opposite direction's DP values: forward = cost_from_terminal of the NEXT hop's rows,
+                       // backward = cost_from_root of THIS hop's rows
+};
+
+constexpr int LANE_MAX_STAGES = 4;
+
+template<typename REAL, int J, int MODE, bool FORWARD, bool DET>
+__device__ __forceinline__ void sweep_lane_bundle(const SweepArgs<REAL>& a, const LaneDesc d, const uint32_t bundle_in_launch, unsigned char* wsm, uint64_t* bars, const REAL* inv_tab, const int lane)
+{
+    using R2 = typename real2<REAL>::type;
+    using In = LaneHopIn<REAL, J>;
+    constexpr bool NEED_DP = FORWARD ? (MODE == MODE_MMA) : (MODE != MODE_PLAIN);
+    constexpr bool NEED_DELTA = (MODE == MODE_MMA);
+    constexpr uint32_t R = sizeof(REAL);
+    constexpr uint32_t HOP_TOPO = 128, HOP_DP = J * 32 * R, HOP_VN = 256, HOP_LOHI = 64 * R;
+    const REAL INF = real_inf<REAL>();
+    const uint32_t NS = a.n_stages, n = a.chunk_hops, H = d.n_hops;
+    const uint32_t nc = (H + n - 1) / n;
+    const uint32_t o_dp = n * HOP_TOPO, o_vn = o_dp + n * HOP_DP, o_lohi = o_vn + n * HOP_VN, o_delta = o_lohi + n * HOP_LOHI;
+    unsigned long long* trace = a.trace ? a.trace + (size_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * TRACE_EVENTS : nullptr;
+    uint32_t trace_k = 1;
+    auto stamp = [&]() { if(trace && lane == 0 && trace_k < TRACE_EVENTS) trace[trace_k] = clock64(); ++trace_k; };
+    stamp();   // 1: descriptor arrived
+
+    // pipeline position i <-> chunk ci(i) = hops [ci*n, min(H, ci*n + n))
+    auto chunk_first = [&](uint32_t i) { return (FORWARD ? i : nc - 1 - i) * n; };
+    // positions [i0, i0 + count): lane l starts copy (l & 3) of position i0 + (l >> 2); all in one UBLKCP issue
+    // copies 0 (topology) and 2 ({var, nr_bdds}) are static data, 1 (DP rows) and 3 ({lo, hi}) are written by the previous pass
+    constexpr uint32_t COPY_STATIC = 0x5u, COPY_DYNAMIC = 0xAu, COPY_ALL = 0xFu;
+    auto issue = [&](uint32_t i0, uint32_t count, uint32_t mask) {
+        const uint32_t k = lane >> 2, which = lane & 3;
+        if(k < count && ((mask >> which) & 1u))
+        {
+            const uint32_t i = i0 + k;
+            const uint32_t h0 = chunk_first(i), cnt = min(n, H - h0);
+            unsigned char* st = wsm + (size_t)(i % NS) * a.stage_bytes;
+            uint64_t* bar = bars + (i % NS);
+            // forward reads cost_from_terminal of the tiles h0+1 .. h0+cnt (the tile after the last hop does not exist)
+            const uint32_t dp_tiles = !NEED_DP ? 0u : (FORWARD ? min(cnt, H - 1 - h0) : cnt);
+            const REAL* dp_src = FORWARD ? a.cft + d.slot_off + (size_t)(h0 + 1) * (J * 32) : a.cfr + d.slot_off + (size_t)h0 * (J * 32);
+            const void* src = a.topo + d.topo_off + h0 * 32u;
+            uint32_t off = 0, bytes = cnt * HOP_TOPO;
+            if(which == 1) { src = dp_src; off = o_dp; bytes = dp_tiles * HOP_DP; }
+            if(which == 2) { src = a.lay_vn + d.lay_off + h0 * 32u; off = o_vn; bytes = cnt * HOP_VN; }
+            if(which == 3) { src = a.lohi_in + d.lay_off + h0 * 32u; off = o_lohi; bytes = cnt * HOP_LOHI; }
+            // the transaction count may run negative until the expect_tx arrives: the phase cannot complete before the arrival
+            if(which == 0) mbar_arrive_expect_tx(bar, cnt * (HOP_TOPO + HOP_VN + HOP_LOHI) + dp_tiles * HOP_DP);
+            if(bytes > 0) bulk_g2s(st + off, src, bytes, bar);
+        }
+    };
+    // gather the delta values of position i; from_global reads the variables from global memory
+    // (does not need the chunk to have landed)
+    auto gather = [&](uint32_t i, bool from_global, uint32_t h_begin) {
+        const uint32_t h0 = chunk_first(i), cnt = min(n, H - h0);
+        unsigned char* st = wsm + (size_t)(i % NS) * a.stage_bytes;
+        const int2* s_vn = reinterpret_cast<const int2*>(st + o_vn) + lane;
+        const int2* g_vn = a.lay_vn + d.lay_off + h0 * 32u + lane;
+        R2* s_delta = reinterpret_cast<R2*>(st + o_delta) + lane;
+        for(uint32_t h = h_begin; h < cnt; h += 4)
+        {
+            int var[4];
+#pragma unroll
+            for(int k = 0; k < 4; ++k)
+            {
+                const uint32_t hk = min(h + k, cnt - 1);
+                var[k] = from_global ? __ldg(&g_vn[hk * 32].x) : s_vn[hk * 32].x;
+            }
+#pragma unroll
+            for(int k = 0; k < 4; ++k)
+                cp_async_gather_if(h + k < cnt && var[k] >= 0, s_delta + (h + k) * 32, a.delta_in + 2 * (size_t)max(var[k], 0));
+        }
+        cp_async_commit();
+    };
+
+    // ---- start-up: static data first (may overlap the previous kernel's tail), then everything the previous pass wrote
+    stamp();       // 2: (unused)
+    constexpr int G0 = 16;                 // variables of the first chunk straight from global memory, in one batch of loads
+    int var0[G0];
+    const uint32_t cnt0 = min(n, H - chunk_first(0));
+    if(NEED_DELTA)
+    {
+        const int2* g_vn = a.lay_vn + d.lay_off + chunk_first(0) * 32u + lane;
+#pragma unroll
+        for(int k = 0; k < G0; ++k) var0[k] = (uint32_t)k < cnt0 ? __ldg(&g_vn[k * 32].x) : -1;
+    }
+    int32_t bdd_index = -1;
+    if(!FORWARD) bdd_index = a.bundle_bdd[d.bdd_base + lane];          // consumed after the last hop
+    stamp();       // 3: variable loads issued
+    pdl_wait();
+    pdl_launch_dependents();
+    stamp();       // 4: previous kernel complete
+    issue(0, 1, COPY_ALL);
+    stamp();       // 5: bulk copies of the first chunk issued
+    R2 dl0[G0];
+    if(NEED_DELTA)
+    {   // scattered LDG is ~4x cheaper to issue than scattered LDGSTS (tools/microbench/issue_cost.cu)
+#pragma unroll
+        for(int k = 0; k < G0; ++k)
+            dl0[k] = *reinterpret_cast<const R2*>(a.delta_in + 2 * (size_t)max(var0[k], 0));
+        if(cnt0 > (uint32_t)G0) gather(0, true, G0); else cp_async_commit();
+    }
+    if(nc > 1) issue(1, min(NS, nc) - 1, COPY_ALL);
+    stamp();       // 6: first gathers (need the variable loads) and the bulk copies of the next chunks issued
+    if(MODE == MODE_MMA && a.zero_buf != nullptr)
+    {   // this warp's share of the delta buffer of the pass after next, cleared while the first chunk is in flight
+        R2* z = reinterpret_cast<R2*>(a.zero_buf);
+        const uint32_t pairs = a.n_zero >> 1;
+        const uint32_t z0 = min(pairs, bundle_in_launch * a.zero_pairs_per_bundle), z1 = min(pairs, z0 + a.zero_pairs_per_bundle);
+        R2 zero; zero.x = 0; zero.y = 0;
+        for(uint32_t i = z0 + lane; i < z1; i += 32) z[i] = zero;
+    }
+    if(NEED_DELTA)
+    {
+        R2* s_delta = reinterpret_cast<R2*>(wsm + o_delta) + lane;
+#pragma unroll
+        for(int k = 0; k < G0; ++k)
+            if((uint32_t)k < cnt0) s_delta[k * 32] = dl0[k];
+    }
+    stamp();       // 7: zeroing issued, first gathers stored
+    mbar_wait(bars + 0, 0);
+    stamp();       // 8: first chunk landed
+
+    REAL fr[J];    // frontier: forward = cost_from_root of this hop's rows, backward = cost_from_terminal of the next hop's rows
+#pragma unroll
+    for(int j = 0; j < J; ++j) fr[j] = INF;
+    if(FORWARD)
+    {   // flush_costs_from_root (bdd_cuda_base.cu:1438-1445): a lane with a BDD has a layer at hop 0
+        if(reinterpret_cast<const int2*>(wsm + o_vn)[lane].x >= 0) fr[0] = 0;
+    }
+    const REAL omega = a.omega;
+    const bool normalize = a.normalize_in != NORM_NONE;
+    const uint32_t inv_tab_s = smem_u32(inv_tab);
+
+    for(uint32_t i = 0; i < nc; ++i)
+    {
+        if(i + 1 < nc)
+        {
+            mbar_wait(bars + ((i + 1) % NS), ((i + 1) / NS) & 1u);
+            if(NEED_DELTA) { gather(i + 1, false, 0); cp_async_wait<1>(); }
+        }
+        else if(NEED_DELTA) cp_async_wait<0>();
+        stamp();   // 9 + 2i: chunk i ready (next chunk landed, own gathers complete; every lane reads only what it gathered itself)
+
+        const uint32_t h0 = chunk_first(i), cnt = min(n, H - h0);
+        const unsigned char* st = wsm + (size_t)(i % NS) * a.stage_bytes;
+        const uint32_t* s_topo = reinterpret_cast<const uint32_t*>(st) + lane;
+        const REAL* s_dp = reinterpret_cast<const REAL*>(st + o_dp) + lane;
+        const int2* s_vn = reinterpret_cast<const int2*>(st + o_vn) + lane;
+        const R2* s_lohi = reinterpret_cast<const R2*>(st + o_lohi) + lane;
+        const R2* s_delta = reinterpret_cast<const R2*>(st + o_delta) + lane;
+        REAL* g_dp = (FORWARD ? a.cfr : a.cft) + d.slot_off + (size_t)h0 * (J * 32) + lane;
+        R2* g_lohi = a.lohi_out + d.lay_off + h0 * 32u + lane;
+        REAL* g_mmd = a.mmd + d.lay_off + h0 * 32u + lane;
+        REAL* g_mm_lo = a.mm_lo_out + d.lay_off + h0 * 32u + lane;
+        REAL* g_mm_hi = a.mm_hi_out + d.lay_off + h0 * 32u + lane;
+
+        auto load = [&](uint32_t h) -> In {
+            In x;
+            x.t = s_topo[h * 32];
+            const int2 vn = s_vn[h * 32];
+            x.var = vn.x;
+            const R2 c2 = s_lohi[h * 32];                      // entries without a layer hold {0, 0}
+            x.lo = c2.x; x.hi = c2.y;
+            x.d0 = 0; x.d1 = 0;
+            if(NEED_DELTA)
+            {
+                const R2 dl = s_delta[h * 32];                 // not gathered (garbage) where var < 0
+                REAL d0, d1;
+                if(DET)
+                {
+                    const REAL nn = normalize ? (REAL)max(vn.y, 1) : (REAL)1;
+                    d0 = dl.x / nn; d1 = dl.y / nn;
+                }
+                else
+                {   // the table holds 1/n (the host selects the DET kernels when some n >= INV_TAB), or ones
+                    const REAL r = normalize ? lds_real<REAL>(inv_tab_s + min((uint32_t)vn.y, (uint32_t)(INV_TAB - 1)) * R) : (REAL)1;
+                    d0 = dl.x * r; d1 = dl.y * r;
+                }
+                x.d0 = vn.x >= 0 ? d0 : (REAL)0; x.d1 = vn.x >= 0 ? d1 : (REAL)0;
+            }
+#pragma unroll
+            for(int r = 0; r < J; ++r) x.c[r] = NEED_DP ? s_dp[(h * J + r) * 32] : INF;
+            return x;
+        };
+        auto bit = [](uint32_t t, int j, int arc, int r) -> bool { return (t & (1u << (j * 2 * J + arc * J + r))) != 0; };
+
+        In cur = load(FORWARD ? 0u : cnt - 1u);
+#pragma unroll 2
+        for(uint32_t hh = 0; hh < cnt; ++hh)
+        {
+            const uint32_t h = FORWARD ? hh : cnt - 1 - hh;
+            const In x = cur;
+            cur = load(FORWARD ? min(h + 1, cnt - 1) : (uint32_t)max((int)h - 1, 0));     // one hop ahead of the arithmetic
+            REAL lo_n = x.lo, hi_n = x.hi, diff = 0;
+
+            if(FORWARD)
+            {
+                if(MODE == MODE_MMA)
+                {
+                    REAL mm0 = INF, mm1 = INF;
+#pragma unroll
+                    for(int j = 0; j < J; ++j)
+                    {
+                        REAL ta = INF, tb = INF;
+#pragma unroll
+                        for(int r = 0; r < J; ++r)
+                        {
+                            ta = bit(x.t, j, 0, r) ? x.c[r] : ta;
+                            tb = bit(x.t, j, 1, r) ? x.c[r] : tb;
+                        }
+                        const REAL m0 = fr[j] + x.lo + ta;     // same association as bdd_cuda_parallel_mma.cu:83-84
+                        const REAL m1 = fr[j] + x.hi + tb;
+                        mm0 = j == 0 ? m0 : rmin(mm0, m0);
+                        mm1 = j == 0 ? m1 : rmin(mm1, m1);
+                    }
+                    diff = mm_difference(omega, mm0, mm1);
+                    lo_n = x.lo + rmin(diff, (REAL)0) + x.d0;
+                    hi_n = x.hi + rmin(-diff, (REAL)0) + x.d1;
+                }
+                REAL nx[J];
+#pragma unroll
+                for(int r = 0; r < J; ++r)
+                {
+#pragma unroll
+                    for(int j = 0; j < J; ++j)
+                    {
+                        const REAL c0 = bit(x.t, j, 0, r) ? fr[j] + lo_n : INF;
+                        const REAL c1 = bit(x.t, j, 1, r) ? fr[j] + hi_n : INF;
+                        const REAL cm = rmin(c0, c1);
+                        nx[r] = j == 0 ? cm : rmin(nx[r], cm);
+                    }
+                }
+#pragma unroll
+                for(int j = 0; j < J; ++j)
+                {
+                    g_dp[(size_t)h * (J * 32) + j * 32] = fr[j];
+                    fr[j] = nx[j];
+                }
+            }
+            else
+            {
+                REAL ta[J], tb[J];
+#pragma unroll
+                for(int j = 0; j < J; ++j)
+                {
+                    ta[j] = INF; tb[j] = INF;
+#pragma unroll
+                    for(int r = 0; r < J; ++r)
+                    {
+                        ta[j] = bit(x.t, j, 0, r) ? fr[r] : ta[j];
+                        tb[j] = bit(x.t, j, 1, r) ? fr[r] : tb[j];
+                    }
+                }
+                if(MODE != MODE_PLAIN)
+                {
+                    REAL mm0 = INF, mm1 = INF;
+#pragma unroll
+                    for(int j = 0; j < J; ++j)
+                    {
+                        REAL m0, m1;
+                        if(MODE == MODE_MMA) { m0 = x.c[j] + x.lo + ta[j]; m1 = x.c[j] + x.hi + tb[j]; }
+                        else { m0 = x.c[j] + (ta[j] + x.lo); m1 = x.c[j] + (tb[j] + x.hi); }   // path costs, bdd_cuda_base.cu:636-641
+                        mm0 = j == 0 ? m0 : rmin(mm0, m0);
+                        mm1 = j == 0 ? m1 : rmin(mm1, m1);
+                    }
+                    if(MODE == MODE_MMA)
+                    {
+                        diff = mm_difference(omega, mm0, mm1);
+                        lo_n = x.lo + rmin(diff, (REAL)0) + x.d0;
+                        hi_n = x.hi + rmin(-diff, (REAL)0) + x.d1;
+                    }
+                    else if(x.var >= 0)
+                    {
+                        g_mm_lo[h * 32] = mm0;
+                        g_mm_hi[h * 32] = mm1;
+                    }
+                }
+#pragma unroll
+                for(int j = 0; j < J; ++j)
+                {
+                    REAL val = rmin(hi_n + tb[j], lo_n + ta[j]);           // bdd_cuda_parallel_mma.cu:286; +inf where there is no node
+                    if(j == 0) val = x.var == LAY_TOP ? (REAL)0 : val;    // set_special_nodes_costs, bdd_cuda_base.cu:217-227
+                    g_dp[(size_t)h * (J * 32) + j * 32] = val;
+                    fr[j] = val;
+                }
+            }
+
+            if(MODE == MODE_MMA)
+            {   // entries without a layer hold lo = hi = 0, collect diff = 0 and read delta 0: writing them back is harmless
+                R2 o; o.x = lo_n; o.y = hi_n;
+                g_lohi[h * 32] = o;
+                g_mmd[h * 32] = diff;
+                // compute_delta_atomic, bdd_cuda_parallel_mma.cu:358-376: |diff| goes to the hi slot if diff > 0, else to lo
+                if(!DET) red_add_if(diff != 0, a.delta_out + 2 * (size_t)max(x.var, 0) + (diff > 0 ? 1 : 0), fabs(diff));
+            }
+        }
+
+        __syncwarp();                                   // every lane is done with stage i % NS
+        stamp();   // 10 + 2i: chunk i computed
+        if(i + NS < nc) issue(i + NS, 1, COPY_ALL);
+    }
+
+    if(!FORWARD)
+    {
+        const REAL root = fr[0];                                    // root = row 0 of hop 0
+        const bool mine_valid = bdd_index >= 0;
+        if(mine_valid) a.bdd_lb[bdd_index] = root;
+        if(a.lb_sum != nullptr)
+        {   // lower_bound, bdd_cuda_base.cu:1243-1251: sum over BDDs in double
+            double v = mine_valid ? (double)root : 0.0;
+#pragma unroll
+            for(int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if(lane == 0) atomicAdd(a.lb_sum, v);
+        }
+    }
+}
+
+template<typename REAL, int MODE, bool FORWARD, bool DET>
+__global__ void __launch_bounds__(512, 1) sweep_lane_kernel(const SweepArgs<REAL> a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ REAL inv_tab[INV_TAB];                        // 1 / n for n < INV_TAB (ones when delta_in is already normalised)
+    __shared__ uint64_t bars_all[16 * LANE_MAX_STAGES];      // one mbarrier per warp and pipeline stage
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t g_lo = blockIdx.x * a.bundles_per_cta + min(blockIdx.x, a.bundles_rem);
+    const uint32_t g_hi = g_lo + a.bundles_per_cta + (blockIdx.x < a.bundles_rem ? 1u : 0u);
+    const uint32_t g = g_lo + warp;
+    const bool active = g < g_hi;
+    if(a.trace && lane == 0 && active)
+    {
+        unsigned long long* tr = a.trace + (size_t)(blockIdx.x * (blockDim.x >> 5) + warp) * TRACE_EVENTS;
+        unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        tr[0] = clock64(); tr[TRACE_EVENTS - 1] = smid;
+    }
+    LaneDesc d{};
+    if(active) d = reinterpret_cast<const LaneDesc*>(a.desc)[a.bundle_first + g];     // in flight during the CTA prologue
+    if(threadIdx.x < (blockDim.x >> 5) * a.n_stages) mbar_init(bars_all + threadIdx.x, 1);
+    if(threadIdx.x == 0) mbar_fence_init();
+    if(MODE == MODE_MMA && !DET)
+        for(uint32_t i = threadIdx.x; i < a.inv_count; i += blockDim.x) inv_tab[i] = a.inv_tab_g[i];
+    __syncthreads();
+    if(FORWARD && a.lb_sum != nullptr && blockIdx.x == 0 && threadIdx.x == 0)
+    {   // the previous backward pass accumulated into it
+        pdl_wait();
+        *a.lb_sum = 0.0;
+    }
+    if(!active) return;
+    unsigned char* wsm = smem_raw + (size_t)warp * a.warp_smem_bytes;
+    uint64_t* bars = bars_all + warp * a.n_stages;
+    constexpr int M = (FORWARD && MODE == MODE_MM) ? MODE_PLAIN : MODE;
+    switch(d.J)
+    {
+        case 1: sweep_lane_bundle<REAL, 1, M, FORWARD, DET>(a, d, g, wsm, bars, inv_tab, lane); break;
+        case 2: sweep_lane_bundle<REAL, 2, M, FORWARD, DET>(a, d, g, wsm, bars, inv_tab, lane); break;
+        case 3: sweep_lane_bundle<REAL, 3, M, FORWARD, DET>(a, d, g, wsm, bars, inv_tab, lane); break;
+        case 4: sweep_lane_bundle<REAL, 4, M, FORWARD, DET>(a, d, g, wsm, bars, inv_tab, lane); break;
+        default: break;
+    }
+}
+
 // ------------------------------------------------------------------ small kernels ------
 
 // deterministic replacement of compute_delta (bdd_cuda_parallel_mma.cu:379-393): per variable,
@@ -938,6 +1364,27 @@ __global__ void bdds_solution_kernel(const BundleDesc* __restrict__ bundles, con
     const uint32_t e0 = bdd_ext_begin[b], n_lay = bdd_ext_begin[b + 1] - e0 - 1;
     uint32_t ts = q << bd.logP;   // root's slot inside the hop-0 tile
     const REAL INF = real_inf<REAL>();
+    if(bd.cls == CLS_LANE)
+    {   // lane-local class: one-hot arc targets per (hop, lane), the BDD stays in lane q
+        const uint32_t J = bd.max_J, mask = (1u << J) - 1u;
+        uint32_t r = 0;
+        for(uint32_t k = 0; k < n_lay; ++k)
+        {
+            const uint32_t word = topo[bd.topo_base + k * 32u + q];
+            const uint32_t s = hops[bd.hop_base + k].node_off + r * 32u + q, sn = hops[bd.hop_base + k + 1].node_off + q;
+            const uint32_t lay = bd.layer_base + k * 32u + q;
+            const uint32_t lo_bits = (word >> (r * 2u * J)) & mask, hi_bits = (word >> (r * 2u * J + J)) & mask;
+            const uint32_t lo_r = lo_bits ? (uint32_t)__ffs((int)lo_bits) - 1u : 0u, hi_r = hi_bits ? (uint32_t)__ffs((int)hi_bits) - 1u : 0u;
+            const REAL c = cfr[s];
+            const REAL lo_path = c + ((lo_bits ? cft[sn + lo_r * 32u] : INF) + lohi[2 * (size_t)lay]);
+            const REAL hi_path = c + ((hi_bits ? cft[sn + hi_r * 32u] : INF) + lohi[2 * (size_t)lay + 1]);
+            const bool take_lo = (hi_path - lo_path > 0);
+            sol[e0 + k] = take_lo ? 0 : 1;
+            r = take_lo ? lo_r : hi_r;
+        }
+        sol[e0 + n_lay] = 0;   // terminal layer
+        return;
+    }
     for(uint32_t k = 0; k < n_lay; ++k)
     {
         const HopRec h = hops[bd.hop_base + k], hn = hops[bd.hop_base + k + 1];

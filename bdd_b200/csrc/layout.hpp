@@ -46,6 +46,9 @@ constexpr uint32_t TOPO_TOP = 0xFFFFFFFEu;
 constexpr uint32_t CHILD_BOT = 0xFFFFu;
 constexpr uint32_t MAX_TILE_SLOTS = 0xFFFFu;      // child slot indices are 16 bit
 constexpr uint32_t SMALL_CLASS_MAX_J = 8;         // bundles with J <= 8 share multi-warp CTAs
+constexpr uint32_t LANE_MAX_J = 4;                // lane-local class: one lane per BDD, at most 4 nodes per layer
+constexpr int32_t LAY_NONE = -1;                  // layer entry without a layer (BDD shorter than its bundle)
+constexpr int32_t LAY_TOP = -2;                   // layer entry of a BDD's terminal hop (its top sink sits in row 0)
 
 struct HopRec {
     uint32_t node_off;   // first slot of the tile
@@ -72,7 +75,32 @@ struct BundleDesc {
     uint32_t max_J;
     uint32_t chunk_base; // index of the bundle's first ChunkRec
     uint32_t n_chunks;
+    uint32_t cls;        // CLS_GENERIC or CLS_LANE
+    uint32_t topo_base;  // CLS_LANE: first topology word (32 per hop)
 };
+enum BundleClass { CLS_GENERIC = 0, CLS_LANE = 1 };
+
+// Lane-local class (CLS_LANE): one lane per BDD and at most LANE_MAX_J nodes per layer, so a
+// BDD never leaves its lane.  Every hop of the bundle owns a tile of J rows (J uniform per
+// bundle): any range of hops is contiguous in every array and chunking is a launch parameter.
+// The topology of one (hop, lane) is ONE word of one-hot arc targets:
+//   bit (j*2J + a*J + r) set  <=>  arc a (0 = lo, 1 = hi) of the node in row j enters row r of the
+//   next hop's tile; no bit = arc into the bot sink (or no node in row j).
+// The terminal hop of a BDD is marked in its layer entry (LAY_TOP).
+struct LaneDesc {
+    uint32_t slot_off;   // first slot of the bundle (hop h, row j, lane l -> slot_off + (h*J + j)*32 + l)
+    uint32_t lay_off;    // first layer entry (hop h, lane l -> lay_off + h*32 + l)
+    uint32_t topo_off;   // first topology word (hop h, lane l -> topo_off + h*32 + l)
+    uint32_t n_hops;     // hops incl. the terminal hop of the longest BDD
+    uint32_t J;
+    uint32_t bdd_base;   // first entry in bundle_bdd (32 entries)
+    uint32_t pad_[2];
+};
+inline uint32_t lane_arc_bit(uint32_t J, uint32_t j, uint32_t arc, uint32_t r) { return 1u << (j * 2 * J + arc * J + r); }
+
+// Shared-memory bytes one hop of a lane-class bundle occupies in a pipeline stage:
+// topology word + the opposite direction's DP rows + {var, nr_bdds} + {lo, hi} + gathered {delta_lo, delta_hi}
+inline size_t lane_hop_bytes(uint32_t J, size_t R) { return 128 + (size_t)J * 32 * R + 256 + 64 * R + 64 * R; }
 
 // Descriptor block of a bundle: DESC_WORDS 32-bit words that a warp fetches with ONE coalesced
 // 128-byte load (lane l reads word l).  There is one block per bundle and pass direction; the
@@ -105,7 +133,12 @@ struct HostLayout {
     size_t n_layers_ext = 0;   // sum over BDDs of (nr variables + 1)
     size_t n_real_nodes = 0;   // non-terminal nodes
     size_t n_slots = 0, n_lay = 0, max_hops = 0;
-    size_t n_small_bundles = 0;          // bundles [0, n_small): every chunk fits the stage budget
+    size_t n_lane_bundles = 0;           // bundles [0, n_lane): lane-local class
+    uint32_t lane_max_J = 0, lane_max_hops = 0;
+    size_t n_generic_slots = 0;          // generic bundles own slots [0, n_generic_slots): topo[slot] is their topology word
+    size_t n_topo = 0;                   // n_generic_slots + 32 words per hop of every lane-class bundle
+    std::vector<LaneDesc> desc_lane;     // one per lane-class bundle
+    size_t n_small_bundles = 0;          // generic bundles [n_lane, n_lane + n_small): every chunk fits the stage budget
     uint32_t max_tile_small = 0, max_tile_large = 0;  // slots
     size_t stage_small = 0, stage_large = 0;          // largest chunk_stage_bytes per class
     std::vector<BundleDesc> bundles;
@@ -139,7 +172,7 @@ constexpr size_t DEFAULT_STAGE_BUDGET = 12 * 1024;   // bytes of one pipeline st
 inline HostLayout build_layout(const bddb200_instruction* instrs, size_t n_instr,
                                const size_t* delims, size_t n_bdds, int lanes_per_bdd,
                                size_t nr_variables_override = 0, size_t real_bytes = 4,
-                               size_t stage_budget = DEFAULT_STAGE_BUDGET)
+                               size_t stage_budget = DEFAULT_STAGE_BUDGET, bool lane_class = true)
 {
     constexpr size_t TOPSINK = (size_t)-1, BOTSINK = (size_t)-1 - 1;
     if(n_bdds == 0) throw layout_error(BDDB200_ERR_INVALID_ARGUMENT, "empty BDD collection");
@@ -221,23 +254,33 @@ inline HostLayout build_layout(const bddb200_instruction* instrs, size_t n_instr
         uint32_t P = lanes_per_bdd ? (uint32_t)lanes_per_bdd : std::min<uint32_t>(32, pow2ceil((bdd_maxw[b] + 3) / 4));
         bdd_logP[b] = (uint8_t)ilog2(P);
     }
-    std::vector<uint32_t> order(n_bdds);
-    std::iota(order.begin(), order.end(), 0u);
     auto nlay = [&](uint32_t b) { return L.bdd_ext_begin[b+1] - L.bdd_ext_begin[b]; };
+    // lane-local class: one lane per BDD, narrow; everything else is generic
+    std::vector<uint32_t> order, lane_order;
+    for(size_t b = 0; b < n_bdds; ++b)
+    {
+        if(lane_class && bdd_logP[b] == 0 && bdd_maxw[b] <= LANE_MAX_J) lane_order.push_back((uint32_t)b);
+        else order.push_back((uint32_t)b);
+    }
     std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
         if(bdd_logP[x] != bdd_logP[y]) return bdd_logP[x] < bdd_logP[y];
         return nlay(x) > nlay(y);
     });
+    std::stable_sort(lane_order.begin(), lane_order.end(), [&](uint32_t x, uint32_t y) {
+        if(bdd_maxw[x] != bdd_maxw[y]) return bdd_maxw[x] < bdd_maxw[y];
+        return nlay(x) > nlay(y);
+    });
+    const size_t n_generic_bdds = order.size();
 
     struct ProtoChunk { uint32_t first, n, J; };
     struct ProtoBundle { uint32_t first, count, logP, n_hops, max_J, work; bool small; std::vector<uint32_t> J; std::vector<ProtoChunk> chunks; };
     std::vector<ProtoBundle> protos;
-    for(size_t pos = 0; pos < n_bdds;)
+    for(size_t pos = 0; pos < n_generic_bdds;)
     {
         const uint32_t logP = bdd_logP[order[pos]];
         const uint32_t bpw = 32u >> logP, P = 1u << logP;
         size_t end = pos;
-        while(end < n_bdds && end - pos < bpw && bdd_logP[order[end]] == logP) ++end;
+        while(end < n_generic_bdds && end - pos < bpw && bdd_logP[order[end]] == logP) ++end;
         ProtoBundle pb;
         pb.first = (uint32_t)pos; pb.count = (uint32_t)(end - pos); pb.logP = logP;
         pb.n_hops = 0;
@@ -308,13 +351,30 @@ inline HostLayout build_layout(const bddb200_instruction* instrs, size_t n_instr
         return protos[x].work > protos[y].work;
     });
 
-    // ---- emit --------------------------------------------------------------------------
-    L.bundles.reserve(protos.size());
+    // ---- lane-class bundles: up to 32 BDDs of the same width ----------------------------
+    struct LaneProto { uint32_t first, count, J, n_hops; };
+    std::vector<LaneProto> lane_protos;
+    for(size_t pos = 0; pos < lane_order.size();)
+    {
+        const uint32_t Jb = bdd_maxw[lane_order[pos]];
+        size_t end = pos;
+        uint32_t nh = 0;
+        while(end < lane_order.size() && end - pos < 32 && bdd_maxw[lane_order[end]] == Jb) { nh = std::max(nh, nlay(lane_order[end])); ++end; }
+        lane_protos.push_back(LaneProto{(uint32_t)pos, (uint32_t)(end - pos), Jb, nh});
+        pos = end;
+    }
+    std::stable_sort(lane_protos.begin(), lane_protos.end(), [](const LaneProto& x, const LaneProto& y) { return x.n_hops * x.J > y.n_hops * y.J; });
+
+    // ---- emit: generic bundles own the first slots (topo is indexed by slot there), lane-class
+    // bundles follow; in bundle order the lane class comes first -------------------------------
+    std::vector<BundleDesc> generic_bundles;
+    generic_bundles.reserve(protos.size());
     size_t slot = 0, lay = 0;
     for(const uint32_t pi : border)
     {
         const ProtoBundle& pb = protos[pi];
         BundleDesc bd{};
+        bd.cls = CLS_GENERIC;
         bd.hop_base = (uint32_t)L.hops.size();
         bd.n_hops = pb.n_hops; bd.logP = pb.logP; bd.max_J = 0;
         lay = (lay + 1) & ~(size_t)1;
@@ -347,11 +407,44 @@ inline HostLayout build_layout(const bddb200_instruction* instrs, size_t n_instr
         if(pb.small) { L.n_small_bundles++; L.max_tile_small = std::max(L.max_tile_small, bd.max_J * 32u); }
         else L.max_tile_large = std::max(L.max_tile_large, bd.max_J * 32u);
         L.max_hops = std::max<size_t>(L.max_hops, pb.n_hops);
+        generic_bundles.push_back(bd);
+    }
+    L.n_generic_slots = slot;
+    size_t topo_words = slot;
+    lay = (lay + 1) & ~(size_t)1;
+    for(const LaneProto& lp : lane_protos)
+    {
+        BundleDesc bd{};
+        bd.cls = CLS_LANE;
+        bd.hop_base = (uint32_t)L.hops.size();
+        bd.n_hops = lp.n_hops; bd.logP = 0; bd.max_J = lp.J;
+        bd.layer_base = (uint32_t)lay;
+        bd.bdd_base = (uint32_t)L.bundle_bdd.size();
+        bd.chunk_base = 0; bd.n_chunks = 0;
+        bd.topo_base = (uint32_t)topo_words;
+        if(slot + 32ull * lp.J * lp.n_hops > 0xFFFFFFFFull || topo_words + 32ull * lp.n_hops > 0xFFFFFFFFull)
+            throw layout_error(BDDB200_ERR_INVALID_ARGUMENT, "collection too large (slot index overflow)");
+        LaneDesc ld{};
+        ld.slot_off = (uint32_t)slot; ld.lay_off = (uint32_t)lay; ld.topo_off = (uint32_t)topo_words;
+        ld.n_hops = lp.n_hops; ld.J = lp.J; ld.bdd_base = bd.bdd_base;
+        L.desc_lane.push_back(ld);
+        for(uint32_t k = 0; k < lp.n_hops; ++k) { L.hops.push_back(HopRec{(uint32_t)slot, lp.J}); slot += 32ull * lp.J; }
+        topo_words += 32ull * lp.n_hops;
+        lay += 32ull * lp.n_hops;
+        for(uint32_t q = 0; q < 32; ++q)
+            L.bundle_bdd.push_back(q < lp.count ? (int32_t)lane_order[lp.first + q] : -1);
+        L.lane_max_J = std::max(L.lane_max_J, lp.J);
+        L.lane_max_hops = std::max(L.lane_max_hops, lp.n_hops);
+        L.max_hops = std::max<size_t>(L.max_hops, lp.n_hops);
         L.bundles.push_back(bd);
     }
+    L.n_lane_bundles = L.bundles.size();
+    L.bundles.insert(L.bundles.end(), generic_bundles.begin(), generic_bundles.end());
+    L.n_topo = topo_words;
+
     L.desc_fwd.assign(L.bundles.size() * DESC_WORDS, 0u);
     L.desc_bwd.assign(L.bundles.size() * DESC_WORDS, 0u);
-    for(size_t g = 0; g < L.bundles.size(); ++g)
+    for(size_t g = L.n_lane_bundles; g < L.bundles.size(); ++g)
     {
         const BundleDesc& bd = L.bundles[g];
         for(int dir = 0; dir < 2; ++dir)
@@ -371,8 +464,10 @@ inline HostLayout build_layout(const bddb200_instruction* instrs, size_t n_instr
     L.n_slots = slot; L.n_lay = lay;
     if(lay > 0xFFFFFFF0ull) throw layout_error(BDDB200_ERR_INVALID_ARGUMENT, "collection too large (layer index overflow)");
 
-    L.topo.assign(L.n_slots, TOPO_PAD);
-    L.lay_var.assign(L.n_lay, -1);
+    L.topo.assign(L.n_topo, TOPO_PAD);
+    for(size_t g = 0; g < L.n_lane_bundles; ++g)
+        std::fill(L.topo.begin() + L.bundles[g].topo_base, L.topo.begin() + L.bundles[g].topo_base + 32ull * L.bundles[g].n_hops, 0u);
+    L.lay_var.assign(L.n_lay, LAY_NONE);
     L.ext2lay.assign(L.n_layers_ext, 0);
     L.root_slot.assign(n_bdds, 0);
     L.top_slot.assign(n_bdds, 0);
@@ -381,6 +476,7 @@ inline HostLayout build_layout(const bddb200_instruction* instrs, size_t n_instr
     for(size_t g = 0; g < L.bundles.size(); ++g)
     {
         const BundleDesc& bd = L.bundles[g];
+        const bool lane_cls = bd.cls == CLS_LANE;
         const uint32_t logP = bd.logP, P = 1u << logP, bpw = 32u >> logP;
         for(uint32_t q = 0; q < bpw; ++q)
         {
@@ -399,7 +495,8 @@ inline HostLayout build_layout(const bddb200_instruction* instrs, size_t n_instr
                 const HopRec& hr = L.hops[bd.hop_base + k];
                 if(e == ee)
                 {
-                    L.topo[hr.node_off + tile_slot(0)] = TOPO_TOP;
+                    if(!lane_cls) L.topo[hr.node_off + tile_slot(0)] = TOPO_TOP;
+                    L.lay_var[layer_entry] = LAY_TOP;
                     L.top_slot[b] = hr.node_off + tile_slot(0);
                     continue;
                 }
@@ -408,6 +505,24 @@ inline HostLayout build_layout(const bddb200_instruction* instrs, size_t n_instr
                 L.lay_var[layer_entry] = L.ext_var[e];
                 L.nr_bdds_per_var[L.ext_var[e]]++;
                 if(k == 0) L.root_slot[b] = hr.node_off + tile_slot(0);
+                if(lane_cls)
+                {
+                    uint32_t word = 0;
+                    for(size_t i = lb; i < le; ++i)
+                    {
+                        const uint32_t j = (uint32_t)(i - lb);
+                        const size_t arcs[2] = {instrs[i].lo, instrs[i].hi};
+                        for(uint32_t arc = 0; arc < 2; ++arc)
+                        {
+                            const size_t c = arcs[arc];
+                            if(c == bot) continue;
+                            const uint32_t r = (c == top) ? 0u : (uint32_t)(c - next_first);
+                            word |= lane_arc_bit(bd.max_J, j, arc, r);
+                        }
+                    }
+                    L.topo[bd.topo_base + k * 32u + q] = word;
+                    continue;
+                }
                 for(size_t i = lb; i < le; ++i)
                 {
                     auto child = [&](size_t c) -> uint32_t {

@@ -48,29 +48,31 @@ def test_create_without_gpu_fails_loudly():
 
 def layout_stats(col, lanes=0):
     lib = _lib.load()
-    out = np.zeros(11, dtype=np.uint64)
+    out = np.zeros(13, dtype=np.uint64)
     instrs = np.ascontiguousarray(col.instrs); delims = np.ascontiguousarray(col.delims)
-    rc = lib.bddb200_layout_stats(instrs.ctypes.data, instrs.shape[0], delims.ctypes.data, delims.shape[0] - 1, lanes, out.ctypes.data, 11)
+    rc = lib.bddb200_layout_stats(instrs.ctypes.data, instrs.shape[0], delims.ctypes.data, delims.shape[0] - 1, lanes, out.ctypes.data, 13)
     if rc != 0:
         raise RuntimeError(lib.bddb200_last_error().decode())
     return dict(zip(["slots", "layer_entries", "bundles", "real_nodes", "max_hops", "max_tile", "small_bundles", "ext_layers",
-                     "chunks", "stage_small", "stage_large"], out.tolist()))
+                     "chunks", "stage_small", "stage_large", "lane_bundles", "topo_words"], out.tolist()))
 
 
 def test_layout_set_cover_is_tight():
     col, _ = instances.set_cover(m=2048, n=4096, k=20, seed=3)
     st = layout_stats(col)
     assert st["real_nodes"] == 2048 * 39
-    assert st["bundles"] == 2048 // 32 and st["small_bundles"] == st["bundles"]
+    # width-2 BDDs: one lane per BDD, lane-local class, uniform tiles of 2 rows
+    assert st["bundles"] == 2048 // 32 and st["lane_bundles"] == st["bundles"] and st["small_bundles"] == 0
     assert st["max_hops"] == 21
-    # one lane per BDD, tiles of a chunk share one height: 21 hops x 2 rows (root and terminal hop padded)
-    assert st["slots"] == st["bundles"] * 32 * 42
-    # 21 hops x 1280 B (float) do not fit one 12 KiB stage: 3 chunks per bundle, each within the budget
-    assert st["chunks"] == 3 * st["bundles"] and 0 < st["stage_small"] <= 12 * 1024 and st["stage_large"] == 0
+    assert st["slots"] == st["bundles"] * 32 * 42          # 21 hops x 2 rows (root and terminal hop padded)
+    assert st["topo_words"] == st["bundles"] * 32 * 21     # one packed topology word per (hop, lane)
+    assert st["chunks"] == 0 and st["stage_small"] == 0 and st["stage_large"] == 0   # chunking is a launch parameter there
     assert st["ext_layers"] == 2048 * 21
-    # forcing more lanes per BDD trades padding for parallelism
+    # forcing more lanes per BDD trades padding for parallelism (generic class: chunked, per-slot topology)
     st2 = layout_stats(col, lanes=2)
-    assert st2["bundles"] == 2048 // 16 and st2["slots"] == st2["bundles"] * 32 * 21
+    assert st2["lane_bundles"] == 0 and st2["bundles"] == 2048 // 16 and st2["slots"] == st2["bundles"] * 32 * 21
+    assert st2["small_bundles"] == st2["bundles"] and st2["topo_words"] == st2["slots"]
+    assert 0 < st2["stage_small"] <= 12 * 1024 and st2["stage_large"] == 0
 
 
 def test_layout_mixed_lengths_and_widths():

@@ -15,10 +15,10 @@ for name, fwd in (("forward", True), ("backward", False)):
         pass
     tr = s.trace_pass(fwd, max_bundles=4096).astype(np.int64)
     t0 = tr[:, 0:1]
-    rel = tr[:, 1:12] - t0
+    rel = tr[:, 1:14] - t0
     valid = tr[:, 1] > 0
     rel = rel[valid]
-    print(f"== {name}: {valid.sum()} bundles; median cycles since warp start at each stamp (1 desc, 2 issued, 3 landed0, then ready/computed per chunk)")
+    print(f"== {name}: {valid.sum()} bundles; median cycles since warp start at each stamp (lane kernel: 1 desc, 2 static copies issued, 3 variable loads issued, 4 previous kernel complete, 5 dynamic copies issued, 6 gathers issued, 7 zeroing issued, 8 first chunk landed, then ready/computed per chunk)")
     print("   median", np.median(rel, axis=0).astype(int).tolist())
     print("   p90   ", np.percentile(rel, 90, axis=0).astype(int).tolist())
     print("   max   ", rel.max(axis=0).tolist())
