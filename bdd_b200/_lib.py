@@ -27,6 +27,7 @@ SYMBOLS = [
     "bddb200_min_marginals", "bddb200_bdds_solution", "bddb200_net_solver_costs", "bddb200_make_dual_feasible",
     "bddb200_gradient_step", "bddb200_synchronize", "bddb200_stream", "bddb200_kernel_launches",
     "bddb200_delta_sum_buffer", "bddb200_layout_stats", "bddb200_trace_pass",
+    "bddb200_delta_sum_index", "bddb200_set_delta_buffers", "bddb200_set_delta_input", "bddb200_delta_exchange",
 ]
 
 
@@ -108,6 +109,10 @@ def load() -> C.CDLL:
         "bddb200_delta_sum_buffer": (i, [vp, C.POINTER(vp)]),
         "bddb200_layout_stats": (i, [vp, sz, vp, sz, i, vp, sz]),
         "bddb200_trace_pass": (i, [vp, i, dbl, vp, sz, C.POINTER(sz)]),
+        "bddb200_delta_sum_index": (i, [vp, C.POINTER(i)]),
+        "bddb200_set_delta_buffers": (i, [vp, vp, vp, vp]),
+        "bddb200_set_delta_input": (i, [vp, vp, sz]),
+        "bddb200_delta_exchange": (i, [vp, i, i, i, vp, vp, C.c_uint32, sz, vp, sz]),
     }
     for name, (res, args) in sig.items():
         f = getattr(lib, name)

@@ -96,6 +96,9 @@ struct bddb200_solver {
     virtual void* stream_handle() = 0;
     virtual size_t kernel_launches() const = 0;
     virtual void* delta_sum_buffer() = 0;
+    virtual int delta_sum_index() const = 0;
+    virtual void set_delta_buffers(void* b0, void* b1, void* b2) = 0;
+    virtual void set_delta_input(void* in, size_t n_shared_vars) = 0;
     virtual size_t trace_pass(int forward, double omega, unsigned long long* out_host, size_t max_bundles) = 0;
     virtual bddb200_solver* clone() const = 0;
 };
@@ -441,6 +444,8 @@ public:
         SweepArgs<REAL> a = base_args();
         a.omega = (REAL)omega;
         a.delta_in = delta_in; a.delta_out = delta_out; a.zero_buf = zero_buf;
+        const bool own_sums = delta_in_override_ != nullptr && delta_in == dbuf(dcur_);     // not for forward_mm / backward_mm on a caller's vector
+        a.delta_in_shared = own_sums ? delta_in_override_ : delta_in; a.n_shared_vars = own_sums ? (uint32_t)n_shared_vars_ : 0u;
         a.normalize_in = !normalize_in ? NORM_NONE : (deterministic_ ? NORM_DIVIDE : NORM_RECIPROCAL);
         a.accumulate = deterministic_ ? 0 : 1;
         launch_sweep<MODE_MMA, FORWARD>(a);
@@ -457,9 +462,9 @@ public:
     {
         set_device();
         if(!backward_valid_) backward_run();     // bdd_cuda_parallel_mma.cu:210-211
-        REAL* in = d_delta_[dcur_].p;
-        REAL* out = d_delta_[(dcur_ + 1) % 3].p;
-        REAL* zero = d_delta_[(dcur_ + 2) % 3].p;
+        REAL* in = dbuf(dcur_);
+        REAL* out = dbuf((dcur_ + 1) % 3);
+        REAL* zero = dbuf((dcur_ + 2) % 3);
         mma_pass<true>(omega, in, delta_needs_norm_, out, zero);
         dcur_ = (dcur_ + 1) % 3; delta_needs_norm_ = true;
         forward_valid_ = true; backward_valid_ = false;
@@ -469,9 +474,9 @@ public:
     {
         set_device();
         if(!forward_valid_) throw api_error(BDDB200_ERR_STATE, "backward_mm needs a valid forward state (call forward_mm first)");
-        REAL* in = d_delta_[dcur_].p;
-        REAL* out = d_delta_[(dcur_ + 1) % 3].p;
-        REAL* zero = d_delta_[(dcur_ + 2) % 3].p;
+        REAL* in = dbuf(dcur_);
+        REAL* out = dbuf((dcur_ + 1) % 3);
+        REAL* zero = dbuf((dcur_ + 2) % 3);
         mma_pass<false>(omega, in, delta_needs_norm_, out, zero);
         dcur_ = (dcur_ + 1) % 3; delta_needs_norm_ = true;
         forward_valid_ = false; backward_valid_ = true; lb_valid_ = false;
@@ -563,7 +568,13 @@ public:
     void get_delta(void* out, int out_is_host) override
     {
         set_device();
-        const REAL* src = d_delta_[dcur_].p;
+        const REAL* src = dbuf(dcur_);
+        if(delta_in_override_ && n_shared_vars_ > 0)
+        {   // exchanged sums of the shared variables, local sums of the rest
+            CUDA_CHECK(cudaMemcpyAsync(d_delta_tmp2_.p, src, sizeof(REAL) * 2 * n_vars_, cudaMemcpyDeviceToDevice, stream_));
+            CUDA_CHECK(cudaMemcpyAsync(d_delta_tmp2_.p, delta_in_override_, sizeof(REAL) * 2 * n_shared_vars_, cudaMemcpyDeviceToDevice, stream_));
+            src = d_delta_tmp2_.p;
+        }
         if(delta_needs_norm_)
         {
             normalize_kernel<REAL><<<blocks_for(2 * n_vars_), 256, 0, stream_>>>(src, d_delta_tmp_.p, d_nr_bdds_.p, (uint32_t)(2 * n_vars_));
@@ -574,7 +585,23 @@ public:
         if(out_is_host) CUDA_CHECK(cudaStreamSynchronize(stream_));
     }
 
-    void* delta_sum_buffer() override { return d_delta_[dcur_].p; }
+    void* delta_sum_buffer() override { return dbuf(dcur_); }
+    int delta_sum_index() const override { return dcur_; }
+    // Multi-GPU exchange over peer memory: the three rotating sum buffers live in caller-owned (symmetric) memory, and the
+    // passes read the exchanged sums from a separate buffer (bddb200_delta_exchange writes it).
+    void set_delta_buffers(void* b0, void* b1, void* b2) override
+    {
+        if(graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
+        ext_delta_[0] = static_cast<REAL*>(b0); ext_delta_[1] = static_cast<REAL*>(b1); ext_delta_[2] = static_cast<REAL*>(b2);
+    }
+    void set_delta_input(void* in, size_t n_shared_vars) override
+    {
+        if(n_shared_vars > n_vars_) throw api_error(BDDB200_ERR_INVALID_ARGUMENT, "more shared variables than variables");
+        if(graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
+        delta_in_override_ = static_cast<REAL*>(in);
+        n_shared_vars_ = in ? n_shared_vars : 0;
+        if(in && d_delta_tmp2_.n == 0) d_delta_tmp2_.alloc(2 * n_vars_);
+    }
 
     // diagnostics: one MMA pass with per-bundle clock64() stamps (kernels.cuh, TRACE_EVENTS per bundle)
     size_t trace_pass(int forward, double omega, unsigned long long* out_host, size_t max_bundles) override
@@ -693,7 +720,8 @@ public:
         distribute_kernel<REAL><<<blocks_for(n_lay_), 256, 0, stream_>>>(d_lay_vn_.p, d_lohi_[cc_].p, d_mmd_.p, (uint32_t)n_lay_);
         ++launches_;
         CUDA_CHECK(cudaGetLastError());
-        for(int i = 0; i < 3; ++i) d_delta_[i].zero(stream_);
+        for(int i = 0; i < 3; ++i) CUDA_CHECK(cudaMemsetAsync(dbuf(i), 0, sizeof(REAL) * 2 * n_vars_, stream_));
+        if(delta_in_override_) CUDA_CHECK(cudaMemsetAsync(delta_in_override_, 0, sizeof(REAL) * 2 * n_shared_vars_, stream_));
         delta_needs_norm_ = false;
         flush_forward(); flush_backward();
     }
@@ -801,6 +829,11 @@ public:
 
 private:
     void set_device() const { CUDA_CHECK(cudaSetDevice(device)); }
+    REAL* dbuf(int i) const { return ext_delta_[i] ? ext_delta_[i] : d_delta_[i].p; }
+    REAL* ext_delta_[3] = {nullptr, nullptr, nullptr};
+    REAL* delta_in_override_ = nullptr;      // exchanged sums of the variables [0, n_shared_vars_)
+    size_t n_shared_vars_ = 0;
+    DevBuf<REAL> d_delta_tmp2_;
 
     static constexpr unsigned LB_BLOCKS = 128;
     cudaStream_t stream_ = nullptr;
@@ -953,6 +986,38 @@ int bddb200_synchronize(bddb200_solver* s) { REQUIRE_SOLVER(s); return guarded([
 void* bddb200_stream(bddb200_solver* s) { return s ? s->stream_handle() : nullptr; }
 size_t bddb200_kernel_launches(const bddb200_solver* s) { return s ? s->kernel_launches() : 0; }
 int bddb200_delta_sum_buffer(bddb200_solver* s, void** out) { REQUIRE_SOLVER(s); return guarded([&] { *out = s->delta_sum_buffer(); }); }
+
+int bddb200_delta_sum_index(const bddb200_solver* s, int* out) { REQUIRE_SOLVER(s); return guarded([&] { *out = s->delta_sum_index(); }); }
+int bddb200_set_delta_buffers(bddb200_solver* s, void* b0, void* b1, void* b2)
+{
+    REQUIRE_SOLVER(s);
+    if((b0 == nullptr) != (b1 == nullptr) || (b0 == nullptr) != (b2 == nullptr)) { g_last_error = "give three buffers or none"; return BDDB200_ERR_INVALID_ARGUMENT; }
+    return guarded([&] { s->set_delta_buffers(b0, b1, b2); });
+}
+int bddb200_set_delta_input(bddb200_solver* s, void* in, size_t n_shared_vars) { REQUIRE_SOLVER(s); return guarded([&] { s->set_delta_input(in, n_shared_vars); }); }
+
+int bddb200_delta_exchange(void* stream, int precision, int world, int rank, const void* const* peer_bufs_dev, uint32_t* const* flags_dev,
+                           uint32_t epoch, size_t offset_elems, void* out_dev, size_t n_exchange)
+{
+    if(world < 1 || world > EXCHANGE_MAX_WORLD || rank < 0 || rank >= world || peer_bufs_dev == nullptr || flags_dev == nullptr || out_dev == nullptr
+       || (n_exchange & 1))
+    { g_last_error = "bddb200_delta_exchange: invalid argument"; return BDDB200_ERR_INVALID_ARGUMENT; }
+    return guarded([&] {
+        int dev = 0, sms = 0;
+        CUDA_CHECK(cudaGetDevice(&dev));
+        CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const size_t pairs = n_exchange / 2;
+        const unsigned blocks = (unsigned)std::max<size_t>(1, std::min<size_t>((pairs + 255) / 256, (size_t)sms * 4));
+        cudaStream_t st = (cudaStream_t)stream;
+        if(precision == BDDB200_DOUBLE)
+            delta_exchange_kernel<double><<<blocks, 256, 0, st>>>(reinterpret_cast<const double* const*>(peer_bufs_dev), flags_dev, world, rank, epoch, offset_elems,
+                                                                  static_cast<double*>(out_dev), pairs);
+        else
+            delta_exchange_kernel<float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float* const*>(peer_bufs_dev), flags_dev, world, rank, epoch, offset_elems,
+                                                                 static_cast<float*>(out_dev), pairs);
+        CUDA_CHECK(cudaGetLastError());
+    });
+}
 
 int bddb200_trace_pass(bddb200_solver* s, int forward, double omega, unsigned long long* out_host, size_t max_bundles, size_t* n_out)
 { REQUIRE_SOLVER(s); return guarded([&] { *n_out = s->trace_pass(forward, omega, out_host, max_bundles); }); }

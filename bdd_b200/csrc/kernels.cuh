@@ -126,6 +126,8 @@ struct SweepArgs {
     typename real2<REAL>::type* lohi_out;
     REAL* mmd;                 // deferred min-marginal difference per layer entry
     const REAL* delta_in;      // 2V
+    const REAL* delta_in_shared;   // sums of the variables [0, n_shared_vars) after the multi-GPU exchange (== delta_in on one GPU)
+    uint32_t n_shared_vars;
     REAL* delta_out;           // 2V (zeroed before the launch or by the previous pass)
     REAL* zero_buf;            // 2V buffer to clear for the pass after next (may be null)
     REAL* mm_lo_out;           // MODE_MM
@@ -332,7 +334,7 @@ __device__ __forceinline__ void sweep_bundle(const SweepArgs<REAL>& a, const uin
             for(uint32_t e = lane; e < g.n * BPW; e += 32)
             {
                 const int var = s_vn[e].x;
-                if(var >= 0) cp_async_gather<(int)sizeof(R2)>(s_delta + e, a.delta_in + 2 * (size_t)var);
+                if(var >= 0) cp_async_gather<(int)sizeof(R2)>(s_delta + e, ((uint32_t)var < a.n_shared_vars ? a.delta_in_shared : a.delta_in) + 2 * (size_t)var);
             }
             cp_async_commit();
         }
@@ -849,6 +851,10 @@ __device__ __forceinline__ void sweep_lane_bundle(const SweepArgs<REAL>& a, cons
             if(bytes > 0) bulk_g2s(st + off, src, bytes, bar);
         }
     };
+    auto delta_src = [&](int var) -> const REAL* {
+        const uint32_t v = (uint32_t)max(var, 0);
+        return (v < a.n_shared_vars ? a.delta_in_shared : a.delta_in) + 2 * (size_t)v;
+    };
     // gather the delta values of position i; from_global reads the variables from global memory
     // (does not need the chunk to have landed)
     auto gather = [&](uint32_t i, bool from_global, uint32_t h_begin) {
@@ -868,7 +874,7 @@ __device__ __forceinline__ void sweep_lane_bundle(const SweepArgs<REAL>& a, cons
             }
 #pragma unroll
             for(int k = 0; k < 4; ++k)
-                cp_async_gather_if(h + k < cnt && var[k] >= 0, s_delta + (h + k) * 32, a.delta_in + 2 * (size_t)max(var[k], 0));
+                cp_async_gather_if(h + k < cnt && var[k] >= 0, s_delta + (h + k) * 32, delta_src(var[k]));
         }
         cp_async_commit();
     };
@@ -897,7 +903,7 @@ __device__ __forceinline__ void sweep_lane_bundle(const SweepArgs<REAL>& a, cons
     {   // scattered LDG is ~4x cheaper to issue than scattered LDGSTS (tools/microbench/issue_cost.cu)
 #pragma unroll
         for(int k = 0; k < G0; ++k)
-            dl0[k] = *reinterpret_cast<const R2*>(a.delta_in + 2 * (size_t)max(var0[k], 0));
+            dl0[k] = *reinterpret_cast<const R2*>(delta_src(var0[k]));
         if(cnt0 > (uint32_t)G0) gather(0, true, G0); else cp_async_commit();
     }
     if(nc > 1) issue(1, min(NS, nc) - 1, COPY_ALL);
@@ -1346,6 +1352,59 @@ __global__ void lb_final_kernel(const double* __restrict__ partial, double* __re
         __syncthreads();
     }
     if(threadIdx.x == 0) out[0] = sh[0];
+}
+
+// ---- multi-GPU exchange over peer memory (NVLink / NVSwitch), SURVEY 8e ------------------------------------------
+// One-shot all-reduce of the per-variable min-marginal sums of one pass: every rank's rotating sum buffers live in
+// symmetric memory (mapped into every peer), peers[r] is rank r's mapping.  Step 1: tell every peer "my pass `epoch`
+// is complete" (a release store of the epoch into slot `rank` of the peer's flag array) and wait until every peer has
+// said so here.  Step 2: out[i] = sum over ranks (fixed order 0..world-1, so all ranks compute bit-identical sums) of
+// peers[r][offset + i] over the exchanged prefix (the variables shared between shards are numbered first; the passes
+// read those from `out` and all other variables from their own sum buffer).
+// No trailing barrier: the buffers rotate with period three passes, so a buffer read here is next written (zeroed) two
+// passes later, after its owner has waited for this rank's NEXT epoch, which is sent after this kernel.
+constexpr int EXCHANGE_MAX_WORLD = 16;
+
+__device__ __forceinline__ void ld_volatile2(const float* p, float& x, float& y) { asm volatile("ld.volatile.global.v2.f32 {%0, %1}, [%2];" : "=f"(x), "=f"(y) : "l"(p)); }
+__device__ __forceinline__ void ld_volatile2(const double* p, double& x, double& y) { asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "l"(p)); }
+
+template<typename REAL>
+__global__ void __launch_bounds__(256) delta_exchange_kernel(const REAL* const* __restrict__ peers, uint32_t* const* __restrict__ flags, int world, int rank,
+                                                             uint32_t epoch, size_t offset, REAL* __restrict__ out, size_t pairs)
+{
+    using R2 = typename real2<REAL>::type;
+    __shared__ const REAL* peer_s[EXCHANGE_MAX_WORLD];
+    if((int)threadIdx.x < world)
+    {
+        peer_s[threadIdx.x] = peers[threadIdx.x] + offset;
+        if(blockIdx.x == 0)
+        {
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(flags[threadIdx.x] + rank), "r"(epoch) : "memory");
+        }
+        const uint32_t* mine = flags[rank] + threadIdx.x;
+        uint32_t seen;
+        for(uint32_t spins = 0;; ++spins)
+        {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+            if((int32_t)(seen - epoch) >= 0) break;
+            if(spins > (1u << 26)) __trap();          // a peer that never arrives must not hang the GPU
+        }
+    }
+    __syncthreads();
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for(size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += stride)
+    {
+        REAL sx = 0, sy = 0;
+        for(int r = 0; r < world; ++r)
+        {
+            REAL x, y;
+            ld_volatile2(peer_s[r] + 2 * i, x, y);
+            sx += x; sy += y;
+        }
+        R2 o; o.x = sx; o.y = sy;
+        reinterpret_cast<R2*>(out)[i] = o;
+    }
 }
 
 // compute_bdd_sol_func, bdd_cuda_base.cu:1103-1135: per BDD follow the cheaper arc from the

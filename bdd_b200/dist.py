@@ -2,12 +2,21 @@
 
 Within a pass BDDs are independent; the only coupling is the per-variable sum of min-marginal
 differences.  Each rank sweeps its own BDDs with the single-GPU kernels in
-shard mode (global ``nr_bdds_per_var``, full 2V delta vector), and after every pass the
-un-normalised delta sums are all-reduced over ``torch.distributed`` (NCCL over NVLink on the
-GPU box, gloo in the CPU tests).  The next pass divides by the GLOBAL BDD count while reading.
-This is the hybrid CPU+GPU solver's exchange (bdd_multi_parallel_mma_base.cu:266-354:
-accumulate_delta / split_delta / normalize_delta around forward_mm / backward_mm) with a
-collective in place of the host copy.
+shard mode (global ``nr_bdds_per_var``, full 2V delta vector) and after every pass the
+un-normalised delta sums of the variables that occur in more than one shard are summed over
+all ranks; the next pass divides by the GLOBAL BDD count while reading.  This is the hybrid
+CPU+GPU solver's exchange (bdd_multi_parallel_mma_base.cu:266-354: accumulate_delta /
+split_delta / normalize_delta around forward_mm / backward_mm) between GPUs.
+
+Variables are relabelled per solve so that the shared ones come first: only that prefix of
+the delta vector crosses NVLink (for a grid-tile sharded MRF a thin boundary set).
+
+Exchange back ends
+  "symm"  the sum buffers live in symmetric memory (torch.distributed._symmetric_memory:
+          every peer maps them); ``bddb200_delta_exchange`` -- one kernel of this library on
+          the solver's stream -- signals the peers, waits for them and reads their buffers
+          directly over NVLink / NVSwitch (one-shot all-reduce, fixed summation order).
+  "nccl"  ``torch.distributed.all_reduce`` on the prefix (also the gloo path of the CPU tests).
 
 The local solver only has to provide ``forward_pass / backward_pass / delta_sum_view /
 lower_bound`` (``bdd_b200.solver.bdd_cuda_parallel_mma`` does), so the sharding logic can be
@@ -15,6 +24,7 @@ exercised on CPU with a stand-in local solver (tests/test_dist_cpu.py).
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -38,17 +48,89 @@ def partition_bdds(col: BddCollection, world: int) -> List[np.ndarray]:
     return [np.arange(bounds[r], bounds[r + 1]) for r in range(world)]
 
 
-def global_nr_bdds_per_var(col: BddCollection, nr_variables: Optional[int] = None) -> np.ndarray:
-    """In how many BDDs each variable occurs (bdd_cuda_base.cu:66-78), for the whole collection."""
+def _layer_heads(col: BddCollection) -> Tuple[np.ndarray, np.ndarray]:
+    """(variable, BDD) of every inner layer of the collection."""
     idx = col.instrs[:, 2]
     inner = idx < BOTSINK
     var = idx[inner].astype(np.int64)
-    # one count per (BDD, variable): count layer heads = positions where the variable changes
     bdd_of = np.repeat(np.arange(col.nr_bdds), np.diff(col.delims.astype(np.int64)))[inner]
     head = np.ones(var.shape[0], dtype=bool)
     head[1:] = (var[1:] != var[:-1]) | (bdd_of[1:] != bdd_of[:-1])
+    return var[head], bdd_of[head]
+
+
+def global_nr_bdds_per_var(col: BddCollection, nr_variables: Optional[int] = None) -> np.ndarray:
+    """In how many BDDs each variable occurs (bdd_cuda_base.cu:66-78), for the whole collection."""
+    var, _ = _layer_heads(col)
     n = int(var.max()) + 1 if nr_variables is None else nr_variables
-    return np.bincount(var[head], minlength=n).astype(np.int32)
+    return np.bincount(var, minlength=n).astype(np.int32)
+
+
+def shared_first_relabeling(col: BddCollection, parts: List[np.ndarray], nr_vars: int) -> Tuple[np.ndarray, int]:
+    """new_of_old[v] = index of variable v after moving the variables that occur in more than one
+    shard to the front (both groups keep their relative order), and the number of shared ones."""
+    var, bdd = _layer_heads(col)
+    shard_of_bdd = np.empty(col.nr_bdds, dtype=np.int64)
+    for r, ids in enumerate(parts):
+        shard_of_bdd[ids] = r
+    sh = shard_of_bdd[bdd]
+    lo = np.full(nr_vars, np.iinfo(np.int64).max, dtype=np.int64)
+    hi = np.full(nr_vars, -1, dtype=np.int64)
+    np.minimum.at(lo, var, sh)
+    np.maximum.at(hi, var, sh)
+    shared = hi > lo
+    order = np.concatenate([np.nonzero(shared)[0], np.nonzero(~shared)[0]])
+    new_of_old = np.empty(nr_vars, dtype=np.int64)
+    new_of_old[order] = np.arange(nr_vars)
+    return new_of_old, int(shared.sum())
+
+
+def relabel_variables(col: BddCollection, new_of_old: np.ndarray) -> BddCollection:
+    instrs = col.instrs.copy()
+    inner = instrs[:, 2] < BOTSINK
+    instrs[inner, 2] = new_of_old[instrs[inner, 2].astype(np.int64)].astype(np.uint64)
+    return BddCollection(instrs, col.delims)
+
+
+class SymmExchange:
+    """Peer-memory exchange: sum buffers in symmetric memory + bddb200_delta_exchange."""
+
+    def __init__(self, local, n_total: int, n_exchange: int, rank: int, world: int, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self.lib, self.local = _lib.load(), local
+        self.rank, self.world, self.n_total, self.n_exchange = rank, world, n_total, n_exchange
+        self.precision = _lib.DOUBLE if local.precision == "double" else _lib.FLOAT
+        grp = group if group is not None else dist.group.WORLD
+        try:
+            symm_mem.enable_symm_mem_for_group(grp.group_name)
+        except Exception:
+            pass
+        dev = local.device
+        self.block = symm_mem.empty(3 * n_total, dtype=local.value_type, device=dev)
+        self.block.zero_()
+        self.flags = symm_mem.empty(64, dtype=torch.int32, device=dev)
+        self.flags.zero_()
+        self.h_block = symm_mem.rendezvous(self.block, grp)
+        self.h_flags = symm_mem.rendezvous(self.flags, grp)
+        self.out = torch.zeros(max(n_exchange, 2), dtype=local.value_type, device=dev)
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=group)
+        local.set_delta_buffers(self.block)
+        local.set_delta_input(self.out, n_exchange // 2)
+        self.epoch = 0
+        self.itemsize = self.block.element_size()
+
+    def __call__(self):
+        from ._lib import check
+        self.epoch += 1
+        idx = self.local.delta_sum_index()
+        check(self.lib.bddb200_delta_exchange(self.local.stream.cuda_stream, self.precision, self.world, self.rank,
+                                              self.h_block.buffer_ptrs_dev, self.h_flags.buffer_ptrs_dev, self.epoch & 0xFFFFFFFF,
+                                              idx * self.n_total, self.out.data_ptr(), self.n_exchange))
+
+    def sums(self) -> torch.Tensor:
+        return self.out
 
 
 class sharded_mma:
@@ -56,16 +138,47 @@ class sharded_mma:
 
     def __init__(self, col: BddCollection, costs: Sequence[float], rank: int, world: int,
                  make_local: Callable[[BddCollection, np.ndarray, int, np.ndarray], object],
-                 group=None, shard_ids: Optional[np.ndarray] = None):
+                 group=None, shard_ids: Optional[np.ndarray] = None, exchange: Optional[str] = None):
         self.rank, self.world, self.group = rank, world, group
         self.nr_vars = col.nr_variables()
         costs = np.asarray(costs, dtype=np.float64)
         if costs.shape[0] < self.nr_vars:
             costs = np.concatenate([costs, np.zeros(self.nr_vars - costs.shape[0])])
-        self.counts = global_nr_bdds_per_var(col, self.nr_vars)
-        self.ids = partition_bdds(col, world)[rank] if shard_ids is None else shard_ids
-        self.local_col = col.select(self.ids)
-        self.local = make_local(self.local_col, costs, self.nr_vars, self.counts)
+        parts = partition_bdds(col, world)
+        if shard_ids is not None:
+            # explicit shard of this rank: the relabelling needs every rank's shard, so all variables count as shared
+            self.ids = shard_ids
+            self.new_of_old, self.n_shared = np.arange(self.nr_vars), self.nr_vars
+        else:
+            self.ids = parts[rank]
+            self.new_of_old, self.n_shared = shared_first_relabeling(col, parts, self.nr_vars)
+        counts = global_nr_bdds_per_var(col, self.nr_vars)
+        self.counts = np.empty_like(counts)
+        self.counts[self.new_of_old] = counts
+        costs_new = np.empty_like(costs)
+        costs_new[self.new_of_old] = costs
+        self.local_col = relabel_variables(col.select(self.ids), self.new_of_old)
+        self.local = make_local(self.local_col, costs_new, self.nr_vars, self.counts)
+        self.n_exchange = 2 * self.n_shared
+        self.symm = None
+        want = exchange or os.environ.get("BDDB200_EXCHANGE", "auto")
+        is_cuda_local = hasattr(self.local, "set_delta_buffers") and world > 1 and dist.is_initialized() and dist.get_backend(group) == "nccl"
+        if want in ("auto", "symm") and is_cuda_local:
+            ok = torch.ones(1, device=self.local.device)
+            try:
+                self.symm = SymmExchange(self.local, 2 * self.nr_vars, self.n_exchange, rank, world, group)
+            except Exception as e:          # no symmetric-memory support on this box: every rank must fall back together
+                if want == "symm":
+                    raise
+                self.symm_error = repr(e)
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if ok.item() == 0 and self.symm is not None:
+                from ._lib import check
+                check(self.local.lib.bddb200_set_delta_buffers(self.local.h, None, None, None))
+                self.local.set_delta_input(None, 0)
+                self.symm = None
+        self.exchange = "symm" if self.symm is not None else ("all_reduce" if world > 1 else "none")
 
     def _allreduce(self, t: torch.Tensor):
         if self.world <= 1:
@@ -77,27 +190,49 @@ class sharded_mma:
         else:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
 
+    def exchange_sums(self):
+        """Sum the last pass's per-variable sums of the shared variables over all ranks."""
+        if self.world <= 1:
+            return
+        if self.symm is not None:
+            self.symm()
+        elif self.n_exchange > 0:
+            self._allreduce(self.local.delta_sum_view()[: self.n_exchange])
+
     def iteration(self, omega: float = 0.5):
-        """bdd_multi_parallel_mma_base.cu:320-354 with all-reduce as the exchange step."""
+        """bdd_multi_parallel_mma_base.cu:320-354 with the GPU-to-GPU exchange in place of the host copy."""
         self.local.forward_pass(omega)
-        self._allreduce(self.local.delta_sum_view())
+        self.exchange_sums()
         self.local.backward_pass(omega)
-        self._allreduce(self.local.delta_sum_view())
+        self.exchange_sums()
+
+    def delta_sums(self) -> np.ndarray:
+        """Un-normalised per-variable sums after the last exchange, in the ORIGINAL variable order (2V, lo/hi interleaved).
+        Entries of variables that occur neither in this rank's shard nor in several shards are not meaningful."""
+        t = self.local.delta_sum_view()
+        if self.symm is not None:           # shared prefix from the exchanged buffer, the rest from the local sums
+            t = torch.cat([self.symm.sums()[: self.n_exchange], t[self.n_exchange:]])
+        st = getattr(self.local, "stream", None)
+        if st is not None and t.is_cuda:
+            torch.cuda.current_stream(t.device).wait_stream(st)
+        a = t.detach().cpu().numpy().reshape(-1, 2)
+        return a[self.new_of_old].reshape(-1).copy()
 
     def lower_bound(self) -> float:
+        """Sum of the shards' lower bounds (the local value is already on the host: lower_bound() synchronises)."""
         lb = torch.tensor([self.local.lower_bound()], dtype=torch.float64)
         if self.world > 1:
             dev = getattr(self.local, "device", None)
             if dev is not None and dist.get_backend(self.group) == "nccl":
                 lb = lb.to(dev)
-            self._allreduce(lb)
+            dist.all_reduce(lb, op=dist.ReduceOp.SUM, group=self.group)     # on the current stream; .item() waits for it
         return float(lb.item())
 
 
 def make_cuda_local(precision: str, device: int, deterministic: bool = False):
-    """Factory for the GPU local solver: bdd_cuda_parallel_mma in shard mode.  The collective is
-    issued under the solver's own stream (NCCL enqueues on torch's current stream), so pass and
-    exchange stay ordered without host synchronisation."""
+    """Factory for the GPU local solver: bdd_cuda_parallel_mma in shard mode.  Collectives and the
+    exchange kernel are issued on the solver's own stream, so pass and exchange stay ordered without
+    host synchronisation."""
     from .solver import bdd_cuda_parallel_mma
 
     def make(col: BddCollection, costs: np.ndarray, nr_vars: int, counts: np.ndarray):

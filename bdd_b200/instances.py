@@ -64,17 +64,18 @@ class BddCollection:
             blk[inner, 0] -= np.uint64(first)
             blk[inner, 1] -= np.uint64(first)
             return BddCollection(blk, self.delims[ids[0]: ids[-1] + 2] - np.uint64(first))
-        parts = []
-        delims = [0]
-        for b in bdd_ids:
-            first, last = int(self.delims[b]), int(self.delims[b + 1])
-            blk = self.instrs[first:last].astype(np.int64)  # sinks wrap to -1 / -2, restored below
-            nn = last - first - 2
-            blk[:nn, 0] += delims[-1] - first
-            blk[:nn, 1] += delims[-1] - first
-            parts.append(blk.astype(np.uint64))
-            delims.append(delims[-1] + (last - first))
-        return BddCollection(np.concatenate(parts, axis=0), np.asarray(delims, dtype=np.uint64))
+        # general case, vectorised: gather the instruction ranges and shift the child indices of inner nodes
+        sizes = np.diff(self.delims.astype(np.int64))
+        sz = sizes[ids]
+        new_delims = np.concatenate([[0], np.cumsum(sz)])
+        old_first = self.delims.astype(np.int64)[ids]
+        src = np.repeat(old_first - new_delims[:-1], sz) + np.arange(int(new_delims[-1]), dtype=np.int64)
+        blk = self.instrs[src].copy()
+        shift = np.repeat(new_delims[:-1] - old_first, sz)
+        inner = blk[:, 2] < BOTSINK
+        blk[inner, 0] = (blk[inner, 0].astype(np.int64) + shift[inner]).astype(np.uint64)
+        blk[inner, 1] = (blk[inner, 1].astype(np.int64) + shift[inner]).astype(np.uint64)
+        return BddCollection(blk, new_delims.astype(np.uint64))
 
 
 # --------------------------------------------------------------------------- templates --
@@ -360,7 +361,9 @@ def grid_mrf(w: int = 260, h: int = 260, K: int = 4, seed: int = 4) -> Tuple[Bdd
         ConstraintBatch([1] + [-1] * K, EQ, 0, m_u),
         ConstraintBatch([1] + [-1] * K, EQ, 0, m_v),
     ])
-    return col, costs
+    # grid-tile order: every constraint is keyed by its (first) vertex, row-major
+    key = np.concatenate([np.arange(nv), edges[:, 0], np.repeat(edges[:, 0], K), np.repeat(edges[:, 0], K)])
+    return col.select(np.argsort(key, kind="stable")), costs
 
 
 def _both_values_feasible(t: QbddTemplate) -> bool:

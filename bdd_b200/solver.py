@@ -168,6 +168,28 @@ class bdd_cuda_parallel_mma:
         with torch.cuda.stream(self.stream):
             return torch.as_tensor(holder, device=self.device)
 
+    def delta_sum_index(self) -> int:
+        """Which of the three rotating sum buffers holds the sums of the last pass."""
+        out = C.c_int()
+        check(self.lib.bddb200_delta_sum_index(self.h, C.byref(out)))
+        return out.value
+
+    def set_delta_buffers(self, block: torch.Tensor):
+        """Use ``block`` (3 x 2V zero-filled REALs, e.g. symmetric memory mapped by the peer GPUs) as the rotating sum buffers."""
+        n = 2 * self.nr_variables()
+        self._in(block, 3 * n)
+        self._delta_block = block
+        item = block.element_size()
+        check(self.lib.bddb200_set_delta_buffers(self.h, block.data_ptr(), block.data_ptr() + n * item, block.data_ptr() + 2 * n * item))
+
+    def set_delta_input(self, t: Optional[torch.Tensor], n_shared_vars: int = 0):
+        """Passes read the (exchanged, un-normalised) sums of variables [0, n_shared_vars) from ``t`` and the rest from
+        the rotating buffers."""
+        if t is not None:
+            self._in(t)
+        self._delta_input = t
+        check(self.lib.bddb200_set_delta_input(self.h, t.data_ptr() if t is not None else None, int(n_shared_vars)))
+
     def lower_bound(self) -> float:
         out = C.c_double()
         check(self.lib.bddb200_lower_bound(self.h, C.byref(out)))

@@ -287,9 +287,9 @@ def run_ours(args):
         if world > 1:
             local.forward_pass(0.5)
             ev[k][1].record(st)
-            solver._allreduce(local.delta_sum_view())
+            solver.exchange_sums()
             local.backward_pass(0.5)
-            solver._allreduce(local.delta_sum_view())
+            solver.exchange_sums()
         else:
             local.forward_pass(0.5)
             ev[k][1].record(st)
@@ -393,7 +393,8 @@ def run_ours(args):
             "dtype": "f32" if precision == "float" else "f64", "data": "synthetic",
             "config": {"workload": args.workload, "precision": precision, **sh, "shards": world,
                        "l2": "flushed (256 MiB memset) between timed steps; back_to_back = steady state without flush",
-                       "parallelism": f"constraint-sharded x{world}, delta all-reduce per pass" if world > 1 else "single GPU"},
+                       "parallelism": (f"constraint-sharded x{world}, per-pass exchange of {solver.n_shared} shared variables via {solver.exchange}"
+                                       if world > 1 else "single GPU")},
             "back_to_back": {"value": shards / (b2b_ms * 1e-3), "unit": unit, "ms_per_step": b2b_ms},
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": 2 * V * R, "d2h_bytes_per_step": 8,
                     "step": "update_costs(host lo, host hi) + iteration() + lower_bound() through the C ABI, wall clock",

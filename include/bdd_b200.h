@@ -176,6 +176,26 @@ size_t bddb200_kernel_launches(const bddb200_solver* s);
  * buffer holding the UN-normalised sums written by the last pass (2 * nr_variables REALs). */
 int bddb200_delta_sum_buffer(bddb200_solver* s, void** sum_dev);
 
+/* ---- multi-GPU exchange over peer memory (NVLink / NVSwitch), SURVEY 8e -----------------------------
+ * The reference has no multi-GPU code; its only multi-device exchange is the hybrid solver's host-staged
+ * copy of the delta vector (bdd_multi_parallel_mma_base.cu:266-318).  Here each rank keeps its three rotating
+ * sum buffers in symmetric memory that every peer maps (bddb200_set_delta_buffers; zero-filled, 2 * nr_variables
+ * REALs each), numbers the variables that occur in more than one shard first, lets the passes read the exchanged
+ * sums of those n_shared variables from a separate buffer (bddb200_set_delta_input) and, after every pass,
+ * launches bddb200_delta_exchange on the solver's stream: a one-shot all-reduce that reads all peers' buffer
+ * `index` (bddb200_delta_sum_index) directly over NVLink.
+ *   peer_bufs_dev : device array of `world` pointers, entry r = rank r's sum-buffer block as mapped here
+ *   flags_dev     : device array of `world` pointers to each rank's flag array (>= world uint32, zero-filled)
+ *   epoch         : 1, 2, 3, ... one per exchange, the same on every rank
+ *   offset_elems  : start of the exchanged buffer inside the block, in REALs
+ *   n_exchange    : leading REALs (2 * n_shared) summed over all ranks into out_dev */
+int bddb200_delta_sum_index(const bddb200_solver* s, int* index_out);
+int bddb200_set_delta_buffers(bddb200_solver* s, void* buf0_dev, void* buf1_dev, void* buf2_dev);
+int bddb200_set_delta_input(bddb200_solver* s, void* shared_in_dev, size_t n_shared_vars);
+int bddb200_delta_exchange(void* stream, int precision, int world, int rank, const void* const* peer_bufs_dev,
+                           uint32_t* const* flags_dev, uint32_t epoch, size_t offset_elems, void* out_dev,
+                           size_t n_exchange);
+
 /* Diagnostics: run ONE forward (forward != 0) or backward MMA pass and return, for the first
  * max_bundles bundles, 16 clock64() stamps each: [0] warp start, [1] descriptor loaded,
  * [2] first bulk copies issued, [3] first chunk landed, [4+2i] chunk i ready, [5+2i] chunk i

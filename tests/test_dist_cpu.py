@@ -65,7 +65,10 @@ def _worker(rank, world, port, gen, q):
         s.iteration()
         lbs.append(s.lower_bound())
     if rank == 0:
-        q.put((lbs, s.local.sums.numpy().copy()))
+        from bdd_b200.instances import BOTSINK
+        local_new = np.unique(s.local_col.instrs[s.local_col.instrs[:, 2] < BOTSINK, 2].astype(np.int64))
+        old_of_new = np.argsort(s.new_of_old)
+        q.put((lbs, s.delta_sums(), s.n_shared, old_of_new[local_new]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -96,7 +99,7 @@ def test_sharded_equals_single(gen, world):
     procs = [ctx.Process(target=_worker, args=(r, world, port, gen, q)) for r in range(world)]
     for p in procs:
         p.start()
-    lbs, sums = q.get(timeout=120)
+    lbs, sums, n_shared, local_vars = q.get(timeout=120)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -105,7 +108,13 @@ def test_sharded_equals_single(gen, world):
     from bdd_b200.dist import global_nr_bdds_per_var
     cnt = np.maximum(global_nr_bdds_per_var(col), 1)
     d = sums.copy(); d[0::2] /= cnt; d[1::2] /= cnt
-    assert np.allclose(d, o.get_delta(), rtol=0, atol=1e-9)
+    # (rank 0 knows the sums of the variables of its own shard; the shared ones among them were exchanged)
+    sel = np.stack([2 * local_vars, 2 * local_vars + 1], axis=1).reshape(-1)
+    assert np.allclose(d[sel], o.get_delta()[sel], rtol=0, atol=1e-9)
+    # only variables that occur in more than one shard are exchanged: a thin boundary set for the tiled grid
+    assert 0 < n_shared <= col.nr_variables()
+    if gen == "mrf" and world == 2:
+        assert n_shared < col.nr_variables() // 2
 
 
 def test_partition_and_counts():
