@@ -769,14 +769,18 @@ template<> __device__ __forceinline__ float lds_real<float>(uint32_t addr) { flo
 template<> __device__ __forceinline__ double lds_real<double>(uint32_t addr) { double v; asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr)); return v; }
 
 // predicated cp.async / red: no branch in the instruction stream
+// (a scattered 8-byte cp.async.ca blocks the warp ~3x longer than two 4-byte ones or one 16-byte .cg:
+// tools/microbench/issue_cost.cu)
 __device__ __forceinline__ void cp_async_gather_if(bool p, float2* dst, const float* src)
 {
-    asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q cp.async.ca.shared.global [%1], [%2], 8; }"
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0;\n"
+                 "@q cp.async.ca.shared.global [%1], [%2], 4;\n"
+                 "@q cp.async.ca.shared.global [%1+4], [%2+4], 4; }"
                  :: "r"((uint32_t)p), "r"(smem_u32(dst)), "l"(__cvta_generic_to_global(src)) : "memory");
 }
 __device__ __forceinline__ void cp_async_gather_if(bool p, double2* dst, const double* src)
 {
-    asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q cp.async.ca.shared.global [%1], [%2], 16; }"
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q cp.async.cg.shared.global [%1], [%2], 16; }"
                  :: "r"((uint32_t)p), "r"(smem_u32(dst)), "l"(__cvta_generic_to_global(src)) : "memory");
 }
 __device__ __forceinline__ void red_add_if(bool p, float* addr, float v)

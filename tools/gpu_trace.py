@@ -10,9 +10,11 @@ col, costs = instances.set_cover()
 s = bdd_cuda_parallel_mma(col, costs, precision="float")
 for _ in range(5):
     s.iteration()
-for name, fwd in (("forward", True), ("backward", False)):
-    if not fwd:
-        pass
+import torch
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+for name, fwd in (("forward", True), ("backward", False), ("forward, L2 flushed", True), ("backward, L2 flushed", False)):
+    if "flushed" in name:
+        flush.zero_(); torch.cuda.synchronize()
     tr = s.trace_pass(fwd, max_bundles=4096).astype(np.int64)
     t0 = tr[:, 0:1]
     rel = tr[:, 1:14] - t0

@@ -71,7 +71,26 @@ __global__ void bench(const float* src, const int* idx, long long* out, float* s
     t[10] = clock64();
     { uint32_t ok = 0; while(!ok) asm volatile("{ .reg .pred P1; mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2; selp.u32 %0, 1, 0, P1; }" : "=r"(ok) : "r"(smem_u32(bar)), "r"(1) : "memory"); }
     t[11] = clock64();
+    // (f) 16 scattered 16-byte cp.async.cg per lane (L1 bypass)
+    long long u[6];
+    u[0] = clock64();
+#pragma unroll
+    for(int k = 0; k < 16; ++k)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(buf + 16384 + (k * 32 + lane) * 16)), "l"(__cvta_generic_to_global(src + 4 * (size_t)((id[k] ^ 0x3333) >> 1))) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    u[1] = clock64();
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    u[2] = clock64();
+    // (g) 16 scattered 4-byte cp.async.ca per lane
+#pragma unroll
+    for(int k = 0; k < 16; ++k)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_u32(buf + 8192 + (k * 32 + lane) * 4)), "l"(__cvta_generic_to_global(src + (size_t)(id[k] ^ 0x1111))) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    u[3] = clock64();
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    u[4] = clock64();
     if(lane == 0) for(int k = 0; k < 12; ++k) out[blockIdx.x * 12 + k] = t[k] - t[0];
+    if(lane == 0) for(int k = 0; k < 5; ++k) out[148 * 12 + blockIdx.x * 5 + k] = u[k] - u[0];
     sink[blockIdx.x * 32 + lane] = acc + reinterpret_cast<float*>(buf)[lane] + reinterpret_cast<float*>(buf + 8192)[lane];
 }
 
@@ -80,7 +99,7 @@ int main()
     const int B = 148;
     float* src; int* idx; long long* out; float* sink;
     cudaMalloc(&src, (size_t)B * 65536 * 4 + (1 << 24)); cudaMemset(src, 0, (size_t)B * 65536 * 4 + (1 << 24));
-    cudaMalloc(&idx, B * 16 * 32 * 4); cudaMalloc(&out, B * 12 * 8); cudaMalloc(&sink, B * 32 * 4);
+    cudaMalloc(&idx, B * 16 * 32 * 4); cudaMalloc(&out, B * 17 * 8); cudaMalloc(&sink, B * 32 * 4);
     int* h = new int[B * 16 * 32];
     uint32_t s = 12345;
     for(int i = 0; i < B * 16 * 32; ++i) { s = s * 1664525u + 1013904223u; h[i] = (s >> 8) % 1000000; }
@@ -101,6 +120,12 @@ int main()
         printf("  16 x coalesced LDGSTS.64 issue: %.0f   wait: %.0f\n", m[6] - m[5], m[7] - m[6]);
         printf("  16 x scattered LDG.64 issue: %.0f   use: %.0f\n", m[8] - m[7], m[9] - m[8]);
         printf("  1 x UBLKCP 4KiB + expect_tx issue: %.0f   land: %.0f\n", m[10] - m[9], m[11] - m[10]);
+        long long hu[B * 5];
+        cudaMemcpy(hu, out + B * 12, sizeof(hu), cudaMemcpyDeviceToHost);
+        double mu[5] = {0};
+        for(int b = 0; b < B; ++b) for(int k = 0; k < 5; ++k) mu[k] += (double)hu[b * 5 + k] / B;
+        printf("  16 x scattered LDGSTS.128 .cg issue: %.0f   wait: %.0f\n", mu[1] - mu[0], mu[2] - mu[1]);
+        printf("  16 x scattered LDGSTS.32 .ca issue: %.0f   wait: %.0f\n", mu[3] - mu[2], mu[4] - mu[3]);
     }
     printf("err %s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
