@@ -28,6 +28,7 @@ SYMBOLS = [
     "bddb200_gradient_step", "bddb200_synchronize", "bddb200_stream", "bddb200_kernel_launches",
     "bddb200_delta_sum_buffer", "bddb200_layout_stats", "bddb200_trace_pass",
     "bddb200_delta_sum_index", "bddb200_set_delta_buffers", "bddb200_set_delta_input", "bddb200_delta_exchange",
+    "bddb200_lbfgs_create", "bddb200_lbfgs_destroy", "bddb200_lbfgs_iteration", "bddb200_lbfgs_flush", "bddb200_lbfgs_stats",
 ]
 
 
@@ -109,6 +110,11 @@ def load() -> C.CDLL:
         "bddb200_delta_sum_buffer": (i, [vp, C.POINTER(vp)]),
         "bddb200_layout_stats": (i, [vp, sz, vp, sz, i, vp, sz]),
         "bddb200_trace_pass": (i, [vp, i, dbl, vp, sz, C.POINTER(sz)]),
+        "bddb200_lbfgs_create": (i, [vp, i, dbl, dbl, dbl, dbl, C.POINTER(vp)]),
+        "bddb200_lbfgs_destroy": (None, [vp]),
+        "bddb200_lbfgs_iteration": (i, [vp]),
+        "bddb200_lbfgs_flush": (i, [vp]),
+        "bddb200_lbfgs_stats": (i, [vp, C.POINTER(sz), C.POINTER(sz), C.POINTER(dbl)]),
         "bddb200_delta_sum_index": (i, [vp, C.POINTER(i)]),
         "bddb200_set_delta_buffers": (i, [vp, vp, vp, vp]),
         "bddb200_set_delta_input": (i, [vp, vp, sz]),

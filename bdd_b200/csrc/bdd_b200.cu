@@ -103,6 +103,8 @@ struct bddb200_solver {
     virtual bddb200_solver* clone() const = 0;
 };
 
+#include "lbfgs.cuh"
+
 namespace {
 
 template<typename REAL>
@@ -986,6 +988,45 @@ int bddb200_synchronize(bddb200_solver* s) { REQUIRE_SOLVER(s); return guarded([
 void* bddb200_stream(bddb200_solver* s) { return s ? s->stream_handle() : nullptr; }
 size_t bddb200_kernel_launches(const bddb200_solver* s) { return s ? s->kernel_launches() : 0; }
 int bddb200_delta_sum_buffer(bddb200_solver* s, void** out) { REQUIRE_SOLVER(s); return guarded([&] { *out = s->delta_sum_buffer(); }); }
+
+// ---- L-BFGS ("lbfgs cuda mma"), lbfgs.cuh ------------------------------------------------------------------------
+int bddb200_lbfgs_create(bddb200_solver* s, int history_size, double init_step_size, double req_rel_lb_increase,
+                         double step_size_decrease_factor, double step_size_increase_factor, bddb200_lbfgs** out)
+{
+    if(out == nullptr) { g_last_error = "null argument"; return BDDB200_ERR_INVALID_ARGUMENT; }
+    *out = nullptr;
+    REQUIRE_SOLVER(s);
+    LbfgsOptions o;
+    if(history_size != 0) o.history_size = history_size;
+    if(init_step_size > 0) o.init_step_size = init_step_size;
+    if(req_rel_lb_increase > 0) o.req_rel_lb_increase = req_rel_lb_increase;
+    if(step_size_decrease_factor > 0) o.step_size_decrease_factor = step_size_decrease_factor;
+    if(step_size_increase_factor > 0) o.step_size_increase_factor = step_size_increase_factor;
+    if(o.history_size < 2 || o.history_size > 64) { g_last_error = "lbfgs history size must be in [2, 64]"; return BDDB200_ERR_INVALID_ARGUMENT; }   // assert(m > 1), lbfgs_impl.h:30
+    return guarded([&] {
+        CUDA_CHECK(cudaSetDevice(s->device));
+        if(s->precision == BDDB200_DOUBLE) *out = new LbfgsImpl<double>(s, o); else *out = new LbfgsImpl<float>(s, o);
+    });
+}
+void bddb200_lbfgs_destroy(bddb200_lbfgs* l) { delete l; }
+int bddb200_lbfgs_iteration(bddb200_lbfgs* l)
+{
+    if(l == nullptr) { g_last_error = "null lbfgs handle"; return BDDB200_ERR_INVALID_ARGUMENT; }
+    return guarded([&] { l->iteration(); });
+}
+int bddb200_lbfgs_flush(bddb200_lbfgs* l)
+{
+    if(l == nullptr) { g_last_error = "null lbfgs handle"; return BDDB200_ERR_INVALID_ARGUMENT; }
+    return guarded([&] { l->flush(); });
+}
+int bddb200_lbfgs_stats(const bddb200_lbfgs* l, size_t* lbfgs_iterations, size_t* mma_iterations, double* step_size)
+{
+    if(l == nullptr) { g_last_error = "null lbfgs handle"; return BDDB200_ERR_INVALID_ARGUMENT; }
+    if(lbfgs_iterations) *lbfgs_iterations = l->lbfgs_iterations();
+    if(mma_iterations) *mma_iterations = l->mma_iterations();
+    if(step_size) *step_size = l->step_size();
+    return BDDB200_OK;
+}
 
 int bddb200_delta_sum_index(const bddb200_solver* s, int* out) { REQUIRE_SOLVER(s); return guarded([&] { *out = s->delta_sum_index(); }); }
 int bddb200_set_delta_buffers(bddb200_solver* s, void* b0, void* b1, void* b2)

@@ -328,6 +328,45 @@ class bdd_cuda_parallel_mma:
         return self.lib.bddb200_kernel_launches(self.h)
 
 
+class lbfgs_cuda_mma(bdd_cuda_parallel_mma):
+    """``lbfgs<bdd_cuda_parallel_mma<REAL>, device_vector<REAL>, REAL, device_vector<char>, true>`` (include/bdd_solver/lbfgs.h:35-110;
+    config strings "lbfgs cuda mma", "cuda lbfgs parallel mma" and the README spelling "lbfgs cuda parallel mma").  ``iteration()`` is the
+    wrapper's: history bookkeeping, L-BFGS step when the history is full, then one MMA iteration -- all on the device
+    (bdd_b200/csrc/lbfgs.cuh)."""
+
+    def __init__(self, bdd_col: BddCollection, costs: Optional[Sequence[float]] = None, precision: str = "float",
+                 history_size: int = 5, init_step_size: float = 1e-6, req_rel_lb_increase: float = 1e-6,
+                 step_size_decrease_factor: float = 0.8, step_size_increase_factor: float = 1.1, **kw):
+        super().__init__(bdd_col, costs, precision=precision, **kw)
+        h = C.c_void_p()
+        check(self.lib.bddb200_lbfgs_create(self.h, int(history_size), float(init_step_size), float(req_rel_lb_increase),
+                                            float(step_size_decrease_factor), float(step_size_increase_factor), C.byref(h)))
+        self.lh = h
+
+    def __del__(self):
+        lh = getattr(self, "lh", None)
+        if lh:
+            self.lib.bddb200_lbfgs_destroy(lh)
+            self.lh = None
+        super().__del__()
+
+    def iteration(self, omega: float = 0.5):
+        check(self.lib.bddb200_lbfgs_iteration(self.lh))
+
+    def mma_iteration(self, omega: float = 0.5):
+        super().iteration(omega)
+
+    def update_costs(self, cost_delta_0, cost_delta_1):
+        check(self.lib.bddb200_lbfgs_flush(self.lh))          # lbfgs<>::update_costs, lbfgs_impl.h:343-348
+        super().update_costs(cost_delta_0, cost_delta_1)
+
+    def lbfgs_stats(self) -> Tuple[int, int, float]:
+        """(L-BFGS iterations, plain MMA iterations, current step size)"""
+        a, b, st = C.c_size_t(), C.c_size_t(), C.c_double()
+        check(self.lib.bddb200_lbfgs_stats(self.lh, C.byref(a), C.byref(b), C.byref(st)))
+        return a.value, b.value, st.value
+
+
 def run_solver(s, max_iter: int = 1000, tolerance: float = 1e-6, improvement_slope: float = 1e-9,
                time_limit: float = 3600.0, verbose: bool = False, log=print):
     """include/run_solver_util.h:10-77: iterate until one of the four stop rules fires.

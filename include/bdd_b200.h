@@ -167,6 +167,22 @@ int bddb200_net_solver_costs(const bddb200_solver* s, void* out_dev);         /*
 int bddb200_make_dual_feasible(const bddb200_solver* s, void* inout_dev);     /* bdd_cuda_base.cu:1277-1303 */
 int bddb200_gradient_step(bddb200_solver* s, const void* dir_dev, double step); /* bdd_cuda_parallel_mma.h:62-77 */
 
+/* ---- L-BFGS wrapper: lbfgs<bdd_cuda_parallel_mma<REAL>, device_vector<REAL>, REAL, device_vector<char>, true> --------
+ * (include/bdd_solver/lbfgs.h:35-110, src/bdd_solver/lbfgs_impl.h; config strings "lbfgs cuda mma" / "cuda lbfgs parallel mma",
+ * src/bdd_solver/bdd_solver.cpp:222-265).  bddb200_lbfgs_iteration is lbfgs<>::iteration(): store the iterate, then either an
+ * L-BFGS step (two-loop recursion, make_dual_feasible, step-size search by lower bound) followed by one MMA iteration, or a plain
+ * MMA iteration while the history fills.  All vectors stay on the device.  Parameters <= 0 select the reference defaults
+ * (history 5, step 1e-6, required relative increase 1e-6, decrease 0.8, increase 1.1; lbfgs.h:29-33).  The solver must outlive the
+ * wrapper; call bddb200_lbfgs_flush after changing costs from outside (lbfgs<>::update_costs, lbfgs_impl.h:343-348).
+ * The reference template is broken at this commit on both back ends, so there is no reference trajectory to pin. */
+typedef struct bddb200_lbfgs bddb200_lbfgs;
+int bddb200_lbfgs_create(bddb200_solver* s, int history_size, double init_step_size, double req_rel_lb_increase,
+                         double step_size_decrease_factor, double step_size_increase_factor, bddb200_lbfgs** out);
+void bddb200_lbfgs_destroy(bddb200_lbfgs* l);
+int bddb200_lbfgs_iteration(bddb200_lbfgs* l);
+int bddb200_lbfgs_flush(bddb200_lbfgs* l);
+int bddb200_lbfgs_stats(const bddb200_lbfgs* l, size_t* lbfgs_iterations, size_t* mma_iterations, double* step_size);
+
 /* ---- stream plumbing / diagnostics ------------------------------------------------------ */
 int bddb200_synchronize(bddb200_solver* s);
 void* bddb200_stream(bddb200_solver* s);
