@@ -28,6 +28,7 @@ SYMBOLS = [
     "bddb200_gradient_step", "bddb200_synchronize", "bddb200_stream", "bddb200_kernel_launches",
     "bddb200_delta_sum_buffer", "bddb200_layout_stats", "bddb200_trace_pass",
     "bddb200_delta_sum_index", "bddb200_set_delta_buffers", "bddb200_set_delta_input", "bddb200_delta_exchange",
+    "bddb200_run_solver", "bddb200_rounding_perturb", "bddb200_incremental_mm_agreement_rounding",
     "bddb200_lbfgs_create", "bddb200_lbfgs_destroy", "bddb200_lbfgs_iteration", "bddb200_lbfgs_flush", "bddb200_lbfgs_stats",
 ]
 
@@ -110,6 +111,9 @@ def load() -> C.CDLL:
         "bddb200_delta_sum_buffer": (i, [vp, C.POINTER(vp)]),
         "bddb200_layout_stats": (i, [vp, sz, vp, sz, i, vp, sz]),
         "bddb200_trace_pass": (i, [vp, i, dbl, vp, sz, C.POINTER(sz)]),
+        "bddb200_run_solver": (i, [vp, vp, sz, dbl, dbl, dbl, C.POINTER(dbl)]),
+        "bddb200_rounding_perturb": (i, [vp, dbl, i, vp, vp, vp, C.POINTER(i)]),
+        "bddb200_incremental_mm_agreement_rounding": (i, [vp, vp, dbl, dbl, i, i, vp, C.POINTER(i), C.POINTER(i)]),
         "bddb200_lbfgs_create": (i, [vp, i, dbl, dbl, dbl, dbl, C.POINTER(vp)]),
         "bddb200_lbfgs_destroy": (None, [vp]),
         "bddb200_lbfgs_iteration": (i, [vp]),

@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <limits>
@@ -96,6 +98,7 @@ struct bddb200_solver {
     virtual void* stream_handle() = 0;
     virtual size_t kernel_launches() const = 0;
     virtual void* delta_sum_buffer() = 0;
+    virtual int rounding_perturb(double delta, int round_index, unsigned long long counts_out[4], char* types_dev, char* sol_host) = 0;
     virtual int delta_sum_index() const = 0;
     virtual void set_delta_buffers(void* b0, void* b1, void* b2) = 0;
     virtual void set_delta_input(void* in, size_t n_shared_vars) = 0;
@@ -267,6 +270,7 @@ public:
         cudaSetDevice(device);
         if(graph_exec_) cudaGraphExecDestroy(graph_exec_);
         if(h_lb_) cudaFreeHost(h_lb_);
+        if(h_round_counts_) cudaFreeHost(h_round_counts_);
         if(h_stage_) { cudaFreeHost(h_stage_); cudaEventDestroy(stage_free_); }
         if(own_stream_ && stream_) cudaStreamDestroy(stream_);
     }
@@ -761,11 +765,7 @@ public:
     void min_marginals(int sorted, int32_t* primal_dev, void* lo_dev, void* hi_dev) override
     {
         set_device();
-        forward_run();                                   // bdd_cuda_base.cu:721
-        SweepArgs<REAL> a = base_args();
-        zero_lb_sum();
-        launch_sweep<MODE_MM, false>(a);                 // backward_run(true), :728
-        backward_valid_ = true; lb_valid_ = false;
+        min_marginals_internal();                        // forward_run, backward_run(true): bdd_cuda_base.cu:721-728
         const unsigned nb = blocks_for(n_ext_);
         const REAL INF = std::numeric_limits<REAL>::infinity();
         DevBuf<REAL> tmp;
@@ -786,6 +786,50 @@ public:
         }
         CUDA_CHECK(cudaGetLastError());
         if(sorted) CUDA_CHECK(cudaStreamSynchronize(stream_));   // tmp is freed on return
+    }
+
+    // compute the min-marginals of every layer entry into d_mm_lo_ / d_mm_hi_ (bdd_cuda_base.cu:716-736)
+    void min_marginals_internal()
+    {
+        forward_run();
+        SweepArgs<REAL> a = base_args();
+        zero_lb_sum();
+        launch_sweep<MODE_MM, false>(a);
+        backward_valid_ = true; lb_valid_ = false;
+    }
+
+    // perturb_primal_costs, incremental_mm_agreement_rounding_cuda.cu:264-335.  Returns 1 (and fills sol_host) when every
+    // variable's min-marginals agree on a value, else applies the perturbation with update_costs and returns 0.
+    int rounding_perturb(double delta, int round_index, unsigned long long counts_out[4], char* types_dev, char* sol_host) override
+    {
+        set_device();
+        distribute_delta();
+        min_marginals_internal();
+        if(d_round_types_.n == 0)
+        {
+            d_round_types_.alloc(n_vars_); d_round_d0_.alloc(n_vars_); d_round_d1_.alloc(n_vars_); d_round_counts_.alloc(4);
+            CUDA_CHECK(cudaMallocHost(&h_round_counts_, 4 * sizeof(unsigned long long)));
+        }
+        d_round_counts_.zero(stream_);
+        rounding_kernel<REAL><<<blocks_for(n_vars_), 256, 0, stream_>>>(d_var_lay_begin_.p, d_var_lay_.p, d_mm_lo_.p, d_mm_hi_.p, delta, (uint32_t)round_index,
+                                                                       d_round_d0_.p, d_round_d1_.p, d_round_types_.p, d_round_counts_.p, (uint32_t)n_vars_);
+        ++launches_;
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaMemcpyAsync(h_round_counts_, d_round_counts_.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream_));
+        if(types_dev) CUDA_CHECK(cudaMemcpyAsync(types_dev, d_round_types_.p, n_vars_, cudaMemcpyDeviceToDevice, stream_));
+        CUDA_CHECK(cudaStreamSynchronize(stream_));
+        for(int i = 0; i < 4; ++i) counts_out[i] = h_round_counts_[i];
+        if(h_round_counts_[MM_ONE] + h_round_counts_[MM_ZERO] == n_vars_)
+        {   // reconstruct the solution from the min-marginals (:300-309): type one -> 1, type zero -> 0
+            if(sol_host)
+            {
+                CUDA_CHECK(cudaMemcpyAsync(sol_host, d_round_types_.p, n_vars_, cudaMemcpyDeviceToHost, stream_));
+                CUDA_CHECK(cudaStreamSynchronize(stream_));
+            }
+            return 1;
+        }
+        update_costs_dev(d_round_d0_.p, n_vars_, d_round_d1_.p, n_vars_);
+        return 0;
     }
 
     // ---------------------------------------------------------------- L-BFGS surface ---
@@ -864,6 +908,10 @@ private:
     DevBuf<int32_t> d_bundle_bdd_, d_ext_var_, d_ext_bdd_, d_nr_bdds_;
     DevBuf<REAL> d_cfr_, d_cft_, d_lohi_[2], d_mmd_, d_mm_lo_, d_mm_hi_, d_delta_[3], d_delta_tmp_, d_bdd_lb_;
     DevBuf<double> d_lb_partial_;
+    DevBuf<char> d_round_types_;
+    DevBuf<REAL> d_round_d0_, d_round_d1_;
+    DevBuf<unsigned long long> d_round_counts_;
+    unsigned long long* h_round_counts_ = nullptr;
     double* h_lb_ = nullptr;
     REAL* h_stage_ = nullptr;            // pinned staging of host cost vectors
     DevBuf<REAL> d_stage_;
@@ -898,6 +946,29 @@ int guarded(F&& f)
 #define REQUIRE_SOLVER(s) if((s) == nullptr) { g_last_error = "null solver handle"; return BDDB200_ERR_INVALID_ARGUMENT; }
 
 } // namespace
+
+namespace {
+// run_solver, include/run_solver_util.h:10-77, on either the plain solver or its L-BFGS wrapper
+template<typename ITERATE>
+void run_solver_native(bddb200_solver* s, ITERATE&& iterate, size_t max_iter, double tolerance, double improvement_slope, double time_limit_s)
+{
+    const auto start = std::chrono::steady_clock::now();
+    const double lb_initial = s->lower_bound();
+    double lb_first_iter = std::numeric_limits<double>::max(), lb_prev = lb_initial, lb_post = lb_initial;
+    for(size_t it = 0; it < max_iter; ++it)
+    {
+        iterate();
+        lb_prev = lb_post;
+        lb_post = s->lower_bound();
+        if(it == 0) lb_first_iter = lb_post;
+        const double spent = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
+        if(spent > time_limit_s) break;
+        if(std::abs(lb_prev - lb_post) < std::abs(tolerance * lb_prev)) break;
+        if(std::abs(lb_prev - lb_post) < improvement_slope * std::abs(lb_initial - lb_first_iter)) break;
+        if(lb_post == std::numeric_limits<double>::infinity()) break;
+    }
+}
+}
 
 // ======================================================================== C ABI ========
 extern "C" {
@@ -988,6 +1059,48 @@ int bddb200_synchronize(bddb200_solver* s) { REQUIRE_SOLVER(s); return guarded([
 void* bddb200_stream(bddb200_solver* s) { return s ? s->stream_handle() : nullptr; }
 size_t bddb200_kernel_launches(const bddb200_solver* s) { return s ? s->kernel_launches() : 0; }
 int bddb200_delta_sum_buffer(bddb200_solver* s, void** out) { REQUIRE_SOLVER(s); return guarded([&] { *out = s->delta_sum_buffer(); }); }
+
+// ---- primal rounding (incremental_mm_agreement_rounding_cuda.cu) ---------------------------------------------------------
+int bddb200_rounding_perturb(bddb200_solver* s, double delta, int round_index, unsigned long long counts_out[4], char* types_dev, char* sol_host, int* solved)
+{
+    REQUIRE_SOLVER(s);
+    if(counts_out == nullptr || solved == nullptr || !(delta > 0)) { g_last_error = "bddb200_rounding_perturb: invalid argument"; return BDDB200_ERR_INVALID_ARGUMENT; }
+    return guarded([&] { *solved = s->rounding_perturb(delta, round_index, counts_out, types_dev, sol_host); });
+}
+
+int bddb200_run_solver(bddb200_solver* s, bddb200_lbfgs* lbfgs, size_t max_iter, double tolerance, double improvement_slope, double time_limit_s, double* lb_out)
+{
+    REQUIRE_SOLVER(s);
+    return guarded([&] {
+        if(lbfgs) run_solver_native(s, [&] { lbfgs->iteration(); }, max_iter, tolerance, improvement_slope, time_limit_s);
+        else run_solver_native(s, [&] { s->iteration(0.5); }, max_iter, tolerance, improvement_slope, time_limit_s);
+        if(lb_out) *lb_out = s->lower_bound();
+    });
+}
+
+int bddb200_incremental_mm_agreement_rounding(bddb200_solver* s, bddb200_lbfgs* lbfgs, double init_delta, double delta_growth_rate, int num_itr_lb, int num_rounds,
+                                              char* sol_host, int* solved, int* rounds_used)
+{
+    REQUIRE_SOLVER(s);
+    if(!(init_delta > 0) || !(delta_growth_rate > 0) || sol_host == nullptr || solved == nullptr)
+    { g_last_error = "bddb200_incremental_mm_agreement_rounding: invalid argument"; return BDDB200_ERR_INVALID_ARGUMENT; }
+    return guarded([&] {
+        *solved = 0;
+        s->distribute_delta();                                        // :344
+        double cur_delta = init_delta / delta_growth_rate;
+        int round = 0;
+        for(; round < num_rounds; ++round)
+        {
+            cur_delta = std::min(cur_delta * delta_growth_rate, 1e6);
+            unsigned long long counts[4];
+            if(lbfgs) lbfgs->flush();                                 // lbfgs<>::update_costs flushes the history (lbfgs_impl.h:343-348)
+            if(s->rounding_perturb(cur_delta, round, counts, nullptr, sol_host)) { *solved = 1; break; }
+            if(lbfgs) run_solver_native(s, [&] { lbfgs->iteration(); }, (size_t)num_itr_lb, 1e-7, 0.0001, std::numeric_limits<double>::max());
+            else run_solver_native(s, [&] { s->iteration(0.5); }, (size_t)num_itr_lb, 1e-7, 0.0001, std::numeric_limits<double>::max());     // :367
+        }
+        if(rounds_used) *rounds_used = round + (*solved ? 1 : 0);
+    });
+}
 
 // ---- L-BFGS ("lbfgs cuda mma"), lbfgs.cuh ------------------------------------------------------------------------
 int bddb200_lbfgs_create(bddb200_solver* s, int history_size, double init_step_size, double req_rel_lb_increase,

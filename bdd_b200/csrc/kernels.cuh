@@ -1411,6 +1411,65 @@ __global__ void __launch_bounds__(256) delta_exchange_kernel(const REAL* const* 
     }
 }
 
+// ---- primal rounding: one perturbation round of incremental_mm_agreement_rounding_cuda ---------------------------
+// (src/bdd_solver/incremental_mm_agreement_rounding_cuda.cu: mm_diff_direction_func :28-42, compute_mm_types :79-110,
+// compute_mm_sums :124-146, mm_types_transform :148-212).  One thread per variable walks the variable's layers (BDD
+// order): direction of every min-marginal pair (-1: mm_0 + 1e-6 <= mm_1, +1: mm_1 + 1e-6 <= mm_0, else 0), type of the
+// variable from the min / max direction (one / zero / equal / inconsistent), sums of mm_0 and mm_1, and the cost
+// perturbation: one -> (delta, 0), zero -> (0, delta), otherwise |r| * delta on the side the sums (or the sign of r)
+// point away from, r uniform in (-delta, delta).  The reference draws r from thrust::default_random_engine
+// (minstd_rand, x -> 48271 x mod 2^31 - 1, seed 1) discarded by (thread id + round); here the discard count is
+// (variable + round), computed by modular exponentiation, so the perturbation is a pure function of (variable, round).
+enum RoundingType { MM_ZERO = 0, MM_ONE = 1, MM_EQUAL = 2, MM_INCONSISTENT = 3 };
+
+__device__ __forceinline__ uint32_t minstd_after(uint32_t n)
+{   // state after n + 1 steps from seed 1: 48271^(n+1) mod (2^31 - 1)
+    const uint64_t M = 2147483647ull;
+    uint64_t result = 1, base = 48271ull, e = (uint64_t)n + 1ull;
+    while(e) { if(e & 1ull) result = (result * base) % M; base = (base * base) % M; e >>= 1; }
+    return (uint32_t)result;
+}
+
+template<typename REAL>
+__global__ void rounding_kernel(const uint32_t* __restrict__ var_lay_begin, const uint32_t* __restrict__ var_lay, const REAL* __restrict__ mm_lo, const REAL* __restrict__ mm_hi,
+                                double delta, uint32_t round_index, REAL* __restrict__ cost_delta_0, REAL* __restrict__ cost_delta_1, char* __restrict__ types,
+                                unsigned long long* __restrict__ counts, uint32_t n_vars)
+{
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if(v >= n_vars) return;
+    int mn = 2, mx = -2;
+    REAL s0 = 0, s1 = 0;
+    for(uint32_t e = var_lay_begin[v]; e < var_lay_begin[v + 1]; ++e)
+    {
+        const uint32_t l = var_lay[e];
+        const REAL m0 = mm_lo[l], m1 = mm_hi[l];
+        const int dir = ((double)m0 + 1e-6 <= (double)m1) ? -1 : (((double)m1 + 1e-6 <= (double)m0) ? 1 : 0);
+        mn = min(mn, dir); mx = max(mx, dir);
+        s0 += m0; s1 += m1;
+    }
+    int type;
+    if(mn == 2) type = MM_ZERO;               // variable in no BDD (cannot happen in the reference: bdd_cuda_base.cu:471): free, keep 0
+    else if(mn > 0) type = MM_ONE;
+    else if(mx < 0) type = MM_ZERO;
+    else if(mx == 0 && mn == 0) type = MM_EQUAL;
+    else type = MM_INCONSISTENT;
+    types[v] = (char)type;
+    atomicAdd(counts + type, 1ull);
+    REAL d0 = 0, d1 = 0;
+    if(type == MM_ONE) d0 = (REAL)delta;
+    else if(type == MM_ZERO) { if(mn != 2) d1 = (REAL)delta; }
+    else
+    {
+        const uint32_t x = minstd_after(v + round_index);
+        const float u = (float)(x - 1u) / 2147483646.0f;                 // [0, 1)
+        const float r = __fadd_rn((float)(-delta), __fmul_rn(u, (float)(2.0 * delta)));      // uniform_real_distribution<float>(-delta, delta), no fma contraction
+        const REAL amount = (REAL)((double)fabsf(r) * delta);
+        if(type == MM_EQUAL) { if(r < 0.0f) d0 = amount; else d1 = amount; }
+        else { if(s0 < s1) d1 = amount; else d0 = amount; }
+    }
+    cost_delta_0[v] = d0; cost_delta_1[v] = d1;
+}
+
 // compute_bdd_sol_func, bdd_cuda_base.cu:1103-1135: per BDD follow the cheaper arc from the
 // root (tie -> hi), comparing hi_path - lo_path > 0 with path = cfr + (cft[child] + cost).
 template<typename REAL>

@@ -210,11 +210,11 @@ class sharded_mma:
         """Un-normalised per-variable sums after the last exchange, in the ORIGINAL variable order (2V, lo/hi interleaved).
         Entries of variables that occur neither in this rank's shard nor in several shards are not meaningful."""
         t = self.local.delta_sum_view()
-        if self.symm is not None:           # shared prefix from the exchanged buffer, the rest from the local sums
-            t = torch.cat([self.symm.sums()[: self.n_exchange], t[self.n_exchange:]])
         st = getattr(self.local, "stream", None)
         if st is not None and t.is_cuda:
-            torch.cuda.current_stream(t.device).wait_stream(st)
+            torch.cuda.current_stream(t.device).wait_stream(st)       # the passes and the exchange run on the solver's stream
+        if self.symm is not None:           # shared prefix from the exchanged buffer, the rest from the local sums
+            t = torch.cat([self.symm.sums()[: self.n_exchange], t[self.n_exchange:]])
         a = t.detach().cpu().numpy().reshape(-1, 2)
         return a[self.new_of_old].reshape(-1).copy()
 

@@ -78,6 +78,24 @@ class BddCollection:
         return BddCollection(blk, new_delims.astype(np.uint64))
 
 
+def bdds_accept(col: "BddCollection", sol: Sequence[int]) -> np.ndarray:
+    """For every BDD: does the 0/1 assignment ``sol`` (indexed by variable) lead from the root to the top sink?
+    (A primal solution is feasible iff every constraint's BDD accepts it.)  Plain loop: for tests and small instances."""
+    instrs = col.instrs.astype(np.int64)      # sinks wrap to -1 (top) / -2 (bot)
+    ok = np.zeros(col.nr_bdds, dtype=bool)
+    for b in range(col.nr_bdds):
+        i = int(col.delims[b])
+        while True:
+            idx = instrs[i, 2]
+            if idx == -1:
+                ok[b] = True
+                break
+            if idx == -2:
+                break
+            i = int(instrs[i, 1] if sol[idx] else instrs[i, 0])
+    return ok
+
+
 # --------------------------------------------------------------------------- templates --
 
 @dataclass

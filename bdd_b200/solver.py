@@ -314,6 +314,34 @@ class bdd_cuda_parallel_mma:
         check(self.lib.bddb200_gradient_step(self.h, self._in(g, self.nr_layers()).data_ptr(), step_size))
 
     # ------------------------------------------------------------------ plumbing -------
+    # ------------------------------------------------------------------ primal rounding --
+    def rounding_perturb(self, delta: float, round_index: int = 0):
+        """perturb_primal_costs (incremental_mm_agreement_rounding_cuda.cu:264-335).  Returns (solution or None, counts, types):
+        counts = variables of type [zero, one, equal, inconsistent], types = per-variable type (CUDA char tensor)."""
+        n = self.nr_variables()
+        counts = np.zeros(4, dtype=np.uint64)
+        types = self._empty(n, dtype=torch.int8)
+        sol = np.zeros(n, dtype=np.int8)
+        solved = C.c_int()
+        check(self.lib.bddb200_rounding_perturb(self.h, float(delta), int(round_index), counts.ctypes.data, types.data_ptr(), sol.ctypes.data, C.byref(solved)))
+        self._out()
+        return (sol if solved.value else None), counts, types
+
+    def incremental_mm_agreement_rounding(self, init_delta: float = 1.0, delta_growth_rate: float = 1.2, num_itr_lb: int = 100,
+                                          num_rounds: int = 500):
+        """incremental_mm_agreement_rounding_cuda (:338-375; defaults of bdd_solver.cpp:318-335).  Returns (solution or None, rounds used)."""
+        sol = np.zeros(self.nr_variables(), dtype=np.int8)
+        solved, rounds = C.c_int(), C.c_int()
+        check(self.lib.bddb200_incremental_mm_agreement_rounding(self.h, getattr(self, "lh", None), float(init_delta), float(delta_growth_rate),
+                                                                 int(num_itr_lb), int(num_rounds), sol.ctypes.data, C.byref(solved), C.byref(rounds)))
+        return (sol if solved.value else None), rounds.value
+
+    def run_solver(self, max_iter: int = 1000, tolerance: float = 1e-6, improvement_slope: float = 1e-9, time_limit: float = 3600.0) -> float:
+        """run_solver (include/run_solver_util.h:10-77) inside the library; returns the final lower bound."""
+        lb = C.c_double()
+        check(self.lib.bddb200_run_solver(self.h, getattr(self, "lh", None), int(max_iter), float(tolerance), float(improvement_slope), float(time_limit), C.byref(lb)))
+        return lb.value
+
     def synchronize(self):
         check(self.lib.bddb200_synchronize(self.h))
 

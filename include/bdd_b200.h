@@ -183,6 +183,22 @@ int bddb200_lbfgs_iteration(bddb200_lbfgs* l);
 int bddb200_lbfgs_flush(bddb200_lbfgs* l);
 int bddb200_lbfgs_stats(const bddb200_lbfgs* l, size_t* lbfgs_iterations, size_t* mma_iterations, double* step_size);
 
+/* ---- termination loop and primal rounding (the steps after construction in bdd_solver::solve, bdd_solver.cpp:277-380) --
+ * bddb200_run_solver = run_solver (include/run_solver_util.h:10-77): iterate until the iteration limit, the time limit, a relative
+ * improvement below `tolerance`, or an improvement below `improvement_slope` x the first iteration's.  `lbfgs` may be NULL.
+ * bddb200_rounding_perturb = perturb_primal_costs (src/bdd_solver/incremental_mm_agreement_rounding_cuda.cu:264-335): distribute_delta,
+ * min-marginals, per-variable agreement type {0 zero, 1 one, 2 equal, 3 inconsistent}; *solved = 1 and sol_host (nr_variables chars) filled
+ * when every variable is decided, else the costs are perturbed (update_costs) and *solved = 0.  counts_out = number of variables per type;
+ * types_dev (nr_variables chars, device) may be NULL.
+ * bddb200_incremental_mm_agreement_rounding = the whole loop (:338-375): delta grows by delta_growth_rate per round (capped at 1e6),
+ * run_solver(num_itr_lb, 1e-7, 1e-4) between rounds. */
+int bddb200_run_solver(bddb200_solver* s, bddb200_lbfgs* lbfgs, size_t max_iter, double tolerance, double improvement_slope,
+                       double time_limit_s, double* lb_out);
+int bddb200_rounding_perturb(bddb200_solver* s, double delta, int round_index, unsigned long long counts_out[4], char* types_dev,
+                             char* sol_host, int* solved);
+int bddb200_incremental_mm_agreement_rounding(bddb200_solver* s, bddb200_lbfgs* lbfgs, double init_delta, double delta_growth_rate,
+                                              int num_itr_lb, int num_rounds, char* sol_host, int* solved, int* rounds_used);
+
 /* ---- stream plumbing / diagnostics ------------------------------------------------------ */
 int bddb200_synchronize(bddb200_solver* s);
 void* bddb200_stream(bddb200_solver* s);
