@@ -89,6 +89,30 @@ __global__ void bench(const float* src, const int* idx, long long* out, float* s
     u[3] = clock64();
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     u[4] = clock64();
+    // (h) 4 bulk copies of 1 KiB by lane 0, each followed by ~300 cycles of dependent ALU work; (i) the ALU work alone
+    long long w[4];
+    float z = acc;
+    w[0] = clock64();
+    if(lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(4096));
+    for(int k = 0; k < 4; ++k)
+    {
+        if(lane == 0)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(smem_u32(buf + k * 1024)), "l"(__cvta_generic_to_global(base + 20480 + k * 4096)), "r"(1024), "r"(smem_u32(bar)) : "memory");
+#pragma unroll 1
+        for(int j = 0; j < 75; ++j) z = z * 1.0001f + 0.5f;
+    }
+    w[1] = clock64();
+#pragma unroll 1
+    for(int k = 0; k < 4; ++k)
+    {
+#pragma unroll 1
+        for(int j = 0; j < 75; ++j) z = z * 1.0001f + 0.5f;
+    }
+    w[2] = clock64();
+    { uint32_t ok = 0; while(!ok) asm volatile("{ .reg .pred P1; mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2; selp.u32 %0, 1, 0, P1; }" : "=r"(ok) : "r"(smem_u32(bar)), "r"(0) : "memory"); }
+    acc += z;
+    if(lane == 0) { out[148 * 17 + blockIdx.x * 2] = w[1] - w[0]; out[148 * 17 + blockIdx.x * 2 + 1] = w[2] - w[1]; }
     if(lane == 0) for(int k = 0; k < 12; ++k) out[blockIdx.x * 12 + k] = t[k] - t[0];
     if(lane == 0) for(int k = 0; k < 5; ++k) out[148 * 12 + blockIdx.x * 5 + k] = u[k] - u[0];
     sink[blockIdx.x * 32 + lane] = acc + reinterpret_cast<float*>(buf)[lane] + reinterpret_cast<float*>(buf + 8192)[lane];
@@ -99,7 +123,7 @@ int main()
     const int B = 148;
     float* src; int* idx; long long* out; float* sink;
     cudaMalloc(&src, (size_t)B * 65536 * 4 + (1 << 24)); cudaMemset(src, 0, (size_t)B * 65536 * 4 + (1 << 24));
-    cudaMalloc(&idx, B * 16 * 32 * 4); cudaMalloc(&out, B * 17 * 8); cudaMalloc(&sink, B * 32 * 4);
+    cudaMalloc(&idx, B * 16 * 32 * 4); cudaMalloc(&out, B * 19 * 8); cudaMalloc(&sink, B * 32 * 4);
     int* h = new int[B * 16 * 32];
     uint32_t s = 12345;
     for(int i = 0; i < B * 16 * 32; ++i) { s = s * 1664525u + 1013904223u; h[i] = (s >> 8) % 1000000; }
@@ -126,6 +150,11 @@ int main()
         for(int b = 0; b < B; ++b) for(int k = 0; k < 5; ++k) mu[k] += (double)hu[b * 5 + k] / B;
         printf("  16 x scattered LDGSTS.128 .cg issue: %.0f   wait: %.0f\n", mu[1] - mu[0], mu[2] - mu[1]);
         printf("  16 x scattered LDGSTS.32 .ca issue: %.0f   wait: %.0f\n", mu[3] - mu[2], mu[4] - mu[3]);
+        long long hw[B * 2];
+        cudaMemcpy(hw, out + B * 17, sizeof(hw), cudaMemcpyDeviceToHost);
+        double mw[2] = {0};
+        for(int b = 0; b < B; ++b) for(int k = 0; k < 2; ++k) mw[k] += (double)hw[b * 2 + k] / B;
+        printf("  4 x (UBLKCP 1KiB + ALU work): %.0f   the ALU work alone: %.0f   => copies cost %.0f\n", mw[0], mw[1], mw[0] - mw[1]);
     }
     printf("err %s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
