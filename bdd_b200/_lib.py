@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbdd_b200.so")
+LIB_PATH = os.environ.get("BDDB200_LIB", os.path.join(_HERE, "libbdd_b200.so"))      # BDDB200_LIB: A/B builds of the library
 
 OK = 0
 FLOAT, DOUBLE = 0, 1

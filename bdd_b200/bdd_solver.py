@@ -5,6 +5,7 @@ perturbation_rounding on the B200-native solver.  Same keys and defaults as the 
     {"input": "<file.lp or LP text>",                       bdd_solver.cpp:44-66
      "precision": "float" | "double",                       :145-147 (default double)
      "relaxation solver": "cuda parallel mma" | "lbfgs cuda mma" | "cuda lbfgs parallel mma" | "lbfgs cuda parallel mma",
+     "split bdds": {"split length": n},                                                        :105-123, bdd_preprocessor.cpp:372-415
      "lbfgs": {"history size", "initial step size", "required relative lb increase",
                "step size decrease factor", "step size increase factor"},                       :177-199
      "termination criteria": {"maximum iterations": 1000, "minimum improvement": 1e-6,
@@ -16,7 +17,7 @@ Deviations from the reference, all documented in SURVEY 3.1: ``precision`` means
 float solver for "double" and vice versa, bdd_solver.cpp:167-174); the README spelling "lbfgs cuda parallel mma"
 (README.md:56), which matches none of the reference's strings and throws there (:237), is accepted; GPU rounding works
 for every GPU solver (the reference's type list omits cuda parallel mma double, :353-356).  CPU solvers
-("sequential mma", "parallel mma", ...), variable reordering, constraint normalisation, BDD splitting and the export keys
+("sequential mma", "parallel mma", ...), variable reordering, constraint normalisation, the implication BDD of the splitter and the export keys
 belong to subsystems outside this build's scope and raise.
 """
 from __future__ import annotations
@@ -74,10 +75,19 @@ class bdd_solver:
 
     # ---- transform_to_BDDs, :112-123 ------------------------------------------------------------------------------------------
     def transform_to_BDDs(self, config: dict):
-        if "split bdds" in config:
-            raise RuntimeError("BDD splitting (split_qbdd) is not implemented")
         self.log("[bdd solver] Compute BDDs")
-        return instances.from_ilp(self.ilp)
+        col, costs = instances.from_ilp(self.ilp)
+        if "split bdds" in config:
+            sb = config["split bdds"] or {}
+            if sb.get("implication bdd", False):
+                raise RuntimeError("the implication BDD of split_qbdd is not implemented")
+            if "split length" not in sb:
+                raise RuntimeError("'split bdds' needs a 'split length' (the reference's occupancy heuristic compute_split_length is GPU-model specific)")
+            from .split import split_long_bdds
+            n_before = col.nr_bdds
+            col, _ = split_long_bdds(col, int(sb["split length"]), nr_variables=len(costs))      # auxiliary variables carry no cost
+            self.log(f"[bdd preprocessor] force split BDDs longer than {sb['split length']}: {n_before} -> {col.nr_bdds} BDDs")
+        return col, costs
 
     # ---- construct_solver, :130-267 --------------------------------------------------------------------------------------------
     def construct_solver(self, config: dict):

@@ -810,6 +810,9 @@ struct LaneHopIn {
 };
 
 constexpr int LANE_MAX_STAGES = 4;
+#ifndef BDDB200_LANE_UNROLL
+#define BDDB200_LANE_UNROLL 2
+#endif
 
 template<typename REAL, int J, int MODE, bool FORWARD, bool DET>
 __device__ __forceinline__ void sweep_lane_bundle(const SweepArgs<REAL>& a, const LaneDesc d, const uint32_t bundle_in_launch, unsigned char* wsm, uint64_t* bars, const REAL* inv_tab, const int lane)
@@ -996,7 +999,8 @@ __device__ __forceinline__ void sweep_lane_bundle(const SweepArgs<REAL>& a, cons
         auto bit = [](uint32_t t, int j, int arc, int r) -> bool { return (t & (1u << (j * 2 * J + arc * J + r))) != 0; };
 
         In cur = load(FORWARD ? 0u : cnt - 1u);
-#pragma unroll 2
+        constexpr int HOP_UNROLL = BDDB200_LANE_UNROLL;
+#pragma unroll HOP_UNROLL
         for(uint32_t hh = 0; hh < cnt; ++hh)
         {
             const uint32_t h = FORWARD ? hh : cnt - 1 - hh;
@@ -1127,7 +1131,10 @@ __device__ __forceinline__ void sweep_lane_bundle(const SweepArgs<REAL>& a, cons
 }
 
 template<typename REAL, int MODE, bool FORWARD, bool DET>
-__global__ void __launch_bounds__(512, 1) sweep_lane_kernel(const SweepArgs<REAL> a)
+#ifndef BDDB200_LANE_MAX_THREADS
+#define BDDB200_LANE_MAX_THREADS 512
+#endif
+__global__ void __launch_bounds__(BDDB200_LANE_MAX_THREADS, 1) sweep_lane_kernel(const SweepArgs<REAL> a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ REAL inv_tab[INV_TAB];                        // 1 / n for n < INV_TAB (ones when delta_in is already normalised)

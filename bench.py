@@ -31,6 +31,8 @@ from __future__ import annotations
 import argparse
 import json
 import os
+
+import numpy as np
 import statistics
 import subprocess
 import sys
@@ -59,6 +61,11 @@ def make_instance(n_shards: int, workload: str):
     if workload == "assignment_5m":
         col, costs = instances.assignment(1118, seed=3)
         return col, costs, "float"
+    if workload == "assignment_5m_split64":      # the same instance after split_qbdd with chunk length 64 (the reference's answer to long BDDs)
+        from bdd_b200.split import split_long_bdds
+        col, costs = instances.assignment(1118, seed=3)
+        col, n_all = split_long_bdds(col, 64)
+        return col, np.concatenate([costs, np.zeros(n_all - len(costs))]), "float"
     raise SystemExit(f"unknown workload {workload}")
 
 

@@ -275,6 +275,17 @@ class RefCollection:
             raise RuntimeError(self.lib.refw_collection_error(self.h).decode())
         return r
 
+    def split_qbdd(self, bdd_nr: int, chunk_size: int, aux_var_start: int) -> Tuple[int, int]:
+        """bdd_collection::split_qbdd without implication BDD; appends the chunks; returns (number of new BDDs, next aux variable)."""
+        f = self.lib.refw_split_qbdd
+        f.restype = C.c_size_t
+        f.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(C.c_size_t)]
+        n = C.c_size_t()
+        nxt = f(self.h, bdd_nr, chunk_size, aux_var_start, C.byref(n))
+        if nxt == 2 ** 64 - 1:
+            raise RuntimeError(self.lib.refw_collection_error(self.h).decode())
+        return n.value, nxt
+
     def export(self) -> Tuple[np.ndarray, np.ndarray]:
         n = self.lib.refw_nr_instructions(self.h)
         b = self.lib.refw_nr_bdds(self.h)

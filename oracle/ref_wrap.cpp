@@ -125,6 +125,18 @@ long refw_add_constraint(void* c, const int* coeffs, const size_t* vars, size_t 
 
 size_t refw_nr_bdds(void* c) { return static_cast<ref_collection*>(c)->col.nr_bdds(); }
 
+// bdd_collection::split_qbdd(bdd_nr, chunk_size, aux_var_start, false) (bdd_collection.cpp:507-790): appends the chunk BDDs,
+// returns the next free auxiliary variable (or (size_t)-1 on error); *nr_new = number of BDDs appended (1 = not split).
+size_t refw_split_qbdd(void* c, size_t bdd_nr, size_t chunk_size, size_t aux_var_start, size_t* nr_new)
+{
+    auto* rc = static_cast<ref_collection*>(c);
+    try {
+        const auto [new_nrs, next_aux] = rc->col.split_qbdd(bdd_nr, chunk_size, aux_var_start, false);
+        *nr_new = new_nrs.size();
+        return next_aux;
+    } catch(const std::exception& e) { rc->last_error = e.what(); return (size_t)-1; }
+}
+
 size_t refw_nr_instructions(void* c)
 {
     const BDD::bdd_collection& col = static_cast<ref_collection*>(c)->col;
