@@ -1173,6 +1173,28 @@ int bddb200_delta_exchange(void* stream, int precision, int world, int rank, con
     });
 }
 
+int bddb200_delta_exchange_two_shot(void* stream, int precision, int world, int rank, const void* const* peer_bufs_dev, void* const* peer_outs_dev,
+                                    uint32_t* const* flags_dev, uint32_t epoch, size_t offset_elems, size_t n_exchange)
+{
+    if(world < 2 || world > EXCHANGE_MAX_WORLD || rank < 0 || rank >= world || peer_bufs_dev == nullptr || peer_outs_dev == nullptr || flags_dev == nullptr || (n_exchange & 1))
+    { g_last_error = "bddb200_delta_exchange_two_shot: invalid argument"; return BDDB200_ERR_INVALID_ARGUMENT; }
+    return guarded([&] {
+        int dev = 0, sms = 0;
+        CUDA_CHECK(cudaGetDevice(&dev));
+        CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const size_t pairs = n_exchange / 2, per = (pairs + world - 1) / world;
+        const unsigned blocks = (unsigned)std::max<size_t>(1, std::min<size_t>((per + 255) / 256, (size_t)sms * 4));     // co-resident: the CTAs wait for each other
+        cudaStream_t st = (cudaStream_t)stream;
+        if(precision == BDDB200_DOUBLE)
+            delta_exchange2_kernel<double><<<blocks, 256, 0, st>>>(reinterpret_cast<const double* const*>(peer_bufs_dev), reinterpret_cast<double* const*>(peer_outs_dev),
+                                                                   flags_dev, world, rank, epoch, offset_elems, pairs);
+        else
+            delta_exchange2_kernel<float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float* const*>(peer_bufs_dev), reinterpret_cast<float* const*>(peer_outs_dev),
+                                                                  flags_dev, world, rank, epoch, offset_elems, pairs);
+        CUDA_CHECK(cudaGetLastError());
+    });
+}
+
 int bddb200_trace_pass(bddb200_solver* s, int forward, double omega, unsigned long long* out_host, size_t max_bundles, size_t* n_out)
 { REQUIRE_SOLVER(s); return guarded([&] { *n_out = s->trace_pass(forward, omega, out_host, max_bundles); }); }
 

@@ -1418,6 +1418,96 @@ __global__ void __launch_bounds__(256) delta_exchange_kernel(const REAL* const* 
     }
 }
 
+// Two-shot variant for many ranks and long prefixes (a one-shot exchange reads (world - 1) x the prefix per rank; this
+// one 2 x (world - 1) / world of it): after the same arrival barrier every rank sums ONE slice of the prefix over all ranks
+// into its own `out` buffer (symmetric memory as well), tells its peers "slice done" (second flag array, sent by the last
+// CTA to finish), waits for theirs and copies the other slices from the peers' `out` buffers.  All CTAs of the launch must
+// be co-resident (they wait for each other): the host launches at most 4 x 256 threads per SM.
+template<typename REAL>
+__global__ void __launch_bounds__(256) delta_exchange2_kernel(const REAL* const* __restrict__ peers, REAL* const* __restrict__ outs, uint32_t* const* __restrict__ flags,
+                                                              int world, int rank, uint32_t epoch, size_t offset, size_t pairs)
+{
+    using R2 = typename real2<REAL>::type;
+    __shared__ const REAL* peer_s[EXCHANGE_MAX_WORLD];
+    __shared__ REAL* out_s[EXCHANGE_MAX_WORLD];
+    __shared__ bool last_cta;
+    uint32_t* my_flags = flags[rank];
+    if((int)threadIdx.x < world)
+    {
+        peer_s[threadIdx.x] = peers[threadIdx.x] + offset;
+        out_s[threadIdx.x] = outs[threadIdx.x];
+        if(blockIdx.x == 0)
+        {
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(flags[threadIdx.x] + rank), "r"(epoch) : "memory");
+        }
+        const uint32_t* mine = my_flags + threadIdx.x;
+        uint32_t seen;
+        for(uint32_t spins = 0;; ++spins)
+        {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+            if((int32_t)(seen - epoch) >= 0) break;
+            if(spins > (1u << 26)) __trap();
+        }
+    }
+    __syncthreads();
+    const size_t per = (pairs + world - 1) / world;
+    const size_t stride = (size_t)gridDim.x * blockDim.x, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    {   // shot 1: my slice, summed over all ranks in rank order
+        const size_t lo = min(pairs, per * rank), hi = min(pairs, lo + per);
+        REAL* out = out_s[rank];
+        for(size_t i = lo + tid; i < hi; i += stride)
+        {
+            REAL sx = 0, sy = 0;
+            for(int r = 0; r < world; ++r)
+            {
+                REAL x, y;
+                ld_volatile2(peer_s[r] + 2 * i, x, y);
+                sx += x; sy += y;
+            }
+            R2 o; o.x = sx; o.y = sy;
+            reinterpret_cast<R2*>(out)[i] = o;
+        }
+    }
+    // "slice done": the last CTA of this launch to get here tells every peer
+    __threadfence_system();
+    __syncthreads();
+    if(threadIdx.x == 0)
+    {
+        const uint32_t done = atomicAdd(my_flags + 48, 1u);
+        last_cta = done == gridDim.x - 1;
+        if(last_cta) my_flags[48] = 0;
+    }
+    __syncthreads();
+    if(last_cta && (int)threadIdx.x < world)
+        asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(flags[threadIdx.x] + 16 + rank), "r"(epoch) : "memory");
+    if((int)threadIdx.x < world)
+    {
+        const uint32_t* mine = my_flags + 16 + threadIdx.x;
+        uint32_t seen;
+        for(uint32_t spins = 0;; ++spins)
+        {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+            if((int32_t)(seen - epoch) >= 0) break;
+            if(spins > (1u << 26)) __trap();
+        }
+    }
+    __syncthreads();
+    // shot 2: the other ranks' slices, copied from their `out` buffers
+    REAL* out = out_s[rank];
+    for(int q = 1; q < world; ++q)
+    {
+        const int r = (rank + q) % world;
+        const size_t lo = min(pairs, per * r), hi = min(pairs, lo + per);
+        for(size_t i = lo + tid; i < hi; i += stride)
+        {
+            R2 o;
+            ld_volatile2(out_s[r] + 2 * i, o.x, o.y);
+            reinterpret_cast<R2*>(out)[i] = o;
+        }
+    }
+}
+
 // ---- primal rounding: one perturbation round of incremental_mm_agreement_rounding_cuda ---------------------------
 // (src/bdd_solver/incremental_mm_agreement_rounding_cuda.cu: mm_diff_direction_func :28-42, compute_mm_types :79-110,
 // compute_mm_sums :124-146, mm_types_transform :148-212).  One thread per variable walks the variable's layers (BDD

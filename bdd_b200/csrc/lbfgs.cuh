@@ -15,7 +15,8 @@
 // of the lower bound), vectors have nr_layers() entries in layer order, terminal layers 0.
 //
 // B200 shape of it: all vectors stay on the device; one fused kernel per history pair in each loop of the
-// recursion (axpy with the previous coefficient + the dot product that yields the next one, accumulated in double),
+// recursion (axpy with the previous coefficient + the dot product that yields the next one, accumulated in double in a
+// fixed order, so a solve is bit-reproducible),
 // coefficients are passed from kernel to kernel through device memory, so computing a direction is 2m + 1 launches and
 // no host synchronisation.  The only host round trips are the curvature test (one scalar per iteration) and the lower
 // bounds of the step-size search, which are decisions the host loop takes.
@@ -30,20 +31,35 @@ namespace bddb200 {
 
 constexpr int LBFGS_THREADS = 256;
 
-__device__ __forceinline__ void block_sum_to(double v, double* target)
+// Grid-wide sum in a FIXED order (bit-reproducible run to run: the step-size search compares lower bounds, and a last-bit
+// difference in a coefficient can flip one of its decisions): every block writes its partial sum, the last block to arrive adds
+// the partials in index order and stores the total.  `counter` must be zero on entry and is left zero.
+__device__ __forceinline__ void grid_sum_to(double v, double* target, double* partials, unsigned int* counter)
 {
     __shared__ double sh[LBFGS_THREADS / 32];
+    __shared__ bool last;
 #pragma unroll
     for(int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();                        // sh may still be read by a previous call
     if(lane == 0) sh[warp] = v;
     __syncthreads();
-    if(warp == 0)
+    if(threadIdx.x == 0)
     {
-        v = lane < LBFGS_THREADS / 32 ? sh[lane] : 0.0;
-#pragma unroll
-        for(int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if(lane == 0 && v != 0.0) atomicAdd(target, v);
+        double t = 0;
+        for(int w = 0; w < LBFGS_THREADS / 32; ++w) t += sh[w];
+        partials[blockIdx.x] = t;
+        __threadfence();
+        last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if(last && threadIdx.x == 0)
+    {
+        __threadfence();
+        double t = 0;
+        for(unsigned int b = 0; b < gridDim.x; ++b) t += partials[b];
+        *target = t;
+        *counter = 0;
     }
 }
 
@@ -51,7 +67,8 @@ __device__ __forceinline__ void block_sum_to(double v, double* target)
 // out[1] += <y, y>; x_prev = x, g_prev = g.
 template<typename REAL>
 __global__ void __launch_bounds__(LBFGS_THREADS) lbfgs_store_kernel(const REAL* __restrict__ x, const char* __restrict__ g, REAL* __restrict__ x_prev, char* __restrict__ g_prev,
-                                                                    REAL* __restrict__ s, signed char* __restrict__ y, double* __restrict__ out, size_t n, int have_prev)
+                                                                    REAL* __restrict__ s, signed char* __restrict__ y, double* __restrict__ out, double* __restrict__ partials,
+                                                                    unsigned int* __restrict__ counters, size_t n, int have_prev)
 {
     double sy = 0, yy = 0;
     for(size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -67,7 +84,7 @@ __global__ void __launch_bounds__(LBFGS_THREADS) lbfgs_store_kernel(const REAL* 
         }
         x_prev[i] = xi; g_prev[i] = gi;
     }
-    if(have_prev) { block_sum_to(sy, out); __syncthreads(); block_sum_to(yy, out + 1); }
+    if(have_prev) { grid_sum_to(sy, out, partials, counters); grid_sum_to(yy, out + 1, partials + gridDim.x, counters + 1); }
 }
 
 // One step of the two-loop recursion:  d += coef * v  (v = y pair or s pair of the previous step; coef is computed from
@@ -79,7 +96,8 @@ template<typename REAL>
 __global__ void __launch_bounds__(LBFGS_THREADS) lbfgs_step_kernel(REAL* __restrict__ d, const char* __restrict__ g, int mode,
                                                                    const REAL* __restrict__ v_s, const signed char* __restrict__ v_y,
                                                                    const double* __restrict__ alpha_dot, double rho_inv, const double* __restrict__ beta_dot, double rho_scaled,
-                                                                   const REAL* __restrict__ w_s, const signed char* __restrict__ w_y, double* __restrict__ out, size_t n)
+                                                                   const REAL* __restrict__ w_s, const signed char* __restrict__ w_y, double* __restrict__ out,
+                                                                   double* __restrict__ partials, unsigned int* __restrict__ counters, size_t n)
 {
     double coef = 0;
     if(mode == 1) coef = -(*alpha_dot / rho_inv);
@@ -97,7 +115,7 @@ __global__ void __launch_bounds__(LBFGS_THREADS) lbfgs_step_kernel(REAL* __restr
         d[i] = di;
         if(out) acc += (double)di * (double)(w_s ? w_s[i] : (REAL)w_y[i]);
     }
-    if(out) block_sum_to(acc, out);
+    if(out) grid_sum_to(acc, out, partials, counters);
 }
 
 struct LbfgsOptions {
@@ -134,10 +152,16 @@ public:
         hist_s_.reset(new DevBuf<REAL>[m_]); hist_y_.reset(new DevBuf<signed char>[m_]);
         for(int i = 0; i < m_; ++i) { hist_s_[i].alloc(n_); hist_y_[i].alloc(n_); free_slots_.push_back(i); }
         scal_.alloc(2 + 2 * (size_t)m_);
+        partials_.alloc(2 * (size_t)blocks_for_n()); counters_.alloc(2);
+        cudaMemsetAsync(counters_.p, 0, 2 * sizeof(unsigned int), stream_);
         if(cudaMallocHost(&h_scal_, 2 * sizeof(double)) != cudaSuccess) throw std::runtime_error("cudaMallocHost failed");
+        blocks_ = blocks_for_n();
+    }
+    unsigned blocks_for_n() const
+    {
         int dev = 0, sms = 0;
         cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        blocks_ = (unsigned)std::max<size_t>(1, std::min<size_t>((n_ + LBFGS_THREADS - 1) / LBFGS_THREADS, (size_t)sms * 8));
+        return (unsigned)std::max<size_t>(1, std::min<size_t>((s_->nr_layers() + LBFGS_THREADS - 1) / LBFGS_THREADS, (size_t)sms * 8));
     }
     ~LbfgsImpl() override { if(h_scal_) cudaFreeHost(h_scal_); }
 
@@ -176,7 +200,7 @@ private:
     {
         s_->net_solver_costs(x_.p);
         check(cudaMemsetAsync(scal_.p, 0, 2 * sizeof(double), stream_), "memset");
-        lbfgs_store_kernel<REAL><<<blocks_, LBFGS_THREADS, 0, stream_>>>(x_.p, g_.p, x_prev_.p, g_prev_.p, s_new_.p, y_new_.p, scal_.p, n_, prev_stored_ ? 1 : 0);
+        lbfgs_store_kernel<REAL><<<blocks_, LBFGS_THREADS, 0, stream_>>>(x_.p, g_.p, x_prev_.p, g_prev_.p, s_new_.p, y_new_.p, scal_.p, partials_.p, counters_.p, n_, prev_stored_ ? 1 : 0);
         check(cudaGetLastError(), "lbfgs_store_kernel");
         if(!prev_stored_) { prev_stored_ = true; return; }
         check(cudaMemcpyAsync(h_scal_, scal_.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream_), "memcpy");
@@ -203,13 +227,13 @@ private:
         auto S = [&](int i) { return hist_s_[history_[i].slot].p; };
         auto Y = [&](int i) { return hist_y_[history_[i].slot].p; };
         // q = g;  dots_a[k-1] = <s_{k-1}, q>
-        lbfgs_step_kernel<REAL><<<blocks_, LBFGS_THREADS, 0, stream_>>>(d_.p, g_.p, 0, nullptr, nullptr, nullptr, 1.0, nullptr, 0.0, S(k - 1), nullptr, dots_a + (k - 1), n_);
+        lbfgs_step_kernel<REAL><<<blocks_, LBFGS_THREADS, 0, stream_>>>(d_.p, g_.p, 0, nullptr, nullptr, nullptr, 1.0, nullptr, 0.0, S(k - 1), nullptr, dots_a + (k - 1), partials_.p, counters_.p, n_);
         // first loop, newest to oldest: q -= alpha_i y_i; the same launch takes the dot product the next step needs
         for(int i = k - 1; i >= 0; --i)
         {
             const bool last = i == 0;
             lbfgs_step_kernel<REAL><<<blocks_, LBFGS_THREADS, 0, stream_>>>(d_.p, nullptr, 1, nullptr, Y(i), dots_a + i, history_[i].rho_inv, nullptr, 0.0,
-                                                                           last ? nullptr : S(i - 1), last ? Y(0) : nullptr, last ? dots_b + 0 : dots_a + (i - 1), n_);
+                                                                           last ? nullptr : S(i - 1), last ? Y(0) : nullptr, last ? dots_b + 0 : dots_a + (i - 1), partials_.p, counters_.p, n_);
         }
         // second loop, oldest to newest: r += (alpha_i - beta_i) s_i, beta_i = rho_i <y_i, r>; the initial Hessian scaling
         // rho_inv_last / <y_last, y_last> multiplies the oldest pair's rho (lbfgs_impl.h:286-292)
@@ -220,7 +244,7 @@ private:
             double rho = 1.0 / history_[i].rho_inv;
             if(i == 0) rho *= h0;
             lbfgs_step_kernel<REAL><<<blocks_, LBFGS_THREADS, 0, stream_>>>(d_.p, nullptr, 2, S(i), nullptr, dots_a + i, history_[i].rho_inv, dots_b + i, rho,
-                                                                           nullptr, last ? nullptr : Y(i + 1), last ? nullptr : dots_b + (i + 1), n_);
+                                                                           nullptr, last ? nullptr : Y(i + 1), last ? nullptr : dots_b + (i + 1), partials_.p, counters_.p, n_);
         }
         check(cudaGetLastError(), "lbfgs_step_kernel");
     }
@@ -282,7 +306,8 @@ private:
     std::unique_ptr<DevBuf<signed char>[]> hist_y_;
     std::vector<int> free_slots_;
     std::deque<Pair> history_;
-    DevBuf<double> scal_;
+    DevBuf<double> scal_, partials_;
+    DevBuf<unsigned int> counters_;
     double* h_scal_ = nullptr;
     std::deque<double> lb_history_;
     bool prev_stored_ = false;

@@ -113,7 +113,15 @@ class SymmExchange:
         self.flags.zero_()
         self.h_block = symm_mem.rendezvous(self.block, grp)
         self.h_flags = symm_mem.rendezvous(self.flags, grp)
-        self.out = torch.zeros(max(n_exchange, 2), dtype=local.value_type, device=dev)
+        # one-shot reads (world - 1) x the prefix per rank, two-shot 2 (world - 1) / world of it at the price of a second barrier
+        mode = os.environ.get("BDDB200_EXCHANGE_SHOTS", "auto")
+        self.two_shot = mode == "2" or (mode == "auto" and world >= 6 and n_exchange >= (1 << 17))
+        if self.two_shot:
+            self.out = symm_mem.empty(max(n_exchange, 2), dtype=local.value_type, device=dev)
+            self.out.zero_()
+            self.h_out = symm_mem.rendezvous(self.out, grp)
+        else:
+            self.out = torch.zeros(max(n_exchange, 2), dtype=local.value_type, device=dev)
         torch.cuda.synchronize(dev)
         dist.barrier(group=group)
         local.set_delta_buffers(self.block)
@@ -125,6 +133,11 @@ class SymmExchange:
         from ._lib import check
         self.epoch += 1
         idx = self.local.delta_sum_index()
+        if self.two_shot:
+            check(self.lib.bddb200_delta_exchange_two_shot(self.local.stream.cuda_stream, self.precision, self.world, self.rank,
+                                                           self.h_block.buffer_ptrs_dev, self.h_out.buffer_ptrs_dev, self.h_flags.buffer_ptrs_dev,
+                                                           self.epoch & 0xFFFFFFFF, idx * self.n_total, self.n_exchange))
+            return
         check(self.lib.bddb200_delta_exchange(self.local.stream.cuda_stream, self.precision, self.world, self.rank,
                                               self.h_block.buffer_ptrs_dev, self.h_flags.buffer_ptrs_dev, self.epoch & 0xFFFFFFFF,
                                               idx * self.n_total, self.out.data_ptr(), self.n_exchange))
@@ -178,7 +191,7 @@ class sharded_mma:
                 check(self.local.lib.bddb200_set_delta_buffers(self.local.h, None, None, None))
                 self.local.set_delta_input(None, 0)
                 self.symm = None
-        self.exchange = "symm" if self.symm is not None else ("all_reduce" if world > 1 else "none")
+        self.exchange = ("symm two-shot" if self.symm.two_shot else "symm") if self.symm is not None else ("all_reduce" if world > 1 else "none")
 
     def _allreduce(self, t: torch.Tensor):
         if self.world <= 1:

@@ -227,6 +227,13 @@ int bddb200_set_delta_input(bddb200_solver* s, void* shared_in_dev, size_t n_sha
 int bddb200_delta_exchange(void* stream, int precision, int world, int rank, const void* const* peer_bufs_dev,
                            uint32_t* const* flags_dev, uint32_t epoch, size_t offset_elems, void* out_dev,
                            size_t n_exchange);
+/* Two-shot variant for many ranks and long prefixes: every rank sums one slice over all ranks into its own out buffer
+ * (symmetric memory too: peer_outs_dev[r] = rank r's out buffer as mapped here; this rank's result is peer_outs_dev[rank]),
+ * then copies the other slices from the peers.  Reads 2 (world-1)/world of the prefix per rank instead of (world-1) times it.
+ * flags: >= 64 uint32 per rank, zero-filled. */
+int bddb200_delta_exchange_two_shot(void* stream, int precision, int world, int rank, const void* const* peer_bufs_dev,
+                                    void* const* peer_outs_dev, uint32_t* const* flags_dev, uint32_t epoch,
+                                    size_t offset_elems, size_t n_exchange);
 
 /* Diagnostics: run ONE forward (forward != 0) or backward MMA pass and return, for the first
  * max_bundles bundles, 16 clock64() stamps each: [0] warp start, [1] descriptor loaded,

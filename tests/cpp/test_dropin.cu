@@ -11,6 +11,7 @@
 // constraint lists and converted by the reference's own converter.
 #include "bdd_solver/bdd_parallel_mma_base.h"
 #include "bdd_solver/bdd_cuda_parallel_mma.h"
+#include "bdd_solver/lbfgs.h"                      // -> bdd_b200/csrc/host/bdd_solver/lbfgs.h (+ the reference header via #include_next)
 #include "bdd_solver/bdd_branch_instruction.h"
 #include "bdd_conversion/convert_pb_to_bdd.h"
 #include "bdd_manager/bdd_mgr.h"
@@ -223,6 +224,32 @@ static void test_lbfgs_surface(const Problem& p)
     std::printf("lbfgs surface %-22s ok\n", p.name);
 }
 
+// The reference's GPU L-BFGS type (bdd_solver.h:60-61) resolves to the device implementation; it runs inside the reference's run_solver
+// and std::variant like any other solver, keeps the bound monotone and ends at or above plain MMA's bound.
+static void test_lbfgs_wrapper(const Problem& p)
+{
+    using lbfgs_type = lbfgs<bdd_cuda_parallel_mma<double>, thrust::device_vector<double>, double, thrust::device_vector<char>, true>;
+    BDD::bdd_collection bdd_col = build_collection(p);
+    std::variant<bdd_cuda_parallel_mma<double>, lbfgs_type> v = lbfgs_type(bdd_col, p.objective, 5, 1e-3, 1e-6, 0.8, 1.1);
+    bdd_cuda_parallel_mma<double> plain(bdd_col, p.objective);
+    double prev = std::visit([](auto& s) { return s.lower_bound(); }, v);
+    for(int i = 0; i < 25; ++i)
+    {
+        std::visit([](auto& s) { s.iteration(); }, v);
+        plain.iteration();
+        const double lb = std::visit([](auto& s) { return s.lower_bound(); }, v);
+        CHECK(lb >= prev - 1e-9);
+        prev = lb;
+    }
+    CHECK(prev >= plain.lower_bound() - 1e-6);
+    lbfgs_type copy = std::get<lbfgs_type>(v);                       // copy construction: own solver state, empty history
+    copy.iteration();
+    CHECK(copy.lower_bound() >= prev - 1e-9);
+    std::visit([&](auto& s) { run_solver(s, 50, 1e-9, 1e-12, 3600.0); }, v);
+    CHECK(std::abs(std::visit([](auto& s) { return s.lower_bound(); }, v) - p.expected_lb) < 1e-6);
+    std::printf("lbfgs wrapper %-22s ok\n", p.name);
+}
+
 int main()
 {
     std::setvbuf(stdout, nullptr, _IONBF, 0);
@@ -237,6 +264,8 @@ int main()
     test_known_answer<float>(problems[0], 1e-4);
     test_run_solver_and_variant(problems[1]);
     test_lbfgs_surface(problems[1]);
+    test_lbfgs_wrapper(problems[1]);
+    test_lbfgs_wrapper(problems[0]);
     std::printf(failures == 0 ? "ALL OK\n" : "%d FAILURES\n", failures);
     return failures == 0 ? 0 : 1;
 }
