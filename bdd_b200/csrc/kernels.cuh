@@ -836,7 +836,7 @@ __device__ __forceinline__ void sweep_lane_bundle(const SweepArgs<REAL>& a, cons
     auto chunk_first = [&](uint32_t i) { return (FORWARD ? i : nc - 1 - i) * n; };
     // positions [i0, i0 + count): lane l starts copy (l & 3) of position i0 + (l >> 2); all in one UBLKCP issue
     // copies 0 (topology) and 2 ({var, nr_bdds}) are static data, 1 (DP rows) and 3 ({lo, hi}) are written by the previous pass
-    constexpr uint32_t COPY_STATIC = 0x5u, COPY_DYNAMIC = 0xAu, COPY_ALL = 0xFu;
+    constexpr uint32_t COPY_ALL = 0xFu;
     auto issue = [&](uint32_t i0, uint32_t count, uint32_t mask) {
         const uint32_t k = lane >> 2, which = lane & 3;
         if(k < count && ((mask >> which) & 1u))

@@ -408,3 +408,23 @@ def test_grid_mrf_parity():
         s.iteration(); o.iteration()
         assert abs(s.lower_bound() - o.lower_bound()) <= 1e-4 * max(1, abs(o.lower_bound()))
     B.oracle_set_num_threads(1)
+
+
+def test_variable_shared_by_more_bdds_than_the_reciprocal_table():
+    """A variable that occurs in >= 1024 BDDs does not fit the lane-class kernels' reciprocal table: the solver switches to exact
+    division and fixed-order sums, and still matches the oracle."""
+    from bdd_b200.instances import ConstraintBatch, from_batches
+    rng = np.random.default_rng(4)
+    m, n, k = 1100, 1500, 6
+    rows = np.stack([np.sort(rng.choice(np.arange(1, n), size=k - 1, replace=False)) for _ in range(m)])
+    rows = np.concatenate([np.zeros((m, 1), dtype=np.int64), rows], axis=1)          # variable 0 is in every row
+    col = from_batches([ConstraintBatch([1] * k, 1, 1, rows), ConstraintBatch([1] * n, 1, 1, np.arange(n)[None, :])])   # + one BDD covering all variables
+    costs = rng.integers(1, 50, size=n).astype(np.float64)
+    for precision in ("double", "float"):
+        s = solver(col, costs, precision)
+        o = B.Oracle(col.instrs, col.delims, costs, precision)
+        assert s.nr_bdds(0) == m + 1 >= 1024
+        for _ in range(6):
+            s.iteration(); o.iteration()
+            assert abs(s.lower_bound() - o.lower_bound()) <= tol(precision, o.lower_bound())
+        assert np.allclose(s.get_delta().cpu().numpy(), o.get_delta(), rtol=0, atol=tol(precision, 100))
