@@ -143,6 +143,23 @@ public:
         if(const char* e = std::getenv("BDDB200_NO_LANE")) lane_class = std::atoi(e) == 0;
         HostLayout L = build_layout(instrs, n_instr, delims, n_bdds, lanes_per_bdd, opt.nr_variables, sizeof(REAL), stage_budget, lane_class);
         n_lane_ = L.n_lane_bundles; lane_max_J_ = L.lane_max_J; lane_max_hops_ = L.lane_max_hops;
+        {   // runs of lane-class bundles with equal (J, n_hops): arithmetic progressions in every array (layout.hpp emits them back to back)
+            bool ok = std::getenv("BDDB200_NO_CLASS_DESC") == nullptr;
+            for(size_t g = 0; g < L.desc_lane.size() && ok; ++g)
+            {
+                const LaneDesc& d = L.desc_lane[g];
+                if(!lane_cls_begin_.empty())
+                {
+                    const LaneDesc& f = lane_cls_first_.back();
+                    const uint32_t q = (uint32_t)g - lane_cls_begin_.back();
+                    if(d.J == f.J && d.n_hops == f.n_hops && d.slot_off == f.slot_off + q * f.n_hops * f.J * 32u && d.lay_off == f.lay_off + q * f.n_hops * 32u
+                       && d.topo_off == f.topo_off + q * f.n_hops * 32u && d.bdd_base == f.bdd_base + q * 32u) continue;
+                }
+                if(lane_cls_begin_.size() == (size_t)LANE_MAX_CLASSES) { ok = false; break; }
+                lane_cls_first_.push_back(d); lane_cls_begin_.push_back((uint32_t)g);
+            }
+            if(!ok) { lane_cls_first_.clear(); lane_cls_begin_.clear(); }
+        }
         n_vars_ = L.n_vars; n_bdds_ = L.n_bdds; n_instr_ = delims[n_bdds] - delims[0];
         n_ext_ = L.n_layers_ext; n_slots_ = L.n_slots; n_lay_ = L.n_lay; max_hops_ = L.max_hops;
         n_bundles_ = L.bundles.size(); n_small_ = L.n_small_bundles;
@@ -240,6 +257,7 @@ public:
         n_sms_ = o.n_sms_; max_optin_ = o.max_optin_; warps_per_cta_ = o.warps_per_cta_; grid_small_ = o.grid_small_; forced_wpc_ = o.forced_wpc_;
         n_stages_ = o.n_stages_; n_stages_large_ = o.n_stages_large_;
         n_lane_ = o.n_lane_; lane_max_J_ = o.lane_max_J_; lane_max_hops_ = o.lane_max_hops_; lane_wpc_ = o.lane_wpc_; lane_grid_ = o.lane_grid_;
+        lane_cls_first_ = o.lane_cls_first_; lane_cls_begin_ = o.lane_cls_begin_;
         lane_chunk_hops_ = o.lane_chunk_hops_; lane_stages_ = o.lane_stages_; lane_stage_bytes_ = o.lane_stage_bytes_; lane_warp_smem_ = o.lane_warp_smem_;
         stage_small_ = o.stage_small_; stage_large_ = o.stage_large_; warp_smem_small_ = o.warp_smem_small_; warp_smem_large_ = o.warp_smem_large_;
         n_vars_ = o.n_vars_; n_bdds_ = o.n_bdds_; n_instr_ = o.n_instr_; n_ext_ = o.n_ext_; n_slots_ = o.n_slots_; n_lay_ = o.n_lay_;
@@ -297,6 +315,8 @@ public:
             a.inv_tab_g = d_inv_tab_.p; a.inv_count = inv_count_;
             a.bundles_per_cta = (uint32_t)(n_lane_ / lane_grid_); a.bundles_rem = (uint32_t)(n_lane_ % lane_grid_);
             a.zero_pairs_per_bundle = (uint32_t)((n_vars_ + n_lane_ - 1) / n_lane_);
+            a.n_classes = (uint32_t)lane_cls_begin_.size();
+            for(size_t c = 0; c < lane_cls_begin_.size(); ++c) { a.cls_first[c] = lane_cls_first_[c]; a.cls_begin[c] = lane_cls_begin_[c]; }
             // programmatic dependent launch: the kernel's start-up (descriptor, static topology, variable indices) overlaps the
             // tail of the previous kernel in the stream; it waits (griddepcontrol.wait) before touching anything a pass writes
             cudaLaunchConfig_t cfg{};
@@ -889,6 +909,8 @@ private:
     size_t n_lane_ = 0;
     uint32_t lane_max_J_ = 0, lane_max_hops_ = 0, lane_chunk_hops_ = 1, lane_stages_ = 2, lane_stage_bytes_ = 0, lane_warp_smem_ = 0;
     unsigned lane_wpc_ = 1, lane_grid_ = 1;
+    std::vector<LaneDesc> lane_cls_first_;
+    std::vector<uint32_t> lane_cls_begin_;
     unsigned warps_per_cta_ = 4, grid_small_ = 1, forced_wpc_ = 0, n_stages_ = 3, n_stages_large_ = 2;
     uint32_t stage_small_ = 0, stage_large_ = 0, warp_smem_small_ = 0, warp_smem_large_ = 0;
     size_t n_vars_ = 0, n_bdds_ = 0, n_instr_ = 0, n_ext_ = 0, n_slots_ = 0, n_lay_ = 0, max_hops_ = 0, n_bundles_ = 0, n_small_ = 0;

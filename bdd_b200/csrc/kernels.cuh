@@ -67,10 +67,17 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
 }
+#ifndef BDDB200_FENCE
+#define BDDB200_FENCE 2
+#endif
 __device__ __forceinline__ void mbar_fence_init()
 {
     // make the generic-proxy mbarrier initialisation visible to the async proxy (TMA) of this CTA
+#if BDDB200_FENCE == 2
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#elif BDDB200_FENCE == 1
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
 {
@@ -113,6 +120,8 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 constexpr uint32_t INV_TAB_BYTES = 1024 * 8;   // INV_TAB REALs, sized for double
 constexpr int TRACE_EVENTS = 16;
 
+constexpr int LANE_MAX_CLASSES = 8;
+
 template<typename REAL>
 struct SweepArgs {
     const uint32_t* desc;      // DESC_WORDS words per bundle, in this pass's direction
@@ -145,6 +154,13 @@ struct SweepArgs {
     uint32_t inv_count;
     uint32_t bundles_per_cta, bundles_rem;   // lane-class kernel: CTA b owns bundles_per_cta (+1 if b < bundles_rem) consecutive bundles
     uint32_t zero_pairs_per_bundle;          // lane-class kernel: every warp clears this many {lo, hi} pairs of zero_buf
+    // lane-class kernel: runs of bundles with equal (J, n_hops) are arithmetic progressions in every array; with at most
+    // LANE_MAX_CLASSES runs the descriptor of a bundle is computed from these kernel parameters instead of being loaded, so
+    // that the CTA prologue contains no global load at all (one memory round trip less before the first copy is issued);
+    // n_classes == 0: load LaneDesc from `desc`
+    LaneDesc cls_first[LANE_MAX_CLASSES];    // descriptor of the first bundle of each run
+    uint32_t cls_begin[LANE_MAX_CLASSES];    // index of that bundle
+    uint32_t n_classes;
     uint32_t warp_smem_bytes;  // n_stages * stage_bytes + 2 frontier buffers + mbarriers, rounded to 128
                                // (the CTA's dynamic shared memory starts with the INV_TAB_BYTES reciprocal table)
     unsigned long long* trace; // diagnostics: TRACE_EVENTS clock64() stamps per bundle (null = off)
@@ -1151,11 +1167,23 @@ __global__ void __launch_bounds__(BDDB200_LANE_MAX_THREADS, 1) sweep_lane_kernel
         tr[0] = clock64(); tr[TRACE_EVENTS - 1] = smid;
     }
     LaneDesc d{};
-    if(active) d = reinterpret_cast<const LaneDesc*>(a.desc)[a.bundle_first + g];     // in flight during the CTA prologue
+    if(active)
+    {
+        if(a.n_classes == 0) d = reinterpret_cast<const LaneDesc*>(a.desc)[a.bundle_first + g];     // in flight during the CTA prologue
+        else
+        {
+            uint32_t c = 0;
+#pragma unroll
+            for(int k = 1; k < LANE_MAX_CLASSES; ++k) if((uint32_t)k < a.n_classes && g >= a.cls_begin[k]) c = k;
+            d = a.cls_first[c];
+            const uint32_t q = g - a.cls_begin[c];
+            d.slot_off += q * d.n_hops * d.J * 32u; d.lay_off += q * d.n_hops * 32u; d.topo_off += q * d.n_hops * 32u; d.bdd_base += q * 32u;
+        }
+    }
     if(threadIdx.x < (blockDim.x >> 5) * a.n_stages) mbar_init(bars_all + threadIdx.x, 1);
     if(threadIdx.x == 0) mbar_fence_init();
-    if(MODE == MODE_MMA && !DET)
-        for(uint32_t i = threadIdx.x; i < a.inv_count; i += blockDim.x) inv_tab[i] = a.inv_tab_g[i];
+    if(MODE == MODE_MMA && !DET)       // 1 / n for the counts that occur (computed, not loaded: no global load in the prologue)
+        for(uint32_t i = threadIdx.x; i < a.inv_count; i += blockDim.x) inv_tab[i] = (REAL)1 / (REAL)(i > 0 ? i : 1);
     __syncthreads();
     if(FORWARD && a.lb_sum != nullptr && blockIdx.x == 0 && threadIdx.x == 0)
     {   // the previous backward pass accumulated into it
