@@ -236,8 +236,8 @@ public:
         for(int i = 0; i < 3; ++i) { d_delta_[i].alloc(2 * n_vars_); d_delta_[i].zero(stream_); }
         d_delta_tmp_.alloc(2 * n_vars_);
         d_bdd_lb_.alloc(n_bdds_);
-        d_lb_partial_.alloc(LB_BLOCKS + 2); d_lb_partial_.zero(stream_);
-        CUDA_CHECK(cudaMallocHost(&h_lb_, sizeof(double)));
+        d_lb_partial_.alloc(LB_BLOCKS + 1 + LB_SLOTS); d_lb_partial_.zero(stream_);
+        CUDA_CHECK(cudaMallocHost(&h_lb_, LB_SLOTS * sizeof(double)));
 
         configure_kernels();
 
@@ -276,7 +276,7 @@ public:
         for(int i = 0; i < 3; ++i) d_delta_[i].clone_from(o.d_delta_[i], stream_);
         d_inv_tab_.clone_from(o.d_inv_tab_, stream_); inv_count_ = o.inv_count_; pdl_ = o.pdl_;
         d_delta_tmp_.clone_from(o.d_delta_tmp_, stream_); d_bdd_lb_.clone_from(o.d_bdd_lb_, stream_); d_lb_partial_.clone_from(o.d_lb_partial_, stream_);
-        CUDA_CHECK(cudaMallocHost(&h_lb_, sizeof(double)));
+        CUDA_CHECK(cudaMallocHost(&h_lb_, LB_SLOTS * sizeof(double)));
         cc_ = o.cc_; dcur_ = o.dcur_; delta_needs_norm_ = o.delta_needs_norm_;
         forward_valid_ = o.forward_valid_; backward_valid_ = o.backward_valid_; lb_valid_ = o.lb_valid_; lb_ = o.lb_;
         configure_kernels();
@@ -394,16 +394,24 @@ public:
         unsigned ctas_per_sm = 1;
         const unsigned forced = env_u("BDDB200_LANE_WARPS_PER_CTA", 0);
         if(forced) { lane_wpc_ = std::min(forced, 16u); lane_grid_ = blocks_for(n_lane_, lane_wpc_); ctas_per_sm = std::max(1u, env_u("BDDB200_LANE_CTAS_PER_SM", 1)); }
-        else if(n_lane_ <= (size_t)n_sms_ * 8)
-        {   // less than one wave: one CTA on every SM, the shared memory goes into deep stages
+        else if(n_lane_ <= (size_t)n_sms_ * 16)
+        {   // at most one wave of 16 warps per SM: one CTA on every SM, the bundles dealt evenly (no second, partly filled wave);
+            // the fewer warps, the deeper the stages the shared memory is spent on
             lane_grid_ = (unsigned)std::min<size_t>(n_lane_, (size_t)n_sms_);
             lane_wpc_ = (unsigned)((n_lane_ + lane_grid_ - 1) / lane_grid_);
         }
         else
-        {   // several waves: as many resident warps as leave every stage about six hops (the per-chunk cost -- four bulk-copy
-            // issues, one batch of gathers -- is about two hops of arithmetic)
-            const size_t warps = std::min<size_t>(16, std::max<size_t>(4, (size_t)(227 * 1024) / (lane_stages_ * 6 * per_hop)));
-            if(warps >= 12) { ctas_per_sm = 2; lane_wpc_ = (unsigned)(warps / 2); } else lane_wpc_ = (unsigned)warps;
+        {   // several waves: between 8 and 16 resident warps per SM, as many as leave every stage about six hops (the per-chunk cost --
+            // four bulk-copy issues, one batch of gathers -- is about two hops of arithmetic), adjusted so that the last wave is
+            // as full as possible (time ~ waves x warps per SM)
+            const size_t w_max = std::min<size_t>(16, std::max<size_t>(8, (size_t)(227 * 1024) / (lane_stages_ * 6 * per_hop)));
+            size_t best_w = w_max, best_cost = ~(size_t)0;
+            for(size_t w = w_max; w >= 8; --w)
+            {
+                const size_t waves = (n_lane_ + (size_t)n_sms_ * w - 1) / ((size_t)n_sms_ * w);
+                if(waves * w < best_cost) { best_cost = waves * w; best_w = w; }
+            }
+            if(best_w >= 12 && best_w % 2 == 0) { ctas_per_sm = 2; lane_wpc_ = (unsigned)(best_w / 2); } else lane_wpc_ = (unsigned)best_w;
             lane_grid_ = blocks_for(n_lane_, lane_wpc_);
         }
         const size_t sm_total = 228 * 1024;                             // per SM; every resident CTA reserves 1 KiB
@@ -447,7 +455,7 @@ public:
 
     void zero_lb_sum()
     {
-        if(!deterministic_) CUDA_CHECK(cudaMemsetAsync(d_lb_partial_.p + LB_BLOCKS + 1, 0, sizeof(double), stream_));
+        if(!deterministic_) CUDA_CHECK(cudaMemsetAsync(d_lb_partial_.p + LB_BLOCKS + 1, 0, LB_SLOTS * sizeof(double), stream_));
     }
 
     SweepArgs<REAL> base_args() const
@@ -678,9 +686,12 @@ public:
                 launches_ += 2;
                 src = d_lb_partial_.p + LB_BLOCKS;
             }
-            CUDA_CHECK(cudaMemcpyAsync(h_lb_, src, sizeof(double), cudaMemcpyDeviceToHost, stream_));
+            const int n_parts = deterministic_ ? 1 : LB_SLOTS;          // the sweep keeps LB_SLOTS partial sums (one per CTA index mod LB_SLOTS)
+            CUDA_CHECK(cudaMemcpyAsync(h_lb_, src, n_parts * sizeof(double), cudaMemcpyDeviceToHost, stream_));
             CUDA_CHECK(cudaStreamSynchronize(stream_));
-            lb_ = *h_lb_; lb_valid_ = true;
+            lb_ = 0.0;
+            for(int i = 0; i < n_parts; ++i) lb_ += h_lb_[i];
+            lb_valid_ = true;
         }
         return lb_;
     }

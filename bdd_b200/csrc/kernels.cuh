@@ -35,6 +35,7 @@
 namespace bddb200 {
 
 enum SweepMode { MODE_MMA = 0, MODE_PLAIN = 1, MODE_MM = 2 };
+constexpr int LB_SLOTS = 64;
 
 template<typename REAL> struct real2;
 template<> struct real2<float> { using type = float2; };
@@ -142,7 +143,8 @@ struct SweepArgs {
     REAL* mm_lo_out;           // MODE_MM
     REAL* mm_hi_out;
     REAL* bdd_lb;              // backward: cost_from_terminal of every BDD's root
-    double* lb_sum;            // backward: += sum of the roots' cost_from_terminal (null = off); forward kernels zero it
+    double* lb_sum;            // backward: LB_SLOTS partial sums of the roots' cost_from_terminal, slot = CTA index mod LB_SLOTS (one address
+                               // would serialise tens of thousands of atomics in L2); null = off; forward kernels zero them
     REAL omega;
     uint32_t n_zero;
     uint32_t bundle_first, bundle_count;
@@ -686,7 +688,7 @@ __device__ __forceinline__ void sweep_bundle(const SweepArgs<REAL>& a, const uin
             double v = mine_valid ? (double)root : 0.0;
 #pragma unroll
             for(int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if(lane == 0) atomicAdd(a.lb_sum, v);
+            if(lane == 0) atomicAdd(a.lb_sum + (blockIdx.x & (LB_SLOTS - 1)), v);
         }
     }
 }
@@ -698,7 +700,8 @@ __global__ void __launch_bounds__(512, 1) sweep_kernel(const SweepArgs<REAL> a)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wpc = blockDim.x >> 5;
     REAL* inv_tab = reinterpret_cast<REAL*>(smem_raw);       // 1 / n for n < INV_TAB, shared by the CTA
-    if(FORWARD && a.lb_sum != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *a.lb_sum = 0.0;
+    if(FORWARD && a.lb_sum != nullptr && blockIdx.x == 0)
+        for(int i = threadIdx.x; i < LB_SLOTS; i += blockDim.x) a.lb_sum[i] = 0.0;
     if(MODE == MODE_MMA)
     {
         if(a.zero_buf != nullptr)
@@ -1141,7 +1144,7 @@ __device__ __forceinline__ void sweep_lane_bundle(const SweepArgs<REAL>& a, cons
             double v = mine_valid ? (double)root : 0.0;
 #pragma unroll
             for(int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if(lane == 0) atomicAdd(a.lb_sum, v);
+            if(lane == 0) atomicAdd(a.lb_sum + (blockIdx.x & (LB_SLOTS - 1)), v);
         }
     }
 }
@@ -1185,10 +1188,10 @@ __global__ void __launch_bounds__(BDDB200_LANE_MAX_THREADS, 1) sweep_lane_kernel
     if(MODE == MODE_MMA && !DET)       // 1 / n for the counts that occur (computed, not loaded: no global load in the prologue)
         for(uint32_t i = threadIdx.x; i < a.inv_count; i += blockDim.x) inv_tab[i] = (REAL)1 / (REAL)(i > 0 ? i : 1);
     __syncthreads();
-    if(FORWARD && a.lb_sum != nullptr && blockIdx.x == 0 && threadIdx.x == 0)
-    {   // the previous backward pass accumulated into it
+    if(FORWARD && a.lb_sum != nullptr && blockIdx.x == 0 && threadIdx.x < 32)
+    {   // the previous backward pass accumulated into them
         pdl_wait();
-        *a.lb_sum = 0.0;
+        for(int i = threadIdx.x; i < LB_SLOTS; i += 32) a.lb_sum[i] = 0.0;
     }
     if(!active) return;
     unsigned char* wsm = smem_raw + (size_t)warp * a.warp_smem_bytes;
