@@ -142,7 +142,8 @@ struct SweepArgs {
     REAL* zero_buf;            // 2V buffer to clear for the pass after next (may be null)
     REAL* mm_lo_out;           // MODE_MM
     REAL* mm_hi_out;
-    REAL* bdd_lb;              // backward: cost_from_terminal of every BDD's root
+    REAL* bdd_lb;              // backward: cost_from_terminal of every BDD's root, in bundle order (entry bdd_base + lane group, like
+                               // bundle_bdd; 0 where a lane group holds no BDD): coalesced stores instead of one scattered store per BDD
     double* lb_sum;            // backward: LB_SLOTS partial sums of the roots' cost_from_terminal, slot = CTA index mod LB_SLOTS (one address
                                // would serialise tens of thousands of atomics in L2); null = off; forward kernels zero them
     REAL omega;
@@ -682,7 +683,7 @@ __device__ __forceinline__ void sweep_bundle(const SweepArgs<REAL>& a, const uin
     {
         const REAL root = SMEM_FRONTIER ? nxt[lane] : fr[0];       // root = node 0 of hop 0
         const bool mine_valid = p == 0 && bdd_index >= 0;
-        if(mine_valid) a.bdd_lb[bdd_index] = root;
+        if(p == 0) a.bdd_lb[bdd_base + bl] = mine_valid ? root : (REAL)0;
         if(a.lb_sum != nullptr)
         {   // lower_bound, bdd_cuda_base.cu:1243-1251: sum over BDDs in double
             double v = mine_valid ? (double)root : 0.0;
@@ -1138,7 +1139,7 @@ __device__ __forceinline__ void sweep_lane_bundle(const SweepArgs<REAL>& a, cons
     {
         const REAL root = fr[0];                                    // root = row 0 of hop 0
         const bool mine_valid = bdd_index >= 0;
-        if(mine_valid) a.bdd_lb[bdd_index] = root;
+        a.bdd_lb[d.bdd_base + lane] = mine_valid ? root : (REAL)0;
         if(a.lb_sum != nullptr)
         {   // lower_bound, bdd_cuda_base.cu:1243-1251: sum over BDDs in double
             double v = mine_valid ? (double)root : 0.0;
