@@ -263,7 +263,7 @@ public:
         n_sms_ = o.n_sms_; max_optin_ = o.max_optin_; warps_per_cta_ = o.warps_per_cta_; grid_small_ = o.grid_small_; forced_wpc_ = o.forced_wpc_;
         n_stages_ = o.n_stages_; n_stages_large_ = o.n_stages_large_;
         n_lane_ = o.n_lane_; lane_max_J_ = o.lane_max_J_; lane_max_hops_ = o.lane_max_hops_; lane_wpc_ = o.lane_wpc_; lane_grid_ = o.lane_grid_;
-        lane_cls_first_ = o.lane_cls_first_; lane_cls_begin_ = o.lane_cls_begin_;
+        lane_cls_first_ = o.lane_cls_first_; lane_cls_begin_ = o.lane_cls_begin_; lane_dense_ = o.lane_dense_;
         lane_chunk_hops_ = o.lane_chunk_hops_; lane_stages_ = o.lane_stages_; lane_stage_bytes_ = o.lane_stage_bytes_; lane_warp_smem_ = o.lane_warp_smem_;
         stage_small_ = o.stage_small_; stage_large_ = o.stage_large_; warp_smem_small_ = o.warp_smem_small_; warp_smem_large_ = o.warp_smem_large_;
         n_vars_ = o.n_vars_; n_bdds_ = o.n_bdds_; n_instr_ = o.n_instr_; n_ext_ = o.n_ext_; n_slots_ = o.n_slots_; n_lay_ = o.n_lay_;
@@ -332,7 +332,8 @@ public:
             attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             attr[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr; cfg.numAttrs = pdl_ ? 1 : 0;
-            if(MODE == MODE_MMA && deterministic_) CUDA_CHECK(cudaLaunchKernelEx(&cfg, sweep_lane_kernel<REAL, MODE, FORWARD, MODE == MODE_MMA>, a));
+            if(MODE == MODE_MMA && !deterministic_ && lane_dense_) CUDA_CHECK(cudaLaunchKernelEx(&cfg, sweep_lane_kernel_dense<REAL, FORWARD>, a));
+            else if(MODE == MODE_MMA && deterministic_) CUDA_CHECK(cudaLaunchKernelEx(&cfg, sweep_lane_kernel<REAL, MODE, FORWARD, MODE == MODE_MMA>, a));
             else CUDA_CHECK(cudaLaunchKernelEx(&cfg, sweep_lane_kernel<REAL, MODE, FORWARD, false>, a));
             ++launches_;
             a.zero_buf = nullptr;
@@ -417,7 +418,11 @@ public:
                 const size_t waves = (n_lane_ + (size_t)n_sms_ * w - 1) / ((size_t)n_sms_ * w);
                 if(waves * w < best_cost) { best_cost = waves * w; best_w = w; }
             }
-            if(best_w >= 12 && best_w % 2 == 0) { ctas_per_sm = 2; lane_wpc_ = (unsigned)(best_w / 2); } else lane_wpc_ = (unsigned)best_w;
+            // float, many waves: the register-capped build of the MMA pass runs 24 warps per SM (3 CTAs of 8) if that leaves >= 3 hops per stage
+            lane_dense_ = sizeof(REAL) == 4 && !deterministic_ && env_u("BDDB200_NO_DENSE", 0) == 0 && n_lane_ >= (size_t)n_sms_ * 48
+                          && ((size_t)(75 * 1024) - INV_TAB * sizeof(REAL) - 1024) / 8 / (lane_stages_ * per_hop) >= 3;
+            if(lane_dense_) { ctas_per_sm = 3; lane_wpc_ = 8; }
+            else if(best_w >= 12 && best_w % 2 == 0) { ctas_per_sm = 2; lane_wpc_ = (unsigned)(best_w / 2); } else lane_wpc_ = (unsigned)best_w;
             lane_grid_ = blocks_for(n_lane_, lane_wpc_);
         }
         const size_t sm_total = 228 * 1024;                             // per SM; every resident CTA reserves 1 KiB
@@ -447,6 +452,8 @@ public:
             CUDA_CHECK(cudaFuncSetAttribute(sweep_lane_kernel<REAL, MODE_PLAIN, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need_lane));
             CUDA_CHECK(cudaFuncSetAttribute(sweep_lane_kernel<REAL, MODE_PLAIN, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need_lane));
             CUDA_CHECK(cudaFuncSetAttribute(sweep_lane_kernel<REAL, MODE_MM, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need_lane));
+            CUDA_CHECK(cudaFuncSetAttribute(sweep_lane_kernel_dense<REAL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, need_lane));
+            CUDA_CHECK(cudaFuncSetAttribute(sweep_lane_kernel_dense<REAL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need_lane));
         }
         const int need = (int)(INV_TAB_BYTES + std::max<size_t>((size_t)warps_per_cta_ * warp_smem_small_, warp_smem_large_));
         if(need > 48 * 1024)
@@ -928,6 +935,7 @@ private:
     size_t n_lane_ = 0;
     uint32_t lane_max_J_ = 0, lane_max_hops_ = 0, lane_chunk_hops_ = 1, lane_stages_ = 2, lane_stage_bytes_ = 0, lane_warp_smem_ = 0;
     unsigned lane_wpc_ = 1, lane_grid_ = 1;
+    bool lane_dense_ = false;          // MMA passes use the register-capped kernel (24 warps per SM)
     std::vector<LaneDesc> lane_cls_first_;
     std::vector<uint32_t> lane_cls_begin_;
     unsigned warps_per_cta_ = 4, grid_small_ = 1, forced_wpc_ = 0, n_stages_ = 3, n_stages_large_ = 2;

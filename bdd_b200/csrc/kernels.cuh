@@ -1151,10 +1151,7 @@ __device__ __forceinline__ void sweep_lane_bundle(const SweepArgs<REAL>& a, cons
 }
 
 template<typename REAL, int MODE, bool FORWARD, bool DET>
-#ifndef BDDB200_LANE_MAX_THREADS
-#define BDDB200_LANE_MAX_THREADS 512
-#endif
-__global__ void __launch_bounds__(BDDB200_LANE_MAX_THREADS, 1) sweep_lane_kernel(const SweepArgs<REAL> a)
+__device__ __forceinline__ void sweep_lane_cta(const SweepArgs<REAL>& a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ REAL inv_tab[INV_TAB];                        // 1 / n for n < INV_TAB (ones when delta_in is already normalised)
@@ -1207,6 +1204,17 @@ __global__ void __launch_bounds__(BDDB200_LANE_MAX_THREADS, 1) sweep_lane_kernel
         default: break;
     }
 }
+
+#ifndef BDDB200_LANE_MAX_THREADS
+#define BDDB200_LANE_MAX_THREADS 512
+#endif
+// up to 16 warps per SM at up to 128 registers per thread
+template<typename REAL, int MODE, bool FORWARD, bool DET>
+__global__ void __launch_bounds__(BDDB200_LANE_MAX_THREADS, 1) sweep_lane_kernel(const SweepArgs<REAL> a) { sweep_lane_cta<REAL, MODE, FORWARD, DET>(a); }
+// the same pass compiled for 24 resident warps per SM (<= 80 registers per thread): HBM-bound instances of many waves gain ~6 % from
+// the extra warps (profiles/r01_v4_ncu_sweep_summary.md); float only -- the double kernels would spill
+template<typename REAL, bool FORWARD>
+__global__ void __launch_bounds__(768, 1) sweep_lane_kernel_dense(const SweepArgs<REAL> a) { sweep_lane_cta<REAL, MODE_MMA, FORWARD, false>(a); }
 
 // ------------------------------------------------------------------ small kernels ------
 

@@ -428,3 +428,26 @@ def test_variable_shared_by_more_bdds_than_the_reciprocal_table():
             s.iteration(); o.iteration()
             assert abs(s.lower_bound() - o.lower_bound()) <= tol(precision, o.lower_bound())
         assert np.allclose(s.get_delta().cpu().numpy(), o.get_delta(), rtol=0, atol=tol(precision, 100))
+
+
+def test_many_waves_float_uses_the_register_capped_kernel():
+    """More than 48 bundles per SM in float: the MMA passes run the 24-warps-per-SM build of the lane kernel (sweep_lane_kernel_dense).
+    Same results as the oracle, and as the regular build (BDDB200_NO_DENSE=1) up to the order of the atomic sums."""
+    from bdd_b200 import instances
+    col, costs = instances.set_cover(m=240000, n=300000, k=4, seed=12)
+    assert col.nr_bdds // 32 >= 148 * 48
+    B.oracle_set_num_threads(8)
+    o = B.Oracle(col.instrs, col.delims, costs, "float")
+    s = solver(col, costs, "float")
+    os.environ["BDDB200_NO_DENSE"] = "1"
+    try:
+        r = solver(col, costs, "float")
+    finally:
+        del os.environ["BDDB200_NO_DENSE"]
+    for _ in range(4):
+        s.iteration(); r.iteration(); o.iteration()
+        assert abs(s.lower_bound() - o.lower_bound()) <= tol("float", o.lower_bound())
+        assert abs(s.lower_bound() - r.lower_bound()) <= tol("float", o.lower_bound())
+    d = s.get_delta().cpu().numpy()
+    assert np.allclose(d, o.get_delta(), rtol=0, atol=tol("float", 100))
+    B.oracle_set_num_threads(1)
