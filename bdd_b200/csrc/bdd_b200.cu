@@ -212,12 +212,6 @@ public:
         d_lay_vn_.upload(lay_vn, stream_);
         d_bundle_bdd_.upload(L.bundle_bdd, stream_);
         d_bdd_bundle_.upload(bdd_bundle, stream_);
-        {   // where each BDD's root value sits in the bundle-ordered bdd_lb array
-            std::vector<uint32_t> bdd_pos(n_bdds);
-            for(size_t b = 0; b < n_bdds; ++b) bdd_pos[b] = L.bundles[bdd_bundle[2 * b]].bdd_base + bdd_bundle[2 * b + 1];
-            d_bdd_pos_.upload(bdd_pos, stream_);
-            n_bdd_slots_ = L.bundle_bdd.size();
-        }
         d_ext2lay_.upload(L.ext2lay, stream_);
         d_ext_var_.upload(L.ext_var, stream_);
         d_ext_bdd_.upload(L.ext_bdd, stream_);
@@ -241,7 +235,7 @@ public:
         d_mm_lo_.alloc(n_lay_); d_mm_hi_.alloc(n_lay_);
         for(int i = 0; i < 3; ++i) { d_delta_[i].alloc(2 * n_vars_); d_delta_[i].zero(stream_); }
         d_delta_tmp_.alloc(2 * n_vars_);
-        d_bdd_lb_.alloc(n_bdd_slots_); d_bdd_lb_.zero(stream_);
+        d_bdd_lb_.alloc(n_bdds_);
         d_lb_partial_.alloc(LB_BLOCKS + 1 + LB_SLOTS); d_lb_partial_.zero(stream_);
         CUDA_CHECK(cudaMallocHost(&h_lb_, LB_SLOTS * sizeof(double)));
 
@@ -271,7 +265,7 @@ public:
         h_nr_bdds_per_var_ = o.h_nr_bdds_per_var_; h_ext_var_ = o.h_ext_var_; h_ext_bdd_ = o.h_ext_bdd_;
         d_bundles_.clone_from(o.d_bundles_, stream_); d_chunks_.clone_from(o.d_chunks_, stream_);
         d_desc_fwd_.clone_from(o.d_desc_fwd_, stream_); d_desc_bwd_.clone_from(o.d_desc_bwd_, stream_); d_desc_lane_.clone_from(o.d_desc_lane_, stream_);
-        d_hops_.clone_from(o.d_hops_, stream_); d_topo_.clone_from(o.d_topo_, stream_); d_bdd_bundle_.clone_from(o.d_bdd_bundle_, stream_); d_bdd_pos_.clone_from(o.d_bdd_pos_, stream_); n_bdd_slots_ = o.n_bdd_slots_;
+        d_hops_.clone_from(o.d_hops_, stream_); d_topo_.clone_from(o.d_topo_, stream_); d_bdd_bundle_.clone_from(o.d_bdd_bundle_, stream_);
         d_ext2lay_.clone_from(o.d_ext2lay_, stream_); d_bdd_ext_begin_.clone_from(o.d_bdd_ext_begin_, stream_);
         d_var_lay_begin_.clone_from(o.d_var_lay_begin_, stream_); d_var_lay_.clone_from(o.d_var_lay_, stream_); d_sorted_ext_.clone_from(o.d_sorted_ext_, stream_);
         d_lay_vn_.clone_from(o.d_lay_vn_, stream_); d_bundle_bdd_.clone_from(o.d_bundle_bdd_, stream_);
@@ -332,7 +326,7 @@ public:
             attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             attr[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr; cfg.numAttrs = pdl_ ? 1 : 0;
-            if(MODE == MODE_MMA && !deterministic_ && lane_dense_) CUDA_CHECK(cudaLaunchKernelEx(&cfg, sweep_lane_kernel_dense<REAL, FORWARD>, a));
+            if(MODE == MODE_MMA && !deterministic_ && lane_dense_) CUDA_CHECK(cudaLaunchKernelEx(&cfg, sweep_lane_kernel<REAL, MODE_MMA, FORWARD, false, 768>, a));
             else if(MODE == MODE_MMA && deterministic_) CUDA_CHECK(cudaLaunchKernelEx(&cfg, sweep_lane_kernel<REAL, MODE, FORWARD, MODE == MODE_MMA>, a));
             else CUDA_CHECK(cudaLaunchKernelEx(&cfg, sweep_lane_kernel<REAL, MODE, FORWARD, false>, a));
             ++launches_;
@@ -452,8 +446,8 @@ public:
             CUDA_CHECK(cudaFuncSetAttribute(sweep_lane_kernel<REAL, MODE_PLAIN, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need_lane));
             CUDA_CHECK(cudaFuncSetAttribute(sweep_lane_kernel<REAL, MODE_PLAIN, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need_lane));
             CUDA_CHECK(cudaFuncSetAttribute(sweep_lane_kernel<REAL, MODE_MM, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need_lane));
-            CUDA_CHECK(cudaFuncSetAttribute(sweep_lane_kernel_dense<REAL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, need_lane));
-            CUDA_CHECK(cudaFuncSetAttribute(sweep_lane_kernel_dense<REAL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need_lane));
+            CUDA_CHECK(cudaFuncSetAttribute(sweep_lane_kernel<REAL, MODE_MMA, true, false, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, need_lane));
+            CUDA_CHECK(cudaFuncSetAttribute(sweep_lane_kernel<REAL, MODE_MMA, false, false, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, need_lane));
         }
         const int need = (int)(INV_TAB_BYTES + std::max<size_t>((size_t)warps_per_cta_ * warp_smem_small_, warp_smem_large_));
         if(need > 48 * 1024)
@@ -694,7 +688,7 @@ public:
             const double* src = d_lb_partial_.p + LB_BLOCKS + 1;      // accumulated by the backward sweep itself
             if(deterministic_)
             {   // fixed-shape two-stage tree over the per-BDD values (bit-reproducible)
-                lb_partial_kernel<REAL><<<LB_BLOCKS, 256, 0, stream_>>>(d_bdd_lb_.p, d_lb_partial_.p, (uint32_t)n_bdd_slots_);
+                lb_partial_kernel<REAL><<<LB_BLOCKS, 256, 0, stream_>>>(d_bdd_lb_.p, d_lb_partial_.p, (uint32_t)n_bdds_);
                 lb_final_kernel<<<1, 256, 0, stream_>>>(d_lb_partial_.p, d_lb_partial_.p + LB_BLOCKS, LB_BLOCKS);
                 launches_ += 2;
                 src = d_lb_partial_.p + LB_BLOCKS;
@@ -713,9 +707,7 @@ public:
     {
         set_device();
         backward_run();
-        permute_kernel<REAL><<<blocks_for(n_bdds_), 256, 0, stream_>>>(d_bdd_pos_.p, d_bdd_lb_.p, static_cast<REAL*>(out_dev), (uint32_t)n_bdds_);
-        ++launches_;
-        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaMemcpyAsync(out_dev, d_bdd_lb_.p, sizeof(REAL) * n_bdds_, cudaMemcpyDeviceToDevice, stream_));
     }
 
     // ---------------------------------------------------------------- costs -------------
@@ -952,8 +944,6 @@ private:
     uint32_t inv_count_ = 1;
     bool pdl_ = true;
     DevBuf<HopRec> d_hops_;
-    DevBuf<uint32_t> d_bdd_pos_;
-    size_t n_bdd_slots_ = 0;
     DevBuf<uint32_t> d_topo_, d_bdd_bundle_, d_ext2lay_, d_bdd_ext_begin_, d_var_lay_begin_, d_var_lay_, d_sorted_ext_;
     DevBuf<int2> d_lay_vn_;
     DevBuf<int32_t> d_bundle_bdd_, d_ext_var_, d_ext_bdd_, d_nr_bdds_;

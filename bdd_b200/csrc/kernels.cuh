@@ -142,8 +142,7 @@ struct SweepArgs {
     REAL* zero_buf;            // 2V buffer to clear for the pass after next (may be null)
     REAL* mm_lo_out;           // MODE_MM
     REAL* mm_hi_out;
-    REAL* bdd_lb;              // backward: cost_from_terminal of every BDD's root, in bundle order (entry bdd_base + lane group, like
-                               // bundle_bdd; 0 where a lane group holds no BDD): coalesced stores instead of one scattered store per BDD
+    REAL* bdd_lb;              // backward: cost_from_terminal of every BDD's root
     double* lb_sum;            // backward: LB_SLOTS partial sums of the roots' cost_from_terminal, slot = CTA index mod LB_SLOTS (one address
                                // would serialise tens of thousands of atomics in L2); null = off; forward kernels zero them
     REAL omega;
@@ -683,7 +682,7 @@ __device__ __forceinline__ void sweep_bundle(const SweepArgs<REAL>& a, const uin
     {
         const REAL root = SMEM_FRONTIER ? nxt[lane] : fr[0];       // root = node 0 of hop 0
         const bool mine_valid = p == 0 && bdd_index >= 0;
-        if(p == 0) a.bdd_lb[bdd_base + bl] = mine_valid ? root : (REAL)0;
+        if(mine_valid) a.bdd_lb[bdd_index] = root;
         if(a.lb_sum != nullptr)
         {   // lower_bound, bdd_cuda_base.cu:1243-1251: sum over BDDs in double
             double v = mine_valid ? (double)root : 0.0;
@@ -1139,7 +1138,7 @@ __device__ __forceinline__ void sweep_lane_bundle(const SweepArgs<REAL>& a, cons
     {
         const REAL root = fr[0];                                    // root = row 0 of hop 0
         const bool mine_valid = bdd_index >= 0;
-        a.bdd_lb[d.bdd_base + lane] = mine_valid ? root : (REAL)0;
+        if(mine_valid) a.bdd_lb[bdd_index] = root;
         if(a.lb_sum != nullptr)
         {   // lower_bound, bdd_cuda_base.cu:1243-1251: sum over BDDs in double
             double v = mine_valid ? (double)root : 0.0;
@@ -1150,8 +1149,14 @@ __device__ __forceinline__ void sweep_lane_bundle(const SweepArgs<REAL>& a, cons
     }
 }
 
-template<typename REAL, int MODE, bool FORWARD, bool DET>
-__device__ __forceinline__ void sweep_lane_cta(const SweepArgs<REAL>& a)
+#ifndef BDDB200_LANE_MAX_THREADS
+#define BDDB200_LANE_MAX_THREADS 512
+#endif
+// MAXT = BDDB200_LANE_MAX_THREADS: up to 16 warps per SM at up to 128 registers per thread.
+// MAXT = 768 ("dense", MMA passes in float only -- the double kernels would spill): the same pass compiled for 24 resident warps per SM
+// (<= 80 registers per thread); HBM-bound instances of many waves gain ~6 % from the extra warps (profiles/r01_v4_ncu_sweep_summary.md).
+template<typename REAL, int MODE, bool FORWARD, bool DET, int MAXT = BDDB200_LANE_MAX_THREADS>
+__global__ void __launch_bounds__(MAXT, 1) sweep_lane_kernel(const SweepArgs<REAL> a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ REAL inv_tab[INV_TAB];                        // 1 / n for n < INV_TAB (ones when delta_in is already normalised)
@@ -1205,16 +1210,6 @@ __device__ __forceinline__ void sweep_lane_cta(const SweepArgs<REAL>& a)
     }
 }
 
-#ifndef BDDB200_LANE_MAX_THREADS
-#define BDDB200_LANE_MAX_THREADS 512
-#endif
-// up to 16 warps per SM at up to 128 registers per thread
-template<typename REAL, int MODE, bool FORWARD, bool DET>
-__global__ void __launch_bounds__(BDDB200_LANE_MAX_THREADS, 1) sweep_lane_kernel(const SweepArgs<REAL> a) { sweep_lane_cta<REAL, MODE, FORWARD, DET>(a); }
-// the same pass compiled for 24 resident warps per SM (<= 80 registers per thread): HBM-bound instances of many waves gain ~6 % from
-// the extra warps (profiles/r01_v4_ncu_sweep_summary.md); float only -- the double kernels would spill
-template<typename REAL, bool FORWARD>
-__global__ void __launch_bounds__(768, 1) sweep_lane_kernel_dense(const SweepArgs<REAL> a) { sweep_lane_cta<REAL, MODE_MMA, FORWARD, false>(a); }
 
 // ------------------------------------------------------------------ small kernels ------
 
