@@ -427,7 +427,14 @@ public:
         if(hops < 1) throw api_error(BDDB200_ERR_TOO_WIDE, "lane-class stage does not fit the shared memory of one SM");
         hops = std::min<size_t>(hops, lane_max_hops_);
         if(const unsigned f = env_u("BDDB200_LANE_CHUNK_HOPS", 0)) hops = std::min<size_t>(hops, f);
-        const size_t nc = (lane_max_hops_ + hops - 1) / hops;
+        size_t nc = (lane_max_hops_ + hops - 1) / hops;
+        if(lane_stages_ == 1 && nc > 1)
+        {   // a single stage only works when a whole bundle fits into it
+            lane_stages_ = 2;
+            hops = std::max<size_t>(1, (warp_budget - 128) / (lane_stages_ * per_hop));
+            hops = std::min<size_t>(hops, lane_max_hops_);
+            nc = (lane_max_hops_ + hops - 1) / hops;
+        }
         hops = (lane_max_hops_ + nc - 1) / nc;                         // chunks of equal length
         lane_chunk_hops_ = (uint32_t)hops;
         lane_stage_bytes_ = (uint32_t)(hops * per_hop);
