@@ -81,12 +81,12 @@ class bdd_solver:
             sb = config["split bdds"] or {}
             if sb.get("implication bdd", False):
                 raise RuntimeError("the implication BDD of split_qbdd is not implemented")
-            if "split length" not in sb:
-                raise RuntimeError("'split bdds' needs a 'split length' (the reference's occupancy heuristic compute_split_length is GPU-model specific)")
-            from .split import split_long_bdds
+            from .split import compute_split_length, split_long_bdds
+            # no length given: a value that fills the GPU (the reference's rule, bdd_preprocessor.cpp:32-121, targets its hop-synchronous kernels)
+            length = int(sb["split length"]) if "split length" in sb else compute_split_length(col)
             n_before = col.nr_bdds
-            col, _ = split_long_bdds(col, int(sb["split length"]), nr_variables=len(costs))      # auxiliary variables carry no cost
-            self.log(f"[bdd preprocessor] force split BDDs longer than {sb['split length']}: {n_before} -> {col.nr_bdds} BDDs")
+            col, _ = split_long_bdds(col, length, nr_variables=len(costs))      # auxiliary variables carry no cost
+            self.log(f"[bdd preprocessor] split BDDs longer than {length}: {n_before} -> {col.nr_bdds} BDDs")
         return col, costs
 
     # ---- construct_solver, :130-267 --------------------------------------------------------------------------------------------

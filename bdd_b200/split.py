@@ -159,3 +159,36 @@ def split_long_bdds(col: BddCollection, split_length: int, nr_variables: int = 0
     whole = BddCollection(all_instrs, all_delims)
     keep = np.concatenate([np.nonzero(~removed)[0], np.arange(col.nr_bdds, whole.nr_bdds)])
     return whole.select(keep), aux
+
+
+def compute_split_length(col: BddCollection, n_sms: int = 148, warps_per_sm: int = 16, min_length: int = 16) -> int:
+    """Split length when the configuration gives none.  The reference's rule (compute_split_length, bdd_preprocessor.cpp:32-121) targets
+    >= 50 % occupancy of its hop-synchronous kernels (nodes per hop against SMs x threads); the sweep here gives every warp a bundle of 32
+    BDDs and walks it alone, so what long BDDs cost is (a) too few bundles to put ``warps_per_sm`` warps on every SM and (b) a pass that is
+    a chain of H dependent hops.  Rule: the largest length that yields at least ``n_sms * warps_per_sm`` bundles, never below ``min_length``
+    (every cut adds a head and a tail gadget and width-many auxiliary variables); collections that already fill the GPU are not split.
+    Returns sys.maxsize when nothing should be split."""
+    import sys
+    sizes = np.diff(col.delims.astype(np.int64)) - 2
+    idx = col.instrs[:, 2]
+    inner = idx < BOTSINK
+    bdd_of = np.repeat(np.arange(col.nr_bdds), np.diff(col.delims.astype(np.int64)))[inner]
+    var = idx[inner]
+    head = np.ones(var.shape[0], dtype=bool)
+    head[1:] = (var[1:] != var[:-1]) | (bdd_of[1:] != bdd_of[:-1])
+    layers = np.bincount(bdd_of[head], minlength=col.nr_bdds)          # layers (variables) per BDD
+    target_bdds = 32 * n_sms * warps_per_sm
+    if col.nr_bdds >= target_bdds or layers.max() <= min_length:
+        return sys.maxsize
+    # number of chunk BDDs for length L: sum over BDDs of ceil(layers / L); find the largest L reaching the target
+    lo, hi = min_length, int(layers.max())
+    if int(np.ceil(layers / lo).sum()) < target_bdds:
+        return lo
+    while lo < hi:
+        mid = (lo + hi + 1) // 2
+        if int(np.ceil(layers / mid).sum()) >= target_bdds:
+            lo = mid
+        else:
+            hi = mid - 1
+    del sizes
+    return lo

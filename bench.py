@@ -61,6 +61,11 @@ def make_instance(n_shards: int, workload: str):
     if workload == "assignment_5m":
         col, costs = instances.assignment(1118, seed=3)
         return col, costs, "float"
+    if workload == "assignment_5m_split_auto":   # split length chosen by bdd_b200.split.compute_split_length (fills 16 warps per SM)
+        from bdd_b200.split import compute_split_length, split_long_bdds
+        col, costs = instances.assignment(1118, seed=3)
+        col, n_all = split_long_bdds(col, compute_split_length(col))
+        return col, np.concatenate([costs, np.zeros(n_all - len(costs))]), "float"
     if workload == "assignment_5m_split64":      # the same instance after split_qbdd with chunk length 64 (the reference's answer to long BDDs)
         from bdd_b200.split import split_long_bdds
         col, costs = instances.assignment(1118, seed=3)

@@ -90,6 +90,20 @@ def test_split_long_bdds_keeps_short_ones():
     assert out.nr_bdds == 2 * col.nr_bdds and n_all == col.nr_variables() + 2 * col.nr_bdds
 
 
+def test_compute_split_length_fills_the_gpu():
+    import sys
+    from bdd_b200.split import compute_split_length
+    col, _ = instances.assignment(300, seed=3)                     # 600 BDDs of 300 variables
+    length = compute_split_length(col)
+    assert 16 <= length < 300
+    out, _ = split_long_bdds(col, length)
+    assert out.nr_bdds >= 32 * 148 * 16 or length == 16            # enough bundles for 16 warps on every SM (or the floor)
+    if length > 16:
+        assert split_long_bdds(col, length + 1)[0].nr_bdds < 32 * 148 * 16     # and it is the largest such length
+    small, _ = instances.set_cover(m=30, n=50, k=5, seed=1)
+    assert compute_split_length(small) == sys.maxsize             # short BDDs are left alone
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("precision", ["double", "float"])
 def test_split_collection_solves_like_the_oracle_on_gpu(precision):
