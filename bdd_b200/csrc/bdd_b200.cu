@@ -182,8 +182,12 @@ public:
 
         // the lane-class kernels normalise through a reciprocal table; a variable shared by more BDDs than it holds
         // switches the solver to exact division + fixed-order sums (the deterministic kernels)
-        if(n_lane_ > 0 && !h_nr_bdds_per_var_.empty() && *std::max_element(h_nr_bdds_per_var_.begin(), h_nr_bdds_per_var_.end()) >= INV_TAB)
+        if(n_lane_ > 0 && !deterministic_ && !h_nr_bdds_per_var_.empty() && *std::max_element(h_nr_bdds_per_var_.begin(), h_nr_bdds_per_var_.end()) >= INV_TAB)
+        {
             deterministic_ = true;
+            if(std::getenv("BDDB200_QUIET") == nullptr)
+                std::fprintf(stderr, "[bdd_b200] a variable occurs in >= %d BDDs: using the deterministic kernels (exact division, fixed-order sums)\n", INV_TAB);
+        }
         CUDA_CHECK(cudaDeviceGetAttribute(&max_optin_, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
         CUDA_CHECK(cudaDeviceGetAttribute(&n_sms_, cudaDevAttrMultiProcessorCount, device));
         plan_launch();
@@ -307,6 +311,11 @@ public:
     void launch_sweep(SweepArgs<REAL> a)
     {
         auto kern = sweep_kernel<REAL, MODE, FORWARD>;
+        // every backward sweep ADDS the roots' values to lb_sum; every forward sweep clears it (block 0).  A backward sweep that
+        // does not directly follow a forward sweep (forward_mm, lower_bound(), backward_mm: the bound in between runs a plain
+        // backward sweep) must clear it first.
+        if(!FORWARD && !deterministic_ && !lb_sum_clean_) zero_lb_sum();
+        lb_sum_clean_ = FORWARD;
         if(n_lane_ > 0)
         {   // lane-local class: bundles [0, n_lane)
             a.desc = reinterpret_cast<const uint32_t*>(d_desc_lane_.p);
@@ -679,7 +688,6 @@ public:
         set_device();
         if(backward_valid_) return;
         SweepArgs<REAL> a = base_args();
-        zero_lb_sum();
         launch_sweep<MODE_PLAIN, false>(a);
         backward_valid_ = true; lb_valid_ = false;
     }
@@ -838,7 +846,6 @@ public:
     {
         forward_run();
         SweepArgs<REAL> a = base_args();
-        zero_lb_sum();
         launch_sweep<MODE_MM, false>(a);
         backward_valid_ = true; lb_valid_ = false;
     }
@@ -970,6 +977,7 @@ private:
     int dcur_ = 0;               // which delta buffer holds the current (pending) sums
     bool delta_needs_norm_ = false;
     bool forward_valid_ = false, backward_valid_ = false, lb_valid_ = false;
+    bool lb_sum_clean_ = false;  // lb_sum holds zeros (the last sweep was a forward one, or it was just cleared)
     double lb_ = 0.0;
     mutable size_t launches_ = 0;
 

@@ -355,6 +355,7 @@ namespace LPMP {
             {
                 assert(g.size() == this->nr_layers());
                 bddb200_detail::check(bddb200_gradient_step(this->h_, thrust::raw_pointer_cast(g.data()), step_size));
+                this->sync();      // `g` is caller-owned: the reference call is synchronous, the caller may overwrite it on return
             }
     };
 

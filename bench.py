@@ -150,12 +150,17 @@ def cpu_solver(col, costs, precision):
     """(solver with .iteration()/.lower_bound(), kind, threads).  The ONLY place bench.py touches oracle/."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import bindings as B
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: count the cores this process may run on instead
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
     if B.ref_available():
-        n = B.ref_max_threads()
+        n = max(B.ref_max_threads(), avail)
         B.ref_set_num_threads(n)
         rc = B.RefCollection.from_arrays(col.instrs, col.delims)
         return B.RefSolver(rc, costs, precision), "reference", n
-    n = B.oracle_max_threads()
+    n = max(B.oracle_max_threads(), avail)
     B.oracle_set_num_threads(n)
     return B.Oracle(col.instrs, col.delims, costs, precision), "port", n
 

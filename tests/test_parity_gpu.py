@@ -104,6 +104,30 @@ def test_pass_protocol(name, precision, deterministic, lanes):
             assert abs(s.lower_bound() - g["lbs_pass"][it]) <= 1e-9
 
 
+@pytest.mark.parametrize("precision", ["double", "float"])
+@pytest.mark.parametrize("name", ["matching_3x3", "long_mrf_chain", "mrf_grid_graph_3x3"])
+def test_queries_between_forward_and_backward_mm(name, precision):
+    """lower_bound(), min_marginals and lower_bound_per_bdd between forward_mm and backward_mm run their own backward
+    sweeps (the reference recomputes backward_run when the state is invalid, bdd_cuda_base.cu:1243-1251); the bound
+    reported after the following backward_mm must not contain their contribution."""
+    g = load(name)
+    s = solver(_col(g["instrs"], g["delims"]), g["costs"], precision)
+    o = B.Oracle(g["instrs"], g["delims"], g["costs"], precision)
+    delta = torch.zeros(2 * s.nr_variables(), dtype=s.value_type, device="cuda")
+    odelta = np.zeros(2 * o.n_vars, dtype=o.dtype)
+    for it in range(4):
+        s.forward_mm(0.5, delta)
+        o.forward_mm(0.5, odelta)
+        mid = s.lower_bound()                       # plain backward sweep on the half-updated costs
+        if it % 2 == 1:
+            s.min_marginals_cuda(False)
+            s.lower_bound_per_bdd()
+        assert np.isfinite(mid)
+        s.backward_mm(0.5, delta)
+        o.backward_mm(0.5, odelta)
+        assert abs(s.lower_bound() - o.lower_bound()) <= tol(precision, o.lower_bound()), f"iteration {it}"
+
+
 @pytest.mark.parametrize("deterministic", [False, True])
 @pytest.mark.parametrize("name", golden_names())
 def test_iteration_trajectory_vs_reference(name, deterministic):
