@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "resident.cuh"
 
 using namespace bddb200;
 
@@ -191,6 +192,7 @@ public:
         CUDA_CHECK(cudaDeviceGetAttribute(&max_optin_, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
         CUDA_CHECK(cudaDeviceGetAttribute(&n_sms_, cudaDevAttrMultiProcessorCount, device));
         plan_launch();
+        plan_resident();
 
         std::vector<int2> lay_vn(L.n_lay);
         for(size_t i = 0; i < L.n_lay; ++i)
@@ -237,10 +239,11 @@ public:
         for(int i = 0; i < 2; ++i) { d_lohi_[i].alloc(2 * n_lay_); d_lohi_[i].zero(stream_); }
         d_mmd_.alloc(n_lay_); d_mmd_.zero(stream_);
         d_mm_lo_.alloc(n_lay_); d_mm_hi_.alloc(n_lay_);
-        for(int i = 0; i < 3; ++i) { d_delta_[i].alloc(2 * n_vars_); d_delta_[i].zero(stream_); }
+        for(int i = 0; i < 3; ++i) { d_delta_[i].alloc(2 * n_vars_ + RES_SCRATCH); d_delta_[i].zero(stream_); }     // + scratch pairs of the on-chip kernel
         d_delta_tmp_.alloc(2 * n_vars_);
         d_bdd_lb_.alloc(n_bdds_);
         d_lb_partial_.alloc(LB_BLOCKS + 1 + LB_SLOTS); d_lb_partial_.zero(stream_);
+        d_barrier_.alloc(32); d_barrier_.zero(stream_);
         CUDA_CHECK(cudaMallocHost(&h_lb_, LB_SLOTS * sizeof(double)));
 
         configure_kernels();
@@ -281,6 +284,8 @@ public:
         d_inv_tab_.clone_from(o.d_inv_tab_, stream_); inv_count_ = o.inv_count_; pdl_ = o.pdl_;
         d_delta_tmp_.clone_from(o.d_delta_tmp_, stream_); d_bdd_lb_.clone_from(o.d_bdd_lb_, stream_); d_lb_partial_.clone_from(o.d_lb_partial_, stream_);
         CUDA_CHECK(cudaMallocHost(&h_lb_, LB_SLOTS * sizeof(double)));
+        d_barrier_.alloc(32); d_barrier_.zero(stream_);
+        res_ok_ = o.res_ok_; res_grid_ = o.res_grid_; res_wpc_ = o.res_wpc_; res_warp_smem_ = o.res_warp_smem_;
         cc_ = o.cc_; dcur_ = o.dcur_; delta_needs_norm_ = o.delta_needs_norm_;
         forward_valid_ = o.forward_valid_; backward_valid_ = o.backward_valid_; lb_valid_ = o.lb_valid_; lb_ = o.lb_;
         configure_kernels();
@@ -450,8 +455,57 @@ public:
         lane_warp_smem_ = (uint32_t)((((size_t)lane_stages_ * lane_stage_bytes_) + 127) & ~(size_t)127);
     }
 
+    // On-chip form (resident.cuh): every bundle is lane class, the collection is at most one wave of 16 warps per SM and the
+    // state of the bundles of one CTA fits the shared memory of an SM.
+    void plan_resident()
+    {
+        res_ok_ = false;
+        if(std::getenv("BDDB200_NO_RESIDENT") != nullptr && std::atoi(std::getenv("BDDB200_NO_RESIDENT")) != 0) return;
+        if(deterministic_ || n_lane_ == 0 || n_lane_ != n_bundles_ || n_lane_ > (size_t)n_sms_ * 16 || n_vars_ >= ((size_t)1 << 26)) return;
+        res_grid_ = (unsigned)std::min<size_t>(n_lane_, (size_t)n_sms_);
+        res_wpc_ = (unsigned)((n_lane_ + res_grid_ - 1) / res_grid_);
+        res_warp_smem_ = (uint32_t)((resident_bundle_bytes(lane_max_hops_, lane_max_J_, sizeof(REAL)) + 127) & ~(size_t)127);
+        const size_t static_smem = INV_TAB * sizeof(REAL) + 16 * 8 + 256;
+        if((size_t)res_wpc_ * res_warp_smem_ + static_smem > (size_t)max_optin_) return;
+        res_ok_ = true;
+    }
+    bool use_resident() const { return res_ok_ && delta_in_override_ == nullptr && ext_delta_[0] == nullptr; }
+
+    // n iterations in ONE cooperative launch; cost_from_terminal is recomputed on chip first when it is stale
+    void launch_resident(double omega, size_t n, unsigned long long* trace = nullptr)
+    {
+        using R2 = typename real2<REAL>::type;
+        while(n > 0)
+        {
+            const size_t k = std::min<size_t>(n, 1u << 16);
+            ResidentArgs<REAL> a{};
+            a.desc = d_desc_lane_.p; a.topo = d_topo_.p; a.lay_vn = d_lay_vn_.p; a.bundle_bdd = d_bundle_bdd_.p;
+            a.cfr = d_cfr_.p; a.cft = d_cft_.p; a.lohi = reinterpret_cast<R2*>(d_lohi_[cc_].p); a.mmd = d_mmd_.p;
+            for(int i = 0; i < 3; ++i) a.delta[i] = dbuf(i);
+            a.cur = (uint32_t)dcur_; a.n_delta = (uint32_t)(2 * n_vars_);
+            a.bdd_lb = d_bdd_lb_.p; a.lb_sum = d_lb_partial_.p + LB_BLOCKS + 1;
+            a.omega = (REAL)omega; a.n_iterations = (uint32_t)k; a.init_backward = backward_valid_ ? 0u : 1u;
+            a.n_bundles = (uint32_t)n_lane_; a.bundles_per_cta = (uint32_t)(n_lane_ / res_grid_); a.bundles_rem = (uint32_t)(n_lane_ % res_grid_);
+            a.zero_pairs_per_bundle = (uint32_t)((n_vars_ + n_lane_ - 1) / n_lane_);
+            a.warp_smem_bytes = res_warp_smem_; a.inv_count = inv_count_; a.barrier = d_barrier_.p;
+            a.n_classes = (uint32_t)lane_cls_begin_.size();
+            for(size_t c = 0; c < lane_cls_begin_.size(); ++c) { a.cls_first[c] = lane_cls_first_[c]; a.cls_begin[c] = lane_cls_begin_[c]; }
+            a.trace = trace;
+            if(const char* e = std::getenv("BDDB200_RES_DEBUG")) a.debug = (uint32_t)std::atoi(e);
+            void* params[] = { &a };
+            CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)resident_kernel<REAL>, dim3(res_grid_), dim3(res_wpc_ * 32), params,
+                                                   (size_t)res_wpc_ * res_warp_smem_, stream_));
+            ++launches_;
+            dcur_ = (int)((dcur_ + 2 * k) % 3); delta_needs_norm_ = true;
+            forward_valid_ = false; backward_valid_ = true; lb_valid_ = false; lb_sum_clean_ = false;
+            n -= k;
+        }
+    }
+
     void configure_kernels()
     {
+        if(res_ok_)
+            CUDA_CHECK(cudaFuncSetAttribute(resident_kernel<REAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)res_wpc_ * res_warp_smem_)));
         const int need_lane = (int)((size_t)lane_wpc_ * lane_warp_smem_);
         if(n_lane_ > 0 && need_lane > 40 * 1024)
         {
@@ -541,6 +595,7 @@ public:
 
     void iteration(double omega) override
     {
+        if(use_resident()) { set_device(); launch_resident(omega, 1); return; }
         forward_pass(omega);
         backward_pass(omega);
     }
@@ -549,6 +604,7 @@ public:
     {
         set_device();
         if(n == 0) return;
+        if(use_resident()) { launch_resident(omega, n); return; }
         if(!backward_valid_) backward_run();
         // The delta buffers rotate with period 3 passes and an iteration is 2 passes: a graph of
         // 3 iterations (6 sweep launches) returns to the same buffer assignment.
@@ -666,6 +722,14 @@ public:
         set_device();
         const size_t n = std::min(max_bundles, n_lane_ > 0 ? n_lane_ : n_small_);      // bundles of the first launch
         DevBuf<unsigned long long> tr; tr.alloc((n_bundles_ + 64) * TRACE_EVENTS); tr.zero(stream_);
+        if(forward == 2)
+        {   // one iteration of the on-chip kernel
+            if(!use_resident()) throw api_error(BDDB200_ERR_STATE, "trace_pass(2): the on-chip kernel is not in use for this solver");
+            launch_resident(omega, 1, tr.p);
+            CUDA_CHECK(cudaMemcpyAsync(out_host, tr.p, n * TRACE_EVENTS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream_));
+            CUDA_CHECK(cudaStreamSynchronize(stream_));
+            return n;
+        }
         trace_ = tr.p;
         if(forward) forward_pass(omega); else backward_pass(omega);
         trace_ = nullptr;
@@ -963,6 +1027,10 @@ private:
     DevBuf<int32_t> d_bundle_bdd_, d_ext_var_, d_ext_bdd_, d_nr_bdds_;
     DevBuf<REAL> d_cfr_, d_cft_, d_lohi_[2], d_mmd_, d_mm_lo_, d_mm_hi_, d_delta_[3], d_delta_tmp_, d_bdd_lb_;
     DevBuf<double> d_lb_partial_;
+    DevBuf<uint32_t> d_barrier_;         // grid barrier of the on-chip kernel: {arrival count, generation}
+    bool res_ok_ = false;
+    unsigned res_grid_ = 1, res_wpc_ = 1;
+    uint32_t res_warp_smem_ = 0;
     DevBuf<char> d_round_types_;
     DevBuf<REAL> d_round_d0_, d_round_d1_;
     DevBuf<unsigned long long> d_round_counts_;

@@ -277,14 +277,22 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    lb0 = solver.lower_bound()
+    # one launch per iteration (the on-chip kernel, bdd_b200/csrc/resident.cuh) when the collection is eligible
+    l0 = local.kernel_launches()
+    if world == 1:
+        local.iteration()
+    fused = world == 1 and local.kernel_launches() - l0 == 1
+
     def one_iteration():
         if world > 1:
             solver.iteration()
+        elif fused:
+            local.iteration()
         else:
             local.forward_pass(0.5)
             local.backward_pass(0.5)
 
-    lb0 = solver.lower_bound()
     for _ in range(max(args.warmup, 3)):
         flush_l2()
         one_iteration()
@@ -307,6 +315,9 @@ def run_ours(args):
             solver.exchange_sums()
             local.backward_pass(0.5)
             solver.exchange_sums()
+        elif fused:
+            local.iteration()
+            ev[k][1].record(st)
         else:
             local.forward_pass(0.5)
             ev[k][1].record(st)
@@ -336,7 +347,11 @@ def run_ours(args):
     b2b_ms = e0.elapsed_time(e1) / nb
 
     # ---- roofline pass timing at N>1 needs the backward kernel alone --------------------------
-    if world == 1:
+    if fused:
+        # the launch IS the iteration: forward and backward pass in one kernel
+        bwd_ms = fwd_ms
+        pass_bytes *= 2
+    elif world == 1:
         bwd_ms = [e[1].elapsed_time(e[2]) for e in ev]
     else:
         bwd_ms = fwd_ms
@@ -418,7 +433,7 @@ def run_ours(args):
                     "run_solver_loop": {"value": shards / rs_s, "unit": unit, "step": "iteration() + lower_bound()"}},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "sweep_kernel<REAL, MODE_MMA, fwd|bwd>", "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": pass_bytes,
+                         "kernel": "resident_kernel<REAL> (one launch = forward + backward pass)" if fused else "sweep_lane_kernel<REAL, MODE_MMA, fwd|bwd>", "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": pass_bytes,
                          "peak_source": peak_src},
             "cpu_baseline": cpu,
             "clocks": clocks,
