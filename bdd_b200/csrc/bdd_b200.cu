@@ -192,7 +192,9 @@ public:
         CUDA_CHECK(cudaDeviceGetAttribute(&max_optin_, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
         CUDA_CHECK(cudaDeviceGetAttribute(&n_sms_, cudaDevAttrMultiProcessorCount, device));
         plan_launch();
+        L_var_lay_begin_ = L.var_lay_begin;
         plan_resident();
+        L_var_lay_begin_.clear(); L_var_lay_begin_.shrink_to_fit();
 
         std::vector<int2> lay_vn(L.n_lay);
         for(size_t i = 0; i < L.n_lay; ++i)
@@ -239,12 +241,12 @@ public:
         for(int i = 0; i < 2; ++i) { d_lohi_[i].alloc(2 * n_lay_); d_lohi_[i].zero(stream_); }
         d_mmd_.alloc(n_lay_); d_mmd_.zero(stream_);
         d_mm_lo_.alloc(n_lay_); d_mm_hi_.alloc(n_lay_);
-        for(int i = 0; i < 3; ++i) { d_delta_[i].alloc(2 * n_vars_ + RES_SCRATCH); d_delta_[i].zero(stream_); }     // + scratch pairs of the on-chip kernel
+        for(int i = 0; i < 3; ++i) { d_delta_[i].alloc(2 * n_vars_); d_delta_[i].zero(stream_); }
         d_delta_tmp_.alloc(2 * n_vars_);
         d_bdd_lb_.alloc(n_bdds_);
         d_lb_partial_.alloc(LB_BLOCKS + 1 + LB_SLOTS); d_lb_partial_.zero(stream_);
-        d_barrier_.alloc(32); d_barrier_.zero(stream_);
         CUDA_CHECK(cudaMallocHost(&h_lb_, LB_SLOTS * sizeof(double)));
+        alloc_resident();
 
         configure_kernels();
 
@@ -284,8 +286,11 @@ public:
         d_inv_tab_.clone_from(o.d_inv_tab_, stream_); inv_count_ = o.inv_count_; pdl_ = o.pdl_;
         d_delta_tmp_.clone_from(o.d_delta_tmp_, stream_); d_bdd_lb_.clone_from(o.d_bdd_lb_, stream_); d_lb_partial_.clone_from(o.d_lb_partial_, stream_);
         CUDA_CHECK(cudaMallocHost(&h_lb_, LB_SLOTS * sizeof(double)));
-        d_barrier_.alloc(32); d_barrier_.zero(stream_);
         res_ok_ = o.res_ok_; res_grid_ = o.res_grid_; res_wpc_ = o.res_wpc_; res_warp_smem_ = o.res_warp_smem_;
+        res_vars_per_bundle_ = o.res_vars_per_bundle_; res_own_cap_ = o.res_own_cap_; res_own_off_ = o.res_own_off_;
+        d_contrib_.clone_from(o.d_contrib_, stream_); d_sums_.clone_from(o.d_sums_, stream_); d_lb_part_.clone_from(o.d_lb_part_, stream_);
+        if(res_ok_) CUDA_CHECK(cudaMallocHost(&h_lb_part_, std::max<size_t>(n_lane_, 1) * sizeof(double)));
+        res_pass_ = o.res_pass_; exch_in_contrib_ = o.exch_in_contrib_; lb_from_resident_ = o.lb_from_resident_;
         cc_ = o.cc_; dcur_ = o.dcur_; delta_needs_norm_ = o.delta_needs_norm_;
         forward_valid_ = o.forward_valid_; backward_valid_ = o.backward_valid_; lb_valid_ = o.lb_valid_; lb_ = o.lb_;
         configure_kernels();
@@ -297,6 +302,7 @@ public:
         cudaSetDevice(device);
         if(graph_exec_) cudaGraphExecDestroy(graph_exec_);
         if(h_lb_) cudaFreeHost(h_lb_);
+        if(h_lb_part_) cudaFreeHost(h_lb_part_);
         if(h_round_counts_) cudaFreeHost(h_round_counts_);
         if(h_stage_) { cudaFreeHost(h_stage_); cudaEventDestroy(stage_free_); }
         if(own_stream_ && stream_) cudaStreamDestroy(stream_);
@@ -319,8 +325,10 @@ public:
         // every backward sweep ADDS the roots' values to lb_sum; every forward sweep clears it (block 0).  A backward sweep that
         // does not directly follow a forward sweep (forward_mm, lower_bound(), backward_mm: the bound in between runs a plain
         // backward sweep) must clear it first.
+        if(MODE == MODE_MMA) ensure_sums();
         if(!FORWARD && !deterministic_ && !lb_sum_clean_) zero_lb_sum();
         lb_sum_clean_ = FORWARD;
+        if(!FORWARD) lb_from_resident_ = false;
         if(n_lane_ > 0)
         {   // lane-local class: bundles [0, n_lane)
             a.desc = reinterpret_cast<const uint32_t*>(d_desc_lane_.p);
@@ -461,15 +469,53 @@ public:
     {
         res_ok_ = false;
         if(std::getenv("BDDB200_NO_RESIDENT") != nullptr && std::atoi(std::getenv("BDDB200_NO_RESIDENT")) != 0) return;
-        if(deterministic_ || n_lane_ == 0 || n_lane_ != n_bundles_ || n_lane_ > (size_t)n_sms_ * 16 || n_vars_ >= ((size_t)1 << 26)) return;
+        if(n_lane_ == 0 || n_lane_ != n_bundles_ || n_lane_ > (size_t)n_sms_ * 16 || n_vars_ >= ((size_t)1 << 26)) return;
         res_grid_ = (unsigned)std::min<size_t>(n_lane_, (size_t)n_sms_);
         res_wpc_ = (unsigned)((n_lane_ + res_grid_ - 1) / res_grid_);
-        res_warp_smem_ = (uint32_t)((resident_bundle_bytes(lane_max_hops_, lane_max_J_, sizeof(REAL)) + 127) & ~(size_t)127);
-        const size_t static_smem = INV_TAB * sizeof(REAL) + 16 * 8 + 256;
-        if((size_t)res_wpc_ * res_warp_smem_ + static_smem > (size_t)max_optin_) return;
-        res_ok_ = true;
+        const uint32_t state_bytes = (uint32_t)((resident_bundle_bytes(lane_max_hops_, lane_max_J_, sizeof(REAL)) + 127) & ~(size_t)127);
+        const size_t static_smem = 16 * 8 + 256;
+        if((size_t)res_wpc_ * state_bytes + static_smem > (size_t)max_optin_) return;
+        // owner duty: bundle g owns vars_per_bundle consecutive variables; their layer lists are staged in shared memory when they fit
+        res_vars_per_bundle_ = (uint32_t)((n_vars_ + n_lane_ - 1) / n_lane_);
+        size_t max_list = 0;
+        for(size_t g = 0; g < n_lane_; ++g)
+        {
+            const size_t b = std::min(n_vars_, g * (size_t)res_vars_per_bundle_), e = std::min(n_vars_, b + res_vars_per_bundle_);
+            max_list = std::max<size_t>(max_list, L_var_lay_begin_[e] - L_var_lay_begin_[b]);
+        }
+        const size_t own_bytes = ((((size_t)res_vars_per_bundle_ + 1 + 3) & ~(size_t)3) + max_list) * 4;
+        res_own_off_ = state_bytes; res_own_cap_ = 0; res_warp_smem_ = state_bytes;
+        if((size_t)res_wpc_ * (state_bytes + ((own_bytes + 127) & ~(size_t)127)) + static_smem <= (size_t)max_optin_)
+        {
+            res_own_cap_ = (uint32_t)std::max<size_t>(max_list, 1);
+            res_warp_smem_ = (uint32_t)(state_bytes + ((own_bytes + 127) & ~(size_t)127));
+        }
+        int coop = 0;
+        CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+        res_ok_ = coop != 0;
+    }
+    void alloc_resident()
+    {
+        if(!res_ok_) return;
+        d_contrib_.alloc(n_lay_ * ExchangeRec<REAL>::CONTRIB); d_contrib_.zero(stream_);
+        d_sums_.alloc((n_vars_ + 1) * ExchangeRec<REAL>::SUM); d_sums_.zero(stream_);
+        d_lb_part_.alloc(n_lane_); d_lb_part_.zero(stream_);
+        CUDA_CHECK(cudaMallocHost(&h_lb_part_, std::max<size_t>(n_lane_, 1) * sizeof(double)));
     }
     bool use_resident() const { return res_ok_ && delta_in_override_ == nullptr && ext_delta_[0] == nullptr; }
+
+    // After a launch of the on-chip kernel the pending per-variable sums exist as the contribution records of its last pass (and
+    // as deffered_mm_diff_): put them into the rotating sum buffer the streaming kernels and the accessors read.
+    void ensure_sums()
+    {
+        if(!exch_in_contrib_) return;
+        delta_segsum_kernel<REAL><<<blocks_for(n_vars_), 256, 0, stream_>>>(d_var_lay_begin_.p, d_var_lay_.p, d_mmd_.p, dbuf(dcur_), (uint32_t)n_vars_);
+        ++launches_;
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaMemsetAsync(dbuf((dcur_ + 1) % 3), 0, sizeof(REAL) * 2 * n_vars_, stream_));      // the next pass accumulates into it
+        delta_needs_norm_ = true;
+        exch_in_contrib_ = false;
+    }
 
     // n iterations in ONE cooperative launch; cost_from_terminal is recomputed on chip first when it is stale
     void launch_resident(double omega, size_t n, unsigned long long* trace = nullptr)
@@ -478,26 +524,35 @@ public:
         while(n > 0)
         {
             const size_t k = std::min<size_t>(n, 1u << 16);
+            uint32_t published = 0;
+            if(!exch_in_contrib_)
+            {   // hand the pending sums of the rotating buffer over to the on-chip kernel's exchange
+                ++res_pass_;
+                publish_sums_kernel<REAL><<<blocks_for(n_vars_), 256, 0, stream_>>>(dbuf(dcur_), d_nr_bdds_.p, d_sums_.p, res_pass_, delta_needs_norm_ ? 1 : 0, (uint32_t)n_vars_);
+                ++launches_;
+                CUDA_CHECK(cudaGetLastError());
+                published = 1;
+            }
             ResidentArgs<REAL> a{};
             a.desc = d_desc_lane_.p; a.topo = d_topo_.p; a.lay_vn = d_lay_vn_.p; a.bundle_bdd = d_bundle_bdd_.p;
             a.cfr = d_cfr_.p; a.cft = d_cft_.p; a.lohi = reinterpret_cast<R2*>(d_lohi_[cc_].p); a.mmd = d_mmd_.p;
-            for(int i = 0; i < 3; ++i) a.delta[i] = dbuf(i);
-            a.cur = (uint32_t)dcur_; a.n_delta = (uint32_t)(2 * n_vars_);
-            a.bdd_lb = d_bdd_lb_.p; a.lb_sum = d_lb_partial_.p + LB_BLOCKS + 1;
+            a.contrib = d_contrib_.p; a.sums = d_sums_.p; a.var_lay_begin = d_var_lay_begin_.p; a.var_lay = d_var_lay_.p; a.nr_bdds = d_nr_bdds_.p;
+            a.n_vars = (uint32_t)n_vars_; a.vars_per_bundle = res_vars_per_bundle_; a.own_list_cap = res_own_cap_; a.own_smem_off = res_own_off_;
+            a.pass0 = res_pass_; a.sums_published = published;
+            a.bdd_lb = d_bdd_lb_.p; a.lb_part = d_lb_part_.p;
             a.omega = (REAL)omega; a.n_iterations = (uint32_t)k; a.init_backward = backward_valid_ ? 0u : 1u;
             a.n_bundles = (uint32_t)n_lane_; a.bundles_per_cta = (uint32_t)(n_lane_ / res_grid_); a.bundles_rem = (uint32_t)(n_lane_ % res_grid_);
-            a.zero_pairs_per_bundle = (uint32_t)((n_vars_ + n_lane_ - 1) / n_lane_);
-            a.warp_smem_bytes = res_warp_smem_; a.inv_count = inv_count_; a.barrier = d_barrier_.p;
+            a.warp_smem_bytes = res_warp_smem_;
             a.n_classes = (uint32_t)lane_cls_begin_.size();
             for(size_t c = 0; c < lane_cls_begin_.size(); ++c) { a.cls_first[c] = lane_cls_first_[c]; a.cls_begin[c] = lane_cls_begin_[c]; }
             a.trace = trace;
-            if(const char* e = std::getenv("BDDB200_RES_DEBUG")) a.debug = (uint32_t)std::atoi(e);
             void* params[] = { &a };
-            CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)resident_kernel<REAL>, dim3(res_grid_), dim3(res_wpc_ * 32), params,
-                                                   (size_t)res_wpc_ * res_warp_smem_, stream_));
+            const void* kern = res_wpc_ <= 8 ? (const void*)resident_kernel<REAL, 256> : (const void*)resident_kernel<REAL, 512>;
+            CUDA_CHECK(cudaLaunchCooperativeKernel(kern, dim3(res_grid_), dim3(res_wpc_ * 32), params, (size_t)res_wpc_ * res_warp_smem_, stream_));
             ++launches_;
-            dcur_ = (int)((dcur_ + 2 * k) % 3); delta_needs_norm_ = true;
-            forward_valid_ = false; backward_valid_ = true; lb_valid_ = false; lb_sum_clean_ = false;
+            res_pass_ += (uint32_t)(2 * k);
+            exch_in_contrib_ = true; delta_needs_norm_ = true;
+            forward_valid_ = false; backward_valid_ = true; lb_valid_ = false; lb_sum_clean_ = false; lb_from_resident_ = true;
             n -= k;
         }
     }
@@ -505,7 +560,10 @@ public:
     void configure_kernels()
     {
         if(res_ok_)
-            CUDA_CHECK(cudaFuncSetAttribute(resident_kernel<REAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)res_wpc_ * res_warp_smem_)));
+        {
+            CUDA_CHECK(cudaFuncSetAttribute(resident_kernel<REAL, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)res_wpc_ * res_warp_smem_)));
+            CUDA_CHECK(cudaFuncSetAttribute(resident_kernel<REAL, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)res_wpc_ * res_warp_smem_)));
+        }
         const int need_lane = (int)((size_t)lane_wpc_ * lane_warp_smem_);
         if(n_lane_ > 0 && need_lane > 40 * 1024)
         {
@@ -681,6 +739,7 @@ public:
     void get_delta(void* out, int out_is_host) override
     {
         set_device();
+        ensure_sums();
         const REAL* src = dbuf(dcur_);
         if(delta_in_override_ && n_shared_vars_ > 0)
         {   // exchanged sums of the shared variables, local sums of the rest
@@ -698,7 +757,7 @@ public:
         if(out_is_host) CUDA_CHECK(cudaStreamSynchronize(stream_));
     }
 
-    void* delta_sum_buffer() override { return dbuf(dcur_); }
+    void* delta_sum_buffer() override { set_device(); ensure_sums(); return dbuf(dcur_); }
     int delta_sum_index() const override { return dcur_; }
     // Multi-GPU exchange over peer memory: the three rotating sum buffers live in caller-owned (symmetric) memory, and the
     // passes read the exchanged sums from a separate buffer (bddb200_delta_exchange writes it).
@@ -765,6 +824,15 @@ public:
         if(!lb_valid_)
         {
             const double* src = d_lb_partial_.p + LB_BLOCKS + 1;      // accumulated by the backward sweep itself
+            if(lb_from_resident_ && !deterministic_)
+            {   // one partial sum per bundle from the on-chip kernel's last backward pass, added in bundle order
+                CUDA_CHECK(cudaMemcpyAsync(h_lb_part_, d_lb_part_.p, n_lane_ * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+                CUDA_CHECK(cudaStreamSynchronize(stream_));
+                lb_ = 0.0;
+                for(size_t i = 0; i < n_lane_; ++i) lb_ += h_lb_part_[i];
+                lb_valid_ = true;
+                return lb_;
+            }
             if(deterministic_)
             {   // fixed-shape two-stage tree over the per-BDD values (bit-reproducible)
                 lb_partial_kernel<REAL><<<LB_BLOCKS, 256, 0, stream_>>>(d_bdd_lb_.p, d_lb_partial_.p, (uint32_t)n_bdds_);
@@ -845,7 +913,7 @@ public:
         CUDA_CHECK(cudaGetLastError());
         for(int i = 0; i < 3; ++i) CUDA_CHECK(cudaMemsetAsync(dbuf(i), 0, sizeof(REAL) * 2 * n_vars_, stream_));
         if(delta_in_override_) CUDA_CHECK(cudaMemsetAsync(delta_in_override_, 0, sizeof(REAL) * 2 * n_shared_vars_, stream_));
-        delta_needs_norm_ = false;
+        delta_needs_norm_ = false; exch_in_contrib_ = false;
         flush_forward(); flush_backward();
     }
     void get_solver_costs(void* lo, void* hi, void* mmd) const override
@@ -860,6 +928,7 @@ public:
     void set_solver_costs(const void* lo, const void* hi, const void* mmd) override
     {
         set_device();
+        ensure_sums();      // the pending sums are separate state (delta_lo_hi_) in the reference
         const unsigned nb = blocks_for(n_ext_);
         scatter_ext_kernel<REAL><<<nb, 256, 0, stream_>>>(d_ext2lay_.p, d_ext_var_.p, static_cast<const REAL*>(lo), d_lohi_[cc_].p, 2u, (uint32_t)n_ext_);
         scatter_ext_kernel<REAL><<<nb, 256, 0, stream_>>>(d_ext2lay_.p, d_ext_var_.p, static_cast<const REAL*>(hi), d_lohi_[cc_].p + 1, 2u, (uint32_t)n_ext_);
@@ -1027,7 +1096,14 @@ private:
     DevBuf<int32_t> d_bundle_bdd_, d_ext_var_, d_ext_bdd_, d_nr_bdds_;
     DevBuf<REAL> d_cfr_, d_cft_, d_lohi_[2], d_mmd_, d_mm_lo_, d_mm_hi_, d_delta_[3], d_delta_tmp_, d_bdd_lb_;
     DevBuf<double> d_lb_partial_;
-    DevBuf<uint32_t> d_barrier_;         // grid barrier of the on-chip kernel: {arrival count, generation}
+    DevBuf<unsigned char> d_contrib_, d_sums_;      // exchange records of the on-chip kernel (resident.cuh)
+    DevBuf<double> d_lb_part_;
+    double* h_lb_part_ = nullptr;
+    uint32_t res_vars_per_bundle_ = 0, res_own_cap_ = 0, res_own_off_ = 0;
+    std::vector<uint32_t> L_var_lay_begin_;         // host copy, alive during planning only
+    uint32_t res_pass_ = 0;              // number of the last pass of the on-chip kernel
+    bool exch_in_contrib_ = false;       // the pending sums exist as contribution records, the rotating sum buffer is stale
+    bool lb_from_resident_ = false;      // the last backward sweep was the on-chip kernel's: the bound is in d_lb_part_
     bool res_ok_ = false;
     unsigned res_grid_ = 1, res_wpc_ = 1;
     uint32_t res_warp_smem_ = 0;

@@ -5,15 +5,25 @@
 // memory of the SM whose warp owns the bundle.  ONE cooperative launch then runs any number of
 //   iteration() = forward_mm, normalize_delta, backward_mm, normalize_delta      (bdd_cuda_parallel_mma.cu:142-153)
 // with the state staying on chip between the passes: it is read from HBM once when the launch starts (bulk-async copies, one
-// mbarrier per warp) and written back once when it ends (bulk-async stores).  Between two passes the only data that leaves the
-// SM are the per-variable sums of min-marginal differences (compute_delta_atomic, :358-376: one predicated red.global.add per
-// layer) and the only synchronisation is one grid-wide barrier -- the sums of pass p must be complete before pass p + 1 reads
-// them.  The three sum buffers rotate as in the streaming kernels (kernels.cuh): read / accumulate / clear for the pass after next.
+// mbarrier per warp) and written back once when it ends (bulk-async stores).
 //
-// The hop arithmetic is the streaming lane kernel's (sweep_lane_bundle) operation for operation, so both produce the same
-// numbers; what differs is where operands live: every hop operand is a shared-memory word at a compile-time offset from one
-// running address, the per-variable values of a pass are gathered and normalised in one batch right after the barrier
-// (all loads in flight together, off the hop-to-hop dependency chain), and the hop loop itself contains no global load.
+// Cross-BDD averaging without atomics and without grid barriers.  What couples the BDDs is, per variable v and pass p, the sum of
+// the min-marginal differences of the layers of v (compute_delta_atomic :358-376, normalize_delta :410-430).  Measured on B200
+// (tools/microbench/scatter_cost2.cu, barrier_cost.cu) a scattered red.global.add costs 2.5 cycles per lane per SM, a scattered
+// load 1.2-1.3, a grid barrier 3 000-4 000 cycles -- together more than the min-plus arithmetic of a pass.  So the exchange is
+// a data-flow protocol of plain stores and loads, every datum travelling with the number of the pass that produced it:
+//   * the hop loop of pass p writes, per layer entry, the record {mm_diff, p} (one coalesced 8-byte store per lane);
+//   * every variable has an owner warp; when that warp starts pass p + 1 it loads the records of the variable's layers (waiting
+//     until each carries p), adds them in BDD order, divides by nr_bdds(v) and publishes {lo, p, hi, p};
+//   * every warp then loads the published sums of the variables of its own layers (waiting for p) and runs its hop loop.
+// A record is written and read as naturally aligned 8-byte {value, pass} pairs, so value and pass number arrive together (the
+// scheme of NCCL's LL protocol); no fence, no atomic, no barrier is involved, warps run ahead of each other by at most one pass,
+// and the sums are added in a fixed order with an exact division: the result is bit-reproducible and equals the single-threaded
+// CPU solver's.  Buffers are single: a record is only overwritten after everyone who needed the old value has produced the data
+// that the overwrite itself waits for (contributions of pass p + 1 need the sums of pass p, which need the contributions of p).
+// Cooperative launch is used only for its guarantee that all CTAs are co-resident (the warps wait for each other's data).
+//
+// The hop arithmetic is the streaming lane kernel's (sweep_lane_bundle, deterministic form) operation for operation.
 #pragma once
 
 #include "kernels.cuh"
@@ -21,11 +31,66 @@
 namespace bddb200 {
 
 constexpr int RES_TRACE_EVENTS = 16;
+constexpr uint32_t RES_MAX_SPINS = 1u << 22;       // x (40 ns sleep + one L2 round trip): seconds
 constexpr uint32_t VN_N_NONE = 0u, VN_N_TOP = 0xFFFFFFFFu;      // shared-memory copy of lay_vn.y for entries without a variable
-constexpr uint32_t RES_SCRATCH = 64;               // REALs behind the 2V sums of every sum buffer: targets of entries without a variable
-#ifndef BDDB200_RES_RED
-#define BDDB200_RES_RED 1       // 1: one unconditional reduction per layer entry (zero differences add +0), 0: skipped (branch) where the difference is 0
-#endif
+
+// ---- exchange records --------------------------------------------------------------------------------------------------
+// float : contribution {diff, pass} 8 B,                               sum {lo, pass, hi, pass} 16 B
+// double: contribution {diff.lo32, pass, diff.hi32, pass} 16 B,        sum {lo.lo32, pass, lo.hi32, pass, hi.lo32, pass, hi.hi32, pass} 32 B
+template<typename REAL> struct ExchangeRec;
+template<> struct ExchangeRec<float> { static constexpr uint32_t CONTRIB = 8, SUM = 16; };
+template<> struct ExchangeRec<double> { static constexpr uint32_t CONTRIB = 16, SUM = 32; };
+
+__device__ __forceinline__ void st_contrib(unsigned char* p, float d, uint32_t pass)
+{
+    asm volatile("st.relaxed.gpu.global.v2.b32 [%0], {%1, %2};" :: "l"(p), "r"(__float_as_uint(d)), "r"(pass) : "memory");
+}
+__device__ __forceinline__ void st_contrib(unsigned char* p, double d, uint32_t pass)
+{
+    const unsigned long long u = (unsigned long long)__double_as_longlong(d);
+    asm volatile("st.relaxed.gpu.global.v4.b32 [%0], {%1, %2, %3, %4};" :: "l"(p), "r"((uint32_t)u), "r"(pass), "r"((uint32_t)(u >> 32)), "r"(pass) : "memory");
+}
+// loads bypass L1 (the producer is another SM); false = the record is not of pass `pass` yet
+__device__ __forceinline__ bool ld_contrib(const unsigned char* p, uint32_t pass, float& d)
+{
+    uint32_t x, f;
+    asm volatile("ld.relaxed.gpu.global.v2.b32 {%0, %1}, [%2];" : "=r"(x), "=r"(f) : "l"(p) : "memory");
+    d = __uint_as_float(x);
+    return f == pass;
+}
+__device__ __forceinline__ bool ld_contrib(const unsigned char* p, uint32_t pass, double& d)
+{
+    uint32_t x0, f0, x1, f1;
+    asm volatile("ld.relaxed.gpu.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(f0), "=r"(x1), "=r"(f1) : "l"(p) : "memory");
+    d = __longlong_as_double((long long)(((unsigned long long)x1 << 32) | x0));
+    return f0 == pass && f1 == pass;
+}
+__device__ __forceinline__ void st_sum(unsigned char* p, float lo, float hi, uint32_t pass)
+{
+    asm volatile("st.relaxed.gpu.global.v4.b32 [%0], {%1, %2, %3, %4};" :: "l"(p), "r"(__float_as_uint(lo)), "r"(pass), "r"(__float_as_uint(hi)), "r"(pass) : "memory");
+}
+__device__ __forceinline__ void st_sum(unsigned char* p, double lo, double hi, uint32_t pass)
+{
+    const unsigned long long a = (unsigned long long)__double_as_longlong(lo), b = (unsigned long long)__double_as_longlong(hi);
+    asm volatile("st.relaxed.gpu.global.v4.b32 [%0], {%1, %2, %3, %4};" :: "l"(p), "r"((uint32_t)a), "r"(pass), "r"((uint32_t)(a >> 32)), "r"(pass) : "memory");
+    asm volatile("st.relaxed.gpu.global.v4.b32 [%0], {%1, %2, %3, %4};" :: "l"(p + 16), "r"((uint32_t)b), "r"(pass), "r"((uint32_t)(b >> 32)), "r"(pass) : "memory");
+}
+__device__ __forceinline__ bool ld_sum(const unsigned char* p, uint32_t pass, float& lo, float& hi)
+{
+    uint32_t x0, f0, x1, f1;
+    asm volatile("ld.relaxed.gpu.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(f0), "=r"(x1), "=r"(f1) : "l"(p) : "memory");
+    lo = __uint_as_float(x0); hi = __uint_as_float(x1);
+    return f0 == pass && f1 == pass;
+}
+__device__ __forceinline__ bool ld_sum(const unsigned char* p, uint32_t pass, double& lo, double& hi)
+{
+    uint32_t x0, f0, x1, f1, y0, g0, y1, g1;
+    asm volatile("ld.relaxed.gpu.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(f0), "=r"(x1), "=r"(f1) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(y0), "=r"(g0), "=r"(y1), "=r"(g1) : "l"(p + 16) : "memory");
+    lo = __longlong_as_double((long long)(((unsigned long long)x1 << 32) | x0));
+    hi = __longlong_as_double((long long)(((unsigned long long)y1 << 32) | y0));
+    return f0 == pass && f1 == pass && g0 == pass && g1 == pass;
+}
 
 template<typename REAL>
 struct ResidentArgs {
@@ -37,24 +102,28 @@ struct ResidentArgs {
     REAL* cft;
     typename real2<REAL>::type* lohi;      // current {lo, hi} buffer, updated in place
     REAL* mmd;
-    REAL* delta[3];                // rotating per-variable sums; pass p of the launch reads delta[(cur + p) % 3]
-    uint32_t cur;
-    uint32_t n_delta;              // 2V
+    unsigned char* contrib;        // one contribution record per layer entry
+    unsigned char* sums;           // one sum record per variable
+    const uint32_t* var_lay_begin; // variable -> its layer entries in BDD order (layout.hpp)
+    const uint32_t* var_lay;
+    const int32_t* nr_bdds;        // per variable (global counts in shard mode)
+    uint32_t n_vars;
+    uint32_t vars_per_bundle;      // bundle g owns the variables [g * vars_per_bundle, (g + 1) * vars_per_bundle)
+    uint32_t own_list_cap;         // > 0: the layer lists of the owned variables (at most this many entries) are staged in shared memory
+    uint32_t pass0;                // number of the last pass before this launch (its records / sums carry it)
+    uint32_t sums_published;       // the sums of pass0 are already in `sums` (published by the host from the rotating sum buffers)
     REAL* bdd_lb;
-    double* lb_sum;                // LB_SLOTS partial sums (zeroed by this kernel, filled by its last backward pass)
+    double* lb_part;               // one partial lower bound per bundle (written by the last backward pass)
     REAL omega;
     uint32_t n_iterations;
     uint32_t init_backward;        // cost_from_terminal is stale (costs were changed): recompute it on chip first (backward_run, bdd_cuda_base.cu:670-713)
     uint32_t n_bundles, bundles_per_cta, bundles_rem;
-    uint32_t zero_pairs_per_bundle;
     uint32_t warp_smem_bytes;
-    uint32_t inv_count;
-    uint32_t* barrier;             // {arrival count, generation}; both return to a consistent state after every barrier
+    uint32_t own_smem_off;         // byte offset of the owner-duty lists inside a warp's shared memory
     LaneDesc cls_first[LANE_MAX_CLASSES];
     uint32_t cls_begin[LANE_MAX_CLASSES];
     uint32_t n_classes;
     unsigned long long* trace;     // diagnostics: RES_TRACE_EVENTS clock stamps per bundle (null = off)
-    uint32_t debug;                // diagnostics (BDDB200_RES_DEBUG): 1 = two barriers + fences, 2 = write back and reload the state between iterations
 };
 
 // bytes of shared memory one bundle of H hops and J rows occupies (plus one spare tile of DP values and one spare hop of
@@ -64,68 +133,25 @@ inline size_t resident_bundle_bytes(uint32_t H, uint32_t J, size_t R)
     return (size_t)H * (128 + 256 + 64 * R + 2 * (size_t)J * 32 * R + 64 * R) + (size_t)J * 32 * R + (128 + 256 + 128 * R + 2 * (size_t)J * 32 * R);
 }
 
-// ---- grid-wide barrier -------------------------------------------------------------------------------------------------
-// All CTAs of the (cooperative, hence co-resident) launch arrive; the last one resets the count and opens the next
-// generation.  Thread 0's release/acquire operations at gpu scope, bracketed by CTA barriers, order every thread's earlier
-// global writes and reductions before every thread's later reads (the cooperative-groups grid.sync() pattern).
-__device__ __forceinline__ void grid_barrier(uint32_t* bar, const uint32_t n_ctas)
-{
-    __syncthreads();
-    if(threadIdx.x == 0)
-    {
-        uint32_t gen, old;
-        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(bar + 1) : "memory");
-        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(bar) : "memory");
-        if(old == n_ctas - 1)
-        {
-            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(bar), "r"(0u) : "memory");
-            asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(bar + 1), "r"(gen + 1u) : "memory");
-        }
-        else
-        {
-            uint32_t seen;
-            do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar + 1) : "memory"); } while(seen == gen);
-        }
-    }
-    __syncthreads();
-}
-
 __device__ __forceinline__ void bulk_s2g(void* dst, const void* src_smem, uint32_t bytes)
 {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                  :: "l"(__cvta_generic_to_global(dst)), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
 }
 
-// compute_delta_atomic, bdd_cuda_parallel_mma.cu:358-376: |diff| is added to the hi sum of the variable if diff > 0, to its lo sum if
-// diff < 0.  `voff` is the byte offset of the variable's {lo, hi} pair.
-template<typename REAL>
-__device__ __forceinline__ void red_delta(REAL* base, uint32_t voff, REAL diff)
-{
-    REAL* addr = reinterpret_cast<REAL*>(reinterpret_cast<unsigned char*>(base) + (voff + (diff > 0 ? (uint32_t)sizeof(REAL) : 0u)));
-#if BDDB200_RES_RED == 1
-    red_add_if(true, addr, fabs(diff));
-#else
-    red_add_if(diff != 0, addr, fabs(diff));
-#endif
-}
-
-template<typename REAL> __device__ __forceinline__ typename real2<REAL>::type ldcg2(const REAL* p);
-template<> __device__ __forceinline__ float2 ldcg2<float>(const float* p) { return __ldcg(reinterpret_cast<const float2*>(p)); }
-template<> __device__ __forceinline__ double2 ldcg2<double>(const double* p) { return __ldcg(reinterpret_cast<const double2*>(p)); }
-
 // One bundle, all iterations of the launch.  Shared-memory layout of the bundle (bytes from `wsm`; every array is hop-major
 // with 32 lanes per row, i.e. the global layout, so that it moves with plain bulk copies):
 //   topo  H x 128            one-hot arc-target word per (hop, lane)
-//   vn    H x 256            {variable | LAY_NONE | LAY_TOP, nr_bdds(variable)}
+//   vn    H x 256            {byte offset of the variable's sum record, nr_bdds | VN_N_NONE | VN_N_TOP}
 //   lohi  H x 64 R           {lo, hi} arc costs, updated in place
 //   cfr   H x J x 32 R       cost_from_root
 //   cft   (H + 1) x J x 32 R cost_from_terminal; tile H is never selected (the last hop has no arcs)
 //   dl    H x 64 R           normalised {delta_lo, delta_hi} of the layer's variable for the current pass
 template<typename REAL, int J>
-__device__ __forceinline__ void resident_bundle(const ResidentArgs<REAL>& a, const LaneDesc d, const uint32_t g, unsigned char* wsm, uint64_t* bar_load,
-                                                const REAL* inv_tab, const int lane, const bool active)
+__device__ __forceinline__ void resident_bundle(const ResidentArgs<REAL>& a, const LaneDesc d, const uint32_t g, unsigned char* wsm, uint64_t* bar_load, const int lane)
 {
     using R2 = typename real2<REAL>::type;
+    using XR = ExchangeRec<REAL>;
     constexpr uint32_t R = sizeof(REAL);
     constexpr uint32_t S_TOPO = 128, S_VN = 256, S_LOHI = 64 * R, S_DP = J * 32 * R, S_DL = 64 * R;
     const REAL INF = real_inf<REAL>();
@@ -136,52 +162,38 @@ __device__ __forceinline__ void resident_bundle(const ResidentArgs<REAL>& a, con
     unsigned char* const m_cfr = m_lohi + H * S_LOHI;
     unsigned char* const m_cft = m_cfr + H * S_DP;
     unsigned char* const m_dl = m_cft + (H + 1) * S_DP;
-    const uint32_t n_ctas = gridDim.x;
+    // owner duty (only when own_list_cap > 0): begin offsets of the owned variables' layer lists and the lists themselves, as byte
+    // offsets of contribution records; placed behind the largest bundle's state
+    uint32_t* const m_own_begin = reinterpret_cast<uint32_t*>(wsm + a.own_smem_off);
+    uint32_t* const m_own_list = m_own_begin + ((a.vars_per_bundle + 1 + 3) & ~3u);
     const REAL omega = a.omega;
 
-    unsigned long long* trace = (a.trace && active) ? a.trace + (size_t)g * RES_TRACE_EVENTS : nullptr;
+    unsigned long long* trace = a.trace ? a.trace + (size_t)g * RES_TRACE_EVENTS : nullptr;
     uint32_t trace_k = 0;
     auto stamp = [&]() { if(trace && lane == 0 && trace_k < RES_TRACE_EVENTS) trace[trace_k] = clock64(); ++trace_k; };
     stamp();   // 0: start
 
-    int32_t bdd_index = -1;
-    if(active)
+    // ---- load: four bulk copies (four lanes, one issue) onto the warp's mbarrier
+    if(lane < 4)
     {
-        // ---- load: four bulk copies (four lanes, one issue) onto the warp's mbarrier
-        if(lane < 4)
-        {
-            const void* src = a.topo + d.topo_off; unsigned char* dst = m_topo; uint32_t bytes = H * S_TOPO;
-            if(lane == 1) { src = a.lay_vn + d.lay_off; dst = m_vn; bytes = H * S_VN; }
-            if(lane == 2) { src = a.lohi + d.lay_off; dst = m_lohi; bytes = H * S_LOHI; }
-            if(lane == 3) { src = a.cft + d.slot_off; dst = m_cft; bytes = a.init_backward ? 0u : H * S_DP; }
-            if(lane == 0) mbar_arrive_expect_tx(bar_load, H * (S_TOPO + S_VN + S_LOHI) + (a.init_backward ? 0u : H * S_DP));
-            if(bytes > 0) bulk_g2s(dst, src, bytes, bar_load);
-        }
-        bdd_index = a.bundle_bdd[d.bdd_base + lane];
-        mbar_wait(bar_load, 0);
+        const void* src = a.topo + d.topo_off; unsigned char* dst = m_topo; uint32_t bytes = H * S_TOPO;
+        if(lane == 1) { src = a.lay_vn + d.lay_off; dst = m_vn; bytes = H * S_VN; }
+        if(lane == 2) { src = a.lohi + d.lay_off; dst = m_lohi; bytes = H * S_LOHI; }
+        if(lane == 3) { src = a.cft + d.slot_off; dst = m_cft; bytes = a.init_backward ? 0u : H * S_DP; }
+        if(lane == 0) mbar_arrive_expect_tx(bar_load, H * (S_TOPO + S_VN + S_LOHI) + (a.init_backward ? 0u : H * S_DP));
+        if(bytes > 0) bulk_g2s(dst, src, bytes, bar_load);
     }
+    const int32_t bdd_index = a.bundle_bdd[d.bdd_base + lane];
+    mbar_wait(bar_load, 0);
     stamp();   // 1: state on chip
-    // {variable, nr_bdds} -> {byte offset of the variable's {lo, hi} pair in a sum buffer, nr_bdds}: the gather and the reductions
-    // address the sum buffers without an index computation.  Entries without a variable point at this lane's scratch pair behind
-    // the sums (they only ever add +0 there and read 0 from there) and carry VN_N_NONE / VN_N_TOP in place of the count.
-    if(active)
-        for(uint32_t h = 0; h < H; ++h)
-        {
-            const uint32_t addr = smem_u32(m_vn) + h * S_VN + lane * 8u;
-            int v, n; asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v), "=r"(n) : "r"(addr));
-            const uint32_t o = v >= 0 ? (uint32_t)v * (2u * R) : (a.n_delta + 2u * lane) * R;
-            const uint32_t c = v >= 0 ? (uint32_t)n : (v == LAY_TOP ? VN_N_TOP : VN_N_NONE);
-            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(addr), "r"(o), "r"(c) : "memory");
-        }
 
     const uint32_t lane_topo = smem_u32(m_topo) + lane * 4u, lane_vn = smem_u32(m_vn) + lane * 8u, lane_lohi = smem_u32(m_lohi) + lane * 2u * R;
     const uint32_t lane_cfr = smem_u32(m_cfr) + lane * R, lane_cft = smem_u32(m_cft) + lane * R, lane_dl = smem_u32(m_dl) + lane * 2u * R;
-    const uint32_t inv_tab_s = smem_u32(inv_tab);
 
+    // every shared-memory access is a volatile asm with a memory clobber: the state changes between the passes of one launch, and
+    // a plain asm load is a pure function of its address to the compiler (which then hoists it out of the iteration loop)
     auto lds_u32 = [](uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; };
     auto lds_i2 = [](uint32_t addr) { int2 v; asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory"); return v; };
-    // volatile: the DP rows change between the passes of one launch (a plain asm load is a pure function of its address to the
-    // compiler, which hoists it out of the iteration loop)
     auto lds_r = [](uint32_t addr) {
         REAL v;
         if constexpr (sizeof(REAL) == 4) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
@@ -204,59 +216,16 @@ __device__ __forceinline__ void resident_bundle(const ResidentArgs<REAL>& a, con
     };
     auto bit = [](uint32_t t, int j, int arc, int r) -> bool { return (t & (1u << (j * 2 * J + arc * J + r))) != 0; };
 
-    struct In { uint32_t t; uint32_t voff, cnt; REAL lo, hi, d0, d1; REAL c[J]; };
-    // operands of hop h: forward reads cost_from_terminal of tile h + 1, backward cost_from_root of tile h
-    auto load_fwd = [&](uint32_t h) {
-        In x;
-        x.t = lds_u32(lane_topo + h * S_TOPO);
-        x.voff = lds_u32(lane_vn + h * S_VN); x.cnt = 0;
-        const R2 c2 = lds_r2(lane_lohi + h * S_LOHI); x.lo = c2.x; x.hi = c2.y;
-        const R2 dl = lds_r2(lane_dl + h * S_DL); x.d0 = dl.x; x.d1 = dl.y;
-#pragma unroll
-        for(int r = 0; r < J; ++r) x.c[r] = lds_r(lane_cft + (h + 1) * S_DP + r * 32 * R);
-        return x;
-    };
-    auto load_bwd = [&](uint32_t h) {
-        In x;
-        x.t = lds_u32(lane_topo + h * S_TOPO);
-        const int2 vn = lds_i2(lane_vn + h * S_VN); x.voff = (uint32_t)vn.x; x.cnt = (uint32_t)vn.y;
-        const R2 c2 = lds_r2(lane_lohi + h * S_LOHI); x.lo = c2.x; x.hi = c2.y;
-        const R2 dl = lds_r2(lane_dl + h * S_DL); x.d0 = dl.x; x.d1 = dl.y;
-#pragma unroll
-        for(int r = 0; r < J; ++r) x.c[r] = lds_r(lane_cfr + h * S_DP + r * 32 * R);
-        return x;
-    };
+    // {variable, nr_bdds} -> {byte offset of the variable's sum record, nr_bdds | VN_N_NONE | VN_N_TOP}
+    for(uint32_t h = 0; h < H; ++h)
+    {
+        const int2 vn = lds_i2(lane_vn + h * S_VN);
+        const uint32_t o = (uint32_t)max(vn.x, 0) * XR::SUM;
+        const uint32_t c = vn.x >= 0 ? (uint32_t)max(vn.y, 1) : (vn.x == LAY_TOP ? VN_N_TOP : VN_N_NONE);
+        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(lane_vn + h * S_VN), "r"(o), "r"(c) : "memory");
+    }
 
-    // gather + normalise the per-variable sums of the previous pass for every hop of the bundle (normalize_delta,
-    // bdd_cuda_parallel_mma.cu:410-430, folded into the read); L2 loads (.cg): the sums were accumulated by other SMs
-    auto gather = [&](const REAL* delta_in) {
-        constexpr uint32_t B = 8;
-        for(uint32_t h0 = 0; h0 < H; h0 += B)
-        {
-            int2 vn[B]; R2 dl[B];
-#pragma unroll
-            for(uint32_t k = 0; k < B; ++k) vn[k] = lds_i2(lane_vn + min(h0 + k, H - 1) * S_VN);
-#pragma unroll
-            for(uint32_t k = 0; k < B; ++k)
-                dl[k] = ldcg2<REAL>(reinterpret_cast<const REAL*>(reinterpret_cast<const unsigned char*>(delta_in) + (uint32_t)vn[k].x));
-#pragma unroll
-            for(uint32_t k = 0; k < B; ++k)
-            {   // entries without a variable read the 0 of their scratch pair; the table holds 1 at 0
-                const REAL r = lds_real<REAL>(inv_tab_s + (uint32_t)max(min(vn[k].y, INV_TAB - 1), 0) * R);      // VN_N_TOP is negative as int
-                const REAL d0 = dl[k].x * r, d1 = dl[k].y * r;
-                if(h0 + k < H) sts_r2(lane_dl + (h0 + k) * S_DL, d0, d1);
-            }
-        }
-    };
-    auto clear_share = [&](REAL* buf) {
-        R2* z = reinterpret_cast<R2*>(buf);
-        const uint32_t pairs = a.n_delta >> 1;
-        const uint32_t z0 = min(pairs, g * a.zero_pairs_per_bundle), z1 = min(pairs, z0 + a.zero_pairs_per_bundle);
-        R2 zero; zero.x = 0; zero.y = 0;
-        for(uint32_t i = z0 + lane; i < z1; i += 32) z[i] = zero;
-    };
-
-    if(active && a.init_backward)
+    if(a.init_backward)
     {   // backward_run(false): plain shortest paths to the top sink with the current arc costs
         REAL fr[J];
 #pragma unroll
@@ -286,18 +255,162 @@ __device__ __forceinline__ void resident_bundle(const ResidentArgs<REAL>& a, con
         }
     }
 
+    struct In { uint32_t t, cnt; REAL lo, hi, d0, d1; REAL c[J]; };
+    // operands of hop h: forward reads cost_from_terminal of tile h + 1, backward cost_from_root of tile h
+    auto load_fwd = [&](uint32_t h) {
+        In x;
+        x.t = lds_u32(lane_topo + h * S_TOPO); x.cnt = 0;
+        const R2 c2 = lds_r2(lane_lohi + h * S_LOHI); x.lo = c2.x; x.hi = c2.y;
+        const R2 dl = lds_r2(lane_dl + h * S_DL); x.d0 = dl.x; x.d1 = dl.y;
+#pragma unroll
+        for(int r = 0; r < J; ++r) x.c[r] = lds_r(lane_cft + (h + 1) * S_DP + r * 32 * R);
+        return x;
+    };
+    auto load_bwd = [&](uint32_t h) {
+        In x;
+        x.t = lds_u32(lane_topo + h * S_TOPO); x.cnt = lds_u32(lane_vn + h * S_VN + 4);
+        const R2 c2 = lds_r2(lane_lohi + h * S_LOHI); x.lo = c2.x; x.hi = c2.y;
+        const R2 dl = lds_r2(lane_dl + h * S_DL); x.d0 = dl.x; x.d1 = dl.y;
+#pragma unroll
+        for(int r = 0; r < J; ++r) x.c[r] = lds_r(lane_cfr + h * S_DP + r * 32 * R);
+        return x;
+    };
+
+    // ---- owner duty: sums of pass `pass` for the variables this bundle owns (compute_delta :379-393 + normalize_delta :410-430,
+    // in BDD order with an exact division like the single-threaded CPU solver)
+    const uint32_t own_begin = min(a.n_vars, g * a.vars_per_bundle), own_end = min(a.n_vars, own_begin + a.vars_per_bundle);
+    const bool own_staged = a.own_list_cap > 0;
+    uint32_t dbg_reduce_retries = 0, dbg_gather_retries = 0; long long dbg_reduce_first = 0, dbg_gather_first = 0, dbg_stage = 0;
+    const long long dbg_t_stage0 = trace ? clock64() : 0;
+    const uint32_t list0 = own_begin < own_end ? a.var_lay_begin[own_begin] : 0u;       // first list entry of the owned range
+    if(own_staged)
+    {
+        const uint32_t n_own = own_end - own_begin, n_list = (own_begin < own_end ? a.var_lay_begin[own_end] : 0u) - list0;
+        for(uint32_t i = lane; i <= n_own; i += 32) m_own_begin[i] = a.var_lay_begin[own_begin + i] - list0;
+        for(uint32_t i = lane; i < n_list; i += 32) m_own_list[i] = a.var_lay[list0 + i] * XR::CONTRIB;
+        __syncwarp();
+    }
+    if(trace) dbg_stage = clock64() - dbg_t_stage0;
+    // list entry i (relative to the owned range) -> byte offset of the contribution record
+    auto own_entry = [&](uint32_t i) -> uint32_t { return own_staged ? m_own_list[i] : a.var_lay[list0 + i] * XR::CONTRIB; };
+    auto reduce_owned = [&](const uint32_t pass) {
+        constexpr uint32_t B = 12;
+        // two variables per lane and round (A: v0 + lane, B: v0 + 32 + lane): their loads are in flight together
+        for(uint32_t v0 = own_begin; v0 < own_end; v0 += 64)
+        {
+            uint32_t vv[2], ib[2], ie[2]; REAL lo[2], hi[2];
+#pragma unroll
+            for(int q = 0; q < 2; ++q)
+            {
+                vv[q] = v0 + q * 32 + lane;
+                const bool mine = vv[q] < own_end;
+                const uint32_t r = vv[q] - own_begin;
+                ib[q] = !mine ? 0u : (own_staged ? m_own_begin[r] : a.var_lay_begin[vv[q]] - list0);
+                ie[q] = !mine ? 0u : (own_staged ? m_own_begin[r + 1] : a.var_lay_begin[vv[q] + 1] - list0);
+                lo[q] = 0; hi[q] = 0;
+            }
+            while(__any_sync(0xffffffffu, ib[0] < ie[0] || ib[1] < ie[1]))
+            {
+                uint32_t src[2][B]; REAL dv[2][B]; uint32_t want = 0, need = 0;       // bit q * B + k
+#pragma unroll
+                for(int q = 0; q < 2; ++q)
+#pragma unroll
+                    for(uint32_t k = 0; k < B; ++k)
+                    {
+                        const bool w = ib[q] + k < ie[q];
+                        src[q][k] = w ? own_entry(ib[q] + k) : 0u;
+                        dv[q][k] = 0;
+                        want |= w ? (1u << (q * B + k)) : 0u;
+                    }
+                // first attempt: all loads in flight together (no load depends on the outcome of another)
+                const long long t_first = trace ? clock64() : 0;
+#pragma unroll
+                for(int q = 0; q < 2; ++q)
+#pragma unroll
+                    for(uint32_t k = 0; k < B; ++k)
+                        if(want & (1u << (q * B + k)))
+                            need |= ld_contrib(a.contrib + src[q][k], pass, dv[q][k]) ? 0u : (1u << (q * B + k));
+                if(trace) { dbg_reduce_first += clock64() - t_first + (need & 0); }
+                for(uint32_t spins = 0; need != 0; ++spins)
+                {   // records of producers that have not got there yet
+                    ++dbg_reduce_retries;
+                    if(spins > RES_MAX_SPINS) __trap();          // a record that never arrives (a protocol bug) must not hang the GPU
+                    __nanosleep(20);
+                    uint32_t still = 0;
+#pragma unroll
+                    for(int q = 0; q < 2; ++q)
+#pragma unroll
+                        for(uint32_t k = 0; k < B; ++k)
+                            if(need & (1u << (q * B + k)))
+                                still |= ld_contrib(a.contrib + src[q][k], pass, dv[q][k]) ? 0u : (1u << (q * B + k));
+                    need = still;
+                }
+#pragma unroll
+                for(int q = 0; q < 2; ++q)
+                {
+#pragma unroll
+                    for(uint32_t k = 0; k < B; ++k)
+                        if(ib[q] + k < ie[q]) { if(dv[q][k] > 0) hi[q] += dv[q][k]; else if(dv[q][k] < 0) lo[q] += -dv[q][k]; }      // compute_delta_atomic, :358-376
+                    ib[q] = min(ib[q] + B, ie[q]);
+                }
+            }
+#pragma unroll
+            for(int q = 0; q < 2; ++q)
+                if(vv[q] < own_end)
+                {
+                    const REAL nn = (REAL)max(a.nr_bdds[vv[q]], 1);
+                    st_sum(a.sums + (size_t)vv[q] * XR::SUM, lo[q] / nn, hi[q] / nn, pass);
+                }
+        }
+    };
+    // the normalised sums of pass `pass` for the variables of this bundle's layers -> dl
+    auto gather = [&](const uint32_t pass) {
+        constexpr uint32_t B = 11;
+        for(uint32_t h0 = 0; h0 < H; h0 += B)
+        {
+            uint32_t src[B]; REAL d0[B], d1[B]; uint32_t want = 0, need = 0;
+#pragma unroll
+            for(uint32_t k = 0; k < B; ++k)
+            {
+                const int2 vn = lds_i2(lane_vn + min(h0 + k, H - 1) * S_VN);
+                src[k] = (uint32_t)vn.x;
+                d0[k] = 0; d1[k] = 0;
+                want |= (h0 + k < H && vn.y > 0) ? (1u << k) : 0u;          // VN_N_TOP is negative as int: entries without a variable read nothing
+            }
+            const long long t_first = trace ? clock64() : 0;
+#pragma unroll
+            for(uint32_t k = 0; k < B; ++k)
+                if(want & (1u << k)) need |= ld_sum(a.sums + src[k], pass, d0[k], d1[k]) ? 0u : (1u << k);
+            if(trace) { dbg_gather_first += clock64() - t_first + (need & 0); }
+            for(uint32_t spins = 0; need != 0; ++spins)
+            {
+                ++dbg_gather_retries;
+                if(spins > RES_MAX_SPINS) __trap();
+                __nanosleep(20);
+                uint32_t still = 0;
+#pragma unroll
+                for(uint32_t k = 0; k < B; ++k)
+                    if(need & (1u << k)) still |= ld_sum(a.sums + src[k], pass, d0[k], d1[k]) ? 0u : (1u << k);
+                need = still;
+            }
+#pragma unroll
+            for(uint32_t k = 0; k < B; ++k)
+                if(h0 + k < H) sts_r2(lane_dl + (h0 + k) * S_DL, d0[k], d1[k]);
+        }
+    };
+
     REAL* const g_mmd = a.mmd + d.lay_off + lane;
-    uint32_t cur = a.cur;
+    unsigned char* const g_contrib = a.contrib + (size_t)(d.lay_off + lane) * XR::CONTRIB;
+    uint32_t pass = a.pass0;       // number of the last completed pass
     for(uint32_t it = 0; it < a.n_iterations; ++it)
     {
         // =========================================================== forward_mm (bdd_cuda_parallel_mma.cu:207-257)
-        if(active)
         {
-            REAL* const delta_out = a.delta[(cur + 1) % 3];
-            gather(a.delta[cur]);
-            clear_share(a.delta[(cur + 2) % 3]);
-            __syncwarp();
-            if(it == 0) stamp();   // 2: first gather done
+            if(!(it == 0 && a.sums_published)) reduce_owned(pass);
+            if(it == 0) stamp();   // 2: owned sums published
+            gather(pass);
+            ++pass;
+            if(it == 0) stamp();   // 3: first gather done
             REAL fr[J];
 #pragma unroll
             for(int j = 0; j < J; ++j) fr[j] = INF;
@@ -348,23 +461,18 @@ __device__ __forceinline__ void resident_bundle(const ResidentArgs<REAL>& a, con
                 }
                 sts_r2(lane_lohi + h * S_LOHI, lo_n, hi_n);
                 g_mmd[h * 32] = diff;
-                // compute_delta_atomic, :358-376: |diff| goes to the hi slot if diff > 0, else to lo
-                red_delta(delta_out, x.voff, diff);
+                st_contrib(g_contrib + (size_t)h * 32 * XR::CONTRIB, diff, pass);
             }
-            if(it == 0) stamp();   // 3: forward hops done
+            if(it == 0) stamp();   // 4: forward hops done
         }
-        grid_barrier(a.barrier, n_ctas);
-        if(it == 0) stamp();       // 4: barrier passed
-        cur = (cur + 1) % 3;
 
         // =========================================================== backward_mm (:301-346)
-        if(active)
         {
-            REAL* const delta_out = a.delta[(cur + 1) % 3];
-            gather(a.delta[cur]);
-            clear_share(a.delta[(cur + 2) % 3]);
-            __syncwarp();
-            if(it == 0) stamp();   // 5: second gather done
+            reduce_owned(pass);
+            if(it == 0) stamp();   // 5: owned sums published
+            gather(pass);
+            ++pass;
+            if(it == 0) stamp();   // 6: second gather done
             REAL fr[J];            // cost_from_terminal of the next hop's rows
 #pragma unroll
             for(int j = 0; j < J; ++j) fr[j] = INF;
@@ -408,105 +516,90 @@ __device__ __forceinline__ void resident_bundle(const ResidentArgs<REAL>& a, con
                 }
                 sts_r2(lane_lohi + h * S_LOHI, lo_n, hi_n);
                 g_mmd[h * 32] = diff;
-                red_delta(delta_out, x.voff, diff);
+                st_contrib(g_contrib + (size_t)h * 32 * XR::CONTRIB, diff, pass);
             }
-            if(it == 0) stamp();   // 6: backward hops done
+            if(it == 0) stamp();   // 7: backward hops done
             if(it + 1 == a.n_iterations)
-            {   // lower_bound, bdd_cuda_base.cu:1243-1251: sum of the roots' cost_from_terminal in double
+            {   // lower_bound, bdd_cuda_base.cu:1243-1251: sum of the roots' cost_from_terminal in double (fixed order)
                 const REAL root = fr[0];
                 const bool mine_valid = bdd_index >= 0;
                 if(mine_valid) a.bdd_lb[bdd_index] = root;
                 double v = mine_valid ? (double)root : 0.0;
 #pragma unroll
                 for(int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if(lane == 0) atomicAdd(a.lb_sum + (blockIdx.x & (LB_SLOTS - 1)), v);
+                if(lane == 0) a.lb_part[g] = v;
             }
-        }
-        cur = (cur + 1) % 3;
-        if(it + 1 < a.n_iterations)
-        {
-            if(a.debug & 1u) { __threadfence(); grid_barrier(a.barrier, n_ctas); __threadfence(); }
-            if((a.debug & 2u) && active)
-            {   // the state takes the round trip through global memory a relaunch would give it
-                for(uint32_t h = 0; h < H; ++h)
-                {
-                    const R2 c2 = lds_r2(lane_lohi + h * S_LOHI);
-                    a.lohi[d.lay_off + h * 32 + lane] = c2;
-                    for(int j = 0; j < J; ++j) a.cft[d.slot_off + (h * J + j) * 32 + lane] = lds_r(lane_cft + h * S_DP + j * 32 * R);
-                }
-                __threadfence();
-                for(uint32_t h = 0; h < H; ++h)
-                {
-                    const R2 c2 = __ldcg(&a.lohi[d.lay_off + h * 32 + lane]);
-                    sts_r2(lane_lohi + h * S_LOHI, c2.x, c2.y);
-                    for(int j = 0; j < J; ++j) sts_r(lane_cft + h * S_DP + j * 32 * R, __ldcg(&a.cft[d.slot_off + (h * J + j) * 32 + lane]));
-                }
-            }
-            grid_barrier(a.barrier, n_ctas);       // the end of the launch orders the last pass
         }
     }
 
     // ---- write the state back: three bulk stores from shared memory
-    if(active)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // generic-proxy writes -> visible to the bulk-copy engine
+    __syncwarp();
+    if(lane < 3)
     {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // generic-proxy writes -> visible to the bulk-copy engine
-        __syncwarp();
-        if(lane < 3)
-        {
-            void* dst = a.lohi + d.lay_off; const unsigned char* src = m_lohi; uint32_t bytes = H * S_LOHI;
-            if(lane == 1) { dst = a.cfr + d.slot_off; src = m_cfr; bytes = H * S_DP; }
-            if(lane == 2) { dst = a.cft + d.slot_off; src = m_cft; bytes = H * S_DP; }
-            bulk_s2g(dst, src, bytes);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-        }
-        __syncwarp();
+        void* dst = a.lohi + d.lay_off; const unsigned char* src = m_lohi; uint32_t bytes = H * S_LOHI;
+        if(lane == 1) { dst = a.cfr + d.slot_off; src = m_cfr; bytes = H * S_DP; }
+        if(lane == 2) { dst = a.cft + d.slot_off; src = m_cft; bytes = H * S_DP; }
+        bulk_s2g(dst, src, bytes);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
-    stamp();   // 7: written back
+    __syncwarp();
+    stamp();   // 8: written back
+    if(trace && lane == 0)
+    {   // diagnostics of the exchange: retry rounds and cycles spent in the first-attempt loads (summed over the launch), list staging
+        trace[9] = dbg_reduce_retries; trace[10] = dbg_gather_retries; trace[11] = (unsigned long long)dbg_reduce_first;
+        trace[12] = (unsigned long long)dbg_gather_first; trace[13] = (unsigned long long)dbg_stage;
+    }
 }
 
 // One CTA per SM, one warp per bundle (dealt evenly: CTA b owns bundles_per_cta (+1 if b < bundles_rem) consecutive bundles).
-// Launched with cudaLaunchCooperativeKernel: all CTAs are co-resident, which the grid barrier needs.
-template<typename REAL>
-__global__ void __launch_bounds__(512, 1) resident_kernel(const ResidentArgs<REAL> a)
+// Launched with cudaLaunchCooperativeKernel: all CTAs are co-resident (the warps wait for each other's records).
+// MAXT = 256: up to 8 warps per CTA with up to 255 registers per thread (no spills); MAXT = 512: up to 16 warps.
+template<typename REAL, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) resident_kernel(const ResidentArgs<REAL> a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ REAL inv_tab[INV_TAB];
     __shared__ uint64_t bars_all[16];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t g_lo = blockIdx.x * a.bundles_per_cta + min(blockIdx.x, a.bundles_rem);
     const uint32_t g_hi = g_lo + a.bundles_per_cta + (blockIdx.x < a.bundles_rem ? 1u : 0u);
     const uint32_t g = g_lo + warp;
-    const bool active = g < g_hi;
-    LaneDesc d{};
-    d.J = 1; d.n_hops = 1;
-    if(active)
-    {
-        if(a.n_classes == 0) d = a.desc[g];
-        else
-        {
-            uint32_t c = 0;
-#pragma unroll
-            for(int k = 1; k < LANE_MAX_CLASSES; ++k) if((uint32_t)k < a.n_classes && g >= a.cls_begin[k]) c = k;
-            d = a.cls_first[c];
-            const uint32_t q = g - a.cls_begin[c];
-            d.slot_off += q * d.n_hops * d.J * 32u; d.lay_off += q * d.n_hops * 32u; d.topo_off += q * d.n_hops * 32u; d.bdd_base += q * 32u;
-        }
-    }
     if(threadIdx.x < (blockDim.x >> 5)) mbar_init(bars_all + threadIdx.x, 1);
     if(threadIdx.x == 0) mbar_fence_init();
-    for(uint32_t i = threadIdx.x; i < a.inv_count; i += blockDim.x) inv_tab[i] = (REAL)1 / (REAL)(i > 0 ? i : 1);
-    if(blockIdx.x == 0)
-        for(uint32_t i = threadIdx.x; i < (uint32_t)LB_SLOTS; i += blockDim.x) a.lb_sum[i] = 0.0;       // filled after at least one grid barrier
     __syncthreads();
+    if(g >= g_hi) return;
+    LaneDesc d;
+    if(a.n_classes == 0) d = a.desc[g];
+    else
+    {
+        uint32_t c = 0;
+#pragma unroll
+        for(int k = 1; k < LANE_MAX_CLASSES; ++k) if((uint32_t)k < a.n_classes && g >= a.cls_begin[k]) c = k;
+        d = a.cls_first[c];
+        const uint32_t q = g - a.cls_begin[c];
+        d.slot_off += q * d.n_hops * d.J * 32u; d.lay_off += q * d.n_hops * 32u; d.topo_off += q * d.n_hops * 32u; d.bdd_base += q * 32u;
+    }
     unsigned char* wsm = smem_raw + (size_t)warp * a.warp_smem_bytes;
     switch(d.J)
     {
-        case 1: resident_bundle<REAL, 1>(a, d, g, wsm, bars_all + warp, inv_tab, lane, active); break;
-        case 2: resident_bundle<REAL, 2>(a, d, g, wsm, bars_all + warp, inv_tab, lane, active); break;
-        case 3: resident_bundle<REAL, 3>(a, d, g, wsm, bars_all + warp, inv_tab, lane, active); break;
-        default: resident_bundle<REAL, 4>(a, d, g, wsm, bars_all + warp, inv_tab, lane, active); break;
+        case 1: resident_bundle<REAL, 1>(a, d, g, wsm, bars_all + warp, lane); break;
+        case 2: resident_bundle<REAL, 2>(a, d, g, wsm, bars_all + warp, lane); break;
+        case 3: resident_bundle<REAL, 3>(a, d, g, wsm, bars_all + warp, lane); break;
+        default: resident_bundle<REAL, 4>(a, d, g, wsm, bars_all + warp, lane); break;
     }
+}
+
+// Hand-over from the rotating sum buffers of the streaming kernels: sums[v] = {delta[2v] / n, delta[2v + 1] / n} tagged with `pass`
+// (normalize_delta, bdd_cuda_parallel_mma.cu:410-430; `normalize` = 0 when the buffer already holds normalised values)
+template<typename REAL>
+__global__ void publish_sums_kernel(const REAL* __restrict__ delta, const int32_t* __restrict__ nr_bdds, unsigned char* __restrict__ sums,
+                                    uint32_t pass, int normalize, uint32_t n_vars)
+{
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if(v >= n_vars) return;
+    const REAL nn = normalize ? (REAL)max(nr_bdds[v], 1) : (REAL)1;
+    st_sum(sums + (size_t)v * ExchangeRec<REAL>::SUM, delta[2 * (size_t)v] / nn, delta[2 * (size_t)v + 1] / nn, pass);
 }
 
 } // namespace bddb200

@@ -279,6 +279,8 @@ def run_ours(args):
 
     lb0 = solver.lower_bound()
     # one launch per iteration (the on-chip kernel, bdd_b200/csrc/resident.cuh) when the collection is eligible
+    if world == 1:
+        local.iteration()
     l0 = local.kernel_launches()
     if world == 1:
         local.iteration()

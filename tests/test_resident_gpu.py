@@ -57,7 +57,11 @@ def test_resident_equals_streaming(shape, precision):
     b = make(col, costs, precision, resident=False)
     l0 = a.kernel_launches()
     a.iterations(7)
-    assert a.kernel_launches() - l0 == 1, "iterations(n) of an eligible solver is one cooperative launch (plus nothing else)"
+    assert a.kernel_launches() - l0 <= 2, "iterations(n) of an eligible solver is one cooperative launch (plus the hand-over of the pending sums)"
+    l1 = a.kernel_launches()
+    a.iterations(2)
+    assert a.kernel_launches() - l1 == 1
+    b.iterations(2)
     for _ in range(7):
         b.forward_pass(0.5)
         b.backward_pass(0.5)
