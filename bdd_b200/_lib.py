@@ -22,7 +22,7 @@ SYMBOLS = [
     "bddb200_backward_pass", "bddb200_forward_mm", "bddb200_backward_mm", "bddb200_normalize_delta",
     "bddb200_get_delta", "bddb200_lower_bound", "bddb200_lower_bound_per_bdd", "bddb200_forward_run",
     "bddb200_backward_run", "bddb200_flush_forward_states", "bddb200_flush_backward_states",
-    "bddb200_update_costs_host", "bddb200_update_costs_host_real", "bddb200_update_costs_dev", "bddb200_set_cost", "bddb200_distribute_delta",
+    "bddb200_update_costs_host", "bddb200_update_costs_host_real", "bddb200_update_costs_dev", "bddb200_step_host", "bddb200_set_cost", "bddb200_distribute_delta",
     "bddb200_get_solver_costs", "bddb200_set_solver_costs", "bddb200_primal_objective_host",
     "bddb200_min_marginals", "bddb200_bdds_solution", "bddb200_net_solver_costs", "bddb200_make_dual_feasible",
     "bddb200_gradient_step", "bddb200_synchronize", "bddb200_stream", "bddb200_kernel_launches",
@@ -95,6 +95,7 @@ def load() -> C.CDLL:
         "bddb200_update_costs_host": (i, [vp, vp, sz, vp, sz]),
         "bddb200_update_costs_dev": (i, [vp, vp, sz, vp, sz]),
         "bddb200_update_costs_host_real": (i, [vp, vp, sz, vp, sz]),
+        "bddb200_step_host": (i, [vp, vp, sz, vp, sz, i, dbl, C.POINTER(dbl)]),
         "bddb200_set_cost": (i, [vp, dbl, sz]),
         "bddb200_distribute_delta": (i, [vp]),
         "bddb200_get_solver_costs": (i, [vp, vp, vp, vp]),

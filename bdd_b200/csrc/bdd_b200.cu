@@ -15,6 +15,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "kernels.cuh"
@@ -85,6 +86,7 @@ struct bddb200_solver {
     virtual void update_costs_host(const double* lo, size_t n_lo, const double* hi, size_t n_hi) = 0;
     virtual void update_costs_host_real(const void* lo, size_t n_lo, const void* hi, size_t n_hi) = 0;
     virtual void update_costs_dev(const void* lo, size_t n_lo, const void* hi, size_t n_hi) = 0;
+    virtual double step_host(const void* lo, size_t n_lo, const void* hi, size_t n_hi, int src_is_real, double omega) = 0;
     virtual void set_cost(double c, size_t var) = 0;
     virtual void distribute_delta() = 0;
     virtual void get_solver_costs(void* lo, void* hi, void* mmd) const = 0;
@@ -142,7 +144,10 @@ public:
         if(const char* e = std::getenv("BDDB200_LANES_PER_BDD")) lanes_per_bdd = std::atoi(e);
         bool lane_class = true;       // BDDB200_NO_LANE=1: run narrow one-lane-per-BDD bundles through the generic kernel (A/B checks)
         if(const char* e = std::getenv("BDDB200_NO_LANE")) lane_class = std::atoi(e) == 0;
-        HostLayout L = build_layout(instrs, n_instr, delims, n_bdds, lanes_per_bdd, opt.nr_variables, sizeof(REAL), stage_budget, lane_class);
+        CUDA_CHECK(cudaDeviceGetAttribute(&n_sms_, cudaDevAttrMultiProcessorCount, device));
+        size_t balance_sms = 0;      // BDDB200_BALANCE=1: bundle count a multiple of the SM count, BDDs dealt evenly (measured neutral on B200: the exchange is bound chip-wide, not per SM)
+        if(const char* e = std::getenv("BDDB200_BALANCE")) if(std::atoi(e) != 0) balance_sms = (size_t)n_sms_;
+        HostLayout L = build_layout(instrs, n_instr, delims, n_bdds, lanes_per_bdd, opt.nr_variables, sizeof(REAL), stage_budget, lane_class, balance_sms);
         n_lane_ = L.n_lane_bundles; lane_max_J_ = L.lane_max_J; lane_max_hops_ = L.lane_max_hops;
         {   // runs of lane-class bundles with equal (J, n_hops): arithmetic progressions in every array (layout.hpp emits them back to back)
             bool ok = std::getenv("BDDB200_NO_CLASS_DESC") == nullptr;
@@ -301,6 +306,7 @@ public:
     {
         cudaSetDevice(device);
         if(graph_exec_) cudaGraphExecDestroy(graph_exec_);
+        for(StepGraph& c : step_graphs_) cudaGraphExecDestroy(c.exec);
         if(h_lb_) cudaFreeHost(h_lb_);
         if(h_lb_part_) cudaFreeHost(h_lb_part_);
         if(h_round_counts_) cudaFreeHost(h_round_counts_);
@@ -468,7 +474,10 @@ public:
     void plan_resident()
     {
         res_ok_ = false;
-        if(std::getenv("BDDB200_NO_RESIDENT") != nullptr && std::atoi(std::getenv("BDDB200_NO_RESIDENT")) != 0) return;
+        // Opt-in (BDDB200_RESIDENT=1): on B200 the exchange of the per-variable sums bounds a pass of such collections -- two scattered
+        // L2 accesses per layer entry, whichever way they are made -- and the streaming kernels are already at that bound
+        // (profiles/r02_*), so keeping the state on chip buys nothing there; the kernel is kept for its bit-reproducible sums.
+        if(std::getenv("BDDB200_RESIDENT") == nullptr || std::atoi(std::getenv("BDDB200_RESIDENT")) == 0) return;
         if(n_lane_ == 0 || n_lane_ != n_bundles_ || n_lane_ > (size_t)n_sms_ * 16 || n_vars_ >= ((size_t)1 << 26)) return;
         res_grid_ = (unsigned)std::min<size_t>(n_lane_, (size_t)n_sms_);
         res_wpc_ = (unsigned)((n_lane_ + res_grid_ - 1) / res_grid_);
@@ -764,12 +773,16 @@ public:
     void set_delta_buffers(void* b0, void* b1, void* b2) override
     {
         if(graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
+        for(StepGraph& c : step_graphs_) cudaGraphExecDestroy(c.exec);
+        step_graphs_.clear();
         ext_delta_[0] = static_cast<REAL*>(b0); ext_delta_[1] = static_cast<REAL*>(b1); ext_delta_[2] = static_cast<REAL*>(b2);
     }
     void set_delta_input(void* in, size_t n_shared_vars) override
     {
         if(n_shared_vars > n_vars_) throw api_error(BDDB200_ERR_INVALID_ARGUMENT, "more shared variables than variables");
         if(graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
+        for(StepGraph& c : step_graphs_) cudaGraphExecDestroy(c.exec);
+        step_graphs_.clear();
         delta_in_override_ = static_cast<REAL*>(in);
         n_shared_vars_ = in ? n_shared_vars : 0;
         if(in && d_delta_tmp2_.n == 0) d_delta_tmp2_.alloc(2 * n_vars_);
@@ -873,8 +886,16 @@ public:
             CUDA_CHECK(cudaEventCreateWithFlags(&stage_free_, cudaEventDisableTiming));
         }
         else CUDA_CHECK(cudaEventSynchronize(stage_free_));     // previous upload has left the staging buffer
-        for(size_t i = 0; i < n_lo; ++i) h_stage_[i] = (REAL)lo[i];          // device_vector<REAL>(cost_begin, cost_end), bdd_cuda_base.cu:485
-        for(size_t i = 0; i < n_hi; ++i) h_stage_[n_lo + i] = (REAL)hi[i];
+        if(std::is_same<SRC, REAL>::value)
+        {
+            if(n_lo) std::memcpy(h_stage_, lo, n_lo * sizeof(REAL));
+            if(n_hi) std::memcpy(h_stage_ + n_lo, hi, n_hi * sizeof(REAL));
+        }
+        else
+        {
+            for(size_t i = 0; i < n_lo; ++i) h_stage_[i] = (REAL)lo[i];          // device_vector<REAL>(cost_begin, cost_end), bdd_cuda_base.cu:485
+            for(size_t i = 0; i < n_hi; ++i) h_stage_[n_lo + i] = (REAL)hi[i];
+        }
         CUDA_CHECK(cudaMemcpyAsync(d_stage_.p, h_stage_, sizeof(REAL) * (n_lo + n_hi), cudaMemcpyHostToDevice, stream_));
         CUDA_CHECK(cudaEventRecord(stage_free_, stream_));
         update_costs_lohi_kernel<REAL><<<blocks_for(n_lay_), 256, 0, stream_>>>(d_lay_vn_.p, d_lohi_[cc_].p, d_stage_.p, (uint32_t)n_lo, (uint32_t)n_hi, (uint32_t)n_lay_);
@@ -895,6 +916,110 @@ public:
         CUDA_CHECK(cudaGetLastError());
         flush_forward(); flush_backward();
     }
+    // One solver step of a host-driven loop in ONE call: update_costs(lo, hi) from host vectors, iteration(omega), lower_bound()
+    // (what the perturbation rounds of bdd_solver.cpp:318-380 and run_solver, run_solver_util.h:37-49, do per step).  Vectors of REAL
+    // in pinned memory are read by the copy engine straight from the caller's buffers (anything else goes through the pinned staging
+    // buffer); upload, cost update, the plain backward sweep the changed costs call for, both MMA sweeps and the read-back of the
+    // bound are ONE CUDA graph launch (one graph per host buffer and rotation state, cached).  The call returns after the bound has
+    // come back, so the caller's buffers are free again.
+    double step_host(const void* lo, size_t n_lo, const void* hi, size_t n_hi, int src_is_real, double omega) override
+    {
+        set_device();
+        if(n_lo > n_vars_ || n_hi > n_vars_) throw api_error(BDDB200_ERR_INVALID_ARGUMENT, "more costs than variables");
+        if(use_resident() || deterministic_)
+        {   // these forms have their own launch structure: plain sequence
+            if(src_is_real) update_costs_host_real(lo, n_lo, hi, n_hi); else update_costs_host(static_cast<const double*>(lo), n_lo, static_cast<const double*>(hi), n_hi);
+            iteration(omega);
+            return lower_bound();
+        }
+        // where the upload reads from: the caller's own memory when it is pinned REAL data, else the pinned staging buffer
+        const void* src_lo = lo; const void* src_hi = hi;
+        if(n_lo + n_hi > 0)
+        {
+            if(h_stage_ == nullptr)
+            {
+                CUDA_CHECK(cudaMallocHost(&h_stage_, sizeof(REAL) * 2 * std::max<size_t>(n_vars_, 1)));
+                d_stage_.alloc(2 * n_vars_);
+                CUDA_CHECK(cudaEventCreateWithFlags(&stage_free_, cudaEventDisableTiming));
+            }
+            auto pinned = [](const void* p) {
+                if(p == nullptr) return true;
+                cudaPointerAttributes at{};
+                if(cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+                return at.type == cudaMemoryTypeHost;
+            };
+            if(!(src_is_real && pinned(n_lo ? lo : nullptr) && pinned(n_hi ? hi : nullptr)))
+            {   // the previous step has been waited for, so the staging buffer is free
+                if(src_is_real)
+                {
+                    if(n_lo) std::memcpy(h_stage_, lo, n_lo * sizeof(REAL));
+                    if(n_hi) std::memcpy(h_stage_ + n_lo, hi, n_hi * sizeof(REAL));
+                }
+                else
+                {
+                    const double* l = static_cast<const double*>(lo); const double* h = static_cast<const double*>(hi);
+                    for(size_t i = 0; i < n_lo; ++i) h_stage_[i] = (REAL)l[i];
+                    for(size_t i = 0; i < n_hi; ++i) h_stage_[n_lo + i] = (REAL)h[i];
+                }
+                src_lo = h_stage_; src_hi = h_stage_ + n_lo;
+            }
+        }
+        ensure_sums();
+        StepKey key{dcur_, cc_, delta_needs_norm_, omega, n_lo, n_hi, n_lo ? src_lo : nullptr, n_hi ? src_hi : nullptr};
+        StepGraph* g = nullptr;
+        for(StepGraph& c : step_graphs_) if(c.key == key) g = &c;
+        if(g == nullptr)
+        {
+            if(step_graphs_.size() >= 24) { for(StepGraph& c : step_graphs_) cudaGraphExecDestroy(c.exec); step_graphs_.clear(); }
+            cudaGraph_t graph = nullptr;
+            const size_t launches_before = launches_;
+            const int dcur0 = dcur_, cc0 = cc_; const bool norm0 = delta_needs_norm_;
+            lb_sum_clean_ = false;           // the captured backward sweep clears the partial sums itself, whatever ran before a replay
+            CUDA_CHECK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+            if(n_lo + n_hi > 0)
+            {   // one copy when the two vectors are adjacent in host memory
+                if(n_lo && n_hi && static_cast<const REAL*>(src_lo) + n_lo == static_cast<const REAL*>(src_hi))
+                    CUDA_CHECK(cudaMemcpyAsync(d_stage_.p, src_lo, sizeof(REAL) * (n_lo + n_hi), cudaMemcpyHostToDevice, stream_));
+                else
+                {
+                    if(n_lo) CUDA_CHECK(cudaMemcpyAsync(d_stage_.p, src_lo, sizeof(REAL) * n_lo, cudaMemcpyHostToDevice, stream_));
+                    if(n_hi) CUDA_CHECK(cudaMemcpyAsync(d_stage_.p + n_lo, src_hi, sizeof(REAL) * n_hi, cudaMemcpyHostToDevice, stream_));
+                }
+            }
+            step_body(n_lo, n_hi, omega);
+            CUDA_CHECK(cudaStreamEndCapture(stream_, &graph));
+            StepGraph ng; ng.key = key; ng.launches = launches_ - launches_before;
+            launches_ = launches_before;
+            CUDA_CHECK(cudaGraphInstantiate(&ng.exec, graph, 0));
+            cudaGraphDestroy(graph);
+            step_graphs_.push_back(ng);
+            g = &step_graphs_.back();
+            dcur_ = dcur0; cc_ = cc0; delta_needs_norm_ = norm0;      // the capture only recorded the step
+        }
+        CUDA_CHECK(cudaGraphLaunch(g->exec, stream_));
+        launches_ += g->launches;
+        dcur_ = (dcur_ + 2) % 3; delta_needs_norm_ = true;          // two passes; the cost buffers swap twice
+        forward_valid_ = false; backward_valid_ = true; lb_sum_clean_ = false; lb_from_resident_ = false;
+        CUDA_CHECK(cudaStreamSynchronize(stream_));
+        lb_ = 0.0;
+        for(int i = 0; i < LB_SLOTS; ++i) lb_ += h_lb_[i];
+        lb_valid_ = true;
+        return lb_;
+    }
+    // what step_host captures (host state changes as in the separate calls)
+    void step_body(size_t n_lo, size_t n_hi, double omega)
+    {
+        if(n_lo + n_hi > 0)
+        {
+            update_costs_lohi_kernel<REAL><<<blocks_for(n_lay_), 256, 0, stream_>>>(d_lay_vn_.p, d_lohi_[cc_].p, d_stage_.p, (uint32_t)n_lo, (uint32_t)n_hi, (uint32_t)n_lay_);
+            ++launches_;
+            flush_forward(); flush_backward();
+        }
+        forward_pass(omega);         // runs the plain backward sweep first when the costs changed
+        backward_pass(omega);
+        CUDA_CHECK(cudaMemcpyAsync(h_lb_, d_lb_partial_.p + LB_BLOCKS + 1, LB_SLOTS * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+    }
+
     void set_cost(double c, size_t var) override
     {
         set_device();
@@ -1125,6 +1250,13 @@ private:
     double lb_ = 0.0;
     mutable size_t launches_ = 0;
 
+    struct StepKey {
+        int dcur, cc; bool norm; double omega; size_t n_lo, n_hi; const void* src_lo; const void* src_hi;
+        bool operator==(const StepKey& o) const
+        { return dcur == o.dcur && cc == o.cc && norm == o.norm && omega == o.omega && n_lo == o.n_lo && n_hi == o.n_hi && src_lo == o.src_lo && src_hi == o.src_hi; }
+    };
+    struct StepGraph { StepKey key; cudaGraphExec_t exec = nullptr; size_t launches = 0; };
+    std::vector<StepGraph> step_graphs_;      // step_host: one graph per rotation state of the sum buffers
     cudaGraphExec_t graph_exec_ = nullptr;
     double graph_omega_ = 0.0;
     int graph_dcur_ = 0, graph_cc_ = 0;
@@ -1236,6 +1368,12 @@ int bddb200_update_costs_host_real(bddb200_solver* s, const void* lo, size_t n_l
 { REQUIRE_SOLVER(s); return guarded([&] { s->update_costs_host_real(lo, n_lo, hi, n_hi); }); }
 int bddb200_update_costs_dev(bddb200_solver* s, const void* lo, size_t n_lo, const void* hi, size_t n_hi)
 { REQUIRE_SOLVER(s); return guarded([&] { s->update_costs_dev(lo, n_lo, hi, n_hi); }); }
+int bddb200_step_host(bddb200_solver* s, const void* lo, size_t n_lo, const void* hi, size_t n_hi, int src_is_real, double omega, double* lb_out)
+{
+    REQUIRE_SOLVER(s);
+    if(lb_out == nullptr) { g_last_error = "null argument"; return BDDB200_ERR_INVALID_ARGUMENT; }
+    return guarded([&] { *lb_out = s->step_host(lo, n_lo, hi, n_hi, src_is_real, omega); });
+}
 int bddb200_set_cost(bddb200_solver* s, double c, size_t var) { REQUIRE_SOLVER(s); return guarded([&] { s->set_cost(c, var); }); }
 int bddb200_distribute_delta(bddb200_solver* s) { REQUIRE_SOLVER(s); return guarded([&] { s->distribute_delta(); }); }
 int bddb200_get_solver_costs(const bddb200_solver* s, void* lo, void* hi, void* mmd) { REQUIRE_SOLVER(s); return guarded([&] { s->get_solver_costs(lo, hi, mmd); }); }

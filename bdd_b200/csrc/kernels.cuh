@@ -792,6 +792,13 @@ template<> __device__ __forceinline__ double lds_real<double>(uint32_t addr) { d
 // tools/microbench/issue_cost.cu)
 __device__ __forceinline__ void cp_async_gather_if(bool p, float2* dst, const float* src)
 {
+#ifndef BDDB200_GATHER4X2
+    // one 8-byte copy: the exchange of the per-variable sums is bound by the number of L2 requests, not by the issue cost
+    // (profiles/r02_exchange_bound.md; two 4-byte copies block the issuing warp for less time but are two requests)
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q cp.async.ca.shared.global [%1], [%2], 8; }"
+                 :: "r"((uint32_t)p), "r"(smem_u32(dst)), "l"(__cvta_generic_to_global(src)) : "memory");
+    return;
+#endif
     asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0;\n"
                  "@q cp.async.ca.shared.global [%1], [%2], 4;\n"
                  "@q cp.async.ca.shared.global [%1+4], [%2+4], 4; }"
@@ -918,6 +925,22 @@ __device__ __forceinline__ void sweep_lane_bundle(const SweepArgs<REAL>& a, cons
     }
     int32_t bdd_index = -1;
     if(!FORWARD) bdd_index = a.bundle_bdd[d.bdd_base + lane];          // consumed after the last hop
+#ifndef BDDB200_NO_PREFETCH_SUMS
+    if(MODE == MODE_MMA && a.n_zero * (uint32_t)sizeof(REAL) <= (4u << 20))
+    {   // the per-variable sum buffers are small and accessed at random (8-byte gathers, 4-byte reductions): when they are not in
+        // L2 (first pass after other work evicted them) every such access is a DRAM sector read.  Every warp asks L2 for its
+        // share of both buffers with coalesced prefetches before anything else (a hint: needs no ordering with the previous pass).
+        // +4 % on the flushed 1 M-node pass; buffers beyond 4 MB are left alone (no gain measured on the 5 M / 20 M-node instances).
+        const uint32_t lines = (a.n_zero * (uint32_t)sizeof(REAL) + 127u) / 128u;
+        const uint32_t per = (lines + a.bundle_count - 1) / a.bundle_count;
+        const uint32_t l0 = min(lines, bundle_in_launch * per), l1 = min(lines, l0 + per);
+        for(uint32_t l = l0 + lane; l < l1; l += 32)
+        {
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const char*>(a.delta_in) + (size_t)l * 128));
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const char*>(a.delta_out) + (size_t)l * 128));
+        }
+    }
+#endif
     stamp();       // 3: variable loads issued
     pdl_wait();
     pdl_launch_dependents();

@@ -172,7 +172,7 @@ constexpr size_t DEFAULT_STAGE_BUDGET = 12 * 1024;   // bytes of one pipeline st
 inline HostLayout build_layout(const bddb200_instruction* instrs, size_t n_instr,
                                const size_t* delims, size_t n_bdds, int lanes_per_bdd,
                                size_t nr_variables_override = 0, size_t real_bytes = 4,
-                               size_t stage_budget = DEFAULT_STAGE_BUDGET, bool lane_class = true)
+                               size_t stage_budget = DEFAULT_STAGE_BUDGET, bool lane_class = true, size_t n_sms = 0)
 {
     constexpr size_t TOPSINK = (size_t)-1, BOTSINK = (size_t)-1 - 1;
     if(n_bdds == 0) throw layout_error(BDDB200_ERR_INVALID_ARGUMENT, "empty BDD collection");
@@ -352,16 +352,45 @@ inline HostLayout build_layout(const bddb200_instruction* instrs, size_t n_instr
     });
 
     // ---- lane-class bundles: up to 32 BDDs of the same width ----------------------------
+    // A pass over a collection of at most one wave of warps is bound by the scattered per-variable accesses, whose cost is per
+    // lane and per SM (tools/microbench/scatter_cost2.cu): the slowest SM is the one with the most BDDs.  With the SM count known
+    // (n_sms > 0) and at most 16 bundles per SM the bundles are made a multiple of the SM count and the BDDs dealt evenly over
+    // them (bundles of fewer than 32 lanes), so that every SM gets the same number of warps AND of BDDs.
     struct LaneProto { uint32_t first, count, J, n_hops; };
     std::vector<LaneProto> lane_protos;
-    for(size_t pos = 0; pos < lane_order.size();)
     {
-        const uint32_t Jb = bdd_maxw[lane_order[pos]];
-        size_t end = pos;
-        uint32_t nh = 0;
-        while(end < lane_order.size() && end - pos < 32 && bdd_maxw[lane_order[end]] == Jb) { nh = std::max(nh, nlay(lane_order[end])); ++end; }
-        lane_protos.push_back(LaneProto{(uint32_t)pos, (uint32_t)(end - pos), Jb, nh});
-        pos = end;
+        struct WidthClass { size_t first, count, bundles; };
+        std::vector<WidthClass> wc;
+        for(size_t pos = 0; pos < lane_order.size();)
+        {
+            size_t end = pos;
+            while(end < lane_order.size() && bdd_maxw[lane_order[end]] == bdd_maxw[lane_order[pos]]) ++end;
+            wc.push_back(WidthClass{pos, end - pos, (end - pos + 31) / 32});
+            pos = end;
+        }
+        size_t total = 0;
+        for(const WidthClass& c : wc) total += c.bundles;
+        if(n_sms > 0 && order.empty() && total > n_sms && total <= 16 * n_sms && total % n_sms != 0)
+        {
+            size_t extra = (total + n_sms - 1) / n_sms * n_sms - total;
+            const size_t n_all = lane_order.size();
+            size_t given = 0;
+            for(WidthClass& c : wc) { const size_t add = extra * c.count / n_all; c.bundles += add; given += add; }
+            for(size_t k = 0; given < extra; ++k, ++given) wc[k % wc.size()].bundles += 1;      // rounding leftovers
+            for(WidthClass& c : wc) c.bundles = std::min(c.bundles, c.count);
+        }
+        for(const WidthClass& c : wc)
+        {
+            size_t pos = c.first;
+            for(size_t i = 0; i < c.bundles; ++i)
+            {
+                const size_t cnt = c.count / c.bundles + (i < c.count % c.bundles ? 1 : 0);
+                uint32_t nh = 0;
+                for(size_t q = pos; q < pos + cnt; ++q) nh = std::max(nh, nlay(lane_order[q]));
+                lane_protos.push_back(LaneProto{(uint32_t)pos, (uint32_t)cnt, bdd_maxw[lane_order[pos]], nh});
+                pos += cnt;
+            }
+        }
     }
     std::stable_sort(lane_protos.begin(), lane_protos.end(), [](const LaneProto& x, const LaneProto& y) { return x.n_hops * x.J > y.n_hops * y.J; });
 

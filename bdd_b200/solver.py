@@ -243,6 +243,29 @@ class bdd_cuda_parallel_mma:
         nhi = 0 if hi is None else hi.size
         check(fn(self.h, lo.ctypes.data if nlo else None, nlo, hi.ctypes.data if nhi else None, nhi))
 
+    def step(self, cost_delta_0, cost_delta_1, omega: float = 0.5) -> float:
+        """update_costs(lo, hi) from host arrays + iteration(omega) + lower_bound() in one library call (bddb200_step_host): one
+        upload straight from the arrays (DMA when they are pinned, e.g. views of ``torch.empty(..., pin_memory=True)``), one CUDA
+        graph launch, one read-back.  Arrays of the solver's REAL type go as they are, anything else is converted to double."""
+        def as_host(x):
+            if x is None:
+                return None
+            if isinstance(x, np.ndarray) and x.dtype == self.np_type and x.flags.c_contiguous:
+                return x
+            return np.ascontiguousarray(x, dtype=np.float64)
+        lo, hi = as_host(cost_delta_0), as_host(cost_delta_1)
+        real = [a.dtype == self.np_type for a in (lo, hi) if a is not None and a.size]
+        is_real = bool(real) and all(real)
+        if not is_real:
+            lo = None if lo is None else np.ascontiguousarray(lo, dtype=np.float64)
+            hi = None if hi is None else np.ascontiguousarray(hi, dtype=np.float64)
+        nlo = 0 if lo is None else lo.size
+        nhi = 0 if hi is None else hi.size
+        out = C.c_double()
+        check(self.lib.bddb200_step_host(self.h, lo.ctypes.data if nlo else None, nlo, hi.ctypes.data if nhi else None, nhi,
+                                         int(is_real), omega, C.byref(out)))
+        return out.value
+
     def set_cost(self, c: float, var: int):
         check(self.lib.bddb200_set_cost(self.h, c, var))
 

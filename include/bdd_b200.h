@@ -146,6 +146,11 @@ int bddb200_update_costs_host(bddb200_solver* s, const double* lo_host, size_t n
  * without waiting for the device; the caller's arrays may be reused immediately. */
 int bddb200_update_costs_host_real(bddb200_solver* s, const void* lo_host, size_t n_lo, const void* hi_host, size_t n_hi);
 int bddb200_update_costs_dev(bddb200_solver* s, const void* lo_dev, size_t n_lo, const void* hi_dev, size_t n_hi);
+/* One step of a host-driven loop in one call: update_costs(lo, hi) from host vectors (of REAL when src_is_real != 0, else of double),
+ * iteration(omega), lower_bound() -- what a perturbation round of bdd_solver.cpp:318-380 / one turn of run_solver
+ * (run_solver_util.h:37-49) does with three calls.  REAL vectors are copied straight from the caller's memory (DMA when it is pinned);
+ * everything after the upload is one CUDA graph launch.  Returns after the bound has arrived: the caller's arrays are free again. */
+int bddb200_step_host(bddb200_solver* s, const void* lo_host, size_t n_lo, const void* hi_host, size_t n_hi, int src_is_real, double omega, double* lb_out);
 int bddb200_set_cost(bddb200_solver* s, double c, size_t var);      /* :439-452 */
 /* distribute_delta (bdd_cuda_base.cu:1396-1436) */
 int bddb200_distribute_delta(bddb200_solver* s);

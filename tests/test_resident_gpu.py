@@ -1,6 +1,6 @@
 """The on-chip ("resident") iteration kernel (bdd_b200/csrc/resident.cuh) against the streaming per-pass kernels and the CPU
-oracle.  iteration() / iterations(n) of a non-deterministic solver whose bundles are all lane class and fit one wave run as ONE
-cooperative launch; forward_pass() / backward_pass() and BDDB200_NO_RESIDENT=1 solvers use the streaming kernels."""
+oracle.  With BDDB200_RESIDENT=1, iteration() / iterations(n) of a solver whose bundles are all lane class and fit one wave run
+as ONE cooperative launch; forward_pass() / backward_pass() and all other solvers use the streaming kernels."""
 import os
 
 import numpy as np
@@ -22,15 +22,15 @@ def _gpu():
 
 def make(col, costs, precision, resident=True, **kw):
     from bdd_b200.solver import bdd_cuda_parallel_mma
-    old = os.environ.pop("BDDB200_NO_RESIDENT", None)
-    if not resident:
-        os.environ["BDDB200_NO_RESIDENT"] = "1"
+    old = os.environ.pop("BDDB200_RESIDENT", None)
+    if resident:
+        os.environ["BDDB200_RESIDENT"] = "1"
     try:
         return bdd_cuda_parallel_mma(col, costs, precision=precision, device=0, **kw)
     finally:
-        os.environ.pop("BDDB200_NO_RESIDENT", None)
+        os.environ.pop("BDDB200_RESIDENT", None)
         if old is not None:
-            os.environ["BDDB200_NO_RESIDENT"] = old
+            os.environ["BDDB200_RESIDENT"] = old
 
 
 def tol(precision, scale=1.0):
@@ -138,3 +138,35 @@ def test_full_size_set_cover_resident_vs_streaming():
     assert abs(la - lb) <= 1e-4 * abs(lb), (la, lb)
     da, db = a.get_delta().cpu().numpy(), b.get_delta().cpu().numpy()
     assert np.allclose(da, db, rtol=0, atol=1e-3 * max(1.0, np.abs(db).max()))
+
+
+@pytest.mark.parametrize("precision", ["float", "double"])
+@pytest.mark.parametrize("as_real", [True, False])
+def test_fused_host_step_equals_three_calls(precision, as_real):
+    """bddb200_step_host == update_costs(host) + iteration() + lower_bound(), step after step (graph replay included), and the
+    solver can be used with the separate calls in between."""
+    from bdd_b200 import instances
+    col, costs = instances.set_cover(m=1500, n=3000, k=10, seed=4)
+    a = make(col, costs, precision, resident=False)
+    b = make(col, costs, precision, resident=False)
+    rng = np.random.default_rng(8)
+    dt = a.np_type if as_real else np.float64
+    n = len(costs)
+    for k in range(9):
+        lo = rng.integers(0, 2, size=n).astype(dt)
+        hi = rng.integers(-2, 3, size=n).astype(dt)
+        if k == 4:                       # a plain iteration in between on both
+            a.iteration(); b.iteration()
+        la = a.step(lo, hi)
+        b.update_costs(lo, hi)
+        b.iteration()
+        lb = b.lower_bound()
+        assert abs(la - lb) <= tol(precision, lb), (k, la, lb)
+    same_state(a, b, precision)
+    # only hi costs, and no costs at all (a bare iteration + bound)
+    la = a.step(None, rng.integers(-1, 2, size=n).astype(dt) * 0 + 1.0)
+    b.update_costs(None, np.ones(n, dtype=dt)); b.iteration()
+    assert abs(la - b.lower_bound()) <= tol(precision, la)
+    la = a.step(None, None)
+    b.iteration()
+    assert abs(la - b.lower_bound()) <= tol(precision, la)
