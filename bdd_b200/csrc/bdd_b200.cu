@@ -105,6 +105,8 @@ struct bddb200_solver {
     virtual int delta_sum_index() const = 0;
     virtual void set_delta_buffers(void* b0, void* b1, void* b2) = 0;
     virtual void set_delta_input(void* in, size_t n_shared_vars) = 0;
+    virtual void set_exchange(int world, int rank, const void* const* peers, uint32_t* const* flags, void* out, void* const* outs,
+                              const void* mc_in, void* mc_out, size_t n_exchange, int mode) = 0;
     virtual size_t trace_pass(int forward, double omega, unsigned long long* out_host, size_t max_bundles) = 0;
     virtual bddb200_solver* clone() const = 0;
 };
@@ -646,6 +648,60 @@ public:
         mma_pass<true>(omega, in, delta_needs_norm_, out, zero);
         dcur_ = (dcur_ + 1) % 3; delta_needs_norm_ = true;
         forward_valid_ = true; backward_valid_ = false;
+        if(xc_.mode != 0) launch_exchange();
+    }
+
+    // ---- multi-GPU: the exchange of the shared variables' sums after every pass, issued by the library itself ----------
+    void set_exchange(int world, int rank, const void* const* peers, uint32_t* const* flags, void* out, void* const* outs,
+                      const void* mc_in, void* mc_out, size_t n_exchange, int mode) override
+    {
+        set_device();
+        if(graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
+        for(StepGraph& c : step_graphs_) cudaGraphExecDestroy(c.exec);
+        step_graphs_.clear();
+        if(mode == 0) { xc_ = Xchg{}; return; }
+        if(world < 2 || world > EXCHANGE_MAX_WORLD || rank < 0 || rank >= world || flags == nullptr || (n_exchange & 1) || n_exchange > 2 * n_vars_ || ext_delta_[0] == nullptr)
+            throw api_error(BDDB200_ERR_INVALID_ARGUMENT, "set_exchange: invalid argument (the sum buffers must be set with set_delta_buffers first)");
+        if((mode == 1 && (peers == nullptr || out == nullptr)) || (mode == 2 && (peers == nullptr || outs == nullptr)) || (mode == 3 && (mc_in == nullptr || mc_out == nullptr)) || mode < 0 || mode > 3)
+            throw api_error(BDDB200_ERR_INVALID_ARGUMENT, "set_exchange: buffers missing for the requested mode");
+        xc_.world = world; xc_.rank = rank; xc_.peers = peers; xc_.flags = flags; xc_.out = static_cast<REAL*>(out); xc_.outs = outs;
+        xc_.mc_in = static_cast<const REAL*>(mc_in); xc_.mc_out = static_cast<REAL*>(mc_out); xc_.n_exchange = n_exchange; xc_.mode = mode;
+        if(d_xc_counters_.n == 0) d_xc_counters_.alloc(8);
+        d_xc_counters_.zero(stream_);
+    }
+    void launch_exchange()
+    {
+        if(xc_.n_exchange == 0) return;
+        const size_t offset = (size_t)(dbuf(dcur_) - dbuf(0));       // the sums of the pass just made, relative to the start of the symmetric block
+        const size_t pairs = xc_.n_exchange / 2;
+        // programmatic dependent launch, like the sweeps: the exchange sets itself up under the tail of the pass and the next pass under the exchange
+        cudaLaunchConfig_t cfg{};
+        cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = stream_;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = pdl_ ? 1 : 0;
+        if(xc_.mode == 1)
+        {
+            cfg.gridDim = dim3((unsigned)std::max<size_t>(1, std::min<size_t>((pairs + 255) / 256, (size_t)n_sms_ * 4)));
+            CUDA_CHECK(cudaLaunchKernelEx(&cfg, delta_exchange_kernel<REAL>, reinterpret_cast<const REAL* const*>(xc_.peers), xc_.flags, xc_.world, xc_.rank, 0u, offset,
+                                          xc_.out, pairs, d_xc_counters_.p));
+        }
+        else if(xc_.mode == 2)
+        {
+            const size_t per = (pairs + xc_.world - 1) / xc_.world;
+            cfg.gridDim = dim3((unsigned)std::max<size_t>(1, std::min<size_t>((per + 255) / 256, (size_t)n_sms_ * 4)));
+            CUDA_CHECK(cudaLaunchKernelEx(&cfg, delta_exchange2_kernel<REAL>, reinterpret_cast<const REAL* const*>(xc_.peers), reinterpret_cast<REAL* const*>(xc_.outs), xc_.flags,
+                                          xc_.world, xc_.rank, 0u, offset, pairs, d_xc_counters_.p));
+        }
+        else
+        {
+            const size_t units = (xc_.n_exchange * sizeof(REAL) + 15) / 16, per = (units + xc_.world - 1) / xc_.world;
+            cfg.gridDim = dim3((unsigned)std::max<size_t>(1, std::min<size_t>((per + 255) / 256, (size_t)n_sms_ * 2)));
+            CUDA_CHECK(cudaLaunchKernelEx(&cfg, delta_exchange_mc_kernel<REAL>, xc_.mc_in, (REAL*)xc_.mc_out, xc_.flags, xc_.world, xc_.rank, offset, xc_.n_exchange, d_xc_counters_.p));
+        }
+        ++launches_;
+        CUDA_CHECK(cudaGetLastError());
     }
 
     void backward_pass(double omega) override
@@ -658,6 +714,7 @@ public:
         mma_pass<false>(omega, in, delta_needs_norm_, out, zero);
         dcur_ = (dcur_ + 1) % 3; delta_needs_norm_ = true;
         forward_valid_ = false; backward_valid_ = true; lb_valid_ = false;
+        if(xc_.mode != 0) launch_exchange();
     }
 
     void iteration(double omega) override
@@ -1187,6 +1244,12 @@ private:
     void set_device() const { CUDA_CHECK(cudaSetDevice(device)); }
     REAL* dbuf(int i) const { return ext_delta_[i] ? ext_delta_[i] : d_delta_[i].p; }
     REAL* ext_delta_[3] = {nullptr, nullptr, nullptr};
+    struct Xchg {
+        int world = 0, rank = 0, mode = 0;         // mode: 0 off, 1 one-shot, 2 two-shot, 3 in-switch (multicast)
+        const void* const* peers = nullptr; uint32_t* const* flags = nullptr; void* const* outs = nullptr;
+        REAL* out = nullptr; const REAL* mc_in = nullptr; REAL* mc_out = nullptr; size_t n_exchange = 0;
+    } xc_;
+    DevBuf<uint32_t> d_xc_counters_;         // {exchanges completed, CTAs finished}: the device-side epoch of the exchange kernels
     REAL* delta_in_override_ = nullptr;      // exchanged sums of the variables [0, n_shared_vars_)
     size_t n_shared_vars_ = 0;
     DevBuf<REAL> d_delta_tmp2_;
@@ -1488,6 +1551,10 @@ int bddb200_set_delta_buffers(bddb200_solver* s, void* b0, void* b1, void* b2)
 }
 int bddb200_set_delta_input(bddb200_solver* s, void* in, size_t n_shared_vars) { REQUIRE_SOLVER(s); return guarded([&] { s->set_delta_input(in, n_shared_vars); }); }
 
+int bddb200_set_exchange(bddb200_solver* s, int world, int rank, const void* const* peer_bufs_dev, uint32_t* const* flags_dev, void* out_dev,
+                         void* const* peer_outs_dev, const void* mc_in, void* mc_out, size_t n_exchange, int mode)
+{ REQUIRE_SOLVER(s); return guarded([&] { s->set_exchange(world, rank, peer_bufs_dev, flags_dev, out_dev, peer_outs_dev, mc_in, mc_out, n_exchange, mode); }); }
+
 int bddb200_delta_exchange(void* stream, int precision, int world, int rank, const void* const* peer_bufs_dev, uint32_t* const* flags_dev,
                            uint32_t epoch, size_t offset_elems, void* out_dev, size_t n_exchange)
 {
@@ -1503,10 +1570,10 @@ int bddb200_delta_exchange(void* stream, int precision, int world, int rank, con
         cudaStream_t st = (cudaStream_t)stream;
         if(precision == BDDB200_DOUBLE)
             delta_exchange_kernel<double><<<blocks, 256, 0, st>>>(reinterpret_cast<const double* const*>(peer_bufs_dev), flags_dev, world, rank, epoch, offset_elems,
-                                                                  static_cast<double*>(out_dev), pairs);
+                                                                  static_cast<double*>(out_dev), pairs, nullptr);
         else
             delta_exchange_kernel<float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float* const*>(peer_bufs_dev), flags_dev, world, rank, epoch, offset_elems,
-                                                                 static_cast<float*>(out_dev), pairs);
+                                                                 static_cast<float*>(out_dev), pairs, nullptr);
         CUDA_CHECK(cudaGetLastError());
     });
 }
@@ -1525,10 +1592,10 @@ int bddb200_delta_exchange_two_shot(void* stream, int precision, int world, int 
         cudaStream_t st = (cudaStream_t)stream;
         if(precision == BDDB200_DOUBLE)
             delta_exchange2_kernel<double><<<blocks, 256, 0, st>>>(reinterpret_cast<const double* const*>(peer_bufs_dev), reinterpret_cast<double* const*>(peer_outs_dev),
-                                                                   flags_dev, world, rank, epoch, offset_elems, pairs);
+                                                                   flags_dev, world, rank, epoch, offset_elems, pairs, nullptr);
         else
             delta_exchange2_kernel<float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float* const*>(peer_bufs_dev), reinterpret_cast<float* const*>(peer_outs_dev),
-                                                                  flags_dev, world, rank, epoch, offset_elems, pairs);
+                                                                  flags_dev, world, rank, epoch, offset_elems, pairs, nullptr);
         CUDA_CHECK(cudaGetLastError());
     });
 }

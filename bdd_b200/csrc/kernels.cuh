@@ -1437,11 +1437,36 @@ constexpr int EXCHANGE_MAX_WORLD = 16;
 __device__ __forceinline__ void ld_volatile2(const float* p, float& x, float& y) { asm volatile("ld.volatile.global.v2.f32 {%0, %1}, [%2];" : "=f"(x), "=f"(y) : "l"(p)); }
 __device__ __forceinline__ void ld_volatile2(const double* p, double& x, double& y) { asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "l"(p)); }
 
+// Device-side epoch (graph replay): with `counters` non-null the epoch of this exchange is counters[0] + 1, and the last CTA of the
+// launch to finish advances counters[0] (counters[1] counts finished CTAs).  All ranks run the same sequence of exchanges, so their
+// counters agree without any host involvement, and a captured launch stays valid however often it is replayed.
+__device__ __forceinline__ uint32_t exchange_epoch(const uint32_t* counters, uint32_t epoch_arg)
+{
+    if(counters == nullptr) return epoch_arg;
+    uint32_t e;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(e) : "l"(counters) : "memory");
+    return e + 1u;
+}
+__device__ __forceinline__ void exchange_epoch_done(uint32_t* counters)
+{   // called by every thread at the end of the kernel
+    if(counters == nullptr) return;
+    __syncthreads();
+    if(threadIdx.x == 0)
+    {
+        __threadfence();
+        const uint32_t done = atomicAdd(counters + 1, 1u);
+        if(done == gridDim.x - 1) { counters[1] = 0; __threadfence(); atomicAdd(counters, 1u); }
+    }
+}
+
 template<typename REAL>
 __global__ void __launch_bounds__(256) delta_exchange_kernel(const REAL* const* __restrict__ peers, uint32_t* const* __restrict__ flags, int world, int rank,
-                                                             uint32_t epoch, size_t offset, REAL* __restrict__ out, size_t pairs)
+                                                             uint32_t epoch_arg, size_t offset, REAL* __restrict__ out, size_t pairs, uint32_t* counters)
 {
     using R2 = typename real2<REAL>::type;
+    pdl_wait();                     // launched with programmatic stream serialisation: the pass before must be complete ...
+    pdl_launch_dependents();        // ... and the next pass may set itself up while this exchange runs (it waits for its completion)
+    const uint32_t epoch = exchange_epoch(counters, epoch_arg);
     __shared__ const REAL* peer_s[EXCHANGE_MAX_WORLD];
     if((int)threadIdx.x < world)
     {
@@ -1474,6 +1499,7 @@ __global__ void __launch_bounds__(256) delta_exchange_kernel(const REAL* const* 
         R2 o; o.x = sx; o.y = sy;
         reinterpret_cast<R2*>(out)[i] = o;
     }
+    exchange_epoch_done(counters);
 }
 
 // Two-shot variant for many ranks and long prefixes (a one-shot exchange reads (world - 1) x the prefix per rank; this
@@ -1483,9 +1509,12 @@ __global__ void __launch_bounds__(256) delta_exchange_kernel(const REAL* const* 
 // be co-resident (they wait for each other): the host launches at most 4 x 256 threads per SM.
 template<typename REAL>
 __global__ void __launch_bounds__(256) delta_exchange2_kernel(const REAL* const* __restrict__ peers, REAL* const* __restrict__ outs, uint32_t* const* __restrict__ flags,
-                                                              int world, int rank, uint32_t epoch, size_t offset, size_t pairs)
+                                                              int world, int rank, uint32_t epoch_arg, size_t offset, size_t pairs, uint32_t* counters)
 {
     using R2 = typename real2<REAL>::type;
+    pdl_wait();                     // launched with programmatic stream serialisation: the pass before must be complete ...
+    pdl_launch_dependents();        // ... and the next pass may set itself up while this exchange runs (it waits for its completion)
+    const uint32_t epoch = exchange_epoch(counters, epoch_arg);
     __shared__ const REAL* peer_s[EXCHANGE_MAX_WORLD];
     __shared__ REAL* out_s[EXCHANGE_MAX_WORLD];
     __shared__ bool last_cta;
@@ -1564,6 +1593,79 @@ __global__ void __launch_bounds__(256) delta_exchange2_kernel(const REAL* const*
             reinterpret_cast<R2*>(out)[i] = o;
         }
     }
+    exchange_epoch_done(counters);
+}
+
+// In-switch variant (NVLink SHARP / NVLS): the rotating sum buffers and the result buffer are symmetric memory with a multicast
+// mapping.  After the arrival barrier every rank reduces ONE slice of the prefix with multimem.ld_reduce (the switch adds the
+// ranks' values and returns the sum: one read of the slice instead of world of them) and broadcasts it into every rank's result
+// buffer with multimem.st; a second barrier tells everyone that all slices are in place.  One rank computes each slice, so all
+// ranks see bit-identical sums.  All CTAs of the launch must be co-resident (they wait for each other).
+__device__ __forceinline__ void mc_reduce_store(const float* mc_in, float* mc_out)
+{   // 16 bytes = two {lo, hi} pairs
+    float a, b, c, d;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "l"(mc_in) : "memory");
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(mc_out), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void mc_reduce_store(const double* mc_in, double* mc_out)
+{   // 16 bytes = one {lo, hi} pair
+    double a, b;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f64 %0, [%1];" : "=d"(a) : "l"(mc_in) : "memory");
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f64 %0, [%1];" : "=d"(b) : "l"(mc_in + 1) : "memory");
+    asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" :: "l"(mc_out), "d"(a) : "memory");
+    asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" :: "l"(mc_out + 1), "d"(b) : "memory");
+}
+
+template<typename REAL>
+__global__ void __launch_bounds__(256) delta_exchange_mc_kernel(const REAL* __restrict__ mc_in, REAL* __restrict__ mc_out, uint32_t* const* __restrict__ flags,
+                                                                int world, int rank, size_t offset, size_t n_exchange, uint32_t* counters)
+{
+    pdl_wait();
+    pdl_launch_dependents();
+    const uint32_t epoch = exchange_epoch(counters, 0u);
+    __shared__ bool last_cta;
+    uint32_t* my_flags = flags[rank];
+    auto wait_all = [&](uint32_t slot0) {
+        if((int)threadIdx.x < world)
+        {
+            const uint32_t* mine = my_flags + slot0 + threadIdx.x;
+            uint32_t seen;
+            for(uint32_t spins = 0;; ++spins)
+            {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+                if((int32_t)(seen - epoch) >= 0) break;
+                if(spins > (1u << 26)) __trap();          // a peer that never arrives must not hang the GPU
+            }
+        }
+        __syncthreads();
+    };
+    if(blockIdx.x == 0 && (int)threadIdx.x < world)
+    {   // "my pass is complete" to every peer
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(flags[threadIdx.x] + rank), "r"(epoch) : "memory");
+    }
+    wait_all(0);
+    // my slice of the prefix, in 16-byte units
+    constexpr size_t PER16 = 16 / sizeof(REAL);
+    const size_t units = (n_exchange + PER16 - 1) / PER16, per = (units + world - 1) / world;
+    const size_t lo = min(units, per * (size_t)rank), hi = min(units, lo + per);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for(size_t u = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; u < hi; u += stride)
+        mc_reduce_store(mc_in + offset + u * PER16, mc_out + u * PER16);
+    // "my slice is everywhere": the last CTA of this launch to get here tells every peer
+    __threadfence_system();
+    __syncthreads();
+    if(threadIdx.x == 0)
+    {
+        const uint32_t done = atomicAdd(my_flags + 48, 1u);
+        last_cta = done == gridDim.x - 1;
+        if(last_cta) my_flags[48] = 0;
+    }
+    __syncthreads();
+    if(last_cta && (int)threadIdx.x < world)
+        asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(flags[threadIdx.x] + 16 + rank), "r"(epoch) : "memory");
+    wait_all(16);
+    exchange_epoch_done(counters);
 }
 
 // ---- primal rounding: one perturbation round of incremental_mm_agreement_rounding_cuda ---------------------------

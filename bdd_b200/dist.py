@@ -93,13 +93,17 @@ def relabel_variables(col: BddCollection, new_of_old: np.ndarray) -> BddCollecti
 
 
 class SymmExchange:
-    """Peer-memory exchange: sum buffers in symmetric memory + bddb200_delta_exchange."""
+    """Peer-memory exchange: sum buffers in symmetric memory, exchange kernels of the library issued BY the library after every
+    pass (``bddb200_set_exchange``; the flag epochs live on the device, so ``iterations(n)`` replays pass + exchange as one CUDA
+    graph).  Modes: "mc" in-switch reduction through the multicast mapping (multimem.ld_reduce / multimem.st), "1" one-shot reads of
+    every peer, "2" two-shot; "auto" = mc where the box offers multicast, else one-shot below 6 ranks and two-shot from 6."""
 
-    def __init__(self, local, n_total: int, n_exchange: int, rank: int, world: int, group=None):
+    def __init__(self, local, n_vars: int, n_exchange: int, rank: int, world: int, group=None):
         import torch.distributed._symmetric_memory as symm_mem
         from . import _lib
+        from ._lib import check
         self.lib, self.local = _lib.load(), local
-        self.rank, self.world, self.n_total, self.n_exchange = rank, world, n_total, n_exchange
+        self.rank, self.world, self.n_exchange = rank, world, n_exchange
         self.precision = _lib.DOUBLE if local.precision == "double" else _lib.FLOAT
         grp = group if group is not None else dist.group.WORLD
         try:
@@ -107,40 +111,56 @@ class SymmExchange:
         except Exception:
             pass
         dev = local.device
-        self.block = symm_mem.empty(3 * n_total, dtype=local.value_type, device=dev)
+        # every sum buffer starts on a 16-byte boundary (the in-switch reduction moves 16-byte units)
+        self.stride = (2 * n_vars + 3) // 4 * 4
+        self.n_total = self.stride
+        n_out = max((n_exchange + 3) // 4 * 4, 4)
+        self.block = symm_mem.empty(3 * self.stride, dtype=local.value_type, device=dev)
         self.block.zero_()
         self.flags = symm_mem.empty(64, dtype=torch.int32, device=dev)
         self.flags.zero_()
         self.h_block = symm_mem.rendezvous(self.block, grp)
         self.h_flags = symm_mem.rendezvous(self.flags, grp)
-        # one-shot reads (world - 1) x the prefix per rank, two-shot 2 (world - 1) / world of it at the price of a second barrier
         mode = os.environ.get("BDDB200_EXCHANGE_SHOTS", "auto")
-        self.two_shot = mode == "2" or (mode == "auto" and world >= 6 and n_exchange >= (1 << 17))
-        if self.two_shot:
-            self.out = symm_mem.empty(max(n_exchange, 2), dtype=local.value_type, device=dev)
+        mc_in = int(getattr(self.h_block, "multicast_ptr", 0) or 0)
+        has_mc = mc_in != 0
+        if mode == "mc" and not has_mc:
+            raise RuntimeError("BDDB200_EXCHANGE_SHOTS=mc: this box offers no multicast mapping of symmetric memory")
+        if mode == "auto":
+            # measured on 2 and 4 x B200 (profiles/r02_multi_gpu.md): one flag barrier + direct reads beat the two barriers of the
+            # in-switch and two-shot forms while (world - 1) x prefix stays small; from 6 ranks on the slice-wise forms read less
+            many = world >= 6 and n_exchange >= (1 << 17)
+            mode = ("mc" if has_mc else "2") if many else "1"
+        # the result buffer: plain device memory for the one-shot form (every pass gathers from it), symmetric for the others
+        mc_out, self.h_out = 0, None
+        if mode == "1":
+            self.out = torch.zeros(n_out, dtype=local.value_type, device=dev)
+        else:
+            self.out = symm_mem.empty(n_out, dtype=local.value_type, device=dev)
             self.out.zero_()
             self.h_out = symm_mem.rendezvous(self.out, grp)
-        else:
-            self.out = torch.zeros(max(n_exchange, 2), dtype=local.value_type, device=dev)
+            mc_out = int(getattr(self.h_out, "multicast_ptr", 0) or 0)
+            if mode == "mc" and mc_out == 0:
+                raise RuntimeError("no multicast mapping for the result buffer")
+        self.mode = {"1": 1, "2": 2, "mc": 3}[mode]
+        self.two_shot = self.mode == 2
         torch.cuda.synchronize(dev)
         dist.barrier(group=group)
-        local.set_delta_buffers(self.block)
+        item = self.block.element_size()
+        check(self.lib.bddb200_set_delta_buffers(local.h, self.block.data_ptr(), self.block.data_ptr() + self.stride * item,
+                                                 self.block.data_ptr() + 2 * self.stride * item))
+        local._delta_block = self.block
         local.set_delta_input(self.out, n_exchange // 2)
-        self.epoch = 0
-        self.itemsize = self.block.element_size()
+        check(self.lib.bddb200_set_exchange(local.h, world, rank, self.h_block.buffer_ptrs_dev, self.h_flags.buffer_ptrs_dev, self.out.data_ptr(),
+                                            self.h_out.buffer_ptrs_dev if self.h_out is not None else None,
+                                            mc_in if self.mode == 3 else None, mc_out if self.mode == 3 else None, n_exchange, self.mode))
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=group)
+
+    name = property(lambda self: {1: "symm one-shot", 2: "symm two-shot", 3: "symm in-switch (multimem)"}[self.mode])
 
     def __call__(self):
-        from ._lib import check
-        self.epoch += 1
-        idx = self.local.delta_sum_index()
-        if self.two_shot:
-            check(self.lib.bddb200_delta_exchange_two_shot(self.local.stream.cuda_stream, self.precision, self.world, self.rank,
-                                                           self.h_block.buffer_ptrs_dev, self.h_out.buffer_ptrs_dev, self.h_flags.buffer_ptrs_dev,
-                                                           self.epoch & 0xFFFFFFFF, idx * self.n_total, self.n_exchange))
-            return
-        check(self.lib.bddb200_delta_exchange(self.local.stream.cuda_stream, self.precision, self.world, self.rank,
-                                              self.h_block.buffer_ptrs_dev, self.h_flags.buffer_ptrs_dev, self.epoch & 0xFFFFFFFF,
-                                              idx * self.n_total, self.out.data_ptr(), self.n_exchange))
+        """Nothing to do: forward_pass / backward_pass of the local solver end with the exchange."""
 
     def sums(self) -> torch.Tensor:
         return self.out
@@ -179,7 +199,7 @@ class sharded_mma:
         if want in ("auto", "symm") and is_cuda_local:
             ok = torch.ones(1, device=self.local.device)
             try:
-                self.symm = SymmExchange(self.local, 2 * self.nr_vars, self.n_exchange, rank, world, group)
+                self.symm = SymmExchange(self.local, self.nr_vars, self.n_exchange, rank, world, group)
             except Exception as e:          # no symmetric-memory support on this box: every rank must fall back together
                 if want == "symm":
                     raise
@@ -188,10 +208,11 @@ class sharded_mma:
             dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
             if ok.item() == 0 and self.symm is not None:
                 from ._lib import check
+                check(self.local.lib.bddb200_set_exchange(self.local.h, 0, 0, None, None, None, None, None, None, 0, 0))
                 check(self.local.lib.bddb200_set_delta_buffers(self.local.h, None, None, None))
                 self.local.set_delta_input(None, 0)
                 self.symm = None
-        self.exchange = ("symm two-shot" if self.symm.two_shot else "symm") if self.symm is not None else ("all_reduce" if world > 1 else "none")
+        self.exchange = self.symm.name if self.symm is not None else ("all_reduce" if world > 1 else "none")
 
     def _allreduce(self, t: torch.Tensor):
         if self.world <= 1:
@@ -218,6 +239,14 @@ class sharded_mma:
         self.exchange_sums()
         self.local.backward_pass(omega)
         self.exchange_sums()
+
+    def iterations(self, n: int, omega: float = 0.5):
+        """n iterations; with the peer-memory exchange they run inside the library (pass, exchange, pass, exchange replayed as a CUDA graph)."""
+        if self.symm is not None:
+            self.local.iterations(n, omega)
+        else:
+            for _ in range(n):
+                self.iteration(omega)
 
     def delta_sums(self) -> np.ndarray:
         """Un-normalised per-variable sums after the last exchange, in the ORIGINAL variable order (2V, lo/hi interleaved).

@@ -8,37 +8,43 @@ whole BDD collection (bdd_cuda_parallel_mma.cu:142-153).
 Workload.  N=1: BASELINE.json configs[1], the synthetic set-cover ILP with 25 000 rows x 50 000
 columns x 20 columns per row = 1 025 000 BDD nodes, float.  N>1 (weak scaling): the
 same generator with N x rows and N x columns (N x 1.025 M nodes) sharded by constraint, one
-shard per GPU, un-normalised per-variable deltas all-reduced after every pass.
+shard per GPU, the per-variable sums of the shared variables exchanged after every pass.
 `value` is in iterations/s of 1.025 M-node shards: N_shards * K / time, i.e. plain iterations/s
 at N=1.
 
-Timed quantities
+Timed quantities of the top-level line
   value      device-resident state, per-step CUDA events on the solver's stream, L2 flushed
              between timed steps (the 1 M-node working set would otherwise live in the 126 MB L2);
              `back_to_back` in the same line is the un-flushed steady state of a real solve.
-  e2e        the same step driven through the reference-facing API with HOST buffers every step:
-             update_costs(host lo, host hi) [H2D of 2V REALs, the perturbation step of the
-             rounding loop, bdd_solver.cpp:318-380] -> iteration() -> lower_bound() [D2H of the
-             bound, what run_solver does each iteration, run_solver_util.h:37-49].
+  e2e        the same step driven with HOST buffers every step: update_costs(host lo, host hi) [H2D of 2V
+             REALs from pinned memory, the perturbation step of the rounding loop, bdd_solver.cpp:318-380]
+             -> iteration() -> lower_bound() [D2H of the bound, what run_solver does each iteration,
+             run_solver_util.h:37-49].  At N=1 through the fused C-ABI call bddb200_step_host; the same step as
+             three separate calls is `e2e.separate_calls`.
   roofline   forward / backward sweep kernel: algorithmic bytes per pass (SURVEY 8d formula)
              divided by the kernel's mean duration from CUDA events around each pass launch.
   cpu_baseline / --impl reference: the reference's own CPU `parallel mma` solver
              (oracle/_ref/libbdd_ref.so, built from /root/reference sources) or, where that
              library is absent, the plain-C port (oracle/liboracle_mma.so), all host threads.
+
+Additional keys (same run, same process)
+  workloads  (N=1) BASELINE configs 3, 4, 5: qap_5m double, grid_mrf_20m float, `lbfgs cuda parallel mma` (history 5) on
+             qap_5m -- value / back_to_back / roofline / cpu_baseline each, measured like the top-level line.
+  lb_vs_time (N=1) lower bound vs wall clock at 1, 10, 100, 1000 iterations: GPU mma, GPU lbfgs, CPU reference.
+  strong_scaling, parity_ok (N>1) config 4 (grid_mrf_20m sharded by constraint over the N GPUs) and the in-process
+             sharded == whole check of tools/gpu_dist_check.py on a small instance.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
-
-import numpy as np
 import statistics
-import subprocess
 import sys
-import tempfile
 import threading
 import time
+
+import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -76,7 +82,6 @@ def make_instance(n_shards: int, workload: str):
 
 def shape_numbers(col, n_vars_total: int):
     """N_nt (non-terminal nodes), L_v (inner layers), V, B, H of a collection."""
-    import numpy as np
     from bdd_b200.instances import BOTSINK
     idx = col.instrs[:, 2]
     inner = idx < BOTSINK
@@ -98,63 +103,65 @@ def algorithmic_bytes_per_pass(sh, R: int) -> float:
 
 # ----------------------------------------------------------------------------- clocks ---
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled in-process through NVML while the timed regions run."""
 
-    def __init__(self, gpu_index: int):
-        self.idx = gpu_index
-        self.proc = None
-        self.path = None
+    def __init__(self, gpu_index: int, period_s: float = 0.02):
+        self.idx, self.period = gpu_index, period_s
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        self.error = None
+
+    def _run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.idx)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
+                     "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
+                     "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
+                     "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4))}
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self._stop.is_set():
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = int(get_reasons(h))
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+                time.sleep(self.period)
+        except Exception as e:       # no NVML on this box: the line says so
+            self.error = repr(e)
 
     def start(self):
-        try:
-            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
-            self.path = f.name
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=f, stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
-            return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        try:
-            for line in open(self.path):
-                p = [x.strip() for x in line.split(",")]
-                if len(p) < 9:
-                    continue
-                try:
-                    sm.append(float(p[1])); mx.append(float(p[2]))
-                except ValueError:
-                    continue
-                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
-            os.unlink(self.path)
-        except Exception:
-            pass
-        if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=2)
+        out = {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+               "samples": len(self.sm), "source": "NVML, sampled in-process every 20 ms during the timed regions"}
+        if self.error:
+            out["error"] = self.error
         return out
 
 
 # ------------------------------------------------------------------------ CPU baseline ---
+def host_threads() -> int:
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: count the cores this process may run on instead
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_solver(col, costs, precision):
     """(solver with .iteration()/.lower_bound(), kind, threads).  The ONLY place bench.py touches oracle/."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import bindings as B
-    # torchrun exports OMP_NUM_THREADS=1 to its workers: count the cores this process may run on instead
-    try:
-        avail = len(os.sched_getaffinity(0))
-    except AttributeError:
-        avail = os.cpu_count() or 1
+    avail = host_threads()
     if B.ref_available():
         n = max(B.ref_max_threads(), avail)
         B.ref_set_num_threads(n)
@@ -179,24 +186,23 @@ class _StdoutToStderr:
         os.close(self.saved)
 
 
-def time_cpu(col, costs, precision, warmup, max_steps, budget_s):
+def time_cpu(col, costs, precision, warmup, max_steps, budget_s, checkpoints=None):
     with _StdoutToStderr():
-        return _time_cpu(col, costs, precision, warmup, max_steps, budget_s)
-
-
-def _time_cpu(col, costs, precision, warmup, max_steps, budget_s):
-    s, kind, threads = cpu_solver(col, costs, precision)
-    for _ in range(warmup):
-        s.iteration()
-    t0 = time.perf_counter()
-    done = 0
-    while done < max_steps:
-        s.iteration()
-        done += 1
-        if time.perf_counter() - t0 > budget_s:
-            break
-    dt = time.perf_counter() - t0
-    return {"iters": done, "seconds": dt, "kind": kind, "threads": threads, "lb": s.lower_bound()}
+        s, kind, threads = cpu_solver(col, costs, precision)
+        for _ in range(warmup):
+            s.iteration()
+        pts = []
+        t0 = time.perf_counter()
+        done = 0
+        while done < max_steps:
+            s.iteration()
+            done += 1
+            if checkpoints and done in checkpoints:
+                pts.append([done, time.perf_counter() - t0, s.lower_bound()])
+            if time.perf_counter() - t0 > budget_s:
+                break
+        dt = time.perf_counter() - t0
+        return {"iters": done, "seconds": dt, "kind": kind, "threads": threads, "lb": s.lower_bound(), "points": pts}
 
 
 def run_reference(args):
@@ -226,245 +232,342 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------- ours --
-def run_ours(args):
-    import numpy as np
-    import torch
-    import torch.distributed as dist
-    from bdd_b200 import dist as bdist
-    from bdd_b200.solver import bdd_cuda_parallel_mma
+class Env:
+    """torch / distributed context of this rank."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
+    def __init__(self, gpus):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != gpus and self.world == 1 and gpus > 1:
             raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
-        args.gpus = world
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        self.peak = float(peaks.get("hbm_gbs", 6650.0))
+        self.peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
 
-    col, costs, precision = make_instance(world, args.workload)
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def max_over_ranks(self, values):
+        t = self.torch.tensor(values, dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t.cpu()]
+
+
+def measure(env: Env, workload: str, K: int, W: int, with_cpu: bool, with_e2e: bool = True, lbfgs: bool = False):
+    """value / back_to_back / e2e / roofline / cpu_baseline of one workload on env.world GPUs (the dict of one bench line)."""
+    torch = env.torch
+    from bdd_b200 import dist as bdist
+    from bdd_b200.solver import bdd_cuda_parallel_mma, lbfgs_cuda_mma
+    world, rank, dev = env.world, env.rank, env.dev
+    col, costs, precision = make_instance(world if workload == "set_cover_1m" else 1, workload)
     R = 4 if precision == "float" else 8
     sh = shape_numbers(col, len(costs))
     V = sh["V"]
 
     t_c0 = time.perf_counter()
     if world > 1:
-        solver = bdist.sharded_mma(col, costs, rank, world, bdist.make_cuda_local(precision, local_rank))
+        solver = bdist.sharded_mma(col, costs, rank, world, bdist.make_cuda_local(precision, env.local_rank))
         local = solver.local
         local_sh = shape_numbers(solver.local_col, V)
+    elif lbfgs:
+        solver = local = lbfgs_cuda_mma(col, costs, precision=precision, device=env.local_rank, history_size=5)
+        local_sh = sh
     else:
-        solver = local = bdd_cuda_parallel_mma(col, costs, precision=precision, device=local_rank)
+        solver = local = bdd_cuda_parallel_mma(col, costs, precision=precision, device=env.local_rank)
         local_sh = sh
     local.synchronize()
     construct_ms = 1e3 * (time.perf_counter() - t_c0)
     st = local.stream
     pass_bytes = algorithmic_bytes_per_pass(local_sh, R)
 
-    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
     def flush_l2():
         with torch.cuda.stream(st):
-            flush_buf.zero_()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
+            env.flush_buf.zero_()
 
     lb0 = solver.lower_bound()
-    # one launch per iteration (the on-chip kernel, bdd_b200/csrc/resident.cuh) when the collection is eligible
-    if world == 1:
-        local.iteration()
-    l0 = local.kernel_launches()
-    if world == 1:
-        local.iteration()
-    fused = world == 1 and local.kernel_launches() - l0 == 1
-
-    def one_iteration():
-        if world > 1:
-            solver.iteration()
-        elif fused:
-            local.iteration()
-        else:
-            local.forward_pass(0.5)
-            local.backward_pass(0.5)
-
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(W, 3)):
         flush_l2()
-        one_iteration()
-    barrier()
+        solver.iteration()
+    env.barrier()
 
     # ---- value: per-step events, L2 flushed between steps ---------------------------------
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    K = args.steps
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
     launches0 = local.kernel_launches()
-    barrier()
+    env.barrier()
     wall0 = time.perf_counter()
     for k in range(K):
         flush_l2()
         ev[k][0].record(st)
-        if world > 1:
-            local.forward_pass(0.5)
-            ev[k][1].record(st)
-            solver.exchange_sums()
-            local.backward_pass(0.5)
-            solver.exchange_sums()
-        elif fused:
-            local.iteration()
+        if lbfgs:
+            solver.iteration()
             ev[k][1].record(st)
         else:
-            local.forward_pass(0.5)
+            local.forward_pass(0.5)          # at N > 1 the pass ends with the exchange of the shared variables' sums
             ev[k][1].record(st)
+            if world > 1:
+                solver.exchange_sums()       # (a no-op when the library issues the exchange itself)
             local.backward_pass(0.5)
+            if world > 1:
+                solver.exchange_sums()
         ev[k][2].record(st)
-    barrier()
+    env.barrier()
     wall = time.perf_counter() - wall0
     launches = local.kernel_launches() - launches0
-    step_ms = [e[0].elapsed_time(e[2]) for e in ev]
+    total_ms = sum(e[0].elapsed_time(e[2]) for e in ev)
     fwd_ms = [e[0].elapsed_time(e[1]) for e in ev]
-    total_ms = sum(step_ms)
+    bwd_ms = [e[1].elapsed_time(e[2]) for e in ev]
+    kern_ms = (sum(fwd_ms) + sum(bwd_ms)) / (2 * K)          # at N > 1: pass + exchange
 
-    # ---- back-to-back steady state (no flush; graph replay at N=1) --------------------------
-    barrier()
+    # ---- back-to-back steady state (no flush; CUDA-graph replay inside the library) ------------
+    env.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     nb = max(K, 300)
-    if world == 1:
-        local.iterations(9)
-    e0.record(st)
-    if world == 1:
-        local.iterations(nb)
-    else:
+    if lbfgs:
+        e0.record(st)
         for _ in range(nb):
             solver.iteration()
-    e1.record(st)
-    barrier()
+        e1.record(st)
+    else:
+        solver.iterations(9)
+        e0.record(st)
+        solver.iterations(nb)
+        e1.record(st)
+    env.barrier()
     b2b_ms = e0.elapsed_time(e1) / nb
 
-    # ---- roofline pass timing at N>1 needs the backward kernel alone --------------------------
-    if fused:
-        # the launch IS the iteration: forward and backward pass in one kernel
-        bwd_ms = fwd_ms
-        pass_bytes *= 2
-    elif world == 1:
-        bwd_ms = [e[1].elapsed_time(e[2]) for e in ev]
-    else:
-        bwd_ms = fwd_ms
-    kern_ms = (sum(fwd_ms) + sum(bwd_ms)) / (len(fwd_ms) + len(bwd_ms))
-
     # ---- e2e: host buffers every step -----------------------------------------------------------
-    # pinned host vectors of the solver's REAL type (std::vector<REAL> overload of update_costs); at N=1 the three calls
-    # update_costs / iteration / lower_bound go through the fused entry point bddb200_step_host (one upload, one graph launch,
-    # one read-back), and the same step made with the three separate calls is reported next to it
-    rng = np.random.default_rng(123)
-    tdt = torch.float64 if precision == "double" else torch.float32
-    # two pinned buffers [lo | hi] (lo = zeros): adjacent vectors go up in one copy
-    buf_a = torch.zeros(2 * V, dtype=tdt, pin_memory=True); buf_b = torch.zeros(2 * V, dtype=tdt, pin_memory=True)
-    pert, neg = buf_a.numpy()[V:], buf_b.numpy()[V:]
-    pert[:] = rng.integers(-1, 2, size=V); neg[:] = -pert
-
-    def e2e_step(k, fused_call):
-        hi = pert if k % 2 == 0 else neg
-        zeros = (buf_a if k % 2 == 0 else buf_b).numpy()[:V]
-        if fused_call:
-            return local.step(zeros, hi)
-        local.update_costs(zeros, hi)
-        one_iteration()
-        return solver.lower_bound()
-
-    def time_e2e(fused_call, steps):
-        for k in range(4):           # even count: the net perturbation is zero again
-            e2e_step(k, fused_call)
-        barrier()
-        total, lbv = 0.0, None
-        for k in range(steps):
-            flush_l2()
-            torch.cuda.synchronize(dev)
-            t0 = time.perf_counter()
-            lbv = e2e_step(k, fused_call)
-            total += time.perf_counter() - t0
-        barrier()
-        return total, lbv
-
+    e2e_total = e2e_sep_total = float("nan")
     e2e_steps = K + (K % 2)
-    e2e_sep_total, lb = time_e2e(False, e2e_steps)
-    if world == 1:
-        e2e_total, lb = time_e2e(True, e2e_steps)
-    else:
-        e2e_total = e2e_sep_total
-    clocks = sampler.stop()
+    lb = None
+    if with_e2e and not lbfgs:
+        rng = np.random.default_rng(123)
+        tdt = torch.float64 if precision == "double" else torch.float32
+        # two pinned buffers [lo | hi] (lo = zeros): adjacent vectors go up in one copy
+        buf_a = torch.zeros(2 * V, dtype=tdt, pin_memory=True); buf_b = torch.zeros(2 * V, dtype=tdt, pin_memory=True)
+        pert, neg = buf_a.numpy()[V:], buf_b.numpy()[V:]
+        pert[:] = rng.integers(-1, 2, size=V); neg[:] = -pert
+
+        def e2e_step(k, fused_call):
+            hi = pert if k % 2 == 0 else neg
+            zeros = (buf_a if k % 2 == 0 else buf_b).numpy()[:V]
+            if fused_call:
+                return local.step(zeros, hi)
+            local.update_costs(zeros, hi)
+            solver.iteration()
+            return solver.lower_bound()
+
+        def time_e2e(fused_call):
+            for k in range(4):           # even count: the net perturbation is zero again
+                e2e_step(k, fused_call)
+            env.barrier()
+            total, lbv = 0.0, None
+            for k in range(e2e_steps):
+                flush_l2()
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                lbv = e2e_step(k, fused_call)
+                total += time.perf_counter() - t0
+            env.barrier()
+            return total, lbv
+
+        e2e_sep_total, lb = time_e2e(False)
+        e2e_total, lb = time_e2e(True) if world == 1 else (e2e_sep_total, lb)
 
     # ---- run_solver-style loop (iteration + LB read-back, no cost upload) --------------------------
     t0 = time.perf_counter()
     for _ in range(K):
-        one_iteration()
+        solver.iteration()
         lb = solver.lower_bound()
     torch.cuda.synchronize(dev)
     rs_s = (time.perf_counter() - t0) / K
 
-    # ---- max over ranks ------------------------------------------------------------------------------
-    red = torch.tensor([total_ms, e2e_total, b2b_ms, kern_ms, rs_s, e2e_sep_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(red, op=dist.ReduceOp.MAX)
-    total_ms, e2e_total, b2b_ms, kern_ms_max, rs_s, e2e_sep_total = (float(x) for x in red.cpu())
+    total_ms, e2e_total, b2b_ms, kern_ms_max, rs_s, e2e_sep_total = env.max_over_ranks([total_ms, e2e_total, b2b_ms, kern_ms, rs_s, e2e_sep_total])
 
-    shards = col.nr_nodes / NODES_PER_SHARD if args.workload == "set_cover_1m" else 1.0
-    unit = "iterations/s (1.025M-node shard equivalents)" if args.workload == "set_cover_1m" else "iterations/s"
-    value = shards * K / (total_ms * 1e-3)
-    e2e_value = shards * e2e_steps / e2e_total
-
+    shards = col.nr_nodes / NODES_PER_SHARD if workload == "set_cover_1m" else 1.0
+    unit = "iterations/s (1.025M-node shard equivalents)" if workload == "set_cover_1m" else "iterations/s"
+    out = None
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         achieved = pass_bytes / (kern_ms * 1e-3) / 1e9
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(workload)
         except Exception:
             pass
         cpu = None
-        if world == 1 and not args.no_cpu:
-            r = time_cpu(col, costs, precision, 2, 40, 12.0)
+        if with_cpu:
+            budget = 12.0 if sh["N"] < 3e6 else 8.0
+            r = time_cpu(col, costs, precision, 1 if sh["N"] > 3e6 else 2, 40, budget)
             cpu = {"value": r["iters"] / r["seconds"], "unit": "iterations/s", "cores": r["threads"], "kind": r["kind"],
-                   "sample": f"{r['iters']} full iterations of the same {sh['N']}-node instance after 2 warm-ups, {r['threads']} OpenMP threads, {r['seconds']:.1f} s"}
-        line = {
-            "metric": "mma_iterations_per_sec", "value": value, "unit": unit, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
-            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                   "sample": f"{r['iters']} full iterations of the same {sh['N']}-node instance after warm-up, {r['threads']} OpenMP threads, {r['seconds']:.1f} s"}
+        out = {
+            "metric": "mma_iterations_per_sec", "value": shards * K / (total_ms * 1e-3), "unit": unit, "n_gpus": world, "steps": K, "warmup": max(W, 3),
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak" if workload == "set_cover_1m" else "strong", "vs_baseline": None,
             "dtype": "f32" if precision == "float" else "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "precision": precision, **sh, "shards": world,
+            "config": {"workload": workload + (" + lbfgs wrapper (history 5)" if lbfgs else ""), "precision": precision, **sh, "shards": world,
                        "l2": "flushed (256 MiB memset) between timed steps; back_to_back = steady state without flush",
                        "parallelism": (f"constraint-sharded x{world}, per-pass exchange of {solver.n_shared} shared variables via {solver.exchange}"
                                        if world > 1 else "single GPU")},
             "back_to_back": {"value": shards / (b2b_ms * 1e-3), "unit": unit, "ms_per_step": b2b_ms},
-            "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": 2 * V * R, "d2h_bytes_per_step": 8,
-                    "step": ("bddb200_step_host(pinned host lo, hi) = update_costs + iteration + lower_bound in one C-ABI call, wall clock" if world == 1
-                             else "update_costs(host lo, host hi) + iteration() + lower_bound() through the C ABI, wall clock"),
-                    "separate_calls": {"value": shards * e2e_steps / e2e_sep_total, "unit": unit, "step": "update_costs(host lo, host hi); iteration(); lower_bound() as three calls"},
-                    "run_solver_loop": {"value": shards / rs_s, "unit": unit, "step": "iteration() + lower_bound()"}},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "resident_kernel<REAL> (one launch = forward + backward pass)" if fused else "sweep_lane_kernel<REAL, MODE_MMA, fwd|bwd>", "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": pass_bytes,
-                         "peak_source": peak_src},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": env.peak, "unit": "GB/s", "frac": achieved / env.peak,
+                         "traffic": traffic, "traffic_source": "profiles/traffic.json (ncu --set full dram__bytes of an earlier capture, not measured in this run)" if traffic else None,
+                         "kernel": "sweep_lane_kernel<REAL, MODE_MMA, fwd|bwd>" + (" + exchange kernel" if world > 1 else ""), "kernel_ms": kern_ms,
+                         "algorithmic_bytes_per_launch": pass_bytes, "peak_source": env.peak_src},
             "cpu_baseline": cpu,
-            "clocks": clocks,
             "construct_ms": construct_ms, "wall_s_timed_region": wall,
             "lower_bound": {"initial": lb0, "final": lb},
         }
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+        if lbfgs:
+            it_l, it_m, step = solver.lbfgs_stats()
+            out["lbfgs"] = {"lbfgs_iterations": it_l, "mma_iterations": it_m, "step_size": step}
+            out["roofline"] = None
+        if with_e2e and not lbfgs:
+            out["e2e"] = {"value": shards * e2e_steps / e2e_total, "unit": unit, "h2d_bytes_per_step": 2 * V * R, "d2h_bytes_per_step": 8,
+                          "step": ("bddb200_step_host(pinned host lo, hi) = update_costs + iteration + lower_bound in one C-ABI call, wall clock" if world == 1
+                                   else "update_costs(host lo, host hi) + iteration() + lower_bound() through the C ABI, wall clock"),
+                          "separate_calls": {"value": shards * e2e_steps / e2e_sep_total, "unit": unit, "step": "update_costs(host lo, host hi); iteration(); lower_bound() as three calls"},
+                          "run_solver_loop": {"value": shards / rs_s, "unit": unit, "step": "iteration() + lower_bound()"}}
+    del solver, local
+    torch.cuda.empty_cache()
+    return out, (col, costs, precision)
+
+
+def lb_vs_time(env: Env, workload: str, instance, with_cpu: bool, cpu_budget: float):
+    """Lower bound vs wall clock at 1, 10, 100, 1000 iterations: GPU mma, GPU lbfgs, CPU reference (BASELINE metric, second half;
+    the reference prints this per iteration, run_solver_util.h:44-49).  GPU iterations run back to back between the checkpoints;
+    every checkpoint ends with a lower_bound() read-back."""
+    torch = env.torch
+    from bdd_b200.solver import bdd_cuda_parallel_mma, lbfgs_cuda_mma
+    col, costs, precision = instance
+    checkpoints = [1, 10, 100, 1000]
+
+    def run_gpu(s, step):
+        pts = [[0, 0.0, s.lower_bound()]]
+        done = 0
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for c in checkpoints:
+            step(s, c - done)
+            done = c
+            pts.append([c, time.perf_counter() - t0, s.lower_bound()])
+        return pts
+
+    out = {"workload": workload, "precision": precision, "columns": ["iterations", "seconds", "lower_bound"]}
+    s = bdd_cuda_parallel_mma(col, costs, precision=precision, device=env.local_rank)
+    out["gpu_mma"] = run_gpu(s, lambda s, n: s.iterations(n))
+    del s
+    l = lbfgs_cuda_mma(col, costs, precision=precision, device=env.local_rank, history_size=5)
+
+    def lstep(s, n):
+        for _ in range(n):
+            s.iteration()
+    out["gpu_lbfgs"] = run_gpu(l, lstep)
+    it_l, it_m, step = l.lbfgs_stats()
+    out["gpu_lbfgs_stats"] = {"lbfgs_iterations": it_l, "mma_iterations": it_m, "step_size": step}
+    del l
+    if with_cpu:
+        r = time_cpu(col, costs, precision, 0, 1000, cpu_budget, checkpoints=set(checkpoints))
+        out["cpu_reference"] = r["points"]
+        out["cpu_reference_note"] = f"{r['kind']}, {r['threads']} OpenMP threads; stopped after {r['iters']} iterations ({cpu_budget:.0f} s budget)"
+    torch.cuda.empty_cache()
+    return out
+
+
+def dist_parity(env: Env) -> bool:
+    """sharded == whole on a small instance, pass by pass (the check of tools/gpu_dist_check.py, in-process)."""
+    torch = env.torch
+    from bdd_b200 import dist as bdist, instances
+    from bdd_b200.instances import BOTSINK
+    from bdd_b200.solver import bdd_cuda_parallel_mma
+    ok = True
+    col, costs = instances.set_cover(m=3000, n=5000, k=9, seed=5)
+    for precision, tol in (("double", 1e-9), ("float", 2e-4)):
+        sh = bdist.sharded_mma(col, costs, env.rank, env.world, bdist.make_cuda_local(precision, env.local_rank))
+        whole = bdd_cuda_parallel_mma(col, costs, precision=precision, device=env.local_rank)
+        local_new = np.unique(sh.local_col.instrs[sh.local_col.instrs[:, 2] < BOTSINK, 2].astype(np.int64))
+        local_vars = np.argsort(sh.new_of_old)[local_new]
+        sel = np.stack([2 * local_vars, 2 * local_vars + 1], axis=1).reshape(-1)
+        cnt = np.maximum(bdist.global_nr_bdds_per_var(col, sh.nr_vars), 1).astype(np.float64)
+        for it in range(4):
+            if it < 2:
+                sh.iteration(); whole.iteration()
+            else:
+                sh.iterations(3); whole.iterations(3)          # the graph-replayed form (pass + exchange inside the library)
+            d_s = sh.delta_sums().astype(np.float64)
+            d_s[0::2] /= cnt; d_s[1::2] /= cnt
+            d_w = whole.get_delta().double().cpu().numpy()
+            err = float(np.abs(d_s[sel] - d_w[sel]).max()) / max(1.0, float(np.abs(d_w).max()))
+            lb_s, lb_w = sh.lower_bound(), whole.lower_bound()
+            ok = ok and err <= tol and abs(lb_s - lb_w) <= tol * max(1.0, abs(lb_w))
+        del sh, whole
+    t = torch.tensor([1 if ok else 0], device=env.dev)
+    if env.world > 1:
+        env.dist.all_reduce(t, op=env.dist.ReduceOp.MIN)
+    return int(t.item()) == 1
+
+
+def run_ours(args):
+    # libraries (NCCL's version banner, the reference's logger) write to stdout: keep the real stdout for the ONE JSON line
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    env = Env(args.gpus)
+    args.gpus = env.world
+    sampler = ClockSampler(env.local_rank)
+    sampler.start()
+    line, instance = measure(env, args.workload, args.steps, args.warmup, with_cpu=(env.world == 1 and not args.no_cpu))
+    extras = not args.no_extras and args.workload == "set_cover_1m"
+    workloads, lbt, strong, parity = {}, [], None, None
+    if extras and env.world == 1:
+        Kx = max(10, min(args.steps, 50))
+        lbt.append(lb_vs_time(env, "set_cover_1m", instance, not args.no_cpu, 6.0))
+        del instance
+        q, q_inst = measure(env, "qap_5m", Kx, 3, with_cpu=not args.no_cpu)
+        workloads["qap_5m"] = q
+        l, _ = measure(env, "qap_5m", Kx, 3, with_cpu=False, lbfgs=True)
+        workloads["lbfgs_qap_5m"] = l
+        lbt.append(lb_vs_time(env, "qap_5m", q_inst, not args.no_cpu, 8.0))
+        del q_inst
+        g, _ = measure(env, "grid_mrf_20m", Kx, 3, with_cpu=not args.no_cpu)
+        workloads["grid_mrf_20m"] = g
+    if extras and env.world > 1:
+        del instance
+        parity = dist_parity(env)
+        strong, _ = measure(env, "grid_mrf_20m", max(10, min(args.steps, 50)), 3, with_cpu=False, with_e2e=False)
+    clocks = sampler.stop()
+    if env.rank == 0:
+        line["clocks"] = clocks
+        if workloads:
+            line["workloads"] = workloads
+        if lbt:
+            line["lb_vs_time"] = lbt
+        if strong is not None:
+            line["strong_scaling"] = strong
+        if parity is not None:
+            line["parity_ok"] = parity
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+    if env.world > 1:
+        env.dist.destroy_process_group()
 
 
 def main():
@@ -474,7 +577,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("BENCH_WORKLOAD", "set_cover_1m"))
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--no-extras", action="store_true", help="only the top-level workload (no workloads / lb_vs_time / strong_scaling keys)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -213,6 +213,15 @@ size_t bddb200_kernel_launches(const bddb200_solver* s);
  * buffer holding the UN-normalised sums written by the last pass (2 * nr_variables REALs). */
 int bddb200_delta_sum_buffer(bddb200_solver* s, void** sum_dev);
 
+/* The library issues the exchange itself after every forward_pass / backward_pass (and inside iteration / iterations, whose CUDA
+ * graph then contains it): register the peer mappings once.  mode 1 = one-shot reads of every peer's sum buffer, 2 = two-shot
+ * (slice-wise reduce, then copy), 3 = in-switch reduction through multicast mappings (multimem.ld_reduce / multimem.st; mc_in = multicast
+ * address of the symmetric block holding the three sum buffers, mc_out = multicast address of the symmetric result buffer), 0 = off.
+ * The epoch of the flag barriers lives on the device, so all ranks must make the same sequence of passes.  Replaces the host-staged
+ * exchange of the hybrid solver, bdd_multi_parallel_mma_base.cu:266-318. */
+int bddb200_set_exchange(bddb200_solver* s, int world, int rank, const void* const* peer_bufs_dev, uint32_t* const* flags_dev, void* out_dev,
+                         void* const* peer_outs_dev, const void* mc_in, void* mc_out, size_t n_exchange, int mode);
+
 /* ---- multi-GPU exchange over peer memory (NVLink / NVSwitch), SURVEY 8e -----------------------------
  * The reference has no multi-GPU code; its only multi-device exchange is the hybrid solver's host-staged
  * copy of the delta vector (bdd_multi_parallel_mma_base.cu:266-318).  Here each rank keeps its three rotating
