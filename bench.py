@@ -205,6 +205,38 @@ def time_cpu(col, costs, precision, warmup, max_steps, budget_s, checkpoints=Non
         return {"iters": done, "seconds": dt, "kind": kind, "threads": threads, "lb": s.lower_bound(), "points": pts}
 
 
+def run_reference_cuda(args):
+    """--impl reference_cuda: the reference's OWN `cuda parallel mma` (src/bdd_solver/bdd_cuda_parallel_mma.cu, compiled for sm_100a by
+    oracle/Makefile from the sources under /root/reference) on this box's GPU 0, same config: a same-box GPU baseline."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    line = time_reference_cuda(args.workload, args.gpus, args.steps, max(args.warmup, 3))
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
+
+def time_reference_cuda(workload, n_shards, steps, warmup, instance=None):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import bindings as B
+    if not B.ref_cuda_available():
+        return {"impl": "reference_cuda", "unavailable": "oracle/_ref/libbdd_ref_cuda.so not built (needs /root/reference at build time)"}
+    col, costs, precision = instance if instance is not None else make_instance(n_shards, workload)
+    sh = shape_numbers(col, len(costs))
+    s = B.RefCudaSolver(col.instrs, col.delims, costs, precision)
+    s.iterations(warmup)
+    seconds = s.iterations(steps)
+    shards = col.nr_nodes / NODES_PER_SHARD if workload == "set_cover_1m" else 1.0
+    unit = "iterations/s (1.025M-node shard equivalents)" if workload == "set_cover_1m" else "iterations/s"
+    value = shards * steps / seconds
+    return {"impl": "reference_cuda", "metric": "mma_iterations_per_sec", "value": value, "unit": unit, "n_gpus": 1, "steps": steps, "warmup": warmup,
+            "ms_per_step": 1e3 * seconds / steps, "higher_is_better": True, "dtype": "f32" if precision == "float" else "f64", "data": "synthetic",
+            "config": {"workload": workload, "precision": precision, **sh, "l2": "not flushed (back to back)"},
+            "what": "reference bdd_cuda_parallel_mma<REAL>::iteration, unmodified sources built for sm_100a, default stream, back to back, wall clock around a synchronised loop",
+            "lower_bound": s.lower_bound()}
+
+
 def run_reference(args):
     """--impl reference: the reference CPU `parallel mma` on this box's host cores, same config."""
     rank = int(os.environ.get("RANK", "0"))
@@ -468,7 +500,8 @@ def lb_vs_time(env: Env, workload: str, instance, with_cpu: bool, cpu_budget: fl
         for c in checkpoints:
             step(s, c - done)
             done = c
-            pts.append([c, time.perf_counter() - t0, s.lower_bound()])
+            lb = s.lower_bound()             # waits for the device: the clock is read after it
+            pts.append([c, time.perf_counter() - t0, lb])
         return pts
 
     out = {"workload": workload, "precision": precision, "columns": ["iterations", "seconds", "lower_bound"]}
@@ -536,13 +569,23 @@ def run_ours(args):
     sampler.start()
     line, instance = measure(env, args.workload, args.steps, args.warmup, with_cpu=(env.world == 1 and not args.no_cpu))
     extras = not args.no_extras and args.workload == "set_cover_1m"
-    workloads, lbt, strong, parity = {}, [], None, None
+    workloads, lbt, strong, parity, ref_cuda = {}, [], None, None, None
     if extras and env.world == 1:
         Kx = max(10, min(args.steps, 50))
         lbt.append(lb_vs_time(env, "set_cover_1m", instance, not args.no_cpu, 6.0))
+        try:
+            with _StdoutToStderr():
+                ref_cuda = {"set_cover_1m": time_reference_cuda("set_cover_1m", 1, 50, 5, instance)}
+        except Exception as e:
+            ref_cuda = {"error": repr(e)}
         del instance
         q, q_inst = measure(env, "qap_5m", Kx, 3, with_cpu=not args.no_cpu)
         workloads["qap_5m"] = q
+        try:
+            with _StdoutToStderr():
+                ref_cuda["qap_5m"] = time_reference_cuda("qap_5m", 1, 20, 3, q_inst)
+        except Exception as e:
+            ref_cuda["qap_5m_error"] = repr(e)
         l, _ = measure(env, "qap_5m", Kx, 3, with_cpu=False, lbfgs=True)
         workloads["lbfgs_qap_5m"] = l
         lbt.append(lb_vs_time(env, "qap_5m", q_inst, not args.no_cpu, 8.0))
@@ -560,6 +603,8 @@ def run_ours(args):
             line["workloads"] = workloads
         if lbt:
             line["lb_vs_time"] = lbt
+        if ref_cuda:
+            line["reference_cuda"] = ref_cuda       # the reference's own CUDA solver on this GPU, back to back (compare with back_to_back)
         if strong is not None:
             line["strong_scaling"] = strong
         if parity is not None:
@@ -575,13 +620,15 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference_cuda"])
     ap.add_argument("--workload", default=os.environ.get("BENCH_WORKLOAD", "set_cover_1m"))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--no-extras", action="store_true", help="only the top-level workload (no workloads / lb_vs_time / strong_scaling keys)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "reference_cuda":
+        run_reference_cuda(args)
     else:
         run_ours(args)
     # the reference's static timers print to stdout at process exit: keep stdout to the JSON line

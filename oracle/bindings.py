@@ -356,3 +356,64 @@ def ref_set_num_threads(n: int):
 
 def ref_max_threads() -> int:
     return int(_ref().refw_max_threads())
+
+
+# ------------------------------------------------------------------ reference CUDA solver ---
+_REF_CUDA_PATH = os.path.join(_HERE, "_ref", "libbdd_ref_cuda.so")
+_ref_cuda_lib = None
+
+
+def ref_cuda_available() -> bool:
+    return os.path.exists(_REF_CUDA_PATH)
+
+
+def _ref_cuda():
+    global _ref_cuda_lib
+    if _ref_cuda_lib is None:
+        lib = C.CDLL(_REF_CUDA_PATH)
+        lib.refcu_solver_new.restype = C.c_void_p
+        lib.refcu_solver_new.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]
+        lib.refcu_solver_free.argtypes = [C.c_void_p]
+        lib.refcu_lower_bound.restype = C.c_double
+        lib.refcu_lower_bound.argtypes = [C.c_void_p]
+        lib.refcu_iterations.restype = C.c_double
+        lib.refcu_iterations.argtypes = [C.c_void_p, C.c_size_t]
+        lib.refcu_nr_hops.restype = C.c_size_t
+        lib.refcu_nr_hops.argtypes = [C.c_void_p]
+        lib.refcu_nr_bdd_nodes.restype = C.c_size_t
+        lib.refcu_nr_bdd_nodes.argtypes = [C.c_void_p]
+        _ref_cuda_lib = lib
+    return _ref_cuda_lib
+
+
+class RefCudaSolver:
+    """The reference's own `cuda parallel mma` (bdd_cuda_parallel_mma<REAL>, src/bdd_solver/bdd_cuda_parallel_mma.cu) compiled for
+    sm_100a from the sources under /root/reference (oracle/Makefile, target ref_cuda).  A same-box GPU baseline and checker."""
+
+    def __init__(self, instrs: np.ndarray, delims: np.ndarray, costs: np.ndarray, precision: str = "double"):
+        self.lib = _ref_cuda()
+        instrs = np.ascontiguousarray(instrs, dtype=np.uint64)
+        delims = np.ascontiguousarray(delims, dtype=np.uint64)
+        costs = np.ascontiguousarray(costs, dtype=np.float64)
+        self.h = self.lib.refcu_solver_new(instrs.ctypes.data, instrs.shape[0], delims.ctypes.data, delims.shape[0] - 1,
+                                           costs.ctypes.data, costs.shape[0], int(precision == "double"))
+        if not self.h:
+            raise RuntimeError("the reference CUDA solver could not be constructed")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.refcu_solver_free(self.h)
+            self.h = None
+
+    def lower_bound(self) -> float:
+        return self.lib.refcu_lower_bound(self.h)
+
+    def iterations(self, n: int) -> float:
+        """n iterations back to back; returns the seconds they took (device synchronised on both sides)."""
+        return self.lib.refcu_iterations(self.h, int(n))
+
+    def iteration(self):
+        self.lib.refcu_iterations(self.h, 1)
+
+    def nr_hops(self) -> int:
+        return self.lib.refcu_nr_hops(self.h)
