@@ -358,6 +358,20 @@ def ref_max_threads() -> int:
     return int(_ref().refw_max_threads())
 
 
+def ref_mm_decode(mm_per_var):
+    """The reference's CPU rounding decoder (mm_primal_decoder) on min-marginals given as a list of [k_v, 2] arrays:
+    (types per variable: 0 zero / 1 one / 2 equal / 3 inconsistent, sums [V, 2], statistics {one, zero, equal, inconsistent}, solution or None)."""
+    lib = _ref()
+    lib.refw_mm_decode.restype = C.c_int
+    lib.refw_mm_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    n = len(mm_per_var)
+    counts = np.array([m.shape[0] for m in mm_per_var], dtype=np.uint64)
+    flat = np.ascontiguousarray(np.concatenate([np.asarray(m, dtype=np.float64).reshape(-1, 2) for m in mm_per_var] + [np.zeros((0, 2))]), dtype=np.float64)
+    types = np.zeros(n, dtype=np.int8); sums = np.zeros((n, 2), dtype=np.float64); stats = np.zeros(4, dtype=np.uint64); sol = np.zeros(n, dtype=np.int8)
+    ok = lib.refw_mm_decode(flat.ctypes.data, counts.ctypes.data, n, types.ctypes.data, sums.ctypes.data, stats.ctypes.data, sol.ctypes.data)
+    return types, sums, {"one": int(stats[0]), "zero": int(stats[1]), "equal": int(stats[2]), "inconsistent": int(stats[3])}, (sol if ok else None)
+
+
 # ------------------------------------------------------------------ reference CUDA solver ---
 _REF_CUDA_PATH = os.path.join(_HERE, "_ref", "libbdd_ref_cuda.so")
 _ref_cuda_lib = None

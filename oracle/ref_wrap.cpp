@@ -39,6 +39,7 @@
 #include "bdd_conversion/convert_pb_to_bdd.h"
 #include "bdd_solver/bdd_parallel_mma_base.h"
 #include "bdd_solver/bdd_branch_instruction.h"
+#include "mm_primal_decoder.h"
 #include <vector>
 #include <array>
 #include <memory>
@@ -281,6 +282,36 @@ void refw_solver_bdds_solution(void* s, char* out)
 void refw_solver_net_solver_costs(void* s, double* out)
 {
     visit(static_cast<ref_solver*>(s), [&](auto& x) { const auto v = x.net_solver_costs(); for(size_t i = 0; i < v.size(); ++i) out[i] = v[i]; return 0; });
+}
+
+// The reference's min-marginal decoder of the CPU primal rounding (include/mm_primal_decoder.h, src/bdd_solver/mm_primal_decoder.cpp;
+// used by include/bdd_solver/incremental_mm_agreement_rounding.hxx:78-140): per variable the agreement type (0 zero, 1 one, 2 equal,
+// 3 inconsistent), the sums of the min-marginals, the type statistics {#one, #zero, #equal, #inconsistent} and, when every variable is
+// zero / one, the solution.  mms: 2 doubles per (variable, BDD) entry, variable-major; counts[v] entries for variable v.
+int refw_mm_decode(const double* mms, const size_t* counts, size_t n_vars, char* types_out, double* sums_out, size_t* stats_out, char* solution_out)
+{
+    std::vector<std::vector<std::array<double,2>>> rows(n_vars);
+    size_t c = 0;
+    for(size_t v = 0; v < n_vars; ++v)
+        for(size_t j = 0; j < counts[v]; ++j, ++c) rows[v].push_back({mms[2*c], mms[2*c+1]});
+    two_dim_variable_array<std::array<double,2>> arr(rows);
+    const mm_primal_decoder dec(std::move(arr));
+    for(size_t v = 0; v < n_vars; ++v)
+    {
+        const mm_type t = dec.compute_mm_type(v);
+        types_out[v] = t == mm_type::zero ? 0 : (t == mm_type::one ? 1 : (t == mm_type::equal ? 2 : 3));
+        const auto sum = dec.mm_sum(v);
+        sums_out[2*v] = sum[0]; sums_out[2*v+1] = sum[1];
+    }
+    const auto st = dec.mm_type_statistics();
+    for(int k = 0; k < 4; ++k) stats_out[k] = st[k];
+    if(dec.can_reconstruct_solution() && solution_out != nullptr)
+    {
+        const auto sol = dec.solution_from_mms();
+        std::memcpy(solution_out, sol.data(), sol.size());
+        return 1;
+    }
+    return 0;
 }
 
 } // extern "C"

@@ -1,0 +1,86 @@
+"""The C++ host driver (bdd_b200/csrc/host/bdd_solver_native.hpp, bdd_solver_cl): its .lp reader and BDD builder against the Python
+ones (which tests/test_host.py pins against the reference's converter) on every fixture -- no GPU needed -- and, on the GPU box, the
+command line solving the fixtures with all four GPU config strings (known answers of test/test_bdd_cuda_parallel_mma.cu:197-247)."""
+import glob
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "bdd_b200", "bdd_solver_cl")
+
+
+def _need_cli():
+    if not os.path.exists(CLI):
+        pytest.skip("bdd_b200/bdd_solver_cl not built")
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "*.lp"))))
+def test_cpp_reader_and_bdd_builder_equal_the_python_ones(path):
+    _need_cli()
+    from bdd_b200 import instances, lp
+    r = subprocess.run([CLI, "--lp-to-bdds", path], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    out = json.loads(r.stdout)
+    ilp = lp.parse_lp(open(path).read())
+    col, costs = instances.from_ilp(ilp)
+    assert out["var_names"] == ilp.var_names
+    assert np.array_equal(np.asarray(out["objective"]), costs) and out["constant"] == ilp.constant
+    assert np.array_equal(np.asarray(out["delims"], dtype=np.uint64), col.delims)
+    assert np.array_equal(np.asarray(out["instrs"], dtype=np.uint64).reshape(-1, 3), col.instrs)
+
+
+def test_cpp_reader_handles_the_lp_subset(tmp_path):
+    """coefficients with '*', constants on the left, multi-line constraints, identifiers, comment lines, =< / =>, a Bounds tail"""
+    _need_cli()
+    from bdd_b200 import instances, lp
+    text = ("\\ a comment\nMinimize\n 2 x_1 - 3 * y(2) + z + 4\nSubject To\n c1: x_1 + 2 y(2)\n   - z >= 1\n x_1 + y(2) + z + w =< 2\n"
+            " r3: 3 w - 2 x_1 + 1 => 0\n w + z = 1\nBounds\n x_1 <= 1\nBinaries\n x_1 z\nEnd\n")
+    p = tmp_path / "t.lp"
+    p.write_text(text)
+    r = subprocess.run([CLI, "--lp-to-bdds", str(p)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    out = json.loads(r.stdout)
+    ilp = lp.parse_lp(text)
+    col, costs = instances.from_ilp(ilp)
+    assert out["var_names"] == ilp.var_names and out["constant"] == ilp.constant == 4.0
+    assert np.array_equal(np.asarray(out["objective"]), costs)
+    assert np.array_equal(np.asarray(out["instrs"], dtype=np.uint64).reshape(-1, 3), col.instrs)
+
+
+EXPECTED = {"matching_3x3": -6.0, "short_chain_shuffled": 1.0, "long_chain": -9.0, "grid_graph_3x3": -8.0}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["cuda parallel mma", "lbfgs cuda mma", "cuda lbfgs parallel mma", "lbfgs cuda parallel mma"])
+@pytest.mark.parametrize("precision", ["double", "float"])
+def test_cli_solves_the_fixtures_on_the_gpu(kind, precision):
+    _need_cli()
+    for name, lb in EXPECTED.items():
+        path = os.path.join(GOLDEN, name + ".lp")
+        if not os.path.exists(path):
+            continue
+        cfg = {"input": path, "precision": precision, "relaxation solver": kind,
+               "termination criteria": {"maximum iterations": 300, "minimum improvement": 1e-12, "improvement slope": 0.0},
+               "perturbation rounding": {"initial perturbation": 0.1, "perturbation growth rate": 1.1, "inner iterations": 100, "outer iterations": 100}}
+        r = subprocess.run([CLI, json.dumps(cfg)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out = json.loads(r.stdout.strip().splitlines()[-1])
+        tol = 1e-6 if precision == "double" else 1e-3
+        assert abs(out["lower_bound"] - lb) <= tol * max(1.0, abs(lb)) + (0.0 if precision == "double" else 0.5), (name, out["lower_bound"])
+        assert "solution" in out and abs(out["objective"] - lb) <= 1e-6, (name, out.get("objective"))
+        assert "[bdd solver] iteration 0, lower bound" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cli_rejects_what_it_does_not_provide():
+    _need_cli()
+    path = os.path.join(GOLDEN, "long_chain.lp")
+    for cfg in ({"input": path, "relaxation solver": "parallel mma"}, {"input": path, "precision": "half"}, {"relaxation solver": "cuda parallel mma"}):
+        r = subprocess.run([CLI, json.dumps(cfg)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+        assert r.returncode == 1 and "bdd_solver_cl:" in r.stderr

@@ -77,3 +77,46 @@ def test_rounding_set_cover_is_feasible(solver_kind):
     assert instances.bdds_accept(col, sol).all()              # every row is covered
     cost = float(np.dot(costs, sol))
     assert cost >= lb - 1e-6 and cost <= 1.25 * lb            # integer costs in [1, 100]; the rounded cover stays near the bound
+
+
+@pytest.mark.parametrize("precision", ["double", "float"])
+@pytest.mark.parametrize("case", ["mrf_grid_graph_3x3", "long_mrf_chain", "matching_3x3", "cover_300x500"])
+def test_perturbation_round_against_the_reference_decoder(case, precision):
+    """The device rounding kernel against the reference's own CPU decoder (mm_primal_decoder, compiled into oracle/_ref): agreement type
+    per variable, type statistics, and the side the perturbation is applied to for every variable whose side is not random
+    (one / zero: by type; inconsistent: by the min-marginal sums, incremental_mm_agreement_rounding.hxx:100-140)."""
+    if not B.ref_available():
+        pytest.skip("oracle/_ref/libbdd_ref.so not built")
+    from bdd_b200 import instances
+    from bdd_b200.solver import bdd_cuda_parallel_mma
+    if case == "cover_300x500":
+        col, costs = instances.set_cover(m=300, n=500, k=6, seed=9)
+    else:
+        g = np.load(os.path.join(GOLDEN, case + ".npz"))
+        col, costs = _col(g), g["costs"]
+    s = bdd_cuda_parallel_mma(col, costs, precision=precision)
+    for _ in range(4):
+        s.iteration()
+    s.distribute_delta()
+    mm = s.min_marginals()
+    types_r, sums_r, stats_r, sol_r = B.ref_mm_decode(mm)
+    obj_before = s.get_primal_objective_vector_host()
+    delta = 0.25
+    sol, counts, types = s.rounding_perturb(delta, 2)
+    types = types.cpu().numpy()
+    assert np.array_equal(types, types_r)
+    assert {"zero": int(counts[0]), "one": int(counts[1]), "equal": int(counts[2]), "inconsistent": int(counts[3])} == stats_r
+    if sol_r is not None:
+        assert sol is not None and np.array_equal(sol, sol_r)
+        return
+    change = s.get_primal_objective_vector_host() - obj_before          # d1 - d0 per variable
+    tol = 1e-9 if precision == "double" else 1e-5
+    for v in range(len(types_r)):
+        if types_r[v] == 1:
+            assert abs(change[v] + delta) <= tol
+        elif types_r[v] == 0:
+            assert abs(change[v] - delta) <= tol
+        elif types_r[v] == 3 and abs(sums_r[v, 0] - sums_r[v, 1]) > 1e-3:
+            assert (change[v] > 0) == (sums_r[v, 0] < sums_r[v, 1]) and 0 < abs(change[v]) <= delta * delta + tol
+        else:
+            assert 0 <= abs(change[v]) <= delta * delta + tol
