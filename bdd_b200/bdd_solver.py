@@ -85,7 +85,10 @@ class bdd_solver:
             # no length given: a value that fills the GPU (the reference's rule, bdd_preprocessor.cpp:32-121, targets its hop-synchronous kernels)
             length = int(sb["split length"]) if "split length" in sb else compute_split_length(col)
             n_before = col.nr_bdds
-            col, _ = split_long_bdds(col, length, nr_variables=len(costs))      # auxiliary variables carry no cost
+            try:
+                col, _ = split_long_bdds(col, length, nr_variables=len(costs))      # auxiliary variables carry no cost
+            except ValueError as e:
+                raise RuntimeError(f"split bdds: {e}") from e
             self.log(f"[bdd preprocessor] split BDDs longer than {length}: {n_before} -> {col.nr_bdds} BDDs")
         return col, costs
 

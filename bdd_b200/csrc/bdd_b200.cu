@@ -890,6 +890,7 @@ public:
     double lower_bound() override
     {
         set_device();
+        if(xc_.mode != 0 && !lb_valid_) check_exchange_status();
         backward_run();
         if(!lb_valid_)
         {
@@ -1236,7 +1237,16 @@ public:
         flush_forward(); flush_backward();
     }
 
-    void synchronize() override { set_device(); CUDA_CHECK(cudaStreamSynchronize(stream_)); }
+    void synchronize() override { set_device(); CUDA_CHECK(cudaStreamSynchronize(stream_)); check_exchange_status(); }
+    // a peer did not arrive within the exchange kernels' time limit (kernels.cuh, EXCHANGE_TIMEOUT_NS)
+    void check_exchange_status()
+    {
+        if(xc_.mode == 0 || d_xc_counters_.n == 0) return;
+        uint32_t st = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&st, d_xc_counters_.p + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));
+        CUDA_CHECK(cudaStreamSynchronize(stream_));
+        if(st != 0) throw api_error(BDDB200_ERR_EXCHANGE, "multi-GPU exchange: a peer did not reach the exchange within the time limit (the sums of this pass are incomplete)");
+    }
     void* stream_handle() override { return (void*)stream_; }
     size_t kernel_launches() const override { return launches_; }
 

@@ -1437,6 +1437,37 @@ constexpr int EXCHANGE_MAX_WORLD = 16;
 __device__ __forceinline__ void ld_volatile2(const float* p, float& x, float& y) { asm volatile("ld.volatile.global.v2.f32 {%0, %1}, [%2];" : "=f"(x), "=f"(y) : "l"(p)); }
 __device__ __forceinline__ void ld_volatile2(const double* p, double& x, double& y) { asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "l"(p)); }
 
+// Waiting for a peer is bounded by wall-clock time, not by a spin count: a peer that is merely late (a host stall, a debugger, an extra
+// synchronisation on one rank) must not kill this rank's context.  After EXCHANGE_TIMEOUT_NS the waiter records the failure in
+// counters[2] (the host turns it into BDDB200_ERR_EXCHANGE at its next synchronisation) and gives up waiting.
+constexpr unsigned long long EXCHANGE_TIMEOUT_NS = 30ull * 1000ull * 1000ull * 1000ull;
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void exchange_wait_flag(const uint32_t* flag, uint32_t epoch, uint32_t* counters)
+{
+    uint32_t seen;
+    unsigned long long t0 = 0;
+    for(uint32_t spins = 0;; ++spins)
+    {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+        if((int32_t)(seen - epoch) >= 0) return;
+        if((spins & 1023u) == 1023u)
+        {
+            const unsigned long long now = global_timer_ns();
+            if(t0 == 0) t0 = now;
+            else if(now - t0 > EXCHANGE_TIMEOUT_NS)
+            {
+                if(counters != nullptr) atomicExch(counters + 2, 1u); else __trap();
+                return;
+            }
+        }
+    }
+}
+
 // Device-side epoch (graph replay): with `counters` non-null the epoch of this exchange is counters[0] + 1, and the last CTA of the
 // launch to finish advances counters[0] (counters[1] counts finished CTAs).  All ranks run the same sequence of exchanges, so their
 // counters agree without any host involvement, and a captured launch stays valid however often it is replayed.
@@ -1476,14 +1507,7 @@ __global__ void __launch_bounds__(256) delta_exchange_kernel(const REAL* const* 
             __threadfence_system();
             asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(flags[threadIdx.x] + rank), "r"(epoch) : "memory");
         }
-        const uint32_t* mine = flags[rank] + threadIdx.x;
-        uint32_t seen;
-        for(uint32_t spins = 0;; ++spins)
-        {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
-            if((int32_t)(seen - epoch) >= 0) break;
-            if(spins > (1u << 26)) __trap();          // a peer that never arrives must not hang the GPU
-        }
+        exchange_wait_flag(flags[rank] + threadIdx.x, epoch, counters);
     }
     __syncthreads();
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -1528,14 +1552,7 @@ __global__ void __launch_bounds__(256) delta_exchange2_kernel(const REAL* const*
             __threadfence_system();
             asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(flags[threadIdx.x] + rank), "r"(epoch) : "memory");
         }
-        const uint32_t* mine = my_flags + threadIdx.x;
-        uint32_t seen;
-        for(uint32_t spins = 0;; ++spins)
-        {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
-            if((int32_t)(seen - epoch) >= 0) break;
-            if(spins > (1u << 26)) __trap();
-        }
+        exchange_wait_flag(my_flags + threadIdx.x, epoch, counters);
     }
     __syncthreads();
     const size_t per = (pairs + world - 1) / world;
@@ -1568,17 +1585,7 @@ __global__ void __launch_bounds__(256) delta_exchange2_kernel(const REAL* const*
     __syncthreads();
     if(last_cta && (int)threadIdx.x < world)
         asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(flags[threadIdx.x] + 16 + rank), "r"(epoch) : "memory");
-    if((int)threadIdx.x < world)
-    {
-        const uint32_t* mine = my_flags + 16 + threadIdx.x;
-        uint32_t seen;
-        for(uint32_t spins = 0;; ++spins)
-        {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
-            if((int32_t)(seen - epoch) >= 0) break;
-            if(spins > (1u << 26)) __trap();
-        }
-    }
+    if((int)threadIdx.x < world) exchange_wait_flag(my_flags + 16 + threadIdx.x, epoch, counters);
     __syncthreads();
     // shot 2: the other ranks' slices, copied from their `out` buffers
     REAL* out = out_s[rank];
@@ -1626,17 +1633,7 @@ __global__ void __launch_bounds__(256) delta_exchange_mc_kernel(const REAL* __re
     __shared__ bool last_cta;
     uint32_t* my_flags = flags[rank];
     auto wait_all = [&](uint32_t slot0) {
-        if((int)threadIdx.x < world)
-        {
-            const uint32_t* mine = my_flags + slot0 + threadIdx.x;
-            uint32_t seen;
-            for(uint32_t spins = 0;; ++spins)
-            {
-                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
-                if((int32_t)(seen - epoch) >= 0) break;
-                if(spins > (1u << 26)) __trap();          // a peer that never arrives must not hang the GPU
-            }
-        }
+        if((int)threadIdx.x < world) exchange_wait_flag(my_flags + slot0 + threadIdx.x, epoch, counters);
         __syncthreads();
     };
     if(blockIdx.x == 0 && (int)threadIdx.x < world)

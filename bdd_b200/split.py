@@ -147,7 +147,14 @@ def split_long_bdds(col: BddCollection, split_length: int, nr_variables: int = 0
     sinks = (instrs[:, 2] == BOTSINK, instrs[:, 2] == TOPSINK)
     for b in range(col.nr_bdds):
         first, last = int(delims[b]), int(delims[b + 1])
-        chunks, aux = split_qbdd(instrs, first, last, split_length, aux, base, sinks)
+        try:
+            chunks, aux_next = split_qbdd(instrs, first, last, split_length, aux, base, sinks)
+        except ValueError as e:
+            # a cut would land in front of a layer of width 1 (the reference asserts, bdd_collection.cpp:598): this BDD stays whole
+            import warnings
+            warnings.warn(f"split_long_bdds: BDD {b} left unsplit ({e})")
+            continue
+        aux = aux_next
         if len(chunks) > 1:
             removed[b] = True
             new_arrays.extend(chunks)
@@ -161,7 +168,17 @@ def split_long_bdds(col: BddCollection, split_length: int, nr_variables: int = 0
     return whole.select(keep), aux
 
 
-def compute_split_length(col: BddCollection, n_sms: int = 148, warps_per_sm: int = 16, min_length: int = 16) -> int:
+def _device_sm_count(default: int = 148) -> int:
+    try:
+        import torch
+        if torch.cuda.is_available():
+            return int(torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count)
+    except Exception:
+        pass
+    return default
+
+
+def compute_split_length(col: BddCollection, n_sms: int = 0, warps_per_sm: int = 16, min_length: int = 16) -> int:
     """Split length when the configuration gives none.  The reference's rule (compute_split_length, bdd_preprocessor.cpp:32-121) targets
     >= 50 % occupancy of its hop-synchronous kernels (nodes per hop against SMs x threads); the sweep here gives every warp a bundle of 32
     BDDs and walks it alone, so what long BDDs cost is (a) too few bundles to put ``warps_per_sm`` warps on every SM and (b) a pass that is
@@ -169,6 +186,8 @@ def compute_split_length(col: BddCollection, n_sms: int = 148, warps_per_sm: int
     (every cut adds a head and a tail gadget and width-many auxiliary variables); collections that already fill the GPU are not split.
     Returns sys.maxsize when nothing should be split."""
     import sys
+    if n_sms <= 0:
+        n_sms = _device_sm_count()          # the SM count of the current device (148 on B200 and where no device is visible)
     sizes = np.diff(col.delims.astype(np.int64)) - 2
     idx = col.instrs[:, 2]
     inner = idx < BOTSINK

@@ -58,7 +58,8 @@ typedef enum bddb200_status {
     BDDB200_ERR_NOT_QBDD = 3,       /* reference: assert(is_qbdd), bdd_cuda_base.cu:100-101 */
     BDDB200_ERR_TOO_WIDE = 4,       /* a BDD layer does not fit the shared-memory frontier  */
     BDDB200_ERR_STATE = 5,          /* e.g. backward_mm without a valid forward state (reference: assert, bdd_cuda_parallel_mma.cu:304) */
-    BDDB200_ERR_NO_DEVICE = 6
+    BDDB200_ERR_NO_DEVICE = 6,
+    BDDB200_ERR_EXCHANGE = 7        /* multi-GPU: a peer did not reach the exchange of a pass within the time limit */
 } bddb200_status;
 
 typedef enum bddb200_precision { BDDB200_FLOAT = 0, BDDB200_DOUBLE = 1 } bddb200_precision;
