@@ -29,6 +29,12 @@
 #pragma once
 
 #include <algorithm>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <climits>
 #include <cstddef>
 #include <cstdint>
@@ -161,6 +167,19 @@ struct HostLayout {
     std::vector<uint32_t> sorted_ext;    // external layers sorted by (var, bdd), terminals last
 };
 
+// BDDB200_LAYOUT_TIMING=1: phase durations of build_layout on stderr
+struct LayoutTimer {
+    bool on; std::chrono::steady_clock::time_point t;
+    LayoutTimer() : on(std::getenv("BDDB200_LAYOUT_TIMING") != nullptr), t(std::chrono::steady_clock::now()) {}
+    void lap(const char* what)
+    {
+        if(!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[bdd_b200 layout] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+        t = now;
+    }
+};
+
 inline uint32_t pow2ceil(uint32_t x) { uint32_t p = 1; while(p < x) p <<= 1; return p; }
 inline uint32_t ilog2(uint32_t x) { uint32_t l = 0; while((1u << l) < x) ++l; return l; }
 
@@ -182,53 +201,83 @@ inline HostLayout build_layout(const bddb200_instruction* instrs, size_t n_instr
 
     HostLayout L;
     L.n_bdds = n_bdds; L.n_instr = n_instr;
+    LayoutTimer timer;
 
     // ---- pass 1: layers of every BDD, validation, widths ------------------------------
     L.bdd_ext_begin.assign(n_bdds + 1, 0);
     std::vector<uint32_t> ext_first_instr;   // per external layer: first instruction; layer e spans [efi[e], efi[e+1])
     std::vector<uint32_t> bdd_maxw(n_bdds, 1);
     size_t max_var = 0;
-    for(size_t b = 0; b < n_bdds; ++b)
+    // errors found inside the parallel loops: the BDD with the smallest index reports (what a sequential scan would have found)
+    size_t err_bdd = (size_t)-1; int err_code = 0; std::string err_msg;
+    auto report = [&](size_t b, int code, const std::string& msg) {
+#pragma omp critical(bddb200_layout_error)
+        if(b < err_bdd) { err_bdd = b; err_code = code; err_msg = msg; }
+    };
+    // (a) layers per BDD
+    std::vector<uint32_t> n_ext_of(n_bdds, 0);
+    size_t n_real = 0;
+#pragma omp parallel for schedule(static) reduction(max : max_var) reduction(+ : n_real)
+    for(long long bb = 0; bb < (long long)n_bdds; ++bb)
     {
+        const size_t b = (size_t)bb;
         const size_t first = delims[b], last = delims[b+1];
-        if(last < first + 3) throw layout_error(BDDB200_ERR_INVALID_ARGUMENT, "BDD " + std::to_string(b) + " has no inner node");
+        if(last < first + 3) { report(b, BDDB200_ERR_INVALID_ARGUMENT, "BDD " + std::to_string(b) + " has no inner node"); continue; }
         // the two sinks close every BDD, in either order (bdd_collection.cpp:403-428 vs :1581-1586)
         if(!((instrs[last-2].index == BOTSINK && instrs[last-1].index == TOPSINK) || (instrs[last-2].index == TOPSINK && instrs[last-1].index == BOTSINK)))
-            throw layout_error(BDDB200_ERR_INVALID_ARGUMENT, "BDD " + std::to_string(b) + ": last two instructions must be the bot and top sink");
-        L.bdd_ext_begin[b] = (uint32_t)ext_first_instr.size();
+        { report(b, BDDB200_ERR_INVALID_ARGUMENT, "BDD " + std::to_string(b) + ": last two instructions must be the bot and top sink"); continue; }
+        size_t prev = TOPSINK;
+        uint32_t cnt = 0;
+        for(size_t i = first; i + 2 < last; ++i)
+        {
+            const size_t var = instrs[i].index;
+            if(var >= BOTSINK) { report(b, BDDB200_ERR_INVALID_ARGUMENT, "terminal instruction inside BDD " + std::to_string(b)); break; }
+            if(var != prev) { ++cnt; prev = var; if(var > max_var) max_var = var; }
+        }
+        n_ext_of[b] = cnt + 1;                               // + the terminal layer entry
+        n_real += last - first - 2;
+    }
+    if(err_code != 0) throw layout_error(err_code, err_msg);
+    L.n_real_nodes = n_real;
+    for(size_t b = 0; b < n_bdds; ++b) L.bdd_ext_begin[b + 1] = L.bdd_ext_begin[b] + n_ext_of[b];
+    L.n_layers_ext = L.bdd_ext_begin[n_bdds];
+    ext_first_instr.resize(L.n_layers_ext); L.ext_var.resize(L.n_layers_ext); L.ext_bdd.resize(L.n_layers_ext);
+    // (b) fill
+#pragma omp parallel for schedule(static)
+    for(long long bb = 0; bb < (long long)n_bdds; ++bb)
+    {
+        const size_t b = (size_t)bb;
+        const size_t first = delims[b], last = delims[b+1];
+        uint32_t e = L.bdd_ext_begin[b];
         size_t prev = TOPSINK;
         for(size_t i = first; i + 2 < last; ++i)
         {
             const size_t var = instrs[i].index;
-            if(var >= BOTSINK) throw layout_error(BDDB200_ERR_INVALID_ARGUMENT, "terminal instruction inside BDD " + std::to_string(b));
             if(var != prev)
             {
-                ext_first_instr.push_back((uint32_t)i);
-                L.ext_var.push_back((int32_t)var);
-                L.ext_bdd.push_back((int32_t)b);
-                prev = var;
-                if(var > max_var) max_var = var;
+                ext_first_instr[e] = (uint32_t)i; L.ext_var[e] = (int32_t)var; L.ext_bdd[e] = (int32_t)b;
+                ++e; prev = var;
             }
         }
-        ext_first_instr.push_back((uint32_t)(last - 2));   // terminal layer entry = end of the inner nodes
-        L.ext_var.push_back(INT_MAX);
-        L.ext_bdd.push_back((int32_t)b);
-        L.n_real_nodes += last - first - 2;
+        ext_first_instr[e] = (uint32_t)(last - 2);            // terminal layer entry = end of the inner nodes
+        L.ext_var[e] = INT_MAX; L.ext_bdd[e] = (int32_t)b;
     }
-    L.bdd_ext_begin[n_bdds] = (uint32_t)ext_first_instr.size();
-    L.n_layers_ext = ext_first_instr.size();
     L.n_vars = std::max(max_var + 1, nr_variables_override);
     if(L.n_vars > (size_t)INT_MAX / 2) throw layout_error(BDDB200_ERR_INVALID_ARGUMENT, "too many variables");
 
+    timer.lap("layers of every BDD");
     // QBDD check (reference: assert(is_qbdd && is_reordered), bdd_cuda_base.cu:100-101):
     // every arc of layer k enters layer k+1 or the bot sink; the top sink only from the last layer.
-    for(size_t b = 0; b < n_bdds; ++b)
+#pragma omp parallel for schedule(static)
+    for(long long bb = 0; bb < (long long)n_bdds; ++bb)
     {
+        const size_t b = (size_t)bb;
         const size_t last = delims[b+1];
         const size_t bot = instrs[last-2].index == BOTSINK ? last - 2 : last - 1, top = instrs[last-2].index == BOTSINK ? last - 1 : last - 2;
         const uint32_t eb = L.bdd_ext_begin[b], ee = L.bdd_ext_begin[b+1] - 1; // ee = terminal layer
         uint32_t maxw = 1;
-        for(uint32_t e = eb; e < ee; ++e)
+        bool bad = false;
+        for(uint32_t e = eb; e < ee && !bad; ++e)
         {
             const size_t lb = ext_first_instr[e], le = ext_first_instr[e+1];
             const bool last_layer = (e + 1 == ee);
@@ -239,14 +288,16 @@ inline HostLayout build_layout(const bddb200_instruction* instrs, size_t n_instr
                 for(const size_t c : {instrs[i].lo, instrs[i].hi})
                 {
                     if(c == bot) continue;
-                    if(last_layer ? (c != top) : !(c >= le && c < ne))
-                        throw layout_error(BDDB200_ERR_NOT_QBDD, "BDD " + std::to_string(b) + " is not a reordered QBDD (arc skips a layer)");
+                    if(last_layer ? (c != top) : !(c >= le && c < ne)) bad = true;
                 }
             }
         }
+        if(bad) report(b, BDDB200_ERR_NOT_QBDD, "BDD " + std::to_string(b) + " is not a reordered QBDD (arc skips a layer)");
         bdd_maxw[b] = maxw;
     }
+    if(err_code != 0) throw layout_error(err_code, err_msg);
 
+    timer.lap("QBDD check, widths");
     // ---- lanes per BDD, sort, bundles --------------------------------------------------
     std::vector<uint8_t> bdd_logP(n_bdds);
     for(size_t b = 0; b < n_bdds; ++b)
@@ -266,10 +317,27 @@ inline HostLayout build_layout(const bddb200_instruction* instrs, size_t n_instr
         if(bdd_logP[x] != bdd_logP[y]) return bdd_logP[x] < bdd_logP[y];
         return nlay(x) > nlay(y);
     });
-    std::stable_sort(lane_order.begin(), lane_order.end(), [&](uint32_t x, uint32_t y) {
-        if(bdd_maxw[x] != bdd_maxw[y]) return bdd_maxw[x] < bdd_maxw[y];
-        return nlay(x) > nlay(y);
-    });
+    {   // by (width ascending, number of layers descending), stable: a counting sort when the key range is small (it always is for
+        // lane-class BDDs: width <= LANE_MAX_J), else a comparison sort
+        uint32_t max_lay = 0;
+        for(const uint32_t b : lane_order) max_lay = std::max(max_lay, nlay(b));
+        const size_t n_keys = (size_t)(LANE_MAX_J + 1) * (max_lay + 1);
+        if(n_keys <= ((size_t)1 << 24))
+        {
+            auto key = [&](uint32_t b) { return (size_t)bdd_maxw[b] * (max_lay + 1) + (max_lay - nlay(b)); };
+            std::vector<uint32_t> count(n_keys + 1, 0);
+            for(const uint32_t b : lane_order) count[key(b) + 1]++;
+            for(size_t k = 0; k < n_keys; ++k) count[k + 1] += count[k];
+            std::vector<uint32_t> sorted(lane_order.size());
+            for(const uint32_t b : lane_order) sorted[count[key(b)]++] = b;
+            lane_order.swap(sorted);
+        }
+        else
+            std::stable_sort(lane_order.begin(), lane_order.end(), [&](uint32_t x, uint32_t y) {
+                if(bdd_maxw[x] != bdd_maxw[y]) return bdd_maxw[x] < bdd_maxw[y];
+                return nlay(x) > nlay(y);
+            });
+    }
     const size_t n_generic_bdds = order.size();
 
     struct ProtoChunk { uint32_t first, n, J; };
@@ -394,6 +462,7 @@ inline HostLayout build_layout(const bddb200_instruction* instrs, size_t n_instr
     }
     std::stable_sort(lane_protos.begin(), lane_protos.end(), [](const LaneProto& x, const LaneProto& y) { return x.n_hops * x.J > y.n_hops * y.J; });
 
+    timer.lap("sort, bundles");
     // ---- emit: generic bundles own the first slots (topo is indexed by slot there), lane-class
     // bundles follow; in bundle order the lane class comes first -------------------------------
     std::vector<BundleDesc> generic_bundles;
@@ -493,6 +562,7 @@ inline HostLayout build_layout(const bddb200_instruction* instrs, size_t n_instr
     L.n_slots = slot; L.n_lay = lay;
     if(lay > 0xFFFFFFF0ull) throw layout_error(BDDB200_ERR_INVALID_ARGUMENT, "collection too large (layer index overflow)");
 
+    timer.lap("emit bundles");
     L.topo.assign(L.n_topo, TOPO_PAD);
     for(size_t g = 0; g < L.n_lane_bundles; ++g)
         std::fill(L.topo.begin() + L.bundles[g].topo_base, L.topo.begin() + L.bundles[g].topo_base + 32ull * L.bundles[g].n_hops, 0u);
@@ -502,8 +572,10 @@ inline HostLayout build_layout(const bddb200_instruction* instrs, size_t n_instr
     L.top_slot.assign(n_bdds, 0);
     L.nr_bdds_per_var.assign(L.n_vars, 0);
 
-    for(size_t g = 0; g < L.bundles.size(); ++g)
+#pragma omp parallel for schedule(dynamic, 64)
+    for(long long gg = 0; gg < (long long)L.bundles.size(); ++gg)
     {
+        const size_t g = (size_t)gg;
         const BundleDesc& bd = L.bundles[g];
         const bool lane_cls = bd.cls == CLS_LANE;
         const uint32_t logP = bd.logP, P = 1u << logP, bpw = 32u >> logP;
@@ -532,7 +604,6 @@ inline HostLayout build_layout(const bddb200_instruction* instrs, size_t n_instr
                 const size_t lb = ext_first_instr[e], le = ext_first_instr[e+1];
                 const size_t next_first = le;   // first instruction of the next layer (or the bot sink)
                 L.lay_var[layer_entry] = L.ext_var[e];
-                L.nr_bdds_per_var[L.ext_var[e]]++;
                 if(k == 0) L.root_slot[b] = hr.node_off + tile_slot(0);
                 if(lane_cls)
                 {
@@ -565,24 +636,42 @@ inline HostLayout build_layout(const bddb200_instruction* instrs, size_t n_instr
         }
     }
 
+    timer.lap("topology, layer entries");
     // ---- variable -> layers (sorted by variable, then BDD index) ------------------------
     L.var_lay_begin.assign(L.n_vars + 1, 0);
     for(size_t e = 0; e < L.n_layers_ext; ++e)
         if(L.ext_var[e] != INT_MAX) L.var_lay_begin[L.ext_var[e] + 1]++;
+    for(size_t v = 0; v < L.n_vars; ++v) L.nr_bdds_per_var[v] = (int32_t)L.var_lay_begin[v + 1];      // in how many BDDs the variable occurs
     for(size_t v = 0; v < L.n_vars; ++v) L.var_lay_begin[v+1] += L.var_lay_begin[v];
     L.var_lay.assign(L.var_lay_begin[L.n_vars], 0);
     L.sorted_ext.assign(L.n_layers_ext, 0);
-    {
-        std::vector<uint32_t> fill(L.var_lay_begin.begin(), L.var_lay_begin.end() - 1);
-        size_t term = L.var_lay_begin[L.n_vars];
-        for(size_t e = 0; e < L.n_layers_ext; ++e)   // external order is BDD-major => BDD index ascending per variable
+    {   // external order is BDD-major => BDD index ascending per variable.  Every thread owns a range of variables and walks ALL external
+        // layers in order, keeping those of its range: reads are repeated per thread, writes are disjoint and in order (stable).
+        int n_threads = 1;
+#ifdef _OPENMP
+        n_threads = std::max(1, std::min(omp_get_max_threads(), 16));
+#endif
+        const size_t n_inner = L.var_lay_begin[L.n_vars];
+#pragma omp parallel for schedule(static, 1) num_threads(n_threads)
+        for(int t = 0; t < n_threads; ++t)
         {
-            if(L.ext_var[e] == INT_MAX) { L.sorted_ext[term++] = (uint32_t)e; continue; }
-            const uint32_t p = fill[L.ext_var[e]]++;
-            L.var_lay[p] = L.ext2lay[e];
-            L.sorted_ext[p] = (uint32_t)e;
+            const size_t v0 = L.n_vars * (size_t)t / n_threads, v1 = L.n_vars * (size_t)(t + 1) / n_threads;
+            if(v0 >= v1) continue;
+            std::vector<uint32_t> fill(L.var_lay_begin.begin() + v0, L.var_lay_begin.begin() + v1);
+            for(size_t e = 0; e < L.n_layers_ext; ++e)
+            {
+                const int32_t var = L.ext_var[e];
+                if(var == INT_MAX || (size_t)var < v0 || (size_t)var >= v1) continue;
+                const uint32_t p = fill[var - v0]++;
+                L.var_lay[p] = L.ext2lay[e];
+                L.sorted_ext[p] = (uint32_t)e;
+            }
         }
+        // terminal layers last, in BDD order
+        size_t term = n_inner;
+        for(size_t b = 0; b < n_bdds; ++b) L.sorted_ext[term++] = L.bdd_ext_begin[b + 1] - 1;
     }
+    timer.lap("variable -> layers");
     return L;
 }
 
