@@ -103,6 +103,7 @@ struct bddb200_solver {
     virtual void* delta_sum_buffer() = 0;
     virtual int rounding_perturb(double delta, int round_index, unsigned long long counts_out[4], char* types_dev, char* sol_host) = 0;
     virtual int delta_sum_index() const = 0;
+    virtual int push_exchange_supported() const = 0;
     virtual void set_delta_buffers(void* b0, void* b1, void* b2) = 0;
     virtual void set_delta_input(void* in, size_t n_shared_vars) = 0;
     virtual void set_exchange(int world, int rank, const void* const* peers, uint32_t* const* flags, void* out, void* const* outs,
@@ -347,6 +348,7 @@ public:
             a.zero_pairs_per_bundle = (uint32_t)((n_vars_ + n_lane_ - 1) / n_lane_);
             a.n_classes = (uint32_t)lane_cls_begin_.size();
             for(size_t c = 0; c < lane_cls_begin_.size(); ++c) { a.cls_first[c] = lane_cls_first_[c]; a.cls_begin[c] = lane_cls_begin_[c]; }
+            if(MODE == MODE_MMA && a.push_counters != nullptr) { a.desc = reinterpret_cast<const uint32_t*>(d_desc_push_.p); a.n_classes = 0; }     // permuted launch order
             // programmatic dependent launch: the kernel's start-up (descriptor, static topology, variable indices) overlaps the
             // tail of the previous kernel in the stream; it waits (griddepcontrol.wait) before touching anything a pass writes
             cudaLaunchConfig_t cfg{};
@@ -356,7 +358,12 @@ public:
             attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             attr[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr; cfg.numAttrs = pdl_ ? 1 : 0;
-            if(MODE == MODE_MMA && !deterministic_ && lane_dense_) CUDA_CHECK(cudaLaunchKernelEx(&cfg, sweep_lane_kernel<REAL, MODE_MMA, FORWARD, false, 768>, a));
+            if(MODE == MODE_MMA && a.push_counters != nullptr)
+            {   // multi-GPU push exchange: the pass adds the shared variables' differences to every rank's buffer itself
+                if(lane_dense_) CUDA_CHECK(cudaLaunchKernelEx(&cfg, sweep_lane_kernel<REAL, MODE_MMA, FORWARD, false, 768, true>, a));
+                else CUDA_CHECK(cudaLaunchKernelEx(&cfg, sweep_lane_kernel<REAL, MODE_MMA, FORWARD, false, BDDB200_LANE_MAX_THREADS, true>, a));
+            }
+            else if(MODE == MODE_MMA && !deterministic_ && lane_dense_) CUDA_CHECK(cudaLaunchKernelEx(&cfg, sweep_lane_kernel<REAL, MODE_MMA, FORWARD, false, 768>, a));
             else if(MODE == MODE_MMA && deterministic_) CUDA_CHECK(cudaLaunchKernelEx(&cfg, sweep_lane_kernel<REAL, MODE, FORWARD, MODE == MODE_MMA>, a));
             else CUDA_CHECK(cudaLaunchKernelEx(&cfg, sweep_lane_kernel<REAL, MODE, FORWARD, false>, a));
             ++launches_;
@@ -587,6 +594,10 @@ public:
             CUDA_CHECK(cudaFuncSetAttribute(sweep_lane_kernel<REAL, MODE_MM, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need_lane));
             CUDA_CHECK(cudaFuncSetAttribute(sweep_lane_kernel<REAL, MODE_MMA, true, false, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, need_lane));
             CUDA_CHECK(cudaFuncSetAttribute(sweep_lane_kernel<REAL, MODE_MMA, false, false, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, need_lane));
+            CUDA_CHECK(cudaFuncSetAttribute(sweep_lane_kernel<REAL, MODE_MMA, true, false, 768, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, need_lane));
+            CUDA_CHECK(cudaFuncSetAttribute(sweep_lane_kernel<REAL, MODE_MMA, false, false, 768, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, need_lane));
+            CUDA_CHECK(cudaFuncSetAttribute(sweep_lane_kernel<REAL, MODE_MMA, true, false, BDDB200_LANE_MAX_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, need_lane));
+            CUDA_CHECK(cudaFuncSetAttribute(sweep_lane_kernel<REAL, MODE_MMA, false, false, BDDB200_LANE_MAX_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, need_lane));
         }
         const int need = (int)(INV_TAB_BYTES + std::max<size_t>((size_t)warps_per_cta_ * warp_smem_small_, warp_smem_large_));
         if(need > 48 * 1024)
@@ -626,6 +637,18 @@ public:
         a.delta_in = delta_in; a.delta_out = delta_out; a.zero_buf = zero_buf;
         const bool own_sums = delta_in_override_ != nullptr && delta_in == dbuf(dcur_);     // not for forward_mm / backward_mm on a caller's vector
         a.delta_in_shared = own_sums ? delta_in_override_ : delta_in; a.n_shared_vars = own_sums ? (uint32_t)n_shared_vars_ : 0u;
+        if(xc_.mode == 4 && delta_in == dbuf(dcur_) && delta_out == dbuf((dcur_ + 1) % 3))
+        {   // push exchange: shared variables' differences go to every rank's buffer through the multicast mapping; the flag barrier
+            // is the tail of this launch and the prologue of the next one
+            a.delta_out_mc = const_cast<REAL*>(xc_.mc_in) + (delta_out - dbuf(0));
+            a.n_push_vars = (uint32_t)(xc_.n_exchange / 2);
+            a.push_counters = d_xc_counters_.p; a.push_flags = xc_.flags; a.push_my_flags = xc_.my_flags;
+            a.push_world = xc_.world; a.push_rank = xc_.rank;
+            // this pass ends push barrier number e (counted mod 3: a rank is never more than one barrier ahead of a peer)
+            const uint32_t e = (xc_phase_ + 1u) % 3u;
+            a.push_send_phase = e; a.push_stale_phase = (e + 1u) % 3u;       // stale = the barrier before the previous one
+            xc_phase_ = e;
+        }
         a.normalize_in = !normalize_in ? NORM_NONE : (deterministic_ ? NORM_DIVIDE : NORM_RECIPROCAL);
         a.accumulate = deterministic_ ? 0 : 1;
         launch_sweep<MODE_MMA, FORWARD>(a);
@@ -662,16 +685,57 @@ public:
         if(mode == 0) { xc_ = Xchg{}; return; }
         if(world < 2 || world > EXCHANGE_MAX_WORLD || rank < 0 || rank >= world || flags == nullptr || (n_exchange & 1) || n_exchange > 2 * n_vars_ || ext_delta_[0] == nullptr)
             throw api_error(BDDB200_ERR_INVALID_ARGUMENT, "set_exchange: invalid argument (the sum buffers must be set with set_delta_buffers first)");
-        if((mode == 1 && (peers == nullptr || out == nullptr)) || (mode == 2 && (peers == nullptr || outs == nullptr)) || (mode == 3 && (mc_in == nullptr || mc_out == nullptr)) || mode < 0 || mode > 3)
+        if((mode == 1 && (peers == nullptr || out == nullptr)) || (mode == 2 && (peers == nullptr || outs == nullptr)) || (mode == 3 && (mc_in == nullptr || mc_out == nullptr))
+           || (mode == 4 && mc_in == nullptr) || mode < 0 || mode > 4)
             throw api_error(BDDB200_ERR_INVALID_ARGUMENT, "set_exchange: buffers missing for the requested mode");
+        if(mode == 4 && (deterministic_ || n_lane_ != n_bundles_ || delta_in_override_ != nullptr))
+            throw api_error(BDDB200_ERR_STATE, "set_exchange: the push exchange needs the default (atomic) sums, a collection of lane-class bundles only and no separate input buffer");
         xc_.world = world; xc_.rank = rank; xc_.peers = peers; xc_.flags = flags; xc_.out = static_cast<REAL*>(out); xc_.outs = outs;
         xc_.mc_in = static_cast<const REAL*>(mc_in); xc_.mc_out = static_cast<REAL*>(mc_out); xc_.n_exchange = n_exchange; xc_.mode = mode;
-        if(d_xc_counters_.n == 0) d_xc_counters_.alloc(8);
+        if(d_xc_counters_.n < 8 + 2 * PUSH_SLOTS) d_xc_counters_.alloc(8 + 2 * PUSH_SLOTS);
         d_xc_counters_.zero(stream_);
+        xc_phase_ = 0;
+        if(mode == 4)
+        {   // this rank's own flag array (the passes poll it; peers write it), and which bundles take part in the flag barrier
+            CUDA_CHECK(cudaMemcpyAsync(&xc_.my_flags, flags + rank, sizeof(uint32_t*), cudaMemcpyDeviceToHost, stream_));
+            DevBuf<unsigned char> d_shared; d_shared.alloc(n_lane_);
+            push_mark_bundles_kernel<<<blocks_for(n_lane_, 8), 256, 0, stream_>>>(d_desc_lane_.p, d_lay_vn_.p, (uint32_t)n_lane_, (uint32_t)(n_exchange / 2), d_shared.p);
+            CUDA_CHECK(cudaGetLastError());
+            std::vector<unsigned char> h_shared(n_lane_);
+            std::vector<LaneDesc> h_desc(n_lane_), h_push(n_lane_);
+            CUDA_CHECK(cudaMemcpyAsync(h_shared.data(), d_shared.p, n_lane_, cudaMemcpyDeviceToHost, stream_));
+            CUDA_CHECK(cudaMemcpyAsync(h_desc.data(), d_desc_lane_.p, n_lane_ * sizeof(LaneDesc), cudaMemcpyDeviceToHost, stream_));
+            CUDA_CHECK(cudaStreamSynchronize(stream_));
+            // launch order of the push builds: bundles with a shared variable first
+            size_t k = 0;
+            for(size_t g = 0; g < n_lane_; ++g) if(h_shared[g]) { h_push[k] = h_desc[g]; h_push[k].pad_[0] = 1; ++k; }
+            const size_t n_with_shared = k;
+            for(size_t g = 0; g < n_lane_; ++g) if(!h_shared[g]) { h_push[k] = h_desc[g]; h_push[k].pad_[0] = 0; ++k; }
+            d_desc_push_.upload(h_push, stream_);
+            // how many bundles count themselves per slot of the pass-end barrier (the predicate of sweep_lane_kernel)
+            const size_t zpb = (n_vars_ + n_lane_ - 1) / n_lane_;
+            std::vector<uint32_t> h_cnt(8 + 2 * PUSH_SLOTS, 0u);
+            for(size_t g = 0; g < n_lane_; ++g)
+                if(g < n_with_shared || g == 0 || g * zpb < n_exchange / 2) ++h_cnt[8 + PUSH_SLOTS + g % PUSH_SLOTS];
+            for(int sl = 0; sl < PUSH_SLOTS; ++sl) h_cnt[3] += h_cnt[8 + PUSH_SLOTS + sl] != 0;
+            CUDA_CHECK(cudaMemcpyAsync(d_xc_counters_.p, h_cnt.data(), h_cnt.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream_));
+            CUDA_CHECK(cudaStreamSynchronize(stream_));
+        }
+    }
+    // push exchange: the sums of the last pass are complete on this rank once every peer has finished that pass (what = 1); before the
+    // peers may push into buffers this rank has cleared outside a pass they must hear about it (what = 2)
+    void push_barrier(int what)
+    {
+        if(xc_.mode != 4) return;
+        const uint32_t stale = (xc_phase_ + 2u) % 3u, send = (xc_phase_ + 1u) % 3u;
+        push_barrier_kernel<<<1, 32, 0, stream_>>>(d_xc_counters_.p, xc_.flags, xc_.my_flags, xc_.world, xc_.rank, what, stale, send);
+        if(what & 2) xc_phase_ = send;
+        ++launches_;
+        CUDA_CHECK(cudaGetLastError());
     }
     void launch_exchange()
     {
-        if(xc_.n_exchange == 0) return;
+        if(xc_.n_exchange == 0 || xc_.mode == 4) return;       // push exchange: done by the pass itself
         const size_t offset = (size_t)(dbuf(dcur_) - dbuf(0));       // the sums of the pass just made, relative to the start of the symmetric block
         const size_t pairs = xc_.n_exchange / 2;
         // programmatic dependent launch, like the sweeps: the exchange sets itself up under the tail of the pass and the next pass under the exchange
@@ -735,7 +799,7 @@ public:
         const size_t per_graph = 3;
         if(n >= per_graph)
         {
-            if(graph_exec_ == nullptr || graph_omega_ != omega || graph_dcur_ != dcur_ || graph_cc_ != cc_ || graph_norm_ != delta_needs_norm_)
+            if(graph_exec_ == nullptr || graph_omega_ != omega || graph_dcur_ != dcur_ || graph_cc_ != cc_ || graph_norm_ != delta_needs_norm_ || graph_phase_ != xc_phase_)
             {
                 if(graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
                 if(!delta_needs_norm_)
@@ -755,7 +819,7 @@ public:
                 launches_ = launches_before;
                 CUDA_CHECK(cudaGraphInstantiate(&graph_exec_, graph, 0));
                 cudaGraphDestroy(graph);
-                graph_omega_ = omega; graph_dcur_ = dcur_; graph_cc_ = cc_; graph_norm_ = delta_needs_norm_;
+                graph_omega_ = omega; graph_dcur_ = dcur_; graph_cc_ = cc_; graph_norm_ = delta_needs_norm_; graph_phase_ = xc_phase_;     // six passes: the phase is back where it was
             }
             while(n >= per_graph && graph_exec_ != nullptr)
             {
@@ -806,6 +870,7 @@ public:
     {
         set_device();
         ensure_sums();
+        push_barrier(1);
         const REAL* src = dbuf(dcur_);
         if(delta_in_override_ && n_shared_vars_ > 0)
         {   // exchanged sums of the shared variables, local sums of the rest
@@ -823,8 +888,9 @@ public:
         if(out_is_host) CUDA_CHECK(cudaStreamSynchronize(stream_));
     }
 
-    void* delta_sum_buffer() override { set_device(); ensure_sums(); return dbuf(dcur_); }
+    void* delta_sum_buffer() override { set_device(); ensure_sums(); push_barrier(1); return dbuf(dcur_); }
     int delta_sum_index() const override { return dcur_; }
+    int push_exchange_supported() const override { return !deterministic_ && n_lane_ == n_bundles_ ? 1 : 0; }
     // Multi-GPU exchange over peer memory: the three rotating sum buffers live in caller-owned (symmetric) memory, and the
     // passes read the exchanged sums from a separate buffer (bddb200_delta_exchange writes it).
     void set_delta_buffers(void* b0, void* b1, void* b2) override
@@ -1023,7 +1089,7 @@ public:
             }
         }
         ensure_sums();
-        StepKey key{dcur_, cc_, delta_needs_norm_, omega, n_lo, n_hi, n_lo ? src_lo : nullptr, n_hi ? src_hi : nullptr};
+        StepKey key{dcur_, cc_, delta_needs_norm_, omega, n_lo, n_hi, n_lo ? src_lo : nullptr, n_hi ? src_hi : nullptr, xc_phase_};
         StepGraph* g = nullptr;
         for(StepGraph& c : step_graphs_) if(c.key == key) g = &c;
         if(g == nullptr)
@@ -1031,7 +1097,7 @@ public:
             if(step_graphs_.size() >= 24) { for(StepGraph& c : step_graphs_) cudaGraphExecDestroy(c.exec); step_graphs_.clear(); }
             cudaGraph_t graph = nullptr;
             const size_t launches_before = launches_;
-            const int dcur0 = dcur_, cc0 = cc_; const bool norm0 = delta_needs_norm_;
+            const int dcur0 = dcur_, cc0 = cc_; const bool norm0 = delta_needs_norm_; const uint32_t phase0 = xc_phase_;
             lb_sum_clean_ = false;           // the captured backward sweep clears the partial sums itself, whatever ran before a replay
             CUDA_CHECK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
             if(n_lo + n_hi > 0)
@@ -1052,11 +1118,12 @@ public:
             cudaGraphDestroy(graph);
             step_graphs_.push_back(ng);
             g = &step_graphs_.back();
-            dcur_ = dcur0; cc_ = cc0; delta_needs_norm_ = norm0;      // the capture only recorded the step
+            dcur_ = dcur0; cc_ = cc0; delta_needs_norm_ = norm0; xc_phase_ = phase0;      // the capture only recorded the step
         }
         CUDA_CHECK(cudaGraphLaunch(g->exec, stream_));
         launches_ += g->launches;
         dcur_ = (dcur_ + 2) % 3; delta_needs_norm_ = true;          // two passes; the cost buffers swap twice
+        if(xc_.mode == 4) xc_phase_ = (xc_phase_ + 2u) % 3u;
         forward_valid_ = false; backward_valid_ = true; lb_sum_clean_ = false; lb_from_resident_ = false;
         CUDA_CHECK(cudaStreamSynchronize(stream_));
         lb_ = 0.0;
@@ -1094,8 +1161,10 @@ public:
         distribute_kernel<REAL><<<blocks_for(n_lay_), 256, 0, stream_>>>(d_lay_vn_.p, d_lohi_[cc_].p, d_mmd_.p, (uint32_t)n_lay_);
         ++launches_;
         CUDA_CHECK(cudaGetLastError());
+        push_barrier(1);        // no peer is still adding to these buffers ...
         for(int i = 0; i < 3; ++i) CUDA_CHECK(cudaMemsetAsync(dbuf(i), 0, sizeof(REAL) * 2 * n_vars_, stream_));
         if(delta_in_override_) CUDA_CHECK(cudaMemsetAsync(delta_in_override_, 0, sizeof(REAL) * 2 * n_shared_vars_, stream_));
+        push_barrier(2);        // ... and none starts again before they are clear
         delta_needs_norm_ = false; exch_in_contrib_ = false;
         flush_forward(); flush_backward();
     }
@@ -1255,11 +1324,14 @@ private:
     REAL* dbuf(int i) const { return ext_delta_[i] ? ext_delta_[i] : d_delta_[i].p; }
     REAL* ext_delta_[3] = {nullptr, nullptr, nullptr};
     struct Xchg {
-        int world = 0, rank = 0, mode = 0;         // mode: 0 off, 1 one-shot, 2 two-shot, 3 in-switch (multicast)
+        int world = 0, rank = 0, mode = 0;         // mode: 0 off, 1 one-shot, 2 two-shot, 3 in-switch (multicast), 4 push (multimem.red inside the pass)
+        uint32_t* my_flags = nullptr;
         const void* const* peers = nullptr; uint32_t* const* flags = nullptr; void* const* outs = nullptr;
         REAL* out = nullptr; const REAL* mc_in = nullptr; REAL* mc_out = nullptr; size_t n_exchange = 0;
     } xc_;
-    DevBuf<uint32_t> d_xc_counters_;         // {exchanges completed, CTAs finished}: the device-side epoch of the exchange kernels
+    DevBuf<uint32_t> d_xc_counters_;         // {exchanges completed, CTAs finished, error, ...}: the device-side epoch of the exchange kernels; push exchange: CTA counts
+    uint32_t xc_phase_ = 0;                  // push exchange: number of push barriers issued so far, mod 3
+    DevBuf<LaneDesc> d_desc_push_;           // push exchange: the lane-class bundle descriptors in launch order (bundles with a variable shared between shards first, marked)
     REAL* delta_in_override_ = nullptr;      // exchanged sums of the variables [0, n_shared_vars_)
     size_t n_shared_vars_ = 0;
     DevBuf<REAL> d_delta_tmp2_;
@@ -1324,15 +1396,16 @@ private:
     mutable size_t launches_ = 0;
 
     struct StepKey {
-        int dcur, cc; bool norm; double omega; size_t n_lo, n_hi; const void* src_lo; const void* src_hi;
+        int dcur, cc; bool norm; double omega; size_t n_lo, n_hi; const void* src_lo; const void* src_hi; uint32_t phase;
         bool operator==(const StepKey& o) const
-        { return dcur == o.dcur && cc == o.cc && norm == o.norm && omega == o.omega && n_lo == o.n_lo && n_hi == o.n_hi && src_lo == o.src_lo && src_hi == o.src_hi; }
+        { return dcur == o.dcur && cc == o.cc && norm == o.norm && omega == o.omega && n_lo == o.n_lo && n_hi == o.n_hi && src_lo == o.src_lo && src_hi == o.src_hi && phase == o.phase; }
     };
     struct StepGraph { StepKey key; cudaGraphExec_t exec = nullptr; size_t launches = 0; };
     std::vector<StepGraph> step_graphs_;      // step_host: one graph per rotation state of the sum buffers
     cudaGraphExec_t graph_exec_ = nullptr;
     double graph_omega_ = 0.0;
     int graph_dcur_ = 0, graph_cc_ = 0;
+    uint32_t graph_phase_ = 0;
     bool graph_norm_ = false;
     size_t graph_launches_ = 0;
 };
@@ -1553,6 +1626,7 @@ int bddb200_lbfgs_stats(const bddb200_lbfgs* l, size_t* lbfgs_iterations, size_t
 }
 
 int bddb200_delta_sum_index(const bddb200_solver* s, int* out) { REQUIRE_SOLVER(s); return guarded([&] { *out = s->delta_sum_index(); }); }
+int bddb200_push_exchange_supported(const bddb200_solver* s, int* out) { REQUIRE_SOLVER(s); return guarded([&] { *out = s->push_exchange_supported(); }); }
 int bddb200_set_delta_buffers(bddb200_solver* s, void* b0, void* b1, void* b2)
 {
     REQUIRE_SOLVER(s);

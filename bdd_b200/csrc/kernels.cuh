@@ -168,6 +168,21 @@ struct SweepArgs {
     unsigned long long* trace; // diagnostics: TRACE_EVENTS clock64() stamps per bundle (null = off)
     int normalize_in;          // divide delta_in by nr_bdds(var) while reading
     int accumulate;            // add |mm_diff| to delta_out with atomics
+    // multi-GPU push exchange (lane-class kernel, PUSH build): the |mm_diff| of the variables [0, n_push_vars) -- those that occur in
+    // more than one shard -- is added to EVERY rank's sum buffer by one multimem.red through the multicast mapping of the symmetric
+    // buffers (the NVSwitch replicates the reduction): each rank's own buffer holds the global sums, there is no exchange kernel and
+    // no second buffer.  Only the bundles that contain such a variable (push_bundle_shared, static) take part in the flag barrier:
+    // they wait for the peers' flags before they read sums, and when the last of them (and of the bundles that clear the shared
+    // prefix of the next buffer) has finished, the peers are told -- all other bundles of pass p + 1 overlap the tail of pass p as
+    // on one GPU.  Flags carry the barrier's ordinal mod 3 (a rank is never more than one barrier ahead of a peer), known to the host.
+    REAL* delta_out_mc;        // multicast address of delta_out
+    uint32_t n_push_vars;
+    uint32_t* push_counters;       // [1] slots completed, [2] error, [3] slots in use, [8 + s] counted bundles of slot s finished, [8 + PUSH_SLOTS + s] how many there are
+    uint32_t* const* push_flags;   // device array: entry r = rank r's flag array as mapped here
+    uint32_t* push_my_flags;       // this rank's flag array (slot r is written by rank r)
+    int push_world, push_rank;
+    uint32_t push_stale_phase;     // a peer whose flag still shows this value has not finished the pass before this one
+    uint32_t push_send_phase;      // what this pass stores into the peers' flag arrays when its counted bundles are done
 };
 
 template<int P, typename REAL>
@@ -820,6 +835,67 @@ __device__ __forceinline__ void red_add_if(bool p, double* addr, double v)
                  :: "r"((uint32_t)p), "l"(__cvta_generic_to_global(addr)), "d"(v) : "memory");
 }
 
+// Waiting for a peer is bounded by wall-clock time, not by a spin count: a peer that is merely late (a host stall, a debugger, an extra
+// synchronisation on one rank) must not kill this rank's context.  After EXCHANGE_TIMEOUT_NS the waiter records the failure in
+// counters[2] (the host turns it into BDDB200_ERR_EXCHANGE at its next synchronisation) and gives up waiting.
+constexpr unsigned long long EXCHANGE_TIMEOUT_NS = 30ull * 1000ull * 1000ull * 1000ull;
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void exchange_wait_flag(const uint32_t* flag, uint32_t epoch, uint32_t* counters)
+{
+    uint32_t seen;
+    unsigned long long t0 = 0;
+    for(uint32_t spins = 0;; ++spins)
+    {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+        if((int32_t)(seen - epoch) >= 0) return;
+        if((spins & 1023u) == 1023u)
+        {
+            const unsigned long long now = global_timer_ns();
+            if(t0 == 0) t0 = now;
+            else if(now - t0 > EXCHANGE_TIMEOUT_NS)
+            {
+                if(counters != nullptr) atomicExch(counters + 2, 1u); else __trap();
+                return;
+            }
+        }
+    }
+}
+
+constexpr int PUSH_SLOTS = 64;
+// push exchange: wait while the peer's flag still shows `stale` (the phase before the one waited for)
+__device__ __forceinline__ void push_wait_flag(const uint32_t* flag, uint32_t stale, uint32_t* counters)
+{
+    uint32_t seen;
+    unsigned long long t0 = 0;
+    for(uint32_t spins = 0;; ++spins)
+    {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+        if(seen != stale) return;
+        if((spins & 1023u) == 1023u)
+        {
+            const unsigned long long now = global_timer_ns();
+            if(t0 == 0) t0 = now;
+            else if(now - t0 > EXCHANGE_TIMEOUT_NS) { atomicExch(counters + 2, 1u); return; }
+        }
+    }
+}
+
+// the same reduction performed on every rank's copy of a symmetric buffer (addr = multicast address), in the switch.
+// A branch, not a predicate: ptxas 12.9 drops the guard of a predicated multimem.red (the SASS REDG is unconditional).
+__device__ __forceinline__ void mc_red_add_if(bool p, float* addr, float v)
+{
+    if(p) asm volatile("multimem.red.relaxed.sys.global.add.f32 [%0], %1;" :: "l"(__cvta_generic_to_global(addr)), "f"(v) : "memory");
+}
+__device__ __forceinline__ void mc_red_add_if(bool p, double* addr, double v)
+{
+    if(p) asm volatile("multimem.red.relaxed.sys.global.add.f64 [%0], %1;" :: "l"(__cvta_generic_to_global(addr)), "d"(v) : "memory");
+}
+
 // programmatic dependent launch: everything before pdl_wait() may overlap the tail of the previous kernel in
 // the stream and must not touch anything that kernel reads or writes
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -840,8 +916,9 @@ constexpr int LANE_MAX_STAGES = 4;
 #define BDDB200_LANE_UNROLL 2
 #endif
 
-template<typename REAL, int J, int MODE, bool FORWARD, bool DET>
-__device__ __forceinline__ void sweep_lane_bundle(const SweepArgs<REAL>& a, const LaneDesc d, const uint32_t bundle_in_launch, unsigned char* wsm, uint64_t* bars, const REAL* inv_tab, const int lane)
+template<typename REAL, int J, int MODE, bool FORWARD, bool DET, bool PUSH = false>
+__device__ __forceinline__ void sweep_lane_bundle(const SweepArgs<REAL>& a, const LaneDesc d, const uint32_t bundle_in_launch, unsigned char* wsm, uint64_t* bars, const REAL* inv_tab, const int lane,
+                                                  const bool waits_for_peers = false)
 {
     using R2 = typename real2<REAL>::type;
     using In = LaneHopIn<REAL, J>;
@@ -945,6 +1022,11 @@ __device__ __forceinline__ void sweep_lane_bundle(const SweepArgs<REAL>& a, cons
     pdl_wait();
     pdl_launch_dependents();
     stamp();       // 4: previous kernel complete
+    if(PUSH && waits_for_peers)
+    {   // this bundle reads sums the peers add to: complete once every peer's flag has left the phase before the previous pass's
+        if(lane < a.push_world && lane != a.push_rank) push_wait_flag(a.push_my_flags + lane, a.push_stale_phase, a.push_counters);
+        __syncwarp();
+    }
     issue(0, 1, COPY_ALL);
     stamp();       // 5: bulk copies of the first chunk issued
     R2 dl0[G0];
@@ -1148,7 +1230,17 @@ __device__ __forceinline__ void sweep_lane_bundle(const SweepArgs<REAL>& a, cons
                 g_lohi[h * 32] = o;
                 g_mmd[h * 32] = diff;
                 // compute_delta_atomic, bdd_cuda_parallel_mma.cu:358-376: |diff| goes to the hi slot if diff > 0, else to lo
-                if(!DET) red_add_if(diff != 0, a.delta_out + 2 * (size_t)max(x.var, 0) + (diff > 0 ? 1 : 0), fabs(diff));
+                if(!DET)
+                {
+                    const size_t slot = 2 * (size_t)max(x.var, 0) + (diff > 0 ? 1 : 0);
+                    if(PUSH)
+                    {   // shared between shards: one reduction on every rank's buffer; everything else stays on this GPU
+                        const bool shared = (uint32_t)x.var < a.n_push_vars;
+                        mc_red_add_if(diff != 0 && shared, a.delta_out_mc + slot, fabs(diff));
+                        red_add_if(diff != 0 && !shared, a.delta_out + slot, fabs(diff));
+                    }
+                    else red_add_if(diff != 0, a.delta_out + slot, fabs(diff));
+                }
             }
         }
 
@@ -1178,7 +1270,7 @@ __device__ __forceinline__ void sweep_lane_bundle(const SweepArgs<REAL>& a, cons
 // MAXT = BDDB200_LANE_MAX_THREADS: up to 16 warps per SM at up to 128 registers per thread.
 // MAXT = 768 ("dense", MMA passes in float only -- the double kernels would spill): the same pass compiled for 24 resident warps per SM
 // (<= 80 registers per thread); HBM-bound instances of many waves gain ~6 % from the extra warps (profiles/r01_v4_ncu_sweep_summary.md).
-template<typename REAL, int MODE, bool FORWARD, bool DET, int MAXT = BDDB200_LANE_MAX_THREADS>
+template<typename REAL, int MODE, bool FORWARD, bool DET, int MAXT = BDDB200_LANE_MAX_THREADS, bool PUSH = false>
 __global__ void __launch_bounds__(MAXT, 1) sweep_lane_kernel(const SweepArgs<REAL> a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1223,16 +1315,73 @@ __global__ void __launch_bounds__(MAXT, 1) sweep_lane_kernel(const SweepArgs<REA
     unsigned char* wsm = smem_raw + (size_t)warp * a.warp_smem_bytes;
     uint64_t* bars = bars_all + warp * a.n_stages;
     constexpr int M = (FORWARD && MODE == MODE_MM) ? MODE_PLAIN : MODE;
+    // push exchange: does this bundle take part in the flag barrier?  The host launches PUSH builds with a permuted descriptor array:
+    // the bundles that contain a shared variable come first (their flag goes out early in the pass and has long arrived when the
+    // peers' next pass starts), marked in the descriptor
+    const bool has_shared = PUSH && d.pad_[0] != 0;
+    const bool counted = PUSH && (has_shared || g == 0 || g * a.zero_pairs_per_bundle < a.n_push_vars);
     switch(d.J)
     {
-        case 1: sweep_lane_bundle<REAL, 1, M, FORWARD, DET>(a, d, g, wsm, bars, inv_tab, lane); break;
-        case 2: sweep_lane_bundle<REAL, 2, M, FORWARD, DET>(a, d, g, wsm, bars, inv_tab, lane); break;
-        case 3: sweep_lane_bundle<REAL, 3, M, FORWARD, DET>(a, d, g, wsm, bars, inv_tab, lane); break;
-        case 4: sweep_lane_bundle<REAL, 4, M, FORWARD, DET>(a, d, g, wsm, bars, inv_tab, lane); break;
+        case 1: sweep_lane_bundle<REAL, 1, M, FORWARD, DET, PUSH>(a, d, g, wsm, bars, inv_tab, lane, has_shared); break;
+        case 2: sweep_lane_bundle<REAL, 2, M, FORWARD, DET, PUSH>(a, d, g, wsm, bars, inv_tab, lane, has_shared); break;
+        case 3: sweep_lane_bundle<REAL, 3, M, FORWARD, DET, PUSH>(a, d, g, wsm, bars, inv_tab, lane, has_shared); break;
+        case 4: sweep_lane_bundle<REAL, 4, M, FORWARD, DET, PUSH>(a, d, g, wsm, bars, inv_tab, lane, has_shared); break;
         default: break;
+    }
+    if(PUSH && counted)
+    {   // pass-end barrier, sending half.  Every counted bundle fences at GPU scope (its multimem reductions and its zeros in the shared
+        // prefix precede its count); the last one, having seen every count, fences at system scope and tells every peer "everything I
+        // push into your buffers in this pass has arrived, and the shared prefix of the buffer you push into next is clear".  One
+        // system-scope fence per pass: one per warp serialises chip-wide (~90 ns each).  Counts are spread over PUSH_SLOTS addresses.
+        __syncwarp();
+        if(lane == 0)
+        {
+            __threadfence();
+            const uint32_t slot = g % PUSH_SLOTS;
+            if(atomicAdd(a.push_counters + 8 + slot, 1u) == a.push_counters[8 + PUSH_SLOTS + slot] - 1)
+            {
+                a.push_counters[8 + slot] = 0;
+                __threadfence();
+                if(atomicAdd(a.push_counters + 1, 1u) == a.push_counters[3] - 1)
+                {
+                    a.push_counters[1] = 0;
+                    __threadfence_system();
+                    for(int r = 0; r < a.push_world; ++r)
+                        if(r != a.push_rank) asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(a.push_flags[r] + a.push_rank), "r"(a.push_send_phase) : "memory");
+                }
+            }
+        }
     }
 }
 
+// push exchange set-up: which lane-class bundles contain a variable of the shared prefix.  One warp per bundle.
+__global__ void push_mark_bundles_kernel(const LaneDesc* __restrict__ desc, const int2* __restrict__ lay_vn, uint32_t n_bundles, uint32_t n_push_vars,
+                                         unsigned char* __restrict__ shared_out)
+{
+    const uint32_t g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if(g >= n_bundles) return;
+    const LaneDesc d = desc[g];
+    bool any = false;
+    for(uint32_t i = lane; i < d.n_hops * 32u; i += 32) any |= (uint32_t)lay_vn[d.lay_off + i].x < n_push_vars;
+    any = __any_sync(0xffffffffu, any);
+    if(lane == 0) shared_out[g] = any ? 1 : 0;
+}
+
+// Push-exchange barrier outside a pass (before the host reads or clears the sum buffers): what & 1 waits until no peer's flag shows
+// `stale_phase` any more (every peer has completed the last pass); what & 2 announces `send_phase` (this rank's buffers are ready to be
+// pushed into again).  One warp.
+__global__ void push_barrier_kernel(uint32_t* counters, uint32_t* const* flags, uint32_t* my_flags, int world, int rank, int what, uint32_t stale_phase, uint32_t send_phase)
+{
+    const int lane = threadIdx.x;
+    if((what & 1) && lane < world && lane != rank) push_wait_flag(my_flags + lane, stale_phase, counters);
+    __syncwarp();
+    if(what & 2)
+    {
+        __threadfence_system();
+        if(lane < world && lane != rank)
+            asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(flags[lane] + rank), "r"(send_phase) : "memory");
+    }
+}
 
 // ------------------------------------------------------------------ small kernels ------
 
@@ -1436,37 +1585,6 @@ constexpr int EXCHANGE_MAX_WORLD = 16;
 
 __device__ __forceinline__ void ld_volatile2(const float* p, float& x, float& y) { asm volatile("ld.volatile.global.v2.f32 {%0, %1}, [%2];" : "=f"(x), "=f"(y) : "l"(p)); }
 __device__ __forceinline__ void ld_volatile2(const double* p, double& x, double& y) { asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "l"(p)); }
-
-// Waiting for a peer is bounded by wall-clock time, not by a spin count: a peer that is merely late (a host stall, a debugger, an extra
-// synchronisation on one rank) must not kill this rank's context.  After EXCHANGE_TIMEOUT_NS the waiter records the failure in
-// counters[2] (the host turns it into BDDB200_ERR_EXCHANGE at its next synchronisation) and gives up waiting.
-constexpr unsigned long long EXCHANGE_TIMEOUT_NS = 30ull * 1000ull * 1000ull * 1000ull;
-__device__ __forceinline__ unsigned long long global_timer_ns()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-__device__ __forceinline__ void exchange_wait_flag(const uint32_t* flag, uint32_t epoch, uint32_t* counters)
-{
-    uint32_t seen;
-    unsigned long long t0 = 0;
-    for(uint32_t spins = 0;; ++spins)
-    {
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
-        if((int32_t)(seen - epoch) >= 0) return;
-        if((spins & 1023u) == 1023u)
-        {
-            const unsigned long long now = global_timer_ns();
-            if(t0 == 0) t0 = now;
-            else if(now - t0 > EXCHANGE_TIMEOUT_NS)
-            {
-                if(counters != nullptr) atomicExch(counters + 2, 1u); else __trap();
-                return;
-            }
-        }
-    }
-}
 
 // Device-side epoch (graph replay): with `counters` non-null the epoch of this exchange is counters[0] + 1, and the last CTA of the
 // launch to finish advances counters[0] (counters[1] counts finished CTAs).  All ranks run the same sequence of exchanges, so their

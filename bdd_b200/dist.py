@@ -95,10 +95,16 @@ def relabel_variables(col: BddCollection, new_of_old: np.ndarray) -> BddCollecti
 class SymmExchange:
     """Peer-memory exchange: sum buffers in symmetric memory, exchange kernels of the library issued BY the library after every
     pass (``bddb200_set_exchange``; the flag epochs live on the device, so ``iterations(n)`` replays pass + exchange as one CUDA
-    graph).  Modes: "mc" in-switch reduction through the multicast mapping (multimem.ld_reduce / multimem.st), "1" one-shot reads of
-    every peer, "2" two-shot; "auto" = mc where the box offers multicast, else one-shot below 6 ranks and two-shot from 6."""
+    graph).  Modes: "push" no exchange kernel at all -- every pass adds the shared variables' differences to ALL ranks' buffers with
+    multimem.red through the multicast mapping and ends with a flag barrier that the next pass's prologue waits for (right when few
+    layer entries belong to shared variables: each is one small packet over NVLink); "mc" in-switch reduction of the finished sums
+    (multimem.ld_reduce / multimem.st), "1" one-shot reads of every peer, "2" two-shot.  "auto" = push when at most PUSH_MAX_ENTRIES
+    layer entries of any shard belong to shared variables and the box offers multicast, else one-shot below 6 ranks and mc / two-shot
+    from 6."""
 
-    def __init__(self, local, n_vars: int, n_exchange: int, rank: int, world: int, group=None):
+    PUSH_MAX_ENTRIES = 1 << 16
+
+    def __init__(self, local, n_vars: int, n_exchange: int, rank: int, world: int, group=None, shared_entries: int = -1):
         import torch.distributed._symmetric_memory as symm_mem
         from . import _lib
         from ._lib import check
@@ -126,14 +132,29 @@ class SymmExchange:
         has_mc = mc_in != 0
         if mode == "mc" and not has_mc:
             raise RuntimeError("BDDB200_EXCHANGE_SHOTS=mc: this box offers no multicast mapping of symmetric memory")
+        if mode == "push" and not has_mc:
+            raise RuntimeError("BDDB200_EXCHANGE_SHOTS=push: this box offers no multicast mapping of symmetric memory")
         if mode == "auto":
             # measured on 2 and 4 x B200 (profiles/r02_multi_gpu.md): one flag barrier + direct reads beat the two barriers of the
             # in-switch and two-shot forms while (world - 1) x prefix stays small; from 6 ranks on the slice-wise forms read less
             many = world >= 6 and n_exchange >= (1 << 17)
             mode = ("mc" if has_mc else "2") if many else "1"
+            if has_mc and shared_entries >= 0:
+                worst = torch.tensor([shared_entries], dtype=torch.int64, device=dev)
+                dist.all_reduce(worst, op=dist.ReduceOp.MAX, group=group)
+                if int(worst.item()) <= self.PUSH_MAX_ENTRIES:
+                    mode = "push"
+        if mode == "push":
+            # needs lane-class bundles only and the atomic sums on every rank: agree before anything is set up
+            okt = torch.tensor([1 if local.push_exchange_supported() else 0], device=dev)
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN, group=group)
+            if int(okt.item()) == 0:        # deterministic sums or wide BDDs on some shard
+                mode = "1"
         # the result buffer: plain device memory for the one-shot form (every pass gathers from it), symmetric for the others
         mc_out, self.h_out = 0, None
-        if mode == "1":
+        if mode == "push":
+            self.out = None
+        elif mode == "1":
             self.out = torch.zeros(n_out, dtype=local.value_type, device=dev)
         else:
             self.out = symm_mem.empty(n_out, dtype=local.value_type, device=dev)
@@ -142,7 +163,7 @@ class SymmExchange:
             mc_out = int(getattr(self.h_out, "multicast_ptr", 0) or 0)
             if mode == "mc" and mc_out == 0:
                 raise RuntimeError("no multicast mapping for the result buffer")
-        self.mode = {"1": 1, "2": 2, "mc": 3}[mode]
+        self.mode = {"1": 1, "2": 2, "mc": 3, "push": 4}[mode]
         self.two_shot = self.mode == 2
         torch.cuda.synchronize(dev)
         dist.barrier(group=group)
@@ -150,19 +171,22 @@ class SymmExchange:
         check(self.lib.bddb200_set_delta_buffers(local.h, self.block.data_ptr(), self.block.data_ptr() + self.stride * item,
                                                  self.block.data_ptr() + 2 * self.stride * item))
         local._delta_block = self.block
-        local.set_delta_input(self.out, n_exchange // 2)
-        check(self.lib.bddb200_set_exchange(local.h, world, rank, self.h_block.buffer_ptrs_dev, self.h_flags.buffer_ptrs_dev, self.out.data_ptr(),
+        if self.out is not None:
+            local.set_delta_input(self.out, n_exchange // 2)
+        check(self.lib.bddb200_set_exchange(local.h, world, rank, self.h_block.buffer_ptrs_dev, self.h_flags.buffer_ptrs_dev,
+                                            self.out.data_ptr() if self.out is not None else None,
                                             self.h_out.buffer_ptrs_dev if self.h_out is not None else None,
-                                            mc_in if self.mode == 3 else None, mc_out if self.mode == 3 else None, n_exchange, self.mode))
+                                            mc_in if self.mode >= 3 else None, mc_out if self.mode == 3 else None, n_exchange, self.mode))
         torch.cuda.synchronize(dev)
         dist.barrier(group=group)
 
-    name = property(lambda self: {1: "symm one-shot", 2: "symm two-shot", 3: "symm in-switch (multimem)"}[self.mode])
+    name = property(lambda self: {1: "symm one-shot", 2: "symm two-shot", 3: "symm in-switch (multimem)", 4: "multimem.red push inside the pass"}[self.mode])
 
     def __call__(self):
         """Nothing to do: forward_pass / backward_pass of the local solver end with the exchange."""
 
-    def sums(self) -> torch.Tensor:
+    def sums(self) -> Optional[torch.Tensor]:
+        """The exchanged sums of the shared prefix (None in push mode: the rank's own buffer holds them)."""
         return self.out
 
 
@@ -199,7 +223,14 @@ class sharded_mma:
         if want in ("auto", "symm") and is_cuda_local:
             ok = torch.ones(1, device=self.local.device)
             try:
-                self.symm = SymmExchange(self.local, self.nr_vars, self.n_exchange, rank, world, group)
+                lv_all = self.local_col.instrs[:, 2]
+                inner = lv_all < BOTSINK
+                lv = lv_all[inner].astype(np.int64)
+                bdd_of = np.repeat(np.arange(self.local_col.nr_bdds), np.diff(self.local_col.delims.astype(np.int64)))[inner]
+                head = np.ones(lv.shape[0], dtype=bool)
+                head[1:] = (lv[1:] != lv[:-1]) | (bdd_of[1:] != bdd_of[:-1])
+                shared_entries = int((lv[head] < self.n_shared).sum())        # layer entries of this shard that push across NVLink
+                self.symm = SymmExchange(self.local, self.nr_vars, self.n_exchange, rank, world, group, shared_entries)
             except Exception as e:          # no symmetric-memory support on this box: every rank must fall back together
                 if want == "symm":
                     raise
@@ -255,7 +286,7 @@ class sharded_mma:
         st = getattr(self.local, "stream", None)
         if st is not None and t.is_cuda:
             torch.cuda.current_stream(t.device).wait_stream(st)       # the passes and the exchange run on the solver's stream
-        if self.symm is not None:           # shared prefix from the exchanged buffer, the rest from the local sums
+        if self.symm is not None and self.symm.sums() is not None:           # shared prefix from the exchanged buffer, the rest from the local sums
             t = torch.cat([self.symm.sums()[: self.n_exchange], t[self.n_exchange:]])
         a = t.detach().cpu().numpy().reshape(-1, 2)
         return a[self.new_of_old].reshape(-1).copy()

@@ -174,6 +174,12 @@ class bdd_cuda_parallel_mma:
         check(self.lib.bddb200_delta_sum_index(self.h, C.byref(out)))
         return out.value
 
+    def push_exchange_supported(self) -> bool:
+        """Whether this solver can run the multi-GPU push exchange (bddb200_set_exchange mode 4)."""
+        out = C.c_int()
+        check(self.lib.bddb200_push_exchange_supported(self.h, C.byref(out)))
+        return out.value != 0
+
     def set_delta_buffers(self, block: torch.Tensor):
         """Use ``block`` (3 x 2V zero-filled REALs, e.g. symmetric memory mapped by the peer GPUs) as the rotating sum buffers."""
         n = 2 * self.nr_variables()

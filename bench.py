@@ -13,16 +13,18 @@ shard per GPU, the per-variable sums of the shared variables exchanged after eve
 at N=1.
 
 Timed quantities of the top-level line
-  value      device-resident state, per-step CUDA events on the solver's stream, L2 flushed
-             between timed steps (the 1 M-node working set would otherwise live in the 126 MB L2);
-             `back_to_back` in the same line is the un-flushed steady state of a real solve.
+  value      device-resident state, one iteration() call per step, CUDA events on the solver's stream
+             around every step, L2 flushed between timed steps (the 1 M-node working set would otherwise
+             live in the 126 MB L2); `back_to_back` in the same line is the un-flushed steady state of a
+             real solve (CUDA-graph replay inside the library).
   e2e        the same step driven with HOST buffers every step: update_costs(host lo, host hi) [H2D of 2V
              REALs from pinned memory, the perturbation step of the rounding loop, bdd_solver.cpp:318-380]
              -> iteration() -> lower_bound() [D2H of the bound, what run_solver does each iteration,
              run_solver_util.h:37-49].  At N=1 through the fused C-ABI call bddb200_step_host; the same step as
              three separate calls is `e2e.separate_calls`.
   roofline   forward / backward sweep kernel: algorithmic bytes per pass (SURVEY 8d formula)
-             divided by the kernel's mean duration from CUDA events around each pass launch.
+             divided by the kernel's mean duration from CUDA events around each pass launch, in a second
+             run of K flushed steps (forward_pass(); event; backward_pass()).
   cpu_baseline / --impl reference: the reference's own CPU `parallel mma` solver
              (oracle/_ref/libbdd_ref.so, built from /root/reference sources) or, where that
              library is absent, the plain-C port (oracle/liboracle_mma.so), all host threads.
@@ -341,33 +343,43 @@ def measure(env: Env, workload: str, K: int, W: int, with_cpu: bool, with_e2e: b
         solver.iteration()
     env.barrier()
 
-    # ---- value: per-step events, L2 flushed between steps ---------------------------------
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    # ---- value: one iteration() call per step, events around every step, L2 flushed between steps ---------------
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
     launches0 = local.kernel_launches()
     env.barrier()
     wall0 = time.perf_counter()
     for k in range(K):
         flush_l2()
         ev[k][0].record(st)
-        if lbfgs:
-            solver.iteration()
-            ev[k][1].record(st)
-        else:
-            local.forward_pass(0.5)          # at N > 1 the pass ends with the exchange of the shared variables' sums
-            ev[k][1].record(st)
+        solver.iteration()                   # forward pass + backward pass (at N > 1 each ends with the exchange of the shared variables' sums)
+        ev[k][1].record(st)
+    env.barrier()
+    wall = time.perf_counter() - wall0
+    launches = local.kernel_launches() - launches0
+    total_ms = sum(e[0].elapsed_time(e[1]) for e in ev)
+
+    # ---- roofline: the same flushed step with an event between the two sweep launches (the event keeps the second launch from
+    # overlapping the first one's tail, so these steps are a little slower than the ones `value` is computed from)
+    kern_ms = float("nan")
+    fwd_ms = bwd_ms = [float("nan")]
+    if not lbfgs:
+        evp = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+        env.barrier()
+        for k in range(K):
+            flush_l2()
+            evp[k][0].record(st)
+            local.forward_pass(0.5)
+            evp[k][1].record(st)
             if world > 1:
                 solver.exchange_sums()       # (a no-op when the library issues the exchange itself)
             local.backward_pass(0.5)
             if world > 1:
                 solver.exchange_sums()
-        ev[k][2].record(st)
-    env.barrier()
-    wall = time.perf_counter() - wall0
-    launches = local.kernel_launches() - launches0
-    total_ms = sum(e[0].elapsed_time(e[2]) for e in ev)
-    fwd_ms = [e[0].elapsed_time(e[1]) for e in ev]
-    bwd_ms = [e[1].elapsed_time(e[2]) for e in ev]
-    kern_ms = (sum(fwd_ms) + sum(bwd_ms)) / (2 * K)          # at N > 1: pass + exchange
+            evp[k][2].record(st)
+        env.barrier()
+        fwd_ms = [e[0].elapsed_time(e[1]) for e in evp]
+        bwd_ms = [e[1].elapsed_time(e[2]) for e in evp]
+        kern_ms = (sum(fwd_ms) + sum(bwd_ms)) / (2 * K)          # at N > 1: pass + exchange
 
     # ---- back-to-back steady state (no flush; CUDA-graph replay inside the library) ------------
     env.barrier()
@@ -462,7 +474,9 @@ def measure(env: Env, workload: str, K: int, W: int, with_cpu: bool, with_e2e: b
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": env.peak, "unit": "GB/s", "frac": achieved / env.peak,
                          "traffic": traffic, "traffic_source": "profiles/traffic.json (ncu --set full dram__bytes of an earlier capture, not measured in this run)" if traffic else None,
-                         "kernel": "sweep_lane_kernel<REAL, MODE_MMA, fwd|bwd>" + (" + exchange kernel" if world > 1 else ""), "kernel_ms": kern_ms,
+                         "kernel": "sweep_lane_kernel<REAL, MODE_MMA, fwd|bwd>" + (" + exchange" if world > 1 else ""), "kernel_ms": kern_ms,
+                         "kernel_ms_fwd_cold": sum(fwd_ms) / K, "kernel_ms_bwd": sum(bwd_ms) / K,
+                         "timing": "CUDA events around each sweep launch of K flushed steps (forward: state from HBM; backward: state the forward pass left in L2)",
                          "algorithmic_bytes_per_launch": pass_bytes, "peak_source": env.peak_src},
             "cpu_baseline": cpu,
             "construct_ms": construct_ms, "wall_s_timed_region": wall,

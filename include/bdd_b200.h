@@ -218,6 +218,9 @@ int bddb200_delta_sum_buffer(bddb200_solver* s, void** sum_dev);
  * graph then contains it): register the peer mappings once.  mode 1 = one-shot reads of every peer's sum buffer, 2 = two-shot
  * (slice-wise reduce, then copy), 3 = in-switch reduction through multicast mappings (multimem.ld_reduce / multimem.st; mc_in = multicast
  * address of the symmetric block holding the three sum buffers, mc_out = multicast address of the symmetric result buffer), 0 = off.
+ * mode 4 = push: no exchange kernel -- the pass itself adds the min-marginal differences of the first n_exchange / 2 variables to EVERY
+ * rank's sum buffer (multimem.red through mc_in), its last warp signals the peers and the next pass's prologue waits for theirs; the
+ * passes then read all sums from the rank's own buffer (no bddb200_set_delta_input).  Needs bddb200_push_exchange_supported.
  * The epoch of the flag barriers lives on the device, so all ranks must make the same sequence of passes.  Replaces the host-staged
  * exchange of the hybrid solver, bdd_multi_parallel_mma_base.cu:266-318. */
 int bddb200_set_exchange(bddb200_solver* s, int world, int rank, const void* const* peer_bufs_dev, uint32_t* const* flags_dev, void* out_dev,
@@ -237,6 +240,9 @@ int bddb200_set_exchange(bddb200_solver* s, int world, int rank, const void* con
  *   offset_elems  : start of the exchanged buffer inside the block, in REALs
  *   n_exchange    : leading REALs (2 * n_shared) summed over all ranks into out_dev */
 int bddb200_delta_sum_index(const bddb200_solver* s, int* index_out);
+/* 1 when this solver can run the push exchange (mode 4 of bddb200_set_exchange): atomic (non-deterministic) sums and every BDD in the
+ * one-lane-per-BDD class */
+int bddb200_push_exchange_supported(const bddb200_solver* s, int* yes_out);
 int bddb200_set_delta_buffers(bddb200_solver* s, void* buf0_dev, void* buf1_dev, void* buf2_dev);
 int bddb200_set_delta_input(bddb200_solver* s, void* shared_in_dev, size_t n_shared_vars);
 int bddb200_delta_exchange(void* stream, int precision, int world, int rank, const void* const* peer_bufs_dev,

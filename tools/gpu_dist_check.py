@@ -49,6 +49,14 @@ def main():
                 err = float(np.abs(d_s[sel] - d_w[sel]).max()) / max(1.0, float(np.abs(d_w).max()))
                 lb_s, lb_w = sh.lower_bound(), whole.lower_bound()
                 worst = max(worst, err, abs(lb_s - lb_w) / scale)
+            # the graph-replayed form (pass + exchange inside the library)
+            sh.iterations(7); whole.iterations(7)
+            d_s = sh.delta_sums().astype(np.float64)
+            d_s[0::2] /= cnt; d_s[1::2] /= cnt
+            d_w = whole.get_delta().double().cpu().numpy()
+            err = float(np.abs(d_s[sel] - d_w[sel]).max()) / max(1.0, float(np.abs(d_w).max()))
+            lb_s, lb_w = sh.lower_bound(), whole.lower_bound()
+            worst = max(worst, err, abs(lb_s - lb_w) / scale)
             good = good and worst <= tol
             ok &= good
             if rank == 0:
