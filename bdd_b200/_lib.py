@@ -15,7 +15,8 @@ FLOAT, DOUBLE = 0, 1
 
 # every symbol include/bdd_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = [
-    "bddb200_default_options", "bddb200_last_error", "bddb200_version", "bddb200_create", "bddb200_destroy", "bddb200_clone",
+    "bddb200_default_options", "bddb200_last_error", "bddb200_version", "bddb200_create", "bddb200_destroy", "bddb200_clone", "bddb200_plan_shard", "bddb200_create_shard",
+    "bddb200_save_size", "bddb200_save", "bddb200_load",
     "bddb200_nr_variables", "bddb200_nr_bdds", "bddb200_nr_layers", "bddb200_nr_bdd_nodes", "bddb200_nr_hops",
     "bddb200_precision_of", "bddb200_device_of", "bddb200_nr_bdds_per_var", "bddb200_layer_primal_indices",
     "bddb200_layer_bdd_indices", "bddb200_iteration", "bddb200_iterations", "bddb200_forward_pass",
@@ -24,13 +25,18 @@ SYMBOLS = [
     "bddb200_backward_run", "bddb200_flush_forward_states", "bddb200_flush_backward_states",
     "bddb200_update_costs_host", "bddb200_update_costs_host_real", "bddb200_update_costs_dev", "bddb200_step_host", "bddb200_set_cost", "bddb200_distribute_delta",
     "bddb200_get_solver_costs", "bddb200_set_solver_costs", "bddb200_primal_objective_host",
-    "bddb200_min_marginals", "bddb200_bdds_solution", "bddb200_net_solver_costs", "bddb200_make_dual_feasible",
+    "bddb200_min_marginals", "bddb200_min_marginals_host", "bddb200_bdds_solution", "bddb200_net_solver_costs", "bddb200_make_dual_feasible",
     "bddb200_gradient_step", "bddb200_synchronize", "bddb200_stream", "bddb200_kernel_launches",
     "bddb200_delta_sum_buffer", "bddb200_layout_stats", "bddb200_trace_pass",
     "bddb200_delta_sum_index", "bddb200_push_exchange_supported", "bddb200_set_delta_buffers", "bddb200_set_delta_input", "bddb200_set_exchange", "bddb200_delta_exchange", "bddb200_delta_exchange_two_shot",
     "bddb200_run_solver", "bddb200_rounding_perturb", "bddb200_incremental_mm_agreement_rounding",
     "bddb200_lbfgs_create", "bddb200_lbfgs_destroy", "bddb200_lbfgs_iteration", "bddb200_lbfgs_flush", "bddb200_lbfgs_stats",
 ]
+
+
+class ShardInfo(C.Structure):
+    """bddb200_shard_info"""
+    _fields_ = [("nr_variables", C.c_size_t), ("n_shared", C.c_size_t), ("shared_entries", C.c_size_t), ("first_bdd", C.c_size_t), ("n_bdds", C.c_size_t)]
 
 
 class Options(C.Structure):
@@ -68,6 +74,11 @@ def load() -> C.CDLL:
         "bddb200_create": (i, [vp, sz, vp, sz, vp, sz, i, C.POINTER(Options), C.POINTER(vp)]),
         "bddb200_destroy": (None, [vp]),
         "bddb200_clone": (i, [vp, C.POINTER(vp)]),
+        "bddb200_plan_shard": (i, [vp, sz, vp, sz, sz, i, i, C.POINTER(ShardInfo), vp, vp]),
+        "bddb200_create_shard": (i, [vp, sz, vp, sz, vp, sz, i, C.POINTER(Options), i, i, C.POINTER(ShardInfo), vp, C.POINTER(vp)]),
+        "bddb200_save_size": (i, [vp, C.POINTER(sz)]),
+        "bddb200_save": (i, [vp, vp, sz, C.POINTER(sz)]),
+        "bddb200_load": (i, [vp, sz, i, C.POINTER(vp)]),
         "bddb200_nr_variables": (sz, [vp]),
         "bddb200_nr_bdds": (sz, [vp]),
         "bddb200_nr_layers": (sz, [vp]),
@@ -102,6 +113,7 @@ def load() -> C.CDLL:
         "bddb200_set_solver_costs": (i, [vp, vp, vp, vp]),
         "bddb200_primal_objective_host": (i, [vp, vp]),
         "bddb200_min_marginals": (i, [vp, i, vp, vp, vp]),
+        "bddb200_min_marginals_host": (i, [vp, i, vp, vp, vp]),
         "bddb200_bdds_solution": (i, [vp, vp]),
         "bddb200_net_solver_costs": (i, [vp, vp]),
         "bddb200_make_dual_feasible": (i, [vp, vp]),

@@ -20,6 +20,7 @@
 
 #include "kernels.cuh"
 #include "resident.cuh"
+#include "shard.hpp"
 
 using namespace bddb200;
 
@@ -93,6 +94,7 @@ struct bddb200_solver {
     virtual void set_solver_costs(const void* lo, const void* hi, const void* mmd) = 0;
     virtual void primal_objective_host(double* out) = 0;
     virtual void min_marginals(int sorted, int32_t* primal_dev, void* lo_dev, void* hi_dev) = 0;
+    virtual void min_marginals_host(int sorted, int32_t* primal_host, double* lo_host, double* hi_host) = 0;
     virtual void bdds_solution(char* sol_dev) = 0;
     virtual void net_solver_costs(void* out_dev) const = 0;
     virtual void make_dual_feasible(void* inout_dev) const = 0;
@@ -110,6 +112,7 @@ struct bddb200_solver {
                               const void* mc_in, void* mc_out, size_t n_exchange, int mode) = 0;
     virtual size_t trace_pass(int forward, double omega, unsigned long long* out_host, size_t max_bundles) = 0;
     virtual bddb200_solver* clone() const = 0;
+    virtual void save(std::vector<unsigned char>& out) const = 0;
 };
 
 #include "lbfgs.cuh"
@@ -301,6 +304,107 @@ public:
         res_pass_ = o.res_pass_; exch_in_contrib_ = o.exch_in_contrib_; lb_from_resident_ = o.lb_from_resident_;
         cc_ = o.cc_; dcur_ = o.dcur_; delta_needs_norm_ = o.delta_needs_norm_;
         forward_valid_ = o.forward_valid_; backward_valid_ = o.backward_valid_; lb_valid_ = o.lb_valid_; lb_ = o.lb_;
+        configure_kernels();
+        CUDA_CHECK(cudaStreamSynchronize(stream_));
+    }
+
+    // ---- serialisation (the reference class is cereal-serialisable, bdd_cuda_base.cu:1486-1544 / bdd_cuda_parallel_mma.cu:475-490: all device
+    // vectors and counters; its pybind module pickles solvers that way, bdd_cuda_parallel_mma_py.cu:29-38).  One blob: header, then every
+    // member the copy constructor copies, device buffers as raw bytes.  The launch plan is part of it, so a blob loads on the same GPU model.
+    struct SaveArchive {
+        std::vector<unsigned char>& out; cudaStream_t st;
+        void raw(const void* p, size_t n) { const unsigned char* b = static_cast<const unsigned char*>(p); out.insert(out.end(), b, b + n); }
+        template<typename T> void pod(T& v) { raw(&v, sizeof(T)); }
+        template<typename T> void vec(std::vector<T>& v) { uint64_t n = v.size(); pod(n); if(n) raw(v.data(), n * sizeof(T)); }
+        template<typename T> void dev(DevBuf<T>& b)
+        {
+            uint64_t n = b.n; pod(n);
+            const size_t off = out.size();
+            out.resize(off + n * sizeof(T));
+            if(n) CUDA_CHECK(cudaMemcpyAsync(out.data() + off, b.p, n * sizeof(T), cudaMemcpyDeviceToHost, st));
+            CUDA_CHECK(cudaStreamSynchronize(st));        // `out` may reallocate on the next append
+        }
+    };
+    struct LoadArchive {
+        const unsigned char* p; size_t left; cudaStream_t st;
+        void raw(void* dst, size_t n)
+        {
+            if(n > left) throw api_error(BDDB200_ERR_INVALID_ARGUMENT, "bddb200_load: truncated blob");
+            std::memcpy(dst, p, n); p += n; left -= n;
+        }
+        template<typename T> void pod(T& v) { raw(&v, sizeof(T)); }
+        template<typename T> void vec(std::vector<T>& v)
+        {
+            uint64_t n = 0; pod(n);
+            if(n * sizeof(T) > left) throw api_error(BDDB200_ERR_INVALID_ARGUMENT, "bddb200_load: truncated blob");
+            v.resize(n); if(n) raw(v.data(), n * sizeof(T));
+        }
+        template<typename T> void dev(DevBuf<T>& b)
+        {
+            uint64_t n = 0; pod(n);
+            if(n * sizeof(T) > left) throw api_error(BDDB200_ERR_INVALID_ARGUMENT, "bddb200_load: truncated blob");
+            b.alloc(n);
+            if(n) CUDA_CHECK(cudaMemcpyAsync(b.p, p, n * sizeof(T), cudaMemcpyHostToDevice, st));
+            p += n * sizeof(T); left -= n * sizeof(T);
+        }
+    };
+    template<typename A>
+    void visit_state(A& ar)
+    {
+        ar.pod(deterministic_);
+        ar.pod(n_sms_); ar.pod(max_optin_); ar.pod(warps_per_cta_); ar.pod(grid_small_); ar.pod(forced_wpc_); ar.pod(n_stages_); ar.pod(n_stages_large_);
+        ar.pod(n_lane_); ar.pod(lane_max_J_); ar.pod(lane_max_hops_); ar.pod(lane_wpc_); ar.pod(lane_grid_); ar.vec(lane_cls_first_); ar.vec(lane_cls_begin_); ar.pod(lane_dense_);
+        ar.pod(lane_chunk_hops_); ar.pod(lane_stages_); ar.pod(lane_stage_bytes_); ar.pod(lane_warp_smem_);
+        ar.pod(stage_small_); ar.pod(stage_large_); ar.pod(warp_smem_small_); ar.pod(warp_smem_large_);
+        ar.pod(n_vars_); ar.pod(n_bdds_); ar.pod(n_instr_); ar.pod(n_ext_); ar.pod(n_slots_); ar.pod(n_lay_);
+        ar.pod(max_hops_); ar.pod(n_bundles_); ar.pod(n_small_); ar.pod(tile_small_); ar.pod(tile_large_);
+        ar.vec(h_nr_bdds_per_var_); ar.vec(h_ext_var_); ar.vec(h_ext_bdd_);
+        ar.dev(d_bundles_); ar.dev(d_chunks_); ar.dev(d_desc_fwd_); ar.dev(d_desc_bwd_); ar.dev(d_desc_lane_);
+        ar.dev(d_hops_); ar.dev(d_topo_); ar.dev(d_bdd_bundle_); ar.dev(d_ext2lay_); ar.dev(d_bdd_ext_begin_);
+        ar.dev(d_var_lay_begin_); ar.dev(d_var_lay_); ar.dev(d_sorted_ext_); ar.dev(d_lay_vn_); ar.dev(d_bundle_bdd_);
+        ar.dev(d_ext_var_); ar.dev(d_ext_bdd_); ar.dev(d_nr_bdds_); ar.dev(d_cfr_); ar.dev(d_cft_);
+        ar.dev(d_lohi_[0]); ar.dev(d_lohi_[1]); ar.dev(d_mmd_); ar.dev(d_mm_lo_); ar.dev(d_mm_hi_);
+        ar.dev(d_delta_[0]); ar.dev(d_delta_[1]); ar.dev(d_delta_[2]);
+        ar.dev(d_inv_tab_); ar.pod(inv_count_); ar.pod(pdl_);
+        ar.dev(d_delta_tmp_); ar.dev(d_bdd_lb_); ar.dev(d_lb_partial_);
+        ar.pod(res_ok_); ar.pod(res_grid_); ar.pod(res_wpc_); ar.pod(res_warp_smem_); ar.pod(res_vars_per_bundle_); ar.pod(res_own_cap_); ar.pod(res_own_off_);
+        ar.dev(d_contrib_); ar.dev(d_sums_); ar.dev(d_lb_part_);
+        ar.pod(res_pass_); ar.pod(exch_in_contrib_); ar.pod(lb_from_resident_);
+        ar.pod(cc_); ar.pod(dcur_); ar.pod(delta_needs_norm_); ar.pod(forward_valid_); ar.pod(backward_valid_); ar.pod(lb_valid_); ar.pod(lb_); ar.pod(lb_sum_clean_);
+    }
+    static constexpr uint64_t SAVE_MAGIC = 0x3130533030324442ull;      // "BD200S01"
+    void save(std::vector<unsigned char>& out) const override
+    {
+        if(ext_delta_[0] != nullptr || xc_.mode != 0)
+            throw api_error(BDDB200_ERR_STATE, "save: a solver whose sum buffers live in caller-owned (symmetric) memory cannot be serialised");
+        SolverImpl& self = const_cast<SolverImpl&>(*this);       // the visitor only reads here
+        self.set_device();
+        CUDA_CHECK(cudaStreamSynchronize(stream_));
+        SaveArchive ar{out, stream_};
+        uint64_t magic = SAVE_MAGIC; int32_t prec = precision;
+        ar.pod(magic); ar.pod(prec);
+        self.visit_state(ar);
+    }
+    // the loading constructor: `blob` points behind the header
+    SolverImpl(const unsigned char* blob, size_t bytes, int dev)
+    {
+        precision = sizeof(REAL) == 8 ? BDDB200_DOUBLE : BDDB200_FLOAT;
+        device = dev;
+        int count = 0;
+        if(cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+            throw api_error(BDDB200_ERR_NO_DEVICE, "no CUDA device available: libbdd_b200 has no CPU fallback");
+        if(device < 0 || device >= count) throw api_error(BDDB200_ERR_INVALID_ARGUMENT, "invalid device ordinal");
+        CUDA_CHECK(cudaSetDevice(device));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking)); own_stream_ = true;
+        LoadArchive ar{blob, bytes, stream_};
+        visit_state(ar);
+        int sms = 0, optin = 0;
+        CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        CUDA_CHECK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        if(sms != n_sms_ || optin != (int)max_optin_)
+            throw api_error(BDDB200_ERR_INVALID_ARGUMENT, "bddb200_load: the blob was saved on a different GPU model (its launch plan does not apply here)");
+        CUDA_CHECK(cudaMallocHost(&h_lb_, LB_SLOTS * sizeof(double)));
+        if(res_ok_) CUDA_CHECK(cudaMallocHost(&h_lb_part_, std::max<size_t>(n_lane_, 1) * sizeof(double)));
         configure_kernels();
         CUDA_CHECK(cudaStreamSynchronize(stream_));
     }
@@ -1226,6 +1330,26 @@ public:
         if(sorted) CUDA_CHECK(cudaStreamSynchronize(stream_));   // tmp is freed on return
     }
 
+    // the same into host memory, as doubles (two_dim_variable_array<std::array<double,2>> min_marginals(), bdd_cuda_base.cu:753-786)
+    void min_marginals_host(int sorted, int32_t* primal_host, double* lo_host, double* hi_host) override
+    {
+        set_device();
+        DevBuf<int32_t> idx; DevBuf<REAL> lo, hi;
+        idx.alloc(n_ext_); lo.alloc(n_ext_); hi.alloc(n_ext_);
+        min_marginals(sorted, idx.p, lo.p, hi.p);
+        std::vector<REAL> h(n_ext_);
+        if(primal_host) CUDA_CHECK(cudaMemcpyAsync(primal_host, idx.p, sizeof(int32_t) * n_ext_, cudaMemcpyDeviceToHost, stream_));
+        for(int k = 0; k < 2; ++k)
+        {
+            double* dst = k == 0 ? lo_host : hi_host;
+            if(dst == nullptr) continue;
+            CUDA_CHECK(cudaMemcpyAsync(h.data(), (k == 0 ? lo : hi).p, sizeof(REAL) * n_ext_, cudaMemcpyDeviceToHost, stream_));
+            CUDA_CHECK(cudaStreamSynchronize(stream_));
+            for(size_t i = 0; i < n_ext_; ++i) dst[i] = (double)h[i];
+        }
+        CUDA_CHECK(cudaStreamSynchronize(stream_));
+    }
+
     // compute the min-marginals of every layer entry into d_mm_lo_ / d_mm_hi_ (bdd_cuda_base.cu:716-736)
     void min_marginals_internal()
     {
@@ -1472,6 +1596,50 @@ int bddb200_create(const bddb200_instruction* instrs, size_t n_instr, const size
         else throw api_error(BDDB200_ERR_INVALID_ARGUMENT, "precision must be BDDB200_FLOAT or BDDB200_DOUBLE");
     });
 }
+// ---- constraint-sharded construction: one rank's solver of a `world`-way split, planned and built in the library ----
+int bddb200_plan_shard(const bddb200_instruction* instrs, size_t n_instr, const size_t* delims, size_t n_bdds, size_t nr_variables_min,
+                       int world, int rank, bddb200_shard_info* info, int32_t* new_of_old_out, int32_t* counts_new_out)
+{
+    (void)n_instr;
+    if(instrs == nullptr || delims == nullptr || info == nullptr || n_bdds == 0) { g_last_error = "null argument"; return BDDB200_ERR_INVALID_ARGUMENT; }
+    return guarded([&] {
+        ShardPlan p;
+        try { p = plan_shard(instrs, delims, n_bdds, nr_variables_min, world, rank); }
+        catch(const std::invalid_argument& e) { throw api_error(BDDB200_ERR_INVALID_ARGUMENT, e.what()); }
+        info->nr_variables = p.n_vars; info->n_shared = p.n_shared; info->shared_entries = p.shared_entries; info->first_bdd = p.first_bdd; info->n_bdds = p.n_bdds;
+        if(new_of_old_out) std::memcpy(new_of_old_out, p.new_of_old.data(), p.n_vars * sizeof(int32_t));
+        if(counts_new_out) std::memcpy(counts_new_out, p.counts_new.data(), p.n_vars * sizeof(int32_t));
+    });
+}
+int bddb200_create_shard(const bddb200_instruction* instrs, size_t n_instr, const size_t* delims, size_t n_bdds, const double* costs_hi, size_t n_costs,
+                         int precision, const bddb200_options* opts, int world, int rank, bddb200_shard_info* info, int32_t* new_of_old_out, bddb200_solver** out)
+{
+    (void)n_instr;
+    if(out == nullptr || instrs == nullptr || delims == nullptr || info == nullptr || n_bdds == 0) { g_last_error = "null argument"; return BDDB200_ERR_INVALID_ARGUMENT; }
+    *out = nullptr;
+    bddb200_options o; bddb200_default_options(&o);
+    if(opts) o = *opts;
+    return guarded([&] {
+        ShardPlan p;
+        try { p = plan_shard(instrs, delims, n_bdds, std::max(n_costs, (size_t)o.nr_variables), world, rank); }
+        catch(const std::invalid_argument& e) { throw api_error(BDDB200_ERR_INVALID_ARGUMENT, e.what()); }
+        if(p.n_bdds == 0) throw api_error(BDDB200_ERR_INVALID_ARGUMENT, "create_shard: more ranks than BDDs (this rank's shard is empty)");
+        info->nr_variables = p.n_vars; info->n_shared = p.n_shared; info->shared_entries = p.shared_entries; info->first_bdd = p.first_bdd; info->n_bdds = p.n_bdds;
+        if(new_of_old_out) std::memcpy(new_of_old_out, p.new_of_old.data(), p.n_vars * sizeof(int32_t));
+        // this rank's instructions with relabelled variables; child indices stay absolute (the base pointer is shifted instead)
+        constexpr size_t BOT = (size_t)-2;
+        const size_t i0 = delims[p.first_bdd], i1 = delims[p.first_bdd + p.n_bdds];
+        std::vector<bddb200_instruction> local(instrs + i0, instrs + i1);
+        for(bddb200_instruction& ins : local) if(ins.index < BOT) ins.index = (size_t)p.new_of_old[ins.index];
+        std::vector<double> costs_new(p.n_vars, 0.0);
+        for(size_t v = 0; v < std::min(n_costs, p.n_vars); ++v) costs_new[(size_t)p.new_of_old[v]] = costs_hi[v];
+        o.nr_variables = p.n_vars; o.nr_bdds_per_var_host = p.counts_new.data();
+        const bddb200_instruction* base = local.data() - i0;
+        if(precision == BDDB200_DOUBLE) *out = new SolverImpl<double>(base, i1, delims + p.first_bdd, p.n_bdds, costs_new.data(), costs_new.size(), o);
+        else if(precision == BDDB200_FLOAT) *out = new SolverImpl<float>(base, i1, delims + p.first_bdd, p.n_bdds, costs_new.data(), costs_new.size(), o);
+        else throw api_error(BDDB200_ERR_INVALID_ARGUMENT, "precision must be BDDB200_FLOAT or BDDB200_DOUBLE");
+    });
+}
 void bddb200_destroy(bddb200_solver* s) { delete s; }
 int bddb200_clone(const bddb200_solver* s, bddb200_solver** out)
 {
@@ -1533,6 +1701,9 @@ int bddb200_primal_objective_host(bddb200_solver* s, double* out) { REQUIRE_SOLV
 
 int bddb200_min_marginals(bddb200_solver* s, int sorted, int32_t* primal, void* lo, void* hi)
 { REQUIRE_SOLVER(s); return guarded([&] { s->min_marginals(sorted, primal, lo, hi); }); }
+
+int bddb200_min_marginals_host(bddb200_solver* s, int sorted, int32_t* primal, double* lo, double* hi)
+{ REQUIRE_SOLVER(s); return guarded([&] { s->min_marginals_host(sorted, primal, lo, hi); }); }
 
 int bddb200_bdds_solution(bddb200_solver* s, char* sol) { REQUIRE_SOLVER(s); return guarded([&] { s->bdds_solution(sol); }); }
 int bddb200_net_solver_costs(const bddb200_solver* s, void* out) { REQUIRE_SOLVER(s); return guarded([&] { s->net_solver_costs(out); }); }
@@ -1625,6 +1796,33 @@ int bddb200_lbfgs_stats(const bddb200_lbfgs* l, size_t* lbfgs_iterations, size_t
     return BDDB200_OK;
 }
 
+int bddb200_save_size(const bddb200_solver* s, size_t* bytes_out)
+{
+    REQUIRE_SOLVER(s);
+    return guarded([&] { std::vector<unsigned char> b; s->save(b); *bytes_out = b.size(); });
+}
+int bddb200_save(const bddb200_solver* s, void* buf, size_t bytes, size_t* written_out)
+{
+    REQUIRE_SOLVER(s);
+    return guarded([&] {
+        std::vector<unsigned char> b; s->save(b);
+        if(written_out) *written_out = b.size();
+        if(buf == nullptr || bytes < b.size()) throw api_error(BDDB200_ERR_INVALID_ARGUMENT, "bddb200_save: buffer too small (ask bddb200_save_size)");
+        std::memcpy(buf, b.data(), b.size());
+    });
+}
+int bddb200_load(const void* buf, size_t bytes, int device, bddb200_solver** out)
+{
+    if(buf == nullptr || out == nullptr || bytes < 12) { g_last_error = "bddb200_load: invalid argument"; return BDDB200_ERR_INVALID_ARGUMENT; }
+    return guarded([&] {
+        const unsigned char* p = static_cast<const unsigned char*>(buf);
+        uint64_t magic; int32_t prec;
+        std::memcpy(&magic, p, 8); std::memcpy(&prec, p + 8, 4);
+        if(magic != 0x3130533030324442ull || (prec != BDDB200_FLOAT && prec != BDDB200_DOUBLE)) throw api_error(BDDB200_ERR_INVALID_ARGUMENT, "bddb200_load: not a solver blob of this library version");
+        if(prec == BDDB200_DOUBLE) *out = new SolverImpl<double>(p + 12, bytes - 12, device);
+        else *out = new SolverImpl<float>(p + 12, bytes - 12, device);
+    });
+}
 int bddb200_delta_sum_index(const bddb200_solver* s, int* out) { REQUIRE_SOLVER(s); return guarded([&] { *out = s->delta_sum_index(); }); }
 int bddb200_push_exchange_supported(const bddb200_solver* s, int* out) { REQUIRE_SOLVER(s); return guarded([&] { *out = s->push_exchange_supported(); }); }
 int bddb200_set_delta_buffers(bddb200_solver* s, void* b0, void* b1, void* b2)

@@ -20,8 +20,9 @@
 //    hop-sorted order; get_primal_variable_index() / get_bdd_index() describe it, and all
 //    per-layer vectors of one solver share it (that is all callers rely on);
 //  * node-level accessors of the reference's internal layout (get_lo_bdd_node_index, ...), the
-//    sum-marginal functions of the learned solver and the cereal save/load are not provided
-//    (out of scope); the protected members are gone, so the learned
+//    sum-marginal functions of the learned solver are not provided (out of scope, SURVEY 2 rows
+//    16-18); cereal save / load carry the library's own state blob (bddb200_save), not the
+//    reference's member list; the protected members are gone, so the learned
 //    subclass bdd_cuda_learned_mma does not build on top of this class.
 #pragma once
 
@@ -282,6 +283,38 @@ namespace LPMP {
                 fetch_sizes();
                 if(std::getenv("BDDB200_DEBUG")) std::fprintf(stderr, "[shim] sizes fetched\n");
             }
+        public:
+            // cereal interface of the reference class (include/bdd_solver/bdd_cuda_base.h:166-170, bdd_cuda_base.cu:1486-1544): the archive
+            // receives the two hop tables and the library's state blob (bddb200_save); load() rebuilds the solver from it on device 0
+            template<class Archive>
+            void save(Archive& archive) const
+            {
+                std::vector<char> blob;
+                if(h_)
+                {
+                    size_t n = 0;
+                    bddb200_detail::check(bddb200_save_size(h_, &n));
+                    blob.resize(n);
+                    bddb200_detail::check(bddb200_save(h_, blob.data(), blob.size(), &n));
+                }
+                archive(cum_nr_bdd_nodes_per_hop_dist_, cum_nr_layers_per_hop_dist_, blob);
+            }
+            template<class Archive>
+            void load(Archive& archive)
+            {
+                std::vector<char> blob;
+                archive(cum_nr_bdd_nodes_per_hop_dist_, cum_nr_layers_per_hop_dist_, blob);
+                if(h_) { bddb200_destroy(h_); h_ = nullptr; }
+                if(blob.empty()) return;
+                bddb200_detail::check(bddb200_load(blob.data(), blob.size(), 0, &h_));
+                if(bddb200_precision_of(h_) != bddb200_detail::precision_of<REAL>::value)
+                {
+                    bddb200_destroy(h_); h_ = nullptr;
+                    throw std::runtime_error("bdd_b200: archive holds a solver of the other precision");
+                }
+                fetch_sizes();
+            }
+        protected:
             void fetch_sizes()
             {
                 nr_vars_ = bddb200_nr_variables(h_); nr_bdds_ = bddb200_nr_bdds(h_);

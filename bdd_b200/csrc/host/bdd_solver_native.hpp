@@ -14,6 +14,7 @@
 #pragma once
 
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <cmath>
 #include <cstdint>
@@ -26,6 +27,7 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <tuple>
 #include <unordered_map>
 #include <vector>
 
@@ -373,7 +375,34 @@ public:
         perturbation_rounding(config);
     }
 
-    double lower_bound() { double lb = 0; check(bddb200_lower_bound(solver_, &lb)); return lb; }
+    double lower_bound() { require_solver(); double lb = 0; check(bddb200_lower_bound(solver_, &lb)); return lb; }
+    // bdd_solver::min_marginals (bdd_solver.cpp:497-514): per variable the (mm_lo, mm_hi) pair of each BDD it occurs in.  The reference
+    // throws for its CUDA solvers; the GPU min-marginal sweep of this build answers.
+    std::vector<std::vector<std::array<double, 2>>> min_marginals()
+    {
+        require_solver();
+        const size_t nl = bddb200_nr_layers(solver_), nv = bddb200_nr_variables(solver_), nb = bddb200_nr_bdds(solver_);
+        std::vector<int32_t> var(nl);
+        std::vector<double> lo(nl), hi(nl);
+        check(bddb200_min_marginals_host(solver_, 1, var.data(), lo.data(), hi.data()));
+        std::vector<std::vector<std::array<double, 2>>> out(nv);
+        for(size_t i = 0; i + nb < nl; ++i) out[(size_t)var[i]].push_back({lo[i], hi[i]});       // sorted by variable, the terminal entries last
+        return out;
+    }
+    // export_min_marginals_with_names: (variable name, mm_lo, mm_hi) averaged over the variable's BDDs
+    std::tuple<std::vector<std::string>, std::vector<double>, std::vector<double>> min_marginals_with_variable_names()
+    {
+        const auto mms = min_marginals();
+        std::tuple<std::vector<std::string>, std::vector<double>, std::vector<double>> out;
+        for(size_t v = 0; v < mms.size() && v < ilp_.nr_variables(); ++v)
+        {
+            double l = 0, h = 0;
+            for(const auto& m : mms[v]) { l += m[0]; h += m[1]; }
+            const double n = std::max<size_t>(mms[v].size(), 1);
+            std::get<0>(out).push_back(ilp_.var_names[v]); std::get<1>(out).push_back(l / n); std::get<2>(out).push_back(h / n);
+        }
+        return out;
+    }
     double dual_lower_bound() const { return dual_lower_bound_; }     // the bound solve_dual ended with (rounding perturbs the costs afterwards)
     const std::vector<char>& solution() const { return solution_; }
     bool has_solution() const { return solved_; }
@@ -392,6 +421,7 @@ private:
     {
         if(code != BDDB200_OK) throw std::runtime_error(std::string("bdd_b200: ") + bddb200_last_error());
     }
+    void require_solver() const { if(solver_ == nullptr) throw std::runtime_error("bdd_solver: no solver constructed yet (call solve first)"); }
     void log(const std::string& s) const { if(verbose) std::fprintf(stderr, "%s\n", s.c_str()); }
 
     // bdd_solver.cpp:44-66

@@ -74,6 +74,43 @@ class bdd_cuda_parallel_mma:
             self.lib.bddb200_destroy(h)
             self.h = None
 
+    # ------------------------------------------------------------------ save / load ----
+    def save(self) -> bytes:
+        """The whole solver state as one blob (cereal save of the reference class, bdd_cuda_base.cu:1486-1544; what the
+        reference's pybind module pickles, bdd_cuda_parallel_mma_py.cu:29-38)."""
+        n = C.c_size_t()
+        check(self.lib.bddb200_save_size(self.h, C.byref(n)))
+        buf = (C.c_ubyte * n.value)()
+        check(self.lib.bddb200_save(self.h, buf, n.value, C.byref(n)))
+        return bytes(buf)[: n.value]
+
+    @classmethod
+    def load(cls, blob: bytes, device: int = 0) -> "bdd_cuda_parallel_mma":
+        """A new solver from ``save()``'s blob, on ``device`` (same GPU model), running on a stream of its own."""
+        self = cls.__new__(cls)
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("bdd_cuda_parallel_mma needs a CUDA device (no CPU fallback)")
+        h = C.c_void_p()
+        raw = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        check(self.lib.bddb200_load(raw, len(blob), device, C.byref(h)))
+        self.h = h
+        self.precision = "double" if self.lib.bddb200_precision_of(h) == _lib.DOUBLE else "float"
+        self.value_type = torch.float64 if self.precision == "double" else torch.float32
+        self.np_type = np.float64 if self.precision == "double" else np.float32
+        self.device = torch.device("cuda", device)
+        self.stream = torch.cuda.ExternalStream(self.lib.bddb200_stream(h), device=self.device)
+        self._nbpv = None
+        return self
+
+    def __getstate__(self):
+        return {"blob": self.save(), "device": self.device.index}
+
+    def __setstate__(self, state):
+        other = type(self).load(state["blob"], state["device"])
+        self.__dict__.update(other.__dict__)
+        other.h = None
+
     # ------------------------------------------------------------------ helpers --------
     def _empty(self, n: int, dtype=None) -> torch.Tensor:
         with torch.cuda.stream(self.stream):

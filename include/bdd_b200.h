@@ -94,9 +94,41 @@ int bddb200_create(const bddb200_instruction* instrs_host, size_t n_instr,
                    const double* costs_hi_host, size_t n_costs,
                    int precision, const bddb200_options* opts, bddb200_solver** out);
 void bddb200_destroy(bddb200_solver* s);
+
+/* ---- constraint-sharded construction (multi-GPU) ----------------------------------------
+ * One process per GPU calls bddb200_create_shard with the WHOLE collection and its (rank, world): the library cuts the collection
+ * into `world` contiguous blocks of BDDs with balanced node counts, renumbers the variables so that those occurring in more than
+ * one block come first ([0, n_shared): only that prefix of the per-variable sums crosses NVLink), and builds this rank's solver in
+ * shard mode (global nr_bdds_per_var, costs split by the global count -- the hybrid solver's split,
+ * bdd_multi_parallel_mma_base.cu:121-124, 191-215).  new_of_old_out (nr_variables entries, may be NULL) receives the renumbering;
+ * solver vectors indexed by variable (delta sums, min-marginals) use the NEW numbering.  bddb200_plan_shard is the planning step
+ * alone (no GPU needed); counts_new_out = global BDD count per NEW variable index.  Afterwards register the symmetric sum buffers
+ * and the exchange (bddb200_set_delta_buffers, bddb200_set_exchange with n_exchange = 2 * n_shared); shared_entries (this shard's
+ * layer entries of shared variables) is what decides between the push exchange (mode 4, few) and the pull forms (many). */
+typedef struct bddb200_shard_info {
+    size_t nr_variables;   /* of the whole problem */
+    size_t n_shared;       /* variables that occur in more than one shard */
+    size_t shared_entries; /* this shard's layer entries of shared variables */
+    size_t first_bdd;      /* this rank's block of BDDs: [first_bdd, first_bdd + n_bdds) */
+    size_t n_bdds;
+} bddb200_shard_info;
+int bddb200_plan_shard(const bddb200_instruction* instrs_host, size_t n_instr, const size_t* delimiters_host, size_t n_bdds,
+                       size_t nr_variables_min, int world, int rank, bddb200_shard_info* info,
+                       int32_t* new_of_old_out, int32_t* counts_new_out);
+int bddb200_create_shard(const bddb200_instruction* instrs_host, size_t n_instr, const size_t* delimiters_host, size_t n_bdds,
+                         const double* costs_hi_host, size_t n_costs, int precision, const bddb200_options* opts,
+                         int world, int rank, bddb200_shard_info* info, int32_t* new_of_old_out, bddb200_solver** out);
 /* copy constructor of the reference class (all its members are thrust::device_vectors): a deep
  * copy with its own stream on the same device */
 int bddb200_clone(const bddb200_solver* s, bddb200_solver** out);
+/* cereal save / load of the reference class (bdd_cuda_base.cu:1486-1544, bdd_cuda_parallel_mma.cu:475-490; what its pybind module
+ * pickles, bdd_cuda_parallel_mma_py.cu:29-38): the whole solver state -- layout, costs, pending sums, validity flags -- as one
+ * byte blob.  bddb200_save writes at most `bytes` bytes and reports the blob size (ask bddb200_save_size first); bddb200_load builds
+ * a new solver from a blob on `device` (same GPU model as the one it was saved on: the launch plan is part of the blob).  Solvers
+ * whose sum buffers live in caller-owned memory (multi-GPU exchange) cannot be saved (BDDB200_ERR_STATE). */
+int bddb200_save_size(const bddb200_solver* s, size_t* bytes_out);
+int bddb200_save(const bddb200_solver* s, void* buf, size_t bytes, size_t* written_out);
+int bddb200_load(const void* buf, size_t bytes, int device, bddb200_solver** out);
 
 /* ---- sizes (bdd_cuda_base.h:101-117) -------------------------------------------------- */
 size_t bddb200_nr_variables(const bddb200_solver* s);
@@ -166,6 +198,9 @@ int bddb200_primal_objective_host(bddb200_solver* s, double* out_host);
  * as min_marginals_cuda(true); sorted = 0: layer order.  All outputs have nr_layers entries
  * and may be NULL. */
 int bddb200_min_marginals(bddb200_solver* s, int sorted, int32_t* primal_index_dev, void* mm_lo_dev, void* mm_hi_dev);
+/* the same into HOST memory as doubles (what min_marginals() returns to host callers, bdd_cuda_base.cu:753-786, and what
+ * bdd_solver::min_marginals hands to Python, bdd_solver.cpp:497-514) */
+int bddb200_min_marginals_host(bddb200_solver* s, int sorted, int32_t* primal_index_host, double* mm_lo_host, double* mm_hi_host);
 
 /* ---- L-BFGS support surface (include/bdd_solver/lbfgs.h:22-27) -------------------------- */
 int bddb200_bdds_solution(bddb200_solver* s, char* sol_dev);                 /* bdds_solution_vec, bdd_cuda_base.cu:1137-1202 */

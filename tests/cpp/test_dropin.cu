@@ -16,9 +16,11 @@
 #include "bdd_conversion/convert_pb_to_bdd.h"
 #include "bdd_manager/bdd_mgr.h"
 #include "run_solver_util.h"
+#include <cereal/archives/binary.hpp>
 #include <cmath>
 #include <cstdio>
 #include <iostream>
+#include <sstream>
 #include <numeric>
 #include <random>
 #include <variant>
@@ -202,6 +204,32 @@ static void test_run_solver_and_variant(const Problem& p)
     std::printf("run_solver / variant / copy %-14s: lb %.9f\n", p.name, lb);
 }
 
+// cereal round trip as the reference's pybind module pickles a solver (src/bdd_solver/bdd_cuda_parallel_mma_py.cu:15-38): archive(solver)
+// calls the member save / load templates
+static void test_save_load(const Problem& p)
+{
+    BDD::bdd_collection bdd_col = build_collection(p);
+    bdd_cuda_parallel_mma<double> a(bdd_col, p.objective);
+    for(int i = 0; i < 3; ++i) a.iteration();
+    std::stringstream ss;
+    {
+        cereal::BinaryOutputArchive out(ss);
+        a.save(out);
+    }
+    bdd_cuda_parallel_mma<double> b;
+    {
+        cereal::BinaryInputArchive in(ss);
+        b.load(in);
+        b.init();
+    }
+    CHECK(b.nr_variables() == a.nr_variables() && b.nr_bdds() == a.nr_bdds() && b.nr_layers() == a.nr_layers() && b.nr_hops() == a.nr_hops());
+    CHECK(b.lower_bound() == a.lower_bound());
+    for(int i = 0; i < 200; ++i) { a.iteration(); b.iteration(); }
+    CHECK(std::abs(a.lower_bound() - b.lower_bound()) < 1e-9);
+    CHECK(std::abs(b.lower_bound() - p.expected_lb) < 1e-3);
+    std::printf("cereal save / load        %-14s: lb %.9f\n", p.name, b.lower_bound());
+}
+
 // L-BFGS support surface as lbfgs<> uses it (include/bdd_solver/lbfgs.h:22-27, src/bdd_solver/lbfgs_impl.h)
 static void test_lbfgs_surface(const Problem& p)
 {
@@ -263,6 +291,8 @@ int main()
     test_known_answer<double>(problems[1], 1e-12);
     test_known_answer<float>(problems[0], 1e-4);
     test_run_solver_and_variant(problems[1]);
+    test_save_load(problems[1]);
+    test_save_load(problems[0]);
     test_lbfgs_surface(problems[1]);
     test_lbfgs_wrapper(problems[1]);
     test_lbfgs_wrapper(problems[0]);

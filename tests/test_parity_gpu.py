@@ -198,6 +198,41 @@ def test_iterations_graph_equals_repeated_iteration():
     assert a.lower_bound() == b.lower_bound()
 
 
+@pytest.mark.parametrize("precision", ["double", "float"])
+@pytest.mark.parametrize("deterministic", [False, True])
+def test_save_load_continues_the_solve(precision, deterministic):
+    """cereal save / load of the reference class (bdd_cuda_base.cu:1486-1544; pickled by bdd_cuda_parallel_mma_py.cu:29-38):
+    a solver restored from its blob in the middle of a solve (pending sums, forward state) continues exactly like the original."""
+    import pickle
+    g = load("mrf_grid_graph_3x3")
+    col = _col(g["instrs"], g["delims"])
+    a = solver(col, g["costs"], precision, deterministic=deterministic)
+    a.iterations(5)
+    a.forward_pass(0.5)      # saved between the two passes of an iteration
+    b = type(a).load(a.save(), device=0)
+    c = pickle.loads(pickle.dumps(a))
+    assert (b.nr_variables(), b.nr_bdds(), b.nr_layers(), b.nr_bdd_nodes(), b.precision) == (a.nr_variables(), a.nr_bdds(), a.nr_layers(), a.nr_bdd_nodes(), a.precision)
+    for s in (a, b, c):
+        s.backward_pass(0.5)
+        s.iterations(4)
+    lb = a.lower_bound()
+    if deterministic:
+        assert b.lower_bound() == lb and c.lower_bound() == lb
+        assert torch.equal(a.get_delta(), b.get_delta()) and torch.equal(a.get_delta(), c.get_delta())
+    else:
+        assert abs(b.lower_bound() - lb) <= tol(precision, lb) and abs(c.lower_bound() - lb) <= tol(precision, lb)
+        assert torch.allclose(a.get_delta(), b.get_delta(), rtol=0, atol=tol(precision) * 10)
+    # known answer after the remaining iterations (test/test_bdd_cuda_parallel_mma.cu:197-247: -8 after 200 iterations + distribute_delta)
+    if precision == "double":
+        b.iterations(200)
+        b.distribute_delta()
+        assert abs(b.lower_bound() - EXPECTED["mrf_grid_graph_3x3"]["lb"]) <= 1e-9
+    with pytest.raises(Exception):
+        type(a).load(a.save()[:100], device=0)
+    with pytest.raises(Exception):
+        type(a).load(b"not a blob at all, but long enough", device=0)
+
+
 # ----------------------------------------------------------------------- min-marginals --
 @pytest.mark.parametrize("precision", ["double", "float"])
 @pytest.mark.parametrize("name", golden_names())
