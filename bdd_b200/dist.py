@@ -66,6 +66,23 @@ def global_nr_bdds_per_var(col: BddCollection, nr_variables: Optional[int] = Non
     return np.bincount(var, minlength=n).astype(np.int32)
 
 
+def plan_shard_native(col: BddCollection, world: int, rank: int, nr_variables_min: int = 0):
+    """The library's own shard planning (``bddb200_plan_shard``, bdd_b200/csrc/shard.hpp; no GPU needed): (info dict, new_of_old,
+    global BDD count per NEW variable index).  Same rules as partition_bdds / shared_first_relabeling / global_nr_bdds_per_var."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    instrs = np.ascontiguousarray(col.instrs, dtype=np.uint64)
+    delims = np.ascontiguousarray(col.delims, dtype=np.uint64)
+    n_vars = max(col.nr_variables(), nr_variables_min)
+    new_of_old = np.empty(n_vars, dtype=np.int32)
+    counts_new = np.empty(n_vars, dtype=np.int32)
+    info = _lib.ShardInfo()
+    _lib.check(lib.bddb200_plan_shard(instrs.ctypes.data, instrs.shape[0], delims.ctypes.data, delims.shape[0] - 1, nr_variables_min, world, rank,
+                                      C.byref(info), new_of_old.ctypes.data, counts_new.ctypes.data))
+    return {k: int(getattr(info, k)) for k, _ in _lib.ShardInfo._fields_}, new_of_old.astype(np.int64), counts_new
+
+
 def shared_first_relabeling(col: BddCollection, parts: List[np.ndarray], nr_vars: int) -> Tuple[np.ndarray, int]:
     """new_of_old[v] = index of variable v after moving the variables that occur in more than one
     shard to the front (both groups keep their relative order), and the number of shared ones."""
@@ -201,6 +218,18 @@ class sharded_mma:
         costs = np.asarray(costs, dtype=np.float64)
         if costs.shape[0] < self.nr_vars:
             costs = np.concatenate([costs, np.zeros(self.nr_vars - costs.shape[0])])
+        self._col = col
+        if isinstance(make_local, dict):
+            # native path: partition, relabelling, global counts and the shard-mode solver all come from the library
+            # (bddb200_create_shard); make_local = {"precision": ..., "device": ..., "deterministic": ...}
+            from .solver import bdd_cuda_parallel_mma
+            self.local, info, self.new_of_old = bdd_cuda_parallel_mma.create_shard(col, costs, rank, world, **make_local)
+            self.nr_vars = info["nr_variables"]
+            self.n_shared = info["n_shared"]
+            self.ids = np.arange(info["first_bdd"], info["first_bdd"] + info["n_bdds"])
+            self._local_col = None
+            self._finish_setup(exchange, info["shared_entries"])
+            return
         parts = partition_bdds(col, world)
         if shard_ids is not None:
             # explicit shard of this rank: the relabelling needs every rank's shard, so all variables count as shared
@@ -214,8 +243,20 @@ class sharded_mma:
         self.counts[self.new_of_old] = counts
         costs_new = np.empty_like(costs)
         costs_new[self.new_of_old] = costs
-        self.local_col = relabel_variables(col.select(self.ids), self.new_of_old)
-        self.local = make_local(self.local_col, costs_new, self.nr_vars, self.counts)
+        self._local_col = relabel_variables(col.select(self.ids), self.new_of_old)
+        self.local = make_local(self._local_col, costs_new, self.nr_vars, self.counts)
+        lv, _ = _layer_heads(self._local_col)
+        self._finish_setup(exchange, int((lv < self.n_shared).sum()))        # layer entries of this shard that push across NVLink
+
+    @property
+    def local_col(self) -> BddCollection:
+        """This rank's sub-collection with relabelled variables (built on demand on the native path)."""
+        if self._local_col is None:
+            self._local_col = relabel_variables(self._col.select(self.ids), self.new_of_old)
+        return self._local_col
+
+    def _finish_setup(self, exchange: Optional[str], shared_entries: int):
+        rank, world, group = self.rank, self.world, self.group
         self.n_exchange = 2 * self.n_shared
         self.symm = None
         want = exchange or os.environ.get("BDDB200_EXCHANGE", "auto")
@@ -223,13 +264,6 @@ class sharded_mma:
         if want in ("auto", "symm") and is_cuda_local:
             ok = torch.ones(1, device=self.local.device)
             try:
-                lv_all = self.local_col.instrs[:, 2]
-                inner = lv_all < BOTSINK
-                lv = lv_all[inner].astype(np.int64)
-                bdd_of = np.repeat(np.arange(self.local_col.nr_bdds), np.diff(self.local_col.delims.astype(np.int64)))[inner]
-                head = np.ones(lv.shape[0], dtype=bool)
-                head[1:] = (lv[1:] != lv[:-1]) | (bdd_of[1:] != bdd_of[:-1])
-                shared_entries = int((lv[head] < self.n_shared).sum())        # layer entries of this shard that push across NVLink
                 self.symm = SymmExchange(self.local, self.nr_vars, self.n_exchange, rank, world, group, shared_entries)
             except Exception as e:          # no symmetric-memory support on this box: every rank must fall back together
                 if want == "symm":
@@ -300,6 +334,12 @@ class sharded_mma:
                 lb = lb.to(dev)
             dist.all_reduce(lb, op=dist.ReduceOp.SUM, group=self.group)     # on the current stream; .item() waits for it
         return float(lb.item())
+
+
+def make_cuda_native(precision: str, device: int, deterministic: bool = False) -> dict:
+    """``make_local`` argument that selects the native path of ``sharded_mma``: the library plans the shard and builds its solver
+    (``bddb200_create_shard``); nothing but the collection itself is prepared in Python."""
+    return {"precision": precision, "device": device, "deterministic": deterministic}
 
 
 def make_cuda_local(precision: str, device: int, deterministic: bool = False):

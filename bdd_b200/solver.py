@@ -103,6 +103,45 @@ class bdd_cuda_parallel_mma:
         self._nbpv = None
         return self
 
+    @classmethod
+    def create_shard(cls, bdd_col: BddCollection, costs: Optional[Sequence[float]], rank: int, world: int, precision: str = "float",
+                     device: int = 0, deterministic: bool = False):
+        """This rank's solver of a ``world``-way constraint-sharded solve, planned and built inside the library
+        (``bddb200_create_shard``): returns (solver, info dict, new_of_old).  Solver vectors indexed by variable use the NEW numbering."""
+        self = cls.__new__(cls)
+        self.lib = _lib.load()
+        if precision not in ("float", "double"):
+            raise ValueError("precision must be 'float' or 'double'")
+        if not torch.cuda.is_available():
+            raise RuntimeError("bdd_cuda_parallel_mma needs a CUDA device (no CPU fallback)")
+        self.precision = precision
+        self.value_type = torch.float64 if precision == "double" else torch.float32
+        self.np_type = np.float64 if precision == "double" else np.float32
+        self.device = torch.device("cuda", device)
+        self.stream = torch.cuda.Stream(self.device)
+        instrs = np.ascontiguousarray(bdd_col.instrs, dtype=np.uint64)
+        delims = np.ascontiguousarray(bdd_col.delims, dtype=np.uint64)
+        opts = Options()
+        self.lib.bddb200_default_options(C.byref(opts))
+        opts.device = device
+        opts.stream = self.stream.cuda_stream
+        opts.deterministic = int(deterministic)
+        self._nbpv = None
+        cptr, ncost = None, 0
+        if costs is not None:
+            self._costs = np.ascontiguousarray(costs, dtype=np.float64)
+            cptr, ncost = self._costs.ctypes.data, self._costs.shape[0]
+        n_vars = max(bdd_col.nr_variables(), ncost)
+        new_of_old = np.empty(n_vars, dtype=np.int32)
+        info = _lib.ShardInfo()
+        h = C.c_void_p()
+        check(self.lib.bddb200_create_shard(instrs.ctypes.data, instrs.shape[0], delims.ctypes.data, delims.shape[0] - 1, cptr, ncost,
+                                            _lib.DOUBLE if precision == "double" else _lib.FLOAT, C.byref(opts), world, rank,
+                                            C.byref(info), new_of_old.ctypes.data, C.byref(h)))
+        self.h = h
+        d = {k: int(getattr(info, k)) for k, _ in _lib.ShardInfo._fields_}
+        return self, d, new_of_old.astype(np.int64)
+
     def __getstate__(self):
         return {"blob": self.save(), "device": self.device.index}
 

@@ -320,7 +320,7 @@ def measure(env: Env, workload: str, K: int, W: int, with_cpu: bool, with_e2e: b
 
     t_c0 = time.perf_counter()
     if world > 1:
-        solver = bdist.sharded_mma(col, costs, rank, world, bdist.make_cuda_local(precision, env.local_rank))
+        solver = bdist.sharded_mma(col, costs, rank, world, bdist.make_cuda_native(precision, env.local_rank))      # the library plans and builds the shard
         local = solver.local
         local_sh = shape_numbers(solver.local_col, V)
     elif lbfgs:
@@ -556,7 +556,7 @@ def dist_parity(env: Env) -> bool:
     ok = True
     col, costs = instances.set_cover(m=3000, n=5000, k=9, seed=5)
     for precision, tol in (("double", 1e-9), ("float", 2e-4)):
-        sh = bdist.sharded_mma(col, costs, env.rank, env.world, bdist.make_cuda_local(precision, env.local_rank))
+        sh = bdist.sharded_mma(col, costs, env.rank, env.world, bdist.make_cuda_native(precision, env.local_rank))
         whole = bdd_cuda_parallel_mma(col, costs, precision=precision, device=env.local_rank)
         local_new = np.unique(sh.local_col.instrs[sh.local_col.instrs[:, 2] < BOTSINK, 2].astype(np.int64))
         local_vars = np.argsort(sh.new_of_old)[local_new]

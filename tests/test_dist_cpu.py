@@ -134,3 +134,29 @@ def test_partition_and_counts():
     sub = col.select(parts[1])
     so = B.Oracle(sub.instrs, sub.delims, None, "double")
     assert so.n_bdds == len(parts[1])
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_native_shard_plan_equals_the_numpy_one(world):
+    """bddb200_plan_shard (bdd_b200/csrc/shard.hpp, what bddb200_create_shard builds a rank's solver from) against partition_bdds /
+    shared_first_relabeling / global_nr_bdds_per_var on four instance shapes; host only."""
+    from bdd_b200 import dist as bdist, instances
+    from bdd_b200.dist import _layer_heads
+    cases = [instances.set_cover(m=300, n=500, k=7, seed=3), instances.grid_mrf(9, 7, 3, seed=6), instances.qap(n=5, seed=7), instances.assignment(12, seed=2)]
+    for col, costs in cases:
+        n_vars = col.nr_variables()
+        parts = bdist.partition_bdds(col, world)
+        new_of_old, n_shared = bdist.shared_first_relabeling(col, parts, n_vars)
+        counts = bdist.global_nr_bdds_per_var(col, n_vars)
+        for rank in range(world):
+            info, noo, counts_new = bdist.plan_shard_native(col, world, rank)
+            assert info["nr_variables"] == n_vars and info["n_shared"] == n_shared
+            assert (info["first_bdd"], info["n_bdds"]) == ((int(parts[rank][0]) if len(parts[rank]) else info["first_bdd"]), len(parts[rank]))
+            assert np.array_equal(noo, new_of_old)
+            want = np.empty_like(counts); want[new_of_old] = counts
+            assert np.array_equal(counts_new, want)
+            local = bdist.relabel_variables(col.select(parts[rank]), new_of_old) if len(parts[rank]) else None
+            entries = int((_layer_heads(local)[0] < n_shared).sum()) if local is not None else 0
+            assert info["shared_entries"] == entries
+    with pytest.raises(Exception):
+        bdist.plan_shard_native(cases[0][0], 2, 2)

@@ -29,7 +29,9 @@ def main():
     for name, gen in cases.items():
         col, costs = gen()
         for precision, det, tol in (("double", True, 1e-9), ("double", False, 1e-9), ("float", False, 2e-4)):
-            sh = bdist.sharded_mma(col, costs, rank, world, bdist.make_cuda_local(precision, local, deterministic=det),
+            # BDDB200_SHARD_NATIVE=0: shard planned in numpy (dist.py); default: by the library (bddb200_create_shard)
+            mk = bdist.make_cuda_local if os.environ.get("BDDB200_SHARD_NATIVE", "1") == "0" else bdist.make_cuda_native
+            sh = bdist.sharded_mma(col, costs, rank, world, mk(precision, local, deterministic=det),
                                    exchange=os.environ.get("BDDB200_EXCHANGE", "auto"))
             whole = bdd_cuda_parallel_mma(col, costs, precision=precision, device=local, deterministic=det)
             lb_s, lb_w = sh.lower_bound(), whole.lower_bound()
