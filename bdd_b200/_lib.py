@@ -28,7 +28,7 @@ SYMBOLS = [
     "bddb200_min_marginals", "bddb200_min_marginals_host", "bddb200_bdds_solution", "bddb200_net_solver_costs", "bddb200_make_dual_feasible",
     "bddb200_gradient_step", "bddb200_synchronize", "bddb200_stream", "bddb200_kernel_launches",
     "bddb200_delta_sum_buffer", "bddb200_layout_stats", "bddb200_trace_pass",
-    "bddb200_delta_sum_index", "bddb200_push_exchange_supported", "bddb200_set_delta_buffers", "bddb200_set_delta_input", "bddb200_set_exchange", "bddb200_delta_exchange", "bddb200_delta_exchange_two_shot",
+    "bddb200_delta_sum_index", "bddb200_push_exchange_supported", "bddb200_set_push_masks", "bddb200_set_delta_buffers", "bddb200_set_delta_input", "bddb200_set_exchange", "bddb200_delta_exchange", "bddb200_delta_exchange_two_shot",
     "bddb200_run_solver", "bddb200_rounding_perturb", "bddb200_incremental_mm_agreement_rounding",
     "bddb200_lbfgs_create", "bddb200_lbfgs_destroy", "bddb200_lbfgs_iteration", "bddb200_lbfgs_flush", "bddb200_lbfgs_stats",
 ]
@@ -74,7 +74,7 @@ def load() -> C.CDLL:
         "bddb200_create": (i, [vp, sz, vp, sz, vp, sz, i, C.POINTER(Options), C.POINTER(vp)]),
         "bddb200_destroy": (None, [vp]),
         "bddb200_clone": (i, [vp, C.POINTER(vp)]),
-        "bddb200_plan_shard": (i, [vp, sz, vp, sz, sz, i, i, C.POINTER(ShardInfo), vp, vp]),
+        "bddb200_plan_shard": (i, [vp, sz, vp, sz, sz, i, i, C.POINTER(ShardInfo), vp, vp, vp]),
         "bddb200_create_shard": (i, [vp, sz, vp, sz, vp, sz, i, C.POINTER(Options), i, i, C.POINTER(ShardInfo), vp, C.POINTER(vp)]),
         "bddb200_save_size": (i, [vp, C.POINTER(sz)]),
         "bddb200_save": (i, [vp, vp, sz, C.POINTER(sz)]),
@@ -134,6 +134,7 @@ def load() -> C.CDLL:
         "bddb200_lbfgs_stats": (i, [vp, C.POINTER(sz), C.POINTER(sz), C.POINTER(dbl)]),
         "bddb200_delta_sum_index": (i, [vp, C.POINTER(i)]),
         "bddb200_push_exchange_supported": (i, [vp, C.POINTER(i)]),
+        "bddb200_set_push_masks": (i, [vp, vp, sz]),
         "bddb200_set_delta_buffers": (i, [vp, vp, vp, vp]),
         "bddb200_set_delta_input": (i, [vp, vp, sz]),
         "bddb200_set_exchange": (i, [vp, i, i, vp, vp, vp, vp, vp, vp, sz, i]),

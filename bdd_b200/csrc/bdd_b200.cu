@@ -106,6 +106,7 @@ struct bddb200_solver {
     virtual int rounding_perturb(double delta, int round_index, unsigned long long counts_out[4], char* types_dev, char* sol_host) = 0;
     virtual int delta_sum_index() const = 0;
     virtual int push_exchange_supported() const = 0;
+    virtual void set_push_masks(const uint16_t* masks_host, size_t n) = 0;
     virtual void set_delta_buffers(void* b0, void* b1, void* b2) = 0;
     virtual void set_delta_input(void* in, size_t n_shared_vars) = 0;
     virtual void set_exchange(int world, int rank, const void* const* peers, uint32_t* const* flags, void* out, void* const* outs,
@@ -744,7 +745,7 @@ public:
         if(xc_.mode == 4 && delta_in == dbuf(dcur_) && delta_out == dbuf((dcur_ + 1) % 3))
         {   // push exchange: shared variables' differences go to every rank's buffer through the multicast mapping; the flag barrier
             // is the tail of this launch and the prologue of the next one
-            a.delta_out_mc = const_cast<REAL*>(xc_.mc_in) + (delta_out - dbuf(0));
+            a.push_peers = reinterpret_cast<REAL* const*>(const_cast<void* const*>(xc_.peers)); a.push_offset = (size_t)(delta_out - dbuf(0)); a.push_mask = d_push_mask_.p;
             a.n_push_vars = (uint32_t)(xc_.n_exchange / 2);
             a.push_counters = d_xc_counters_.p; a.push_flags = xc_.flags; a.push_my_flags = xc_.my_flags;
             a.push_world = xc_.world; a.push_rank = xc_.rank;
@@ -790,7 +791,7 @@ public:
         if(world < 2 || world > EXCHANGE_MAX_WORLD || rank < 0 || rank >= world || flags == nullptr || (n_exchange & 1) || n_exchange > 2 * n_vars_ || ext_delta_[0] == nullptr)
             throw api_error(BDDB200_ERR_INVALID_ARGUMENT, "set_exchange: invalid argument (the sum buffers must be set with set_delta_buffers first)");
         if((mode == 1 && (peers == nullptr || out == nullptr)) || (mode == 2 && (peers == nullptr || outs == nullptr)) || (mode == 3 && (mc_in == nullptr || mc_out == nullptr))
-           || (mode == 4 && mc_in == nullptr) || mode < 0 || mode > 4)
+           || (mode == 4 && peers == nullptr) || mode < 0 || mode > 4)
             throw api_error(BDDB200_ERR_INVALID_ARGUMENT, "set_exchange: buffers missing for the requested mode");
         if(mode == 4 && (deterministic_ || n_lane_ != n_bundles_ || delta_in_override_ != nullptr))
             throw api_error(BDDB200_ERR_STATE, "set_exchange: the push exchange needs the default (atomic) sums, a collection of lane-class bundles only and no separate input buffer");
@@ -802,6 +803,13 @@ public:
         if(mode == 4)
         {   // this rank's own flag array (the passes poll it; peers write it), and which bundles take part in the flag barrier
             CUDA_CHECK(cudaMemcpyAsync(&xc_.my_flags, flags + rank, sizeof(uint32_t*), cudaMemcpyDeviceToHost, stream_));
+            // which other ranks hold each shared variable (bddb200_create_shard / bddb200_set_push_masks); without that knowledge: all of them
+            {
+                const size_t n_sh = n_exchange / 2;
+                std::vector<uint16_t> m(std::max<size_t>(n_sh, 1), (uint16_t)(((1u << world) - 1u) & ~(1u << rank)));
+                if(h_push_mask_.size() >= n_sh) for(size_t v = 0; v < n_sh; ++v) m[v] = (uint16_t)(h_push_mask_[v] & ((1u << world) - 1u) & ~(1u << rank));
+                d_push_mask_.upload(m, stream_);
+            }
             DevBuf<unsigned char> d_shared; d_shared.alloc(n_lane_);
             push_mark_bundles_kernel<<<blocks_for(n_lane_, 8), 256, 0, stream_>>>(d_desc_lane_.p, d_lay_vn_.p, (uint32_t)n_lane_, (uint32_t)(n_exchange / 2), d_shared.p);
             CUDA_CHECK(cudaGetLastError());
@@ -994,6 +1002,7 @@ public:
 
     void* delta_sum_buffer() override { set_device(); ensure_sums(); push_barrier(1); return dbuf(dcur_); }
     int delta_sum_index() const override { return dcur_; }
+    void set_push_masks(const uint16_t* masks_host, size_t n) override { h_push_mask_.assign(masks_host, masks_host + n); }
     int push_exchange_supported() const override { return !deterministic_ && n_lane_ == n_bundles_ ? 1 : 0; }
     // Multi-GPU exchange over peer memory: the three rotating sum buffers live in caller-owned (symmetric) memory, and the
     // passes read the exchanged sums from a separate buffer (bddb200_delta_exchange writes it).
@@ -1455,6 +1464,8 @@ private:
     } xc_;
     DevBuf<uint32_t> d_xc_counters_;         // {exchanges completed, CTAs finished, error, ...}: the device-side epoch of the exchange kernels; push exchange: CTA counts
     uint32_t xc_phase_ = 0;                  // push exchange: number of push barriers issued so far, mod 3
+    std::vector<uint16_t> h_push_mask_;      // push exchange: per shared variable the ranks whose shards contain it (bit r = rank r), from the shard plan
+    DevBuf<uint16_t> d_push_mask_;           // ... without this rank's own bit
     DevBuf<LaneDesc> d_desc_push_;           // push exchange: the lane-class bundle descriptors in launch order (bundles with a variable shared between shards first, marked)
     REAL* delta_in_override_ = nullptr;      // exchanged sums of the variables [0, n_shared_vars_)
     size_t n_shared_vars_ = 0;
@@ -1598,7 +1609,7 @@ int bddb200_create(const bddb200_instruction* instrs, size_t n_instr, const size
 }
 // ---- constraint-sharded construction: one rank's solver of a `world`-way split, planned and built in the library ----
 int bddb200_plan_shard(const bddb200_instruction* instrs, size_t n_instr, const size_t* delims, size_t n_bdds, size_t nr_variables_min,
-                       int world, int rank, bddb200_shard_info* info, int32_t* new_of_old_out, int32_t* counts_new_out)
+                       int world, int rank, bddb200_shard_info* info, int32_t* new_of_old_out, int32_t* counts_new_out, uint16_t* share_mask_out)
 {
     (void)n_instr;
     if(instrs == nullptr || delims == nullptr || info == nullptr || n_bdds == 0) { g_last_error = "null argument"; return BDDB200_ERR_INVALID_ARGUMENT; }
@@ -1609,6 +1620,7 @@ int bddb200_plan_shard(const bddb200_instruction* instrs, size_t n_instr, const 
         info->nr_variables = p.n_vars; info->n_shared = p.n_shared; info->shared_entries = p.shared_entries; info->first_bdd = p.first_bdd; info->n_bdds = p.n_bdds;
         if(new_of_old_out) std::memcpy(new_of_old_out, p.new_of_old.data(), p.n_vars * sizeof(int32_t));
         if(counts_new_out) std::memcpy(counts_new_out, p.counts_new.data(), p.n_vars * sizeof(int32_t));
+        if(share_mask_out) std::memcpy(share_mask_out, p.share_mask.data(), p.n_shared * sizeof(uint16_t));
     });
 }
 int bddb200_create_shard(const bddb200_instruction* instrs, size_t n_instr, const size_t* delims, size_t n_bdds, const double* costs_hi, size_t n_costs,
@@ -1638,6 +1650,7 @@ int bddb200_create_shard(const bddb200_instruction* instrs, size_t n_instr, cons
         if(precision == BDDB200_DOUBLE) *out = new SolverImpl<double>(base, i1, delims + p.first_bdd, p.n_bdds, costs_new.data(), costs_new.size(), o);
         else if(precision == BDDB200_FLOAT) *out = new SolverImpl<float>(base, i1, delims + p.first_bdd, p.n_bdds, costs_new.data(), costs_new.size(), o);
         else throw api_error(BDDB200_ERR_INVALID_ARGUMENT, "precision must be BDDB200_FLOAT or BDDB200_DOUBLE");
+        (*out)->set_push_masks(p.share_mask.data(), p.n_shared);
     });
 }
 void bddb200_destroy(bddb200_solver* s) { delete s; }
@@ -1824,6 +1837,12 @@ int bddb200_load(const void* buf, size_t bytes, int device, bddb200_solver** out
     });
 }
 int bddb200_delta_sum_index(const bddb200_solver* s, int* out) { REQUIRE_SOLVER(s); return guarded([&] { *out = s->delta_sum_index(); }); }
+int bddb200_set_push_masks(bddb200_solver* s, const uint16_t* masks_host, size_t n)
+{
+    REQUIRE_SOLVER(s);
+    if(masks_host == nullptr && n > 0) { g_last_error = "null argument"; return BDDB200_ERR_INVALID_ARGUMENT; }
+    return guarded([&] { s->set_push_masks(masks_host, n); });
+}
 int bddb200_push_exchange_supported(const bddb200_solver* s, int* out) { REQUIRE_SOLVER(s); return guarded([&] { *out = s->push_exchange_supported(); }); }
 int bddb200_set_delta_buffers(bddb200_solver* s, void* b0, void* b1, void* b2)
 {

@@ -23,6 +23,7 @@ struct ShardPlan {
     size_t first_bdd = 0, n_bdds = 0;     // this rank's contiguous block of BDDs
     std::vector<int32_t> new_of_old;      // relabelling (shared first; both groups keep their relative order)
     std::vector<int32_t> counts_new;      // global nr_bdds_per_var, indexed by the NEW variable index
+    std::vector<uint16_t> share_mask;     // per shared variable (new index): the shards that contain it, bit r = rank r (world <= 16)
 };
 
 // contiguous blocks of BDDs with balanced node counts (constraint order is kept: a grid-tile ordered instance gets compact shards)
@@ -49,7 +50,7 @@ inline std::vector<size_t> shard_bounds(const size_t* delims, size_t n_bdds, int
 
 inline ShardPlan plan_shard(const bddb200_instruction* instrs, const size_t* delims, size_t n_bdds, size_t n_vars_min, int world, int rank)
 {
-    if(world < 1 || rank < 0 || rank >= world) throw std::invalid_argument("plan_shard: rank / world");
+    if(world < 1 || world > 16 || rank < 0 || rank >= world) throw std::invalid_argument("plan_shard: rank / world (at most 16 ranks)");
     constexpr size_t BOT = (size_t)-2;
     ShardPlan p;
     const std::vector<size_t> bounds = shard_bounds(delims, n_bdds, world);
@@ -59,6 +60,7 @@ inline ShardPlan plan_shard(const bddb200_instruction* instrs, const size_t* del
         if(instrs[i].index < BOT) { max_var = std::max(max_var, instrs[i].index); any = true; }
     p.n_vars = std::max(n_vars_min, any ? max_var + 1 : (size_t)0);
     std::vector<int32_t> lo(p.n_vars, std::numeric_limits<int32_t>::max()), hi(p.n_vars, -1), counts(p.n_vars, 0);
+    std::vector<uint16_t> mask(p.n_vars, 0);
     int shard = 0;
     for(size_t b = 0; b < n_bdds; ++b)
     {
@@ -71,6 +73,7 @@ inline ShardPlan plan_shard(const bddb200_instruction* instrs, const size_t* del
             if(v != prev)
             {   // one layer entry per (variable, BDD): the nodes of a layer are adjacent (quasi-reduced, levelled BDDs)
                 lo[v] = std::min(lo[v], (int32_t)shard); hi[v] = std::max(hi[v], (int32_t)shard); ++counts[v];
+                mask[v] |= (uint16_t)(1u << shard);
                 prev = v;
             }
         }
@@ -82,6 +85,8 @@ inline ShardPlan plan_shard(const bddb200_instruction* instrs, const size_t* del
     for(size_t v = 0; v < p.n_vars; ++v) if(!(hi[v] > lo[v])) p.new_of_old[v] = (int32_t)k++;
     p.counts_new.assign(p.n_vars, 0);
     for(size_t v = 0; v < p.n_vars; ++v) p.counts_new[(size_t)p.new_of_old[v]] = counts[v];
+    p.share_mask.assign(p.n_shared, 0);
+    for(size_t v = 0; v < p.n_vars; ++v) if(hi[v] > lo[v]) p.share_mask[(size_t)p.new_of_old[v]] = mask[v];
     for(size_t b = p.first_bdd; b < p.first_bdd + p.n_bdds; ++b)
     {
         size_t prev = BOT;

@@ -77,10 +77,25 @@ def plan_shard_native(col: BddCollection, world: int, rank: int, nr_variables_mi
     n_vars = max(col.nr_variables(), nr_variables_min)
     new_of_old = np.empty(n_vars, dtype=np.int32)
     counts_new = np.empty(n_vars, dtype=np.int32)
+    masks = np.zeros(n_vars, dtype=np.uint16)
     info = _lib.ShardInfo()
     _lib.check(lib.bddb200_plan_shard(instrs.ctypes.data, instrs.shape[0], delims.ctypes.data, delims.shape[0] - 1, nr_variables_min, world, rank,
-                                      C.byref(info), new_of_old.ctypes.data, counts_new.ctypes.data))
-    return {k: int(getattr(info, k)) for k, _ in _lib.ShardInfo._fields_}, new_of_old.astype(np.int64), counts_new
+                                      C.byref(info), new_of_old.ctypes.data, counts_new.ctypes.data, masks.ctypes.data))
+    d = {k: int(getattr(info, k)) for k, _ in _lib.ShardInfo._fields_}
+    d["share_mask"] = masks[: d["n_shared"]].copy()       # per shared variable (new index): the shards that contain it, bit r = rank r
+    return d, new_of_old.astype(np.int64), counts_new
+
+
+def share_masks(col: BddCollection, parts: List[np.ndarray], new_of_old: np.ndarray, n_shared: int) -> np.ndarray:
+    """Per shared variable (new index) the shards that contain it, bit r = rank r (what the push exchange sends a variable's
+    differences to)."""
+    var, bdd = _layer_heads(col)
+    shard_of_bdd = np.empty(col.nr_bdds, dtype=np.int64)
+    for r, ids in enumerate(parts):
+        shard_of_bdd[ids] = r
+    m = np.zeros(new_of_old.shape[0], dtype=np.uint16)
+    np.bitwise_or.at(m, new_of_old[var], (1 << shard_of_bdd[bdd]).astype(np.uint16))
+    return m[:n_shared].copy()
 
 
 def shared_first_relabeling(col: BddCollection, parts: List[np.ndarray], nr_vars: int) -> Tuple[np.ndarray, int]:
@@ -112,12 +127,12 @@ def relabel_variables(col: BddCollection, new_of_old: np.ndarray) -> BddCollecti
 class SymmExchange:
     """Peer-memory exchange: sum buffers in symmetric memory, exchange kernels of the library issued BY the library after every
     pass (``bddb200_set_exchange``; the flag epochs live on the device, so ``iterations(n)`` replays pass + exchange as one CUDA
-    graph).  Modes: "push" no exchange kernel at all -- every pass adds the shared variables' differences to ALL ranks' buffers with
-    multimem.red through the multicast mapping and ends with a flag barrier that the next pass's prologue waits for (right when few
-    layer entries belong to shared variables: each is one small packet over NVLink); "mc" in-switch reduction of the finished sums
+    graph).  Modes: "push" no exchange kernel at all -- every pass adds the shared variables' differences to its own buffer and, with
+    peer-memory reductions over NVLink, to the buffers of the other ranks that hold the variable; the bundles with shared variables run
+    first and carry a flag barrier (right when few layer entries belong to shared variables: each is one small packet over NVLink);
+    "mc" in-switch reduction of the finished sums
     (multimem.ld_reduce / multimem.st), "1" one-shot reads of every peer, "2" two-shot.  "auto" = push when at most PUSH_MAX_ENTRIES
-    layer entries of any shard belong to shared variables and the box offers multicast, else one-shot below 6 ranks and mc / two-shot
-    from 6."""
+    layer entries of any shard belong to shared variables, else one-shot below 6 ranks and mc / two-shot from 6."""
 
     PUSH_MAX_ENTRIES = 1 << 16
 
@@ -149,14 +164,12 @@ class SymmExchange:
         has_mc = mc_in != 0
         if mode == "mc" and not has_mc:
             raise RuntimeError("BDDB200_EXCHANGE_SHOTS=mc: this box offers no multicast mapping of symmetric memory")
-        if mode == "push" and not has_mc:
-            raise RuntimeError("BDDB200_EXCHANGE_SHOTS=push: this box offers no multicast mapping of symmetric memory")
         if mode == "auto":
             # measured on 2 and 4 x B200 (profiles/r02_multi_gpu.md): one flag barrier + direct reads beat the two barriers of the
             # in-switch and two-shot forms while (world - 1) x prefix stays small; from 6 ranks on the slice-wise forms read less
             many = world >= 6 and n_exchange >= (1 << 17)
             mode = ("mc" if has_mc else "2") if many else "1"
-            if has_mc and shared_entries >= 0:
+            if shared_entries >= 0:
                 worst = torch.tensor([shared_entries], dtype=torch.int64, device=dev)
                 dist.all_reduce(worst, op=dist.ReduceOp.MAX, group=group)
                 if int(worst.item()) <= self.PUSH_MAX_ENTRIES:
@@ -197,7 +210,7 @@ class SymmExchange:
         torch.cuda.synchronize(dev)
         dist.barrier(group=group)
 
-    name = property(lambda self: {1: "symm one-shot", 2: "symm two-shot", 3: "symm in-switch (multimem)", 4: "multimem.red push inside the pass"}[self.mode])
+    name = property(lambda self: {1: "symm one-shot", 2: "symm two-shot", 3: "symm in-switch (multimem)", 4: "peer-memory push inside the pass"}[self.mode])
 
     def __call__(self):
         """Nothing to do: forward_pass / backward_pass of the local solver end with the exchange."""
@@ -245,6 +258,8 @@ class sharded_mma:
         costs_new[self.new_of_old] = costs
         self._local_col = relabel_variables(col.select(self.ids), self.new_of_old)
         self.local = make_local(self._local_col, costs_new, self.nr_vars, self.counts)
+        if shard_ids is None and hasattr(self.local, "set_push_masks") and world <= 16:
+            self.local.set_push_masks(share_masks(col, parts, self.new_of_old, self.n_shared))
         lv, _ = _layer_heads(self._local_col)
         self._finish_setup(exchange, int((lv < self.n_shared).sum()))        # layer entries of this shard that push across NVLink
 

@@ -256,6 +256,11 @@ class bdd_cuda_parallel_mma:
         check(self.lib.bddb200_push_exchange_supported(self.h, C.byref(out)))
         return out.value != 0
 
+    def set_push_masks(self, masks: np.ndarray):
+        """Per shared variable the ranks whose shards contain it (bit r = rank r): where the push exchange sends its differences."""
+        m = np.ascontiguousarray(masks, dtype=np.uint16)
+        check(self.lib.bddb200_set_push_masks(self.h, m.ctypes.data, m.shape[0]))
+
     def set_delta_buffers(self, block: torch.Tensor):
         """Use ``block`` (3 x 2V zero-filled REALs, e.g. symmetric memory mapped by the peer GPUs) as the rotating sum buffers."""
         n = 2 * self.nr_variables()

@@ -114,7 +114,11 @@ typedef struct bddb200_shard_info {
 } bddb200_shard_info;
 int bddb200_plan_shard(const bddb200_instruction* instrs_host, size_t n_instr, const size_t* delimiters_host, size_t n_bdds,
                        size_t nr_variables_min, int world, int rank, bddb200_shard_info* info,
-                       int32_t* new_of_old_out, int32_t* counts_new_out);
+                       int32_t* new_of_old_out, int32_t* counts_new_out, uint16_t* share_mask_out);
+/* Which ranks' shards contain each shared variable (n = n_shared entries, NEW numbering, bit r = rank r; share_mask_out of
+ * bddb200_plan_shard): the push exchange sends a variable's differences only there.  bddb200_create_shard sets it itself; a caller
+ * that planned the shard elsewhere passes it before bddb200_set_exchange(mode 4) (default: every shared variable goes to all ranks). */
+int bddb200_set_push_masks(bddb200_solver* s, const uint16_t* masks_host, size_t n);
 int bddb200_create_shard(const bddb200_instruction* instrs_host, size_t n_instr, const size_t* delimiters_host, size_t n_bdds,
                          const double* costs_hi_host, size_t n_costs, int precision, const bddb200_options* opts,
                          int world, int rank, bddb200_shard_info* info, int32_t* new_of_old_out, bddb200_solver** out);
@@ -253,9 +257,10 @@ int bddb200_delta_sum_buffer(bddb200_solver* s, void** sum_dev);
  * graph then contains it): register the peer mappings once.  mode 1 = one-shot reads of every peer's sum buffer, 2 = two-shot
  * (slice-wise reduce, then copy), 3 = in-switch reduction through multicast mappings (multimem.ld_reduce / multimem.st; mc_in = multicast
  * address of the symmetric block holding the three sum buffers, mc_out = multicast address of the symmetric result buffer), 0 = off.
- * mode 4 = push: no exchange kernel -- the pass itself adds the min-marginal differences of the first n_exchange / 2 variables to EVERY
- * rank's sum buffer (multimem.red through mc_in), its last warp signals the peers and the next pass's prologue waits for theirs; the
- * passes then read all sums from the rank's own buffer (no bddb200_set_delta_input).  Needs bddb200_push_exchange_supported.
+ * mode 4 = push: no exchange kernel -- the pass itself adds the min-marginal differences of the first n_exchange / 2 variables to its own
+ * sum buffer and, with peer-memory reductions over NVLink through peer_bufs_dev, to the buffers of the other ranks that hold the variable
+ * (bddb200_set_push_masks); the bundles that contain such variables run first, signal the peers when done, and wait for the peers' flags
+ * in the next pass; all sums are then read from the rank's own buffer (no bddb200_set_delta_input).  Needs bddb200_push_exchange_supported.
  * The epoch of the flag barriers lives on the device, so all ranks must make the same sequence of passes.  Replaces the host-staged
  * exchange of the hybrid solver, bdd_multi_parallel_mma_base.cu:266-318. */
 int bddb200_set_exchange(bddb200_solver* s, int world, int rank, const void* const* peer_bufs_dev, uint32_t* const* flags_dev, void* out_dev,

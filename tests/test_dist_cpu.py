@@ -158,5 +158,7 @@ def test_native_shard_plan_equals_the_numpy_one(world):
             local = bdist.relabel_variables(col.select(parts[rank]), new_of_old) if len(parts[rank]) else None
             entries = int((_layer_heads(local)[0] < n_shared).sum()) if local is not None else 0
             assert info["shared_entries"] == entries
+            assert np.array_equal(info["share_mask"], bdist.share_masks(col, parts, new_of_old, n_shared))
+            assert all(bin(int(m)).count("1") >= 2 for m in info["share_mask"])
     with pytest.raises(Exception):
         bdist.plan_shard_native(cases[0][0], 2, 2)
