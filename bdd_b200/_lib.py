@@ -50,6 +50,7 @@ class Options(C.Structure):
         ("stage_bytes", C.c_int),
         ("n_stages", C.c_int),
         ("warps_per_cta", C.c_int),
+        ("n_shared_vars", C.c_size_t),
     ]
 
 

@@ -154,7 +154,7 @@ public:
         CUDA_CHECK(cudaDeviceGetAttribute(&n_sms_, cudaDevAttrMultiProcessorCount, device));
         size_t balance_sms = 0;      // BDDB200_BALANCE=1: bundle count a multiple of the SM count, BDDs dealt evenly (measured neutral on B200: the exchange is bound chip-wide, not per SM)
         if(const char* e = std::getenv("BDDB200_BALANCE")) if(std::atoi(e) != 0) balance_sms = (size_t)n_sms_;
-        HostLayout L = build_layout(instrs, n_instr, delims, n_bdds, lanes_per_bdd, opt.nr_variables, sizeof(REAL), stage_budget, lane_class, balance_sms);
+        HostLayout L = build_layout(instrs, n_instr, delims, n_bdds, lanes_per_bdd, opt.nr_variables, sizeof(REAL), stage_budget, lane_class, balance_sms, opt.n_shared_vars);
         n_lane_ = L.n_lane_bundles; lane_max_J_ = L.lane_max_J; lane_max_hops_ = L.lane_max_hops;
         {   // runs of lane-class bundles with equal (J, n_hops): arithmetic progressions in every array (layout.hpp emits them back to back)
             bool ok = std::getenv("BDDB200_NO_CLASS_DESC") == nullptr;
@@ -746,6 +746,7 @@ public:
         {   // push exchange: shared variables' differences go to every rank's buffer through the multicast mapping; the flag barrier
             // is the tail of this launch and the prologue of the next one
             a.push_peers = reinterpret_cast<REAL* const*>(const_cast<void* const*>(xc_.peers)); a.push_offset = (size_t)(delta_out - dbuf(0)); a.push_mask = d_push_mask_.p;
+            a.delta_out_mc = xc_.mc_in != nullptr ? const_cast<REAL*>(xc_.mc_in) + a.push_offset : nullptr;
             a.n_push_vars = (uint32_t)(xc_.n_exchange / 2);
             a.push_counters = d_xc_counters_.p; a.push_flags = xc_.flags; a.push_my_flags = xc_.my_flags;
             a.push_world = xc_.world; a.push_rank = xc_.rank;
@@ -1645,7 +1646,7 @@ int bddb200_create_shard(const bddb200_instruction* instrs, size_t n_instr, cons
         for(bddb200_instruction& ins : local) if(ins.index < BOT) ins.index = (size_t)p.new_of_old[ins.index];
         std::vector<double> costs_new(p.n_vars, 0.0);
         for(size_t v = 0; v < std::min(n_costs, p.n_vars); ++v) costs_new[(size_t)p.new_of_old[v]] = costs_hi[v];
-        o.nr_variables = p.n_vars; o.nr_bdds_per_var_host = p.counts_new.data();
+        o.nr_variables = p.n_vars; o.nr_bdds_per_var_host = p.counts_new.data(); o.n_shared_vars = p.n_shared;
         const bddb200_instruction* base = local.data() - i0;
         if(precision == BDDB200_DOUBLE) *out = new SolverImpl<double>(base, i1, delims + p.first_bdd, p.n_bdds, costs_new.data(), costs_new.size(), o);
         else if(precision == BDDB200_FLOAT) *out = new SolverImpl<float>(base, i1, delims + p.first_bdd, p.n_bdds, costs_new.data(), costs_new.size(), o);

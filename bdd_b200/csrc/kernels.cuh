@@ -169,14 +169,15 @@ struct SweepArgs {
     int normalize_in;          // divide delta_in by nr_bdds(var) while reading
     int accumulate;            // add |mm_diff| to delta_out with atomics
     // multi-GPU push exchange (lane-class kernel, PUSH build): the |mm_diff| of the variables [0, n_push_vars) -- those that occur in
-    // more than one shard -- is added to this rank's sum buffer AND, with a peer-memory reduction over NVLink, to the buffer of every
-    // other rank whose shard contains the variable (push_mask): each rank's own buffer holds the global sums of its variables, there is
-    // no exchange kernel and no second buffer.  (A multimem.red through the multicast mapping does the same in one instruction, but it
-    // delivers every reduction to ALL ranks: on 8 GPUs each rank received 8x what it needed and the pass waited for it.)
+    // more than one shard -- is added to EVERY rank's sum buffer by one multimem.red through the multicast mapping of the symmetric
+    // buffers (the NVSwitch replicates the reduction) or, where there is no multicast mapping, to this rank's buffer and with
+    // peer-memory reductions to the buffers of the other ranks whose shards contain the variable (push_mask): each rank's own buffer
+    // holds the global sums of its variables, there is no exchange kernel and no second buffer.
     // Only the bundles that contain such a variable (marked in their descriptor) take part in the flag barrier: they wait for the
     // peers' flags before they read sums, and when the last of them (and of the bundles that clear the shared prefix of the next
     // buffer) has finished, the peers are told -- all other bundles of pass p + 1 overlap the tail of pass p as on one GPU.  Flags
     // carry the barrier's ordinal mod 3 (a rank is never more than one barrier ahead of a peer), known to the host.
+    REAL* delta_out_mc;            // multicast address of delta_out, or null: then the peers are addressed one by one
     REAL* const* push_peers;       // device array: entry r = rank r's block of the three sum buffers as mapped here
     size_t push_offset;            // delta_out relative to the start of the block, in REALs
     const uint16_t* push_mask;     // per shared variable: the OTHER ranks whose shards contain it
@@ -889,6 +890,16 @@ __device__ __forceinline__ void push_wait_flag(const uint32_t* flag, uint32_t st
     }
 }
 
+// the same reduction performed on every rank's copy of a symmetric buffer (addr = multicast address), in the switch.
+// Never predicate it: ptxas 12.9 drops the guard of a predicated multimem.red (the SASS REDG is unconditional); branch around it.
+__device__ __forceinline__ void mc_red_add(float* addr, float v)
+{
+    asm volatile("multimem.red.relaxed.sys.global.add.f32 [%0], %1;" :: "l"(__cvta_generic_to_global(addr)), "f"(v) : "memory");
+}
+__device__ __forceinline__ void mc_red_add(double* addr, double v)
+{
+    asm volatile("multimem.red.relaxed.sys.global.add.f64 [%0], %1;" :: "l"(__cvta_generic_to_global(addr)), "d"(v) : "memory");
+}
 // reduction on a peer GPU's memory (its mapping here), over NVLink
 __device__ __forceinline__ void peer_red_add(float* addr, float v)
 {
@@ -1238,11 +1249,14 @@ __device__ __forceinline__ void sweep_lane_bundle(const SweepArgs<REAL>& a, cons
                     const size_t slot = 2 * (size_t)max(x.var, 0) + (diff > 0 ? 1 : 0);
                     if(PUSH)
                     {   // shared between shards: one reduction on every rank's buffer; everything else stays on this GPU
-                        red_add_if(diff != 0, a.delta_out + slot, fabs(diff));
-                        if(diff != 0 && (uint32_t)x.var < a.n_push_vars)
-                        {   // shared between shards (rare): the same reduction on the buffers of the other ranks that hold the variable
-                            for(uint32_t m = a.push_mask[x.var]; m != 0; m &= m - 1)
-                                peer_red_add(a.push_peers[__ffs(m) - 1] + a.push_offset + slot, fabs(diff));
+                        const bool shared = (uint32_t)x.var < a.n_push_vars, mc = a.delta_out_mc != nullptr;
+                        red_add_if(diff != 0 && !(shared && mc), a.delta_out + slot, fabs(diff));
+                        if(diff != 0 && shared)
+                        {   // shared between shards (rare): the same reduction on every rank's buffer, in the switch ...
+                            if(mc) mc_red_add(a.delta_out_mc + slot, fabs(diff));
+                            else   // ... or on the buffers of the other ranks that hold the variable, one by one
+                                for(uint32_t m = a.push_mask[x.var]; m != 0; m &= m - 1)
+                                    peer_red_add(a.push_peers[__ffs(m) - 1] + a.push_offset + slot, fabs(diff));
                         }
                     }
                     else red_add_if(diff != 0, a.delta_out + slot, fabs(diff));

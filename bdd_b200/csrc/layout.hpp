@@ -191,7 +191,7 @@ constexpr size_t DEFAULT_STAGE_BUDGET = 12 * 1024;   // bytes of one pipeline st
 inline HostLayout build_layout(const bddb200_instruction* instrs, size_t n_instr,
                                const size_t* delims, size_t n_bdds, int lanes_per_bdd,
                                size_t nr_variables_override = 0, size_t real_bytes = 4,
-                               size_t stage_budget = DEFAULT_STAGE_BUDGET, bool lane_class = true, size_t n_sms = 0)
+                               size_t stage_budget = DEFAULT_STAGE_BUDGET, bool lane_class = true, size_t n_sms = 0, size_t n_shared_vars = 0)
 {
     constexpr size_t TOPSINK = (size_t)-1, BOTSINK = (size_t)-1 - 1;
     if(n_bdds == 0) throw layout_error(BDDB200_ERR_INVALID_ARGUMENT, "empty BDD collection");
@@ -216,6 +216,9 @@ inline HostLayout build_layout(const bddb200_instruction* instrs, size_t n_instr
     };
     // (a) layers per BDD
     std::vector<uint32_t> n_ext_of(n_bdds, 0);
+    // shard mode: does the BDD contain a variable that other shards contain too (variables [0, n_shared_vars))?  Those BDDs are kept
+    // together when bundles are formed, so that few bundles take part in the multi-GPU flag barrier of a pass
+    std::vector<uint8_t> bdd_shared(n_shared_vars > 0 ? n_bdds : 0, 0);
     size_t n_real = 0;
 #pragma omp parallel for schedule(static) reduction(max : max_var) reduction(+ : n_real)
     for(long long bb = 0; bb < (long long)n_bdds; ++bb)
@@ -232,7 +235,7 @@ inline HostLayout build_layout(const bddb200_instruction* instrs, size_t n_instr
         {
             const size_t var = instrs[i].index;
             if(var >= BOTSINK) { report(b, BDDB200_ERR_INVALID_ARGUMENT, "terminal instruction inside BDD " + std::to_string(b)); break; }
-            if(var != prev) { ++cnt; prev = var; if(var > max_var) max_var = var; }
+            if(var != prev) { ++cnt; prev = var; if(var > max_var) max_var = var; if(var < n_shared_vars) bdd_shared[b] = 1; }
         }
         n_ext_of[b] = cnt + 1;                               // + the terminal layer entry
         n_real += last - first - 2;
@@ -321,10 +324,10 @@ inline HostLayout build_layout(const bddb200_instruction* instrs, size_t n_instr
         // lane-class BDDs: width <= LANE_MAX_J), else a comparison sort
         uint32_t max_lay = 0;
         for(const uint32_t b : lane_order) max_lay = std::max(max_lay, nlay(b));
-        const size_t n_keys = (size_t)(LANE_MAX_J + 1) * (max_lay + 1);
+        const size_t n_keys = (size_t)(LANE_MAX_J + 1) * (max_lay + 1) * 2;
         if(n_keys <= ((size_t)1 << 24))
-        {
-            auto key = [&](uint32_t b) { return (size_t)bdd_maxw[b] * (max_lay + 1) + (max_lay - nlay(b)); };
+        {   // within (width, length): BDDs with a variable shared between shards first
+            auto key = [&](uint32_t b) { return ((size_t)bdd_maxw[b] * (max_lay + 1) + (max_lay - nlay(b))) * 2 + (!bdd_shared.empty() && bdd_shared[b] ? 0 : 1); };
             std::vector<uint32_t> count(n_keys + 1, 0);
             for(const uint32_t b : lane_order) count[key(b) + 1]++;
             for(size_t k = 0; k < n_keys; ++k) count[k + 1] += count[k];
@@ -335,7 +338,8 @@ inline HostLayout build_layout(const bddb200_instruction* instrs, size_t n_instr
         else
             std::stable_sort(lane_order.begin(), lane_order.end(), [&](uint32_t x, uint32_t y) {
                 if(bdd_maxw[x] != bdd_maxw[y]) return bdd_maxw[x] < bdd_maxw[y];
-                return nlay(x) > nlay(y);
+                if(nlay(x) != nlay(y)) return nlay(x) > nlay(y);
+                return !bdd_shared.empty() && bdd_shared[x] > bdd_shared[y];
             });
     }
     const size_t n_generic_bdds = order.size();

@@ -257,7 +257,10 @@ class sharded_mma:
         costs_new = np.empty_like(costs)
         costs_new[self.new_of_old] = costs
         self._local_col = relabel_variables(col.select(self.ids), self.new_of_old)
-        self.local = make_local(self._local_col, costs_new, self.nr_vars, self.counts)
+        try:
+            self.local = make_local(self._local_col, costs_new, self.nr_vars, self.counts, self.n_shared if shard_ids is None else 0)
+        except TypeError:          # a stand-in local solver (tests) that does not take the hint
+            self.local = make_local(self._local_col, costs_new, self.nr_vars, self.counts)
         if shard_ids is None and hasattr(self.local, "set_push_masks") and world <= 16:
             self.local.set_push_masks(share_masks(col, parts, self.new_of_old, self.n_shared))
         lv, _ = _layer_heads(self._local_col)
@@ -363,8 +366,8 @@ def make_cuda_local(precision: str, device: int, deterministic: bool = False):
     host synchronisation."""
     from .solver import bdd_cuda_parallel_mma
 
-    def make(col: BddCollection, costs: np.ndarray, nr_vars: int, counts: np.ndarray):
+    def make(col: BddCollection, costs: np.ndarray, nr_vars: int, counts: np.ndarray, n_shared: int = 0):
         return bdd_cuda_parallel_mma(col, costs, precision=precision, device=device, deterministic=deterministic,
-                                     nr_variables=nr_vars, nr_bdds_per_var=counts)
+                                     nr_variables=nr_vars, nr_bdds_per_var=counts, n_shared_vars=n_shared)
 
     return make

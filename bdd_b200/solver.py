@@ -34,7 +34,7 @@ class bdd_cuda_parallel_mma:
 
     def __init__(self, bdd_col: BddCollection, costs: Optional[Sequence[float]] = None, precision: str = "float",
                  device: int = 0, deterministic: bool = False, lanes_per_bdd: int = 0, nr_variables: int = 0,
-                 nr_bdds_per_var: Optional[np.ndarray] = None, stream: Optional[torch.cuda.Stream] = None):
+                 nr_bdds_per_var: Optional[np.ndarray] = None, stream: Optional[torch.cuda.Stream] = None, n_shared_vars: int = 0):
         self.lib = _lib.load()
         if precision not in ("float", "double"):
             raise ValueError("precision must be 'float' or 'double'")
@@ -54,6 +54,7 @@ class bdd_cuda_parallel_mma:
         opts.deterministic = int(deterministic)
         opts.lanes_per_bdd = int(lanes_per_bdd)
         opts.nr_variables = int(nr_variables)
+        opts.n_shared_vars = int(n_shared_vars)
         self._nbpv = None
         if nr_bdds_per_var is not None:
             self._nbpv = np.ascontiguousarray(nr_bdds_per_var, dtype=np.int32)

@@ -80,6 +80,8 @@ typedef struct bddb200_options {
     int stage_bytes;                /* shared-memory budget of one pipeline stage (chunk of hops)      */
     int n_stages;                   /* pipeline depth per warp, 2..8 (default 3)                       */
     int warps_per_cta;              /* bundles (warps) per CTA for bundles that fit the stage budget   */
+    size_t n_shared_vars;           /* shard mode: variables [0, n_shared_vars) occur in other shards too: the BDDs that contain one *
+                                     * are bundled together (few bundles then take part in the multi-GPU flag barrier); 0 = none   */
 } bddb200_options;
 
 void bddb200_default_options(bddb200_options* opts);
