@@ -156,6 +156,7 @@ public:
         if(const char* e = std::getenv("BDDB200_BALANCE")) if(std::atoi(e) != 0) balance_sms = (size_t)n_sms_;
         HostLayout L = build_layout(instrs, n_instr, delims, n_bdds, lanes_per_bdd, opt.nr_variables, sizeof(REAL), stage_budget, lane_class, balance_sms, opt.n_shared_vars);
         n_lane_ = L.n_lane_bundles; lane_max_J_ = L.lane_max_J; lane_max_hops_ = L.lane_max_hops;
+        n_lane_shared_ = L.n_lane_shared_bundles; layout_shared_vars_ = opt.n_shared_vars;
         {   // runs of lane-class bundles with equal (J, n_hops): arithmetic progressions in every array (layout.hpp emits them back to back)
             bool ok = std::getenv("BDDB200_NO_CLASS_DESC") == nullptr;
             for(size_t g = 0; g < L.desc_lane.size() && ok; ++g)
@@ -277,6 +278,7 @@ public:
         CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking)); own_stream_ = true;
         n_sms_ = o.n_sms_; max_optin_ = o.max_optin_; warps_per_cta_ = o.warps_per_cta_; grid_small_ = o.grid_small_; forced_wpc_ = o.forced_wpc_;
         n_stages_ = o.n_stages_; n_stages_large_ = o.n_stages_large_;
+        n_lane_shared_ = o.n_lane_shared_; layout_shared_vars_ = o.layout_shared_vars_;
         n_lane_ = o.n_lane_; lane_max_J_ = o.lane_max_J_; lane_max_hops_ = o.lane_max_hops_; lane_wpc_ = o.lane_wpc_; lane_grid_ = o.lane_grid_;
         lane_cls_first_ = o.lane_cls_first_; lane_cls_begin_ = o.lane_cls_begin_; lane_dense_ = o.lane_dense_;
         lane_chunk_hops_ = o.lane_chunk_hops_; lane_stages_ = o.lane_stages_; lane_stage_bytes_ = o.lane_stage_bytes_; lane_warp_smem_ = o.lane_warp_smem_;
@@ -354,6 +356,7 @@ public:
     {
         ar.pod(deterministic_);
         ar.pod(n_sms_); ar.pod(max_optin_); ar.pod(warps_per_cta_); ar.pod(grid_small_); ar.pod(forced_wpc_); ar.pod(n_stages_); ar.pod(n_stages_large_);
+        ar.pod(n_lane_shared_); ar.pod(layout_shared_vars_);
         ar.pod(n_lane_); ar.pod(lane_max_J_); ar.pod(lane_max_hops_); ar.pod(lane_wpc_); ar.pod(lane_grid_); ar.vec(lane_cls_first_); ar.vec(lane_cls_begin_); ar.pod(lane_dense_);
         ar.pod(lane_chunk_hops_); ar.pod(lane_stages_); ar.pod(lane_stage_bytes_); ar.pod(lane_warp_smem_);
         ar.pod(stage_small_); ar.pod(stage_large_); ar.pod(warp_smem_small_); ar.pod(warp_smem_large_);
@@ -453,7 +456,6 @@ public:
             a.zero_pairs_per_bundle = (uint32_t)((n_vars_ + n_lane_ - 1) / n_lane_);
             a.n_classes = (uint32_t)lane_cls_begin_.size();
             for(size_t c = 0; c < lane_cls_begin_.size(); ++c) { a.cls_first[c] = lane_cls_first_[c]; a.cls_begin[c] = lane_cls_begin_[c]; }
-            if(MODE == MODE_MMA && a.push_counters != nullptr) { a.desc = reinterpret_cast<const uint32_t*>(d_desc_push_.p); a.n_classes = 0; }     // permuted launch order
             // programmatic dependent launch: the kernel's start-up (descriptor, static topology, variable indices) overlaps the
             // tail of the previous kernel in the stream; it waits (griddepcontrol.wait) before touching anything a pass writes
             cudaLaunchConfig_t cfg{};
@@ -747,7 +749,8 @@ public:
             // is the tail of this launch and the prologue of the next one
             a.push_peers = reinterpret_cast<REAL* const*>(const_cast<void* const*>(xc_.peers)); a.push_offset = (size_t)(delta_out - dbuf(0)); a.push_mask = d_push_mask_.p;
             a.delta_out_mc = xc_.mc_in != nullptr ? const_cast<REAL*>(xc_.mc_in) + a.push_offset : nullptr;
-            a.n_push_vars = (uint32_t)(xc_.n_exchange / 2);
+            a.push_debug = push_debug_;
+            a.n_push_vars = (uint32_t)(xc_.n_exchange / 2); a.push_n_shared_bundles = (uint32_t)push_n_shared_bundles_;
             a.push_counters = d_xc_counters_.p; a.push_flags = xc_.flags; a.push_my_flags = xc_.my_flags;
             a.push_world = xc_.world; a.push_rank = xc_.rank;
             // this pass ends push barrier number e (counted mod 3: a rank is never more than one barrier ahead of a peer)
@@ -811,21 +814,12 @@ public:
                 if(h_push_mask_.size() >= n_sh) for(size_t v = 0; v < n_sh; ++v) m[v] = (uint16_t)(h_push_mask_[v] & ((1u << world) - 1u) & ~(1u << rank));
                 d_push_mask_.upload(m, stream_);
             }
-            DevBuf<unsigned char> d_shared; d_shared.alloc(n_lane_);
-            push_mark_bundles_kernel<<<blocks_for(n_lane_, 8), 256, 0, stream_>>>(d_desc_lane_.p, d_lay_vn_.p, (uint32_t)n_lane_, (uint32_t)(n_exchange / 2), d_shared.p);
-            CUDA_CHECK(cudaGetLastError());
-            std::vector<unsigned char> h_shared(n_lane_);
-            std::vector<LaneDesc> h_desc(n_lane_), h_push(n_lane_);
-            CUDA_CHECK(cudaMemcpyAsync(h_shared.data(), d_shared.p, n_lane_, cudaMemcpyDeviceToHost, stream_));
-            CUDA_CHECK(cudaMemcpyAsync(h_desc.data(), d_desc_lane_.p, n_lane_ * sizeof(LaneDesc), cudaMemcpyDeviceToHost, stream_));
-            CUDA_CHECK(cudaStreamSynchronize(stream_));
-            // launch order of the push builds: bundles with a shared variable first
-            size_t k = 0;
-            for(size_t g = 0; g < n_lane_; ++g) if(h_shared[g]) { h_push[k] = h_desc[g]; h_push[k].pad_[0] = 1; ++k; }
-            const size_t n_with_shared = k;
-            for(size_t g = 0; g < n_lane_; ++g) if(!h_shared[g]) { h_push[k] = h_desc[g]; h_push[k].pad_[0] = 0; ++k; }
-            d_desc_push_.upload(h_push, stream_);
-            // how many bundles count themselves per slot of the pass-end barrier (the predicate of sweep_lane_kernel)
+            // the bundles that take part in the pass-end barrier: those with shared variables -- the first n_lane_shared_ when the layout
+            // was built knowing the shared prefix (bddb200_options.n_shared_vars), else all of them -- and those that clear the prefix
+            push_n_shared_bundles_ = (layout_shared_vars_ == n_exchange / 2) ? n_lane_shared_ : n_lane_;
+            push_debug_ = 0;
+            if(const char* e = std::getenv("BDDB200_PUSH_DEBUG")) push_debug_ = (uint32_t)std::atoi(e);      // diagnostics only (kernels.cuh: SweepArgs::push_debug)
+            const size_t n_with_shared = push_n_shared_bundles_;
             const size_t zpb = (n_vars_ + n_lane_ - 1) / n_lane_;
             std::vector<uint32_t> h_cnt(8 + 2 * PUSH_SLOTS, 0u);
             for(size_t g = 0; g < n_lane_; ++g)
@@ -1467,7 +1461,8 @@ private:
     uint32_t xc_phase_ = 0;                  // push exchange: number of push barriers issued so far, mod 3
     std::vector<uint16_t> h_push_mask_;      // push exchange: per shared variable the ranks whose shards contain it (bit r = rank r), from the shard plan
     DevBuf<uint16_t> d_push_mask_;           // ... without this rank's own bit
-    DevBuf<LaneDesc> d_desc_push_;           // push exchange: the lane-class bundle descriptors in launch order (bundles with a variable shared between shards first, marked)
+    uint32_t push_debug_ = 0;
+    size_t n_lane_shared_ = 0, layout_shared_vars_ = 0, push_n_shared_bundles_ = 0;      // shard mode: lane-class bundles [0, n_lane_shared_) contain a variable < layout_shared_vars_
     REAL* delta_in_override_ = nullptr;      // exchanged sums of the variables [0, n_shared_vars_)
     size_t n_shared_vars_ = 0;
     DevBuf<REAL> d_delta_tmp2_;

@@ -188,6 +188,8 @@ struct SweepArgs {
     int push_world, push_rank;
     uint32_t push_stale_phase;     // a peer whose flag still shows this value has not finished the pass before this one
     uint32_t push_send_phase;      // what this pass stores into the peers' flag arrays when its counted bundles are done
+    uint32_t push_n_shared_bundles;    // bundles [0, n) contain a variable shared between shards
+    uint32_t push_debug;           // diagnostics (BDDB200_PUSH_DEBUG): bit 0 skip the per-bundle fence, bit 1 skip the system fence, bit 2 no reductions to peers
 };
 
 template<int P, typename REAL>
@@ -1251,7 +1253,7 @@ __device__ __forceinline__ void sweep_lane_bundle(const SweepArgs<REAL>& a, cons
                     {   // shared between shards: one reduction on every rank's buffer; everything else stays on this GPU
                         const bool shared = (uint32_t)x.var < a.n_push_vars, mc = a.delta_out_mc != nullptr;
                         red_add_if(diff != 0 && !(shared && mc), a.delta_out + slot, fabs(diff));
-                        if(diff != 0 && shared)
+                        if(diff != 0 && shared && !(a.push_debug & 4u))
                         {   // shared between shards (rare): the same reduction on every rank's buffer, in the switch ...
                             if(mc) mc_red_add(a.delta_out_mc + slot, fabs(diff));
                             else   // ... or on the buffers of the other ranks that hold the variable, one by one
@@ -1335,10 +1337,9 @@ __global__ void __launch_bounds__(MAXT, 1) sweep_lane_kernel(const SweepArgs<REA
     unsigned char* wsm = smem_raw + (size_t)warp * a.warp_smem_bytes;
     uint64_t* bars = bars_all + warp * a.n_stages;
     constexpr int M = (FORWARD && MODE == MODE_MM) ? MODE_PLAIN : MODE;
-    // push exchange: does this bundle take part in the flag barrier?  The host launches PUSH builds with a permuted descriptor array:
-    // the bundles that contain a shared variable come first (their flag goes out early in the pass and has long arrived when the
-    // peers' next pass starts), marked in the descriptor
-    const bool has_shared = PUSH && d.pad_[0] != 0;
+    // push exchange: does this bundle take part in the flag barrier?  In shard mode the layout puts the bundles that contain a shared
+    // variable first (their flag goes out early in the pass and has long arrived when the peers' next pass starts)
+    const bool has_shared = PUSH && g < a.push_n_shared_bundles;
     const bool counted = PUSH && (has_shared || g == 0 || g * a.zero_pairs_per_bundle < a.n_push_vars);
     switch(d.J)
     {
@@ -1356,7 +1357,7 @@ __global__ void __launch_bounds__(MAXT, 1) sweep_lane_kernel(const SweepArgs<REA
         __syncwarp();
         if(lane == 0)
         {
-            __threadfence();
+            if(!(a.push_debug & 1u)) __threadfence();
             const uint32_t slot = g % PUSH_SLOTS;
             if(atomicAdd(a.push_counters + 8 + slot, 1u) == a.push_counters[8 + PUSH_SLOTS + slot] - 1)
             {
@@ -1365,26 +1366,13 @@ __global__ void __launch_bounds__(MAXT, 1) sweep_lane_kernel(const SweepArgs<REA
                 if(atomicAdd(a.push_counters + 1, 1u) == a.push_counters[3] - 1)
                 {
                     a.push_counters[1] = 0;
-                    __threadfence_system();
+                    if(!(a.push_debug & 2u)) __threadfence_system();
                     for(int r = 0; r < a.push_world; ++r)
                         if(r != a.push_rank) asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(a.push_flags[r] + a.push_rank), "r"(a.push_send_phase) : "memory");
                 }
             }
         }
     }
-}
-
-// push exchange set-up: which lane-class bundles contain a variable of the shared prefix.  One warp per bundle.
-__global__ void push_mark_bundles_kernel(const LaneDesc* __restrict__ desc, const int2* __restrict__ lay_vn, uint32_t n_bundles, uint32_t n_push_vars,
-                                         unsigned char* __restrict__ shared_out)
-{
-    const uint32_t g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if(g >= n_bundles) return;
-    const LaneDesc d = desc[g];
-    bool any = false;
-    for(uint32_t i = lane; i < d.n_hops * 32u; i += 32) any |= (uint32_t)lay_vn[d.lay_off + i].x < n_push_vars;
-    any = __any_sync(0xffffffffu, any);
-    if(lane == 0) shared_out[g] = any ? 1 : 0;
 }
 
 // Push-exchange barrier outside a pass (before the host reads or clears the sum buffers): what & 1 waits until no peer's flag shows

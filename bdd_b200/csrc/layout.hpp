@@ -140,6 +140,7 @@ struct HostLayout {
     size_t n_real_nodes = 0;   // non-terminal nodes
     size_t n_slots = 0, n_lay = 0, max_hops = 0;
     size_t n_lane_bundles = 0;           // bundles [0, n_lane): lane-local class
+    size_t n_lane_shared_bundles = 0;    // shard mode: lane-class bundles [0, n_lane_shared) contain a BDD with a variable shared between shards
     uint32_t lane_max_J = 0, lane_max_hops = 0;
     size_t n_generic_slots = 0;          // generic bundles own slots [0, n_generic_slots): topo[slot] is their topology word
     size_t n_topo = 0;                   // n_generic_slots + 32 words per hop of every lane-class bundle
@@ -326,8 +327,8 @@ inline HostLayout build_layout(const bddb200_instruction* instrs, size_t n_instr
         for(const uint32_t b : lane_order) max_lay = std::max(max_lay, nlay(b));
         const size_t n_keys = (size_t)(LANE_MAX_J + 1) * (max_lay + 1) * 2;
         if(n_keys <= ((size_t)1 << 24))
-        {   // within (width, length): BDDs with a variable shared between shards first
-            auto key = [&](uint32_t b) { return ((size_t)bdd_maxw[b] * (max_lay + 1) + (max_lay - nlay(b))) * 2 + (!bdd_shared.empty() && bdd_shared[b] ? 0 : 1); };
+        {   // by (width, BDDs with a variable shared between shards first, length descending)
+            auto key = [&](uint32_t b) { return ((size_t)bdd_maxw[b] * 2 + (!bdd_shared.empty() && bdd_shared[b] ? 0 : 1)) * (max_lay + 1) + (max_lay - nlay(b)); };
             std::vector<uint32_t> count(n_keys + 1, 0);
             for(const uint32_t b : lane_order) count[key(b) + 1]++;
             for(size_t k = 0; k < n_keys; ++k) count[k + 1] += count[k];
@@ -338,8 +339,8 @@ inline HostLayout build_layout(const bddb200_instruction* instrs, size_t n_instr
         else
             std::stable_sort(lane_order.begin(), lane_order.end(), [&](uint32_t x, uint32_t y) {
                 if(bdd_maxw[x] != bdd_maxw[y]) return bdd_maxw[x] < bdd_maxw[y];
-                if(nlay(x) != nlay(y)) return nlay(x) > nlay(y);
-                return !bdd_shared.empty() && bdd_shared[x] > bdd_shared[y];
+                if(!bdd_shared.empty() && bdd_shared[x] != bdd_shared[y]) return bdd_shared[x] > bdd_shared[y];
+                return nlay(x) > nlay(y);
             });
     }
     const size_t n_generic_bdds = order.size();
@@ -428,7 +429,7 @@ inline HostLayout build_layout(const bddb200_instruction* instrs, size_t n_instr
     // lane and per SM (tools/microbench/scatter_cost2.cu): the slowest SM is the one with the most BDDs.  With the SM count known
     // (n_sms > 0) and at most 16 bundles per SM the bundles are made a multiple of the SM count and the BDDs dealt evenly over
     // them (bundles of fewer than 32 lanes), so that every SM gets the same number of warps AND of BDDs.
-    struct LaneProto { uint32_t first, count, J, n_hops; };
+    struct LaneProto { uint32_t first, count, J, n_hops; bool shared; };
     std::vector<LaneProto> lane_protos;
     {
         struct WidthClass { size_t first, count, bundles; };
@@ -458,13 +459,20 @@ inline HostLayout build_layout(const bddb200_instruction* instrs, size_t n_instr
             {
                 const size_t cnt = c.count / c.bundles + (i < c.count % c.bundles ? 1 : 0);
                 uint32_t nh = 0;
-                for(size_t q = pos; q < pos + cnt; ++q) nh = std::max(nh, nlay(lane_order[q]));
-                lane_protos.push_back(LaneProto{(uint32_t)pos, (uint32_t)cnt, bdd_maxw[lane_order[pos]], nh});
+                bool sh = false;
+                for(size_t q = pos; q < pos + cnt; ++q) { nh = std::max(nh, nlay(lane_order[q])); sh = sh || (!bdd_shared.empty() && bdd_shared[lane_order[q]]); }
+                lane_protos.push_back(LaneProto{(uint32_t)pos, (uint32_t)cnt, bdd_maxw[lane_order[pos]], nh, sh});
                 pos += cnt;
             }
         }
     }
-    std::stable_sort(lane_protos.begin(), lane_protos.end(), [](const LaneProto& x, const LaneProto& y) { return x.n_hops * x.J > y.n_hops * y.J; });
+    // heavy bundles first; in shard mode the bundles with shared variables before all others: they carry the multi-GPU flag barrier of a
+    // pass (kernels.cuh, PUSH builds), whose flag should go out early in the pass
+    std::stable_sort(lane_protos.begin(), lane_protos.end(), [](const LaneProto& x, const LaneProto& y) {
+        if(x.shared != y.shared) return x.shared;
+        return x.n_hops * x.J > y.n_hops * y.J;
+    });
+    for(const LaneProto& lp : lane_protos) L.n_lane_shared_bundles += lp.shared ? 1 : 0;
 
     timer.lap("sort, bundles");
     // ---- emit: generic bundles own the first slots (topo is indexed by slot there), lane-class

@@ -26,12 +26,19 @@ def main():
     else:
         col, costs = instances.set_cover(m=25000 * world, n=50000 * world, k=20, seed=1); prec = "float"
     out = {}
-    for mode in ("push", "1", "none"):
+    modes = sys.argv[2].split(",") if len(sys.argv) > 2 else ["push", "1", "none"]
+    for mode in modes:
+        if mode.startswith("push") and len(mode) > 4:      # push<bits>: BDDB200_PUSH_DEBUG
+            os.environ["BDDB200_PUSH_DEBUG"] = mode[4:]
+            mode_name, mode = mode, "push"
+        else:
+            os.environ.pop("BDDB200_PUSH_DEBUG", None)
+            mode_name = mode
         os.environ["BDDB200_EXCHANGE_SHOTS"] = "1" if mode == "none" else mode
         s = bdist.sharded_mma(col, costs, rank, world, bdist.make_cuda_local(prec, local))
         if mode == "none":
             check(s.local.lib.bddb200_set_exchange(s.local.h, 0, 0, None, None, None, None, None, None, 0, 0))
-        out[mode] = timed(s.local, 300)
+        out[mode_name] = timed(s.local, 300)
         nodes = s.local_col.nr_nodes; bdds = s.local_col.nr_bdds
         del s
         torch.cuda.empty_cache()
