@@ -205,6 +205,11 @@ public:
         CUDA_CHECK(cudaDeviceGetAttribute(&max_optin_, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
         CUDA_CHECK(cudaDeviceGetAttribute(&n_sms_, cudaDevAttrMultiProcessorCount, device));
         plan_launch();
+        // a collection of few, long BDDs leaves most of the GPU idle: a pass is then one dependency chain of max_hops steps per warp
+        // (assignment_5m, 2 x 1118 hops: 0.17 of the HBM roofline; after split_qbdd with chunk length 64: 0.68).  Tell the caller once.
+        if(n_bundles_ < (size_t)n_sms_ * 8 && max_hops_ >= 256 && std::getenv("BDDB200_QUIET") == nullptr)
+            std::fprintf(stderr, "[bdd_b200] %zu bundles of up to %zu hops occupy fewer than 8 warps on each of the %d SMs: every pass is a chain of %zu dependent steps; "
+                                 "splitting the long BDDs (bdd_collection::split_qbdd; driver key \"split bdds\") shortens it\n", n_bundles_, max_hops_, n_sms_, max_hops_);
         L_var_lay_begin_ = L.var_lay_begin;
         plan_resident();
         L_var_lay_begin_.clear(); L_var_lay_begin_.shrink_to_fit();
