@@ -34,6 +34,7 @@
 #include <nlohmann/json.hpp>
 
 #include "../../../include/bdd_b200.h"
+#include "split.hpp"
 
 namespace bddb200_host {
 
@@ -359,7 +360,7 @@ public:
     void solve() { solve(config_); }
     void solve(const json& config)
     {
-        for(const char* key : {"export lp", "export bdd lp", "export bdd graph", "split bdds"})
+        for(const char* key : {"export lp", "export bdd lp", "export bdd graph"})
             if(config.contains(key)) throw std::runtime_error(std::string("'") + key + "' is not provided by the C++ driver of this build");
         if(solver_ == nullptr)
         {
@@ -367,6 +368,21 @@ public:
             if(config.value("variable order", std::string("input")) != "input") throw std::runtime_error("variable reordering is outside this build's scope");
             log("[bdd solver] Compute BDDs");
             bdd_col_ = bdds_from_ilp(ilp_);
+            if(config.contains("split bdds"))
+            {   // bdd_solver.cpp:105-123 -> bdd_preprocessor.cpp:372-415: "split bdds": {"split length": n}, or a computed length
+                const json sb = config["split bdds"].is_object() ? config["split bdds"] : json::object();
+                if(sb.value("implication bdd", false)) throw std::runtime_error("the implication BDD of split_qbdd is not implemented");
+                const size_t length = sb.contains("split length") ? sb["split length"].get<size_t>() : compute_split_length(bdd_col_);
+                if(length != std::numeric_limits<size_t>::max())
+                {
+                    SplitCollection sc;
+                    size_t n_split = 0;
+                    const size_t before = bdd_col_.nr_bdds();
+                    split_long_bdds(bdd_col_, length, ilp_.nr_variables(), sc, &n_split);      // auxiliary variables carry no cost
+                    if(n_split > 0) { bdd_col_.instrs.swap(sc.instrs); bdd_col_.delims.swap(sc.delims); }
+                    log("[bdd preprocessor] split " + std::to_string(n_split) + " BDDs longer than " + std::to_string(length) + ": " + std::to_string(before) + " -> " + std::to_string(bdd_col_.nr_bdds()) + " BDDs");
+                }
+            }
             if(config.contains("print statistics"))
                 log("[print_statistics] #variables = " + std::to_string(ilp_.nr_variables()) + ", #constraints = " + std::to_string(ilp_.constraints.size()) + ", #BDDs = " + std::to_string(bdd_col_.nr_bdds()));
             construct_solver(config);

@@ -53,6 +53,59 @@ def test_cpp_reader_handles_the_lp_subset(tmp_path):
     assert np.array_equal(np.asarray(out["instrs"], dtype=np.uint64).reshape(-1, 3), col.instrs)
 
 
+def _write_assignment_lp(path, n, seed=3):
+    """n x n assignment problem as an .lp file: 2n simplex constraints over n variables each (long, thin BDDs)"""
+    rng = np.random.default_rng(seed)
+    c = rng.integers(0, 100, size=(n, n))
+    lines = ["Minimize", " " + " + ".join(f"{int(c[i, j])} x_{i}_{j}" for i in range(n) for j in range(n)), "Subject To"]
+    for i in range(n):
+        lines.append(" " + " + ".join(f"x_{i}_{j}" for j in range(n)) + " = 1")
+    for j in range(n):
+        lines.append(" " + " + ".join(f"x_{i}_{j}" for i in range(n)) + " = 1")
+    lines.append("End")
+    path.write_text("\n".join(lines) + "\n")
+
+
+@pytest.mark.parametrize("length", [3, 4, 7, 16])
+def test_cpp_splitter_equals_the_python_one(tmp_path, length):
+    """bdd_b200/csrc/host/split.hpp (the C++ driver's "split bdds") against bdd_b200/split.py, whose instruction arrays are pinned
+    bit for bit to the reference's bdd_collection::split_qbdd (tests/test_split.py): same chunks, same auxiliary variables, same order."""
+    _need_cli()
+    from bdd_b200 import instances, lp
+    from bdd_b200.split import split_long_bdds
+    paths = sorted(glob.glob(os.path.join(GOLDEN, "*.lp")))
+    big = tmp_path / "assignment_24.lp"
+    _write_assignment_lp(big, 24)
+    for path in paths + [str(big)]:
+        r = subprocess.run([CLI, "--split", str(length), path], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=60)
+        assert r.returncode == 0, r.stderr
+        out = json.loads(r.stdout)
+        ilp = lp.parse_lp(open(path).read())
+        col, costs = instances.from_ilp(ilp)
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want, n_vars = split_long_bdds(col, length, nr_variables=len(costs))
+        assert out["nr_variables"] == n_vars, path
+        assert np.array_equal(np.asarray(out["delims"], dtype=np.uint64), want.delims), path
+        assert np.array_equal(np.asarray(out["instrs"], dtype=np.uint64).reshape(-1, 3), want.instrs), path
+
+
+def test_cpp_split_length_rule_equals_the_python_one(tmp_path):
+    _need_cli()
+    from bdd_b200 import instances, lp
+    from bdd_b200.split import compute_split_length
+    big = tmp_path / "assignment_40.lp"
+    _write_assignment_lp(big, 40)
+    r = subprocess.run([CLI, "--split", "auto", str(big)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    out = json.loads(r.stdout)
+    col, _ = instances.from_ilp(lp.parse_lp(open(big).read()))
+    want = compute_split_length(col, n_sms=148)
+    assert out["split_length"] == (want if want < 2 ** 62 else -1)
+    assert out["n_split"] == 80      # 80 BDDs of 40 variables, fewer than one wave of bundles: all are cut at the minimum length
+
+
 EXPECTED = {"matching_3x3": -6.0, "short_chain_shuffled": 1.0, "long_chain": -9.0, "grid_graph_3x3": -8.0}
 
 
@@ -84,3 +137,39 @@ def test_cli_rejects_what_it_does_not_provide():
     for cfg in ({"input": path, "relaxation solver": "parallel mma"}, {"input": path, "precision": "half"}, {"relaxation solver": "cuda parallel mma"}):
         r = subprocess.run([CLI, json.dumps(cfg)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
         assert r.returncode == 1 and "bdd_solver_cl:" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cli_split_bdds_solves_the_assignment_problem(tmp_path):
+    """"split bdds" in the C++ driver (bdd_solver.cpp:105-123 -> bdd_preprocessor.cpp:372-415): the split relaxation of an n x n assignment
+    problem reaches the same optimum (the LP is integral), the rounded solution is feasible and optimal, and the Python driver agrees."""
+    _need_cli()
+    from scipy.optimize import linear_sum_assignment
+    n = 24
+    big = tmp_path / "assignment_24.lp"
+    _write_assignment_lp(big, n)
+    c = np.random.default_rng(3).integers(0, 100, size=(n, n))
+    rows, cols = linear_sum_assignment(c)
+    opt = float(c[rows, cols].sum())
+    base = {"input": str(big), "precision": "double", "relaxation solver": "cuda parallel mma",
+            "termination criteria": {"maximum iterations": 3000, "minimum improvement": 1e-12, "improvement slope": 0.0},
+            "perturbation rounding": {"initial perturbation": 0.1, "perturbation growth rate": 1.1, "inner iterations": 100, "outer iterations": 100}}
+    for split in (None, {"split length": 8}, {}):
+        cfg = dict(base)
+        if split is not None:
+            cfg["split bdds"] = split
+        r = subprocess.run([CLI, json.dumps(cfg)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out = json.loads(r.stdout.strip().splitlines()[-1])
+        assert out["lower_bound"] <= opt + 1e-6 and out["lower_bound"] >= opt - 0.05 * abs(opt), (split, out["lower_bound"], opt)
+        assert "solution" in out and abs(out["objective"] - opt) <= 1e-6, (split, out.get("objective"), opt)
+        if split is not None:
+            assert "[bdd preprocessor] split 48 BDDs" in r.stderr
+    # the Python driver on the same configuration (dual only: rounding perturbs the costs the bound is read from)
+    from bdd_b200.bdd_solver import bdd_solver
+    cfg = {k: v for k, v in base.items() if k != "perturbation rounding"}
+    s = bdd_solver(log=lambda *a: None)
+    s.solve({**cfg, "split bdds": {"split length": 8}})
+    r = subprocess.run([CLI, json.dumps({**cfg, "split bdds": {"split length": 8}})], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert abs(s.lower_bound() - json.loads(r.stdout.strip().splitlines()[-1])["lower_bound"]) <= 1e-6 * max(1.0, abs(opt))
