@@ -48,7 +48,8 @@ struct DevBuf {
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { if(p) cudaFree(p); }
     void alloc(size_t count) { if(p) { cudaFree(p); p = nullptr; } n = count; CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T))); }
-    void upload(const std::vector<T>& h, cudaStream_t st) { alloc(h.size()); if(!h.empty()) CUDA_CHECK(cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st)); }
+    template<typename A>
+    void upload(const std::vector<T, A>& h, cudaStream_t st) { alloc(h.size()); if(!h.empty()) CUDA_CHECK(cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st)); }
     void zero(cudaStream_t st) { if(n) CUDA_CHECK(cudaMemsetAsync(p, 0, n * sizeof(T), st)); }
     void clone_from(const DevBuf& o, cudaStream_t st) { alloc(o.n); if(o.n) CUDA_CHECK(cudaMemcpyAsync(p, o.p, o.n * sizeof(T), cudaMemcpyDeviceToDevice, st)); }
 };
@@ -192,7 +193,7 @@ public:
                 h_nr_bdds_per_var_[v] = opt.nr_bdds_per_var_host[v];
             }
         }
-        h_ext_var_ = L.ext_var; h_ext_bdd_ = L.ext_bdd;
+        h_ext_var_.assign(L.ext_var.begin(), L.ext_var.end()); h_ext_bdd_.assign(L.ext_bdd.begin(), L.ext_bdd.end());
 
         // the lane-class kernels normalise through a reciprocal table; a variable shared by more BDDs than it holds
         // switches the solver to exact division + fixed-order sums (the deterministic kernels)
@@ -214,12 +215,6 @@ public:
         plan_resident();
         L_var_lay_begin_.clear(); L_var_lay_begin_.shrink_to_fit();
 
-        std::vector<int2> lay_vn(L.n_lay);
-        for(size_t i = 0; i < L.n_lay; ++i)
-        {
-            const int v = L.lay_var[i];
-            lay_vn[i] = make_int2(v, v >= 0 ? h_nr_bdds_per_var_[v] : 0);
-        }
         std::vector<uint32_t> bdd_bundle(2 * n_bdds);
         for(size_t g = 0; g < L.bundles.size(); ++g)
             for(uint32_t q = 0; q < (32u >> L.bundles[g].logP); ++q)
@@ -235,7 +230,6 @@ public:
         d_desc_lane_.upload(L.desc_lane, stream_);
         d_hops_.upload(L.hops, stream_);
         d_topo_.upload(L.topo, stream_);
-        d_lay_vn_.upload(lay_vn, stream_);
         d_bundle_bdd_.upload(L.bundle_bdd, stream_);
         d_bdd_bundle_.upload(bdd_bundle, stream_);
         d_ext2lay_.upload(L.ext2lay, stream_);
@@ -246,6 +240,14 @@ public:
         d_var_lay_.upload(L.var_lay, stream_);
         d_sorted_ext_.upload(L.sorted_ext, stream_);
         d_nr_bdds_.upload(h_nr_bdds_per_var_, stream_);
+        {   // per layer entry {variable, nr_bdds(variable)}: paired on the device (the host loop was a gather over tens of megabytes)
+            DevBuf<int32_t> d_lay_var;
+            d_lay_var.upload(L.lay_var, stream_);
+            d_lay_vn_.alloc(L.n_lay);
+            pair_lay_vn_kernel<<<blocks_for(L.n_lay), 256, 0, stream_>>>(d_lay_var.p, d_nr_bdds_.p, d_lay_vn_.p, (uint32_t)L.n_lay);
+            CUDA_CHECK(cudaGetLastError());
+            CUDA_CHECK(cudaStreamSynchronize(stream_));      // d_lay_var is freed here
+        }
         {   // reciprocals for the lane-class kernels' normalisation (same rounding as the device division)
             std::vector<REAL> inv(INV_TAB);
             for(int i = 0; i < INV_TAB; ++i) inv[i] = (REAL)1 / (REAL)(i > 0 ? i : 1);

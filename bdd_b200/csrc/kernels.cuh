@@ -1393,6 +1393,15 @@ __global__ void push_barrier_kernel(uint32_t* counters, uint32_t* const* flags, 
 
 // ------------------------------------------------------------------ small kernels ------
 
+// construction: per layer entry {variable or marker, nr_bdds(variable)}
+__global__ void pair_lay_vn_kernel(const int32_t* __restrict__ lay_var, const int32_t* __restrict__ nr_bdds, int2* __restrict__ out, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    const int32_t v = lay_var[i];
+    out[i] = make_int2(v, v >= 0 ? nr_bdds[v] : 0);
+}
+
 // deterministic replacement of compute_delta (bdd_cuda_parallel_mma.cu:379-393): per variable,
 // sum its layers' mm differences in BDD order (the order the single-threaded CPU solver uses).
 template<typename REAL>

@@ -39,8 +39,11 @@
 #include <cstddef>
 #include <cstdint>
 #include <numeric>
+#include <memory>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "../../include/bdd_b200.h"
@@ -134,6 +137,27 @@ struct layout_error : std::runtime_error {
     layout_error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
 };
 
+// Large host arrays: std::vector value-initialises its elements on one thread, and for arrays of tens of megabytes that first touch
+// (page faults) costs more than the work that fills them (20 M nodes: 130 ms of 350).  uvec<T> leaves new elements uninitialised
+// (trivial T only); par_fill touches and fills them from all threads.
+template<typename T>
+struct default_init_allocator : std::allocator<T> {
+    template<typename U> struct rebind { using other = default_init_allocator<U>; };
+    using std::allocator<T>::allocator;
+    template<typename U> void construct(U* p) noexcept(std::is_nothrow_default_constructible<U>::value) { ::new(static_cast<void*>(p)) U; }
+    template<typename U, typename... Args> void construct(U* p, Args&&... args) { ::new(static_cast<void*>(p)) U(std::forward<Args>(args)...); }
+};
+template<typename T> using uvec = std::vector<T, default_init_allocator<T>>;
+template<typename T>
+inline void par_fill(uvec<T>& v, size_t n, T value)
+{
+    v.clear();
+    v.resize(n);              // no touch
+    T* p = v.data();
+#pragma omp parallel for schedule(static)
+    for(long long i = 0; i < (long long)n; ++i) p[i] = value;
+}
+
 struct HostLayout {
     size_t n_vars = 0, n_bdds = 0, n_instr = 0;
     size_t n_layers_ext = 0;   // sum over BDDs of (nr variables + 1)
@@ -153,19 +177,19 @@ struct HostLayout {
     std::vector<uint32_t> desc_fwd, desc_bwd;   // DESC_WORDS per bundle
     std::vector<HopRec> hops;
     std::vector<int32_t> bundle_bdd;     // per bundle lane group: external BDD index or -1
-    std::vector<uint32_t> topo;          // per slot
-    std::vector<int32_t> lay_var;        // per layer entry: variable or -1
-    std::vector<uint32_t> ext2lay;       // external layer -> layer entry
-    std::vector<int32_t> ext_var;        // external layer -> variable (INT_MAX terminal)
-    std::vector<int32_t> ext_bdd;        // external layer -> BDD
+    uvec<uint32_t> topo;          // per slot
+    uvec<int32_t> lay_var;        // per layer entry: variable or -1
+    uvec<uint32_t> ext2lay;       // external layer -> layer entry
+    uvec<int32_t> ext_var;        // external layer -> variable (INT_MAX terminal)
+    uvec<int32_t> ext_bdd;        // external layer -> BDD
     std::vector<uint32_t> bdd_ext_begin; // per BDD: first external layer (n_bdds+1)
     std::vector<uint32_t> root_slot, top_slot;  // per BDD
     std::vector<int32_t> nr_bdds_per_var;       // counted from this collection
     // variable -> layer entries in (variable, BDD index) order (deterministic delta sums,
     // make_dual_feasible, sorted min-marginals)
     std::vector<uint32_t> var_lay_begin; // n_vars+1
-    std::vector<uint32_t> var_lay;       // layer entries
-    std::vector<uint32_t> sorted_ext;    // external layers sorted by (var, bdd), terminals last
+    uvec<uint32_t> var_lay;       // layer entries
+    uvec<uint32_t> sorted_ext;    // external layers sorted by (var, bdd), terminals last
 };
 
 // BDDB200_LAYOUT_TIMING=1: phase durations of build_layout on stderr
@@ -206,7 +230,7 @@ inline HostLayout build_layout(const bddb200_instruction* instrs, size_t n_instr
 
     // ---- pass 1: layers of every BDD, validation, widths ------------------------------
     L.bdd_ext_begin.assign(n_bdds + 1, 0);
-    std::vector<uint32_t> ext_first_instr;   // per external layer: first instruction; layer e spans [efi[e], efi[e+1])
+    uvec<uint32_t> ext_first_instr;   // per external layer: first instruction; layer e spans [efi[e], efi[e+1])
     std::vector<uint32_t> bdd_maxw(n_bdds, 1);
     size_t max_var = 0;
     // errors found inside the parallel loops: the BDD with the smallest index reports (what a sequential scan would have found)
@@ -575,11 +599,12 @@ inline HostLayout build_layout(const bddb200_instruction* instrs, size_t n_instr
     if(lay > 0xFFFFFFF0ull) throw layout_error(BDDB200_ERR_INVALID_ARGUMENT, "collection too large (layer index overflow)");
 
     timer.lap("emit bundles");
-    L.topo.assign(L.n_topo, TOPO_PAD);
-    for(size_t g = 0; g < L.n_lane_bundles; ++g)
+    par_fill(L.topo, L.n_topo, (uint32_t)TOPO_PAD);
+#pragma omp parallel for schedule(static)
+    for(long long g = 0; g < (long long)L.n_lane_bundles; ++g)
         std::fill(L.topo.begin() + L.bundles[g].topo_base, L.topo.begin() + L.bundles[g].topo_base + 32ull * L.bundles[g].n_hops, 0u);
-    L.lay_var.assign(L.n_lay, LAY_NONE);
-    L.ext2lay.assign(L.n_layers_ext, 0);
+    par_fill(L.lay_var, L.n_lay, (int32_t)LAY_NONE);
+    L.ext2lay.clear(); L.ext2lay.resize(L.n_layers_ext);         // every entry is written below
     L.root_slot.assign(n_bdds, 0);
     L.top_slot.assign(n_bdds, 0);
     L.nr_bdds_per_var.assign(L.n_vars, 0);
@@ -590,6 +615,55 @@ inline HostLayout build_layout(const bddb200_instruction* instrs, size_t n_instr
         const size_t g = (size_t)gg;
         const BundleDesc& bd = L.bundles[g];
         const bool lane_cls = bd.cls == CLS_LANE;
+        if(lane_cls)
+        {   // hop-major: the 32 words of a hop are written together (the tile rows of this class are 32 consecutive entries; walking
+            // BDD by BDD touches a different cache line of every array per layer), the 32 BDDs' instructions stay in L1 meanwhile
+            struct Lane { size_t b, bot, top; uint32_t eb, ee; };
+            Lane ln[32]; bool has[32];
+            for(uint32_t q = 0; q < 32; ++q)
+            {
+                const int32_t bi = L.bundle_bdd[bd.bdd_base + q];
+                has[q] = bi >= 0;
+                if(!has[q]) continue;
+                const size_t b = (size_t)bi, last = delims[b+1];
+                ln[q] = Lane{b, instrs[last-2].index == BOTSINK ? last - 2 : last - 1, instrs[last-2].index == BOTSINK ? last - 1 : last - 2,
+                             L.bdd_ext_begin[b], L.bdd_ext_begin[b+1] - 1};
+            }
+            for(uint32_t k = 0; k < bd.n_hops; ++k)
+            {
+                const HopRec& hr = L.hops[bd.hop_base + k];
+                for(uint32_t q = 0; q < 32; ++q)
+                {
+                    if(!has[q] || ln[q].eb + k > ln[q].ee) continue;
+                    const uint32_t e = ln[q].eb + k, layer_entry = bd.layer_base + k * 32u + q;
+                    L.ext2lay[e] = layer_entry;
+                    if(e == ln[q].ee)
+                    {
+                        L.lay_var[layer_entry] = LAY_TOP;
+                        L.top_slot[ln[q].b] = hr.node_off + q;
+                        continue;
+                    }
+                    const size_t lb = ext_first_instr[e], le = ext_first_instr[e+1];
+                    L.lay_var[layer_entry] = L.ext_var[e];
+                    if(k == 0) L.root_slot[ln[q].b] = hr.node_off + q;
+                    uint32_t word = 0;
+                    for(size_t i = lb; i < le; ++i)
+                    {
+                        const uint32_t j = (uint32_t)(i - lb);
+                        const size_t arcs[2] = {instrs[i].lo, instrs[i].hi};
+                        for(uint32_t arc = 0; arc < 2; ++arc)
+                        {
+                            const size_t c = arcs[arc];
+                            if(c == ln[q].bot) continue;
+                            const uint32_t r = (c == ln[q].top) ? 0u : (uint32_t)(c - le);
+                            word |= lane_arc_bit(bd.max_J, j, arc, r);
+                        }
+                    }
+                    L.topo[bd.topo_base + k * 32u + q] = word;
+                }
+            }
+            continue;
+        }
         const uint32_t logP = bd.logP, P = 1u << logP, bpw = 32u >> logP;
         for(uint32_t q = 0; q < bpw; ++q)
         {
@@ -650,33 +724,70 @@ inline HostLayout build_layout(const bddb200_instruction* instrs, size_t n_instr
 
     timer.lap("topology, layer entries");
     // ---- variable -> layers (sorted by variable, then BDD index) ------------------------
+    // External order is BDD-major, so a STABLE sort of the inner layer entries by variable is what is needed.  Two levels: the entries
+    // are first dealt into buckets of consecutive variables (every thread owns a range of entries; per-thread bucket counts make the
+    // deal stable and race-free, all reads and writes sequential), then every bucket is counting-sorted on its own (its variables'
+    // counters and its slice of the output fit the cache).
     L.var_lay_begin.assign(L.n_vars + 1, 0);
-    for(size_t e = 0; e < L.n_layers_ext; ++e)
-        if(L.ext_var[e] != INT_MAX) L.var_lay_begin[L.ext_var[e] + 1]++;
-    for(size_t v = 0; v < L.n_vars; ++v) L.nr_bdds_per_var[v] = (int32_t)L.var_lay_begin[v + 1];      // in how many BDDs the variable occurs
-    for(size_t v = 0; v < L.n_vars; ++v) L.var_lay_begin[v+1] += L.var_lay_begin[v];
-    L.var_lay.assign(L.var_lay_begin[L.n_vars], 0);
-    L.sorted_ext.assign(L.n_layers_ext, 0);
-    {   // external order is BDD-major => BDD index ascending per variable.  Every thread owns a range of variables and walks ALL external
-        // layers in order, keeping those of its range: reads are repeated per thread, writes are disjoint and in order (stable).
+    L.sorted_ext.clear(); L.sorted_ext.resize(L.n_layers_ext);    // every entry is written below
+    {
         int n_threads = 1;
 #ifdef _OPENMP
-        n_threads = std::max(1, std::min(omp_get_max_threads(), 16));
+        n_threads = std::max(1, std::min(omp_get_max_threads(), 64));
 #endif
-        const size_t n_inner = L.var_lay_begin[L.n_vars];
+        uint32_t shift = 0;
+        while(((L.n_vars + ((size_t)1 << shift) - 1) >> shift) > 2048) ++shift;
+        const size_t n_buckets = std::max<size_t>(1, (L.n_vars + ((size_t)1 << shift) - 1) >> shift);
+        const size_t n_e = L.n_layers_ext;
+        std::vector<size_t> cnt((size_t)n_threads * n_buckets, 0);
 #pragma omp parallel for schedule(static, 1) num_threads(n_threads)
         for(int t = 0; t < n_threads; ++t)
         {
-            const size_t v0 = L.n_vars * (size_t)t / n_threads, v1 = L.n_vars * (size_t)(t + 1) / n_threads;
-            if(v0 >= v1) continue;
-            std::vector<uint32_t> fill(L.var_lay_begin.begin() + v0, L.var_lay_begin.begin() + v1);
-            for(size_t e = 0; e < L.n_layers_ext; ++e)
+            size_t* c = cnt.data() + (size_t)t * n_buckets;
+            const size_t e0 = n_e * (size_t)t / n_threads, e1 = n_e * (size_t)(t + 1) / n_threads;
+            for(size_t e = e0; e < e1; ++e) if(L.ext_var[e] != INT_MAX) ++c[(size_t)L.ext_var[e] >> shift];
+        }
+        // start of (bucket, thread) in the dealt arrays: bucket-major, threads in entry order inside a bucket
+        std::vector<size_t> bucket_begin(n_buckets + 1, 0);
+        size_t run = 0;
+        for(size_t k = 0; k < n_buckets; ++k)
+        {
+            bucket_begin[k] = run;
+            for(int t = 0; t < n_threads; ++t) { const size_t c = cnt[(size_t)t * n_buckets + k]; cnt[(size_t)t * n_buckets + k] = run; run += c; }
+        }
+        bucket_begin[n_buckets] = run;
+        const size_t n_inner = run;
+        uvec<uint32_t> d_e(n_inner), d_v(n_inner), d_l(n_inner);
+#pragma omp parallel for schedule(static, 1) num_threads(n_threads)
+        for(int t = 0; t < n_threads; ++t)
+        {
+            size_t* c = cnt.data() + (size_t)t * n_buckets;
+            const size_t e0 = n_e * (size_t)t / n_threads, e1 = n_e * (size_t)(t + 1) / n_threads;
+            for(size_t e = e0; e < e1; ++e)
             {
                 const int32_t var = L.ext_var[e];
-                if(var == INT_MAX || (size_t)var < v0 || (size_t)var >= v1) continue;
-                const uint32_t p = fill[var - v0]++;
-                L.var_lay[p] = L.ext2lay[e];
-                L.sorted_ext[p] = (uint32_t)e;
+                if(var == INT_MAX) continue;
+                const size_t p = c[(size_t)var >> shift]++;
+                d_e[p] = (uint32_t)e; d_v[p] = (uint32_t)var; d_l[p] = L.ext2lay[e];
+            }
+        }
+        // in how many BDDs every variable occurs (each bucket owns its variables' counters), then the global offsets
+#pragma omp parallel for schedule(dynamic, 8)
+        for(long long kk = 0; kk < (long long)n_buckets; ++kk)
+            for(size_t p = bucket_begin[kk]; p < bucket_begin[kk + 1]; ++p) L.var_lay_begin[d_v[p] + 1]++;
+        for(size_t v = 0; v < L.n_vars; ++v) L.nr_bdds_per_var[v] = (int32_t)L.var_lay_begin[v + 1];
+        for(size_t v = 0; v < L.n_vars; ++v) L.var_lay_begin[v+1] += L.var_lay_begin[v];
+        L.var_lay.clear(); L.var_lay.resize(n_inner);               // every entry is written below
+#pragma omp parallel for schedule(dynamic, 8)
+        for(long long kk = 0; kk < (long long)n_buckets; ++kk)
+        {
+            const size_t v0 = (size_t)kk << shift, v1 = std::min(L.n_vars, ((size_t)kk + 1) << shift);
+            std::vector<uint32_t> fill(L.var_lay_begin.begin() + v0, L.var_lay_begin.begin() + v1);
+            for(size_t p = bucket_begin[kk]; p < bucket_begin[kk + 1]; ++p)
+            {
+                const uint32_t q = fill[d_v[p] - v0]++;
+                L.var_lay[q] = d_l[p];
+                L.sorted_ext[q] = d_e[p];
             }
         }
         // terminal layers last, in BDD order
