@@ -423,6 +423,10 @@ public:
     ~SolverImpl() override
     {
         cudaSetDevice(device);
+        if(xc_.mode == 4 && push_pending_)
+        {   // peers may still be adding to this rank's (caller-owned, symmetric) sum buffers: they must be done before the caller frees them
+            try { push_barrier(1); cudaStreamSynchronize(stream_); } catch(...) {}
+        }
         if(graph_exec_) cudaGraphExecDestroy(graph_exec_);
         for(StepGraph& c : step_graphs_) cudaGraphExecDestroy(c.exec);
         if(h_lb_) cudaFreeHost(h_lb_);
@@ -764,6 +768,7 @@ public:
             const uint32_t e = (xc_phase_ + 1u) % 3u;
             a.push_send_phase = e; a.push_stale_phase = (e + 1u) % 3u;       // stale = the barrier before the previous one
             xc_phase_ = e;
+            push_pending_ = true;
         }
         a.normalize_in = !normalize_in ? NORM_NONE : (deterministic_ ? NORM_DIVIDE : NORM_RECIPROCAL);
         a.accumulate = deterministic_ ? 0 : 1;
@@ -810,7 +815,7 @@ public:
         xc_.mc_in = static_cast<const REAL*>(mc_in); xc_.mc_out = static_cast<REAL*>(mc_out); xc_.n_exchange = n_exchange; xc_.mode = mode;
         if(d_xc_counters_.n < 8 + 2 * PUSH_SLOTS) d_xc_counters_.alloc(8 + 2 * PUSH_SLOTS);
         d_xc_counters_.zero(stream_);
-        xc_phase_ = 0;
+        xc_phase_ = 0; push_pending_ = false;
         if(mode == 4)
         {   // this rank's own flag array (the passes poll it; peers write it), and which bundles take part in the flag barrier
             CUDA_CHECK(cudaMemcpyAsync(&xc_.my_flags, flags + rank, sizeof(uint32_t*), cudaMemcpyDeviceToHost, stream_));
@@ -841,6 +846,7 @@ public:
     void push_barrier(int what)
     {
         if(xc_.mode != 4) return;
+        if(what == 1) { if(!push_pending_) return; push_pending_ = false; }       // nothing pushed since the last wait
         const uint32_t stale = (xc_phase_ + 2u) % 3u, send = (xc_phase_ + 1u) % 3u;
         push_barrier_kernel<<<1, 32, 0, stream_>>>(d_xc_counters_.p, xc_.flags, xc_.my_flags, xc_.world, xc_.rank, what, stale, send);
         if(what & 2) xc_phase_ = send;
@@ -1071,6 +1077,7 @@ public:
     double lower_bound() override
     {
         set_device();
+        if(xc_.mode == 4) push_barrier(1);           // a natural end point of a sharded solve: the peers are done adding to this rank's sums
         if(xc_.mode != 0 && !lb_valid_) check_exchange_status();
         backward_run();
         if(!lb_valid_)
@@ -1469,6 +1476,7 @@ private:
     std::vector<uint16_t> h_push_mask_;      // push exchange: per shared variable the ranks whose shards contain it (bit r = rank r), from the shard plan
     DevBuf<uint16_t> d_push_mask_;           // ... without this rank's own bit
     uint32_t push_debug_ = 0;
+    bool push_pending_ = false;              // a push pass ran since this rank last waited for the peers' flags
     size_t n_lane_shared_ = 0, layout_shared_vars_ = 0, push_n_shared_bundles_ = 0;      // shard mode: lane-class bundles [0, n_lane_shared_) contain a variable < layout_shared_vars_
     REAL* delta_in_override_ = nullptr;      // exchanged sums of the variables [0, n_shared_vars_)
     size_t n_shared_vars_ = 0;
