@@ -880,9 +880,9 @@ __device__ __forceinline__ void push_wait_flag(const uint32_t* flag, uint32_t st
     uint32_t seen;
     unsigned long long t0 = 0;
     for(uint32_t spins = 0;; ++spins)
-    {
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
-        if(seen != stale) return;
+    {   // relaxed polls, one acquire fence when the flag has moved (ld.acquire.sys invalidates L1 on every poll)
+        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+        if(seen != stale) { asm volatile("fence.acq_rel.sys;" ::: "memory"); return; }
         if((spins & 1023u) == 1023u)
         {
             const unsigned long long now = global_timer_ns();
@@ -1357,18 +1357,20 @@ __global__ void __launch_bounds__(MAXT, 1) sweep_lane_kernel(const SweepArgs<REA
         __syncwarp();
         if(lane == 0)
         {
-            if(!(a.push_debug & 1u)) __threadfence();
+            if(!(a.push_debug & 1u)) asm volatile("fence.acq_rel.gpu;" ::: "memory");      // (not __threadfence(): that is the sequentially consistent MEMBAR.SC)
             const uint32_t slot = g % PUSH_SLOTS;
             if(atomicAdd(a.push_counters + 8 + slot, 1u) == a.push_counters[8 + PUSH_SLOTS + slot] - 1)
             {
                 a.push_counters[8 + slot] = 0;
-                __threadfence();
+                asm volatile("fence.acq_rel.gpu;" ::: "memory");
                 if(atomicAdd(a.push_counters + 1, 1u) == a.push_counters[3] - 1)
                 {
                     a.push_counters[1] = 0;
-                    if(!(a.push_debug & 2u)) __threadfence_system();
+                    // ONE system-scope fence, then relaxed flag stores: a st.release.sys per peer is a system-scope MEMBAR per peer
+                    // (seven in a row on eight GPUs, on the critical path of every rank's next pass)
+                    if(!(a.push_debug & 2u)) asm volatile("fence.acq_rel.sys;" ::: "memory");
                     for(int r = 0; r < a.push_world; ++r)
-                        if(r != a.push_rank) asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(a.push_flags[r] + a.push_rank), "r"(a.push_send_phase) : "memory");
+                        if(r != a.push_rank) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" :: "l"(a.push_flags[r] + a.push_rank), "r"(a.push_send_phase) : "memory");
                 }
             }
         }
@@ -1385,9 +1387,9 @@ __global__ void push_barrier_kernel(uint32_t* counters, uint32_t* const* flags, 
     __syncwarp();
     if(what & 2)
     {
-        __threadfence_system();
+        asm volatile("fence.acq_rel.sys;" ::: "memory");
         if(lane < world && lane != rank)
-            asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(flags[lane] + rank), "r"(send_phase) : "memory");
+            asm volatile("st.relaxed.sys.global.u32 [%0], %1;" :: "l"(flags[lane] + rank), "r"(send_phase) : "memory");
     }
 }
 
