@@ -33,6 +33,16 @@ SYMBOLS = [
     "bddb200_lbfgs_create", "bddb200_lbfgs_destroy", "bddb200_lbfgs_iteration", "bddb200_lbfgs_flush", "bddb200_lbfgs_stats",
 ]
 
+# every symbol include/bdd_b200_collection.h declares (host-side BDD collection; no GPU needed)
+COLLECTION_SYMBOLS = [
+    "bddb200_collection_create", "bddb200_collection_destroy", "bddb200_collection_nr_bdds", "bddb200_collection_nr_instructions", "bddb200_collection_export",
+    "bddb200_collection_simplex_constraint", "bddb200_collection_not_all_false_constraint", "bddb200_collection_all_equal_constraint",
+    "bddb200_collection_cardinality_constraint", "bddb200_collection_rebase", "bddb200_collection_negate", "bddb200_collection_invert",
+    "bddb200_collection_variables", "bddb200_collection_is_qbdd", "bddb200_collection_is_reordered", "bddb200_collection_evaluate",
+    "bddb200_collection_reorder", "bddb200_collection_make_qbdd", "bddb200_collection_bdd_and", "bddb200_collection_remove",
+    "bddb200_collection_split_qbdd", "bddb200_collection_split_long_bdds",
+]
+
 
 class ShardInfo(C.Structure):
     """bddb200_shard_info"""
@@ -141,6 +151,28 @@ def load() -> C.CDLL:
         "bddb200_set_exchange": (i, [vp, i, i, vp, vp, vp, vp, vp, vp, sz, i]),
         "bddb200_delta_exchange": (i, [vp, i, i, i, vp, vp, C.c_uint32, sz, vp, sz]),
         "bddb200_delta_exchange_two_shot": (i, [vp, i, i, i, vp, vp, vp, C.c_uint32, sz, sz]),
+        "bddb200_collection_create": (i, [vp, sz, vp, sz, C.POINTER(vp)]),
+        "bddb200_collection_destroy": (i, [vp]),
+        "bddb200_collection_nr_bdds": (i, [vp, C.POINTER(sz)]),
+        "bddb200_collection_nr_instructions": (i, [vp, C.POINTER(sz)]),
+        "bddb200_collection_export": (i, [vp, vp, vp]),
+        "bddb200_collection_simplex_constraint": (i, [vp, sz, C.POINTER(sz)]),
+        "bddb200_collection_not_all_false_constraint": (i, [vp, sz, C.POINTER(sz)]),
+        "bddb200_collection_all_equal_constraint": (i, [vp, sz, C.POINTER(sz)]),
+        "bddb200_collection_cardinality_constraint": (i, [vp, sz, sz, C.POINTER(sz)]),
+        "bddb200_collection_rebase": (i, [vp, sz, vp, sz]),
+        "bddb200_collection_negate": (i, [vp, sz]),
+        "bddb200_collection_invert": (i, [vp, sz, sz]),
+        "bddb200_collection_variables": (i, [vp, sz, vp, sz, C.POINTER(sz)]),
+        "bddb200_collection_is_qbdd": (i, [vp, sz, C.POINTER(i)]),
+        "bddb200_collection_is_reordered": (i, [vp, sz, C.POINTER(i)]),
+        "bddb200_collection_evaluate": (i, [vp, sz, vp, sz, C.POINTER(i)]),
+        "bddb200_collection_reorder": (i, [vp, sz]),
+        "bddb200_collection_make_qbdd": (i, [vp, sz, C.POINTER(sz)]),
+        "bddb200_collection_bdd_and": (i, [vp, vp, sz, C.POINTER(sz)]),
+        "bddb200_collection_remove": (i, [vp, vp, sz]),
+        "bddb200_collection_split_qbdd": (i, [vp, sz, sz, sz, i, C.POINTER(sz), C.POINTER(sz)]),
+        "bddb200_collection_split_long_bdds": (i, [vp, sz, sz, i, C.POINTER(sz), C.POINTER(sz)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(lib, name)

@@ -21,6 +21,7 @@
 #include "kernels.cuh"
 #include "resident.cuh"
 #include "shard.hpp"
+#include "last_error.hpp"
 
 using namespace bddb200;
 
@@ -1570,6 +1571,9 @@ int guarded(F&& f)
 #define REQUIRE_SOLVER(s) if((s) == nullptr) { g_last_error = "null solver handle"; return BDDB200_ERR_INVALID_ARGUMENT; }
 
 } // namespace
+
+// the host-only translation units of the library (host/collection_abi.cpp) report their failures through the same string
+void bddb200::detail::set_last_error(const std::string& message) { g_last_error = message; }
 
 namespace {
 // run_solver, include/run_solver_util.h:10-77, on either the plain solver or its L-BFGS wrapper

@@ -33,23 +33,22 @@ int main(int argc, char** argv)
             std::cout << out.dump() << std::endl;
             return 0;
         }
-        if(argc == 4 && std::strcmp(argv[1], "--split") == 0)
-        {   // --split <length | auto> <file.lp>: convert, split the long BDDs, print the collection (host-side check of split.hpp)
+        if((argc == 4 || (argc == 5 && std::strcmp(argv[4], "--implication-bdd") == 0)) && std::strcmp(argv[1], "--split") == 0)
+        {   // --split <length | auto> <file.lp> [--implication-bdd]: convert, split the long BDDs, print the collection (host-side check)
             std::ifstream f(argv[3]);
             if(!f.good()) throw std::runtime_error(std::string("cannot open ") + argv[3]);
             std::stringstream ss; ss << f.rdbuf();
             const ILP ilp = parse_lp(ss.str());
-            const BddCollection col = bdds_from_ilp(ilp);
+            BddCollection col = bdds_from_ilp(ilp);
             const size_t length = std::strcmp(argv[2], "auto") == 0 ? compute_split_length(col) : (size_t)std::stoull(argv[2]);
-            SplitCollection sc;
             size_t n_split = 0, n_vars = ilp.nr_variables();
-            if(length != std::numeric_limits<size_t>::max()) n_vars = split_long_bdds(col, length, ilp.nr_variables(), sc, &n_split);
-            const std::vector<bddb200_instruction>& ins = n_split > 0 ? sc.instrs : col.instrs;
+            if(length != std::numeric_limits<size_t>::max()) n_vars = split_long_bdds(col, length, ilp.nr_variables(), argc == 5, &n_split);
+            const std::vector<bddb200_instruction>& ins = col.instrs;
             nlohmann::json out;
             out["split_length"] = length == std::numeric_limits<size_t>::max() ? -1 : (long long)length;
             out["n_split"] = n_split;
             out["nr_variables"] = n_vars;
-            out["delims"] = n_split > 0 ? sc.delims : col.delims;
+            out["delims"] = col.delims;
             std::vector<unsigned long long> flat;
             for(const bddb200_instruction& i : ins) { flat.push_back(i.lo); flat.push_back(i.hi); flat.push_back(i.index); }
             out["instrs"] = flat;
@@ -58,7 +57,7 @@ int main(int argc, char** argv)
         }
         if(argc != 2)
         {
-            std::fprintf(stderr, "usage: bdd_solver_cl <config.json | inline json>\n       bdd_solver_cl --lp-to-bdds <file.lp>\n       bdd_solver_cl --split <length | auto> <file.lp>\n");
+            std::fprintf(stderr, "usage: bdd_solver_cl <config.json | inline json>\n       bdd_solver_cl --lp-to-bdds <file.lp>\n       bdd_solver_cl --split <length | auto> <file.lp> [--implication-bdd]\n");
             return 2;
         }
         bdd_solver s{std::string(argv[1])};

@@ -34,7 +34,7 @@
 #include <nlohmann/json.hpp>
 
 #include "../../../include/bdd_b200.h"
-#include "split.hpp"
+#include "bdd_collection.hpp"
 
 namespace bddb200_host {
 
@@ -303,11 +303,7 @@ inline QbddTemplate qbdd_template(const std::vector<long long>& a, int ineq, lon
     return t;
 }
 
-struct BddCollection {
-    std::vector<bddb200_instruction> instrs;
-    std::vector<size_t> delims{0};
-    size_t nr_bdds() const { return delims.size() - 1; }
-};
+using BddCollection = bdd_collection;       // host/bdd_collection.hpp: instruction array + delimiters, generators, splitting
 
 // One BDD per constraint, in constraint order (bdd_preprocessor::add_ilp, bdd_preprocessor.cpp:123-228); templates are cached per
 // (coefficients, relation, right-hand side)
@@ -371,15 +367,14 @@ public:
             if(config.contains("split bdds"))
             {   // bdd_solver.cpp:105-123 -> bdd_preprocessor.cpp:372-415: "split bdds": {"split length": n}, or a computed length
                 const json sb = config["split bdds"].is_object() ? config["split bdds"] : json::object();
-                if(sb.value("implication bdd", false)) throw std::runtime_error("the implication BDD of split_qbdd is not implemented");
+                // the reference tests the key "implication bdd" and then reads "implication" (bdd_solver.cpp:119); both spellings are taken here
+                const bool implication = sb.value("implication bdd", false) || sb.value("implication", false);
                 const size_t length = sb.contains("split length") ? sb["split length"].get<size_t>() : compute_split_length(bdd_col_);
                 if(length != std::numeric_limits<size_t>::max())
                 {
-                    SplitCollection sc;
                     size_t n_split = 0;
                     const size_t before = bdd_col_.nr_bdds();
-                    split_long_bdds(bdd_col_, length, ilp_.nr_variables(), sc, &n_split);      // auxiliary variables carry no cost
-                    if(n_split > 0) { bdd_col_.instrs.swap(sc.instrs); bdd_col_.delims.swap(sc.delims); }
+                    split_long_bdds(bdd_col_, length, ilp_.nr_variables(), implication, &n_split);      // in place; auxiliary variables carry no cost
                     log("[bdd preprocessor] split " + std::to_string(n_split) + " BDDs longer than " + std::to_string(length) + ": " + std::to_string(before) + " -> " + std::to_string(bdd_col_.nr_bdds()) + " BDDs");
                 }
             }

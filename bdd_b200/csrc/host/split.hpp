@@ -1,7 +1,8 @@
 // bdd_b200/csrc/host/split.hpp -- splitting long BDDs into chunks linked by auxiliary variables, in C++ for the host driver.
-// Follows bdd_collection::split_qbdd without the optional implication BDD (src/bdd_collection/bdd_collection.cpp:507-790) and the driver
-// loop of bdd_preprocessor (src/bdd_conversion/bdd_preprocessor.cpp:372-415); same construction as bdd_b200/split.py, whose instruction
-// arrays are bit-identical to the reference's (tests/test_split.py against oracle/_ref) and which tests/test_cpp_driver.py compares this with.
+// The chunk construction of bdd_collection::split_qbdd (src/bdd_collection/bdd_collection.cpp:507-790); same construction as
+// bdd_b200/split.py, whose instruction arrays are bit-identical to the reference's (tests/test_split.py against oracle/_ref) and which
+// tests/test_cpp_driver.py compares this with.  The collection class around it -- split_qbdd with the optional implication BDD, the
+// preprocessor's loop over all BDDs -- is host/bdd_collection.hpp.
 //
 // Cutting a quasi-reduced BDD in front of a layer of width w introduces w auxiliary 0/1 variables that one-hot encode which node of
 // that layer the path goes through (aux variable w-1-k is 1 iff node k is used): the chunk before the cut ends in a *tail* gadget that
@@ -19,12 +20,6 @@
 #include "../../../include/bdd_b200.h"
 
 namespace bddb200_host {
-
-struct SplitCollection {
-    std::vector<bddb200_instruction> instrs;
-    std::vector<size_t> delims{0};
-    size_t nr_bdds() const { return delims.size() - 1; }
-};
 
 namespace split_detail {
 
@@ -120,71 +115,6 @@ inline size_t split_qbdd(const bddb200_instruction* ins, size_t first, size_t la
 }
 
 } // namespace split_detail
-
-// bdd_preprocessor.cpp:372-415 with a forced split length: every BDD over more than split_length variables is replaced by its chunks
-// (appended at the end, in BDD order); auxiliary variables are numbered from nr_variables on.  Returns the total number of variables.
-// A BDD whose cut would land in front of a layer of width 1 (the reference asserts) stays whole.
-template<typename COLLECTION>
-inline size_t split_long_bdds(const COLLECTION& col, size_t split_length, size_t nr_variables, SplitCollection& result, size_t* n_split_out = nullptr)
-{
-    using namespace split_detail;
-    if(split_length == 0) throw std::invalid_argument("split length must be positive");
-    size_t aux = nr_variables;
-    for(const bddb200_instruction& i : col.instrs) if(i.index < BOTSINK) aux = std::max(aux, i.index + 1);
-    const size_t nb = col.delims.size() - 1;
-    std::vector<char> removed(nb, 0);
-    // chunk BDDs are built behind the original array (absolute child indices), then everything kept is rebased into `result`
-    std::vector<bddb200_instruction> chunks;
-    std::vector<size_t> chunk_delims;                  // ends of the chunk BDDs, absolute
-    const size_t orig_end = col.delims[nb];
-    size_t n_split = 0;
-    for(size_t b = 0; b < nb; ++b)
-    {
-        size_t aux_b = aux;
-        std::vector<bddb200_instruction> local;      // the chunks of this BDD, child indices relative to local[0]
-        std::vector<size_t> local_delims;
-        size_t n = 0;
-        try { n = split_qbdd(col.instrs.data(), col.delims[b], col.delims[b + 1], split_length, aux_b, 0, local, local_delims); }
-        catch(const std::invalid_argument&) { continue; }        // this BDD stays whole
-        if(n <= 1) continue;
-        const size_t shift = orig_end + chunks.size();            // where local[0] sits behind the original array
-        for(bddb200_instruction ins : local)
-        {
-            if(ins.index < BOTSINK) { ins.lo += shift; ins.hi += shift; }
-            chunks.push_back(ins);
-        }
-        for(const size_t d : local_delims) chunk_delims.push_back(shift + d);
-        removed[b] = 1; ++n_split; aux = aux_b;
-    }
-    if(n_split_out) *n_split_out = n_split;
-    result.instrs.clear(); result.delims.assign(1, 0);
-    auto append = [&](const bddb200_instruction* src, size_t first, size_t last) {
-        const size_t to = result.instrs.size();
-        for(size_t i = first; i < last; ++i)
-        {
-            bddb200_instruction ins = src[i];
-            if(ins.index < BOTSINK) { ins.lo = ins.lo - first + to; ins.hi = ins.hi - first + to; }
-            result.instrs.push_back(ins);
-        }
-        result.delims.push_back(result.instrs.size());
-    };
-    for(size_t b = 0; b < nb; ++b)
-        if(!removed[b]) append(col.instrs.data(), col.delims[b], col.delims[b + 1]);
-    size_t prev = orig_end;
-    for(const size_t d : chunk_delims)
-    {   // chunk instructions live at absolute positions [prev, d) = chunks[prev - orig_end, d - orig_end)
-        const size_t to = result.instrs.size();
-        for(size_t i = prev; i < d; ++i)
-        {
-            bddb200_instruction ins = chunks[i - orig_end];
-            if(ins.index < BOTSINK) { ins.lo = ins.lo - prev + to; ins.hi = ins.hi - prev + to; }
-            result.instrs.push_back(ins);
-        }
-        result.delims.push_back(result.instrs.size());
-        prev = d;
-    }
-    return aux;
-}
 
 // Split length when the configuration gives none: the largest length that yields at least n_sms * warps_per_sm bundles of 32 BDDs, never
 // below min_length; SIZE_MAX when nothing should be split (bdd_b200/split.py: compute_split_length; the reference's rule,

@@ -286,6 +286,74 @@ class RefCollection:
             raise RuntimeError(self.lib.refw_collection_error(self.h).decode())
         return n.value, nxt
 
+    # the reference's direct generators and structural operations, one to one (ref_wrap.cpp)
+    def _call(self, name: str, *args, restype=C.c_size_t):
+        f = getattr(self.lib, name)
+        f.restype = restype
+        f.argtypes = [C.c_void_p] + [_szp if isinstance(a, np.ndarray) else C.c_size_t for a in args]
+        return f(self.h, *args)
+
+    def simplex_constraint(self, n: int) -> int:
+        return self._call("refw_simplex_constraint", n)
+
+    def not_all_false_constraint(self, n: int) -> int:
+        return self._call("refw_not_all_false_constraint", n)
+
+    def all_equal_constraint(self, n: int) -> int:
+        return self._call("refw_all_equal_constraint", n)
+
+    def cardinality_constraint(self, n: int, k: int) -> int:
+        return self._call("refw_cardinality_constraint", n, k)
+
+    def rebase(self, bdd_nr: int, variables) -> None:
+        v = np.ascontiguousarray(variables, dtype=np.uint64)
+        self._call("refw_rebase", bdd_nr, v, v.shape[0], restype=None)
+
+    def negate(self, bdd_nr: int) -> None:
+        self._call("refw_negate", bdd_nr, restype=None)
+
+    def invert(self, bdd_nr: int, var: int) -> None:
+        self._call("refw_invert", bdd_nr, var, restype=None)
+
+    def reorder(self, bdd_nr: int) -> None:
+        self._call("refw_reorder", bdd_nr, restype=None)
+
+    def make_qbdd(self, bdd_nr: int) -> int:
+        return self._call("refw_make_qbdd", bdd_nr)
+
+    def bdd_and(self, bdd_nrs) -> int:
+        v = np.ascontiguousarray(bdd_nrs, dtype=np.uint64)
+        return self._call("refw_bdd_and", v, v.shape[0])
+
+    def remove(self, bdd_nrs) -> None:
+        v = np.ascontiguousarray(bdd_nrs, dtype=np.uint64)
+        self._call("refw_remove", v, v.shape[0], restype=None)
+
+    def is_qbdd(self, bdd_nr: int) -> bool:
+        return bool(self._call("refw_is_qbdd", bdd_nr, restype=C.c_int))
+
+    def is_reordered(self, bdd_nr: int) -> bool:
+        return bool(self._call("refw_is_reordered", bdd_nr, restype=C.c_int))
+
+    def variables(self, bdd_nr: int) -> np.ndarray:
+        f = self.lib.refw_variables
+        f.restype = C.c_size_t
+        f.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        out = np.empty(f(self.h, bdd_nr, None), dtype=np.uint64)
+        f(self.h, bdd_nr, out.ctypes.data)
+        return out
+
+    def split_qbdd_implication(self, bdd_nr: int, chunk_size: int, aux_var_start: int) -> Tuple[int, int]:
+        """bdd_collection::split_qbdd WITH the implication BDD; returns (number of new BDDs, next aux variable)."""
+        f = self.lib.refw_split_qbdd_implication
+        f.restype = C.c_size_t
+        f.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(C.c_size_t)]
+        n = C.c_size_t()
+        nxt = f(self.h, bdd_nr, chunk_size, aux_var_start, C.byref(n))
+        if nxt == 2 ** 64 - 1:
+            raise RuntimeError(self.lib.refw_collection_error(self.h).decode())
+        return n.value, nxt
+
     def export(self) -> Tuple[np.ndarray, np.ndarray]:
         n = self.lib.refw_nr_instructions(self.h)
         b = self.lib.refw_nr_bdds(self.h)

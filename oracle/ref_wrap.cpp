@@ -138,6 +138,38 @@ size_t refw_split_qbdd(void* c, size_t bdd_nr, size_t chunk_size, size_t aux_var
     } catch(const std::exception& e) { rc->last_error = e.what(); return (size_t)-1; }
 }
 
+// The reference's direct generators and structural operations (bdd_collection.cpp:2039-2263, :1429, :1670, :31-315, :2023-2037),
+// called one to one so that tests/test_collection.py can compare bddb200_host::bdd_collection with them bit for bit.
+size_t refw_simplex_constraint(void* c, size_t n) { return static_cast<ref_collection*>(c)->col.simplex_constraint(n); }
+size_t refw_not_all_false_constraint(void* c, size_t n) { return static_cast<ref_collection*>(c)->col.not_all_false_constraint(n); }
+size_t refw_all_equal_constraint(void* c, size_t n) { return static_cast<ref_collection*>(c)->col.all_equal_constraint(n); }
+size_t refw_cardinality_constraint(void* c, size_t n, size_t k) { return static_cast<ref_collection*>(c)->col.cardinality_constraint(n, k); }
+void refw_rebase(void* c, size_t bdd_nr, const size_t* vars, size_t n) { static_cast<ref_collection*>(c)->col.rebase(bdd_nr, vars, vars + n); }
+void refw_negate(void* c, size_t bdd_nr) { static_cast<ref_collection*>(c)->col.negate(bdd_nr); }
+void refw_invert(void* c, size_t bdd_nr, size_t var) { static_cast<ref_collection*>(c)->col.invert(bdd_nr, var); }
+void refw_reorder(void* c, size_t bdd_nr) { static_cast<ref_collection*>(c)->col.reorder(bdd_nr); }
+size_t refw_make_qbdd(void* c, size_t bdd_nr) { return static_cast<ref_collection*>(c)->col.make_qbdd(bdd_nr); }
+size_t refw_bdd_and(void* c, const size_t* nrs, size_t n) { return static_cast<ref_collection*>(c)->col.bdd_and(nrs, nrs + n); }
+void refw_remove(void* c, const size_t* nrs, size_t n) { static_cast<ref_collection*>(c)->col.remove(nrs, nrs + n); }
+int refw_is_qbdd(void* c, size_t bdd_nr) { return static_cast<ref_collection*>(c)->col.is_qbdd(bdd_nr) ? 1 : 0; }
+int refw_is_reordered(void* c, size_t bdd_nr) { return static_cast<ref_collection*>(c)->col.is_reordered(bdd_nr) ? 1 : 0; }
+size_t refw_variables(void* c, size_t bdd_nr, size_t* out)
+{
+    const auto vars = static_cast<ref_collection*>(c)->col.variables(bdd_nr);
+    if(out != nullptr) std::copy(vars.begin(), vars.end(), out);
+    return vars.size();
+}
+// split_qbdd with the implication BDD switched on (bdd_collection.cpp:805-940); same return convention as refw_split_qbdd
+size_t refw_split_qbdd_implication(void* c, size_t bdd_nr, size_t chunk_size, size_t aux_var_start, size_t* nr_new)
+{
+    auto* rc = static_cast<ref_collection*>(c);
+    try {
+        const auto [new_nrs, next_aux] = rc->col.split_qbdd(bdd_nr, chunk_size, aux_var_start, true);
+        *nr_new = new_nrs.size();
+        return next_aux;
+    } catch(const std::exception& e) { rc->last_error = e.what(); return (size_t)-1; }
+}
+
 size_t refw_nr_instructions(void* c)
 {
     const BDD::bdd_collection& col = static_cast<ref_collection*>(c)->col;

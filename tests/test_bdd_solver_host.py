@@ -45,8 +45,24 @@ def test_split_key():
     assert np.array_equal(costs, costs2)                                   # auxiliary variables carry no cost
     if longest > 2 * 2 + 2:
         assert split.nr_bdds > whole.nr_bdds and split.nr_variables() > whole.nr_variables()
-    with pytest.raises(RuntimeError, match="implication"):
-        s.transform_to_BDDs({"split bdds": {"split length": 2, "implication bdd": True}})
+    # with the implication BDD: the same chunks in the same order, plus at most one BDD over auxiliary variables per cut BDD
+    with_imp, _ = s.transform_to_BDDs({"split bdds": {"split length": 2, "implication bdd": True}})
+    assert split.nr_bdds <= with_imp.nr_bdds and with_imp.nr_variables() == split.nr_variables()
+    n_orig = whole.nr_variables()
+    extra = 0
+    for b in range(with_imp.nr_bdds):
+        idx = with_imp.instrs[int(with_imp.delims[b]):int(with_imp.delims[b + 1]) - 2, 2]
+        extra += bool((idx >= n_orig).all())
+    assert extra == with_imp.nr_bdds - split.nr_bdds
+    # a constraint long enough for three cuts whose paths exclude combinations of cut nodes: one implication BDD
+    s = drv.bdd_solver(log=quiet)
+    s.ilp = s.read_ILP({"input": "Minimize\n " + " + ".join(f"{i + 1} x{i}" for i in range(8)) + "\nSubject To\n " + " + ".join(f"x{i}" for i in range(8)) + " = 3\nEnd\n"})
+    split, _ = s.transform_to_BDDs({"split bdds": {"split length": 2}})
+    for key in ("implication bdd", "implication"):
+        with_imp, _ = s.transform_to_BDDs({"split bdds": {"split length": 2, key: True}})
+        assert (split.nr_bdds, with_imp.nr_bdds) == (4, 5)
+        assert np.array_equal(with_imp.instrs[: split.nr_nodes, 2], split.instrs[:, 2])
+        assert (with_imp.instrs[split.nr_nodes:-2, 2] >= 8).all()
 
 
 def test_unsupported_keys_and_missing_gpu():

@@ -1,0 +1,379 @@
+"""The host-side BDD collection (include/bdd_b200_collection.h, bdd_b200/csrc/host/bdd_collection.hpp, bdd_b200/collection.py) against the
+reference's own BDD::bdd_collection compiled into oracle/_ref: direct generators, relabelling, reorder, make_qbdd, bdd_and, remove and
+split_qbdd with the implication BDD -- instruction arrays bit for bit -- and against the meaning of each operation by enumeration.
+CPU only."""
+import itertools
+
+import numpy as np
+import pytest
+
+import bindings as B
+from bdd_b200 import instances
+from bdd_b200.collection import bdd_collection
+from bdd_b200.instances import BddCollection, bdds_accept
+
+needs_ref = pytest.mark.skipif(not B.ref_available(), reason="oracle/_ref not built")
+
+
+def from_rows(rows) -> BddCollection:
+    """rows of (coefficients, variables, relation 0 '<=' / 1 '>=' / 2 '=', right-hand side)"""
+    from types import SimpleNamespace
+    return instances.from_constraints([SimpleNamespace(coefficients=c, variables=v, ineq=i, rhs=r) for c, v, i, r in rows])
+
+
+def assert_same(mine: bdd_collection, ref: "B.RefCollection"):
+    m = mine.export()
+    r_instrs, r_delims = ref.export()
+    assert np.array_equal(m.delims, r_delims)
+    assert np.array_equal(m.instrs[:, 2], r_instrs[:, 2])
+    inner = m.instrs[:, 2] < instances.BOTSINK
+    assert np.array_equal(m.instrs[inner], r_instrs[inner])              # lo / hi of the sink instructions carry no meaning
+
+
+def both():
+    return bdd_collection(), B.RefCollection()
+
+
+# ------------------------------------------------------------------------------------------------ generators
+@needs_ref
+def test_generators_match_the_reference_bit_for_bit():
+    mine, ref = both()
+    for n in (1, 2, 3, 7, 40):
+        assert mine.simplex_constraint(n) == ref.simplex_constraint(n)
+        assert mine.not_all_false_constraint(n) == ref.not_all_false_constraint(n)
+    for n in (2, 3, 7, 40):
+        assert mine.all_equal_constraint(n) == ref.all_equal_constraint(n)
+    for n, k in [(2, 0), (2, 1), (2, 2), (5, 0), (5, 1), (5, 2), (5, 3), (5, 5), (9, 4), (30, 7), (30, 29)]:
+        assert mine.cardinality_constraint(n, k) == ref.cardinality_constraint(n, k)
+    assert_same(mine, ref)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 6])
+def test_generators_mean_what_they_say(n):
+    col = bdd_collection()
+    kinds = [("simplex", col.simplex_constraint(n), lambda s: s == 1), ("some", col.not_all_false_constraint(n), lambda s: s >= 1)]
+    if n > 1:
+        kinds.append(("equal", col.all_equal_constraint(n), lambda s: s in (0, n)))
+        for k in range(n + 1):
+            kinds.append((f"card{k}", col.cardinality_constraint(n, k), lambda s, k=k: s == k))
+    for x in itertools.product((0, 1), repeat=n):
+        for name, b, want in kinds:
+            assert col.evaluate(b, x) == want(sum(x)), (name, x)
+    for name, b, _ in kinds:
+        assert col.is_qbdd(b) == (name != "some" or n == 1), name          # arcs may skip layers only into the bot sink
+
+
+def test_generator_arguments_are_checked():
+    from bdd_b200._lib import BddB200Error
+    col = bdd_collection()
+    for call in (lambda: col.simplex_constraint(0), lambda: col.all_equal_constraint(1), lambda: col.cardinality_constraint(3, 4),
+                 lambda: col.negate(0), lambda: col.bdd_and([0])):
+        with pytest.raises(BddB200Error):
+            call()
+    assert col.nr_bdds() == 0
+
+
+# ------------------------------------------------------------------------------------------------ relabelling, reorder, make_qbdd, remove
+@needs_ref
+def test_rebase_negate_invert_remove_match_the_reference():
+    mine, ref = both()
+    for c in (mine, ref):
+        a = c.simplex_constraint(5)
+        c.rebase(a, [3, 8, 9, 20, 21])
+        b = c.not_all_false_constraint(4)
+        c.rebase(b, [1, 2, 5, 7])
+        c.invert(b, 5)
+        d = c.cardinality_constraint(6, 3)
+        c.negate(d)
+        e = c.all_equal_constraint(3)
+        c.invert(e, 0)
+    assert_same(mine, ref)
+    assert np.array_equal(mine.variables(1), ref.variables(1)) and list(mine.variables(1)) == [1, 2, 5, 7]
+    for c in (mine, ref):
+        c.remove([0, 2])
+    assert_same(mine, ref)
+    assert mine.nr_bdds() == 2
+
+
+@needs_ref
+def test_reorder_and_variable_order_match_the_reference():
+    """bdd_and writes its result in reverse post-order, which is not layered: reorder has something to do there; a rebase onto
+    non-monotone variables makes `variables` fall back to the topological order of the layers (bdd_collection.cpp:1232-1304)"""
+    mine, ref = both()
+    for c in (mine, ref):
+        ops = _operands(c, range(6))
+        made = [c.bdd_and(ops[:3]), c.bdd_and(ops[2:]), c.bdd_and(ops)]
+        s = c.simplex_constraint(5)
+        c.rebase(s, [7, 3, 9, 1, 4])
+        k = c.cardinality_constraint(6, 2)
+        c.rebase(k, [5, 4, 30, 2, 1, 0])
+        x = c.not_all_false_constraint(4)
+        c.rebase(x, [9, 2, 6, 3])
+        made += [s, k, x, c.make_qbdd(x)]
+    moved = 0
+    for b in made:
+        assert np.array_equal(mine.variables(b), ref.variables(b))
+        assert mine.is_reordered(b) == ref.is_reordered(b) and mine.is_qbdd(b) == ref.is_qbdd(b)
+        moved += not mine.is_reordered(b)
+        mine.reorder(b)
+        ref.reorder(b)
+        assert mine.is_reordered(b)
+    assert moved >= 3
+    assert list(mine.variables(made[3])) == [7, 3, 9, 1, 4] and list(mine.variables(made[4])) == [5, 4, 30, 2, 1, 0]
+    assert_same(mine, ref)
+
+
+@needs_ref
+def test_make_qbdd_matches_the_reference():
+    mine, ref = both()
+    for c in (mine, ref):
+        made = []
+        for n in (1, 2, 5, 9):
+            made.append(c.not_all_false_constraint(n))
+        for n in (2, 3, 8):
+            made.append(c.all_equal_constraint(n))
+        b = c.cardinality_constraint(7, 0)
+        made.append(b)
+        x = c.not_all_false_constraint(6)
+        c.rebase(x, [2, 3, 11, 12, 40, 41])
+        c.invert(x, 11)
+        made.append(x)
+        made.append(c.simplex_constraint(4))                            # quasi-reduced already: make_qbdd copies it
+        ops = _operands(c, range(6))
+        made.append(c.bdd_and(ops[:3]))                                 # reduced conjunctions skip layers in many places
+        made.append(c.bdd_and(ops[1:]))
+        for b in made:
+            q = c.make_qbdd(b)
+            assert c.is_qbdd(q)
+    assert_same(mine, ref)
+
+
+@pytest.mark.parametrize("n", [2, 4, 6])
+def test_make_qbdd_keeps_the_function(n):
+    col = bdd_collection()
+    for b in (col.not_all_false_constraint(n), col.all_equal_constraint(n), col.cardinality_constraint(n, 0)):
+        q = col.make_qbdd(b)
+        assert col.is_qbdd(q) and col.is_reordered(q)
+        for x in itertools.product((0, 1), repeat=n):
+            assert col.evaluate(q, x) == col.evaluate(b, x)
+
+
+# ------------------------------------------------------------------------------------------------ bdd_and
+def _operands(c, which):
+    """a handful of BDDs over overlapping ascending variables"""
+    made = []
+    def add(b, variables, inverted=()):
+        c.rebase(b, variables)
+        for v in inverted:
+            c.invert(b, v)
+        made.append(b)
+    add(c.simplex_constraint(4), [0, 2, 4, 6])
+    add(c.not_all_false_constraint(3), [1, 2, 3], inverted=[2])
+    add(c.cardinality_constraint(5, 2), [3, 4, 5, 7, 8])
+    add(c.all_equal_constraint(3), [0, 5, 9])
+    add(c.not_all_false_constraint(4), [4, 6, 8, 9], inverted=[4])
+    add(c.simplex_constraint(3), [7, 8, 9])
+    return [made[i] for i in which]
+
+
+@needs_ref
+@pytest.mark.parametrize("which", [(0, 1), (2, 3), (0, 1, 2), (1, 3, 4), (0, 1, 2, 3), (0, 1, 2, 3, 4, 5), (5, 0, 3)])
+def test_bdd_and_matches_the_reference(which):
+    mine, ref = both()
+    nrs = [_operands(c, which) for c in (mine, ref)]
+    assert nrs[0] == nrs[1]
+    assert mine.bdd_and(nrs[0]) == ref.bdd_and(nrs[1])
+    assert_same(mine, ref)
+
+
+@needs_ref
+def test_bdd_and_of_more_operands_than_the_reference_takes_at_once():
+    """above 49 operands the reference sorts and batches (bdd_collection.h:506-546); the result is the same canonical BDD"""
+    mine, ref = both()
+    nrs = []
+    for c in (mine, ref):
+        mine_nrs = []
+        for i in range(60):
+            b = c.not_all_false_constraint(3)
+            c.rebase(b, [i % 7, 7 + i % 5, 12 + i % 3])
+            if i % 2:
+                c.invert(b, 7 + i % 5)
+            mine_nrs.append(b)
+        b = c.simplex_constraint(4)
+        c.rebase(b, [0, 3, 9, 14])
+        mine_nrs.append(b)
+        nrs.append(mine_nrs)
+    a, b = mine.bdd_and(nrs[0]), ref.bdd_and(nrs[1])
+    m, (r_instrs, r_delims) = mine.export(), ref.export()
+    got = m.instrs[int(m.delims[a]):int(m.delims[a + 1])].astype(np.int64) - int(m.delims[a])
+    want = r_instrs[int(r_delims[b]):int(r_delims[b + 1])].astype(np.int64) - int(r_delims[b])
+    assert np.array_equal(got[:-2, :2], want[:-2, :2]) and np.array_equal(m.instrs[int(m.delims[a]):int(m.delims[a + 1]), 2], r_instrs[int(r_delims[b]):int(r_delims[b + 1]), 2])
+
+
+def test_bdd_and_is_the_conjunction():
+    col = bdd_collection()
+    nrs = _operands(col, range(6))
+    for which in [(0, 1), (1, 2, 3), (0, 1, 2, 3, 4), (2, 4, 5)]:
+        a = col.bdd_and([nrs[i] for i in which])
+        for x in itertools.product((0, 1), repeat=10):
+            assert col.evaluate(a, x) == all(col.evaluate(nrs[i], x) for i in which)
+
+
+# ------------------------------------------------------------------------------------------------ split_qbdd with the implication BDD
+def _long_bdds():
+    """quasi-reduced BDDs whose paths rule out combinations of cut nodes (so that the implication BDD is not trivial) and some that do not"""
+    cols = [instances.random_inequalities(10, 16, max_len=14, max_coeff=5, seed=s)[0] for s in (3, 11)]
+    cols.append(from_rows([([1] * 9, list(range(9)), 2, 4), ([1] * 10, list(range(10)), 0, 3), ([2, 3, 1, 4, 2, 3, 1, 2, 5, 1], list(range(10)), 1, 9)]))
+    cols.append(instances.assignment(9, seed=1)[0])
+    return cols
+
+
+@needs_ref
+@pytest.mark.parametrize("chunk", [2, 3, 4])
+def test_split_with_implication_bdd_matches_the_reference(chunk):
+    n_implication = 0
+    for col in _long_bdds():
+        mine, ref = bdd_collection(col), B.RefCollection.from_arrays(col.instrs, col.delims)
+        aux = aux_ref = col.nr_variables()
+        for b in range(col.nr_bdds):
+            layers = np.unique(col.instrs[int(col.delims[b]):int(col.delims[b + 1]) - 2, 2]).shape[0]
+            widths = np.unique(col.instrs[int(col.delims[b]):int(col.delims[b + 1]) - 2, 2], return_counts=True)[1]
+            if layers <= chunk or any(widths[c] <= 1 for c in range(chunk, layers, chunk)):
+                continue                      # short, or a cut in front of a width-1 layer (the reference asserts there, bdd_collection.cpp:598)
+            new_nrs, aux = mine.split_qbdd(b, chunk, aux, True)
+            n_new, aux_ref = ref.split_qbdd_implication(b, chunk, aux_ref)
+            assert aux == aux_ref and len(new_nrs) == n_new
+            nr_chunks = -(-layers // chunk)
+            n_implication += n_new == nr_chunks + 1
+        assert_same(mine, ref)
+        for b in range(mine.nr_bdds()):
+            assert mine.is_qbdd(b)
+    assert n_implication > 0 or chunk == 4
+
+
+@pytest.mark.parametrize("rows, chunk", [
+    ([([1] * 6, list(range(6)), 2, 2)], 2),                             # exactly 2 of 6: three chunks
+    ([([1] * 8, list(range(8)), 2, 1)], 2),                             # a simplex over 8: four chunks, three cuts
+    ([([2, 1, 3, 1, 2, 1], list(range(6)), 0, 5), ([1, 2, 1, 2, 1, 1, 2], list(range(7)), 1, 4)], 2),
+])
+def test_implication_bdd_accepts_exactly_the_cut_patterns_of_the_paths(rows, chunk):
+    """every assignment of the original variables that the BDD accepts extends in exactly one way to the auxiliary variables such that
+    all chunks accept, and the implication BDD accepts that extension; the implication BDD only looks at auxiliary variables"""
+    col = from_rows(rows)
+    n_orig = col.nr_variables()
+    c = bdd_collection(col)
+    aux = n_orig
+    for b in range(col.nr_bdds):
+        n_layers = len(c.variables(b))
+        first = c.nr_bdds()
+        new_nrs, aux_next = c.split_qbdd(b, chunk, aux, True)
+        assert len(new_nrs) == -(-n_layers // chunk) + 1, "these BDDs have non-trivial implications"
+        imp = new_nrs[-1]
+        assert c.is_qbdd(imp) and all(aux <= v < aux_next for v in c.variables(imp))
+        n_aux = aux_next - aux
+        assert n_aux <= 12
+        for x in itertools.product((0, 1), repeat=n_orig):
+            full = np.zeros(aux_next, dtype=np.int8)
+            full[:n_orig] = x
+            accepted = c.evaluate(b, full)
+            extensions = 0
+            for y in itertools.product((0, 1), repeat=n_aux):
+                full[aux:aux_next] = y
+                if all(c.evaluate(k, full) for k in new_nrs[:-1]):
+                    extensions += 1
+                    assert c.evaluate(imp, full)
+            assert extensions == (1 if accepted else 0), x
+        aux = aux_next
+        assert first + len(new_nrs) == c.nr_bdds()
+
+
+def test_split_long_bdds_equals_the_python_splitter_without_implication_bdd():
+    from bdd_b200.split import split_long_bdds
+    for col in _long_bdds():
+        for length in (3, 5):
+            want, n_vars_want = split_long_bdds(col, length)
+            c = bdd_collection(col)
+            n_split, n_vars = c.split_long_bdds(length, col.nr_variables(), False)
+            got = c.export()
+            assert n_vars == n_vars_want and n_split > 0
+            assert np.array_equal(got.delims, want.delims) and np.array_equal(got.instrs[:, 2], want.instrs[:, 2])
+            inner = got.instrs[:, 2] < instances.BOTSINK
+            assert np.array_equal(got.instrs[inner], want.instrs[inner])
+
+
+def test_split_long_bdds_with_implication_bdd_keeps_the_feasible_set():
+    """the split problem has exactly one solution per solution of the original one (the auxiliary variables are functions of the path)"""
+    col = from_rows([([1] * 6, list(range(6)), 2, 2), ([1, 2, 1, 2, 1, 2], list(range(6)), 0, 5), ([1, 1], [0, 5], 0, 1)])
+    c = bdd_collection(col)
+    n_split, n_vars = c.split_long_bdds(2, col.nr_variables(), True)
+    assert n_split == 2
+    flat = c.export()
+    assert flat.nr_bdds == 1 + 2 * (3 + 1)                                # the short BDD, then per long BDD three chunks and the implication BDD
+    blocks = []                                                          # auxiliary variables of each group of four BDDs
+    for g in range(2):
+        vs = np.unique(np.concatenate([c.variables(1 + 4 * g + k) for k in range(4)]))
+        blocks.append([int(v) for v in vs if v >= 6])
+    assert not set(blocks[0]) & set(blocks[1]) and len(blocks[0]) + len(blocks[1]) == n_vars - 6 and max(map(len, blocks)) <= 8
+    for x in itertools.product((0, 1), repeat=6):
+        want = bool(bdds_accept(col, x).all())
+        full = np.zeros(n_vars, dtype=np.int8)
+        full[:6] = x
+        n_ext = int(c.evaluate(0, full))
+        for g in range(2):
+            count = 0
+            for y in itertools.product((0, 1), repeat=len(blocks[g])):
+                full[blocks[g]] = y
+                count += all(c.evaluate(1 + 4 * g + k, full) for k in range(4))
+            n_ext *= count
+        assert n_ext == (1 if want else 0), x
+
+
+# ------------------------------------------------------------------------------------------------ solving what the splitter produces
+def _cardinality_problem(seed=5, n_vars=24, n_rows=10, row_len=9, k=3):
+    """exactly k of row_len variables per row: long BDDs of width up to k + 1 whose cuts have non-trivial implications"""
+    rng = np.random.default_rng(seed)
+    rows = [([1] * row_len, sorted(rng.choice(n_vars, size=row_len, replace=False).tolist()), 2, k) for _ in range(n_rows)]
+    return from_rows(rows), rng.normal(size=n_vars)
+
+
+def _split_with_implication(col, costs, length):
+    c = bdd_collection(col)
+    n_split, n_all = c.split_long_bdds(length, len(costs), True)
+    flat = c.export()
+    assert n_split == col.nr_bdds and flat.nr_bdds == col.nr_bdds * (-(-9 // length) + 1)         # every row: its chunks and one implication BDD
+    return flat, np.concatenate([costs, np.zeros(n_all - len(costs))])
+
+
+def test_oracle_solves_a_collection_with_implication_bdds():
+    """the split relaxation with implication BDDs is a relaxation of the same problem: its bound stays below the whole problem's bound
+    -- which both reach from below -- and is at least as good as random guessing, i.e. finite and increasing"""
+    col, costs = _cardinality_problem()
+    flat, c = _split_with_implication(col, costs, 3)
+    B.oracle_set_num_threads(1)
+    whole, split = B.Oracle(col.instrs, col.delims, costs, "double"), B.Oracle(flat.instrs, flat.delims, c, "double")
+    lbs = [split.lower_bound()]
+    for _ in range(200):
+        whole.iteration(); split.iteration()
+        lbs.append(split.lower_bound())
+    assert np.isfinite(lbs).all() and lbs[-1] >= lbs[0] and all(b >= a - 1e-9 for a, b in zip(lbs, lbs[1:]))
+    assert lbs[-1] <= whole.lower_bound() + 1e-6 * max(1.0, abs(whole.lower_bound()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["double", "float"])
+@pytest.mark.parametrize("length", [2, 3])
+def test_collection_with_implication_bdds_solves_like_the_oracle_on_gpu(precision, length):
+    """chunks plus implication BDDs (pass-through nodes, top sink before bot sink) go through the sweep kernels like any other
+    collection: iteration-by-iteration parity with the CPU oracle"""
+    pytest.importorskip("torch")
+    from bdd_b200.solver import bdd_cuda_parallel_mma
+    col, costs = _cardinality_problem()
+    flat, c = _split_with_implication(col, costs, length)
+    B.oracle_set_num_threads(1)
+    s = bdd_cuda_parallel_mma(flat, c, precision=precision, deterministic=(precision == "double"))
+    o = B.Oracle(flat.instrs, flat.delims, c, precision)
+    tol = 1e-9 if precision == "double" else 1e-4
+    assert abs(s.lower_bound() - o.lower_bound()) <= tol * max(1.0, abs(o.lower_bound()))
+    for _ in range(15):
+        s.iteration(); o.iteration()
+        assert abs(s.lower_bound() - o.lower_bound()) <= tol * max(1.0, abs(o.lower_bound()))

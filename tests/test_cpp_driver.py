@@ -91,6 +91,34 @@ def test_cpp_splitter_equals_the_python_one(tmp_path, length):
         assert np.array_equal(np.asarray(out["instrs"], dtype=np.uint64).reshape(-1, 3), want.instrs), path
 
 
+@pytest.mark.parametrize("length", [2, 3])
+def test_cpp_splitter_with_implication_bdd_equals_the_library(tmp_path, length):
+    """bdd_solver_cl --split ... --implication-bdd (the header-only class inside the C++ driver) against the same class behind the C ABI
+    (bdd_b200/collection.py), which tests/test_collection.py pins to the reference's split_qbdd(..., with_implication_bdd = true)"""
+    _need_cli()
+    from bdd_b200 import instances, lp
+    from bdd_b200.collection import bdd_collection
+    rng = np.random.default_rng(4)
+    lines = ["Minimize", " " + " + ".join(f"{int(rng.integers(1, 9))} x{i}" for i in range(20)), "Subject To"]
+    for r in range(6):
+        vs = sorted(rng.choice(20, size=9, replace=False).tolist())
+        lines.append(" " + " + ".join(f"x{v}" for v in vs) + (" = 3" if r % 2 else " <= 4"))
+    lines.append("End")
+    path = tmp_path / "cardinality.lp"
+    path.write_text("\n".join(lines) + "\n")
+    r = subprocess.run([CLI, "--split", str(length), str(path), "--implication-bdd"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    out = json.loads(r.stdout)
+    col, costs = instances.from_ilp(lp.parse_lp(path.read_text()))
+    c = bdd_collection(col)
+    n_split, n_vars = c.split_long_bdds(length, len(costs), True)
+    want = c.export()
+    assert out["n_split"] == n_split == 6 and out["nr_variables"] == n_vars
+    assert want.nr_bdds > 6 * -(-9 // length), "no implication BDD in this instance"
+    assert np.array_equal(np.asarray(out["delims"], dtype=np.uint64), want.delims)
+    assert np.array_equal(np.asarray(out["instrs"], dtype=np.uint64).reshape(-1, 3), want.instrs)
+
+
 def test_cpp_split_length_rule_equals_the_python_one(tmp_path):
     _need_cli()
     from bdd_b200 import instances, lp

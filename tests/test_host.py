@@ -13,12 +13,14 @@ from bdd_b200 import _lib
 
 def test_library_exports_every_declared_symbol():
     lib = _lib.load()
-    header = open(os.path.join(ROOT, "include", "bdd_b200.h")).read()
-    declared = set(re.findall(r"\b(bddb200_[a-z_0-9]+)\s*\(", header))
-    declared -= {"bddb200_solver", "bddb200_instruction", "bddb200_status", "bddb200_precision", "bddb200_options"}
-    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
-    for name in declared:
-        assert hasattr(lib, name), name
+    for header_name, symbols in (("bdd_b200.h", _lib.SYMBOLS), ("bdd_b200_collection.h", _lib.COLLECTION_SYMBOLS)):
+        header = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", header_name)).read(), flags=re.S)      # declarations only
+        declared = set(re.findall(r"\b(bddb200_[a-z_0-9]+)\s*\(", header))
+        declared -= {"bddb200_solver", "bddb200_instruction", "bddb200_status", "bddb200_precision", "bddb200_options"}
+        assert declared == set(symbols), declared ^ set(symbols)
+        for name in declared:
+            assert hasattr(lib, name), name
+    assert sorted(os.listdir(os.path.join(ROOT, "include"))) == ["bdd_b200.h", "bdd_b200_collection.h"]
     assert b"sm_100a" in lib.bddb200_version()
 
 
