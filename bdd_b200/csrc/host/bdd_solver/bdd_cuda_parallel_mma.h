@@ -18,7 +18,8 @@
 // Differences to the reference class, all outside what its callers use:
 //  * the per-layer vectors are in BDD-major "layer order" (include/bdd_b200.h) instead of the
 //    hop-sorted order; get_primal_variable_index() / get_bdd_index() describe it, and all
-//    per-layer vectors of one solver share it (that is all callers rely on);
+//    per-layer vectors of one solver share it (that is all callers rely on); reference_layer_order()
+//    gives the permutation onto the reference's order for data that crosses between the two;
 //  * node-level accessors of the reference's internal layout (get_lo_bdd_node_index, ...), the
 //    sum-marginal functions of the learned solver are not provided (out of scope, SURVEY 2 rows
 //    16-18); cereal save / load carry the library's own state blob (bddb200_save), not the
@@ -26,6 +27,7 @@
 //    subclass bdd_cuda_learned_mma does not build on top of this class.
 #pragma once
 
+#include <algorithm>
 #include <array>
 #include <cassert>
 #include <climits>
@@ -212,6 +214,27 @@ namespace LPMP {
             const thrust::device_vector<int> get_primal_variable_index() const { return thrust::device_vector<int>(primal_variable_index_host_.begin(), primal_variable_index_host_.end()); }
             const thrust::device_vector<int> get_bdd_index() const { return thrust::device_vector<int>(bdd_index_host_.begin(), bdd_index_host_.end()); }
             const thrust::device_vector<int>& get_num_bdds_per_var() const { return num_bdds_per_var_; }
+
+            // perm[k] = position, in this class's BDD-major layer order, of the layer the reference class keeps at position k.
+            // The reference sorts its nodes by (hop distance, primal variable, BDD) and compresses equal keys to layers
+            // (bdd_cuda_base.cu:146-188, :240-285; both sinks of a BDD share the hop after its last variable and the variable INT_MAX,
+            // :113-129).  thrust::gather(perm, v) turns a per-layer vector of this class into the reference's order, thrust::scatter
+            // brings one saved from the reference back (pinned against the reference's own CUDA build in tests/test_layer_order_gpu.py).
+            std::vector<int> reference_layer_order() const
+            {
+                const size_t n = bdd_index_host_.size();
+                std::vector<int> hop(n), perm(n);
+                for(size_t k = 0, first = 0; k < n; ++k)
+                {
+                    if(k > 0 && bdd_index_host_[k] != bdd_index_host_[k - 1]) first = k;
+                    hop[k] = int(k - first);
+                    perm[k] = int(k);
+                }
+                std::sort(perm.begin(), perm.end(), [&](int a, int b) {
+                    return std::make_tuple(hop[a], primal_variable_index_host_[a], bdd_index_host_[a]) < std::make_tuple(hop[b], primal_variable_index_host_[b], bdd_index_host_[b]);
+                });
+                return perm;
+            }
 
             void distribute_delta() { bddb200_detail::check(bddb200_distribute_delta(h_)); }
 

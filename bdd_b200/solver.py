@@ -25,6 +25,21 @@ from .instances import BddCollection
 INT_MAX = 2 ** 31 - 1
 
 
+def reference_layer_order(primal_index: np.ndarray, bdd_index: np.ndarray) -> np.ndarray:
+    """The reference sorts its BDD nodes by (hop distance from the root, primal variable, BDD) and compresses equal keys to layers
+    (bdd_cuda_base.cu:146-188, :240-285); the two sinks of a BDD share the hop after its last variable and the variable INT_MAX
+    (:113-129).  Its per-layer vectors are therefore ordered by (position of the layer in its BDD, variable, BDD), terminal layers
+    last within their hop.  Given the per-layer variable and BDD of a BDD-major order (layers of BDD 0, its terminal layer, BDD 1, ...),
+    returns the permutation that lists the BDD-major positions in the reference's order."""
+    primal_index = np.asarray(primal_index, dtype=np.int64)
+    bdd_index = np.asarray(bdd_index, dtype=np.int64)
+    n = bdd_index.shape[0]
+    first = np.flatnonzero(np.concatenate([[True], bdd_index[1:] != bdd_index[:-1]])) if n else np.zeros(0, dtype=np.int64)
+    run = np.cumsum(np.concatenate([[True], bdd_index[1:] != bdd_index[:-1]])) - 1 if n else np.zeros(0, dtype=np.int64)
+    hop = np.arange(n, dtype=np.int64) - first[run]
+    return np.lexsort((bdd_index, primal_index, hop)).astype(np.int64)
+
+
 class bdd_cuda_parallel_mma:
     """``bdd_cuda_parallel_mma<REAL>(bdd_col, costs)`` (bdd_cuda_parallel_mma.cu:7-17).
 
@@ -200,6 +215,13 @@ class bdd_cuda_parallel_mma:
         out = np.empty(self.nr_layers(), dtype=np.int32)
         check(self.lib.bddb200_layer_bdd_indices(self.h, out.ctypes.data))
         return out
+
+    def reference_layer_order(self) -> np.ndarray:
+        """``perm`` with ``perm[k]`` = position, in this class's BDD-major layer order, of the layer the reference's
+        ``bdd_cuda_base`` keeps at position ``k`` (see :func:`reference_layer_order`).  ``v[perm]`` turns a per-layer vector of
+        this solver (``get_solver_costs``, ``net_solver_costs``, ``bdds_solution_vec``, ...) into the reference's order;
+        ``w = empty_like(v); w[perm] = v_ref`` brings one saved from the reference back."""
+        return reference_layer_order(self.get_primal_variable_index(), self.get_bdd_index())
 
     # ------------------------------------------------------------------ hot path -------
     def iteration(self, omega: float = 0.5):

@@ -464,6 +464,10 @@ def _ref_cuda():
         lib.refcu_nr_hops.argtypes = [C.c_void_p]
         lib.refcu_nr_bdd_nodes.restype = C.c_size_t
         lib.refcu_nr_bdd_nodes.argtypes = [C.c_void_p]
+        lib.refcu_nr_layers.restype = C.c_size_t
+        lib.refcu_nr_layers.argtypes = [C.c_void_p]
+        lib.refcu_layer_indices.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.refcu_get_solver_costs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _ref_cuda_lib = lib
     return _ref_cuda_lib
 
@@ -499,3 +503,17 @@ class RefCudaSolver:
 
     def nr_hops(self) -> int:
         return self.lib.refcu_nr_hops(self.h)
+
+    def nr_layers(self) -> int:
+        return self.lib.refcu_nr_layers(self.h)
+
+    def layer_indices(self) -> Tuple[np.ndarray, np.ndarray]:
+        """(get_primal_variable_index(), get_bdd_index()) in the reference's own layer order."""
+        primal, bdd = np.empty(self.nr_layers(), dtype=np.int32), np.empty(self.nr_layers(), dtype=np.int32)
+        self.lib.refcu_layer_indices(self.h, primal.ctypes.data, bdd.ctypes.data)
+        return primal, bdd
+
+    def get_solver_costs(self) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        out = [np.empty(self.nr_layers(), dtype=np.float64) for _ in range(3)]
+        self.lib.refcu_get_solver_costs(self.h, *(o.ctypes.data for o in out))
+        return tuple(out)

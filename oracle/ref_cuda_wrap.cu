@@ -12,6 +12,10 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <thrust/copy.h>
+#include <thrust/device_vector.h>
+#include <tuple>
+#include <type_traits>
 
 #define private public          // fill bdd_instructions / bdd_delimiters verbatim (see oracle/ref_wrap.cpp)
 #include "bdd_collection/bdd_collection.h"
@@ -26,6 +30,17 @@ struct refcu_solver {
     std::unique_ptr<bdd_cuda_parallel_mma<double>> d;
     std::unique_ptr<bdd_cuda_parallel_mma<float>> f;
 };
+template<typename SOLVER>
+void solver_costs(SOLVER& x, double* lo_out, double* hi_out, double* mm_out)
+{
+    const auto costs = x.get_solver_costs();
+    const auto& lo = std::get<0>(costs); const auto& hi = std::get<1>(costs); const auto& mm = std::get<2>(costs);
+    using REAL = typename std::decay_t<decltype(lo)>::value_type;
+    std::vector<REAL> tmp(lo.size());
+    thrust::copy(lo.begin(), lo.end(), tmp.begin()); std::copy(tmp.begin(), tmp.end(), lo_out);
+    thrust::copy(hi.begin(), hi.end(), tmp.begin()); std::copy(tmp.begin(), tmp.end(), hi_out);
+    thrust::copy(mm.begin(), mm.end(), tmp.begin()); std::copy(tmp.begin(), tmp.end(), mm_out);
+}
 }
 
 extern "C" {
@@ -71,6 +86,23 @@ double refcu_iterations(void* h, size_t n)
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 size_t refcu_nr_hops(void* h) { refcu_solver* s = static_cast<refcu_solver*>(h); return s->is_double ? s->d->nr_hops() : s->f->nr_hops(); }
+// The reference's per-layer vectors in ITS layer order (hop-sorted, bdd_cuda_base.cu:146-188, :240-285): primal variable and BDD of
+// every layer (get_primal_variable_index / get_bdd_index, include/bdd_solver/bdd_cuda_base.h:147-148) and the lo / hi costs and deferred
+// min-marginal differences (get_solver_costs, :124-128).  tests/test_layer_order_gpu.py pins reference_layer_order() to them.
+size_t refcu_nr_layers(void* h) { refcu_solver* s = static_cast<refcu_solver*>(h); return s->is_double ? s->d->nr_layers() : s->f->nr_layers(); }
+void refcu_layer_indices(void* h, int* primal_out, int* bdd_out)
+{
+    refcu_solver* s = static_cast<refcu_solver*>(h);
+    const thrust::device_vector<int> p = s->is_double ? s->d->get_primal_variable_index() : s->f->get_primal_variable_index();
+    const thrust::device_vector<int> b = s->is_double ? s->d->get_bdd_index() : s->f->get_bdd_index();
+    thrust::copy(p.begin(), p.end(), primal_out);
+    thrust::copy(b.begin(), b.end(), bdd_out);
+}
+void refcu_get_solver_costs(void* h, double* lo_out, double* hi_out, double* mm_out)
+{
+    refcu_solver* s = static_cast<refcu_solver*>(h);
+    if(s->is_double) solver_costs(*s->d, lo_out, hi_out, mm_out); else solver_costs(*s->f, lo_out, hi_out, mm_out);
+}
 size_t refcu_nr_bdd_nodes(void* h) { refcu_solver* s = static_cast<refcu_solver*>(h); return s->is_double ? s->d->nr_bdd_nodes() : s->f->nr_bdd_nodes(); }
 
 }
