@@ -27,13 +27,14 @@ def _instances():
     }
 
 
+@pytest.mark.parametrize("init_step_size", [1e-3, 1e-6])       # 1e-6 is the reference's default (include/bdd_solver/lbfgs.h:29-33)
 @pytest.mark.parametrize("name", ["set_cover", "grid_mrf", "qap"])
-def test_lbfgs_matches_numpy_restatement(name):
+def test_lbfgs_matches_numpy_restatement(name, init_step_size):
     from bdd_b200.solver import lbfgs_cuda_mma
     col, costs = _instances()[name]()
     B.oracle_set_num_threads(1)
-    s = lbfgs_cuda_mma(col, costs, precision="double", deterministic=True, init_step_size=1e-3)
-    o = LbfgsOracle(B.Oracle(col.instrs, col.delims, costs, "double"), init_step_size=1e-3)
+    s = lbfgs_cuda_mma(col, costs, precision="double", deterministic=True, init_step_size=init_step_size)
+    o = LbfgsOracle(B.Oracle(col.instrs, col.delims, costs, "double"), init_step_size=init_step_size)
     scale = max(1.0, abs(o.lower_bound()))
     assert abs(s.lower_bound() - o.lower_bound()) <= 1e-9 * scale
     for it in range(30):
