@@ -201,21 +201,20 @@ public:
         need(b);
         bool ascending = true;
         std::vector<size_t> vars;
-        std::vector<std::array<size_t, 2>> arcs;
         for(size_t i = delims[b]; i + 2 < delims[b + 1]; ++i)
         {
             const bddb200_instruction& x = instrs[i];
             for(const size_t child : {x.lo, x.hi})
-                if(!is_terminal(child))
-                {
-                    if(x.index > instrs[child].index) ascending = false;
-                    arcs.push_back({x.index, instrs[child].index});
-                }
+                if(!is_terminal(child) && x.index > instrs[child].index) ascending = false;
             if(vars.empty() || vars.back() != x.index) vars.push_back(x.index);
         }
         std::sort(vars.begin(), vars.end());
         vars.erase(std::unique(vars.begin(), vars.end()), vars.end());
         if(ascending) return vars;
+        std::vector<std::array<size_t, 2>> arcs;
+        for(size_t i = delims[b]; i + 2 < delims[b + 1]; ++i)
+            for(const size_t child : {instrs[i].lo, instrs[i].hi})
+                if(!is_terminal(child)) arcs.push_back({instrs[i].index, instrs[child].index});
         std::sort(arcs.begin(), arcs.end());
         arcs.erase(std::unique(arcs.begin(), arcs.end()), arcs.end());
         std::unordered_map<size_t, size_t> first_arc, pending;
@@ -261,27 +260,23 @@ public:
     // nodes grouped by variable, groups in variable order (:1510-1530)
     bool is_reordered(size_t b) const
     {
-        const std::unordered_map<size_t, size_t> rank = ranks(variables(b));
-        for(size_t i = delims[b]; i + 3 < delims[b + 1]; ++i)
-        {
-            const size_t r0 = rank.at(instrs[i].index), r1 = rank.at(instrs[i + 1].index);
-            if(r1 != r0 && r1 != r0 + 1) return false;
-        }
+        const std::vector<size_t> r = node_ranks(b, variables(b));
+        for(size_t i = 0; i + 1 < r.size(); ++i)
+            if(r[i + 1] != r[i] && r[i + 1] != r[i] + 1) return false;
         return true;
     }
     // every arc ends in the next layer or in the bot sink (:500-505, :1614-1640)
     bool is_qbdd(size_t b) const
     {
         need(b);
-        const std::vector<size_t> vars = variables(b);
-        const std::unordered_map<size_t, size_t> rank = ranks(vars);
-        for(size_t i = delims[b]; i + 2 < delims[b + 1]; ++i)
-            for(const size_t child : {instrs[i].lo, instrs[i].hi})
+        const std::vector<size_t> vars = variables(b), r = node_ranks(b, vars);
+        const size_t first = delims[b], n = r.size();
+        for(size_t i = 0; i < n; ++i)
+            for(const size_t child : {instrs[first + i].lo, instrs[first + i].hi})
             {
-                if(child <= i || child >= delims[b + 1]) return false;
+                if(child <= first + i || child >= delims[b + 1]) return false;
                 if(instrs[child].index == BOTSINK) continue;
-                const size_t r = rank.at(instrs[i].index);
-                if(r + 1 == vars.size() ? instrs[child].index != TOPSINK : (is_terminal(child) || rank.at(instrs[child].index) != r + 1)) return false;
+                if(r[i] + 1 == vars.size() ? instrs[child].index != TOPSINK : (child - first >= n || r[child - first] != r[i] + 1)) return false;
             }
         return true;
     }
@@ -296,13 +291,15 @@ public:
     // stable sort of the nodes by the rank of their variable (:1429-1508); nothing moves when the BDD is layered already
     void reorder(size_t b)
     {
-        if(is_reordered(b)) return;
-        const std::unordered_map<size_t, size_t> rank = ranks(variables(b));
-        const size_t first = delims[b], n = delims[b + 1] - 2 - first;
-        std::vector<size_t> start(rank.size() + 1, 0), where(n + 2);
-        for(size_t i = 0; i < n; ++i) ++start[rank.at(instrs[first + i].index) + 1];
-        for(size_t r = 0; r < rank.size(); ++r) start[r + 1] += start[r];
-        for(size_t i = 0; i < n; ++i) where[i] = start[rank.at(instrs[first + i].index)]++;
+        const std::vector<size_t> vars = variables(b), r = node_ranks(b, vars);
+        bool layered = true;
+        for(size_t i = 0; i + 1 < r.size() && layered; ++i) layered = r[i + 1] == r[i] || r[i + 1] == r[i] + 1;
+        if(layered) return;
+        const size_t first = delims[b], n = r.size();
+        std::vector<size_t> start(vars.size() + 1, 0), where(n + 2);
+        for(size_t i = 0; i < n; ++i) ++start[r[i] + 1];
+        for(size_t l = 0; l < vars.size(); ++l) start[l + 1] += start[l];
+        for(size_t i = 0; i < n; ++i) where[i] = start[r[i]]++;
         where[n] = n; where[n + 1] = n + 1;
         std::vector<bddb200_instruction> sorted(n);
         for(size_t i = 0; i < n; ++i)
@@ -319,14 +316,13 @@ public:
     size_t make_qbdd(size_t b)
     {
         need(b);
-        const std::vector<size_t> vars = variables(b);
-        const std::unordered_map<size_t, size_t> rank = ranks(vars);
+        const std::vector<size_t> vars = variables(b), rank = node_ranks(b, vars);
         const size_t first = delims[b], n = delims[b + 1] - 2 - first, depth = vars.size();
         constexpr size_t TOP = (size_t)-1, BOT = (size_t)-2, NONE = (size_t)-3;
         struct raw { size_t lo, hi, layer; };
         std::vector<raw> nodes(n);
         auto local = [&](size_t child) { return instrs[child].index == TOPSINK ? TOP : (instrs[child].index == BOTSINK ? BOT : child - first); };
-        for(size_t i = 0; i < n; ++i) nodes[i] = {local(instrs[first + i].lo), local(instrs[first + i].hi), rank.at(instrs[first + i].index)};
+        for(size_t i = 0; i < n; ++i) nodes[i] = {local(instrs[first + i].lo), local(instrs[first + i].hi), rank[i]};
         std::unordered_map<std::array<size_t, 2>, size_t, collection_detail::pair_hash> chain;          // (layer, target) -> pass-through node
         auto target_layer = [&](size_t t) { return t == TOP ? depth : nodes[t].layer; };
         auto route = [&](size_t from_layer, size_t t) -> size_t {            // where an arc from from_layer towards t has to land
@@ -479,6 +475,28 @@ private:
         for(size_t i = 0; i < vars.size(); ++i) r.emplace(vars[i], i);
         return r;
     }
+    // per inner node the position of its variable in `vars`: when `vars` ascends (the usual case) the next layer's variable is tried
+    // first and a binary search decides otherwise; a topological order goes through a hash map, one lookup per run of equal variables
+    std::vector<size_t> node_ranks(size_t b, const std::vector<size_t>& vars) const
+    {
+        const size_t first = delims[b], n = delims[b + 1] - 2 - first;
+        std::vector<size_t> r(n);
+        if(std::is_sorted(vars.begin(), vars.end()))
+        {
+            for(size_t i = 0; i < n; ++i)
+            {
+                const size_t var = instrs[first + i].index, prev = i > 0 ? r[i - 1] : 0;
+                if(vars[prev] == var) r[i] = prev;
+                else if(prev + 1 < vars.size() && vars[prev + 1] == var) r[i] = prev + 1;
+                else r[i] = size_t(std::lower_bound(vars.begin(), vars.end(), var) - vars.begin());
+            }
+            return r;
+        }
+        const std::unordered_map<size_t, size_t> rank = ranks(vars);
+        for(size_t i = 0; i < n; ++i)
+            r[i] = i > 0 && instrs[first + i].index == instrs[first + i - 1].index ? r[i - 1] : rank.at(instrs[first + i].index);
+        return r;
+    }
     // BDD b as a function in the store; children sit behind their parents in the array (bdd_basic_check, :951-988)
     size_t load(collection_detail::robdd_store& store, size_t b) const
     {
@@ -584,9 +602,14 @@ inline size_t split_long_bdds(bdd_collection& col, size_t split_length, size_t n
     for(const bddb200_instruction& x : col.instrs) if(x.index < bdd_collection::BOTSINK) aux = std::max(aux, x.index + 1);
     std::vector<size_t> replaced;
     const size_t nr_orig = col.nr_bdds();
+    size_t long_nodes = 0;                             // the chunks repeat the nodes of the BDDs they replace and add the gadgets
+    std::vector<char> is_long(nr_orig, 0);
+    for(size_t b = 0; b < nr_orig; ++b)
+        if(col.layer_offsets(b).size() > split_length) { is_long[b] = 1; long_nodes += col.nr_bdd_nodes(b); }
+    col.instrs.reserve(col.instrs.size() + long_nodes + long_nodes / 2);
     for(size_t b = 0; b < nr_orig; ++b)
     {
-        if(col.layer_offsets(b).size() <= split_length) continue;
+        if(!is_long[b]) continue;
         try
         {
             const auto [new_nrs, next_aux] = col.split_qbdd(b, split_length, aux, with_implication_bdd);

@@ -251,6 +251,19 @@ def test_split_with_implication_bdd_matches_the_reference(chunk):
     assert n_implication > 0 or chunk == 4
 
 
+@needs_ref
+def test_split_with_implication_bdd_matches_the_reference_on_long_bdds():
+    """BASELINE config 3b's shape: simplex rows over 1118 variables cut every 64 (17 cuts per BDD, ~290 constraints in the conjunction)"""
+    col = instances.assignment(1118, seed=3)[0].select([0, 1, 1118, 2235])
+    mine, ref = bdd_collection(col), B.RefCollection.from_arrays(col.instrs, col.delims)
+    aux = aux_ref = 1118 * 1118
+    for b in range(col.nr_bdds):
+        new_nrs, aux = mine.split_qbdd(b, 64, aux, True)
+        n_new, aux_ref = ref.split_qbdd_implication(b, 64, aux_ref)
+        assert aux == aux_ref and len(new_nrs) == n_new == 18 + 1
+    assert_same(mine, ref)
+
+
 @pytest.mark.parametrize("rows, chunk", [
     ([([1] * 6, list(range(6)), 2, 2)], 2),                             # exactly 2 of 6: three chunks
     ([([1] * 8, list(range(8)), 2, 1)], 2),                             # a simplex over 8: four chunks, three cuts
