@@ -37,7 +37,7 @@ SYMBOLS = [
 COLLECTION_SYMBOLS = [
     "bddb200_collection_create", "bddb200_collection_destroy", "bddb200_collection_nr_bdds", "bddb200_collection_nr_instructions", "bddb200_collection_export",
     "bddb200_collection_simplex_constraint", "bddb200_collection_not_all_false_constraint", "bddb200_collection_all_equal_constraint",
-    "bddb200_collection_cardinality_constraint", "bddb200_collection_rebase", "bddb200_collection_negate", "bddb200_collection_invert",
+    "bddb200_collection_cardinality_constraint", "bddb200_collection_add_linear_constraint", "bddb200_collection_rebase", "bddb200_collection_negate", "bddb200_collection_invert",
     "bddb200_collection_variables", "bddb200_collection_is_qbdd", "bddb200_collection_is_reordered", "bddb200_collection_evaluate",
     "bddb200_collection_reorder", "bddb200_collection_make_qbdd", "bddb200_collection_bdd_and", "bddb200_collection_remove",
     "bddb200_collection_split_qbdd", "bddb200_collection_split_long_bdds",
@@ -160,6 +160,7 @@ def load() -> C.CDLL:
         "bddb200_collection_not_all_false_constraint": (i, [vp, sz, C.POINTER(sz)]),
         "bddb200_collection_all_equal_constraint": (i, [vp, sz, C.POINTER(sz)]),
         "bddb200_collection_cardinality_constraint": (i, [vp, sz, sz, C.POINTER(sz)]),
+        "bddb200_collection_add_linear_constraint": (i, [vp, vp, vp, sz, i, C.c_longlong, C.POINTER(sz)]),
         "bddb200_collection_rebase": (i, [vp, sz, vp, sz]),
         "bddb200_collection_negate": (i, [vp, sz]),
         "bddb200_collection_invert": (i, [vp, sz, sz]),

@@ -66,6 +66,16 @@ class bdd_collection:
     def cardinality_constraint(self, n: int, k: int) -> int:
         return self._size(self._lib.bddb200_collection_cardinality_constraint, n, k)
 
+    def add_linear_constraint(self, coefficients: Sequence[int], variables: Sequence[int], ineq: int, rhs: int) -> Optional[int]:
+        """The quasi-reduced BDD of ``sum coefficients[k] * x[variables[k]]  {0 '<=', 1 '>=', 2 '='}  rhs`` (variables ascending), built
+        directly (bdd_preprocessor.cpp:175-228 without the BDD manager).  ``None`` when the constraint is always satisfied."""
+        co = np.ascontiguousarray(coefficients, dtype=np.int64)
+        va = np.ascontiguousarray(variables, dtype=np.uint64)
+        if co.shape != va.shape:
+            raise ValueError("one coefficient per variable")
+        nr = self._size(self._lib.bddb200_collection_add_linear_constraint, co.ctypes.data, va.ctypes.data, co.shape[0], int(ineq), int(rhs))
+        return None if nr == 2 ** 64 - 1 else nr
+
     # ------------------------------------------------------------------ relabelling
     def rebase(self, bdd_nr: int, variables: Sequence[int]) -> None:
         v = np.ascontiguousarray(variables, dtype=np.uint64)

@@ -27,6 +27,8 @@
 #include <cstdint>
 #include <deque>
 #include <limits>
+#include <map>
+#include <set>
 #include <stdexcept>
 #include <string>
 #include <tuple>
@@ -83,6 +85,82 @@ private:
 };
 
 } // namespace collection_detail
+
+// ---------------------------------------------------------------------------------------------------------------- QBDD builder
+// The quasi-reduced BDD of one linear constraint  sum_k a_k x_k  {<=, >=, =}  rhs  over 0/1 variables, built directly: states are the
+// reachable partial sums, equal sub-functions are merged bottom-up, layers the function does not depend on are spliced out.  It is the
+// canonical form the reference reaches through lineq_bdd -> bdd_mgr -> add_bdd -> reorder -> make_qbdd (bdd_preprocessor.cpp:175-228)
+// up to the order of the nodes inside a layer (tests/test_host.py, tests/test_collection.py against the reference's converter).
+enum Ineq { LE = 0, GE = 1, EQ = 2 };
+
+// One BDD with local numbering: node i branches on position layer[i] of the constraint's variable list; children are local node ids,
+// -1 = bot sink, -2 = top sink; nodes are ordered layer by layer.
+struct QbddTemplate {
+    bool trivial = false;              // the constraint is always satisfied: no BDD
+    std::vector<long long> layer, lo, hi;
+};
+
+inline QbddTemplate qbdd_template(const std::vector<long long>& a, int ineq, long long rhs)
+{
+    const size_t n = a.size();
+    if(n == 0) throw std::runtime_error("empty constraint");
+    constexpr long long BOT = -1, TOP = -2;
+    std::vector<std::vector<long long>> sums(n + 1);
+    sums[0] = {0};
+    for(size_t k = 0; k < n; ++k)
+    {
+        std::set<long long> nxt;
+        for(long long s : sums[k]) { nxt.insert(s); nxt.insert(s + a[k]); }
+        sums[k + 1].assign(nxt.begin(), nxt.end());
+    }
+    auto accept = [&](long long s) { return ineq == LE ? s <= rhs : (ineq == GE ? s >= rhs : s == rhs); };
+    std::vector<std::map<long long, long long>> ident(n + 1);         // sub-function id of every state, bottom-up
+    for(long long s : sums[n]) ident[n][s] = accept(s) ? TOP : BOT;
+    std::vector<std::vector<std::pair<long long, long long>>> nodes(n);
+    for(size_t kk = n; kk-- > 0;)
+    {
+        std::map<std::pair<long long, long long>, long long> table;
+        for(long long s : sums[kk])
+        {
+            const std::pair<long long, long long> key(ident[kk + 1][s], ident[kk + 1][s + a[kk]]);
+            if(key.first == BOT && key.second == BOT) { ident[kk][s] = BOT; continue; }
+            auto it = table.find(key);
+            if(it == table.end()) { it = table.emplace(key, (long long)nodes[kk].size()).first; nodes[kk].push_back(key); }
+            ident[kk][s] = it->second;
+        }
+    }
+    if(ident[0][0] == BOT) throw std::runtime_error("problem is infeasible");
+    QbddTemplate t;
+    bool any_bot = false;
+    for(const auto& nl : nodes) for(const auto& key : nl) any_bot = any_bot || key.first == BOT || key.second == BOT;
+    if(!any_bot) { t.trivial = true; return t; }
+    // a variable the function does not depend on (every node of its layer has lo == hi) gets no layer: splice such layers out
+    std::vector<char> keep(n);
+    for(size_t k = 0; k < n; ++k) { keep[k] = 0; for(const auto& key : nodes[k]) if(key.first != key.second) keep[k] = 1; }
+    std::vector<long long> offset(n, 0);
+    long long off = 0;
+    for(size_t k = 0; k < n; ++k) if(keep[k]) { offset[k] = off; off += (long long)nodes[k].size(); }
+    auto stands_for = [&](size_t k, long long i) -> long long {      // global id of the first kept node reached, or a terminal code
+        while(true)
+        {
+            if(i < 0) return i;
+            if(keep[k]) return offset[k] + i;
+            i = nodes[k][(size_t)i].first;
+            ++k;
+        }
+    };
+    for(size_t k = 0; k < n; ++k)
+    {
+        if(!keep[k]) continue;
+        for(const auto& key : nodes[k])
+        {
+            t.layer.push_back((long long)k);
+            t.lo.push_back(key.first >= 0 ? stands_for(k + 1, key.first) : key.first);
+            t.hi.push_back(key.second >= 0 ? stands_for(k + 1, key.second) : key.second);
+        }
+    }
+    return t;
+}
 
 class bdd_collection {
 public:
@@ -161,6 +239,26 @@ public:
         instrs.push_back(botsink());
         delims.push_back(instrs.size());
         return nr_bdds() - 1;
+    }
+
+    // the BDD of a template over the given variables (position k of the constraint -> variables[k]); SIZE_MAX when the constraint is
+    // always satisfied and no BDD is added (bdd_preprocessor.cpp:183-184)
+    size_t add_bdd(const QbddTemplate& t, const std::vector<size_t>& variables)
+    {
+        if(t.trivial) return std::numeric_limits<size_t>::max();
+        const size_t first = instrs.size(), nn = t.layer.size();
+        auto child = [&](long long x) -> size_t { return x == -1 ? first + nn : (x == -2 ? first + nn + 1 : first + (size_t)x); };
+        for(size_t i = 0; i < nn; ++i) instrs.push_back({child(t.lo[i]), child(t.hi[i]), variables.at((size_t)t.layer[i])});
+        return close(first + nn, first + nn + 1);
+    }
+    // one linear constraint over 0/1 variables (ascending variable indices, as the reference's converter expects them)
+    size_t add_linear_constraint(const std::vector<long long>& coefficients, const std::vector<size_t>& variables, int ineq, long long rhs)
+    {
+        if(coefficients.size() != variables.size()) throw std::invalid_argument("add_linear_constraint: one coefficient per variable");
+        if(ineq != LE && ineq != GE && ineq != EQ) throw std::invalid_argument("add_linear_constraint: relation must be 0 (<=), 1 (>=) or 2 (=)");
+        for(size_t k = 0; k + 1 < variables.size(); ++k)
+            if(!(variables[k] < variables[k + 1])) throw std::invalid_argument("add_linear_constraint: variables must ascend");
+        return add_bdd(qbdd_template(coefficients, ineq, rhs), variables);
     }
 
     // ---------------------------------------------------------------------------------------- relabelling

@@ -38,7 +38,7 @@
 
 namespace bddb200_host {
 
-enum Ineq { LE = 0, GE = 1, EQ = 2 };
+// relations LE / GE / EQ: host/bdd_collection.hpp
 
 struct Constraint {
     std::string identifier;
@@ -233,76 +233,6 @@ inline ILP parse_lp(const std::string& text)
     return ilp;
 }
 
-// ---------------------------------------------------------------------------------------------------------------- QBDD builder
-// One BDD with local numbering: node i branches on position layer[i] of the constraint's variable list; children are local node ids,
-// -1 = bot sink, -2 = top sink; nodes are ordered layer by layer.
-struct QbddTemplate {
-    bool trivial = false;              // the constraint is always satisfied: no BDD
-    std::vector<long long> layer, lo, hi;
-};
-
-inline QbddTemplate qbdd_template(const std::vector<long long>& a, int ineq, long long rhs)
-{
-    const size_t n = a.size();
-    if(n == 0) throw std::runtime_error("empty constraint");
-    constexpr long long BOT = -1, TOP = -2;
-    std::vector<std::vector<long long>> sums(n + 1);
-    sums[0] = {0};
-    for(size_t k = 0; k < n; ++k)
-    {
-        std::set<long long> nxt;
-        for(long long s : sums[k]) { nxt.insert(s); nxt.insert(s + a[k]); }
-        sums[k + 1].assign(nxt.begin(), nxt.end());
-    }
-    auto accept = [&](long long s) { return ineq == LE ? s <= rhs : (ineq == GE ? s >= rhs : s == rhs); };
-    std::vector<std::map<long long, long long>> ident(n + 1);         // sub-function id of every state, bottom-up
-    for(long long s : sums[n]) ident[n][s] = accept(s) ? TOP : BOT;
-    std::vector<std::vector<std::pair<long long, long long>>> nodes(n);
-    for(size_t kk = n; kk-- > 0;)
-    {
-        std::map<std::pair<long long, long long>, long long> table;
-        for(long long s : sums[kk])
-        {
-            const std::pair<long long, long long> key(ident[kk + 1][s], ident[kk + 1][s + a[kk]]);
-            if(key.first == BOT && key.second == BOT) { ident[kk][s] = BOT; continue; }
-            auto it = table.find(key);
-            if(it == table.end()) { it = table.emplace(key, (long long)nodes[kk].size()).first; nodes[kk].push_back(key); }
-            ident[kk][s] = it->second;
-        }
-    }
-    if(ident[0][0] == BOT) throw std::runtime_error("problem is infeasible");
-    QbddTemplate t;
-    bool any_bot = false;
-    for(const auto& nl : nodes) for(const auto& key : nl) any_bot = any_bot || key.first == BOT || key.second == BOT;
-    if(!any_bot) { t.trivial = true; return t; }
-    // a variable the function does not depend on (every node of its layer has lo == hi) gets no layer: splice such layers out
-    std::vector<char> keep(n);
-    for(size_t k = 0; k < n; ++k) { keep[k] = 0; for(const auto& key : nodes[k]) if(key.first != key.second) keep[k] = 1; }
-    std::vector<long long> offset(n, 0);
-    long long off = 0;
-    for(size_t k = 0; k < n; ++k) if(keep[k]) { offset[k] = off; off += (long long)nodes[k].size(); }
-    auto stands_for = [&](size_t k, long long i) -> long long {      // global id of the first kept node reached, or a terminal code
-        while(true)
-        {
-            if(i < 0) return i;
-            if(keep[k]) return offset[k] + i;
-            i = nodes[k][(size_t)i].first;
-            ++k;
-        }
-    };
-    for(size_t k = 0; k < n; ++k)
-    {
-        if(!keep[k]) continue;
-        for(const auto& key : nodes[k])
-        {
-            t.layer.push_back((long long)k);
-            t.lo.push_back(key.first >= 0 ? stands_for(k + 1, key.first) : key.first);
-            t.hi.push_back(key.second >= 0 ? stands_for(k + 1, key.second) : key.second);
-        }
-    }
-    return t;
-}
-
 using BddCollection = bdd_collection;       // host/bdd_collection.hpp: instruction array + delimiters, generators, splitting
 
 // One BDD per constraint, in constraint order (bdd_preprocessor::add_ilp, bdd_preprocessor.cpp:123-228); templates are cached per
@@ -311,20 +241,12 @@ inline BddCollection bdds_from_ilp(const ILP& ilp)
 {
     BddCollection col;
     std::map<std::tuple<std::vector<long long>, int, long long>, QbddTemplate> cache;
-    constexpr size_t TOPSINK = (size_t)-1, BOTSINK = (size_t)-2;
     for(const Constraint& c : ilp.constraints)
     {
         const auto key = std::make_tuple(c.coefficients, c.ineq, c.rhs);
         auto it = cache.find(key);
         if(it == cache.end()) it = cache.emplace(key, qbdd_template(c.coefficients, c.ineq, c.rhs)).first;
-        const QbddTemplate& t = it->second;
-        if(t.trivial) continue;
-        const size_t first = col.instrs.size(), nn = t.layer.size();
-        auto child = [&](long long x) -> size_t { return x == -1 ? first + nn : (x == -2 ? first + nn + 1 : first + (size_t)x); };
-        for(size_t i = 0; i < nn; ++i) col.instrs.push_back(bddb200_instruction{child(t.lo[i]), child(t.hi[i]), c.variables[(size_t)t.layer[i]]});
-        col.instrs.push_back(bddb200_instruction{BOTSINK, BOTSINK, BOTSINK});
-        col.instrs.push_back(bddb200_instruction{TOPSINK, TOPSINK, TOPSINK});
-        col.delims.push_back(col.instrs.size());
+        col.add_bdd(it->second, c.variables);
     }
     return col;
 }

@@ -59,6 +59,15 @@ int bddb200_collection_all_equal_constraint(bddb200_collection* c, size_t n, siz
 int bddb200_collection_cardinality_constraint(bddb200_collection* c, size_t n, size_t k, size_t* bdd_nr_out)
 { REQUIRE_COLLECTION(c); REQUIRE_OUT(bdd_nr_out); return guarded([&] { *bdd_nr_out = c->col.cardinality_constraint(n, k); }); }
 
+int bddb200_collection_add_linear_constraint(bddb200_collection* c, const long long* coefficients, const size_t* variables, size_t n,
+                                             int relation, long long rhs, size_t* bdd_nr_out)
+{
+    REQUIRE_COLLECTION(c); REQUIRE_OUT(coefficients); REQUIRE_OUT(variables); REQUIRE_OUT(bdd_nr_out);
+    return guarded([&] {
+        *bdd_nr_out = c->col.add_linear_constraint(std::vector<long long>(coefficients, coefficients + n), std::vector<size_t>(variables, variables + n), relation, rhs);
+    });
+}
+
 int bddb200_collection_rebase(bddb200_collection* c, size_t bdd_nr, const size_t* vars, size_t n_vars)
 { REQUIRE_COLLECTION(c); REQUIRE_OUT(vars); return guarded([&] { c->col.rebase(bdd_nr, vars, vars + n_vars); }); }
 int bddb200_collection_negate(bddb200_collection* c, size_t bdd_nr) { REQUIRE_COLLECTION(c); return guarded([&] { c->col.negate(bdd_nr); }); }

@@ -35,6 +35,12 @@ int bddb200_collection_not_all_false_constraint(bddb200_collection* c, size_t n,
 int bddb200_collection_all_equal_constraint(bddb200_collection* c, size_t n, size_t* bdd_nr_out);            /* :2136 (reduced, not quasi-reduced) */
 int bddb200_collection_cardinality_constraint(bddb200_collection* c, size_t n, size_t k, size_t* bdd_nr_out);/* :2187 */
 
+/* one linear constraint sum_k coefficients[k] * x[variables[k]] {0 '<=', 1 '>=', 2 '='} rhs over 0/1 variables (ascending), converted
+ * directly to its quasi-reduced BDD: what bdd_preprocessor.cpp:175-228 reaches through lineq_bdd -> bdd_mgr -> add_bdd -> reorder ->
+ * make_qbdd -> rebase, up to the node order inside a layer.  *bdd_nr_out = SIZE_MAX when the constraint is always satisfied (no BDD). */
+int bddb200_collection_add_linear_constraint(bddb200_collection* c, const long long* coefficients, const size_t* variables, size_t n,
+                                             int relation, long long rhs, size_t* bdd_nr_out);
+
 int bddb200_collection_rebase(bddb200_collection* c, size_t bdd_nr, const size_t* vars, size_t n_vars);     /* variable i -> vars[i], header :311 */
 int bddb200_collection_negate(bddb200_collection* c, size_t bdd_nr);                                         /* :2023 */
 int bddb200_collection_invert(bddb200_collection* c, size_t bdd_nr, size_t var);                             /* :2029 */

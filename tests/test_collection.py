@@ -73,6 +73,47 @@ def test_generator_arguments_are_checked():
     assert col.nr_bdds() == 0
 
 
+@needs_ref
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_add_linear_constraint_builds_the_bdd_of_the_reference_converter(seed):
+    """the direct builder against the reference's lineq_bdd -> bdd_mgr -> add_bdd -> reorder -> make_qbdd -> rebase chain
+    (bdd_preprocessor.cpp:175-228): same BDDs emitted or skipped, same layers, same widths, same function; node order inside a layer
+    is the one thing the BDD manager decides differently.  And bit for bit against the Python builder (bdd_b200/instances.py)."""
+    rng = np.random.default_rng(seed)
+    mine, ref, rows = bdd_collection(), B.RefCollection(), []
+    for _ in range(40):
+        n = int(rng.integers(1, 11))
+        variables = sorted(rng.choice(30, size=n, replace=False).tolist())
+        coeffs = [int(c) for c in rng.integers(-4, 6, size=n) if True]
+        coeffs = [c if c != 0 else 1 for c in coeffs]
+        ineq = int(rng.integers(0, 3))
+        lo, hi = sum(c for c in coeffs if c < 0), sum(c for c in coeffs if c > 0)
+        rhs = int(rng.integers(lo, hi + 1))
+        try:
+            want = ref.add_constraint(coeffs, variables, ineq, rhs)
+        except RuntimeError:
+            with pytest.raises(Exception):
+                mine.add_linear_constraint(coeffs, variables, ineq, rhs)
+            continue
+        got = mine.add_linear_constraint(coeffs, variables, ineq, rhs)
+        assert (got is None) == (want == -1), (coeffs, variables, ineq, rhs)
+        if got is not None:
+            assert got == want
+            rows.append((coeffs, variables, ineq, rhs))
+    m = mine.export()
+    r_instrs, r_delims = ref.export()
+    sinks_alike = lambda idx: np.where(idx >= instances.BOTSINK, instances.TOPSINK, idx)       # the reference's add_bdd / make_qbdd put the top sink first
+    assert m.nr_bdds > 10 and np.array_equal(m.delims, r_delims) and np.array_equal(sinks_alike(m.instrs[:, 2]), sinks_alike(r_instrs[:, 2]))
+    r = BddCollection(r_instrs, r_delims)
+    for _ in range(200):
+        x = rng.integers(0, 2, size=30)
+        assert np.array_equal(bdds_accept(m, x), bdds_accept(r, x))
+        assert np.array_equal(bdds_accept(m, x), [(sum(c * x[v] for c, v in zip(co, va)) <= rhs) if i == 0 else (sum(c * x[v] for c, v in zip(co, va)) >= rhs) if i == 1
+                                                  else (sum(c * x[v] for c, v in zip(co, va)) == rhs) for co, va, i, rhs in rows])
+    py = from_rows(rows)
+    assert np.array_equal(py.delims, m.delims) and np.array_equal(py.instrs, m.instrs)
+
+
 # ------------------------------------------------------------------------------------------------ relabelling, reorder, make_qbdd, remove
 @needs_ref
 def test_rebase_negate_invert_remove_match_the_reference():
