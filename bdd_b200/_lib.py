@@ -41,6 +41,8 @@ COLLECTION_SYMBOLS = [
     "bddb200_collection_variables", "bddb200_collection_is_qbdd", "bddb200_collection_is_reordered", "bddb200_collection_evaluate",
     "bddb200_collection_reorder", "bddb200_collection_make_qbdd", "bddb200_collection_bdd_and", "bddb200_collection_remove",
     "bddb200_collection_split_qbdd", "bddb200_collection_split_long_bdds",
+    "bddb200_ilp_read", "bddb200_ilp_destroy", "bddb200_ilp_nr_variables", "bddb200_ilp_nr_constraints", "bddb200_ilp_objective",
+    "bddb200_ilp_variable_name", "bddb200_ilp_constraint", "bddb200_ilp_to_bdds",
 ]
 
 
@@ -174,6 +176,14 @@ def load() -> C.CDLL:
         "bddb200_collection_remove": (i, [vp, vp, sz]),
         "bddb200_collection_split_qbdd": (i, [vp, sz, sz, sz, i, C.POINTER(sz), C.POINTER(sz)]),
         "bddb200_collection_split_long_bdds": (i, [vp, sz, sz, i, C.POINTER(sz), C.POINTER(sz)]),
+        "bddb200_ilp_read": (i, [C.c_char_p, C.POINTER(vp)]),
+        "bddb200_ilp_destroy": (i, [vp]),
+        "bddb200_ilp_nr_variables": (i, [vp, C.POINTER(sz)]),
+        "bddb200_ilp_nr_constraints": (i, [vp, C.POINTER(sz)]),
+        "bddb200_ilp_objective": (i, [vp, vp, C.POINTER(dbl)]),
+        "bddb200_ilp_variable_name": (i, [vp, sz, C.POINTER(C.c_char_p)]),
+        "bddb200_ilp_constraint": (i, [vp, sz, C.POINTER(sz), vp, vp, sz, C.POINTER(i), C.POINTER(C.c_longlong)]),
+        "bddb200_ilp_to_bdds": (i, [vp, C.POINTER(vp)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(lib, name)

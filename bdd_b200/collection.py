@@ -19,10 +19,12 @@ from .instances import BddCollection
 
 
 class bdd_collection:
-    def __init__(self, col: Optional[BddCollection] = None):
+    def __init__(self, col: Optional[BddCollection] = None, _handle: Optional[C.c_void_p] = None):
         self._lib = _lib.load()
         self._h = C.c_void_p()
-        if col is None:
+        if _handle is not None:
+            self._h = _handle
+        elif col is None:
             _lib.check(self._lib.bddb200_collection_create(None, 0, None, 0, C.byref(self._h)))
         else:
             instrs = np.ascontiguousarray(col.instrs, dtype=np.uint64)
@@ -138,3 +140,59 @@ class bdd_collection:
         n_split, n_vars = C.c_size_t(), C.c_size_t()
         _lib.check(self._lib.bddb200_collection_split_long_bdds(self._h, split_length, nr_variables, int(with_implication_bdd), C.byref(n_split), C.byref(n_vars)))
         return n_split.value, n_vars.value
+
+
+class ilp_input:
+    """The library's .lp reader (bdd_b200/csrc/host/lp_reader.hpp behind ``bddb200_ilp_*``): ``ILP_input`` as far as the drivers need
+    it (src/ILP/ILP_parser.cpp:25-160; ``bdd_solver::read_ILP``, src/bdd_solver/bdd_solver.cpp:44-66).  ``file_or_text`` is the name of a
+    readable ``.lp`` file, else the LP text itself."""
+
+    def __init__(self, file_or_text: str):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        _lib.check(self._lib.bddb200_ilp_read(file_or_text.encode(), C.byref(self._h)))
+
+    def __del__(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.bddb200_ilp_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def _size(self, f) -> int:
+        out = C.c_size_t()
+        _lib.check(f(self._h, C.byref(out)))
+        return out.value
+
+    def nr_variables(self) -> int:
+        return self._size(self._lib.bddb200_ilp_nr_variables)
+
+    def nr_constraints(self) -> int:
+        return self._size(self._lib.bddb200_ilp_nr_constraints)
+
+    def objective(self) -> Tuple[np.ndarray, float]:
+        """(coefficient of every variable, constant term)"""
+        out = np.empty(self.nr_variables(), dtype=np.float64)
+        const = C.c_double()
+        _lib.check(self._lib.bddb200_ilp_objective(self._h, out.ctypes.data, C.byref(const)))
+        return out, const.value
+
+    def variable_names(self) -> List[str]:
+        names = []
+        for v in range(self.nr_variables()):
+            p = C.c_char_p()
+            _lib.check(self._lib.bddb200_ilp_variable_name(self._h, v, C.byref(p)))
+            names.append(p.value.decode())
+        return names
+
+    def constraint(self, c: int) -> Tuple[List[int], List[int], int, int]:
+        """(variables, coefficients, relation 0 '<=' / 1 '>=' / 2 '=', right-hand side)"""
+        n, rel, rhs = C.c_size_t(), C.c_int(), C.c_longlong()
+        _lib.check(self._lib.bddb200_ilp_constraint(self._h, c, C.byref(n), None, None, 0, None, None))
+        va, co = np.empty(n.value, dtype=np.uint64), np.empty(n.value, dtype=np.int64)
+        _lib.check(self._lib.bddb200_ilp_constraint(self._h, c, C.byref(n), va.ctypes.data, co.ctypes.data, n.value, C.byref(rel), C.byref(rhs)))
+        return va.astype(np.int64).tolist(), co.tolist(), rel.value, rhs.value
+
+    def to_bdds(self) -> bdd_collection:
+        """One quasi-reduced BDD per constraint that is not always satisfied (bdd_preprocessor.cpp:123-228)."""
+        h = C.c_void_p()
+        _lib.check(self._lib.bddb200_ilp_to_bdds(self._h, C.byref(h)))
+        return bdd_collection(_handle=h)

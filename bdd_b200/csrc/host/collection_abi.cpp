@@ -9,8 +9,10 @@
 #include "../../../include/bdd_b200_collection.h"
 #include "../last_error.hpp"
 #include "bdd_collection.hpp"
+#include "lp_reader.hpp"
 
 struct bddb200_collection { bddb200_host::bdd_collection col; };
+struct bddb200_ilp { bddb200_host::ILP ilp; };
 
 namespace {
 template<typename F>
@@ -114,6 +116,59 @@ int bddb200_collection_split_long_bdds(bddb200_collection* c, size_t split_lengt
 {
     REQUIRE_COLLECTION(c); REQUIRE_OUT(nr_variables_out);
     return guarded([&] { *nr_variables_out = bddb200_host::split_long_bdds(c->col, split_length, nr_variables, with_implication_bdd != 0, n_split_out); });
+}
+
+// ---- ILP input ----
+#define REQUIRE_ILP(p) if((p) == nullptr) return fail("null ILP handle");
+
+int bddb200_ilp_read(const char* file_or_text, bddb200_ilp** out)
+{
+    REQUIRE_OUT(out); *out = nullptr; REQUIRE_OUT(file_or_text);
+    return guarded([&] {
+        std::unique_ptr<bddb200_ilp> p(new bddb200_ilp());
+        p->ilp = bddb200_host::read_ilp(file_or_text);
+        *out = p.release();
+    });
+}
+int bddb200_ilp_destroy(bddb200_ilp* ilp) { delete ilp; return BDDB200_OK; }
+int bddb200_ilp_nr_variables(const bddb200_ilp* ilp, size_t* out) { REQUIRE_ILP(ilp); REQUIRE_OUT(out); *out = ilp->ilp.nr_variables(); return BDDB200_OK; }
+int bddb200_ilp_nr_constraints(const bddb200_ilp* ilp, size_t* out) { REQUIRE_ILP(ilp); REQUIRE_OUT(out); *out = ilp->ilp.constraints.size(); return BDDB200_OK; }
+int bddb200_ilp_objective(const bddb200_ilp* ilp, double* coefficients_out, double* constant_out)
+{
+    REQUIRE_ILP(ilp);
+    if(coefficients_out != nullptr) std::copy(ilp->ilp.objective.begin(), ilp->ilp.objective.end(), coefficients_out);
+    if(constant_out != nullptr) *constant_out = ilp->ilp.constant;
+    return BDDB200_OK;
+}
+int bddb200_ilp_variable_name(const bddb200_ilp* ilp, size_t var, const char** name_out)
+{
+    REQUIRE_ILP(ilp); REQUIRE_OUT(name_out);
+    if(var >= ilp->ilp.nr_variables()) return fail("no such variable");
+    *name_out = ilp->ilp.var_names[var].c_str();
+    return BDDB200_OK;
+}
+int bddb200_ilp_constraint(const bddb200_ilp* ilp, size_t c, size_t* n_out, size_t* variables_out, long long* coefficients_out, size_t capacity,
+                           int* relation_out, long long* rhs_out)
+{
+    REQUIRE_ILP(ilp); REQUIRE_OUT(n_out);
+    if(c >= ilp->ilp.constraints.size()) return fail("no such constraint");
+    const bddb200_host::Constraint& k = ilp->ilp.constraints[c];
+    *n_out = k.variables.size();
+    const size_t n = std::min(capacity, k.variables.size());
+    if(variables_out != nullptr) std::copy(k.variables.begin(), k.variables.begin() + n, variables_out);
+    if(coefficients_out != nullptr) std::copy(k.coefficients.begin(), k.coefficients.begin() + n, coefficients_out);
+    if(relation_out != nullptr) *relation_out = k.ineq;
+    if(rhs_out != nullptr) *rhs_out = k.rhs;
+    return BDDB200_OK;
+}
+int bddb200_ilp_to_bdds(const bddb200_ilp* ilp, bddb200_collection** out)
+{
+    REQUIRE_ILP(ilp); REQUIRE_OUT(out); *out = nullptr;
+    return guarded([&] {
+        std::unique_ptr<bddb200_collection> c(new bddb200_collection());
+        c->col = bddb200_host::bdds_from_ilp(ilp->ilp);
+        *out = c.release();
+    });
 }
 
 } // extern "C"

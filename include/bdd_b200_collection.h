@@ -64,6 +64,25 @@ int bddb200_collection_split_qbdd(bddb200_collection* c, size_t bdd_nr, size_t c
 int bddb200_collection_split_long_bdds(bddb200_collection* c, size_t split_length, size_t nr_variables, int with_implication_bdd,
                                        size_t* n_split_out, size_t* nr_variables_out);
 
+/* ---- ILP input: the .lp reader in front of the collection (src/ILP/ILP_parser.cpp:25-160, ILP_input; bdd_solver::read_ILP,
+ * src/bdd_solver/bdd_solver.cpp:44-66).  Minimisation over 0/1 variables, linear constraints with integer coefficients. ---- */
+typedef struct bddb200_ilp bddb200_ilp;
+
+/* file_or_text: the name of a readable .lp file, else the LP text itself (as "input" of the JSON configuration) */
+int bddb200_ilp_read(const char* file_or_text, bddb200_ilp** out);
+int bddb200_ilp_destroy(bddb200_ilp* ilp);
+int bddb200_ilp_nr_variables(const bddb200_ilp* ilp, size_t* out);
+int bddb200_ilp_nr_constraints(const bddb200_ilp* ilp, size_t* out);
+int bddb200_ilp_objective(const bddb200_ilp* ilp, double* coefficients_out, double* constant_out);   /* nr_variables doubles; either may be NULL */
+int bddb200_ilp_variable_name(const bddb200_ilp* ilp, size_t var, const char** name_out);            /* valid until the ILP is destroyed */
+/* constraint c: *n_out terms; with non-NULL outputs (capacity >= *n_out of a first call) its variables, coefficients, relation
+ * (0 '<=', 1 '>=', 2 '=') and right-hand side */
+int bddb200_ilp_constraint(const bddb200_ilp* ilp, size_t c, size_t* n_out, size_t* variables_out, long long* coefficients_out, size_t capacity,
+                           int* relation_out, long long* rhs_out);
+/* one quasi-reduced BDD per constraint that is not always satisfied, in constraint order (bdd_preprocessor::add_ilp,
+ * bdd_preprocessor.cpp:123-228); an infeasible constraint is an error */
+int bddb200_ilp_to_bdds(const bddb200_ilp* ilp, bddb200_collection** out);
+
 #ifdef __cplusplus
 }
 #endif

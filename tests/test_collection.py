@@ -3,11 +3,13 @@ reference's own BDD::bdd_collection compiled into oracle/_ref: direct generators
 split_qbdd with the implication BDD -- instruction arrays bit for bit -- and against the meaning of each operation by enumeration.
 CPU only."""
 import itertools
+import os
 
 import numpy as np
 import pytest
 
 import bindings as B
+from conftest import GOLDEN, golden_names
 from bdd_b200 import instances
 from bdd_b200.collection import bdd_collection
 from bdd_b200.instances import BddCollection, bdds_accept
@@ -112,6 +114,36 @@ def test_add_linear_constraint_builds_the_bdd_of_the_reference_converter(seed):
                                                   else (sum(c * x[v] for c, v in zip(co, va)) == rhs) for co, va, i, rhs in rows])
     py = from_rows(rows)
     assert np.array_equal(py.delims, m.delims) and np.array_equal(py.instrs, m.instrs)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_library_lp_reader_and_builder_equal_the_python_ones(name):
+    """bddb200_ilp_* (the C++ reader behind the C ABI) on every fixture, from the file and from its text: variables, objective, every
+    constraint and the BDD collection equal those of bdd_b200/lp.py + instances.py, which tests/test_host.py pins against the
+    reference's own converter"""
+    from bdd_b200 import lp
+    from bdd_b200.collection import ilp_input
+    path = os.path.join(GOLDEN, name + ".lp")
+    want = lp.parse_lp(open(path).read())
+    col, costs = instances.from_ilp(want)
+    for source in (path, open(path).read()):
+        got = ilp_input(source)
+        assert got.nr_variables() == len(want.var_names) and got.variable_names() == want.var_names
+        obj, const = got.objective()
+        assert np.array_equal(obj, costs) and const == want.constant
+        assert got.nr_constraints() == len(want.constraints)
+        for c, k in enumerate(want.constraints):
+            assert got.constraint(c) == (list(k.variables), list(k.coefficients), k.ineq, k.rhs)
+        flat = got.to_bdds().export()
+        assert np.array_equal(flat.delims, col.delims) and np.array_equal(flat.instrs, col.instrs)
+
+
+def test_library_lp_reader_rejects_what_it_cannot_read():
+    from bdd_b200._lib import BddB200Error
+    from bdd_b200.collection import ilp_input
+    for text in ("Minimize\n x +\nSubject To\n x + y >= \nEnd\n", "Subject To\n c: x + y = 1\nEnd\n", "Minimize\n x\nSubject To\n x + y >= 3\nEnd\n"):
+        with pytest.raises(BddB200Error):
+            ilp_input(text).to_bdds()
 
 
 # ------------------------------------------------------------------------------------------------ relabelling, reorder, make_qbdd, remove
