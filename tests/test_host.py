@@ -24,6 +24,35 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in lib.bddb200_version()
 
 
+def test_public_headers_are_plain_c(tmp_path):
+    """the drop-in boundary is a C ABI: both headers compile as C99 with nothing but the standard library, and a C program links every
+    host-side entry point it needs to go from an .lp text to a split BDD collection (no GPU involved)"""
+    import subprocess
+    src = tmp_path / "use.c"
+    src.write_text('''#include <stdio.h>
+#include "bdd_b200_collection.h"
+int main(void)
+{
+    bddb200_ilp* ilp; bddb200_collection* col; size_t n_bdds, n_vars, n_split, n_all;
+    if(bddb200_ilp_read("Minimize\\n x1 + 2 x2 + x3 + x4 + 3 x5\\nSubject To\\n x1 + x2 + x3 + x4 + x5 = 2\\n x1 + x5 <= 1\\nEnd\\n", &ilp)) { puts(bddb200_last_error()); return 1; }
+    if(bddb200_ilp_to_bdds(ilp, &col) || bddb200_ilp_nr_variables(ilp, &n_vars)) { puts(bddb200_last_error()); return 1; }
+    if(bddb200_collection_split_long_bdds(col, 2, n_vars, 1, &n_split, &n_all) || bddb200_collection_nr_bdds(col, &n_bdds)) { puts(bddb200_last_error()); return 1; }
+    printf("%zu %zu %zu %zu\\n", n_vars, n_split, n_bdds, n_all);
+    bddb200_collection_destroy(col); bddb200_ilp_destroy(ilp);
+    return 0;
+}
+''')
+    exe = tmp_path / "use"
+    lib_dir = os.path.dirname(_lib.LIB_PATH)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"), "-o", str(exe), str(src),
+                        "-L" + lib_dir, "-lbdd_b200", "-Wl,-rpath," + lib_dir], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    r = subprocess.run([str(exe)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=60)
+    assert r.returncode == 0, r.stdout
+    n_vars, n_split, n_bdds, n_all = map(int, r.stdout.split())
+    assert (n_vars, n_split) == (5, 1) and n_bdds == 1 + 3 + 1 and n_all > n_vars          # three chunks and their implication BDD, the short BDD stays
+
+
 def test_cuda_library_is_sm100a_only():
     """The product library carries sm_100a SASS and no other architecture."""
     import subprocess
