@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <fstream>
+#include <limits>
 #include <map>
 #include <sstream>
 #include <stdexcept>
@@ -231,6 +232,71 @@ inline BddCollection bdds_from_ilp(const ILP& ilp)
         col.add_bdd(it->second, c.variables);
     }
     return col;
+}
+
+// ILP_input::feasible / evaluate (include/ILP/ILP_input.h:147-200): every constraint holds; objective value or +infinity
+template<typename SOLUTION>
+inline bool feasible(const ILP& ilp, const SOLUTION& x)
+{
+    if(x.size() != ilp.nr_variables()) return false;
+    for(const Constraint& c : ilp.constraints)
+    {
+        long long s = 0;
+        for(size_t k = 0; k < c.variables.size(); ++k) s += c.coefficients[k] * (x[c.variables[k]] ? 1 : 0);
+        if(c.ineq == LE ? s > c.rhs : (c.ineq == GE ? s < c.rhs : s != c.rhs)) return false;
+    }
+    return true;
+}
+template<typename SOLUTION>
+inline double evaluate(const ILP& ilp, const SOLUTION& x)
+{
+    if(!feasible(ilp, x)) return std::numeric_limits<double>::infinity();
+    double cost = ilp.constant;
+    for(size_t v = 0; v < ilp.objective.size(); ++v) if(x[v]) cost += ilp.objective[v];
+    return cost;
+}
+
+// one more constraint, terms on the same variable merged, variables in the order they first appear (as the reader does)
+inline void add_constraint(ILP& ilp, const std::string& identifier, const std::vector<std::string>& var_names, const std::vector<long long>& coefficients,
+                           int ineq, long long rhs)
+{
+    if(var_names.size() != coefficients.size()) throw std::runtime_error("one coefficient per variable");
+    if(ineq != LE && ineq != GE && ineq != EQ) throw std::runtime_error("inequality type not supported");
+    Constraint c;
+    c.identifier = identifier; c.ineq = ineq; c.rhs = rhs;
+    std::map<size_t, long long> merged;
+    for(size_t k = 0; k < var_names.size(); ++k)
+    {
+        const size_t v = ilp.get_or_add_var(var_names[k]);
+        if(!merged.count(v)) { merged[v] = 0; c.variables.push_back(v); }
+        merged[v] += coefficients[k];
+    }
+    for(const size_t v : c.variables) c.coefficients.push_back(merged[v]);
+    ilp.constraints.push_back(std::move(c));
+}
+
+// ILP_input::write_lp (include/ILP/ILP_input.h:229-303): the same sections in the same order; numbers are written with the digits
+// they need to read back exactly (the reference uses the stream's default six)
+inline std::string write_lp(const ILP& ilp)
+{
+    std::ostringstream s;
+    s.precision(17);
+    auto term = [&](double c) { s << (c < 0.0 ? " - " : " + ") << std::abs(c); };
+    s << "Minimize\n";
+    for(size_t v = 0; v < ilp.objective.size(); ++v) { term(ilp.objective[v]); s << " " << ilp.var_names[v] << "\n"; }
+    if(ilp.constant != 0.0) { term(ilp.constant); s << "\n"; }
+    s << "Subject To\n";
+    for(const Constraint& c : ilp.constraints)
+    {
+        if(!c.identifier.empty()) s << c.identifier << ":";
+        for(size_t k = 0; k < c.variables.size(); ++k)
+            if(c.coefficients[k] != 0) { s << (c.coefficients[k] < 0 ? " - " : " + ") << std::llabs(c.coefficients[k]) << " " << ilp.var_names[c.variables[k]]; }
+        s << (c.ineq == LE ? " <= " : (c.ineq == GE ? " >= " : " = ")) << c.rhs << "\n";
+    }
+    s << "Bounds\nBinaries\n";
+    for(const std::string& name : ilp.var_names) s << name << "\n";
+    s << "End\n";
+    return s.str();
 }
 
 // bdd_solver::read_ILP (src/bdd_solver/bdd_solver.cpp:44-66): the name of a readable file, else the LP text itself

@@ -1,9 +1,9 @@
 // bdd_b200/csrc/host/py/bdd_cuda_parallel_mma_py.cpp -- pybind11 module `bdd_cuda_parallel_mma_py`: the Python surface of the solver
 // class (src/bdd_solver/bdd_cuda_parallel_mma_py.cu:26-71 of the reference: class bdd_cuda_parallel_mma (double) with pickling,
 // __repr__, nr_primal_variables, nr_layers([hop]), nr_hops, nr_bdds, lower_bound, compute_and_set_min_marginal_diff(device pointer))
-// over the C ABI of libbdd_b200.so.  The reference constructs from its pybind'ed ILP_input (Eigen and PEGTL, neither in this image);
-// here the constructor takes the text of an .lp file (or its name) and goes through this build's reader and QBDD builder
-// (bdd_solver_native.hpp).  iteration / iterations are added so the class is usable on its own.  Host code only.
+// over the C ABI of libbdd_b200.so.  As in the reference the constructor takes an ILP_instance (module ILP_instance_py of this
+// build, host/py/ILP_instance_py.cpp); the text of an .lp file or its name is accepted as well.  BDDs come from this build's QBDD
+// builder (host/bdd_collection.hpp).  iteration / iterations are added so the class is usable on its own.  Host code only.
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
@@ -30,12 +30,10 @@ struct solver_t {
 
     static solver_t* from_lp(const std::string& lp, const std::string& precision, int device)
     {
-        std::string text = lp;
-        {
-            std::ifstream f(lp);
-            if(f.good()) { std::stringstream ss; ss << f.rdbuf(); text = ss.str(); }
-        }
-        const bddb200_host::ILP ilp = bddb200_host::parse_lp(text);
+        return from_ilp(bddb200_host::read_ilp(lp), precision, device);
+    }
+    static solver_t* from_ilp(const bddb200_host::ILP& ilp, const std::string& precision, int device)
+    {
         const bddb200_host::BddCollection col = bddb200_host::bdds_from_ilp(ilp);
         auto s = std::make_unique<solver_t>();
         bddb200_options opt;
@@ -91,8 +89,11 @@ struct solver_t {
 PYBIND11_MODULE(bdd_cuda_parallel_mma_py, m)
 {
     m.doc() = "Python binding for the bdd-based solver on B200 (drop-in surface of the reference's bdd_cuda_parallel_mma_py)";
+    py::module_::import("ILP_instance_py");          // the ILP_instance type the reference's constructor takes (bdd_cuda_parallel_mma_py.cu:39-44)
     py::class_<solver_t>(m, "bdd_cuda_parallel_mma")
         .def(py::pickle([](const solver_t& s) { return s.save(); }, [](const py::bytes& b) { return solver_t::load(b); }))
+        .def(py::init([](const bddb200_host::ILP& ilp, const std::string& precision, int device) { return solver_t::from_ilp(ilp, precision, device); }),
+             py::arg("ilp"), py::arg("precision") = "double", py::arg("device") = 0, "ilp: an ILP_instance_py.ILP_instance")
         .def(py::init([](const std::string& lp, const std::string& precision, int device) { return solver_t::from_lp(lp, precision, device); }),
              py::arg("lp"), py::arg("precision") = "double", py::arg("device") = 0, "lp: the text of an .lp file, or its file name")
         .def("__repr__", [](const solver_t& s) {

@@ -39,6 +39,47 @@ def test_modules_expose_the_reference_surface():
         bs.bdd_solver({"relaxation solver": "cuda parallel mma"}).solve()        # no input
 
 
+def test_ilp_instance_py_surface(tmp_path):
+    """ILP_instance_py with the reference's names (src/ILP/ILP_instance_py.cpp:70-132): reading, building an instance by hand, evaluate /
+    feasible, write_lp round trip -- against bdd_b200/lp.py on every fixture"""
+    _modules()
+    import ILP_instance_py as ip
+    from bdd_b200 import lp
+    assert (int(ip.smaller_equal), int(ip.greater_equal), int(ip.equal)) == (lp.LE, lp.GE, lp.EQ) and ip.inequality_type.equal == ip.equal
+    for path in sorted(glob.glob(os.path.join(GOLDEN, "*.lp"))):
+        want = lp.parse_lp(open(path).read())
+        for ilp in (ip.read_ILP(path), ip.parse_ILP(open(path).read())):
+            assert ilp.nr_variables() == len(want.var_names) and ilp.nr_constraints() == len(want.constraints)
+            assert ilp.objective() == want.objective and ilp.constant() == want.constant
+            assert [ilp.get_var_name(v) for v in range(ilp.nr_variables())] == want.var_names
+            assert all(ilp.get_var_index(n) == v for v, n in enumerate(want.var_names))
+            for c, k in enumerate(want.constraints):
+                ident, variables, coeffs, ineq, rhs = ilp.constraint(c)
+                assert (ident, variables, coeffs, int(ineq), rhs) == (k.identifier, list(k.variables), list(k.coefficients), k.ineq, k.rhs)
+            out = tmp_path / "round_trip.lp"
+            ilp.write_lp(str(out))
+            again = lp.parse_lp(out.read_text())
+            assert again.var_names == want.var_names and again.objective == want.objective and again.constant == want.constant
+            assert [(k.variables, k.coefficients, k.ineq, k.rhs) for k in again.constraints] == [(k.variables, k.coefficients, k.ineq, k.rhs) for k in want.constraints]
+    # by hand: min x + 2 y - z  s.t.  x + y >= 1,  y + z = 1,  x + y + z <= 2 (terms on one variable are merged)
+    ilp = ip.ILP_instance()
+    assert [ilp.add_new_variable_with_obj(n, c) for n, c in (("x", 1.0), ("y", 2.0), ("z", -1.0))] == [0, 1, 2]
+    ilp.add_new_constraint("cover", ["x", "y"], [1, 1], 1, ip.greater_equal)
+    ilp.add_new_constraint("pick", ["y", "z"], [1, 1], 1, ip.equal)
+    ilp.add_new_constraint("cap", ["x", "y", "z", "x"], [1, 1, 1, 0], 2, ip.smaller_equal)
+    with pytest.raises(RuntimeError):
+        ilp.add_new_variable_with_obj("x", 1.0)
+    assert (ilp.nr_variables(), ilp.nr_constraints()) == (3, 3) and ilp.constraint(2)[1:3] == ([0, 1, 2], [1, 1, 1])
+    assert ilp.feasible([1, 0, 1]) and ilp.evaluate([1, 0, 1]) == 0.0
+    assert not ilp.feasible([0, 0, 1]) and ilp.evaluate([0, 0, 1]) == float("inf") and not ilp.feasible([1, 0])
+    assert not ilp.feasible([1, 1, 1])
+    best = min(ilp.evaluate([a, b, c]) for a in (0, 1) for b in (0, 1) for c in (0, 1))
+    assert best == 0.0
+    text = str(ilp)
+    assert text.startswith("Minimize\n + 1 x\n + 2 y\n - 1 z\nSubject To\ncover: + 1 x + 1 y >= 1\n") and text.endswith("Bounds\nBinaries\nx\ny\nz\nEnd\n")
+    assert lp.parse_lp(text).objective == [1.0, 2.0, -1.0]
+
+
 def test_no_gpu_no_answer():
     """The product path has no CPU fallback: without a device the constructors raise the library's error."""
     torch = pytest.importorskip("torch")
@@ -48,6 +89,11 @@ def test_no_gpu_no_answer():
     lp = open(os.path.join(GOLDEN, "matching_3x3.lp")).read()
     with pytest.raises(RuntimeError, match="no CUDA device"):
         bc.bdd_cuda_parallel_mma(lp)
+    import ILP_instance_py as ip
+    with pytest.raises(RuntimeError, match="no CUDA device"):                  # the reference's constructor: from an ILP_instance
+        bc.bdd_cuda_parallel_mma(ip.parse_ILP(lp))
+    with pytest.raises(TypeError):
+        bc.bdd_cuda_parallel_mma(3)
     s = bs.bdd_solver({"input": lp, "relaxation solver": "cuda parallel mma"})
     s.verbose = False
     with pytest.raises(RuntimeError, match="no CUDA device"):
@@ -91,6 +137,11 @@ def test_bdd_cuda_parallel_mma_py_class():
     assert sum(s.nr_layers(h) for h in range(s.nr_hops() + 1)) == s.nr_layers()
     assert "nr_variables: %d" % ref.nr_variables() in repr(s)
     assert abs(s.lower_bound() - ref.lower_bound()) <= 1e-12
+    # the reference's constructor takes an ILP_instance (bdd_cuda_parallel_mma_py.cu:39-44)
+    import ILP_instance_py as ip
+    from_ilp = bc.bdd_cuda_parallel_mma(ip.read_ILP(path))
+    assert (from_ilp.nr_primal_variables(), from_ilp.nr_bdds(), from_ilp.nr_layers()) == (s.nr_primal_variables(), s.nr_bdds(), s.nr_layers())
+    assert from_ilp.lower_bound() == s.lower_bound()
     for _ in range(7):
         s.iteration(); ref.iteration()
     assert abs(s.lower_bound() - ref.lower_bound()) <= 1e-9
