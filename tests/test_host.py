@@ -164,6 +164,38 @@ End
         ("c1", [0, 1, 2], [1, 1, 1], lp.GE, 1), ("", [0, 3], [-1, 2], lp.LE, 1), ("named[2]", [1, 3], [1, -1], lp.EQ, 0)]
 
 
+REF_PARSER_CASES = [      # test/test_ILP_parser.cpp:8-27 of the reference: ILP_example, ILP_example_hash
+    ("Minimize\nx1 + 2*x2 + 1.5 * x3 - 0.5*x4 - x5\nSubject To\nx1 + 2*x2 + 3 * x3 - 5*x4 - x5 >= 1\nBounds\n x1 <= 1\n x2 >= 0\nEnd",
+     ["x1", "x2", "x3", "x4", "x5"], ""),
+    ("Minimize\nx1 + 2*x2 + 1.5 * x#3 - 0.5*x#4 - x3\nSubject To\n b_cuta_;0;14_1;@41d: x1 + 2*x2 + 3 * x#3 - 5*x#4 - x3 >= 1\nBounds\n x1 <= 1\n x2 >= 0\nEnd",
+     ["x1", "x2", "x#3", "x#4", "x3"], "b_cuta_;0;14_1;@41d"),
+]
+
+
+@pytest.mark.parametrize("text, names, identifier", REF_PARSER_CASES)
+def test_readers_pass_the_reference_parser_known_answers(text, names, identifier):
+    """the reference's own parser test (test/test_ILP_parser.cpp:38-79): five variables with these names and objective coefficients, one
+    constraint -- through the Python reader, the C++ reader behind the C ABI and the pybind11 module"""
+    import glob
+    import sys
+    from bdd_b200.collection import ilp_input
+    want_constraint = ([0, 1, 2, 3, 4], [1, 2, 3, -5, -1], lp.GE, 1)
+    ilp = lp.parse_lp(text)
+    assert ilp.var_names == names and ilp.objective == [1.0, 2.0, 1.5, -0.5, -1.0] and len(ilp.constraints) == 1
+    c = ilp.constraints[0]
+    assert (c.identifier, c.variables, c.coefficients, c.ineq, c.rhs) == (identifier,) + want_constraint
+    native = ilp_input(text)
+    assert native.variable_names() == names and native.objective()[0].tolist() == [1.0, 2.0, 1.5, -0.5, -1.0]
+    assert native.nr_constraints() == 1 and native.constraint(0) == want_constraint
+    pkg = os.path.join(ROOT, "bdd_b200")
+    if glob.glob(os.path.join(pkg, "ILP_instance_py*.so")):
+        sys.path.insert(0, pkg)
+        import ILP_instance_py as ip
+        bound = ip.parse_ILP(text)
+        assert [bound.get_var_name(v) for v in range(bound.nr_variables())] == names and bound.objective() == [1.0, 2.0, 1.5, -0.5, -1.0]
+        assert bound.nr_constraints() == 1 and bound.constraint(0)[0] == identifier and bound.constraint(0)[1:3] == want_constraint[:2]
+
+
 def test_generator_sizes():
     t = instances.qbdd_template([1] * 20, lp.GE, 1)
     assert len(t.layer) + 2 == 41                       # SURVEY 8d: 2k-1 inner nodes + 2 terminals
