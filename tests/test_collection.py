@@ -463,3 +463,96 @@ def test_collection_with_implication_bdds_solves_like_the_oracle_on_gpu(precisio
     for _ in range(15):
         s.iteration(); o.iteration()
         assert abs(s.lower_bound() - o.lower_bound()) <= tol * max(1.0, abs(o.lower_bound()))
+
+
+# ------------------------------------------------------------------------------------------------ the reference's own collection tests
+def test_reference_collection_known_answers():
+    """test/bdd/test_bdd_collection_layer_widths.cpp, _layer_offsets.cpp, _remove.cpp, _qbdd.cpp of the reference, as they stand"""
+    col = bdd_collection()
+    for i in range(2, 15):
+        b = col.simplex_constraint(i)
+        flat = col.export()
+        first, last = int(flat.delims[b]), int(flat.delims[b + 1]) - 2
+        idx = flat.instrs[first:last, 2]
+        starts = np.flatnonzero(np.concatenate([[True], idx[1:] != idx[:-1]]))
+        widths = np.diff(np.concatenate([starts, [last - first]]))
+        assert len(widths) == i and (widths[1:] == 2).all()                       # layer_widths
+        assert starts[0] == 0 and all(starts[v] == 2 * v - 1 for v in range(1, i))   # layer_offsets relative to offset(b)
+    col = bdd_collection()
+    s3, s4 = col.simplex_constraint(3), col.simplex_constraint(4)
+    sizes = np.diff(col.export().delims.astype(np.int64))
+    assert sizes[s3] == 2 * 3 - 1 + 2 and sizes[s4] == 2 * 4 - 1 + 2 and col.nr_bdds() == 2
+    col.remove(0)
+    assert col.nr_bdds() == 1 and np.diff(col.export().delims.astype(np.int64))[0] == 2 * 4 - 1 + 2
+    col = bdd_collection()
+    for i in range(2, 17):
+        b = col.not_all_false_constraint(i)
+        q = col.make_qbdd(b)
+        sizes = np.diff(col.export().delims.astype(np.int64))
+        assert col.is_qbdd(q) and not col.is_qbdd(b) and sizes[b] < sizes[q]
+
+
+@pytest.mark.parametrize("with_implication_bdd", [False, True])
+def test_reference_split_protocol_on_cardinality_constraints(with_implication_bdd):
+    """test/bdd/test_bdd_collection_split_qbdd.cpp:14-56: a cardinality constraint cut into chunks (with and without the implication BDD)
+    is solved to the sum of its k smallest costs by 200 MMA iterations, like the constraint as a whole; for k = 1 the auxiliary variables
+    are two per cut.  The solver is the CPU oracle (pinned to the reference's CPU solver, tests/test_oracle_vs_ref.py)."""
+    rng = np.random.default_rng(0)
+    B.oracle_set_num_threads(1)
+    n_cases = 0
+    for i in range(4, 17, 3):
+        for k in sorted({1, 2, i // 2, i - 2} - {0}):
+            if k >= i - 1:
+                continue
+            for chunk in sorted({2, 3, i // 2, i - 2}):
+                if chunk < 2 or chunk + 1 >= i:
+                    continue
+                col = bdd_collection()
+                card = col.cardinality_constraint(i, k)
+                whole = col.export()
+                new_nrs, next_aux = col.split_qbdd(card, chunk, i, with_implication_bdd)
+                nr_chunks = -(-i // chunk)
+                assert len(new_nrs) in (nr_chunks, nr_chunks + 1) and len(new_nrs) > 1
+                assert with_implication_bdd or len(new_nrs) == nr_chunks
+                if k == 1:
+                    assert next_aux == i + 2 * (nr_chunks - 1)
+                col.remove(card)
+                split = col.export()
+                costs = rng.uniform(-10, 10, size=i)
+                want = np.sort(costs)[:k].sum()
+                o_whole = B.Oracle(whole.instrs, whole.delims, costs, "double")
+                o_split = B.Oracle(split.instrs, split.delims, np.concatenate([costs, np.zeros(next_aux - i)]), "double")
+                for _ in range(200):
+                    o_split.iteration()
+                assert abs(o_whole.lower_bound() - want) <= 1e-6, (i, k, chunk)
+                assert abs(o_split.lower_bound() - want) <= 1e-6, (i, k, chunk, o_split.lower_bound(), want)
+                n_cases += 1
+    assert n_cases >= 30
+
+
+@pytest.mark.parametrize("with_implication_bdd", [False, True])
+@pytest.mark.parametrize("name", golden_names())
+def test_reference_split_protocol_on_the_test_problems(name, with_implication_bdd):
+    """test/bdd/test_bdd_collection_split_qbdd.cpp:58-84: every BDD of a test problem cut at length 2; after 300 iterations the bound
+    of the split collection equals the bound of the original one"""
+    from bdd_b200 import lp
+    ilp = lp.parse_lp(open(os.path.join(GOLDEN, name + ".lp")).read())
+    flat, costs = instances.from_ilp(ilp)
+    col = bdd_collection(flat)
+    aux, removed = len(costs), []
+    for b in range(flat.nr_bdds):
+        try:
+            new_nrs, nxt = col.split_qbdd(b, 2, aux, with_implication_bdd)
+        except Exception:
+            continue                                   # cut in front of a layer of width 1: the reference asserts (bdd_collection.cpp:598)
+        if len(new_nrs) > 1:
+            removed.append(b)
+            aux = nxt
+    col.remove(removed)
+    split = col.export()
+    B.oracle_set_num_threads(1)
+    o_whole = B.Oracle(flat.instrs, flat.delims, costs, "double")
+    o_split = B.Oracle(split.instrs, split.delims, np.concatenate([costs, np.zeros(aux - len(costs))]), "double")
+    for _ in range(300):
+        o_whole.iteration(); o_split.iteration()
+    assert abs(o_whole.lower_bound() - o_split.lower_bound()) <= 1e-6 * max(1.0, abs(o_whole.lower_bound())), (len(removed), o_whole.lower_bound(), o_split.lower_bound())
