@@ -556,3 +556,39 @@ def test_reference_split_protocol_on_the_test_problems(name, with_implication_bd
     for _ in range(300):
         o_whole.iteration(); o_split.iteration()
     assert abs(o_whole.lower_bound() - o_split.lower_bound()) <= 1e-6 * max(1.0, abs(o_whole.lower_bound())), (len(removed), o_whole.lower_bound(), o_split.lower_bound())
+
+
+def test_reference_variables_protocol():
+    """test/bdd/test_bdd_collection_variables.cpp: variables() of simplex and not-all-false BDDs, also after a rebase onto reversed and
+    onto shuffled variables (the order of the layers, not of the indices)"""
+    col = bdd_collection()
+    for i in range(2, 29):
+        order = list(range(i))
+        s, n = col.simplex_constraint(i), col.not_all_false_constraint(i)
+        assert list(col.variables(s)) == order and list(col.variables(n)) == order
+        col.rebase(s, order[::-1]); col.rebase(n, order[::-1])
+        assert list(col.variables(s)) == order[::-1] and list(col.variables(n)) == order[::-1]
+    rng = np.random.default_rng(1)
+    shuffled = np.cumsum(rng.integers(1, 43, size=42))
+    rng.shuffle(shuffled)
+    b = col.simplex_constraint(42)
+    assert list(col.variables(b)) == list(range(42))
+    col.rebase(b, shuffled)
+    assert list(col.variables(b)) == shuffled.tolist() and col.is_qbdd(b) and col.is_reordered(b)
+
+
+def test_reference_bdd_and_protocol():
+    """test/bdd/test_bdd_collection_and.cpp: the conjunction of the three covering constraints over (0,1,3), (0,2,4), (1,2,5) is the
+    function the BDD manager computes for them (here: checked on all 64 assignments, and reduced: no node with lo == hi, no duplicates)"""
+    col = bdd_collection()
+    parts = []
+    for variables in ([0, 1, 3], [0, 2, 4], [1, 2, 5]):
+        b = col.not_all_false_constraint(3)
+        col.rebase(b, variables)
+        parts.append(b)
+    both = col.bdd_and(parts)
+    for x in itertools.product((0, 1), repeat=6):
+        assert col.evaluate(both, x) == ((x[0] or x[1] or x[3]) and (x[0] or x[2] or x[4]) and (x[1] or x[2] or x[5]))
+    flat = col.export()
+    nodes = flat.instrs[int(flat.delims[both]):int(flat.delims[both + 1]) - 2]
+    assert (nodes[:, 0] != nodes[:, 1]).all() and len({tuple(r) for r in nodes.tolist()}) == len(nodes)
