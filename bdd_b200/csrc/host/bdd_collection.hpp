@@ -92,6 +92,7 @@ private:
 // canonical form the reference reaches through lineq_bdd -> bdd_mgr -> add_bdd -> reorder -> make_qbdd (bdd_preprocessor.cpp:175-228)
 // up to the order of the nodes inside a layer (tests/test_host.py, tests/test_collection.py against the reference's converter).
 enum Ineq { LE = 0, GE = 1, EQ = 2 };
+constexpr size_t MAX_PARTIAL_SUMS = size_t(1) << 20;     // the builder enumerates the reachable partial sums of a layer; a solver layer holds at most 65 504 nodes anyway
 
 // One BDD with local numbering: node i branches on position layer[i] of the constraint's variable list; children are local node ids,
 // -1 = bot sink, -2 = top sink; nodes are ordered layer by layer.
@@ -111,6 +112,9 @@ inline QbddTemplate qbdd_template(const std::vector<long long>& a, int ineq, lon
     {
         std::set<long long> nxt;
         for(long long s : sums[k]) { nxt.insert(s); nxt.insert(s + a[k]); }
+        if(nxt.size() > MAX_PARTIAL_SUMS)
+            throw std::runtime_error("constraint with more than " + std::to_string(MAX_PARTIAL_SUMS) + " distinct partial sums in a layer: outside the direct BDD "
+                                     "builder's scope (the reference converts such knapsack rows through its BDD manager, test/hard_ineqs.h)");
         sums[k + 1].assign(nxt.begin(), nxt.end());
     }
     auto accept = [&](long long s) { return ineq == LE ? s <= rhs : (ineq == GE ? s >= rhs : s == rhs); };

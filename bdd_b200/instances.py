@@ -109,6 +109,9 @@ class QbddTemplate:
     hi: np.ndarray  # int64 [n]
 
 
+MAX_PARTIAL_SUMS = 1 << 20     # the direct builder enumerates the reachable partial sums of a layer; a solver layer holds at most 65 504 nodes anyway
+
+
 def qbdd_template(coeffs: Sequence[int], ineq: int, rhs: int) -> Optional[QbddTemplate]:
     """Quasi-reduced BDD of ``sum_i coeffs[i] * x_i  (<=|>=|=)  rhs`` in the given variable
     order.  Returns ``None`` if the constraint is always satisfied; raises if infeasible.
@@ -128,6 +131,9 @@ def qbdd_template(coeffs: Sequence[int], ineq: int, rhs: int) -> Optional[QbddTe
         for s in sums[k]:
             nxt.add(s)
             nxt.add(s + a[k])
+        if len(nxt) > MAX_PARTIAL_SUMS:
+            raise ValueError(f"constraint with more than {MAX_PARTIAL_SUMS} distinct partial sums in a layer: outside the direct BDD builder's scope "
+                             "(the reference converts such knapsack rows through its BDD manager, test/hard_ineqs.h)")
         sums.append(sorted(nxt))
 
     def accept(s: int) -> bool:

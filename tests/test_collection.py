@@ -138,6 +138,21 @@ def test_library_lp_reader_and_builder_equal_the_python_ones(name):
         assert np.array_equal(flat.delims, col.delims) and np.array_equal(flat.instrs, col.instrs)
 
 
+def test_knapsack_rows_beyond_the_direct_builder_are_refused_not_attempted():
+    """distinct powers of two make every subset sum different: the builder stops at 2^20 states per layer with a clear message instead
+    of running out of memory (the reference's test/hard_ineqs.h rows are of this kind and go through its BDD manager)"""
+    import time
+    from bdd_b200._lib import BddB200Error
+    coeffs, variables = [2 ** k for k in range(40)], list(range(40))
+    t = time.time()
+    with pytest.raises(BddB200Error, match="partial sums"):
+        bdd_collection().add_linear_constraint(coeffs, variables, 0, 2 ** 39)
+    with pytest.raises(ValueError, match="partial sums"):
+        instances.qbdd_template(coeffs, 0, 2 ** 39)
+    assert time.time() - t < 60
+    assert bdd_collection().add_linear_constraint(coeffs[:12], variables[:12], 0, 2 ** 11) is not None
+
+
 def test_library_lp_reader_rejects_what_it_cannot_read():
     from bdd_b200._lib import BddB200Error
     from bdd_b200.collection import ilp_input
