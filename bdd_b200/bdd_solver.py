@@ -17,7 +17,7 @@ Deviations from the reference, all documented in SURVEY 3.1: ``precision`` means
 float solver for "double" and vice versa, bdd_solver.cpp:167-174); the README spelling "lbfgs cuda parallel mma"
 (README.md:56), which matches none of the reference's strings and throws there (:237), is accepted; GPU rounding works
 for every GPU solver (the reference's type list omits cuda parallel mma double, :353-356).  CPU solvers
-("sequential mma", "parallel mma", ...), variable reordering, constraint normalisation and the export keys belong to subsystems
+("sequential mma", "parallel mma", ...), variable reordering, constraint normalisation and the keys "export bdd lp" / "export bdd graph" belong to subsystems
 outside this build's scope and raise.  ``"split bdds": {"implication bdd": true}`` (also spelled ``"implication"``, the key
 the reference reads, bdd_solver.cpp:119) adds the splitter's implication BDDs through the library's host-side collection.
 """
@@ -73,6 +73,17 @@ class bdd_solver:
             raise RuntimeError("variable reordering is outside this build's scope (SURVEY 2, row 23)")
         if config.get("normalize constraints", False):
             raise RuntimeError("constraint normalisation is outside this build's scope")
+
+    # ---- export_lp, :412-430 ---------------------------------------------------------------------------------------------------
+    def export_lp(self, config: dict):
+        if "export lp" not in config:
+            return
+        path = config["export lp"]
+        extension = os.path.splitext(path)[1]
+        if extension != ".lp":          # the reference also writes .opb and .mps
+            raise RuntimeError(f"Cannot recognize file extension {extension} for exporting problem file")
+        with open(path, "w") as f:
+            f.write(lp.write_lp(self.ilp))
 
     # ---- transform_to_BDDs, :112-123 ------------------------------------------------------------------------------------------
     def transform_to_BDDs(self, config: dict):
@@ -151,12 +162,13 @@ class bdd_solver:
     def solve(self, config):
         if isinstance(config, str):
             config = read_config(config)
-        for key in ("export lp", "export bdd lp", "export bdd graph"):
+        for key in ("export bdd lp", "export bdd graph"):
             if key in config:
                 raise RuntimeError(f"'{key}' is outside this build's scope")
         if self.ilp is None:
             self.ilp = self.read_ILP(config)
             self.process_ILP(config)
+            self.export_lp(config)
             self.bdd_col, self.costs = self.transform_to_BDDs(config)
             if "print statistics" in config:
                 self.log(f"[print_statistics] #variables = {self.ilp.nr_variables()}, #constraints = {len(self.ilp.constraints)}, #BDDs = {self.bdd_col.nr_bdds}")

@@ -66,12 +66,22 @@ public:
     void solve() { solve(config_); }
     void solve(const json& config)
     {
-        for(const char* key : {"export lp", "export bdd lp", "export bdd graph"})
+        for(const char* key : {"export bdd lp", "export bdd graph"})
             if(config.contains(key)) throw std::runtime_error(std::string("'") + key + "' is not provided by the C++ driver of this build");
         if(solver_ == nullptr)
         {
             read_ILP(config);
             if(config.value("variable order", std::string("input")) != "input") throw std::runtime_error("variable reordering is outside this build's scope");
+            if(config.contains("export lp"))
+            {   // bdd_solver::export_lp, bdd_solver.cpp:412-430 (the reference also writes .opb and .mps)
+                const std::string file = config["export lp"].get<std::string>();
+                const size_t dot = file.rfind('.');
+                const std::string extension = dot == std::string::npos ? std::string() : file.substr(dot);
+                if(extension != ".lp") throw std::runtime_error("Cannot recognize file extension " + extension + " for exporting problem file");
+                std::ofstream f(file);
+                if(!f.good()) throw std::runtime_error("cannot write " + file);
+                f << write_lp(ilp_);
+            }
             log("[bdd solver] Compute BDDs");
             bdd_col_ = bdds_from_ilp(ilp_);
             if(config.contains("split bdds"))

@@ -144,7 +144,9 @@ def parse_lp(text: str) -> ILP:
 def write_lp(ilp: ILP) -> str:
     """Inverse of :func:`parse_lp` (for round-trip tests and for feeding the reference)."""
     out = ["Minimize"]
-    obj = " ".join(f"{'+' if c >= 0 else '-'} {abs(c):g} {n}" for c, n in zip(ilp.objective, ilp.var_names))
+    obj = " ".join(f"{'+' if c >= 0 else '-'} {abs(c)!r} {n}" for c, n in zip(ilp.objective, ilp.var_names))
+    if ilp.constant != 0.0:
+        obj += f" {'+' if ilp.constant >= 0 else '-'} {abs(ilp.constant)!r}"
     out.append(obj)
     out.append("Subject To")
     rel = {LE: "<=", GE: ">=", EQ: "="}

@@ -72,7 +72,40 @@ def test_unsupported_keys_and_missing_gpu():
     with pytest.raises(RuntimeError, match="scope"):
         drv.bdd_solver({"input": os.path.join(GOLDEN, "matching_3x3.lp"), "variable order": "bfs"}, log=quiet)
     with pytest.raises(RuntimeError, match="scope"):
-        drv.bdd_solver({"input": os.path.join(GOLDEN, "matching_3x3.lp"), "export lp": "x.lp"}, log=quiet)
+        drv.bdd_solver({"input": os.path.join(GOLDEN, "matching_3x3.lp"), "export bdd lp": "x.lp"}, log=quiet)
+    with pytest.raises(RuntimeError, match="file extension"):
+        drv.bdd_solver({"input": os.path.join(GOLDEN, "matching_3x3.lp"), "export lp": "x.mps"}, log=quiet)
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError):                                  # no CPU fallback
             drv.bdd_solver({"input": os.path.join(GOLDEN, "matching_3x3.lp"), "relaxation solver": "cuda parallel mma"}, log=quiet)
+
+
+@pytest.mark.parametrize("name", ["matching_3x3", "long_mrf_chain"])
+def test_export_lp_key_writes_the_problem_back(tmp_path, name):
+    """"export lp" (bdd_solver.cpp:412-430) in the Python driver and in the C++ command line: the exported file reads back as the same ILP
+    (the export happens before a solver is constructed, so it works without a GPU; the solve itself then fails loudly here)"""
+    import subprocess
+    import torch
+    from bdd_b200 import lp
+    src = os.path.join(GOLDEN, name + ".lp")
+    want = lp.parse_lp(open(src).read())
+
+    def same(path):
+        got = lp.parse_lp(open(path).read())
+        assert got.var_names == want.var_names and got.objective == want.objective and got.constant == want.constant
+        assert [(k.variables, k.coefficients, k.ineq, k.rhs) for k in got.constraints] == [(k.variables, k.coefficients, k.ineq, k.rhs) for k in want.constraints]
+
+    out = tmp_path / "py.lp"
+    cfg = {"input": src, "relaxation solver": "cuda parallel mma", "export lp": str(out), "termination criteria": {"maximum iterations": 2}}
+    try:
+        drv.bdd_solver(cfg, log=quiet)
+    except RuntimeError:
+        assert not torch.cuda.is_available()
+    same(out)
+    cli = os.path.join(os.path.dirname(GOLDEN), "..", "bdd_b200", "bdd_solver_cl")
+    if os.path.exists(cli):
+        out = tmp_path / "cpp.lp"
+        cfg["export lp"] = str(out)
+        r = subprocess.run([cli, json.dumps(cfg)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+        assert r.returncode == 0 or not torch.cuda.is_available()
+        same(out)
