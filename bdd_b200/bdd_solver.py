@@ -17,7 +17,7 @@ Deviations from the reference, all documented in SURVEY 3.1: ``precision`` means
 float solver for "double" and vice versa, bdd_solver.cpp:167-174); the README spelling "lbfgs cuda parallel mma"
 (README.md:56), which matches none of the reference's strings and throws there (:237), is accepted; GPU rounding works
 for every GPU solver (the reference's type list omits cuda parallel mma double, :353-356).  CPU solvers
-("sequential mma", "parallel mma", ...), variable reordering, constraint normalisation and the keys "export bdd lp" / "export bdd graph" belong to subsystems
+("sequential mma", "parallel mma", ...), variable reordering, constraint normalisation and the key "export bdd graph" belong to subsystems
 outside this build's scope and raise.  ``"split bdds": {"implication bdd": true}`` (also spelled ``"implication"``, the key
 the reference reads, bdd_solver.cpp:119) adds the splitter's implication BDDs through the library's host-side collection.
 """
@@ -162,14 +162,16 @@ class bdd_solver:
     def solve(self, config):
         if isinstance(config, str):
             config = read_config(config)
-        for key in ("export bdd lp", "export bdd graph"):
-            if key in config:
-                raise RuntimeError(f"'{key}' is outside this build's scope")
+        if "export bdd graph" in config:
+            raise RuntimeError("'export bdd graph' is outside this build's scope")
         if self.ilp is None:
             self.ilp = self.read_ILP(config)
             self.process_ILP(config)
             self.export_lp(config)
             self.bdd_col, self.costs = self.transform_to_BDDs(config)
+            if "export bdd lp" in config:        # export_bdd_lp, :400-410: the relaxation as a linear programme over arc-flow variables
+                from .collection import bdd_collection
+                bdd_collection(self.bdd_col).write_bdd_lp(config["export bdd lp"], self.costs)
             if "print statistics" in config:
                 self.log(f"[print_statistics] #variables = {self.ilp.nr_variables()}, #constraints = {len(self.ilp.constraints)}, #BDDs = {self.bdd_col.nr_bdds}")
             self.solver = self.construct_solver(config)

@@ -126,6 +126,12 @@ class bdd_collection:
         v = np.ascontiguousarray([bdd_nrs] if np.isscalar(bdd_nrs) else list(bdd_nrs), dtype=np.uint64)
         _lib.check(self._lib.bddb200_collection_remove(self._h, v.ctypes.data, v.shape[0]))
 
+    def write_bdd_lp(self, path: str, costs: Sequence[float]) -> None:
+        """``bdd_collection::write_bdd_lp``: the relaxation the dual solvers work on as an ``.lp`` file (arc-flow variables per BDD linked
+        through the shared variables ``x_<var>``); its optimum is the best bound the BDD decomposition can give."""
+        c = np.ascontiguousarray(costs, dtype=np.float64)
+        _lib.check(self._lib.bddb200_collection_write_bdd_lp(self._h, c.ctypes.data, c.shape[0], str(path).encode()))
+
     # ------------------------------------------------------------------ splitting
     def split_qbdd(self, bdd_nr: int, chunk_size: int, aux_var_start: int, with_implication_bdd: bool = False) -> Tuple[List[int], int]:
         """``bdd_collection::split_qbdd``: returns (numbers of the new BDDs -- ``[bdd_nr]`` when nothing was cut --, next free auxiliary variable)."""

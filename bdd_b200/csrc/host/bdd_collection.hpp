@@ -24,6 +24,7 @@
 
 #include <algorithm>
 #include <array>
+#include <cmath>
 #include <cstdint>
 #include <deque>
 #include <limits>
@@ -549,6 +550,56 @@ public:
         for(size_t c = 0; c < nr_chunks; ++c) new_nrs[c] = nr_before + c;
         if(with_implication_bdd && nr_chunks > 2 && add_implication_bdd(src, chunk_size, nr_chunks, aux_var_start)) new_nrs.push_back(nr_bdds() - 1);
         return {new_nrs, aux};
+    }
+
+    // ---------------------------------------------------------------------------------------- export
+    // The linear programme whose optimum is the bound the dual solvers approach, in .lp syntax (write_bdd_lp, header :731-830; "export
+    // bdd lp" of the driver): one 0/1 variable arc_<bdd>_<node>_<value> per arc that does not end in the bot sink, one unit of flow
+    // from every root (R_<bdd>), conserved at every other node (FC_<bdd>_<node>), and per BDD and layer the flow over the hi arcs
+    // equal to the shared variable x_<var>.  Text identical to the reference's for BDDs over ascending variables
+    // (tests/test_collection.py); for the chunks of a split BDD, whose auxiliary variables come first, the reference ties the first
+    // layer to the wrong variable (:800) -- here every layer is tied to its own.
+    template<typename STREAM>
+    void write_bdd_lp(STREAM& s, const std::vector<double>& costs) const
+    {
+        auto arc = [](size_t b, size_t node, int value) { return "arc_" + std::to_string(b) + "_" + std::to_string(node) + "_" + std::to_string(value); };
+        s << "Minimize\n";
+        for(size_t v = 0; v < costs.size(); ++v) s << (costs[v] < 0 ? "-" : "+") << std::abs(costs[v]) << " x_" << v << "\n";
+        s << "Subject To\n";
+        std::vector<std::string> inflow;                                       // per node: " - arc" of every arc that enters it
+        for(size_t b = 0; b < nr_bdds(); ++b)
+        {
+            const size_t first = delims[b], n = delims[b + 1] - 2 - first;
+            inflow.assign(n, std::string());
+            for(size_t k = 0; k < n; ++k)
+            {
+                const bddb200_instruction& x = instrs[first + k];
+                if(k == 0) s << "R_" << b << ": "; else s << "FC_" << b << "_" << k << ": ";
+                if(instrs[x.lo].index != BOTSINK) s << arc(b, k, 0);
+                if(instrs[x.hi].index != BOTSINK) s << " + " << arc(b, k, 1);
+                s << inflow[k] << (k == 0 ? " = 1\n" : " = 0\n");
+                if(!is_terminal(x.lo)) inflow[x.lo - first] += " - " + arc(b, k, 0);
+                if(!is_terminal(x.hi)) inflow[x.hi - first] += " - " + arc(b, k, 1);
+            }
+        }
+        for(size_t b = 0; b < nr_bdds(); ++b)
+        {
+            const size_t first = delims[b], n = delims[b + 1] - 2 - first;
+            size_t layer_var = instrs[first].index;      // (the reference starts from the BDD's smallest variable, which is the root's only when the variables ascend)
+            for(size_t k = 0; k < n; ++k)
+            {
+                const bddb200_instruction& x = instrs[first + k];
+                if(x.index != layer_var) { s << " - x_" << layer_var << " = 0\n"; layer_var = x.index; }
+                if(instrs[x.hi].index != BOTSINK) s << " + " << arc(b, k, 1);
+            }
+            s << " - x_" << layer_var << " = 0\n";
+        }
+        s << "Bounds\nBinaries\n";
+        for(size_t b = 0; b < nr_bdds(); ++b)
+            for(size_t k = 0; k + 2 < delims[b + 1] - delims[b]; ++k)
+                for(int value = 0; value < 2; ++value)
+                    if(instrs[value ? instrs[delims[b] + k].hi : instrs[delims[b] + k].lo].index != BOTSINK) s << arc(b, k, value) << "\n";
+        s << "End\n";
     }
 
     static bddb200_instruction botsink() { return {BOTSINK, BOTSINK, BOTSINK}; }

@@ -66,8 +66,7 @@ public:
     void solve() { solve(config_); }
     void solve(const json& config)
     {
-        for(const char* key : {"export bdd lp", "export bdd graph"})
-            if(config.contains(key)) throw std::runtime_error(std::string("'") + key + "' is not provided by the C++ driver of this build");
+        if(config.contains("export bdd graph")) throw std::runtime_error("'export bdd graph' is not provided by the C++ driver of this build");
         if(solver_ == nullptr)
         {
             read_ILP(config);
@@ -97,6 +96,13 @@ public:
                     split_long_bdds(bdd_col_, length, ilp_.nr_variables(), implication, &n_split);      // in place; auxiliary variables carry no cost
                     log("[bdd preprocessor] split " + std::to_string(n_split) + " BDDs longer than " + std::to_string(length) + ": " + std::to_string(before) + " -> " + std::to_string(bdd_col_.nr_bdds()) + " BDDs");
                 }
+            }
+            if(config.contains("export bdd lp"))
+            {   // bdd_solver::export_bdd_lp, bdd_solver.cpp:400-410
+                const std::string file = config["export bdd lp"].get<std::string>();
+                std::ofstream f(file);
+                if(!f.good()) throw std::runtime_error("cannot write " + file);
+                bdd_col_.write_bdd_lp(f, ilp_.objective);
             }
             if(config.contains("print statistics"))
                 log("[print_statistics] #variables = " + std::to_string(ilp_.nr_variables()) + ", #constraints = " + std::to_string(ilp_.constraints.size()) + ", #BDDs = " + std::to_string(bdd_col_.nr_bdds()));

@@ -2,6 +2,7 @@
 // Host code only (compiled by g++ and linked into libbdd_b200.so next to the CUDA translation unit); failures go to the same
 // per-thread string bddb200_last_error() returns.
 #include <algorithm>
+#include <fstream>
 #include <memory>
 #include <new>
 #include <string>
@@ -100,6 +101,17 @@ int bddb200_collection_bdd_and(bddb200_collection* c, const size_t* bdd_nrs, siz
 { REQUIRE_COLLECTION(c); REQUIRE_OUT(bdd_nrs); REQUIRE_OUT(bdd_nr_out); return guarded([&] { *bdd_nr_out = c->col.bdd_and(bdd_nrs, bdd_nrs + n); }); }
 int bddb200_collection_remove(bddb200_collection* c, const size_t* bdd_nrs, size_t n)
 { REQUIRE_COLLECTION(c); if(n == 0) return BDDB200_OK; REQUIRE_OUT(bdd_nrs); return guarded([&] { c->col.remove(bdd_nrs, bdd_nrs + n); }); }
+
+int bddb200_collection_write_bdd_lp(const bddb200_collection* c, const double* costs, size_t n_costs, const char* path)
+{
+    REQUIRE_COLLECTION(c); REQUIRE_OUT(path);
+    if(n_costs > 0 && costs == nullptr) return fail("null argument");
+    return guarded([&] {
+        std::ofstream f(path);
+        if(!f.good()) throw std::runtime_error(std::string("cannot write ") + path);
+        c->col.write_bdd_lp(f, std::vector<double>(costs, costs + n_costs));
+    });
+}
 
 int bddb200_collection_split_qbdd(bddb200_collection* c, size_t bdd_nr, size_t chunk_size, size_t aux_var_start, int with_implication_bdd,
                                   size_t* nr_new_out, size_t* next_aux_out)

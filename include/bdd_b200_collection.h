@@ -54,6 +54,10 @@ int bddb200_collection_make_qbdd(bddb200_collection* c, size_t bdd_nr, size_t* b
 int bddb200_collection_bdd_and(bddb200_collection* c, const size_t* bdd_nrs, size_t n, size_t* bdd_nr_out);  /* :31-315, header :494; appended */
 int bddb200_collection_remove(bddb200_collection* c, const size_t* bdd_nrs, size_t n);                       /* ascending numbers, header :371 */
 
+/* bdd_collection::write_bdd_lp (header :731-830; "export bdd lp" of the driver, bdd_solver.cpp:400-410): the linear programme of the
+ * relaxation the dual solvers work on -- arc-flow variables per BDD, linked through the shared variables x_<var> -- as an .lp file */
+int bddb200_collection_write_bdd_lp(const bddb200_collection* c, const double* costs, size_t n_costs, const char* path);
+
 /* bdd_collection::split_qbdd (:507-949): chunks (and, with_implication_bdd != 0, the implication BDD when it is not trivial) are
  * appended; *nr_new_out is how many BDDs were appended (0: the BDD is short enough and stays), *next_aux_out the next free
  * auxiliary variable.  BDDB200_ERR_INVALID_ARGUMENT when a cut would land in front of a layer of width 1 (reference: assert, :598). */

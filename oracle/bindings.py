@@ -343,6 +343,16 @@ class RefCollection:
         f(self.h, bdd_nr, out.ctypes.data)
         return out
 
+    def write_bdd_lp(self, costs) -> str:
+        f = self.lib.refw_write_bdd_lp
+        f.restype = C.c_size_t
+        f.argtypes = [C.c_void_p, _f64p, C.c_size_t, C.c_char_p, C.c_size_t]
+        costs = np.ascontiguousarray(costs, dtype=np.float64)
+        n = f(self.h, costs, costs.shape[0], None, 0)
+        buf = C.create_string_buffer(n)
+        f(self.h, costs, costs.shape[0], buf, n)
+        return buf.raw[:n].decode()
+
     def split_qbdd_implication(self, bdd_nr: int, chunk_size: int, aux_var_start: int) -> Tuple[int, int]:
         """bdd_collection::split_qbdd WITH the implication BDD; returns (number of new BDDs, next aux variable)."""
         f = self.lib.refw_split_qbdd_implication

@@ -24,6 +24,7 @@
 #include <unordered_map>
 #include <unordered_set>
 #include <iostream>
+#include <sstream>
 #include <iterator>
 #include <ostream>
 #include <limits>
@@ -168,6 +169,16 @@ size_t refw_split_qbdd_implication(void* c, size_t bdd_nr, size_t chunk_size, si
         *nr_new = new_nrs.size();
         return next_aux;
     } catch(const std::exception& e) { rc->last_error = e.what(); return (size_t)-1; }
+}
+
+// bdd_collection::write_bdd_lp (include/bdd_collection/bdd_collection.h:731-830) into a caller buffer; returns the length of the text
+size_t refw_write_bdd_lp(void* c, const double* costs, size_t n_costs, char* out, size_t capacity)
+{
+    std::ostringstream s;
+    static_cast<ref_collection*>(c)->col.write_bdd_lp(s, costs, costs + n_costs);
+    const std::string text = s.str();
+    if(out != nullptr) std::memcpy(out, text.data(), std::min(capacity, text.size()));
+    return text.size();
 }
 
 size_t refw_nr_instructions(void* c)

@@ -72,7 +72,7 @@ def test_unsupported_keys_and_missing_gpu():
     with pytest.raises(RuntimeError, match="scope"):
         drv.bdd_solver({"input": os.path.join(GOLDEN, "matching_3x3.lp"), "variable order": "bfs"}, log=quiet)
     with pytest.raises(RuntimeError, match="scope"):
-        drv.bdd_solver({"input": os.path.join(GOLDEN, "matching_3x3.lp"), "export bdd lp": "x.lp"}, log=quiet)
+        drv.bdd_solver({"input": os.path.join(GOLDEN, "matching_3x3.lp"), "export bdd graph": "x.dot"}, log=quiet)
     with pytest.raises(RuntimeError, match="file extension"):
         drv.bdd_solver({"input": os.path.join(GOLDEN, "matching_3x3.lp"), "export lp": "x.mps"}, log=quiet)
     if not torch.cuda.is_available():
@@ -95,17 +95,21 @@ def test_export_lp_key_writes_the_problem_back(tmp_path, name):
         assert got.var_names == want.var_names and got.objective == want.objective and got.constant == want.constant
         assert [(k.variables, k.coefficients, k.ineq, k.rhs) for k in got.constraints] == [(k.variables, k.coefficients, k.ineq, k.rhs) for k in want.constraints]
 
-    out = tmp_path / "py.lp"
-    cfg = {"input": src, "relaxation solver": "cuda parallel mma", "export lp": str(out), "termination criteria": {"maximum iterations": 2}}
+    out, bdd_out = tmp_path / "py.lp", tmp_path / "py_bdd.lp"
+    cfg = {"input": src, "relaxation solver": "cuda parallel mma", "export lp": str(out), "export bdd lp": str(bdd_out),
+           "termination criteria": {"maximum iterations": 2}}
     try:
         drv.bdd_solver(cfg, log=quiet)
     except RuntimeError:
         assert not torch.cuda.is_available()
     same(out)
+    py_bdd_lp = bdd_out.read_text()
+    assert py_bdd_lp.startswith("Minimize\n") and "\nR_0: " in py_bdd_lp and py_bdd_lp.endswith("End\n")
     cli = os.path.join(os.path.dirname(GOLDEN), "..", "bdd_b200", "bdd_solver_cl")
     if os.path.exists(cli):
         out = tmp_path / "cpp.lp"
-        cfg["export lp"] = str(out)
+        cfg["export lp"], cfg["export bdd lp"] = str(out), str(tmp_path / "cpp_bdd.lp")
         r = subprocess.run([cli, json.dumps(cfg)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
         assert r.returncode == 0 or not torch.cuda.is_available()
         same(out)
+        assert (tmp_path / "cpp_bdd.lp").read_text() == py_bdd_lp          # both drivers export the same relaxation (tests/test_collection.py solves it)

@@ -607,3 +607,90 @@ def test_reference_bdd_and_protocol():
     flat = col.export()
     nodes = flat.instrs[int(flat.delims[both]):int(flat.delims[both + 1]) - 2]
     assert (nodes[:, 0] != nodes[:, 1]).all() and len({tuple(r) for r in nodes.tolist()}) == len(nodes)
+
+
+# ------------------------------------------------------------------------------------------------ write_bdd_lp
+def _relaxation_optimum(lp_text: str) -> float:
+    """the exported .lp read back with the package's own reader and solved as a linear programme over [0, 1] by HiGHS (scipy)"""
+    from scipy.optimize import linprog
+    from scipy.sparse import lil_matrix
+    from bdd_b200 import lp
+    ilp = lp.parse_lp(lp_text)
+    n = len(ilp.var_names)
+    A = lil_matrix((len(ilp.constraints), n))
+    b = np.zeros(len(ilp.constraints))
+    for r, k in enumerate(ilp.constraints):
+        assert k.ineq == lp.EQ
+        for v, a in zip(k.variables, k.coefficients):
+            A[r, v] = a
+        b[r] = k.rhs
+    res = linprog(np.asarray(ilp.objective), A_eq=A.tocsr(), b_eq=b, bounds=(0, 1), method="highs")
+    assert res.status == 0, res.message
+    return float(res.fun)
+
+
+@needs_ref
+def test_write_bdd_lp_matches_the_reference_byte_for_byte(tmp_path):
+    rng = np.random.default_rng(2)
+    cases = []
+    for name in golden_names():
+        g = np.load(os.path.join(GOLDEN, name + ".npz"))
+        cases.append((BddCollection(g["instrs"], g["delims"]), g["costs"]))
+    col, _ = instances.random_inequalities(15, 20, max_len=9, max_coeff=4, seed=8)
+    cases.append((col, np.concatenate([[1.5, -1.0 / 3.0, 1e-7, 12345678.9, -0.0, 0.0], rng.normal(size=14) * 100])))
+    n_equal = 0
+    for k, (col, costs) in enumerate(cases):
+        path = tmp_path / f"bdd_{k}.lp"
+        bdd_collection(col).write_bdd_lp(path, costs)
+        want = B.RefCollection.from_arrays(col.instrs, col.delims).write_bdd_lp(costs)
+        c = bdd_collection(col)
+        ascending = all(np.all(np.diff(c.variables(b).astype(np.int64)) > 0) for b in range(col.nr_bdds))
+        got = path.read_text()
+        if got == want:
+            n_equal += 1
+            continue
+        # the reference ties the first layer of a BDD to the BDD's smallest variable (header :800), which is wrong when the root branches
+        # on another one: only then may the texts differ, and only in the rows that link the layers to the shared variables
+        assert not ascending, k
+        first_diff = next(i for i, (x, y) in enumerate(zip(got, want)) if x != y)
+        last_flow_row = max(want.rindex("\nFC_"), want.rindex("\nR_"))
+        assert first_diff > want.index("\n", last_flow_row + 1), k
+    assert n_equal >= 5
+
+
+@pytest.mark.parametrize("name, known", [("matching_3x3", -6.0), ("short_chain_shuffled", 1.0), ("long_chain", -9.0), ("grid_graph_3x3", -8.0)])
+def test_exported_relaxation_has_the_published_optimum_and_bounds_the_dual_solver(tmp_path, name, known):
+    """the linear programme write_bdd_lp exports is the relaxation itself: solved by an LP solver that knows nothing of BDD sweeps it
+    gives the reference's published answers (test/test_bdd_cuda_parallel_mma.cu:197-247), and the MMA bound approaches it from below"""
+    if not os.path.exists(os.path.join(GOLDEN, name + ".npz")):
+        pytest.skip("fixture not present")
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    col = BddCollection(g["instrs"], g["delims"])
+    path = tmp_path / "relaxation.lp"
+    bdd_collection(col).write_bdd_lp(path, g["costs"])
+    optimum = _relaxation_optimum(path.read_text())
+    assert abs(optimum - known) <= 1e-7
+    B.oracle_set_num_threads(1)
+    o = B.Oracle(col.instrs, col.delims, g["costs"], "double")
+    for _ in range(300):
+        o.iteration()
+        assert o.lower_bound() <= optimum + 1e-9
+    assert o.lower_bound() >= optimum - 1e-6
+
+
+def test_split_relaxation_with_implication_bdds_is_as_tight_as_the_whole():
+    """cutting a BDD adds auxiliary variables; with the chunks (and the implication BDD) the LP bound of a single cardinality constraint
+    stays the sum of its k smallest costs"""
+    import tempfile
+    rng = np.random.default_rng(3)
+    for n, k, chunk in ((8, 3, 2), (9, 2, 3), (10, 5, 3)):
+        costs = np.round(rng.uniform(-10, 10, size=n), 2)          # the file carries six significant digits
+        for with_implication_bdd in (False, True):
+            c = bdd_collection()
+            card = c.cardinality_constraint(n, k)
+            _, n_all = c.split_qbdd(card, chunk, n, with_implication_bdd)
+            c.remove(card)
+            with tempfile.TemporaryDirectory() as d:
+                path = os.path.join(d, "split.lp")
+                c.write_bdd_lp(path, np.concatenate([costs, np.zeros(n_all - n)]))
+                assert abs(_relaxation_optimum(open(path).read()) - np.sort(costs)[:k].sum()) <= 1e-7
