@@ -694,3 +694,26 @@ def test_split_relaxation_with_implication_bdds_is_as_tight_as_the_whole():
                 path = os.path.join(d, "split.lp")
                 c.write_bdd_lp(path, np.concatenate([costs, np.zeros(n_all - n)]))
                 assert abs(_relaxation_optimum(open(path).read()) - np.sort(costs)[:k].sum()) <= 1e-7
+
+
+@pytest.mark.parametrize("make", [lambda: instances.set_cover(m=25, n=40, k=6, seed=3), lambda: instances.grid_mrf(4, 3, 3, seed=2), lambda: instances.qap(n=4, seed=5),
+                                  lambda: instances.assignment(6, seed=1)], ids=["set_cover", "grid_mrf", "qap", "assignment"])
+def test_dual_bounds_never_exceed_the_lp_optimum_of_the_relaxation(tmp_path, make):
+    """every iterate of the CPU oracle and of its L-BFGS wrapper is a feasible dual point: its bound stays below the optimum of the
+    exported linear programme (HiGHS), on the four benchmark shapes in small"""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(B.__file__))))
+    from lbfgs_oracle import LbfgsOracle
+    col, costs = make()
+    costs = np.round(costs, 3)                       # the exported file carries six significant digits
+    path = tmp_path / "relaxation.lp"
+    bdd_collection(col).write_bdd_lp(path, costs)
+    optimum = _relaxation_optimum(path.read_text())
+    B.oracle_set_num_threads(1)
+    plain = B.Oracle(col.instrs, col.delims, costs, "double")
+    wrapped = LbfgsOracle(B.Oracle(col.instrs, col.delims, costs, "double"), init_step_size=1e-3)
+    slack = 1e-7 * max(1.0, abs(optimum))
+    for _ in range(150):
+        plain.iteration(); wrapped.iteration()
+        assert plain.lower_bound() <= optimum + slack and wrapped.lower_bound() <= optimum + slack
+    assert plain.lower_bound() >= optimum - 0.1 * max(1.0, abs(optimum))          # MMA stops at a fixed point, which need not be the optimum
