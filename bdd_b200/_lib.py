@@ -40,7 +40,7 @@ COLLECTION_SYMBOLS = [
     "bddb200_collection_cardinality_constraint", "bddb200_collection_add_linear_constraint", "bddb200_collection_rebase", "bddb200_collection_negate", "bddb200_collection_invert",
     "bddb200_collection_variables", "bddb200_collection_is_qbdd", "bddb200_collection_is_reordered", "bddb200_collection_evaluate",
     "bddb200_collection_reorder", "bddb200_collection_make_qbdd", "bddb200_collection_bdd_and", "bddb200_collection_remove",
-    "bddb200_collection_write_bdd_lp", "bddb200_collection_split_qbdd", "bddb200_collection_split_long_bdds",
+    "bddb200_create_from_collection", "bddb200_collection_write_bdd_lp", "bddb200_collection_split_qbdd", "bddb200_collection_split_long_bdds",
     "bddb200_ilp_read", "bddb200_ilp_destroy", "bddb200_ilp_nr_variables", "bddb200_ilp_nr_constraints", "bddb200_ilp_objective",
     "bddb200_ilp_variable_name", "bddb200_ilp_constraint", "bddb200_ilp_to_bdds",
 ]
@@ -174,6 +174,7 @@ def load() -> C.CDLL:
         "bddb200_collection_make_qbdd": (i, [vp, sz, C.POINTER(sz)]),
         "bddb200_collection_bdd_and": (i, [vp, vp, sz, C.POINTER(sz)]),
         "bddb200_collection_remove": (i, [vp, vp, sz]),
+        "bddb200_create_from_collection": (i, [vp, vp, sz, i, C.POINTER(Options), C.POINTER(vp)]),
         "bddb200_collection_write_bdd_lp": (i, [vp, vp, sz, C.c_char_p]),
         "bddb200_collection_split_qbdd": (i, [vp, sz, sz, sz, i, C.POINTER(sz), C.POINTER(sz)]),
         "bddb200_collection_split_long_bdds": (i, [vp, sz, sz, i, C.POINTER(sz), C.POINTER(sz)]),

@@ -102,6 +102,14 @@ int bddb200_collection_bdd_and(bddb200_collection* c, const size_t* bdd_nrs, siz
 int bddb200_collection_remove(bddb200_collection* c, const size_t* bdd_nrs, size_t n)
 { REQUIRE_COLLECTION(c); if(n == 0) return BDDB200_OK; REQUIRE_OUT(bdd_nrs); return guarded([&] { c->col.remove(bdd_nrs, bdd_nrs + n); }); }
 
+int bddb200_create_from_collection(const bddb200_collection* c, const double* costs_hi, size_t n_costs, int precision,
+                                   const bddb200_options* opts, bddb200_solver** out)
+{
+    REQUIRE_COLLECTION(c); REQUIRE_OUT(out);
+    if(c->col.nr_bdds() == 0) { *out = nullptr; return fail("empty BDD collection"); }
+    return bddb200_create(c->col.instrs.data(), c->col.instrs.size(), c->col.delims.data(), c->col.nr_bdds(), costs_hi, n_costs, precision, opts, out);
+}
+
 int bddb200_collection_write_bdd_lp(const bddb200_collection* c, const double* costs, size_t n_costs, const char* path)
 {
     REQUIRE_COLLECTION(c); REQUIRE_OUT(path);

@@ -54,6 +54,11 @@ int bddb200_collection_make_qbdd(bddb200_collection* c, size_t bdd_nr, size_t* b
 int bddb200_collection_bdd_and(bddb200_collection* c, const size_t* bdd_nrs, size_t n, size_t* bdd_nr_out);  /* :31-315, header :494; appended */
 int bddb200_collection_remove(bddb200_collection* c, const size_t* bdd_nrs, size_t n);                       /* ascending numbers, header :371 */
 
+/* bddb200_create (bdd_b200.h) on the collection's own arrays: the constructor bdd_cuda_parallel_mma(bdd_col, costs)
+ * (src/bdd_solver/bdd_cuda_parallel_mma.cu:7-27) without an export in between; costs beyond n_costs are zero (auxiliary variables) */
+int bddb200_create_from_collection(const bddb200_collection* c, const double* costs_hi, size_t n_costs, int precision,
+                                   const bddb200_options* opts, bddb200_solver** out);
+
 /* bdd_collection::write_bdd_lp (header :731-830; "export bdd lp" of the driver, bdd_solver.cpp:400-410): the linear programme of the
  * relaxation the dual solvers work on -- arc-flow variables per BDD, linked through the shared variables x_<var> -- as an .lp file */
 int bddb200_collection_write_bdd_lp(const bddb200_collection* c, const double* costs, size_t n_costs, const char* path);

@@ -38,6 +38,13 @@ int main(void)
     if(bddb200_ilp_to_bdds(ilp, &col) || bddb200_ilp_nr_variables(ilp, &n_vars)) { puts(bddb200_last_error()); return 1; }
     if(bddb200_collection_split_long_bdds(col, 2, n_vars, 1, &n_split, &n_all) || bddb200_collection_nr_bdds(col, &n_bdds)) { puts(bddb200_last_error()); return 1; }
     printf("%zu %zu %zu %zu\\n", n_vars, n_split, n_bdds, n_all);
+    {   /* the solver straight from the collection: works on a GPU box, fails loudly without a device (no CPU fallback) */
+        double costs[5]; bddb200_solver* s = NULL; int rc;
+        bddb200_ilp_objective(ilp, costs, NULL);
+        rc = bddb200_create_from_collection(col, costs, 5, BDDB200_DOUBLE, NULL, &s);
+        if(rc == BDDB200_OK) { double lb; bddb200_iterations(s, 0.5, 50); bddb200_lower_bound(s, &lb); if(lb > 2.0 + 1e-9) return 2; bddb200_destroy(s); }
+        else if(rc != BDDB200_ERR_NO_DEVICE && rc != BDDB200_ERR_CUDA) { puts(bddb200_last_error()); return 3; }
+    }
     bddb200_collection_destroy(col); bddb200_ilp_destroy(ilp);
     return 0;
 }
