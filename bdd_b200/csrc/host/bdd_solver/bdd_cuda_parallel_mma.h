@@ -106,6 +106,15 @@ namespace LPMP {
                 bddb200_detail::check(bddb200_update_costs_dev(h_, thrust::raw_pointer_cast(cost_delta_0), delta_0_size, thrust::raw_pointer_cast(cost_delta_1), delta_1_size));
                 sync();
             }
+            // host ranges of any arithmetic type, e.g. update_costs(c.begin(), c.begin(), c.begin(), c.end()) to add c to the hi costs: what
+            // bdd_cuda<REAL> (src/bdd_cuda.cpp:63) and the reference's pybind constructor (bdd_cuda_parallel_mma_py.cu:42) call
+            // (bdd_cuda_base.cu:476-503).  Variables behind the end of a range keep their costs.
+            template<typename COST_ITERATOR>
+            void update_costs(COST_ITERATOR cost_lo_begin, COST_ITERATOR cost_lo_end, COST_ITERATOR cost_hi_begin, COST_ITERATOR cost_hi_end)
+            {
+                const std::vector<double> lo(cost_lo_begin, cost_lo_end), hi(cost_hi_begin, cost_hi_end);
+                bddb200_detail::check(bddb200_update_costs_host(h_, lo.data(), lo.size(), hi.data(), hi.size()));
+            }
             void set_cost(const double c, const size_t var) { bddb200_detail::check(bddb200_set_cost(h_, c, var)); }
 
             // two_dim_variable_array<array<double,2>>: per variable the (mm_lo, mm_hi) of each of its BDDs (bdd_cuda_base.cu:753-786)

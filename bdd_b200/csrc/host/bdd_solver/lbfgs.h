@@ -1,7 +1,7 @@
 // bdd_b200/csrc/host/bdd_solver/lbfgs.h -- drop-in for the reference's include/bdd_solver/lbfgs.h.
 //
-// With bdd_b200/csrc/host ahead of the reference's include/ on the include path, `#include "bdd_solver/lbfgs.h"` lands here.
-// The reference header is pulled in unchanged (#include_next), so lbfgs<SOLVER, ...> over the CPU solvers is the reference's own;
+// It takes the place of the reference's header (which moves to bdd_solver/lbfgs_generic.h) or sits ahead of it on the
+// include path.  The reference header is pulled in unchanged, so lbfgs<SOLVER, ...> over the CPU solvers is the reference's own;
 // for the GPU solver the partial specialisation below replaces it:
 //     lbfgs<bdd_cuda_parallel_mma<REAL>, VECTOR, REAL, INT_VECTOR, true>
 // (bdd_solver.h:60-61: cuda_lbfgs_parallel_mma_{float,double}_type) -> bddb200_lbfgs_* of libbdd_b200.so, where the history, the
@@ -10,7 +10,11 @@
 // Same constructors, iteration(), update_costs(); copyable / movable like the reference class (a copy starts with an empty history).
 #pragma once
 
-#include_next "bdd_solver/lbfgs.h"
+#if __has_include("bdd_solver/lbfgs_generic.h")
+#include "bdd_solver/lbfgs_generic.h"        // the reference's lbfgs.h under this name, when this file has taken its place in the tree
+#else
+#include_next "bdd_solver/lbfgs.h"           // this file merely sits ahead of the reference's include directory (tests/cpp/test_dropin.cu)
+#endif
 
 #include "bdd_solver/bdd_cuda_parallel_mma.h"
 
