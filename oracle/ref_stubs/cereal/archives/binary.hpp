@@ -8,9 +8,17 @@
 #include <istream>
 #include <ostream>
 #include <type_traits>
+#include <utility>
 #include <vector>
 
 namespace cereal {
+
+namespace stub_detail {
+template<typename T, typename A, typename = void> struct has_member_save : std::false_type {};
+template<typename T, typename A> struct has_member_save<T, A, decltype(std::declval<const T&>().save(std::declval<A&>()), void())> : std::true_type {};
+template<typename T, typename A, typename = void> struct has_member_load : std::false_type {};
+template<typename T, typename A> struct has_member_load<T, A, decltype(std::declval<T&>().load(std::declval<A&>()), void())> : std::true_type {};
+}
 
 class BinaryOutputArchive {
 public:
@@ -25,7 +33,9 @@ private:
         put(n);
         for(const T& x : v) put(x);
     }
-    template<typename T> typename std::enable_if<!std::is_arithmetic<T>::value>::type put(const T& v) { save(*this, v); }
+    // classes serialise through a member save(archive) when they have one (cereal's member form), else through a free save(archive, object)
+    template<typename T> typename std::enable_if<!std::is_arithmetic<T>::value && stub_detail::has_member_save<T, BinaryOutputArchive>::value>::type put(const T& v) { v.save(*this); }
+    template<typename T> typename std::enable_if<!std::is_arithmetic<T>::value && !stub_detail::has_member_save<T, BinaryOutputArchive>::value>::type put(const T& v) { save(*this, v); }
     std::ostream& s_;
 };
 
@@ -43,7 +53,8 @@ private:
         v.resize(n);
         for(T& x : v) get(x);
     }
-    template<typename T> typename std::enable_if<!std::is_arithmetic<T>::value>::type get(T& v) { load(*this, v); }
+    template<typename T> typename std::enable_if<!std::is_arithmetic<T>::value && stub_detail::has_member_load<T, BinaryInputArchive>::value>::type get(T& v) { v.load(*this); }
+    template<typename T> typename std::enable_if<!std::is_arithmetic<T>::value && !stub_detail::has_member_load<T, BinaryInputArchive>::value>::type get(T& v) { load(*this, v); }
     std::istream& s_;
 };
 
