@@ -717,3 +717,23 @@ def test_dual_bounds_never_exceed_the_lp_optimum_of_the_relaxation(tmp_path, mak
         plain.iteration(); wrapped.iteration()
         assert plain.lower_bound() <= optimum + slack and wrapped.lower_bound() <= optimum + slack
     assert plain.lower_bound() >= optimum - 0.1 * max(1.0, abs(optimum))          # MMA stops at a fixed point, which need not be the optimum
+
+
+def test_reference_loose_covering_problem(tmp_path):
+    """test/test_loose_covering_problem.cpp:8-59: three covering rows over six unit-cost variables have relaxation value 1.5 (the
+    reference reaches it with 200 iterations of its sequential solver, tolerance 1e-4); with the cut x1 + ... + x6 >= 2 it is 2.
+    Here: the LP optimum of the exported relaxation, and the bound the parallel-MMA oracle reaches."""
+    from bdd_b200 import lp
+    base = "Minimize\nx1 + x2 + x3 + x4 + x5 + x6\nSubject To\nx1 + x2 + x4 >= 1\nx1 + x3 + x5 >= 1\nx2 + x3 + x6 >= 1\n"
+    for extra, want in (("", 1.5), ("x1 + x2 + x3 + x4 + x5 + x6 >= 2\n", 2.0)):
+        col, costs = instances.from_ilp(lp.parse_lp(base + extra + "Bounds\nBinaries\nx1\nx2\nx3\nx4\nx5\nx6\nEnd"))
+        path = tmp_path / "cover.lp"
+        bdd_collection(col).write_bdd_lp(path, costs)
+        assert abs(_relaxation_optimum(path.read_text()) - want) <= 1e-9
+        B.oracle_set_num_threads(1)
+        o = B.Oracle(col.instrs, col.delims, costs, "double")
+        for _ in range(200):
+            o.iteration()
+        assert o.lower_bound() <= want + 1e-9
+        if not extra:
+            assert abs(o.lower_bound() - want) <= 1e-4           # with the cut, min-marginal averaging stops at a fixed point below the optimum (5/3)
