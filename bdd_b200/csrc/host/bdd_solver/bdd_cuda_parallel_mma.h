@@ -3,14 +3,14 @@
 //   include/bdd_solver/bdd_cuda_base.h          (class LPMP::bdd_cuda_base<REAL>, :57-226)
 // on top of the C ABI of libbdd_b200.so (include/bdd_b200.h).
 //
-// Put bdd_b200/csrc/host ahead of the reference's include/ on the include path (or copy the two
-// files over include/bdd_solver/) and link libbdd_b200.so instead of compiling
-// src/bdd_solver/bdd_cuda_base.cu and bdd_cuda_parallel_mma.cu: every caller of the class --
-// run_solver (include/run_solver_util.h:27-76), lbfgs<> (include/bdd_solver/lbfgs.h:22-27), the
-// GPU rounding (src/bdd_solver/incremental_mm_agreement_rounding_cuda.cu:264-372), the hybrid
-// solver (src/bdd_solver/bdd_multi_parallel_mma_base.cu:130-157) and the reference's own tests --
-// compiles unchanged: same class name, same method names, argument types (thrust::device_vector
-// like the reference) and error behaviour (std::runtime_error).  See INTEGRATION.md.
+// Put this file and bdd_cuda_base.h in the place of the reference's two headers (include/bdd_solver/bdd_solver.h includes them by
+// bare name, so being ahead on the include path is not enough for it) and link libbdd_b200.so instead of
+// compiling src/bdd_solver/bdd_cuda_base.cu and bdd_cuda_parallel_mma.cu: every caller of the class --
+// run_solver (include/run_solver_util.h:27-76), lbfgs<> (include/bdd_solver/lbfgs.h:22-27), the JSON driver
+// (src/bdd_solver/bdd_solver.cpp), the GPU rounding (src/bdd_solver/incremental_mm_agreement_rounding_cuda.cu:264-372), the pimpl
+// bdd_cuda<REAL> (src/bdd_cuda.cpp), the hybrid solver (src/bdd_solver/bdd_multi_parallel_mma_base.cu:130-157) and the reference's
+// own tests of the class -- compiles unchanged (`make -C oracle integration` does exactly that): same class name, same method
+// names, argument types (thrust::device_vector like the reference) and error behaviour (std::runtime_error).
 //
 // Host-side glue only: no kernel lives here.  Needs nvcc (thrust::device_vector) and the
 // reference's bdd_collection / two_dimensional_variable_array headers, like the file it replaces.
