@@ -537,7 +537,7 @@ public:
     {
         need(b);
         if(chunk_size == 0) throw std::invalid_argument("split_qbdd: chunk size must be positive");
-        if(!is_qbdd(b) || !is_reordered(b)) throw std::invalid_argument("split_qbdd: BDD " + std::to_string(b) + " is not a layered quasi-reduced BDD");
+        if(!is_layered_qbdd(b)) throw std::invalid_argument("split_qbdd: BDD " + std::to_string(b) + " is not a layered quasi-reduced BDD");
         // a private copy with indices relative to the BDD: the chunks are appended to the array the BDD lives in
         const size_t first = delims[b], n = delims[b + 1] - first;
         std::vector<bddb200_instruction> src(instrs.begin() + first, instrs.begin() + first + n);
@@ -627,6 +627,23 @@ private:
         r.reserve(vars.size());
         for(size_t i = 0; i < vars.size(); ++i) r.emplace(vars[i], i);
         return r;
+    }
+    // is_qbdd and is_reordered in one pass over the BDD (what split_qbdd needs of its input)
+    bool is_layered_qbdd(size_t b) const
+    {
+        const std::vector<size_t> vars = variables(b), r = node_ranks(b, vars);
+        const size_t first = delims[b], n = r.size();
+        for(size_t i = 0; i < n; ++i)
+        {
+            if(i + 1 < n && r[i + 1] != r[i] && r[i + 1] != r[i] + 1) return false;
+            for(const size_t child : {instrs[first + i].lo, instrs[first + i].hi})
+            {
+                if(child <= first + i || child >= delims[b + 1]) return false;
+                if(instrs[child].index == BOTSINK) continue;
+                if(r[i] + 1 == vars.size() ? instrs[child].index != TOPSINK : (child - first >= n || r[child - first] != r[i] + 1)) return false;
+            }
+        }
+        return true;
     }
     // per inner node the position of its variable in `vars`: when `vars` ascends (the usual case) the next layer's variable is tried
     // first and a binary search decides otherwise; a topological order goes through a hash map, one lookup per run of equal variables
