@@ -24,6 +24,38 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in lib.bddb200_version()
 
 
+def test_every_entry_point_refuses_a_null_handle():
+    """all 90-odd entry points that take a solver / L-BFGS / collection / ILP handle, called with NULL for every pointer and 0 for every
+    number (in a child process: a crash would take the test runner with it): an error status or a neutral value, never a fault"""
+    import subprocess
+    import sys
+    code = r'''
+import ctypes as C, sys
+sys.path.insert(0, %r)
+from bdd_b200 import _lib
+lib = _lib.load()
+skip = {"bddb200_default_options", "bddb200_last_error", "bddb200_version", "bddb200_create", "bddb200_plan_shard", "bddb200_create_shard", "bddb200_load",
+        "bddb200_layout_stats", "bddb200_delta_exchange", "bddb200_delta_exchange_two_shot", "bddb200_collection_create", "bddb200_ilp_read"}
+neutral = {"bddb200_precision_of", "bddb200_device_of", "bddb200_collection_destroy", "bddb200_ilp_destroy"}
+n = 0
+for name in _lib.SYMBOLS + _lib.COLLECTION_SYMBOLS:
+    if name in skip:
+        continue
+    f = getattr(lib, name)
+    args = [None if (t in (C.c_void_p, C.c_char_p) or (isinstance(t, type) and issubclass(t, C._Pointer))) else (0.5 if t is C.c_double else 0) for t in f.argtypes]
+    r = f(*args)
+    n += 1
+    if f.restype is C.c_int and name not in neutral and r == 0:
+        sys.exit("accepted a null handle: " + name)
+    if f.restype is C.c_size_t and r != 0:
+        sys.exit("non-zero size for a null handle: " + name)
+print("ok", n)
+''' % ROOT
+    r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.startswith("ok "), r.stdout
+    assert int(r.stdout.split()[1]) >= 90
+
+
 def test_public_headers_are_plain_c(tmp_path):
     """the drop-in boundary is a C ABI: both headers compile as C99 with nothing but the standard library, and a C program links every
     host-side entry point it needs to go from an .lp text to a split BDD collection (no GPU involved)"""
