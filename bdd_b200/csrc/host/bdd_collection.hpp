@@ -178,7 +178,7 @@ public:
         : instrs(ins, ins + n_instr), delims(d, d + n_bdds + 1)
     {
         if(delims.front() != 0 || delims.back() != n_instr || !std::is_sorted(delims.begin(), delims.end())) throw std::invalid_argument("bdd_collection: delimiters do not partition the instruction array");
-        for(size_t b = 0; b < n_bdds; ++b) check_sinks(b);
+        for(size_t b = 0; b < n_bdds; ++b) check_structure(b);
     }
 
     size_t nr_bdds() const { return delims.size() - 1; }
@@ -525,6 +525,11 @@ public:
         return nr_bdds() - 1;
     }
     size_t bdd_and(size_t i, size_t j) { const std::array<size_t, 2> two{i, j}; return bdd_and(two.begin(), two.end()); }
+    size_t bdd_and(int i, int j)                                               // integer literals, as in the reference (:73-82)
+    {
+        if(i < 0 || j < 0) throw std::invalid_argument("bdd_and: negative BDD number");
+        return bdd_and(size_t(i), size_t(j));
+    }
 
     // ---------------------------------------------------------------------------------------- splitting
     // Cuts the quasi-reduced BDD b into chunks of at most chunk_size variables linked by one-hot auxiliary variables (numbered from
@@ -607,11 +612,16 @@ public:
 
 private:
     void need(size_t b) const { if(b >= nr_bdds()) throw std::out_of_range("bdd_collection: no BDD " + std::to_string(b)); }
-    void check_sinks(size_t b) const
+    // what every method relies on (bdd_basic_check, :951-988): the two sinks close the BDD, every other instruction is an inner node
+    // whose children lie behind it inside the same BDD
+    void check_structure(size_t b) const
     {
-        const size_t e = delims[b + 1];
-        if(e - delims[b] < 3 || !((instrs[e - 1].index == TOPSINK && instrs[e - 2].index == BOTSINK) || (instrs[e - 1].index == BOTSINK && instrs[e - 2].index == TOPSINK)))
+        const size_t first = delims[b], e = delims[b + 1];
+        if(e - first < 3 || !((instrs[e - 1].index == TOPSINK && instrs[e - 2].index == BOTSINK) || (instrs[e - 1].index == BOTSINK && instrs[e - 2].index == TOPSINK)))
             throw std::invalid_argument("bdd_collection: BDD " + std::to_string(b) + " does not end in its two sinks");
+        for(size_t i = first; i + 2 < e; ++i)
+            if(instrs[i].index >= BOTSINK || instrs[i].lo <= i || instrs[i].lo >= e || instrs[i].hi <= i || instrs[i].hi >= e)
+                throw std::invalid_argument("bdd_collection: instruction " + std::to_string(i - first) + " of BDD " + std::to_string(b) + " is not an inner node with its children behind it");
     }
     size_t close(size_t bot, size_t top)
     {

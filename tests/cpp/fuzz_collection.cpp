@@ -43,6 +43,43 @@ int main()
             }
         }
     }
+    // malformed arrays: the constructor refuses them (children out of range or pointing backwards, sinks missing, delimiters off) or what
+    // it lets through is safe to work on
+    size_t refused = 0;
+    for(int rep = 0; rep < 2000; ++rep)
+    {
+        bdd_collection good;
+        const size_t a = good.cardinality_constraint(3 + rng() % 6, 1 + rng() % 3), b = good.simplex_constraint(2 + rng() % 7);
+        (void)a; (void)b;
+        std::vector<bddb200_instruction> ins = good.instrs;
+        std::vector<size_t> del = good.delims;
+        for(int e = 0, n_edits = 1 + (int)(rng() % 3); e < n_edits; ++e)
+        {
+            const size_t i = rng() % ins.size();
+            switch(rng() % 6)
+            {
+                case 0: ins[i].lo = rng() % (ins.size() + 4); break;
+                case 1: ins[i].hi = rng() % (ins.size() + 4); break;
+                case 2: ins[i].index = (size_t)-1 - rng() % 3; break;
+                case 3: ins[i].lo = ins[i].hi = i; break;
+                case 4: del[1 + rng() % (del.size() - 1)] += (size_t)(rng() % 5) - 2; break;
+                default: ins[i].hi = (size_t)-1 - rng() % 4; break;
+            }
+        }
+        try
+        {
+            bdd_collection c(ins.data(), ins.size(), del.data(), del.size() - 1);
+            for(size_t k = 0, n_given = c.nr_bdds(); k < n_given; ++k)
+            {
+                total += c.variables(k).size() + c.is_qbdd(k) + c.is_reordered(k);
+                try { c.evaluate(k, std::vector<char>(64, (char)(rep & 1))); } catch(const std::out_of_range&) {}
+                try { c.reorder(k); const size_t q = c.make_qbdd(k); total += c.nr_bdd_nodes(q); } catch(const std::exception&) {}
+            }
+            try { total += c.bdd_and(0, 1); } catch(const std::exception&) {}
+        }
+        catch(const std::invalid_argument&) { ++refused; }
+    }
+    if(refused < 500) { std::cerr << "only " << refused << " malformed collections refused\n"; return 1; }
     bdd_collection g;
     for(size_t n = 1; n < 30; ++n) { g.simplex_constraint(n); g.not_all_false_constraint(n); if(n > 1) { g.all_equal_constraint(n); for(size_t k = 0; k <= n; ++k) g.cardinality_constraint(n, k); } }
     std::cout << "ok " << total << " " << g.nr_bdds() << "\n";
