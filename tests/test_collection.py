@@ -737,3 +737,37 @@ def test_reference_loose_covering_problem(tmp_path):
         assert o.lower_bound() <= want + 1e-9
         if not extra:
             assert abs(o.lower_bound() - want) <= 1e-4           # with the cut, min-marginal averaging stops at a fixed point below the optimum (5/3)
+
+
+@pytest.mark.parametrize("n", list(range(3, 14)))
+def test_reference_single_inequality_protocol(n):
+    """test/test_random_inequality_to_bdd.cpp:14-47: one random inequality as one BDD -- the bound of the solver is then the minimum
+    over the feasible assignments (enumeration), to 1e-8.  BDD from the direct builder, bound from the CPU oracle."""
+    rng = np.random.default_rng(100 + n)
+    tested = 0
+    for attempt in range(12):
+        coeffs = [int(c) if c != 0 else 1 for c in rng.integers(-5, 6, size=n)]
+        ineq = int(rng.integers(0, 3))
+        rhs = int(rng.integers(sum(c for c in coeffs if c < 0), sum(c for c in coeffs if c > 0) + 1))
+        costs = rng.normal(size=n)
+        best = min((float(np.dot(costs, x)) for x in itertools.product((0, 1), repeat=n)
+                    if (np.dot(coeffs, x) <= rhs if ineq == 0 else np.dot(coeffs, x) >= rhs if ineq == 1 else np.dot(coeffs, x) == rhs)), default=None)
+        c = bdd_collection()
+        try:
+            nr = c.add_linear_constraint(coeffs, list(range(n)), ineq, rhs)
+        except Exception:
+            assert best is None                      # infeasible
+            continue
+        if nr is None:                               # always satisfied: every variable is free
+            assert abs(best - np.minimum(costs, 0).sum()) <= 1e-8
+            continue
+        flat = c.export()
+        # variables the constraint does not depend on have no layer: they are free as well
+        used = set(flat.instrs[:-2, 2].astype(np.int64).tolist())
+        free = sum(min(costs[v], 0.0) for v in range(n) if v not in used)
+        o = B.Oracle(flat.instrs, flat.delims, None, "double")
+        for v in used:
+            o.set_cost(float(costs[v]), v)
+        assert abs(o.lower_bound() + free - best) <= 1e-8, (coeffs, ineq, rhs)
+        tested += 1
+    assert tested >= 4
