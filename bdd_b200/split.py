@@ -2,8 +2,9 @@
 thousands of variables, whose BDDs are long and thin and make every pass a chain of thousands of dependent hops
 (SURVEY 5 "long BDDs", 8f row 4).
 
-``split_qbdd`` follows ``bdd_collection::split_qbdd`` without the optional implication BDD
-(src/bdd_collection/bdd_collection.cpp:507-790); ``split_long_bdds`` follows the driver loop of
+``split_qbdd`` follows the chunk construction of ``bdd_collection::split_qbdd``
+(src/bdd_collection/bdd_collection.cpp:507-790; the optional implication BDD, :805-940, is built by the library's collection class,
+``bdd_b200.collection.bdd_collection.split_qbdd(..., with_implication_bdd=True)``); ``split_long_bdds`` follows the driver loop of
 ``bdd_preprocessor`` (src/bdd_conversion/bdd_preprocessor.cpp:372-415).  Cutting a quasi-reduced BDD in front of a layer
 of width w introduces w auxiliary 0/1 variables that one-hot encode which node of that layer the path goes through
 (aux variable w-1-k is 1 iff node k is used): the chunk before the cut ends in a *tail* gadget that accepts exactly the
