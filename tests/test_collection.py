@@ -771,3 +771,20 @@ def test_reference_single_inequality_protocol(n):
         assert abs(o.lower_bound() + free - best) <= 1e-8, (coeffs, ineq, rhs)
         tested += 1
     assert tested >= 4
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 8])
+def test_reference_utility_protocol(n):
+    """test/bdd/test_bdd_collection_utility.cpp: each generator encodes its function and negate turns it into the complement (the
+    reference compares with its BDD manager's simplex / all_false / all_equal / cardinality; here: all 2^n assignments)"""
+    col = bdd_collection()
+    made = [(col.simplex_constraint(n), lambda s: s == 1), (col.not_all_false_constraint(n), lambda s: s >= 1)]
+    if n >= 2:
+        made.append((col.all_equal_constraint(n), lambda s: s in (0, n)))
+        made += [(col.cardinality_constraint(n, k), lambda s, k=k: s == k) for k in range(1, n + 1)]
+    for x in itertools.product((0, 1), repeat=n):
+        assert all(col.evaluate(b, x) == want(sum(x)) for b, want in made), x
+    for b, _ in made:
+        col.negate(b)
+    for x in itertools.product((0, 1), repeat=n):
+        assert all(col.evaluate(b, x) == (not want(sum(x))) for b, want in made), x
