@@ -173,6 +173,13 @@ inline ILP parse_lp(const std::string& text)
         size_t e = p.size();
         while(e > 0 && (std::isdigit((unsigned char)p[e - 1]) || p[e - 1] == '.')) --e;
         if(e == p.size()) continue;                                   // no number at the end yet
+        {   // digits, optionally a point and more digits (the reference's grammar and bdd_b200/lp.py); anything else is not a right-hand side yet
+            size_t q = e;
+            while(q < p.size() && std::isdigit((unsigned char)p[q])) ++q;
+            const bool has_int = q > e;
+            if(q < p.size() && p[q] == '.') { ++q; while(q < p.size() && std::isdigit((unsigned char)p[q])) ++q; }
+            if(!has_int || q != p.size()) continue;
+        }
         size_t n0 = e;
         while(n0 > 0 && std::isspace((unsigned char)p[n0 - 1])) --n0;
         double sgn = 1.0;

@@ -153,6 +153,51 @@ def test_knapsack_rows_beyond_the_direct_builder_are_refused_not_attempted():
     assert bdd_collection().add_linear_constraint(coeffs[:12], variables[:12], 0, 2 ** 11) is not None
 
 
+@pytest.mark.parametrize("seed", [5, 11])
+def test_the_two_lp_readers_agree_on_mutated_files(seed):
+    """differential test: every fixture mutated a few characters at a time goes through the Python reader (bdd_b200/lp.py) and the C++
+    reader (bddb200_ilp_*); both reject it or both read the same ILP"""
+    import random
+    from bdd_b200 import lp
+    from bdd_b200.collection import ilp_input
+    rnd = random.Random(seed)
+    alphabet = " \n\t+-*<=>:0123456789.xyzXe_()[]\\/"
+    n_same = n_rejected = 0
+    for name in golden_names():
+        base = open(os.path.join(GOLDEN, name + ".lp")).read()
+        for _ in range(60):
+            t = base
+            for _ in range(rnd.randint(1, 4)):
+                pos, kind = rnd.randrange(len(t)), rnd.randrange(4)
+                if kind == 0:
+                    t = t[:pos] + t[pos + rnd.randint(1, 8):]
+                elif kind == 1:
+                    t = t[:pos] + rnd.choice(alphabet) + t[pos:]
+                elif kind == 2:
+                    t = t[:pos] + rnd.choice(alphabet) + t[pos + 1:]
+                else:
+                    q = rnd.randrange(len(t))
+                    t = t[:pos] + t[q:q + rnd.randint(0, 20)] + t[pos:]
+            try:
+                a = lp.parse_lp(t)
+                got_py = (a.var_names, a.objective, a.constant, [(c.variables, c.coefficients, c.ineq, c.rhs) for c in a.constraints])
+            except Exception:
+                got_py = None
+            try:
+                b = ilp_input(t)
+                obj, const = b.objective()
+                got_cpp = (b.variable_names(), obj.tolist(), const, [b.constraint(c) for c in range(b.nr_constraints())])
+            except Exception:
+                got_cpp = None
+            assert (got_py is None) == (got_cpp is None), t
+            if got_py is None:
+                n_rejected += 1
+            else:
+                assert got_py == got_cpp, t
+                n_same += 1
+    assert n_same >= 100 and n_rejected >= 100
+
+
 def test_library_lp_reader_rejects_what_it_cannot_read():
     from bdd_b200._lib import BddB200Error
     from bdd_b200.collection import ilp_input
