@@ -1,0 +1,62 @@
+"""The reference's OWN command-line driver -- src/bdd_solver/bdd_solver_cl.cpp + bdd_solver.cpp with every solver, converter and input
+source they pull in, unmodified -- linked against the drop-in GPU class and libbdd_b200.so (oracle/Makefile: ref_driver; the .lp reader
+and Eigen / tsl are stood in for by test infrastructure, see there).  Here `"relaxation solver": "cuda parallel mma"` is the reference's
+construct_solver building LPMP::bdd_cuda_parallel_mma<REAL> into its std::variant, its run_solver loop and its log lines -- with this
+repository's kernels underneath.
+
+CPU part: the executable runs the reference's CPU solvers to the published answers (so the shimmed input path is right) and, without a
+device, fails in the drop-in constructor with the library's message.  The GPU part could not be run on hardware in the round it was
+written (the GPU budget was spent): it is marked xfail(strict=False) so that it reports without gating the suite, and it is the last
+file pytest collects."""
+import json
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+BIN = os.path.join(ROOT, "oracle", "_ref", "ref_bdd_solver_cl")
+EXPECTED = {"matching_3x3": -6.0, "short_chain_shuffled": 1.0, "long_chain": -9.0, "grid_graph_3x3": -8.0}
+needs_bin = pytest.mark.skipif(not os.path.exists(BIN), reason="oracle/_ref/ref_bdd_solver_cl not built (needs /root/reference at build time)")
+
+
+def run(name, solver, precision="double", extra=None):
+    cfg = {"input": os.path.join(GOLDEN, name + ".lp"), "relaxation solver": solver, "precision": precision,
+           "termination criteria": {"maximum iterations": 300, "improvement slope": 0.0, "minimum improvement": 0.0, "time limit": 1e10}}
+    cfg.update(extra or {})
+    r = subprocess.run([BIN, json.dumps(cfg)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    m = re.findall(r"final lower bound = (\S+)", r.stdout)
+    return r, (float(m[-1]) if m else None)
+
+
+@needs_bin
+@pytest.mark.parametrize("name", sorted(EXPECTED))
+@pytest.mark.parametrize("solver", ["parallel mma", "sequential mma"])
+def test_reference_driver_with_its_cpu_solvers(name, solver):
+    r, lb = run(name, solver)
+    assert r.returncode == 0 and lb is not None, r.stdout[-2000:]
+    assert abs(lb - EXPECTED[name]) <= 1e-5 * max(1.0, abs(EXPECTED[name])), r.stdout[-500:]
+
+
+@needs_bin
+def test_reference_driver_reaches_the_dropin_constructor():
+    torch = pytest.importorskip("torch")
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    for solver in ("cuda parallel mma", "lbfgs cuda mma", "cuda lbfgs parallel mma"):
+        r, _ = run("matching_3x3", solver)
+        assert r.returncode != 0 and "no CUDA device available: libbdd_b200 has no CPU fallback" in r.stdout, r.stdout[-1000:]
+
+
+@needs_bin
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="not yet run on hardware (written after the round's GPU budget was spent); reports without gating")
+@pytest.mark.parametrize("precision", ["double", "float"])
+@pytest.mark.parametrize("solver", ["cuda parallel mma", "lbfgs cuda mma", "cuda lbfgs parallel mma"])
+def test_reference_driver_on_the_dropin_class(solver, precision):
+    for name, want in EXPECTED.items():
+        r, lb = run(name, solver, precision)
+        assert r.returncode == 0 and lb is not None, r.stdout[-2000:]
+        assert abs(lb - want) <= 1e-3 * max(1.0, abs(want)), (name, lb)       # the reference builds the float solver for "double" and vice versa (bdd_solver.cpp:167-174)
