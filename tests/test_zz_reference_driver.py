@@ -22,11 +22,11 @@ EXPECTED = {"matching_3x3": -6.0, "short_chain_shuffled": 1.0, "long_chain": -9.
 needs_bin = pytest.mark.skipif(not os.path.exists(BIN), reason="oracle/_ref/ref_bdd_solver_cl not built (needs /root/reference at build time)")
 
 
-def run(name, solver, precision="double", extra=None):
+def run(name, solver, precision="double", extra=None, timeout=120):
     cfg = {"input": os.path.join(GOLDEN, name + ".lp"), "relaxation solver": solver, "precision": precision,
            "termination criteria": {"maximum iterations": 300, "improvement slope": 0.0, "minimum improvement": 0.0, "time limit": 1e10}}
     cfg.update(extra or {})
-    r = subprocess.run([BIN, json.dumps(cfg)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    r = subprocess.run([BIN, json.dumps(cfg)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout)
     m = re.findall(r"final lower bound = (\S+)", r.stdout)
     return r, (float(m[-1]) if m else None)
 
@@ -57,6 +57,6 @@ def test_reference_driver_reaches_the_dropin_constructor():
 @pytest.mark.parametrize("solver", ["cuda parallel mma", "lbfgs cuda mma", "cuda lbfgs parallel mma"])
 def test_reference_driver_on_the_dropin_class(solver, precision):
     for name, want in EXPECTED.items():
-        r, lb = run(name, solver, precision)
+        r, lb = run(name, solver, precision, timeout=45)            # a run takes a second; the first failure ends the test
         assert r.returncode == 0 and lb is not None, r.stdout[-2000:]
         assert abs(lb - want) <= 1e-3 * max(1.0, abs(want)), (name, lb)       # the reference builds the float solver for "double" and vice versa (bdd_solver.cpp:167-174)
