@@ -41,6 +41,25 @@ def test_reference_driver_with_its_cpu_solvers(name, solver):
 
 
 @needs_bin
+@pytest.mark.parametrize("name", ["matching_3x3", "long_mrf_chain", "mrf_grid_graph_3x3"])
+def test_files_written_by_the_reference_are_read_by_both_readers(tmp_path, name):
+    """"export lp" of the reference's driver is its own ILP_input::write_lp (include/ILP/ILP_input.h:229-303): the file it writes reads
+    back, through the Python reader and through the C++ reader behind the C ABI, as the problem that went in"""
+    from bdd_b200 import lp
+    from bdd_b200.collection import ilp_input
+    out = tmp_path / "exported.lp"
+    r, lb = run(name, "parallel mma", extra={"export lp": str(out), "termination criteria": {"maximum iterations": 1}})
+    assert r.returncode == 0 and out.exists(), r.stdout[-1000:]
+    want = lp.parse_lp(open(os.path.join(GOLDEN, name + ".lp")).read())
+    got = lp.parse_lp(out.read_text())
+    assert got.var_names == want.var_names and got.objective == want.objective
+    assert [(k.variables, k.coefficients, k.ineq, k.rhs) for k in got.constraints] == [(k.variables, k.coefficients, k.ineq, k.rhs) for k in want.constraints]
+    native = ilp_input(str(out))
+    assert native.variable_names() == want.var_names and native.objective()[0].tolist() == want.objective
+    assert [native.constraint(c) for c in range(native.nr_constraints())] == [(k.variables, k.coefficients, k.ineq, k.rhs) for k in want.constraints]
+
+
+@needs_bin
 def test_reference_driver_reaches_the_dropin_constructor():
     torch = pytest.importorskip("torch")
     if torch.cuda.is_available():
