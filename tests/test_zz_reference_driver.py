@@ -84,6 +84,49 @@ def test_relaxation_exported_by_the_reference_equals_ours(tmp_path, name):
 
 
 @needs_bin
+def test_reference_cpu_lbfgs_equals_its_plain_mma(tmp_path):
+    """BASELINE config 5 compares with the reference's `lbfgs parallel mma`.  Run through the reference's own driver it never accepts a
+    step at this commit (the stored alpha is uninitialised): its bounds are those of plain `parallel mma`, iteration by
+    iteration, while the algorithm its comments describe (oracle/lbfgs_oracle.py, which the GPU implementation follows) does better on
+    the same instance.  profiles/r02_reference_cpu_lbfgs.md has the numbers."""
+    import sys
+    import numpy as np
+    import bindings as B
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from lbfgs_oracle import LbfgsOracle
+    from bdd_b200 import instances, lp
+    rng = np.random.default_rng(1)
+    m, n, k = 300, 500, 8
+    rows = []
+    for r in range(m):
+        cols = {r % n}
+        while len(cols) < k:
+            cols.add(int(rng.integers(0, n)))
+        rows.append(sorted(cols))
+    c = rng.integers(1, 101, size=n)
+    path = tmp_path / "cover.lp"
+    path.write_text("Minimize\n " + " + ".join(f"{int(c[j])} x{j}" for j in range(n)) + "\nSubject To\n" + "\n".join(" " + " + ".join(f"x{j}" for j in row) + " >= 1" for row in rows) + "\nEnd\n")
+    traces = {}
+    for solver in ("parallel mma", "lbfgs parallel mma"):
+        cfg = {"input": str(path), "relaxation solver": solver, "precision": "double", "lbfgs": {"history size": 5},
+               "termination criteria": {"maximum iterations": 120, "improvement slope": 0.0, "minimum improvement": 0.0, "time limit": 1e10}}
+        r = subprocess.run([BIN, json.dumps(cfg)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout[-1000:]
+        traces[solver] = [float(x) for x in re.findall(r"iteration \d+, lower bound = (\S+),", r.stdout)]
+        if solver.startswith("lbfgs"):
+            assert r.stdout.count("step size selection unsuccessful") >= 6
+    assert len(traces["parallel mma"]) == len(traces["lbfgs parallel mma"]) == 120
+    assert np.allclose(traces["parallel mma"], traces["lbfgs parallel mma"], rtol=2e-5, atol=0)      # rejected trial steps are undone: a last printed digit may differ
+    col, costs = instances.from_ilp(lp.parse_lp(path.read_text()))
+    B.oracle_set_num_threads(1)
+    plain, wrapped = B.Oracle(col.instrs, col.delims, costs, "double"), LbfgsOracle(B.Oracle(col.instrs, col.delims, costs, "double"))
+    for _ in range(120):
+        plain.iteration(); wrapped.iteration()
+    assert abs(plain.lower_bound() - traces["parallel mma"][-1]) <= 1e-3 * abs(plain.lower_bound())       # the driver prints six digits
+    assert wrapped.lbfgs_iterations > 0 and wrapped.lower_bound() > plain.lower_bound() + 1.0
+
+
+@needs_bin
 def test_reference_driver_reaches_the_dropin_constructor():
     torch = pytest.importorskip("torch")
     if torch.cuda.is_available():
